@@ -1,0 +1,198 @@
+/* tslam_b200.h — C-ABI of libtslam_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the numerical hot path of SJTU-ViSYS/TextSLAM. The reference has no FFI
+ * layer; its boundary is two C++ classes whose bodies call Ceres / OpenCV:
+ *     TextSLAM::optimizer      /root/reference/src/optimizer.h:52-135
+ *     TextSLAM::ORBextractor   /root/reference/src/ORBextractor.h:45-114
+ * A maintainer keeps those class surfaces and replaces the Ceres / OpenCV calls inside
+ * optimizer.cc / ORBextractor.cc with the entry points below (see INTEGRATION.md for the shim).
+ *
+ * Conventions: plain C, caller-owned HOST memory for every pointer in the public structs,
+ * SoA layouts, int return (0 = ok, <0 = error; text via tslam_last_error()), every call blocks
+ * until its outputs are in host memory. One context per host thread. No CPU fallback: if no
+ * CUDA device / kernel image is usable the call fails with TSLAM_ERR_CUDA.
+ */
+#ifndef TSLAM_B200_H_
+#define TSLAM_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSLAM_OK 0
+#define TSLAM_ERR_ARG (-1)
+#define TSLAM_ERR_CUDA (-2)
+#define TSLAM_ERR_NUMERIC (-3)
+#define TSLAM_ERR_NCCL (-4)
+
+/* ---- residual kinds ---------------------------------------------------------------------- */
+/* point functors: include/auto_BAScene.h:89-92, auto_BASceneNW.h, auto_PoseOptimScene.h:90-93,
+ * auto_RhoScene.h:66-69 */
+#define TSLAM_PT_BA 0      /* J 2x13: [d_c(3) t_c(3) d_h(3) t_h(3) rho], weighted   */
+#define TSLAM_PT_BA_NW 1   /* same, weights forced to 1                              */
+#define TSLAM_PT_POSE 2    /* J 2x6 : [d_c t_c]                                      */
+#define TSLAM_PT_RHO 3     /* J 2x1 : [rho], weights forced to 1                     */
+/* text functors: include/nume_BAText.h:97-100, nume_PoseOptimText.h:81-84, nume_thetaText.h:77-80 */
+#define TSLAM_TX_BA 0      /* J 8x15: [d_c t_c d_h t_h theta(3)]                     */
+#define TSLAM_TX_POSE 1    /* J 8x6                                                   */
+#define TSLAM_TX_THETA 2   /* J 8x3, weight forced to 1                               */
+/* text Jacobian mode */
+#define TSLAM_JAC_ANALYTIC 0      /* closed form                             */
+#define TSLAM_JAC_CENTRAL_DIFF 1  /* replica of ceres::NumericDiffCostFunction<CENTRAL> step rule */
+
+/* ---- problem description (shared by eval and solve) ---------------------------------------- */
+/* Replaces the ceres::Problem built in src/optimizer.cc:1106-1208 (pose), :1359-1588 (local BA),
+ * :1716-1830 (global BA), :1869-1972 (landmarks), :2175-2200 (theta).
+ * Keyframe poses that the reference passes as constant matrices (Trw / Twr / Tcr of
+ * auto_PoseOptimScene, auto_RhoScene, nume_PoseOptimText, nume_thetaText) are entries of `cams`
+ * with cam_fixed = 1; constant landmarks are entries with rho_fixed / theta_fixed = 1. */
+typedef struct tslam_ba_problem {
+  int32_t n_cams;
+  double* cams;             /* n_cams x 7 : qw qx qy qz tx ty tz of T_cw (in/out for solve) */
+  const uint8_t* cam_fixed; /* n_cams, 1 = SetParameterBlockConstant                         */
+  int32_t n_points;
+  double* rho;              /* n_points inverse depths (in/out)                               */
+  const uint8_t* rho_fixed;
+  int32_t n_planes;
+  double* theta;            /* n_planes x 3 plane parameters (in/out)                         */
+  const uint8_t* theta_fixed;
+
+  /* point observations; order = AddResidualBlock order */
+  int32_t n_pobs;
+  const double* p_uv;       /* n_pobs x 2  level-0 observation (u,v)            */
+  const double* p_ray;      /* n_pobs x 2  host-frame ray (x,y), z == 1         */
+  const int32_t* p_cam;     /* observing keyframe                               */
+  const int32_t* p_host;    /* host keyframe of the landmark                    */
+  const int32_t* p_lm;      /* index into rho                                   */
+  double K_point[4];        /* fx fy cx cy (level 0, src/optimizer.cc:1403)     */
+  double w_point[2];        /* 1/1.2 (local/pose) or 1 (global)                 */
+  double huber_point;       /* delta; <= 0 disables the loss                    */
+
+  /* text feature blocks (8 pixel residuals each) */
+  int32_t n_tobs;
+  const double* t_rays;     /* n_tobs x 8 x 2 pattern rays (x,y), z == 1        */
+  const double* t_iref;     /* n_tobs x 8 normalised reference intensities      */
+  const double* t_musigma;  /* n_tobs x 2 (mu, sigma) of the current-image quad */
+  const int32_t* t_cam;
+  const int32_t* t_host;
+  const int32_t* t_plane;   /* index into theta                                 */
+  const int32_t* t_img;     /* index into imgs                                  */
+  int32_t n_imgs, img_w, img_h;
+  const uint8_t* imgs;      /* n_imgs x img_h x img_w, stride == img_w          */
+  double K_text[4];         /* intrinsics of the pyramid level of imgs          */
+  double w_text;            /* 1/0.2 or 1                                       */
+  double huber_text;        /* delta; <= 0 disables                             */
+} tslam_ba_problem;
+
+typedef struct tslam_solve_options {
+  int32_t max_iters;        /* ceres max_num_iterations (10 / 20 / 50)                     */
+  int32_t text_jac_mode;    /* TSLAM_JAC_*                                                 */
+  int32_t n_threads;        /* oracle only: host threads for the evaluation pass (>=1)     */
+  int32_t dense_full;       /* oracle only: 1 = solve the full (cams+landmarks) system     */
+  double function_tolerance;   /* <= 0 -> Ceres default 1e-6  */
+  double gradient_tolerance;   /* <= 0 -> 1e-10               */
+  double parameter_tolerance;  /* <= 0 -> 1e-8                */
+  double initial_radius;       /* <= 0 -> 1e4                 */
+} tslam_solve_options;
+
+#define TSLAM_TERM_NO_CONVERGENCE 0
+#define TSLAM_TERM_FUNCTION_TOL 1
+#define TSLAM_TERM_PARAMETER_TOL 2
+#define TSLAM_TERM_GRADIENT_TOL 3
+#define TSLAM_TERM_FAILURE (-1)
+
+typedef struct tslam_solve_summary {
+  int32_t iterations;        /* LM iterations performed (excluding iteration 0)             */
+  int32_t successful_steps;
+  int32_t unsuccessful_steps;
+  int32_t termination;       /* TSLAM_TERM_*                                                */
+  double initial_cost, final_cost, fixed_cost;
+  double total_ms;           /* wall time of the call                                       */
+  double solve_ms;           /* device/CPU time inside the LM loop (excl. problem upload)   */
+  double setup_ms;           /* structure analysis + upload                                 */
+  int32_t n_free_cams, n_free_points, n_free_planes, reduced_dim;
+} tslam_solve_summary;
+
+/* trace row (optional, per iteration incl. 0): cost, radius, relative_decrease, accepted(0/1/-1) */
+#define TSLAM_TRACE_COLS 4
+
+/* ---- context ------------------------------------------------------------------------------ */
+typedef struct tslam_ctx tslam_ctx;
+const char* tslam_last_error(void);
+int tslam_version(void);
+int tslam_ctx_create(int device_id, tslam_ctx** out);
+void tslam_ctx_destroy(tslam_ctx* ctx);
+/* Multi-GPU global BA: rank/world of a one-process-per-GPU job. `nccl_unique_id` is the 128-byte
+ * ncclUniqueId produced by tslam_nccl_unique_id() on rank 0 and broadcast by the host program
+ * (torch.distributed / MPI / sockets). */
+int tslam_nccl_unique_id(uint8_t id_out[128]);
+int tslam_ctx_init_comm(tslam_ctx* ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
+
+/* ---- residual + Jacobian evaluation (the metric kernel) --------------------------------------- */
+/* Replaces ceres::AutoDiffCostFunction<...>::Evaluate + QuaternionParameterization projection for
+ * every residual block of the given kind.  r: n_pobs x 2.  J: n_pobs x 2 x ncols (ncols 13/6/1),
+ * observation-major, row-major inside a block; may be NULL. */
+int tslam_eval_points(tslam_ctx* ctx, int kind, const tslam_ba_problem* p, double* r, double* J);
+/* Replaces ceres::NumericDiffCostFunction<..., CENTRAL, 8, ...>::Evaluate (+ projection).
+ * r: n_tobs x 8. J: n_tobs x 8 x ncols (15/6/3). */
+int tslam_eval_text(tslam_ctx* ctx, int kind, int jac_mode, const tslam_ba_problem* p, double* r, double* J);
+
+/* ---- Levenberg-Marquardt solve --------------------------------------------------------------- */
+/* Replaces ceres::Solve (src/optimizer.cc:1222,1602,1840,1982,2209) followed by
+ * Problem::Evaluate (:1228-1233,1609-1614): parameters are updated in place; final_residuals
+ * (2*n_pobs + 8*n_tobs, loss-corrected, insertion order; may be NULL) feed the caller's chi^2 gates.
+ * trace (may be NULL): (max_iters+1) x TSLAM_TRACE_COLS. */
+int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt,
+                tslam_solve_summary* summary, double* final_residuals, double* trace);
+
+/* ---- device-resident handles for benchmarking (inputs already in HBM) ------------------------- */
+typedef struct tslam_dev_problem tslam_dev_problem;
+int tslam_dev_upload(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem** out);
+void tslam_dev_free(tslam_ctx* ctx, tslam_dev_problem* d);
+/* Launch the point residual+Jacobian kernel `reps` times on the context stream into device-resident
+ * outputs; returns the mean kernel time in ms measured with CUDA events on that stream. If
+ * flush_l2 != 0 a >L2-sized buffer is rewritten between launches (outside the timed events). */
+int tslam_dev_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int reps, int flush_l2, float* ms_mean);
+int tslam_dev_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, int reps, int flush_l2, float* ms_mean);
+/* Run `iters` LM iterations on the device-resident problem (parameters reset to the uploaded
+ * values first); per-phase mean times in ms (CUDA events) are written to phase_ms[8]:
+ * 0 eval+J, 1 landmark/Schur prep, 2 reduced-system build, 3 all-reduce, 4 Cholesky, 5 back-subst,
+ * 6 candidate cost, 7 whole iteration. */
+int tslam_dev_lm_iterations(tslam_ctx* ctx, tslam_dev_problem* d, const tslam_solve_options* opt, int iters,
+                            float* phase_ms, tslam_solve_summary* summary);
+/* Copy back device outputs of the last tslam_dev_eval_* (for parity checks of the timed path). */
+int tslam_dev_download_eval(tslam_ctx* ctx, tslam_dev_problem* d, int which /*0 pts,1 text*/, double* r, double* J, int ncols);
+int tslam_dev_download_params(tslam_ctx* ctx, tslam_dev_problem* d, double* cams, double* rho, double* theta);
+
+/* ---- ORB extractor ------------------------------------------------------------------------ */
+/* Replaces ORBextractor::ORBextractor (src/ORBextractor.cc:410-471) and operator()
+ * (src/ORBextractor.cc:1054-1116). Keypoints use the 28-byte cv::KeyPoint layout
+ * (pt.x pt.y size angle response : f32, octave class_id : i32). */
+typedef struct tslam_orb tslam_orb;
+typedef struct tslam_keypoint {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} tslam_keypoint;
+int tslam_orb_create(tslam_ctx* ctx, int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+                     int blur_variant /*0: OpenCV>=3.4/4.x taps, 1: OpenCV 3.3.1 taps*/, tslam_orb** out);
+void tslam_orb_destroy(tslam_orb* h);
+/* imgs: n_imgs pointers to CV_8UC1 images of w x h, row stride `stride` bytes.
+ * kp_out: n_imgs x max_kp keypoints, desc_out: n_imgs x max_kp x 32 bytes, counts_out: n_imgs. */
+int tslam_orb_extract(tslam_orb* h, const uint8_t* const* imgs, int n_imgs, int w, int hgt, int stride,
+                      int max_kp, tslam_keypoint* kp_out, uint8_t* desc_out, int32_t* counts_out);
+/* Public pyramid (mvImagePyramid, src/ORBextractor.h:85): copy level `level` of image `img` of the
+ * last extract call (without border) into out (level_w x level_h, tight). */
+int tslam_orb_level_size(tslam_orb* h, int level, int* w, int* hgt);
+int tslam_orb_get_level(tslam_orb* h, int img, int level, uint8_t* out);
+/* Benchmark hook: images already resident in HBM; runs the full extractor `reps` times and returns
+ * the mean ms per batch (CUDA events) and the total keypoints of the last batch. */
+int tslam_orb_dev_bench(tslam_orb* h, const uint8_t* const* imgs, int n_imgs, int w, int hgt, int stride,
+                        int reps, float* ms_mean, int64_t* n_kp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSLAM_B200_H_ */
