@@ -1,0 +1,45 @@
+"""Loader of the in-tree CUDA library (textslam_b200/libtslam_b200.so).
+
+There is NO CPU fallback: if the library is missing it must be built (`python __graft_entry__.py`
+or `make -C textslam_b200/csrc`), and every compute call raises if no sm_100 device is usable.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtslam_b200.so")
+_LIB = None
+
+# every symbol include/tslam_b200.h declares
+EXPORTS = [
+    "tslam_last_error", "tslam_version", "tslam_ctx_create", "tslam_ctx_destroy", "tslam_nccl_unique_id",
+    "tslam_ctx_init_comm", "tslam_eval_points", "tslam_eval_text", "tslam_solve", "tslam_dev_upload", "tslam_dev_free",
+    "tslam_dev_eval_points", "tslam_dev_eval_text", "tslam_dev_lm_iterations", "tslam_dev_download_eval",
+    "tslam_dev_download_params", "tslam_orb_create", "tslam_orb_destroy", "tslam_orb_extract", "tslam_orb_level_size",
+    "tslam_orb_get_level", "tslam_orb_dev_bench",
+]
+
+
+class TslamError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise TslamError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                             "(nvcc, sm_100a). textslam_b200 has no CPU fallback.")
+        _LIB = C.CDLL(LIB_PATH)
+        _LIB.tslam_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            if name not in ("tslam_last_error", "tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy"):
+                getattr(_LIB, name).restype = C.c_int
+        for name in ("tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy"):
+            getattr(_LIB, name).restype = None
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise TslamError(f"libtslam_b200 error {rc}: {lib().tslam_last_error().decode(errors='replace')}")

@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference interface for the hot path, on top of the C-ABI.
+
+Names follow the reference: `Optimizer.PoseOptim / LocalBundleAdjustment / GlobalBA` correspond to
+src/optimizer.h:57-70 (here they take the flattened SoA problem that optimizer.cc:213-279 builds out
+of the map instead of the pointer graph), `ORBextractor.__call__` to src/ORBextractor.h:51-61.
+"""
+import ctypes as C
+import numpy as np
+from ._lib import lib, check, TslamError  # noqa: F401
+from ._abi import (BAProblem, SolveSummaryC, KeyPointC, KP_DTYPE, PT_NCOLS, TX_NCOLS, TRACE_COLS, solve_options,
+                   c_dp, c_bp, PT_BA, PT_BA_NW, PT_POSE, PT_RHO, TX_BA, TX_POSE, TX_THETA, JAC_ANALYTIC,
+                   JAC_CENTRAL_DIFF)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+class Context:
+    """One per host thread / GPU (tslam_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().tslam_ctx_create(C.c_int(device), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().tslam_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU -------------------------------------------------------------------------
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(lib().tslam_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def init_comm(self, rank, world, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib().tslam_ctx_init_comm(self._h, C.c_int(rank), C.c_int(world), buf))
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def eval_points(self, prob, kind, want_J=True):
+        n, nc = prob.n_pobs, PT_NCOLS[kind]
+        r = np.zeros((n, 2))
+        J = np.zeros((n, 2, nc)) if want_J else None
+        pc = prob.as_c()
+        check(lib().tslam_eval_points(self._h, C.c_int(kind), C.byref(pc), _dp(r), _dp(J)))
+        return r, J
+
+    def eval_text(self, prob, kind, jac_mode=JAC_ANALYTIC, want_J=True):
+        n, nc = prob.n_tobs, TX_NCOLS[kind]
+        r = np.zeros((n, 8))
+        J = np.zeros((n, 8, nc)) if want_J else None
+        pc = prob.as_c()
+        check(lib().tslam_eval_text(self._h, C.c_int(kind), C.c_int(jac_mode), C.byref(pc), _dp(r), _dp(J)))
+        return r, J
+
+    # ---- solve ---------------------------------------------------------------------------------
+    def solve(self, prob, max_iters=10, text_jac_mode=JAC_ANALYTIC, want_trace=True, **kw):
+        """ceres::Solve + Problem::Evaluate replacement; updates `prob` parameters in place."""
+        opt = solve_options(max_iters, text_jac_mode, **kw)
+        summ = SolveSummaryC()
+        fr = np.zeros(2 * prob.n_pobs + 8 * prob.n_tobs)
+        tr = np.full((max_iters + 1, TRACE_COLS), np.nan)
+        pc = prob.as_c()
+        check(lib().tslam_solve(self._h, C.byref(pc), C.byref(opt), C.byref(summ), _dp(fr), _dp(tr) if want_trace else None))
+        return summ.as_dict(), fr, tr
+
+    # ---- device-resident handles (benchmarks) --------------------------------------------------
+    def upload(self, prob):
+        return DeviceProblem(self, prob)
+
+
+class DeviceProblem:
+    def __init__(self, ctx, prob):
+        self.ctx, self.prob = ctx, prob
+        self._h = C.c_void_p()
+        pc = prob.as_c()
+        check(lib().tslam_dev_upload(ctx._h, C.byref(pc), C.byref(self._h)))
+
+    def free(self):
+        if self._h:
+            lib().tslam_dev_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def eval_points(self, kind, reps=1, flush_l2=False):
+        ms = C.c_float()
+        check(lib().tslam_dev_eval_points(self.ctx._h, self._h, C.c_int(kind), C.c_int(reps), C.c_int(int(flush_l2)), C.byref(ms)))
+        return ms.value
+
+    def eval_text(self, kind, jac_mode=JAC_ANALYTIC, reps=1, flush_l2=False):
+        ms = C.c_float()
+        check(lib().tslam_dev_eval_text(self.ctx._h, self._h, C.c_int(kind), C.c_int(jac_mode), C.c_int(reps),
+                                        C.c_int(int(flush_l2)), C.byref(ms)))
+        return ms.value
+
+    def download_eval(self, which, ncols):
+        n = self.prob.n_pobs if which == 0 else self.prob.n_tobs
+        rows = 2 if which == 0 else 8
+        r = np.zeros((n, rows)); J = np.zeros((n, rows, ncols))
+        check(lib().tslam_dev_download_eval(self.ctx._h, self._h, C.c_int(which), _dp(r), _dp(J), C.c_int(ncols)))
+        return r, J
+
+    def lm_iterations(self, iters, max_iters=None, text_jac_mode=JAC_ANALYTIC):
+        opt = solve_options(max_iters if max_iters is not None else iters, text_jac_mode)
+        phase = (C.c_float * 8)()
+        summ = SolveSummaryC()
+        check(lib().tslam_dev_lm_iterations(self.ctx._h, self._h, C.byref(opt), C.c_int(iters), phase, C.byref(summ)))
+        return list(phase), summ.as_dict()
+
+    def download_params(self):
+        p = self.prob
+        cams = np.zeros_like(p.cams); rho = np.zeros_like(p.rho); theta = np.zeros_like(p.theta)
+        check(lib().tslam_dev_download_params(self.ctx._h, self._h, _dp(cams), _dp(rho), _dp(theta)))
+        return cams, rho, theta
+
+
+class Optimizer:
+    """Mirror of TextSLAM::optimizer's solve entry points (src/optimizer.h:57-70) on flattened problems.
+    Iteration counts are the reference's: 10 (pose, local BA; src/optimizer.cc:180,286), 20 (global BA, :413)."""
+
+    def __init__(self, ctx, text_jac_mode=JAC_ANALYTIC):
+        self.ctx, self.text_jac_mode = ctx, text_jac_mode
+
+    def PoseOptim(self, prob, its=10):
+        return self.ctx.solve(prob, its, self.text_jac_mode)
+
+    def LocalBundleAdjustment(self, prob, its=10):
+        return self.ctx.solve(prob, its, self.text_jac_mode)
+
+    def GlobalBA(self, prob, its=20):
+        return self.ctx.solve(prob, its, self.text_jac_mode)
+
+
+class ORBextractor:
+    """Mirror of TextSLAM::ORBextractor (src/ORBextractor.h:45-114): ctor args and operator()."""
+
+    def __init__(self, ctx, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, blur_variant=0):
+        self.ctx = ctx
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = C.c_void_p()
+        check(lib().tslam_orb_create(ctx._h, C.c_int(nfeatures), C.c_float(scaleFactor), C.c_int(nlevels),
+                                     C.c_int(iniThFAST), C.c_int(minThFAST), C.c_int(blur_variant), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().tslam_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ptrs(self, imgs):
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        n, h, w = imgs.shape
+        ptrs = (C.c_void_p * n)(*[imgs[i].ctypes.data for i in range(n)])
+        return imgs, ptrs, n, h, w
+
+    def extract_batch(self, imgs, max_kp=None):
+        """imgs: (n,h,w) u8. Returns list of (keypoints structured array, descriptors (k,32) u8)."""
+        imgs, ptrs, n, h, w = self._ptrs(imgs)
+        max_kp = max_kp or (self.nfeatures + 4 * self.nlevels + 64)
+        kp = np.zeros((n, max_kp), dtype=KP_DTYPE)
+        desc = np.zeros((n, max_kp, 32), dtype=np.uint8)
+        cnt = np.zeros(n, dtype=np.int32)
+        check(lib().tslam_orb_extract(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(max_kp),
+                                      kp.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(c_bp),
+                                      cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        return [(kp[i, :cnt[i]].copy(), desc[i, :cnt[i]].copy()) for i in range(n)]
+
+    def __call__(self, image, mask=None):
+        """operator()(image, mask, keypoints, descriptors) — mask ignored like the reference (src/ORBextractor.cc:1054)."""
+        return self.extract_batch(image)[0]
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        check(lib().tslam_orb_level_size(self._h, C.c_int(level), C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def get_level(self, img, level):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), dtype=np.uint8)
+        check(lib().tslam_orb_get_level(self._h, C.c_int(img), C.c_int(level), out.ctypes.data_as(c_bp)))
+        return out
+
+    def dev_bench(self, imgs, reps=5):
+        imgs, ptrs, n, h, w = self._ptrs(imgs)
+        ms = C.c_float(); nk = C.c_int64()
+        check(lib().tslam_orb_dev_bench(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(reps),
+                                        C.byref(ms), C.byref(nk)))
+        return ms.value, nk.value

@@ -1,0 +1,251 @@
+// C-ABI glue of libtslam_b200.so: context, problem upload, evaluation entry points, timing hooks.
+#include <cstdarg>
+#include <cstring>
+#include <chrono>
+#include "ctx.cuh"
+
+namespace tsl {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int flush_l2(tslam_ctx* ctx) {
+  // rewrite a buffer larger than L2 so that the next launch reads its inputs from HBM
+  const size_t n = ctx->l2_bytes * 2;
+  TSL_CUDA(ctx->flush.reserve(n));
+  TSL_CUDA(cudaMemsetAsync(ctx->flush.p, 0x5a, n, ctx->stream));
+  return TSLAM_OK;
+}
+
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d) {
+  if (!p) return set_error(TSLAM_ERR_ARG, "null problem");
+  if (p->n_cams <= 0 || !p->cams) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
+  for (int i = 0; i < p->n_pobs; ++i) {
+    if ((unsigned)p->p_cam[i] >= (unsigned)p->n_cams || (unsigned)p->p_host[i] >= (unsigned)p->n_cams || (unsigned)p->p_lm[i] >= (unsigned)p->n_points)
+      return set_error(TSLAM_ERR_ARG, "point observation %d has an index out of range", i);
+  }
+  for (int i = 0; i < p->n_tobs; ++i) {
+    if ((unsigned)p->t_cam[i] >= (unsigned)p->n_cams || (unsigned)p->t_host[i] >= (unsigned)p->n_cams || (unsigned)p->t_plane[i] >= (unsigned)p->n_planes ||
+        (unsigned)p->t_img[i] >= (unsigned)p->n_imgs)
+      return set_error(TSLAM_ERR_ARG, "text block %d has an index out of range", i);
+  }
+  cudaStream_t s = ctx->stream;
+  d->n_cams = p->n_cams; d->n_points = p->n_points; d->n_planes = p->n_planes;
+  d->n_pobs = p->n_pobs; d->n_tobs = p->n_tobs; d->n_imgs = p->n_imgs; d->img_w = p->img_w; d->img_h = p->img_h;
+  memcpy(d->K_point, p->K_point, sizeof(d->K_point)); memcpy(d->w_point, p->w_point, sizeof(d->w_point));
+  memcpy(d->K_text, p->K_text, sizeof(d->K_text));
+  d->huber_point = p->huber_point; d->w_text = p->w_text; d->huber_text = p->huber_text;
+  std::vector<uint8_t> zc(p->n_cams, 0), zr(p->n_points, 0), zt(p->n_planes, 0);
+  d->h_cam_fixed.assign(p->cam_fixed ? p->cam_fixed : zc.data(), (p->cam_fixed ? p->cam_fixed : zc.data()) + p->n_cams);
+  d->h_rho_fixed.assign(p->rho_fixed ? p->rho_fixed : zr.data(), (p->rho_fixed ? p->rho_fixed : zr.data()) + p->n_points);
+  d->h_theta_fixed.assign(p->theta_fixed ? p->theta_fixed : zt.data(), (p->theta_fixed ? p->theta_fixed : zt.data()) + p->n_planes);
+  TSL_CUDA(d->cams.upload(p->cams, 7 * (size_t)p->n_cams, s));
+  TSL_CUDA(d->cams0.upload(p->cams, 7 * (size_t)p->n_cams, s));
+  TSL_CUDA(d->rho.upload(p->rho, p->n_points, s));
+  TSL_CUDA(d->rho0.upload(p->rho, p->n_points, s));
+  TSL_CUDA(d->theta.upload(p->theta, 3 * (size_t)p->n_planes, s));
+  TSL_CUDA(d->theta0.upload(p->theta, 3 * (size_t)p->n_planes, s));
+  TSL_CUDA(d->cam_fixed.upload(d->h_cam_fixed.data(), p->n_cams, s));
+  TSL_CUDA(d->rho_fixed.upload(d->h_rho_fixed.data(), p->n_points, s));
+  TSL_CUDA(d->theta_fixed.upload(d->h_theta_fixed.data(), p->n_planes, s));
+  TSL_CUDA(d->p_uv.upload(p->p_uv, 2 * (size_t)p->n_pobs, s));
+  TSL_CUDA(d->p_ray.upload(p->p_ray, 2 * (size_t)p->n_pobs, s));
+  TSL_CUDA(d->p_cam.upload(p->p_cam, p->n_pobs, s));
+  TSL_CUDA(d->p_host.upload(p->p_host, p->n_pobs, s));
+  TSL_CUDA(d->p_lm.upload(p->p_lm, p->n_pobs, s));
+  TSL_CUDA(d->t_rays.upload(p->t_rays, 16 * (size_t)p->n_tobs, s));
+  TSL_CUDA(d->t_iref.upload(p->t_iref, 8 * (size_t)p->n_tobs, s));
+  TSL_CUDA(d->t_musigma.upload(p->t_musigma, 2 * (size_t)p->n_tobs, s));
+  TSL_CUDA(d->t_cam.upload(p->t_cam, p->n_tobs, s));
+  TSL_CUDA(d->t_host.upload(p->t_host, p->n_tobs, s));
+  TSL_CUDA(d->t_plane.upload(p->t_plane, p->n_tobs, s));
+  TSL_CUDA(d->t_img.upload(p->t_img, p->n_tobs, s));
+  TSL_CUDA(d->imgs.upload(p->imgs, (size_t)p->n_imgs * p->img_w * p->img_h, s));
+  d->h_p_cam.assign(p->p_cam, p->p_cam + p->n_pobs); d->h_p_host.assign(p->p_host, p->p_host + p->n_pobs);
+  d->h_p_lm.assign(p->p_lm, p->p_lm + p->n_pobs);
+  d->h_t_cam.assign(p->t_cam, p->t_cam + p->n_tobs); d->h_t_host.assign(p->t_host, p->t_host + p->n_tobs);
+  d->h_t_plane.assign(p->t_plane, p->t_plane + p->n_tobs);
+  TSL_CUDA(cudaStreamSynchronize(s));  // host arrays are caller-owned and may change after return
+  return TSLAM_OK;
+}
+
+}  // namespace tsl
+
+using namespace tsl;
+
+extern "C" {
+
+const char* tslam_last_error(void) { return g_last_error.c_str(); }
+int tslam_version(void) { return 100; }
+
+int tslam_ctx_create(int device_id, tslam_ctx** out) {
+  if (!out) return set_error(TSLAM_ERR_ARG, "out == NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(TSLAM_ERR_CUDA, "no CUDA device available (%s); libtslam_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device_id < 0 || device_id >= n) return set_error(TSLAM_ERR_ARG, "device %d out of range (%d devices)", device_id, n);
+  TSL_CUDA(cudaSetDevice(device_id));
+  tslam_ctx* c = new tslam_ctx();
+  c->device = device_id;
+  cudaDeviceProp prop;
+  TSL_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) {
+    delete c;
+    return set_error(TSLAM_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a kernels only", device_id, prop.major, prop.minor);
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->l2_bytes = (size_t)prop.l2CacheSize;
+  TSL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  TSL_CUDA(cudaEventCreate(&c->ev0));
+  TSL_CUDA(cudaEventCreate(&c->ev1));
+  TSL_CUDA(cudaHostAlloc(&c->h_scalars, 64 * sizeof(double), cudaHostAllocDefault));
+  *out = c;
+  return TSLAM_OK;
+}
+
+void tslam_comm_destroy(tslam_ctx* ctx);
+
+void tslam_ctx_destroy(tslam_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  tslam_comm_destroy(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  delete c;
+}
+
+int tslam_dev_upload(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem** out) {
+  if (!ctx || !out) return set_error(TSLAM_ERR_ARG, "null argument");
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  tslam_dev_problem* d = new tslam_dev_problem();
+  int rc = upload_problem(ctx, p, d);
+  if (rc != TSLAM_OK) { delete d; return rc; }
+  *out = d;
+  return TSLAM_OK;
+}
+
+void tslam_dev_free(tslam_ctx* ctx, tslam_dev_problem* d) {
+  if (!d) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  free_solver(d);
+  delete d;
+}
+
+static int download(tslam_ctx* ctx, const double* dev, double* host, size_t n) {
+  if (!host || n == 0) return TSLAM_OK;
+  TSL_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return TSLAM_OK;
+}
+
+int tslam_eval_points(tslam_ctx* ctx, int kind, const tslam_ba_problem* p, double* r, double* J) {
+  if (!ctx || !p || !r) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (kind < 0 || kind > 3) return set_error(TSLAM_ERR_ARG, "bad point kind %d", kind);
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  tslam_dev_problem d;
+  int rc = upload_problem(ctx, p, &d);
+  if (rc) return rc;
+  rc = launch_eval_points(ctx, &d, kind, J != nullptr);
+  if (rc) return rc;
+  if ((rc = download(ctx, d.pr.p, r, 2 * (size_t)d.n_pobs))) return rc;
+  if (J && (rc = download(ctx, d.pJ.p, J, (size_t)d.n_pobs * 2 * d.pJ_cols))) return rc;
+  TSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TSLAM_OK;
+}
+
+int tslam_eval_text(tslam_ctx* ctx, int kind, int jac_mode, const tslam_ba_problem* p, double* r, double* J) {
+  if (!ctx || !p || !r) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (kind < 0 || kind > 2) return set_error(TSLAM_ERR_ARG, "bad text kind %d", kind);
+  if (jac_mode != TSLAM_JAC_ANALYTIC && jac_mode != TSLAM_JAC_CENTRAL_DIFF) return set_error(TSLAM_ERR_ARG, "bad jac_mode %d", jac_mode);
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  tslam_dev_problem d;
+  int rc = upload_problem(ctx, p, &d);
+  if (rc) return rc;
+  rc = launch_eval_text(ctx, &d, kind, jac_mode, J != nullptr);
+  if (rc) return rc;
+  if ((rc = download(ctx, d.tr.p, r, 8 * (size_t)d.n_tobs))) return rc;
+  if (J && (rc = download(ctx, d.tJ.p, J, (size_t)d.n_tobs * 8 * d.tJ_cols))) return rc;
+  TSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TSLAM_OK;
+}
+
+// Timed launches on device-resident inputs. Events bracket each launch individually so that the
+// optional L2 flush (a memset of 2x L2 bytes) stays outside the measured interval.
+static int timed_loop(tslam_ctx* ctx, int reps, int flush, float* ms_mean, int (*fn)(tslam_ctx*, void*), void* arg) {
+  if (reps <= 0) return set_error(TSLAM_ERR_ARG, "reps must be > 0");
+  double total = 0;
+  for (int i = 0; i < reps; ++i) {
+    if (flush) { int rc = flush_l2(ctx); if (rc) return rc; }
+    TSL_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = fn(ctx, arg);
+    if (rc) return rc;
+    TSL_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    TSL_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    TSL_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    total += ms;
+  }
+  if (ms_mean) *ms_mean = (float)(total / reps);
+  return TSLAM_OK;
+}
+
+struct EvalCall { tslam_dev_problem* d; int kind, jac_mode; };
+static int call_points(tslam_ctx* ctx, void* a) { EvalCall* c = (EvalCall*)a; return launch_eval_points(ctx, c->d, c->kind, true); }
+static int call_text(tslam_ctx* ctx, void* a) { EvalCall* c = (EvalCall*)a; return launch_eval_text(ctx, c->d, c->kind, c->jac_mode, true); }
+
+int tslam_dev_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int reps, int flush, float* ms_mean) {
+  if (!ctx || !d) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (kind < 0 || kind > 3) return set_error(TSLAM_ERR_ARG, "bad point kind %d", kind);
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  EvalCall c{d, kind, 0};
+  return timed_loop(ctx, reps, flush, ms_mean, call_points, &c);
+}
+
+int tslam_dev_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, int reps, int flush, float* ms_mean) {
+  if (!ctx || !d) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (kind < 0 || kind > 2) return set_error(TSLAM_ERR_ARG, "bad text kind %d", kind);
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  EvalCall c{d, kind, jac_mode};
+  return timed_loop(ctx, reps, flush, ms_mean, call_text, &c);
+}
+
+int tslam_dev_download_eval(tslam_ctx* ctx, tslam_dev_problem* d, int which, double* r, double* J, int ncols) {
+  if (!ctx || !d) return set_error(TSLAM_ERR_ARG, "null argument");
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  int rc;
+  if (which == 0) {
+    if (J && ncols != d->pJ_cols) return set_error(TSLAM_ERR_ARG, "ncols %d != last eval's %d", ncols, d->pJ_cols);
+    if ((rc = download(ctx, d->pr.p, r, 2 * (size_t)d->n_pobs))) return rc;
+    if ((rc = download(ctx, d->pJ.p, J, (size_t)d->n_pobs * 2 * ncols))) return rc;
+  } else {
+    if (J && ncols != d->tJ_cols) return set_error(TSLAM_ERR_ARG, "ncols %d != last eval's %d", ncols, d->tJ_cols);
+    if ((rc = download(ctx, d->tr.p, r, 8 * (size_t)d->n_tobs))) return rc;
+    if ((rc = download(ctx, d->tJ.p, J, (size_t)d->n_tobs * 8 * ncols))) return rc;
+  }
+  TSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TSLAM_OK;
+}
+
+int tslam_dev_download_params(tslam_ctx* ctx, tslam_dev_problem* d, double* cams, double* rho, double* theta) {
+  if (!ctx || !d) return set_error(TSLAM_ERR_ARG, "null argument");
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = download(ctx, d->cams.p, cams, 7 * (size_t)d->n_cams))) return rc;
+  if ((rc = download(ctx, d->rho.p, rho, d->n_points))) return rc;
+  if ((rc = download(ctx, d->theta.p, theta, 3 * (size_t)d->n_planes))) return rc;
+  TSL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TSLAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Context, error handling and the device-resident problem (HBM layout) of libtslam_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/tslam_b200.h"
+
+namespace tsl {
+
+extern thread_local std::string g_last_error;
+int set_error(int code, const char* fmt, ...);
+
+#define TSL_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return tsl::set_error(TSLAM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define TSL_CHECK_LAUNCH() TSL_CUDA(cudaGetLastError())
+
+template <typename T>
+struct DevBuf {  // simple RAII device buffer (grow-only)
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  cudaError_t upload(const T* h, size_t n, cudaStream_t s) {
+    cudaError_t e = reserve(n);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+struct NcclApi;  // dlopen'ed NCCL entry points (comm.cu)
+
+}  // namespace tsl
+
+struct tslam_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // L2 flush buffer (> L2 size) used between timed launches
+  tsl::DevBuf<uint8_t> flush;
+  size_t l2_bytes = 0;
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  // pinned staging for scalars
+  double* h_scalars = nullptr;  // cudaHostAlloc, 64 doubles
+};
+
+// Device-resident problem: everything the kernels read, SoA, FP64 / int32 / u8.
+struct tslam_dev_problem {
+  int n_cams = 0, n_points = 0, n_planes = 0, n_pobs = 0, n_tobs = 0, n_imgs = 0, img_w = 0, img_h = 0;
+  double K_point[4], w_point[2], huber_point, K_text[4], w_text, huber_text;
+  tsl::DevBuf<double> cams, rho, theta;            // current parameters
+  tsl::DevBuf<double> cams0, rho0, theta0;         // uploaded values (reset point for benchmarks)
+  tsl::DevBuf<uint8_t> cam_fixed, rho_fixed, theta_fixed;
+  tsl::DevBuf<double> p_uv, p_ray;                 // n_pobs x 2 each (16 B / obs each)
+  tsl::DevBuf<int32_t> p_cam, p_host, p_lm;
+  tsl::DevBuf<double> t_rays, t_iref, t_musigma;
+  tsl::DevBuf<int32_t> t_cam, t_host, t_plane, t_img;
+  tsl::DevBuf<uint8_t> imgs;
+  // evaluation outputs (observation-major): r, J
+  tsl::DevBuf<double> pr, pJ, tr, tJ;
+  int pJ_cols = 0, tJ_cols = 0;
+  // host copy kept for structure analysis in the solver
+  std::vector<int32_t> h_p_cam, h_p_host, h_p_lm, h_t_cam, h_t_host, h_t_plane;
+  std::vector<uint8_t> h_cam_fixed, h_rho_fixed, h_theta_fixed;
+  void* solver = nullptr;  // tsl::Solver*, owned (ba_solve.cu)
+};
+
+namespace tsl {
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d);
+int flush_l2(tslam_ctx* ctx);
+void free_solver(tslam_dev_problem* d);
+// kernels (ba_eval.cu)
+int launch_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, bool want_J);
+int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, bool want_J);
+}  // namespace tsl
