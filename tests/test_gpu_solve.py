@@ -1,0 +1,101 @@
+"""GPU parity of the LM solver (tslam_solve through the C-ABI) against the Ceres-faithful CPU oracle:
+same iteration count, same accept/reject sequence, costs and parameters within 1e-5 relative
+(BASELINE.json north_star tolerance) after the same number of LM iterations."""
+import numpy as np
+import pytest
+from textslam_b200 import synth
+from textslam_b200._abi import JAC_ANALYTIC, JAC_CENTRAL_DIFF
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _compare(ctx, oracle, prob, iters, jac_mode=JAC_ANALYTIC, rtol=RTOL, n_threads=8):
+    a, b = prob.copy(), prob.copy()
+    so, fo, to = oracle.solve(a, iters, jac_mode, n_threads=n_threads)
+    sg, fg, tg = ctx.solve(b, iters, jac_mode)
+    assert sg["iterations"] == so["iterations"], (sg, so)
+    assert sg["successful_steps"] == so["successful_steps"] and sg["termination"] == so["termination"], (sg, so)
+    assert sg["n_free_cams"] == so["n_free_cams"] and sg["n_free_points"] == so["n_free_points"]
+    n = so["iterations"] + 1
+    assert np.allclose(tg[:n, 0], to[:n, 0], rtol=1e-7), (tg[:n], to[:n])          # cost per iteration
+    assert np.array_equal(tg[:n, 3], to[:n, 3])                                      # accept / reject sequence
+    assert np.allclose(tg[:n, 1], to[:n, 1], rtol=1e-5)                              # trust-region radius
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-8 * so["final_cost"] + 1e-12
+    assert np.isclose(sg["fixed_cost"], so["fixed_cost"], rtol=1e-10, atol=1e-12)
+
+    def rel(x, y):
+        return np.abs(x - y).max() / (np.abs(y).max() + 1e-300) if y.size else 0.0
+
+    assert rel(b.cams, a.cams) < rtol, rel(b.cams, a.cams)
+    assert rel(b.rho, a.rho) < rtol, rel(b.rho, a.rho)
+    assert rel(b.theta, a.theta) < rtol, rel(b.theta, a.theta)
+    assert np.allclose(fg, fo, rtol=1e-6, atol=1e-6 * (np.abs(fo).max() + 1))       # Problem::Evaluate residuals
+    return so, sg
+
+
+def test_pose_only_c3(ctx, oracle):
+    _compare(ctx, oracle, synth.c3_pose_only(seed=21), 10, JAC_ANALYTIC)
+
+
+def test_pose_only_c3_central_diff(ctx, oracle):
+    _compare(ctx, oracle, synth.c3_pose_only(seed=22), 10, JAC_CENTRAL_DIFF, rtol=1e-4)
+
+
+def test_local_ba_c4(ctx, oracle):
+    _compare(ctx, oracle, synth.c4_local_ba(seed=23), 10, JAC_ANALYTIC)
+
+
+def test_local_ba_points_only(ctx, oracle):
+    _compare(ctx, oracle, synth.c4_local_ba(seed=24, n_planes=0), 10)
+
+
+def test_local_ba_with_external_hosts(ctx, oracle):
+    prob = synth.make_ba_problem(seed=25, n_kf=8, n_lm=400, obs_per_lm=3, band=8, fixed_cams=(0, 1, 2), n_ext=4,
+                                 frac_ext_lm=0.3, n_planes=8)
+    so, sg = _compare(ctx, oracle, prob, 10)
+    assert so["fixed_cost"] > 0
+
+
+def test_rho_only_and_theta_only(ctx, oracle):
+    # PyrLandmarkers / PyrThetaOptim shape: every camera constant, only landmarks free (src/optimizer.cc:1853-2242)
+    prob = synth.make_ba_problem(seed=26, n_kf=6, n_lm=300, obs_per_lm=3, band=6, fixed_cams=(0, 1, 2, 3, 4, 5), n_planes=6,
+                                 w_point=1.0, w_text=1.0, huber_text=2.0)
+    so, sg = _compare(ctx, oracle, prob, 15)
+    assert so["n_free_cams"] == 0 and so["reduced_dim"] == 0
+
+
+def test_zero_noise_converges_to_ground_truth(ctx, oracle):
+    prob = synth.make_ba_problem(seed=27, n_kf=10, n_lm=600, obs_per_lm=3, band=10, fixed_cams=(0, 1, 2),
+                                 pix_noise=0.0, outlier_frac=0.0)
+    q = prob.copy()
+    s, fr, tr = ctx.solve(q, 30)
+    cg, rg, _ = prob.gt
+    assert s["final_cost"] < 1e-9 * s["initial_cost"]
+    assert np.abs(q.cams - cg).max() < 1e-6 and np.abs(q.rho - rg).max() < 1e-6
+    _compare(ctx, oracle, prob, 30, rtol=1e-5)
+
+
+def test_medium_global_ba(ctx, oracle):
+    # 60 keyframes: reduced system 348 -> several Cholesky panels + padding
+    prob = synth.c5_global_ba(seed=28, n_kf=60, n_lm=3000)
+    _compare(ctx, oracle, prob, 8)
+
+
+def test_global_ba_c5_full_size(ctx, oracle):
+    prob = synth.c5_global_ba(seed=0)
+    so, sg = _compare(ctx, oracle, prob, 5)
+    assert sg["reduced_dim"] == 2988
+
+
+def test_device_resident_lm_matches_solve(ctx, oracle):
+    prob = synth.c4_local_ba(seed=29)
+    d = ctx.upload(prob)
+    phases, summ = d.lm_iterations(6)
+    cams, rho, theta = d.download_params()
+    q = prob.copy()
+    s, _, _ = ctx.solve(q, 6)
+    assert summ["iterations"] == s["iterations"]
+    assert np.allclose(cams, q.cams, rtol=1e-12, atol=1e-14) and np.allclose(rho, q.rho, rtol=1e-12, atol=1e-14)
+    assert phases[7] > 0
+    d.free()

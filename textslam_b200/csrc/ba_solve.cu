@@ -1,0 +1,1314 @@
+// Levenberg-Marquardt solver with landmark marginalisation (Schur complement) on one or more B200s.
+//
+// Replaces `ceres::Solve` + `Problem::Evaluate` at src/optimizer.cc:1222-1233 (pose-only),
+// :1602-1614 (local BA), :1840 (global BA), :1982 (landmarks), :2209 (theta). The trust-region loop
+// follows Ceres' published TrustRegionMinimizer / LevenbergMarquardtStrategy behaviour
+// (Ceres is not under /root/reference) and is mirrored by oracle/ba_lm.cpp.
+//
+// Per LM iteration on the device:
+//   eval (ba_eval.cu)   r, J per observation, observation-major, Huber-corrected
+//   accum               per landmark  V = J_l'J_l, g_l ; per (landmark,camera) slot E = J_c'J_l
+//   vinv                (V + D^2)^-1 for the current radius
+//   block               one warp per non-zero 6x6 block of the reduced camera matrix: gathers the
+//                       J_a'J_b terms and the -E_a V^-1 E_b' terms from precomputed entry lists
+//                       (deterministic, no atomics), warp-shuffle reduction, plus b and the raw gradient
+//   [all-reduce]        one NCCL sum over [blocks | b | gradient | costs] (multi-GPU global BA)
+//   scatter + Cholesky  dense FP64 blocked Cholesky (chol.cu), forward solve folded in
+//   backsub             landmark steps, candidate parameters (Ceres Plus), step norms
+//   model / candidate   model cost change -(Jd)'(r + Jd/2) and the candidate cost
+// The host only reads back a handful of scalars per iteration to take the accept / reject decision.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include "ctx.cuh"
+#include "solver.cuh"
+#include "ba_device.cuh"
+
+namespace tsl {
+
+// ------------------------------------------------------------------------------------------------
+// scalar slots (device, doubles). [0..7] are summed across ranks, mx[] is max-reduced.
+// ------------------------------------------------------------------------------------------------
+enum { SC_COST = 0, SC_FIXED = 1, SC_CAND = 2, SC_CAND_FIXED = 3, SC_MCC = 4, SC_STEP2 = 5, SC_CNORM2 = 6, SC_XNORM2 = 7, SC_N = 8 };
+enum { MX_GMAX = 0, MX_FAIL = 1, MX_N = 2 };
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+
+// deterministic two-level sum: parts[0..n) (stride 1) -> *out (+= if accumulate)
+__global__ void __launch_bounds__(256) sum_parts_kernel(const double* __restrict__ parts, int n, int stride, int offset, double* out, int accumulate) {
+  __shared__ double s[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += parts[(size_t)i * stride + offset];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = accumulate ? *out + s[0] : s[0];
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* s) {
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  return s[0];
+}
+
+// ---- per-landmark accumulation: V (DxD), g (D), both in the Jacobi-scaled system ------------------
+template <int D, int ROWS, int JC>
+__global__ void lm_accum_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
+                                const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
+                                double* __restrict__ g) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  double Vv[D * D], gv[D];
+#pragma unroll
+  for (int k = 0; k < D * D; ++k) Vv[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) gv[k] = 0.0;
+  for (int e = obs_ptr[v]; e < obs_ptr[v + 1]; ++e) {
+    const int i = obs[e];
+    const double* Ji = J + (size_t)i * ROWS * JC;
+    const double* ri = r + (size_t)i * ROWS;
+#pragma unroll
+    for (int row = 0; row < ROWS; ++row) {
+      double jl[D];
+#pragma unroll
+      for (int a = 0; a < D; ++a) jl[a] = Ji[row * JC + 12 + a];
+      const double rr = ri[row];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        gv[a] += jl[a] * rr;
+#pragma unroll
+        for (int b = 0; b < D; ++b) Vv[a * D + b] += jl[a] * jl[b];
+      }
+    }
+  }
+  double s[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) s[a] = scale[v * D + a];
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    g[v * D + a] = gv[a] * s[a];
+#pragma unroll
+    for (int b = 0; b < D; ++b) V[(size_t)v * D * D + a * D + b] = Vv[a * D + b] * s[a] * s[b];
+  }
+}
+
+// ---- per (landmark, camera) slot: E = S_c J_c' J_l S_l  (6 x D) ----------------------------------------
+template <int D, int ROWS, int JC>
+__global__ void slot_accum_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
+                                  const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
+                                  const double* __restrict__ scale_l, double* __restrict__ E) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= ns) return;
+  double Ev[6 * D];
+#pragma unroll
+  for (int k = 0; k < 6 * D; ++k) Ev[k] = 0.0;
+  for (int e = ent_ptr[sidx]; e < ent_ptr[sidx + 1]; ++e) {
+    const int code = ent[e];
+    const int i = code >> 1, off = (code & 1) * 6;
+    const double* Ji = J + (size_t)i * ROWS * JC;
+#pragma unroll
+    for (int row = 0; row < ROWS; ++row) {
+      double jl[D];
+#pragma unroll
+      for (int a = 0; a < D; ++a) jl[a] = Ji[row * JC + 12 + a];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double jc = Ji[row * JC + off + c];
+#pragma unroll
+        for (int a = 0; a < D; ++a) Ev[c * D + a] += jc * jl[a];
+      }
+    }
+  }
+  const int cam = slot_cam[sidx], lm = slot_lm[sidx];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const double sc = scale_c[6 * cam + c];
+#pragma unroll
+    for (int a = 0; a < D; ++a) E[(size_t)sidx * 6 * D + c * D + a] = Ev[c * D + a] * sc * scale_l[lm * D + a];
+  }
+}
+
+__device__ __forceinline__ double lm_damp(double d, double inv_radius) { return fmin(fmax(d, 1e-6), 1e32) * inv_radius; }
+
+// ---- (V + D^2)^-1 for the current trust-region radius ----------------------------------------------
+template <int D>
+__global__ void lm_vinv_kernel(int nv, const double* __restrict__ V, double inv_radius, double* __restrict__ Vinv, double* __restrict__ mx) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  if (D == 1) {
+    const double d = V[v];
+    Vinv[v] = 1.0 / (d + lm_damp(d, inv_radius));
+  } else {
+    const double* A = V + (size_t)v * 9;
+    const double a = A[0] + lm_damp(A[0], inv_radius), b = A[1], c = A[2];
+    const double d = A[4] + lm_damp(A[4], inv_radius), e = A[5], f = A[8] + lm_damp(A[8], inv_radius);
+    const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+    const double det = a * c00 + b * c01 + c * c02;
+    if (!(det > 0.0) || !(a > 0.0)) atomicMax(reinterpret_cast<unsigned long long*>(mx + MX_FAIL), __double_as_longlong(1.0));
+    const double id = 1.0 / det;
+    double* o = Vinv + (size_t)v * 9;
+    o[0] = c00 * id; o[1] = c01 * id; o[2] = c02 * id;
+    o[3] = o[1]; o[4] = (a * f - c * c) * id; o[5] = (b * c - a * e) * id;
+    o[6] = o[2]; o[7] = o[5]; o[8] = (a * d - b * b) * id;
+  }
+}
+
+// ---- Jacobi scaling (iteration 0): unscaled squared column norms ------------------------------------
+// one warp per free camera: sum over the diagonal block's direct entries
+struct BlockLists {
+  const int* dp_ptr; const int* dp;   // direct point entries  (obs << 2 | code)
+  const int* dt_ptr; const int* dt;   // direct text entries
+  const int* sp_ptr; const int2* sp;  // schur point entries (slot_i, slot_j)
+  const int* st_ptr; const int2* st;  // schur text entries
+};
+
+__device__ __forceinline__ void code_offsets(int code, int& ox, int& oy) {
+  // 0: (c,c)  1: (h,h)  2: rows = cam cols = host  3: rows = host cols = cam
+  ox = (code == 1 || code == 3) ? 6 : 0;
+  oy = (code == 1 || code == 2) ? 6 : 0;
+}
+
+__global__ void cam_colnorm_kernel(int nc, const int* __restrict__ diag_blk, BlockLists L, const double* __restrict__ pJ,
+                                   const double* __restrict__ tJ, double* __restrict__ out /*6nc*/) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nc) return;
+  const int blk = diag_blk[warp];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = L.dp_ptr[blk] + lane; e < L.dp_ptr[blk + 1]; e += 32) {
+    const int code = L.dp[e]; int ox, oy; code_offsets(code & 3, ox, oy);
+    const double* Ji = pJ + (size_t)(code >> 2) * 26;
+#pragma unroll
+    for (int row = 0; row < 2; ++row)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double j = Ji[row * 13 + ox + c]; acc[c] += j * j; }
+  }
+  for (int e = L.dt_ptr[blk] + lane; e < L.dt_ptr[blk + 1]; e += 32) {
+    const int code = L.dt[e]; int ox, oy; code_offsets(code & 3, ox, oy);
+    const double* Ji = tJ + (size_t)(code >> 2) * 120;
+#pragma unroll
+    for (int row = 0; row < 8; ++row)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { const double j = Ji[row * 15 + ox + c]; acc[c] += j * j; }
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  if (lane < 6) out[6 * warp + lane] = acc[lane];
+}
+
+__global__ void scale_from_norm_kernel(int n, const double* __restrict__ d2, double* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale[i] = 1.0 / (1.0 + sqrt(d2[i]));
+}
+// landmark scales from the diagonal of the (unscaled, scale == 1) V
+template <int D>
+__global__ void lm_scale_kernel(int nv, const double* __restrict__ V, double* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv * D) return;
+  const int v = i / D, a = i - v * D;
+  scale[i] = 1.0 / (1.0 + sqrt(V[(size_t)v * D * D + a * D + a]));
+}
+__global__ void fill_kernel(double* p, int n, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- reduced camera system: one warp per non-zero upper block (a <= b) -------------------------------
+struct BlockArgs {
+  int nblk; const int* blk_a; const int* blk_b; BlockLists L;
+  const double* pJ; const double* pr; const double* tJ; const double* tr;
+  const double* scale_c;
+  const double* Ep; const double* Vinvp; const double* gp; const int* sp_lm;
+  const double* Et; const double* Vinvt; const double* gt; const int* st_lm;
+  double* Sblk;   // nblk x 36, block (a,b) row-major: rows = a's tangent, cols = b's tangent (UNDAMPED)
+  double* bvec;   // 6 nc : reduced right-hand side (scaled)
+  double* graw;   // 6 nc : unscaled gradient J'r of the camera blocks
+  double* udiag;  // 6 nc : diagonal of the scaled J_c'J_c (the LM damping term is built from it after the reduce)
+};
+
+__global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
+  const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blk >= A.nblk) return;
+  const int a = A.blk_a[blk], b = A.blk_b[blk];
+  const bool diag = a == b;
+  double sa[6], sb[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) { sa[c] = A.scale_c[6 * a + c]; sb[c] = A.scale_c[6 * b + c]; }
+  double acc[36], gr[6];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) gr[k] = 0.0;
+  // ---- direct J_a' J_b terms (scaled on load) ----
+  for (int e = A.L.dp_ptr[blk] + lane; e < A.L.dp_ptr[blk + 1]; e += 32) {
+    const int code = A.L.dp[e]; int ox, oy; code_offsets(code & 3, ox, oy);
+    const int i = code >> 2;
+    const double* Ji = A.pJ + (size_t)i * 26;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      double jx[6], jy[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { jx[c] = Ji[row * 13 + ox + c] * sa[c]; jy[c] = Ji[row * 13 + oy + c] * sb[c]; }
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[p * 6 + q] += jx[p] * jy[q];
+      if (diag) {
+        const double rr = A.pr[(size_t)i * 2 + row];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) gr[p] += jx[p] * rr;
+      }
+    }
+  }
+  for (int e = A.L.dt_ptr[blk] + lane; e < A.L.dt_ptr[blk + 1]; e += 32) {
+    const int code = A.L.dt[e]; int ox, oy; code_offsets(code & 3, ox, oy);
+    const int i = code >> 2;
+    const double* Ji = A.tJ + (size_t)i * 120;
+    for (int row = 0; row < 8; ++row) {
+      double jx[6], jy[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { jx[c] = Ji[row * 15 + ox + c] * sa[c]; jy[c] = Ji[row * 15 + oy + c] * sb[c]; }
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[p * 6 + q] += jx[p] * jy[q];
+      if (diag) {
+        const double rr = A.tr[(size_t)i * 8 + row];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) gr[p] += jx[p] * rr;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  double bred[6];
+  if (diag) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gr[k] += __shfl_xor_sync(0xffffffffu, gr[k], o);
+      bred[k] = 0.0;
+    }
+  }
+  // ---- Schur terms: - E_i V^-1 E_j' (and - E_i V^-1 g for the right-hand side) ----
+  double sch[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) sch[k] = 0.0;
+  for (int e = A.L.sp_ptr[blk] + lane; e < A.L.sp_ptr[blk + 1]; e += 32) {
+    const int2 sl = A.L.sp[e];
+    const double* Ei = A.Ep + (size_t)sl.x * 6;
+    const double* Ej = A.Ep + (size_t)sl.y * 6;
+    const int lm = A.sp_lm[sl.x];
+    const double vi = A.Vinvp[lm];
+    double ei[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) ei[p] = Ei[p] * vi;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sch[p * 6 + q] += ei[p] * Ej[q];
+    if (diag && sl.x == sl.y) {
+      const double gl = A.gp[lm];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) bred[p] += ei[p] * gl;
+    }
+  }
+  for (int e = A.L.st_ptr[blk] + lane; e < A.L.st_ptr[blk + 1]; e += 32) {
+    const int2 sl = A.L.st[e];
+    const double* Ei = A.Et + (size_t)sl.x * 18;
+    const double* Ej = A.Et + (size_t)sl.y * 18;
+    const int lm = A.st_lm[sl.x];
+    const double* Vi = A.Vinvt + (size_t)lm * 9;
+    double ev[18];  // E_i V^-1 (6x3)
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ev[p * 3 + c] = Ei[p * 3] * Vi[c] + Ei[p * 3 + 1] * Vi[3 + c] + Ei[p * 3 + 2] * Vi[6 + c];
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sch[p * 6 + q] += ev[p * 3] * Ej[q * 3] + ev[p * 3 + 1] * Ej[q * 3 + 1] + ev[p * 3 + 2] * Ej[q * 3 + 2];
+    if (diag && sl.x == sl.y) {
+      const double* gl = A.gt + (size_t)lm * 3;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) bred[p] += ev[p * 3] * gl[0] + ev[p * 3 + 1] * gl[1] + ev[p * 3 + 2] * gl[2];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sch[k] += __shfl_xor_sync(0xffffffffu, sch[k], o);
+  if (diag) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bred[k] += __shfl_xor_sync(0xffffffffu, bred[k], o);
+  }
+  if (diag) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (lane == k) A.udiag[6 * a + k] = acc[7 * k];
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] -= sch[k];
+  double* out = A.Sblk + (size_t)blk * 36;
+#pragma unroll
+  for (int k = 0; k < 36; ++k)
+    if ((k & 31) == lane) out[k] = acc[k];
+  if (diag) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (lane == k) { A.bvec[6 * a + k] = gr[k] - bred[k]; A.graw[6 * a + k] = gr[k] / sa[k]; }
+  }
+}
+
+// The LM damping term clamp(diag(J'J))/radius must see the GLOBAL diagonal: ranks exchange un-damped
+// blocks plus udiag, and the damping is added while scattering into the dense matrix.
+struct ScatterArgs {
+  int nblk; const int* blk_a; const int* blk_b; const double* Sblk; const double* bvec; const double* udiag; double inv_radius;
+  double* A; int ld; int n; int rows_total; int Rb;
+};
+__global__ void scatter_kernel(ScatterArgs S) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb36 = S.nblk * 36;
+  if (t < nb36) {
+    const int blk = t / 36, k = t - blk * 36, p = k / 6, q = k - p * 6;
+    const int a = S.blk_a[blk], b = S.blk_b[blk];
+    double v = S.Sblk[t];
+    if (a == b && p == q) v += lm_damp(S.udiag[6 * a + p], S.inv_radius);
+    // block (a,b), a <= b, holds rows a / cols b; the lower triangle wants rows b / cols a
+    const int R = 6 * b + q, Cc = 6 * a + p;
+    if (a != b || R >= Cc) S.A[(size_t)R * S.ld + Cc] = v;
+  } else {
+    const int u = t - nb36;
+    if (u < S.n) S.A[(size_t)S.Rb * S.ld + u] = S.bvec[u];                       // b row
+    else if (u < S.ld) S.A[(size_t)u * S.ld + u] = 1.0;                          // identity padding
+  }
+}
+
+// ---- landmark back-substitution, steps and candidate parameters ---------------------------------------
+template <int D>
+__global__ void backsub_kernel(int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
+                               const double* __restrict__ Vinv, const double* __restrict__ g, const double* __restrict__ yc,
+                               const double* __restrict__ scale_l, double* __restrict__ delta_l) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  double t[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) t[a] = g[v * D + a];
+  for (int s = slot_ptr[v]; s < slot_ptr[v + 1]; ++s) {
+    const double* y = yc + 6 * slot_cam[s];
+    const double* Es = E + (size_t)s * 6 * D;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+#pragma unroll
+      for (int a = 0; a < D; ++a) t[a] -= Es[c * D + a] * y[c];
+  }
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    double y = 0.0;
+#pragma unroll
+    for (int b = 0; b < D; ++b) y += Vinv[(size_t)v * D * D + a * D + b] * t[b];
+    delta_l[v * D + a] = -y * scale_l[v * D + a];
+  }
+}
+
+// cameras: delta_c = -y_c * scale ; x_c = Plus(x, delta); partial norms (one block, cams are few)
+__global__ void __launch_bounds__(256) candidate_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x,
+                                                             const double* __restrict__ yc, const double* __restrict__ scale_c,
+                                                             double* __restrict__ delta_c, double* __restrict__ xc,
+                                                             double* __restrict__ sc, double norm_weight) {
+  __shared__ double sred[256];
+  double step2 = 0.0, cn2 = 0.0;
+  for (int k = threadIdx.x; k < n_cams; k += 256) {
+    const int s = camslot[k];
+    const double* xk = x + 7 * (size_t)k;
+    double* ok = xc + 7 * (size_t)k;
+    if (s < 0) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) ok[c] = xk[c];
+      continue;
+    }
+    double d[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { d[c] = -yc[6 * s + c] * scale_c[6 * s + c]; delta_c[6 * s + c] = d[c]; }
+    // ceres::QuaternionParameterization::Plus
+    const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    double q[4];
+    if (nrm > 0.0) {
+      const double sn = sin(nrm) / nrm;
+      const double z0 = cos(nrm), z1 = sn * d[0], z2 = sn * d[1], z3 = sn * d[2];
+      q[0] = z0 * xk[0] - z1 * xk[1] - z2 * xk[2] - z3 * xk[3];
+      q[1] = z0 * xk[1] + z1 * xk[0] + z2 * xk[3] - z3 * xk[2];
+      q[2] = z0 * xk[2] - z1 * xk[3] + z2 * xk[0] + z3 * xk[1];
+      q[3] = z0 * xk[3] + z1 * xk[2] - z2 * xk[1] + z3 * xk[0];
+    } else {
+      q[0] = xk[0]; q[1] = xk[1]; q[2] = xk[2]; q[3] = xk[3];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { ok[c] = q[c]; const double df = xk[c] - q[c]; step2 += df * df; cn2 += q[c] * q[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const double v = xk[4 + c] + d[3 + c]; ok[4 + c] = v; step2 += d[3 + c] * d[3 + c]; cn2 += v * v; }
+  }
+  const double a = block_sum_256(step2, sred);
+  __syncthreads();
+  const double b = block_sum_256(cn2, sred);
+  if (threadIdx.x == 0) { sc[SC_STEP2] = a * norm_weight; sc[SC_CNORM2] = b * norm_weight; }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
+                                                           const double* __restrict__ delta_l, double* __restrict__ xc,
+                                                           double* __restrict__ parts /*2 per block*/) {
+  __shared__ double sred[256];
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  double step2 = 0.0, cn2 = 0.0;
+  if (v < nv) {
+    const int gidx = v_gl[v];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const double d = delta_l[v * D + a];
+      const double val = x[(size_t)gidx * D + a] + d;
+      xc[(size_t)gidx * D + a] = val;
+      step2 += d * d; cn2 += val * val;
+    }
+  }
+  const double a = block_sum_256(step2, sred);
+  __syncthreads();
+  const double b = block_sum_256(cn2, sred);
+  if (threadIdx.x == 0) { parts[2 * blockIdx.x] = a; parts[2 * blockIdx.x + 1] = b; }
+}
+
+// squared norm of the free ambient parameters (x_norm at start)
+__global__ void __launch_bounds__(256) xnorm_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, double* out, double w) {
+  __shared__ double sred[256];
+  double a = 0.0;
+  for (int k = threadIdx.x; k < n_cams; k += 256)
+    if (camslot[k] >= 0)
+      for (int c = 0; c < 7; ++c) a += x[7 * (size_t)k + c] * x[7 * (size_t)k + c];
+  const double t = block_sum_256(a, sred);
+  if (threadIdx.x == 0) *out = t * w;
+}
+template <int D>
+__global__ void __launch_bounds__(256) xnorm_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x, double* parts) {
+  __shared__ double sred[256];
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  double a = 0.0;
+  if (v < nv)
+    for (int k = 0; k < D; ++k) { const double t = x[(size_t)v_gl[v] * D + k]; a += t * t; }
+  const double t = block_sum_256(a, sred);
+  if (threadIdx.x == 0) parts[blockIdx.x] = t;
+}
+
+// ---- model cost change: -(J d)'(r + J d / 2) per observation ---------------------------------------------
+template <int D, int ROWS, int JC>
+__global__ void __launch_bounds__(256) model_cost_kernel(int n, const int* __restrict__ cs, const int* __restrict__ hs, const int* __restrict__ ls,
+                                                         const double* __restrict__ J, const double* __restrict__ r,
+                                                         const double* __restrict__ delta_c, const double* __restrict__ delta_l,
+                                                         double* __restrict__ parts) {
+  __shared__ double sred[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  double acc = 0.0;
+  if (i < n) {
+    const int c = cs[i], h = hs[i], l = ls[i];
+    double dc[6], dh[6], dl[D];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { dc[k] = c >= 0 ? delta_c[6 * c + k] : 0.0; dh[k] = h >= 0 ? delta_c[6 * h + k] : 0.0; }
+#pragma unroll
+    for (int k = 0; k < D; ++k) dl[k] = l >= 0 ? delta_l[l * D + k] : 0.0;
+    const double* Ji = J + (size_t)i * ROWS * JC;
+#pragma unroll
+    for (int row = 0; row < ROWS; ++row) {
+      double m = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) m += Ji[row * JC + k] * dc[k] + Ji[row * JC + 6 + k] * dh[k];
+#pragma unroll
+      for (int k = 0; k < D; ++k) m += Ji[row * JC + 12 + k] * dl[k];
+      acc -= m * (r[(size_t)i * ROWS + row] + m * 0.5);
+    }
+  }
+  const double t = block_sum_256(acc, sred);
+  if (threadIdx.x == 0) parts[blockIdx.x] = t;
+}
+
+// ---- gradient max norm ||x - Plus(x, -g)||_inf (Ceres) -------------------------------------------------------
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+__global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, const double* __restrict__ graw,
+                                 double* __restrict__ mx) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_cams) return;
+  const int s = camslot[k];
+  if (s < 0) return;
+  const double* xk = x + 7 * (size_t)k;
+  const double d[3] = {-graw[6 * s], -graw[6 * s + 1], -graw[6 * s + 2]};
+  const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  double m = 0.0;
+  if (nrm > 0.0) {
+    const double sn = sin(nrm) / nrm;
+    const double z0 = cos(nrm), z1 = sn * d[0], z2 = sn * d[1], z3 = sn * d[2];
+    const double q0 = z0 * xk[0] - z1 * xk[1] - z2 * xk[2] - z3 * xk[3];
+    const double q1 = z0 * xk[1] + z1 * xk[0] + z2 * xk[3] - z3 * xk[2];
+    const double q2 = z0 * xk[2] - z1 * xk[3] + z2 * xk[0] + z3 * xk[1];
+    const double q3 = z0 * xk[3] + z1 * xk[2] - z2 * xk[1] + z3 * xk[0];
+    m = fmax(fmax(fabs(xk[0] - q0), fabs(xk[1] - q1)), fmax(fabs(xk[2] - q2), fabs(xk[3] - q3)));
+  }
+#pragma unroll
+  for (int c = 3; c < 6; ++c) m = fmax(m, fabs(graw[6 * s + c]));
+  atomic_max_nonneg(mx + MX_GMAX, m);
+}
+__global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomic_max_nonneg(mx + MX_GMAX, fabs(g_scaled[i] / scale[i]));
+}
+
+__global__ void copy_fail_kernel(const int* fail, double* mx) {
+  if (*fail) atomic_max_nonneg(mx + MX_FAIL, 1.0);
+}
+// final residual scatter into the global residual vector (multi-GPU: other ranks' entries stay 0)
+__global__ void scatter_rows_kernel(int n, int width, const int* __restrict__ gsel, const double* __restrict__ src, double* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const int i = t / width, k = t - i * width;
+  dst[(size_t)(gsel ? gsel[i] : i) * width + k] = src[t];
+}
+template <int D>
+__global__ void export_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nv * D) return;
+  const int v = t / D, a = t - v * D;
+  out[(size_t)v_gl[v] * D + a] = x[(size_t)v_gl[v] * D + a];
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct Solver {
+  tslam_ctx* ctx = nullptr;
+  tslam_dev_problem* d = nullptr;
+  int K = 0, nc = 0, nl = 0, npl = 0;         // global free counts
+  int lp = 0, lt = 0;                         // local observations
+  int nvp = 0, nvt = 0, nsp = 0, nst = 0;     // owned landmarks / slots
+  int nblk = 0;
+  int n = 0, ld = 0, rows = 0, Tn = 0;        // reduced system dims
+  std::vector<int> camslot;
+  std::vector<int> vp_gl_h, vt_gl_h, lmfree_p_h, lmfree_t_h;
+  // device index structures
+  DevBuf<int> camslot_d, p_cs, p_hs, p_ls, t_cs, t_hs, t_ls;
+  DevBuf<uint8_t> p_active, t_active, t_fmask;
+  DevBuf<int> vp_gl, vt_gl, vp_obs_ptr, vp_obs, vt_obs_ptr, vt_obs;
+  DevBuf<int> sp_ptr, sp_cam, sp_lm, spe_ptr, spe, st_ptr, st_cam, st_lm, ste_ptr, ste;
+  DevBuf<int> blk_a, blk_b, diag_blk, bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr, gsel_p, gsel_t;
+  DevBuf<int2> bsp, bst;
+  // values
+  DevBuf<double> xc_cams, xc_rho, xc_theta;
+  DevBuf<double> pr, pJ, tr, tJ, cr_p, cr_t;   // cr_*: candidate residual scratch
+  DevBuf<double> scale_c, scale_vp, scale_vt, colnorm_c;
+  DevBuf<double> Vp, gp, Vinvp, Vt, gt, Vinvt, Ep, Et;
+  DevBuf<double> red;        // [Sblk | b | graw | udiag]  (one all-reduce)
+  DevBuf<double> scl, scr;   // local scalars / reduced copy
+  DevBuf<double> mx;         // max-reduced scalars
+  DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts;
+  DevBuf<int> fail;
+  size_t red_n = 0;
+  double *Sblk = nullptr, *bvec = nullptr, *graw = nullptr, *udiag = nullptr, *sc = nullptr;
+  double* x_cams = nullptr; double* x_rho = nullptr; double* x_theta = nullptr;   // current (alias d-> buffers or xc)
+  double* c_cams = nullptr; double* c_rho = nullptr; double* c_theta = nullptr;   // candidate
+  double setup_ms = 0;
+  // phase timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_kind;   // phase that STARTS at this mark (0..6), 7 = end marker
+  int ev_used = 0;
+  ~Solver() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+template <typename T>
+static cudaError_t up(DevBuf<T>& b, const std::vector<T>& h, cudaStream_t s) { return b.upload(h.data(), h.size(), s); }
+
+// counting-sort based CSR builder: keys in [0, nkeys)
+static void build_csr(int nkeys, const std::vector<int>& keys, std::vector<int>& ptr, std::vector<int>& order) {
+  ptr.assign(nkeys + 1, 0);
+  for (int k : keys) ptr[k + 1]++;
+  for (int i = 0; i < nkeys; ++i) ptr[i + 1] += ptr[i];
+  order.resize(keys.size());
+  std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+  for (size_t i = 0; i < keys.size(); ++i) order[cur[keys[i]]++] = (int)i;
+}
+
+struct LmStruct {  // landmark-side structure for one landmark type (points or planes)
+  std::vector<int> v_gl, obs_ptr, obs, slot_ptr, slot_cam, slot_lm, ent_ptr, ent;
+  std::vector<int> obs_ls;  // per local observation: owned landmark index or -1
+  // per landmark list of (global) camslots, for ALL free landmarks of this type (global block structure)
+};
+
+// Builds slot structure for the locally owned landmarks from local observations.
+//  free_gl[l] >= 0  iff landmark l is free & used (global); local obs arrays index global landmarks.
+static void build_landmark_side(int n_obs, const int* o_lm, const std::vector<int>& o_cs, const std::vector<int>& o_hs,
+                                const std::vector<uint8_t>& o_active, const std::vector<int>& lmslot_gl, int n_lm_total, LmStruct& S) {
+  // owned landmarks = free landmarks that appear in local active observations (ownership rule guarantees all their obs are local)
+  std::vector<int> local_of(n_lm_total, -1);
+  S.v_gl.clear();
+  S.obs_ls.assign(n_obs, -1);
+  for (int i = 0; i < n_obs; ++i) {
+    const int l = o_lm[i];
+    if (!o_active[i] || lmslot_gl[l] < 0) continue;
+    if (local_of[l] < 0) { local_of[l] = (int)S.v_gl.size(); S.v_gl.push_back(l); }
+  }
+  // keep owned landmarks in ascending global order (deterministic, independent of obs order)
+  std::sort(S.v_gl.begin(), S.v_gl.end());
+  for (size_t v = 0; v < S.v_gl.size(); ++v) local_of[S.v_gl[v]] = (int)v;
+  const int nv = (int)S.v_gl.size();
+  std::vector<int> keys; std::vector<int> idx;
+  for (int i = 0; i < n_obs; ++i) {
+    const int l = o_lm[i];
+    if (!o_active[i] || lmslot_gl[l] < 0) continue;
+    S.obs_ls[i] = local_of[l];
+    keys.push_back(local_of[l]); idx.push_back(i);
+  }
+  std::vector<int> order;
+  build_csr(nv, keys, S.obs_ptr, order);
+  S.obs.resize(order.size());
+  for (size_t k = 0; k < order.size(); ++k) S.obs[k] = idx[order[k]];
+  // slots: per landmark, distinct camslots (ascending) among cam / host of its observations
+  S.slot_ptr.assign(nv + 1, 0); S.slot_cam.clear(); S.slot_lm.clear(); S.ent_ptr.clear(); S.ent.clear();
+  S.ent_ptr.push_back(0);
+  std::vector<std::pair<int, int>> tmp;  // (camslot, obs<<1|role)
+  for (int v = 0; v < nv; ++v) {
+    tmp.clear();
+    for (int e = S.obs_ptr[v]; e < S.obs_ptr[v + 1]; ++e) {
+      const int i = S.obs[e];
+      if (o_cs[i] >= 0) tmp.emplace_back(o_cs[i], (i << 1) | 0);
+      if (o_hs[i] >= 0) tmp.emplace_back(o_hs[i], (i << 1) | 1);
+    }
+    std::sort(tmp.begin(), tmp.end());
+    for (size_t k = 0; k < tmp.size(); ++k) {
+      if (k == 0 || tmp[k].first != tmp[k - 1].first) {
+        if (k != 0) S.ent_ptr.push_back((int)S.ent.size());
+        S.slot_cam.push_back(tmp[k].first); S.slot_lm.push_back(v);
+      }
+      S.ent.push_back(tmp[k].second);
+    }
+    if (!tmp.empty()) S.ent_ptr.push_back((int)S.ent.size());
+    S.slot_ptr[v + 1] = (int)S.slot_cam.size();
+  }
+}
+
+static int analyze_and_upload(Solver& S) {
+  auto T0 = std::chrono::steady_clock::now();
+  tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
+  cudaStream_t st = ctx->stream;
+  const int K = d->n_cams; S.K = K;
+  const int GP = d->g_pobs, GT = d->g_tobs;
+  auto cf = [&](int k) { return d->h_cam_fixed[k] != 0; };
+  // ---- global layout (same on every rank) ----
+  std::vector<uint8_t> cu(K, 0), lu(d->n_points, 0), pu(d->n_planes, 0);
+  std::vector<uint8_t> gp_active(GP), gt_active(GT);
+  for (int i = 0; i < GP; ++i) {
+    const int c = d->h_p_cam[i], h = d->h_p_host[i], l = d->h_p_lm[i];
+    const bool act = !cf(c) || !cf(h) || !d->h_rho_fixed[l];
+    gp_active[i] = act;
+    if (act) { cu[c] = cu[h] = 1; lu[l] = 1; }
+  }
+  for (int i = 0; i < GT; ++i) {
+    const int c = d->h_t_cam[i], h = d->h_t_host[i], l = d->h_t_plane[i];
+    const bool act = !cf(c) || !cf(h) || !d->h_theta_fixed[l];
+    gt_active[i] = act;
+    if (act) { cu[c] = cu[h] = 1; pu[l] = 1; }
+  }
+  S.camslot.assign(K, -1); S.nc = 0;
+  for (int k = 0; k < K; ++k) if (cu[k] && !cf(k)) S.camslot[k] = S.nc++;
+  S.lmfree_p_h.assign(d->n_points, -1); S.nl = 0;
+  for (int k = 0; k < d->n_points; ++k) if (lu[k] && !d->h_rho_fixed[k]) S.lmfree_p_h[k] = S.nl++;
+  S.lmfree_t_h.assign(d->n_planes, -1); S.npl = 0;
+  for (int k = 0; k < d->n_planes; ++k) if (pu[k] && !d->h_theta_fixed[k]) S.lmfree_t_h[k] = S.npl++;
+  const int nc = S.nc;
+  S.n = 6 * nc;
+  S.Tn = chol_workspace_dims(S.n, &S.ld, &S.rows);
+
+  // ---- global block structure: unique (a<=b) camslot pairs from every active observation / landmark ----
+  // per landmark camslot sets (global), via sort of (landmark, camslot)
+  std::vector<uint64_t> bkeys;
+  bkeys.reserve((size_t)(GP + GT) * 3);
+  auto add_key = [&](int a, int b) { if (a > b) std::swap(a, b); bkeys.push_back((uint64_t)a * (uint64_t)nc + (uint64_t)b); };
+  {
+    // direct pairs
+    for (int i = 0; i < GP; ++i) if (gp_active[i]) {
+      const int cs = S.camslot[d->h_p_cam[i]], hs = S.camslot[d->h_p_host[i]];
+      if (cs >= 0) add_key(cs, cs);
+      if (hs >= 0) add_key(hs, hs);
+      if (cs >= 0 && hs >= 0 && cs != hs) add_key(cs, hs);
+    }
+    for (int i = 0; i < GT; ++i) if (gt_active[i]) {
+      const int cs = S.camslot[d->h_t_cam[i]], hs = S.camslot[d->h_t_host[i]];
+      if (cs >= 0) add_key(cs, cs);
+      if (hs >= 0) add_key(hs, hs);
+      if (cs >= 0 && hs >= 0 && cs != hs) add_key(cs, hs);
+    }
+    // schur pairs: all pairs of distinct camslots touching the same free landmark
+    auto schur_pairs = [&](int n_obs, const std::vector<int32_t>& ocam, const std::vector<int32_t>& ohost, const std::vector<int32_t>& olm,
+                           const std::vector<uint8_t>& act, const std::vector<int>& lmfree, int nlm) {
+      std::vector<int> keys; std::vector<int> cams;
+      for (int i = 0; i < n_obs; ++i) {
+        if (!act[i] || lmfree[olm[i]] < 0) continue;
+        const int cs = S.camslot[ocam[i]], hs = S.camslot[ohost[i]];
+        if (cs >= 0) { keys.push_back(lmfree[olm[i]]); cams.push_back(cs); }
+        if (hs >= 0) { keys.push_back(lmfree[olm[i]]); cams.push_back(hs); }
+      }
+      std::vector<int> ptr, order;
+      build_csr(nlm, keys, ptr, order);
+      std::vector<int> set;
+      for (int l = 0; l < nlm; ++l) {
+        set.clear();
+        for (int e = ptr[l]; e < ptr[l + 1]; ++e) set.push_back(cams[order[e]]);
+        std::sort(set.begin(), set.end());
+        set.erase(std::unique(set.begin(), set.end()), set.end());
+        for (size_t x = 0; x < set.size(); ++x)
+          for (size_t y = x; y < set.size(); ++y) add_key(set[x], set[y]);
+      }
+    };
+    schur_pairs(GP, d->h_p_cam, d->h_p_host, d->h_p_lm, gp_active, S.lmfree_p_h, S.nl);
+    schur_pairs(GT, d->h_t_cam, d->h_t_host, d->h_t_plane, gt_active, S.lmfree_t_h, S.npl);
+  }
+  std::sort(bkeys.begin(), bkeys.end());
+  bkeys.erase(std::unique(bkeys.begin(), bkeys.end()), bkeys.end());
+  S.nblk = (int)bkeys.size();
+  std::vector<int> blk_a(S.nblk), blk_b(S.nblk), diag_blk(nc, -1);
+  for (int b = 0; b < S.nblk; ++b) {
+    blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); blk_b[b] = (int)(bkeys[b] % (uint64_t)nc);
+    if (blk_a[b] == blk_b[b]) diag_blk[blk_a[b]] = b;
+  }
+  auto blk_of = [&](int a, int b) {
+    if (a > b) std::swap(a, b);
+    const uint64_t key = (uint64_t)a * (uint64_t)nc + (uint64_t)b;
+    return (int)(std::lower_bound(bkeys.begin(), bkeys.end(), key) - bkeys.begin());
+  };
+
+  // ---- local observations ----
+  const int lp = d->n_pobs, lt = d->n_tobs; S.lp = lp; S.lt = lt;
+  auto gidx_p = [&](int i) { return d->sharded ? d->gsel_p[i] : i; };
+  auto gidx_t = [&](int i) { return d->sharded ? d->gsel_t[i] : i; };
+  std::vector<int> p_cs(lp), p_hs(lp), t_cs(lt), t_hs(lt);
+  std::vector<uint8_t> p_act(lp), t_act(lt), t_fm(lt);
+  std::vector<int32_t> lp_lm(lp), lt_lm(lt);
+  for (int i = 0; i < lp; ++i) {
+    const int g = gidx_p(i);
+    p_cs[i] = S.camslot[d->h_p_cam[g]]; p_hs[i] = S.camslot[d->h_p_host[g]]; lp_lm[i] = d->h_p_lm[g]; p_act[i] = gp_active[g];
+  }
+  for (int i = 0; i < lt; ++i) {
+    const int g = gidx_t(i);
+    t_cs[i] = S.camslot[d->h_t_cam[g]]; t_hs[i] = S.camslot[d->h_t_host[g]]; lt_lm[i] = d->h_t_plane[g]; t_act[i] = gt_active[g];
+    t_fm[i] = (uint8_t)((t_cs[i] >= 0 ? 1 : 0) | (t_hs[i] >= 0 ? 2 : 0) | (S.lmfree_t_h[lt_lm[i]] >= 0 ? 4 : 0));
+  }
+  LmStruct LP, LT;
+  build_landmark_side(lp, lp_lm.data(), p_cs, p_hs, p_act, S.lmfree_p_h, d->n_points, LP);
+  build_landmark_side(lt, lt_lm.data(), t_cs, t_hs, t_act, S.lmfree_t_h, d->n_planes, LT);
+  S.nvp = (int)LP.v_gl.size(); S.nvt = (int)LT.v_gl.size();
+  S.nsp = (int)LP.slot_cam.size(); S.nst = (int)LT.slot_cam.size();
+  S.vp_gl_h = LP.v_gl; S.vt_gl_h = LT.v_gl;
+
+  // ---- local entry lists per block ----
+  std::vector<int> kdp, vdp, kdt, vdt, ksp, kst;
+  std::vector<int2> vsp, vst;
+  auto direct = [&](int n_obs, const std::vector<int>& cs, const std::vector<int>& hs, const std::vector<uint8_t>& act,
+                    std::vector<int>& keys, std::vector<int>& vals) {
+    for (int i = 0; i < n_obs; ++i) {
+      if (!act[i]) continue;
+      const int c = cs[i], h = hs[i];
+      if (c >= 0) { keys.push_back(diag_blk[c]); vals.push_back((i << 2) | 0); }
+      if (h >= 0) { keys.push_back(diag_blk[h]); vals.push_back((i << 2) | 1); }
+      if (c >= 0 && h >= 0) {
+        if (c < h) { keys.push_back(blk_of(c, h)); vals.push_back((i << 2) | 2); }
+        else if (h < c) { keys.push_back(blk_of(h, c)); vals.push_back((i << 2) | 3); }
+        else {  // cam == host never happens in the reference (src/optimizer.cc:1397); keep the maths right anyway
+          keys.push_back(diag_blk[c]); vals.push_back((i << 2) | 2);
+          keys.push_back(diag_blk[c]); vals.push_back((i << 2) | 3);
+        }
+      }
+    }
+  };
+  direct(lp, p_cs, p_hs, p_act, kdp, vdp);
+  direct(lt, t_cs, t_hs, t_act, kdt, vdt);
+  auto schur = [&](const LmStruct& L, std::vector<int>& keys, std::vector<int2>& vals) {
+    const int nv = (int)L.v_gl.size();
+    for (int v = 0; v < nv; ++v)
+      for (int x = L.slot_ptr[v]; x < L.slot_ptr[v + 1]; ++x)
+        for (int y = x; y < L.slot_ptr[v + 1]; ++y) { keys.push_back(blk_of(L.slot_cam[x], L.slot_cam[y])); vals.push_back(make_int2(x, y)); }
+  };
+  schur(LP, ksp, vsp);
+  schur(LT, kst, vst);
+  auto csr_i = [&](const std::vector<int>& keys, const std::vector<int>& vals, std::vector<int>& ptr, std::vector<int>& out) {
+    std::vector<int> order; build_csr(S.nblk, keys, ptr, order);
+    out.resize(order.size());
+    for (size_t k = 0; k < order.size(); ++k) out[k] = vals[order[k]];
+  };
+  auto csr_2 = [&](const std::vector<int>& keys, const std::vector<int2>& vals, std::vector<int>& ptr, std::vector<int2>& out) {
+    std::vector<int> order; build_csr(S.nblk, keys, ptr, order);
+    out.resize(order.size());
+    for (size_t k = 0; k < order.size(); ++k) out[k] = vals[order[k]];
+  };
+  std::vector<int> bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr;
+  std::vector<int2> bsp, bst;
+  csr_i(kdp, vdp, bdp_ptr, bdp); csr_i(kdt, vdt, bdt_ptr, bdt);
+  csr_2(ksp, vsp, bsp_ptr, bsp); csr_2(kst, vst, bst_ptr, bst);
+
+  // ---- upload ----
+  TSL_CUDA(up(S.camslot_d, S.camslot, st));
+  TSL_CUDA(up(S.p_cs, p_cs, st)); TSL_CUDA(up(S.p_hs, p_hs, st)); TSL_CUDA(up(S.p_ls, LP.obs_ls, st));
+  TSL_CUDA(up(S.t_cs, t_cs, st)); TSL_CUDA(up(S.t_hs, t_hs, st)); TSL_CUDA(up(S.t_ls, LT.obs_ls, st));
+  TSL_CUDA(up(S.p_active, p_act, st)); TSL_CUDA(up(S.t_active, t_act, st)); TSL_CUDA(up(S.t_fmask, t_fm, st));
+  TSL_CUDA(up(S.vp_gl, LP.v_gl, st)); TSL_CUDA(up(S.vt_gl, LT.v_gl, st));
+  TSL_CUDA(up(S.vp_obs_ptr, LP.obs_ptr, st)); TSL_CUDA(up(S.vp_obs, LP.obs, st));
+  TSL_CUDA(up(S.vt_obs_ptr, LT.obs_ptr, st)); TSL_CUDA(up(S.vt_obs, LT.obs, st));
+  TSL_CUDA(up(S.sp_ptr, LP.slot_ptr, st)); TSL_CUDA(up(S.sp_cam, LP.slot_cam, st)); TSL_CUDA(up(S.sp_lm, LP.slot_lm, st));
+  TSL_CUDA(up(S.spe_ptr, LP.ent_ptr, st)); TSL_CUDA(up(S.spe, LP.ent, st));
+  TSL_CUDA(up(S.st_ptr, LT.slot_ptr, st)); TSL_CUDA(up(S.st_cam, LT.slot_cam, st)); TSL_CUDA(up(S.st_lm, LT.slot_lm, st));
+  TSL_CUDA(up(S.ste_ptr, LT.ent_ptr, st)); TSL_CUDA(up(S.ste, LT.ent, st));
+  TSL_CUDA(up(S.blk_a, blk_a, st)); TSL_CUDA(up(S.blk_b, blk_b, st)); TSL_CUDA(up(S.diag_blk, diag_blk, st));
+  TSL_CUDA(up(S.bdp_ptr, bdp_ptr, st)); TSL_CUDA(up(S.bdp, bdp, st)); TSL_CUDA(up(S.bdt_ptr, bdt_ptr, st)); TSL_CUDA(up(S.bdt, bdt, st));
+  TSL_CUDA(up(S.bsp_ptr, bsp_ptr, st)); TSL_CUDA(up(S.bsp, bsp, st)); TSL_CUDA(up(S.bst_ptr, bst_ptr, st)); TSL_CUDA(up(S.bst, bst, st));
+  if (d->sharded) { TSL_CUDA(up(S.gsel_p, d->gsel_p, st)); TSL_CUDA(up(S.gsel_t, d->gsel_t, st)); }
+  // ---- value buffers ----
+  TSL_CUDA(S.xc_cams.reserve(7 * (size_t)K)); TSL_CUDA(S.xc_rho.reserve(d->n_points)); TSL_CUDA(S.xc_theta.reserve(3 * (size_t)d->n_planes));
+  TSL_CUDA(S.pr.reserve(2 * (size_t)lp)); TSL_CUDA(S.pJ.reserve(26 * (size_t)lp)); TSL_CUDA(S.cr_p.reserve(2 * (size_t)lp));
+  TSL_CUDA(S.tr.reserve(8 * (size_t)lt)); TSL_CUDA(S.tJ.reserve(120 * (size_t)lt)); TSL_CUDA(S.cr_t.reserve(8 * (size_t)lt));
+  TSL_CUDA(S.scale_c.reserve(6 * (size_t)nc)); TSL_CUDA(S.colnorm_c.reserve(6 * (size_t)nc));
+  TSL_CUDA(S.scale_vp.reserve(S.nvp)); TSL_CUDA(S.scale_vt.reserve(3 * (size_t)S.nvt));
+  TSL_CUDA(S.Vp.reserve(S.nvp)); TSL_CUDA(S.gp.reserve(S.nvp)); TSL_CUDA(S.Vinvp.reserve(S.nvp));
+  TSL_CUDA(S.Vt.reserve(9 * (size_t)S.nvt)); TSL_CUDA(S.gt.reserve(3 * (size_t)S.nvt)); TSL_CUDA(S.Vinvt.reserve(9 * (size_t)S.nvt));
+  TSL_CUDA(S.Ep.reserve(6 * (size_t)S.nsp)); TSL_CUDA(S.Et.reserve(18 * (size_t)S.nst));
+  S.red_n = (size_t)S.nblk * 36 + 18 * (size_t)nc;
+  TSL_CUDA(S.red.reserve(S.red_n));
+  S.Sblk = S.red.p; S.bvec = S.red.p + (size_t)S.nblk * 36; S.graw = S.bvec + 6 * (size_t)nc; S.udiag = S.graw + 6 * (size_t)nc;
+  TSL_CUDA(cudaMemsetAsync(S.red.p, 0, (S.red_n ? S.red_n : 1) * sizeof(double), st));
+  TSL_CUDA(S.scl.reserve(SC_N)); TSL_CUDA(S.scr.reserve(SC_N));
+  S.sc = S.scl.p;
+  TSL_CUDA(cudaMemsetAsync(S.scl.p, 0, SC_N * sizeof(double), st));
+  TSL_CUDA(S.mx.reserve(MX_N));
+  TSL_CUDA(S.A.reserve((size_t)S.rows * S.ld)); TSL_CUDA(S.ywork.reserve(S.ld)); TSL_CUDA(S.yc.reserve(S.ld));
+  TSL_CUDA(S.delta_c.reserve(6 * (size_t)nc)); TSL_CUDA(S.delta_vp.reserve(S.nvp)); TSL_CUDA(S.delta_vt.reserve(3 * (size_t)S.nvt));
+  const size_t nparts = 2 * ((size_t)(lp + 127) / 128 + (size_t)(8 * (size_t)lt + 127) / 128) + 2 * ((size_t)(S.nvp + 255) / 256 + (size_t)(S.nvt + 255) / 256) + 64;
+  TSL_CUDA(S.parts.reserve(nparts));
+  TSL_CUDA(S.fail.reserve(1));
+  TSL_CUDA(cudaStreamSynchronize(st));
+  S.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+  return TSLAM_OK;
+}
+
+// ---- phase timing helpers -----------------------------------------------------------------------------
+static void mark(Solver& S, int kind) {
+  if (!S.timing) return;
+  if (S.ev_used == (int)S.ev.size()) { cudaEvent_t e; cudaEventCreate(&e); S.ev.push_back(e); S.ev_kind.push_back(0); }
+  S.ev_kind[S.ev_used] = kind;
+  cudaEventRecord(S.ev[S.ev_used++], S.ctx->stream);
+}
+
+static inline int grid_for(int n, int b) { return n > 0 ? (n + b - 1) / b : 0; }
+
+// Evaluate residuals (+ Jacobians) at (cams, rho, theta); cost -> sc[cost_slot], sc[cost_slot+1]
+static int eval_at(Solver& S, const double* cams, const double* rho, const double* theta, bool want_J, int jac_mode, int cost_slot,
+                   double* pr, double* tr) {
+  tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
+  int np = 0, nt = 0;
+  double* parts = S.parts.p;
+  int rc = launch_eval_points_robust(ctx, d, cams, rho, S.p_active.p, pr, want_J ? S.pJ.p : nullptr, parts, &np);
+  if (rc) return rc;
+  rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? S.tJ.p : nullptr, parts + 2 * np, &nt);
+  if (rc) return rc;
+  sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 0, S.sc + cost_slot, 0);
+  sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 1, S.sc + cost_slot + 1, 0);
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
+}
+
+static BlockLists block_lists(Solver& S) {
+  BlockLists L;
+  L.dp_ptr = S.bdp_ptr.p; L.dp = S.bdp.p; L.dt_ptr = S.bdt_ptr.p; L.dt = S.bdt.p;
+  L.sp_ptr = S.bsp_ptr.p; L.sp = S.bsp.p; L.st_ptr = S.bst_ptr.p; L.st = S.bst.p;
+  return L;
+}
+
+// after a new Jacobian: V, g, E in the scaled system
+static int accumulate_landmarks(Solver& S) {
+  cudaStream_t st = S.ctx->stream;
+  if (S.nvp) {
+    lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p);
+    if (S.nsp) slot_accum_kernel<1, 2, 13><<<grid_for(S.nsp, 128), 128, 0, st>>>(S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p);
+  }
+  if (S.nvt) {
+    lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p);
+    if (S.nst) slot_accum_kernel<3, 8, 15><<<grid_for(S.nst, 64), 64, 0, st>>>(S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p);
+  }
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
+}
+
+static int compute_jacobi_scaling(Solver& S) {
+  cudaStream_t st = S.ctx->stream;
+  const int nc = S.nc;
+  // unscaled column norms: cameras via the diagonal blocks' direct entries, landmarks via V with scale == 1
+  if (nc) {
+    cam_colnorm_kernel<<<grid_for(nc * 32, 128), 128, 0, st>>>(nc, S.diag_blk.p, block_lists(S), S.pJ.p, S.tJ.p, S.colnorm_c.p);
+    TSL_CHECK_LAUNCH();
+    int rc = comm_allreduce_sum(S.ctx, S.colnorm_c.p, 6 * (size_t)nc);
+    if (rc) return rc;
+    scale_from_norm_kernel<<<grid_for(6 * nc, 256), 256, 0, st>>>(6 * nc, S.colnorm_c.p, S.scale_c.p);
+  }
+  if (S.nvp) {
+    fill_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.scale_vp.p, S.nvp, 1.0);
+    lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p);
+    lm_scale_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, S.scale_vp.p);
+  }
+  if (S.nvt) {
+    fill_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.scale_vt.p, 3 * S.nvt, 1.0);
+    lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p);
+    lm_scale_kernel<3><<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.nvt, S.Vt.p, S.scale_vt.p);
+  }
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
+}
+
+// One linear solve for the current radius: builds the reduced system, reduces it across ranks,
+// factors it and back-substitutes; leaves delta_* and the candidate parameters on the device.
+static int compute_step(Solver& S, double radius) {
+  tslam_ctx* ctx = S.ctx; cudaStream_t st = ctx->stream;
+  const double inv_radius = 1.0 / radius;
+  const int nc = S.nc;
+  mark(S, 1);  // landmark / Schur prep
+  TSL_CUDA(cudaMemsetAsync(S.mx.p, 0, MX_N * sizeof(double), st));
+  TSL_CUDA(cudaMemsetAsync(S.fail.p, 0, sizeof(int), st));
+  if (S.nvp) lm_vinv_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, inv_radius, S.Vinvp.p, S.mx.p);
+  if (S.nvt) lm_vinv_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.Vt.p, inv_radius, S.Vinvt.p, S.mx.p);
+  mark(S, 2);  // reduced system build
+  if (S.nblk) {
+    BlockArgs B;
+    B.nblk = S.nblk; B.blk_a = S.blk_a.p; B.blk_b = S.blk_b.p; B.L = block_lists(S);
+    B.pJ = S.pJ.p; B.pr = S.pr.p; B.tJ = S.tJ.p; B.tr = S.tr.p; B.scale_c = S.scale_c.p;
+    B.Ep = S.Ep.p; B.Vinvp = S.Vinvp.p; B.gp = S.gp.p; B.sp_lm = S.sp_lm.p;
+    B.Et = S.Et.p; B.Vinvt = S.Vinvt.p; B.gt = S.gt.p; B.st_lm = S.st_lm.p;
+    B.Sblk = S.Sblk; B.bvec = S.bvec; B.graw = S.graw; B.udiag = S.udiag;
+    schur_block_kernel<<<grid_for(S.nblk * 32, 128), 128, 0, st>>>(B);
+    TSL_CHECK_LAUNCH();
+  }
+  mark(S, 3);  // all-reduce
+  if (ctx->world > 1) {
+    int rc = comm_allreduce_sum(ctx, S.red.p, S.red_n);
+    if (rc) return rc;
+  }
+  mark(S, 4);  // Cholesky
+  if (nc) {
+    TSL_CUDA(cudaMemsetAsync(S.A.p, 0, (size_t)S.rows * S.ld * sizeof(double), st));
+    ScatterArgs Sa{S.nblk, S.blk_a.p, S.blk_b.p, S.Sblk, S.bvec, S.udiag, inv_radius, S.A.p, S.ld, S.n, S.rows, S.Tn * 64};
+    const int total = S.nblk * 36 + S.ld;
+    scatter_kernel<<<grid_for(total, 256), 256, 0, st>>>(Sa);
+    TSL_CHECK_LAUNCH();
+    int rc = chol_solve(ctx, S.A.p, S.n, S.ywork.p, S.yc.p, S.fail.p);
+    if (rc) return rc;
+    copy_fail_kernel<<<1, 1, 0, st>>>(S.fail.p, S.mx.p);
+  }
+  mark(S, 5);  // back-substitution + candidate
+  if (S.nvp) backsub_kernel<1><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p);
+  if (S.nvt) backsub_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p);
+  candidate_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0);
+  const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
+  double* parts = S.parts.p;
+  if (S.nvp) candidate_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts);
+  if (S.nvt) candidate_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp);
+  if (gvp + gvt) {
+    sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 0, S.sc + SC_STEP2, 1);
+    sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 1, S.sc + SC_CNORM2, 1);
+  }
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
+}
+
+static int model_and_candidate_cost(Solver& S, int jac_mode) {
+  cudaStream_t st = S.ctx->stream;
+  mark(S, 6);  // model cost change + candidate cost
+  const int gp = grid_for(S.lp, 256), gt = grid_for(S.lt, 256);
+  double* parts = S.parts.p;
+  if (S.lp) model_cost_kernel<1, 2, 13><<<gp, 256, 0, st>>>(S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts);
+  if (S.lt) model_cost_kernel<3, 8, 15><<<gt, 256, 0, st>>>(S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp);
+  sum_parts_kernel<<<1, 256, 0, st>>>(parts, gp + gt, 1, 0, S.sc + SC_MCC, 0);
+  TSL_CHECK_LAUNCH();
+  int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, false, jac_mode, SC_CAND, S.cr_p.p, S.cr_t.p);
+  if (rc) return rc;
+  mark(S, 7);  // end of the iteration's device work
+  return TSLAM_OK;
+}
+
+static int gradient_max_norm(Solver& S) {
+  cudaStream_t st = S.ctx->stream;
+  // graw (cams) is produced by schur_block_kernel and already all-reduced; landmark gradients are local
+  gmax_cams_kernel<<<grid_for(S.K, 128), 128, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.graw, S.mx.p);
+  if (S.nvp) gmax_lm_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.gp.p, S.scale_vp.p, S.mx.p);
+  if (S.nvt) gmax_lm_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p);
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
+}
+
+static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tslam_solve_summary* out, double* trace) {
+  tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d; cudaStream_t st = ctx->stream;
+  auto T0 = std::chrono::steady_clock::now();
+  const double ftol = opt->function_tolerance > 0 ? opt->function_tolerance : 1e-6;
+  const double gtol = opt->gradient_tolerance > 0 ? opt->gradient_tolerance : 1e-10;
+  const double ptol = opt->parameter_tolerance > 0 ? opt->parameter_tolerance : 1e-8;
+  double radius = opt->initial_radius > 0 ? opt->initial_radius : 1e4;
+  const double max_radius = 1e16, min_radius = 1e-32, min_rel_dec = 1e-3;
+  double decrease_factor = 2.0;
+  const int jac_mode = opt->text_jac_mode;
+  tslam_solve_summary sum{};
+  sum.n_free_cams = S.nc; sum.n_free_points = S.nl; sum.n_free_planes = S.npl; sum.reduced_dim = S.n; sum.setup_ms = S.setup_ms;
+  double* h = ctx->h_scalars;
+
+  // current / candidate parameter buffers
+  S.x_cams = d->cams.p; S.x_rho = d->rho.p; S.x_theta = d->theta.p;
+  S.c_cams = S.xc_cams.p; S.c_rho = S.xc_rho.p; S.c_theta = S.xc_theta.p;
+  TSL_CUDA(cudaMemcpyAsync(S.c_rho, S.x_rho, sizeof(double) * d->n_points, cudaMemcpyDeviceToDevice, st));
+  TSL_CUDA(cudaMemcpyAsync(S.c_theta, S.x_theta, sizeof(double) * 3 * (size_t)d->n_planes, cudaMemcpyDeviceToDevice, st));
+
+  // ---- iteration 0 ----
+  mark(S, 0);
+  int rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.pr.p, S.tr.p);
+  if (rc) return rc;
+  if ((rc = compute_jacobi_scaling(S))) return rc;
+  if ((rc = accumulate_landmarks(S))) return rc;
+  // x_norm
+  {
+    xnorm_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.sc + SC_XNORM2, ctx->rank == 0 ? 1.0 : 0.0);
+    const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
+    if (S.nvp) xnorm_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.parts.p);
+    if (S.nvt) xnorm_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.parts.p + gvp);
+    if (gvp + gvt) sum_parts_kernel<<<1, 256, 0, st>>>(S.parts.p, gvp + gvt, 1, 0, S.sc + SC_XNORM2, 1);
+    TSL_CHECK_LAUNCH();
+  }
+  double x_cost = 0, fixed_cost = 0, x_norm = 0, gmax = 0;
+  int iter = 0, n_ok = 0, n_bad = 0, invalid_run = 0, term = TSLAM_TERM_NO_CONVERGENCE;
+  bool have_cost = false;
+  auto T1 = std::chrono::steady_clock::now();
+
+  while (true) {
+    if (iter >= max_iters) { term = TSLAM_TERM_NO_CONVERGENCE; break; }
+    if (radius <= min_radius) { term = TSLAM_TERM_NO_CONVERGENCE; break; }
+    if (S.nc + S.nl + S.npl == 0) break;
+    // ---- linear solve + candidate (speculative: the gradient test for THIS iteration is read back with it) ----
+    if ((rc = compute_step(S, radius))) return rc;
+    if ((rc = gradient_max_norm(S))) return rc;
+    if ((rc = model_and_candidate_cost(S, jac_mode))) return rc;
+    const double* sc_src = S.sc;
+    if (ctx->world > 1) {  // reduce a COPY: the local slots (cost at x, x-norm) persist across iterations
+      TSL_CUDA(cudaMemcpyAsync(S.scr.p, S.sc, SC_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if ((rc = comm_allreduce_sum(ctx, S.scr.p, SC_N))) return rc;
+      if ((rc = comm_allreduce_max(ctx, S.mx.p, MX_N))) return rc;
+      sc_src = S.scr.p;
+    }
+    TSL_CUDA(cudaMemcpyAsync(h, sc_src, SC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TSL_CUDA(cudaMemcpyAsync(h + SC_N, S.mx.p, MX_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TSL_CUDA(cudaStreamSynchronize(st));
+    if (!have_cost) {
+      x_cost = h[SC_COST]; fixed_cost = h[SC_FIXED]; x_norm = std::sqrt(h[SC_XNORM2]); have_cost = true;
+      sum.initial_cost = x_cost + fixed_cost; sum.fixed_cost = fixed_cost;
+      if (trace) { trace[0] = x_cost + fixed_cost; trace[1] = radius; trace[2] = 0; trace[3] = 1; }
+    }
+    gmax = h[SC_N + MX_GMAX];
+    if (gmax <= gtol) { term = TSLAM_TERM_GRADIENT_TOL; break; }  // Ceres tests this before computing the step
+    ++iter;
+    const bool lin_fail = h[SC_N + MX_FAIL] != 0.0;
+    const double mcc = h[SC_MCC], cand_cost = h[SC_CAND], step_norm = std::sqrt(h[SC_STEP2]);
+    const bool finite = std::isfinite(mcc) && std::isfinite(cand_cost) && std::isfinite(step_norm);
+    if (lin_fail || !finite || !(mcc > 0.0)) {
+      ++invalid_run; ++n_bad;
+      if (trace) { double* t = trace + 4 * iter; t[0] = x_cost + fixed_cost; t[1] = radius; t[2] = 0; t[3] = -1; }
+      if (invalid_run >= 5) { term = TSLAM_TERM_FAILURE; break; }
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      continue;
+    }
+    invalid_run = 0;
+    if (step_norm <= ptol * (x_norm + ptol)) {
+      term = TSLAM_TERM_PARAMETER_TOL;
+      if (trace) { double* t = trace + 4 * iter; t[0] = x_cost + fixed_cost; t[1] = radius; t[2] = 0; t[3] = 0; }
+      break;
+    }
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= ftol * x_cost) {
+      term = TSLAM_TERM_FUNCTION_TOL;
+      if (trace) { double* t = trace + 4 * iter; t[0] = x_cost + fixed_cost; t[1] = radius; t[2] = 0; t[3] = 0; }
+      break;
+    }
+    const double rel = cost_change / mcc;
+    if (rel > min_rel_dec) {
+      std::swap(S.x_cams, S.c_cams); std::swap(S.x_rho, S.c_rho); std::swap(S.x_theta, S.c_theta);
+      // the candidate buffers must carry the untouched (fixed / non-owned) entries too
+      TSL_CUDA(cudaMemcpyAsync(S.c_rho, S.x_rho, sizeof(double) * d->n_points, cudaMemcpyDeviceToDevice, st));
+      TSL_CUDA(cudaMemcpyAsync(S.c_theta, S.x_theta, sizeof(double) * 3 * (size_t)d->n_planes, cudaMemcpyDeviceToDevice, st));
+      x_norm = std::sqrt(h[SC_CNORM2]);
+      mark(S, 0);  // eval + J (the next iteration's linearisation point)
+      if ((rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.pr.p, S.tr.p))) return rc;
+      if ((rc = accumulate_landmarks(S))) return rc;
+      x_cost = cand_cost;  // identical evaluation point; the device value is re-read next iteration for the trace only
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      radius = std::min(max_radius, radius); decrease_factor = 2.0;
+      ++n_ok;
+      if (trace) { double* t = trace + 4 * iter; t[0] = x_cost + fixed_cost; t[1] = radius; t[2] = rel; t[3] = 1; }
+    } else {
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      ++n_bad;
+      if (trace) { double* t = trace + 4 * iter; t[0] = cand_cost + fixed_cost; t[1] = radius; t[2] = rel; t[3] = 0; }
+    }
+  }
+  TSL_CUDA(cudaStreamSynchronize(st));
+  // make d->cams / rho / theta hold the solution
+  if (S.x_cams != d->cams.p) {
+    TSL_CUDA(cudaMemcpyAsync(d->cams.p, S.x_cams, sizeof(double) * 7 * (size_t)S.K, cudaMemcpyDeviceToDevice, st));
+    TSL_CUDA(cudaMemcpyAsync(d->rho.p, S.x_rho, sizeof(double) * d->n_points, cudaMemcpyDeviceToDevice, st));
+    TSL_CUDA(cudaMemcpyAsync(d->theta.p, S.x_theta, sizeof(double) * 3 * (size_t)d->n_planes, cudaMemcpyDeviceToDevice, st));
+    TSL_CUDA(cudaStreamSynchronize(st));
+    S.x_cams = d->cams.p; S.x_rho = d->rho.p; S.x_theta = d->theta.p;
+  }
+  auto T2 = std::chrono::steady_clock::now();
+  sum.iterations = iter; sum.successful_steps = n_ok; sum.unsuccessful_steps = n_bad; sum.termination = term;
+  sum.final_cost = x_cost + fixed_cost;
+  sum.solve_ms = std::chrono::duration<double, std::milli>(T2 - T1).count() + std::chrono::duration<double, std::milli>(T1 - T0).count();
+  if (out) *out = sum;
+  return TSLAM_OK;
+}
+
+void free_solver(tslam_dev_problem* d) {
+  if (d && d->solver) { delete static_cast<Solver*>(d->solver); d->solver = nullptr; }
+}
+
+static int get_solver(tslam_ctx* ctx, tslam_dev_problem* d, Solver** out) {
+  if (!d->solver) {
+    Solver* S = new Solver();
+    S->ctx = ctx; S->d = d;
+    int rc = analyze_and_upload(*S);
+    if (rc) { delete S; return rc; }
+    d->solver = S;
+  }
+  *out = static_cast<Solver*>(d->solver);
+  return TSLAM_OK;
+}
+
+}  // namespace tsl
+
+using namespace tsl;
+
+extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, tslam_solve_summary* summary,
+                           double* final_residuals, double* trace) {
+  if (!ctx || !p || !opt) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (opt->max_iters < 0) return set_error(TSLAM_ERR_ARG, "max_iters < 0");
+  auto T0 = std::chrono::steady_clock::now();
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  tslam_dev_problem d;
+  int rc = upload_problem(ctx, p, &d, /*shard=*/true);
+  if (rc) return rc;
+  struct Guard { tslam_dev_problem* d; ~Guard() { free_solver(d); } } guard{&d};
+  Solver* S = nullptr;
+  if ((rc = get_solver(ctx, &d, &S))) return rc;
+  auto T1 = std::chrono::steady_clock::now();
+  tslam_solve_summary sum{};
+  if ((rc = run_lm(*S, opt, opt->max_iters, &sum, trace))) return rc;
+  cudaStream_t st = ctx->stream;
+  // ---- results back to the caller's arrays ----
+  if (ctx->world > 1) {
+    // every rank owns a subset of the landmarks: zero the others, sum across ranks, keep originals where nobody owns
+    DevBuf<double> orho, oth;
+    TSL_CUDA(orho.reserve(d.n_points)); TSL_CUDA(oth.reserve(3 * (size_t)d.n_planes));
+    TSL_CUDA(cudaMemsetAsync(orho.p, 0, sizeof(double) * d.n_points, st));
+    TSL_CUDA(cudaMemsetAsync(oth.p, 0, sizeof(double) * 3 * (size_t)d.n_planes, st));
+    if (S->nvp) export_lm_kernel<1><<<(S->nvp + 255) / 256, 256, 0, st>>>(S->nvp, S->vp_gl.p, d.rho.p, orho.p);
+    if (S->nvt) export_lm_kernel<3><<<(3 * S->nvt + 255) / 256, 256, 0, st>>>(S->nvt, S->vt_gl.p, d.theta.p, oth.p);
+    if ((rc = comm_allreduce_sum(ctx, orho.p, d.n_points))) return rc;
+    if ((rc = comm_allreduce_sum(ctx, oth.p, 3 * (size_t)d.n_planes))) return rc;
+    std::vector<double> hr(d.n_points), ht(3 * (size_t)d.n_planes);
+    TSL_CUDA(cudaMemcpyAsync(hr.data(), orho.p, sizeof(double) * d.n_points, cudaMemcpyDeviceToHost, st));
+    TSL_CUDA(cudaMemcpyAsync(ht.data(), oth.p, sizeof(double) * 3 * (size_t)d.n_planes, cudaMemcpyDeviceToHost, st));
+    TSL_CUDA(cudaMemcpyAsync(p->cams, d.cams.p, sizeof(double) * 7 * (size_t)d.n_cams, cudaMemcpyDeviceToHost, st));
+    TSL_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < d.n_points; ++k) if (S->lmfree_p_h[k] >= 0) p->rho[k] = hr[k];
+    for (int k = 0; k < d.n_planes; ++k) if (S->lmfree_t_h[k] >= 0) for (int a = 0; a < 3; ++a) p->theta[3 * k + a] = ht[3 * (size_t)k + a];
+  } else {
+    TSL_CUDA(cudaMemcpyAsync(p->cams, d.cams.p, sizeof(double) * 7 * (size_t)d.n_cams, cudaMemcpyDeviceToHost, st));
+    if (d.n_points) TSL_CUDA(cudaMemcpyAsync(p->rho, d.rho.p, sizeof(double) * d.n_points, cudaMemcpyDeviceToHost, st));
+    if (d.n_planes) TSL_CUDA(cudaMemcpyAsync(p->theta, d.theta.p, sizeof(double) * 3 * (size_t)d.n_planes, cudaMemcpyDeviceToHost, st));
+  }
+  if (final_residuals) {
+    // Problem::Evaluate: loss-corrected residuals of every block, insertion order (Appendix A.6)
+    if ((rc = eval_at(*S, d.cams.p, d.rho.p, d.theta.p, false, opt->text_jac_mode, SC_CAND, S->cr_p.p, S->cr_t.p))) return rc;
+    const size_t total = 2 * (size_t)d.g_pobs + 8 * (size_t)d.g_tobs;
+    if (ctx->world > 1) {
+      DevBuf<double> fr;
+      TSL_CUDA(fr.reserve(total));
+      TSL_CUDA(cudaMemsetAsync(fr.p, 0, total * sizeof(double), st));
+      if (S->lp) scatter_rows_kernel<<<(2 * S->lp + 255) / 256, 256, 0, st>>>(S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p);
+      if (S->lt) scatter_rows_kernel<<<(8 * S->lt + 255) / 256, 256, 0, st>>>(S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs);
+      if ((rc = comm_allreduce_sum(ctx, fr.p, total))) return rc;
+      TSL_CUDA(cudaMemcpyAsync(final_residuals, fr.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+      TSL_CUDA(cudaStreamSynchronize(st));
+    } else {
+      if (S->lp) TSL_CUDA(cudaMemcpyAsync(final_residuals, S->cr_p.p, 2 * (size_t)S->lp * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (S->lt) TSL_CUDA(cudaMemcpyAsync(final_residuals + 2 * (size_t)d.g_pobs, S->cr_t.p, 8 * (size_t)S->lt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+  }
+  TSL_CUDA(cudaStreamSynchronize(st));
+  auto T2 = std::chrono::steady_clock::now();
+  sum.setup_ms = std::chrono::duration<double, std::milli>(T1 - T0).count();
+  sum.total_ms = std::chrono::duration<double, std::milli>(T2 - T0).count();
+  if (summary) *summary = sum;
+  return TSLAM_OK;
+}
+
+extern "C" int tslam_dev_lm_iterations(tslam_ctx* ctx, tslam_dev_problem* d, const tslam_solve_options* opt, int iters, float* phase_ms,
+                                       tslam_solve_summary* summary) {
+  if (!ctx || !d || !opt) return set_error(TSLAM_ERR_ARG, "null argument");
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  Solver* S = nullptr;
+  int rc = get_solver(ctx, d, &S);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  // reset parameters to the uploaded values
+  TSL_CUDA(cudaMemcpyAsync(d->cams.p, d->cams0.p, sizeof(double) * 7 * (size_t)d->n_cams, cudaMemcpyDeviceToDevice, st));
+  TSL_CUDA(cudaMemcpyAsync(d->rho.p, d->rho0.p, sizeof(double) * d->n_points, cudaMemcpyDeviceToDevice, st));
+  TSL_CUDA(cudaMemcpyAsync(d->theta.p, d->theta0.p, sizeof(double) * 3 * (size_t)d->n_planes, cudaMemcpyDeviceToDevice, st));
+  S->timing = phase_ms != nullptr; S->ev_used = 0;
+  tslam_solve_summary sum{};
+  TSL_CUDA(cudaEventRecord(ctx->ev0, st));
+  rc = run_lm(*S, opt, iters, &sum, nullptr);
+  if (rc) return rc;
+  TSL_CUDA(cudaEventRecord(ctx->ev1, st));
+  TSL_CUDA(cudaEventSynchronize(ctx->ev1));
+  if (phase_ms) {
+    for (int k = 0; k < 8; ++k) phase_ms[k] = 0.f;
+    float whole = 0.f;
+    cudaEventElapsedTime(&whole, ctx->ev0, ctx->ev1);
+    for (int k = 0; k + 1 < S->ev_used; ++k) {
+      const int ph = S->ev_kind[k];
+      if (ph < 0 || ph > 6) continue;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, S->ev[k], S->ev[k + 1]);
+      phase_ms[ph] += ms;
+    }
+    const int denom = sum.iterations > 0 ? sum.iterations : 1;
+    for (int k = 0; k < 7; ++k) phase_ms[k] /= denom;
+    phase_ms[7] = whole / denom;
+  }
+  S->timing = false;
+  if (summary) *summary = sum;
+  return TSLAM_OK;
+}

@@ -26,7 +26,14 @@ int flush_l2(tslam_ctx* ctx) {
   return TSLAM_OK;
 }
 
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d) {
+template <typename T>
+static std::vector<T> gather_rows(const T* src, const std::vector<int32_t>& sel, int width) {
+  std::vector<T> out(sel.size() * (size_t)width);
+  for (size_t i = 0; i < sel.size(); ++i) memcpy(&out[i * width], src + (size_t)sel[i] * width, sizeof(T) * width);
+  return out;
+}
+
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard) {
   if (!p) return set_error(TSLAM_ERR_ARG, "null problem");
   if (p->n_cams <= 0 || !p->cams) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
   for (int i = 0; i < p->n_pobs; ++i) {
@@ -40,7 +47,8 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
   }
   cudaStream_t s = ctx->stream;
   d->n_cams = p->n_cams; d->n_points = p->n_points; d->n_planes = p->n_planes;
-  d->n_pobs = p->n_pobs; d->n_tobs = p->n_tobs; d->n_imgs = p->n_imgs; d->img_w = p->img_w; d->img_h = p->img_h;
+  d->g_pobs = p->n_pobs; d->g_tobs = p->n_tobs;
+  d->n_imgs = p->n_imgs; d->img_w = p->img_w; d->img_h = p->img_h;
   memcpy(d->K_point, p->K_point, sizeof(d->K_point)); memcpy(d->w_point, p->w_point, sizeof(d->w_point));
   memcpy(d->K_text, p->K_text, sizeof(d->K_text));
   d->huber_point = p->huber_point; d->w_text = p->w_text; d->huber_text = p->huber_text;
@@ -48,6 +56,10 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
   d->h_cam_fixed.assign(p->cam_fixed ? p->cam_fixed : zc.data(), (p->cam_fixed ? p->cam_fixed : zc.data()) + p->n_cams);
   d->h_rho_fixed.assign(p->rho_fixed ? p->rho_fixed : zr.data(), (p->rho_fixed ? p->rho_fixed : zr.data()) + p->n_points);
   d->h_theta_fixed.assign(p->theta_fixed ? p->theta_fixed : zt.data(), (p->theta_fixed ? p->theta_fixed : zt.data()) + p->n_planes);
+  d->h_p_cam.assign(p->p_cam, p->p_cam + p->n_pobs); d->h_p_host.assign(p->p_host, p->p_host + p->n_pobs);
+  d->h_p_lm.assign(p->p_lm, p->p_lm + p->n_pobs);
+  d->h_t_cam.assign(p->t_cam, p->t_cam + p->n_tobs); d->h_t_host.assign(p->t_host, p->t_host + p->n_tobs);
+  d->h_t_plane.assign(p->t_plane, p->t_plane + p->n_tobs);
   TSL_CUDA(d->cams.upload(p->cams, 7 * (size_t)p->n_cams, s));
   TSL_CUDA(d->cams0.upload(p->cams, 7 * (size_t)p->n_cams, s));
   TSL_CUDA(d->rho.upload(p->rho, p->n_points, s));
@@ -57,24 +69,46 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
   TSL_CUDA(d->cam_fixed.upload(d->h_cam_fixed.data(), p->n_cams, s));
   TSL_CUDA(d->rho_fixed.upload(d->h_rho_fixed.data(), p->n_points, s));
   TSL_CUDA(d->theta_fixed.upload(d->h_theta_fixed.data(), p->n_planes, s));
-  TSL_CUDA(d->p_uv.upload(p->p_uv, 2 * (size_t)p->n_pobs, s));
-  TSL_CUDA(d->p_ray.upload(p->p_ray, 2 * (size_t)p->n_pobs, s));
-  TSL_CUDA(d->p_cam.upload(p->p_cam, p->n_pobs, s));
-  TSL_CUDA(d->p_host.upload(p->p_host, p->n_pobs, s));
-  TSL_CUDA(d->p_lm.upload(p->p_lm, p->n_pobs, s));
-  TSL_CUDA(d->t_rays.upload(p->t_rays, 16 * (size_t)p->n_tobs, s));
-  TSL_CUDA(d->t_iref.upload(p->t_iref, 8 * (size_t)p->n_tobs, s));
-  TSL_CUDA(d->t_musigma.upload(p->t_musigma, 2 * (size_t)p->n_tobs, s));
-  TSL_CUDA(d->t_cam.upload(p->t_cam, p->n_tobs, s));
-  TSL_CUDA(d->t_host.upload(p->t_host, p->n_tobs, s));
-  TSL_CUDA(d->t_plane.upload(p->t_plane, p->n_tobs, s));
-  TSL_CUDA(d->t_img.upload(p->t_img, p->n_tobs, s));
   TSL_CUDA(d->imgs.upload(p->imgs, (size_t)p->n_imgs * p->img_w * p->img_h, s));
-  d->h_p_cam.assign(p->p_cam, p->p_cam + p->n_pobs); d->h_p_host.assign(p->p_host, p->p_host + p->n_pobs);
-  d->h_p_lm.assign(p->p_lm, p->p_lm + p->n_pobs);
-  d->h_t_cam.assign(p->t_cam, p->t_cam + p->n_tobs); d->h_t_host.assign(p->t_host, p->t_host + p->n_tobs);
-  d->h_t_plane.assign(p->t_plane, p->t_plane + p->n_tobs);
-  TSL_CUDA(cudaStreamSynchronize(s));  // host arrays are caller-owned and may change after return
+  d->sharded = shard && ctx->world > 1;
+  d->gsel_p.clear(); d->gsel_t.clear();
+  if (!d->sharded) {
+    d->n_pobs = p->n_pobs; d->n_tobs = p->n_tobs;
+    TSL_CUDA(d->p_uv.upload(p->p_uv, 2 * (size_t)p->n_pobs, s));
+    TSL_CUDA(d->p_ray.upload(p->p_ray, 2 * (size_t)p->n_pobs, s));
+    TSL_CUDA(d->p_cam.upload(p->p_cam, p->n_pobs, s));
+    TSL_CUDA(d->p_host.upload(p->p_host, p->n_pobs, s));
+    TSL_CUDA(d->p_lm.upload(p->p_lm, p->n_pobs, s));
+    TSL_CUDA(d->t_rays.upload(p->t_rays, 16 * (size_t)p->n_tobs, s));
+    TSL_CUDA(d->t_iref.upload(p->t_iref, 8 * (size_t)p->n_tobs, s));
+    TSL_CUDA(d->t_musigma.upload(p->t_musigma, 2 * (size_t)p->n_tobs, s));
+    TSL_CUDA(d->t_cam.upload(p->t_cam, p->n_tobs, s));
+    TSL_CUDA(d->t_host.upload(p->t_host, p->n_tobs, s));
+    TSL_CUDA(d->t_plane.upload(p->t_plane, p->n_tobs, s));
+    TSL_CUDA(d->t_img.upload(p->t_img, p->n_tobs, s));
+    TSL_CUDA(cudaStreamSynchronize(s));  // host arrays are caller-owned and may change after return
+    return TSLAM_OK;
+  }
+  // landmark-sharded upload: an observation lives with its landmark
+  for (int i = 0; i < p->n_pobs; ++i)
+    if (obs_owner(!d->h_rho_fixed[p->p_lm[i]], p->p_lm[i], i, ctx->world) == ctx->rank) d->gsel_p.push_back(i);
+  for (int i = 0; i < p->n_tobs; ++i)
+    if (obs_owner(!d->h_theta_fixed[p->t_plane[i]], p->t_plane[i], i, ctx->world) == ctx->rank) d->gsel_t.push_back(i);
+  d->n_pobs = (int)d->gsel_p.size(); d->n_tobs = (int)d->gsel_t.size();
+  {
+    auto uv = gather_rows(p->p_uv, d->gsel_p, 2); auto ray = gather_rows(p->p_ray, d->gsel_p, 2);
+    auto c = gather_rows(p->p_cam, d->gsel_p, 1); auto h = gather_rows(p->p_host, d->gsel_p, 1); auto l = gather_rows(p->p_lm, d->gsel_p, 1);
+    auto tr = gather_rows(p->t_rays, d->gsel_t, 16); auto ti = gather_rows(p->t_iref, d->gsel_t, 8); auto tm = gather_rows(p->t_musigma, d->gsel_t, 2);
+    auto tc = gather_rows(p->t_cam, d->gsel_t, 1); auto th = gather_rows(p->t_host, d->gsel_t, 1); auto tp = gather_rows(p->t_plane, d->gsel_t, 1);
+    auto tg = gather_rows(p->t_img, d->gsel_t, 1);
+    TSL_CUDA(d->p_uv.upload(uv.data(), uv.size(), s)); TSL_CUDA(d->p_ray.upload(ray.data(), ray.size(), s));
+    TSL_CUDA(d->p_cam.upload(c.data(), c.size(), s)); TSL_CUDA(d->p_host.upload(h.data(), h.size(), s)); TSL_CUDA(d->p_lm.upload(l.data(), l.size(), s));
+    TSL_CUDA(d->t_rays.upload(tr.data(), tr.size(), s)); TSL_CUDA(d->t_iref.upload(ti.data(), ti.size(), s));
+    TSL_CUDA(d->t_musigma.upload(tm.data(), tm.size(), s));
+    TSL_CUDA(d->t_cam.upload(tc.data(), tc.size(), s)); TSL_CUDA(d->t_host.upload(th.data(), th.size(), s));
+    TSL_CUDA(d->t_plane.upload(tp.data(), tp.size(), s)); TSL_CUDA(d->t_img.upload(tg.data(), tg.size(), s));
+    TSL_CUDA(cudaStreamSynchronize(s));
+  }
   return TSLAM_OK;
 }
 
@@ -130,7 +164,7 @@ int tslam_dev_upload(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_proble
   if (!ctx || !out) return set_error(TSLAM_ERR_ARG, "null argument");
   TSL_CUDA(cudaSetDevice(ctx->device));
   tslam_dev_problem* d = new tslam_dev_problem();
-  int rc = upload_problem(ctx, p, d);
+  int rc = upload_problem(ctx, p, d, /*shard=*/true);
   if (rc != TSLAM_OK) { delete d; return rc; }
   *out = d;
   return TSLAM_OK;

@@ -28,7 +28,7 @@ struct DevBuf {  // simple RAII device buffer (grow-only)
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
+    if (p && n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
@@ -76,14 +76,20 @@ struct tslam_dev_problem {
   // evaluation outputs (observation-major): r, J
   tsl::DevBuf<double> pr, pJ, tr, tJ;
   int pJ_cols = 0, tJ_cols = 0;
-  // host copy kept for structure analysis in the solver
+  // host copies (GLOBAL problem) kept for the solver's structure analysis
+  int g_pobs = 0, g_tobs = 0;                       // global observation counts (== n_pobs/n_tobs unless sharded)
   std::vector<int32_t> h_p_cam, h_p_host, h_p_lm, h_t_cam, h_t_host, h_t_plane;
   std::vector<uint8_t> h_cam_fixed, h_rho_fixed, h_theta_fixed;
+  std::vector<int32_t> gsel_p, gsel_t;              // global index of each local observation (sharded upload)
+  bool sharded = false;
   void* solver = nullptr;  // tsl::Solver*, owned (ba_solve.cu)
 };
 
 namespace tsl {
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d);
+// shard = true: keep only the observations this rank owns (multi-GPU global BA, ctx->world > 1)
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false);
+// observation ownership rule shared by upload and the solver's structure analysis
+inline int obs_owner(bool lm_free, int lm_index, int obs_index, int world) { return (lm_free ? lm_index : obs_index) % world; }
 int flush_l2(tslam_ctx* ctx);
 void free_solver(tslam_dev_problem* d);
 // kernels (ba_eval.cu)
