@@ -123,6 +123,8 @@ typedef struct tslam_solve_summary {
 typedef struct tslam_ctx tslam_ctx;
 const char* tslam_last_error(void);
 int tslam_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches) */
+long long tslam_launch_count(void);
 int tslam_ctx_create(int device_id, tslam_ctx** out);
 void tslam_ctx_destroy(tslam_ctx* ctx);
 /* Multi-GPU global BA: rank/world of a one-process-per-GPU job. `nccl_unique_id` is the 128-byte

@@ -75,3 +75,69 @@ def quat_plus(x, d):
     f = lambda a: _dp(np.ascontiguousarray(a, dtype=np.float64))
     lib().tso_quat_plus(f(x), f(d), _dp(out))
     return out
+
+
+# ---- ORB ----------------------------------------------------------------------------------------
+def orb_extract(img, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, blur_variant=0, max_kp=None):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    max_kp = max_kp or (nfeatures + 4 * nlevels + 64)
+    kp = np.zeros(max_kp, dtype=KP_DTYPE)
+    desc = np.zeros((max_kp, 32), dtype=np.uint8)
+    n = lib().tso_orb_extract(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(nfeatures), C.c_float(scale),
+                              C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), C.c_int(blur_variant), C.c_int(max_kp),
+                              kp.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p))
+    assert n >= 0, "max_kp too small"
+    return kp[:n].copy(), desc[:n].copy()
+
+
+def orb_level_size(w, h, scale, nlevels, level):
+    lw, lh = C.c_int(), C.c_int()
+    lib().tso_orb_level_size(C.c_int(w), C.c_int(h), C.c_float(scale), C.c_int(nlevels), C.c_int(level), C.byref(lw), C.byref(lh))
+    return lw.value, lh.value
+
+
+def orb_pyramid_level(img, scale, nlevels, level):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    lw, lh = orb_level_size(w, h, scale, nlevels, level)
+    out = np.zeros((lh, lw), dtype=np.uint8)
+    lib().tso_orb_pyramid_level(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(w), C.c_float(scale), C.c_int(nlevels),
+                                C.c_int(level), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def orb_features_per_level(nfeatures, scale, nlevels):
+    out = np.zeros(nlevels, dtype=np.int32)
+    lib().tso_orb_features_per_level(C.c_int(nfeatures), C.c_float(scale), C.c_int(nlevels), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    lib().tso_resize_linear(src.ctypes.data_as(C.c_void_p), C.c_int(src.shape[1]), C.c_int(src.shape[0]), out.ctypes.data_as(C.c_void_p),
+                            C.c_int(dw), C.c_int(dh))
+    return out
+
+
+def gaussian7(src, variant=0):
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    out = np.zeros_like(src)
+    lib().tso_gaussian7(src.ctypes.data_as(C.c_void_p), C.c_int(src.shape[1]), C.c_int(src.shape[0]), out.ctypes.data_as(C.c_void_p), C.c_int(variant))
+    return out
+
+
+def fast(img, threshold, max_kp=200000):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    xyr = np.zeros((max_kp, 3), dtype=np.int32)
+    n = lib().tso_fast(img.ctypes.data_as(C.c_void_p), C.c_int(img.shape[1]), C.c_int(img.shape[0]), C.c_int(threshold), C.c_int(max_kp),
+                       xyr.ctypes.data_as(C.c_void_p))
+    assert n <= max_kp
+    return xyr[:n].copy()
+
+
+def fast_atan2(y, x):
+    f = lib().tso_fast_atan2
+    f.restype = C.c_float
+    return f(C.c_float(y), C.c_float(x))

@@ -1,0 +1,85 @@
+"""CPU tests pinning the ORB oracle: committed cv2 golden vectors (always), live cv2 cross-checks (when
+cv2 imports), structural properties of the full extractor output."""
+import os
+import numpy as np
+import pytest
+from textslam_b200 import synth
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "orb_cv2_golden.npz"))
+
+
+def test_golden_resize_blur(oracle):
+    img = G["img"]
+    l1 = oracle.resize_linear(img, 267, 200)
+    assert np.array_equal(l1, G["resize_267x200"])
+    assert np.array_equal(oracle.resize_linear(l1, 222, 167), G["resize_222x167"])
+    assert np.array_equal(oracle.gaussian7(img, 0), G["blur7"])
+    assert not np.array_equal(oracle.gaussian7(img, 1), G["blur7"])  # 3.3.1 taps differ
+
+
+@pytest.mark.parametrize("t", [20, 7])
+def test_golden_fast(oracle, t):
+    img = G["img"]
+    assert np.array_equal(oracle.fast(img, t), G[f"fast{t}_full"])
+    roi = np.ascontiguousarray(img[30:30 + 41, 50:50 + 38])
+    assert np.array_equal(oracle.fast(roi, t), G[f"fast{t}_roi"])
+
+
+def test_golden_atan2_and_round(oracle):
+    out = np.array([oracle.fast_atan2(float(y), float(x)) for y, x in G["atan2_in"]], dtype=np.float32)
+    assert np.array_equal(out, G["atan2_out"])
+    lib = oracle.lib()
+    lib.tso_cv_round.argtypes = [__import__("ctypes").c_double]
+    assert [lib.tso_cv_round(float(v)) for v in G["round_in"]] == list(G["round_out"])
+
+
+def test_live_cv2_primitives(oracle):
+    cv2 = pytest.importorskip("cv2")
+    img = synth.orb_images(seed=2, n=1)[0]
+    lvl = img
+    for l in range(1, 8):  # the reference's pyramid chain (each level from the previous one)
+        w, h = oracle.orb_level_size(640, 480, 1.2, 8, l)
+        ref = cv2.resize(lvl, (w, h), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(oracle.resize_linear(lvl, w, h), ref), l
+        assert np.array_equal(oracle.orb_pyramid_level(img, 1.2, 8, l), ref)
+        lvl = ref
+    assert np.array_equal(oracle.gaussian7(lvl, 0), cv2.GaussianBlur(lvl, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+    for t in (20, 7):
+        det = cv2.FastFeatureDetector_create(threshold=t, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+        ref = np.array([[int(k.pt[0]), int(k.pt[1]), int(k.response)] for k in det.detect(img)], dtype=np.int32)
+        assert np.array_equal(oracle.fast(img, t), ref)
+
+
+def test_level_sizes_and_feature_budget(oracle):
+    sizes = [oracle.orb_level_size(640, 480, 1.2, 8, l) for l in range(8)]
+    assert sizes == [(640, 480), (533, 400), (444, 333), (370, 278), (309, 231), (257, 193), (214, 161), (179, 134)]
+    assert list(oracle.orb_features_per_level(1000, 1.2, 8)) == [217, 181, 151, 126, 105, 87, 73, 60]
+
+
+def test_full_extractor_structure(oracle):
+    img = synth.orb_images(seed=4, n=1)[0]
+    kp, desc = oracle.orb_extract(img)
+    per = oracle.orb_features_per_level(1000, 1.2, 8)
+    cnt = np.bincount(kp["octave"], minlength=8)
+    assert np.all(cnt >= per) and np.all(cnt <= per + 3)          # quad-tree may overshoot by up to 3 (Appendix B)
+    assert np.all(np.diff(kp["octave"]) >= 0)                      # level-major output order
+    scale = np.float32(1.2) ** kp["octave"]
+    x_l, y_l = kp["x"] / scale, kp["y"] / scale                    # level coordinates stay inside the 19 px margin
+    for l in range(8):
+        w, h = oracle.orb_level_size(640, 480, 1.2, 8, l)
+        m = kp["octave"] == l
+        assert x_l[m].min() >= 18.9 and x_l[m].max() <= w - 19 + 0.1 and y_l[m].min() >= 18.9 and y_l[m].max() <= h - 19 + 0.1
+    assert np.all((kp["angle"] >= 0) & (kp["angle"] < 360.01)) and np.all(kp["response"] >= 7)
+    assert desc.shape == (len(kp), 32) and desc.any()
+    kp2, desc2 = oracle.orb_extract(img)
+    assert np.array_equal(kp, kp2) and np.array_equal(desc, desc2)  # deterministic
+
+
+def test_flat_and_tiny_inputs(oracle):
+    flat = np.full((480, 640), 77, dtype=np.uint8)
+    kp, desc = oracle.orb_extract(flat)
+    assert len(kp) == 0
+    few = flat.copy()
+    few[200:230, 300:340] = 200   # one rectangle: a handful of corners, far fewer than requested
+    kp, desc = oracle.orb_extract(few)
+    assert 0 < len(kp) < 200

@@ -12,7 +12,7 @@ _LIB = None
 
 # every symbol include/tslam_b200.h declares
 EXPORTS = [
-    "tslam_last_error", "tslam_version", "tslam_ctx_create", "tslam_ctx_destroy", "tslam_nccl_unique_id",
+    "tslam_last_error", "tslam_version", "tslam_launch_count", "tslam_ctx_create", "tslam_ctx_destroy", "tslam_nccl_unique_id",
     "tslam_ctx_init_comm", "tslam_eval_points", "tslam_eval_text", "tslam_solve", "tslam_dev_upload", "tslam_dev_free",
     "tslam_dev_eval_points", "tslam_dev_eval_text", "tslam_dev_lm_iterations", "tslam_dev_download_eval",
     "tslam_dev_download_params", "tslam_orb_create", "tslam_orb_destroy", "tslam_orb_extract", "tslam_orb_level_size",
@@ -35,6 +35,7 @@ def lib():
         for name in EXPORTS:
             if name not in ("tslam_last_error", "tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy"):
                 getattr(_LIB, name).restype = C.c_int
+        _LIB.tslam_launch_count.restype = C.c_longlong
         for name in ("tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy"):
             getattr(_LIB, name).restype = None
     return _LIB

@@ -224,19 +224,19 @@ int launch_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, bool want
   PointArgs a = make_point_args(d, kind == TSLAM_PT_BA_NW || kind == TSLAM_PT_RHO);
   const int grid = (d->n_pobs + kEvalThreads - 1) / kEvalThreads;
   double2* r = reinterpret_cast<double2*>(d->pr.p);
-  if (!want_J) point_eval_kernel<0, 13, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr);
-  else if (ncols == 13) point_eval_kernel<0, 13, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p);
-  else if (ncols == 6) point_eval_kernel<0, 6, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p);
-  else point_eval_kernel<12, 1, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p);
+  if (!want_J) LAUNCH(point_eval_kernel<0, 13, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr));
+  else if (ncols == 13) LAUNCH(point_eval_kernel<0, 13, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+  else if (ncols == 6) LAUNCH(point_eval_kernel<0, 6, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+  else LAUNCH(point_eval_kernel<12, 1, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
 
 template <int MODE>
 static void launch_text_mode(tslam_ctx* ctx, tslam_dev_problem* d, int kind, const TextArgs& a, int grid) {
-  if (kind == TSLAM_TX_BA) text_eval_kernel<0, 15, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p);
-  else if (kind == TSLAM_TX_POSE) text_eval_kernel<0, 6, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p);
-  else text_eval_kernel<12, 3, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p);
+  if (kind == TSLAM_TX_BA) LAUNCH(text_eval_kernel<0, 15, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p));
+  else if (kind == TSLAM_TX_POSE) LAUNCH(text_eval_kernel<0, 6, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p));
+  else LAUNCH(text_eval_kernel<12, 3, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p));
 }
 
 int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, bool want_J) {
@@ -247,7 +247,7 @@ int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mod
   TextArgs a = make_text_args(d, kind == TSLAM_TX_THETA);
   a.free_mask = kind == TSLAM_TX_BA ? 7u : (kind == TSLAM_TX_POSE ? 1u : 4u);
   const int grid = (8 * d->n_tobs + kEvalThreads - 1) / kEvalThreads;
-  if (!want_J) text_eval_kernel<0, 15, 0, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, nullptr);
+  if (!want_J) LAUNCH(text_eval_kernel<0, 15, 0, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, nullptr));
   else if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) launch_text_mode<TSLAM_JAC_CENTRAL_DIFF>(ctx, d, kind, a, grid);
   else launch_text_mode<TSLAM_JAC_ANALYTIC>(ctx, d, kind, a, grid);
   TSL_CHECK_LAUNCH();
@@ -263,8 +263,8 @@ int launch_eval_points_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double
   a.cams = cams; a.rho = rho; a.huber = d->huber_point; a.active = active; a.cost_part = cost_part;
   const int grid = (d->n_pobs + kEvalThreads - 1) / kEvalThreads;
   *n_parts = grid;
-  if (J) point_eval_kernel<0, 13, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, reinterpret_cast<double2*>(r), J);
-  else point_eval_kernel<0, 13, false, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, reinterpret_cast<double2*>(r), nullptr);
+  if (J) LAUNCH(point_eval_kernel<0, 13, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, reinterpret_cast<double2*>(r), J));
+  else LAUNCH(point_eval_kernel<0, 13, false, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, reinterpret_cast<double2*>(r), nullptr));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -276,9 +276,9 @@ int launch_eval_text_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double* 
   a.cams = cams; a.theta = theta; a.huber = d->huber_text; a.active = active; a.cost_part = cost_part; a.free_masks = free_masks;
   const int grid = (8 * d->n_tobs + kEvalThreads - 1) / kEvalThreads;
   *n_parts = grid;
-  if (!J) text_eval_kernel<0, 15, 0, false, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr);
-  else if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) text_eval_kernel<0, 15, TSLAM_JAC_CENTRAL_DIFF, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, J);
-  else text_eval_kernel<0, 15, TSLAM_JAC_ANALYTIC, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, J);
+  if (!J) LAUNCH(text_eval_kernel<0, 15, 0, false, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr));
+  else if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) LAUNCH(text_eval_kernel<0, 15, TSLAM_JAC_CENTRAL_DIFF, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, J));
+  else LAUNCH(text_eval_kernel<0, 15, TSLAM_JAC_ANALYTIC, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, J));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }

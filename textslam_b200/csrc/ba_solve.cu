@@ -626,6 +626,7 @@ struct Solver {
   DevBuf<double> mx;         // max-reduced scalars
   DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts;
   DevBuf<int> fail;
+  CholSymbolic chol;
   size_t red_n = 0;
   double *Sblk = nullptr, *bvec = nullptr, *graw = nullptr, *udiag = nullptr, *sc = nullptr;
   double* x_cams = nullptr; double* x_rho = nullptr; double* x_theta = nullptr;   // current (alias d-> buffers or xc)
@@ -794,6 +795,16 @@ static int analyze_and_upload(Solver& S) {
     blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); blk_b[b] = (int)(bkeys[b] % (uint64_t)nc);
     if (blk_a[b] == blk_b[b]) diag_blk[blk_a[b]] = b;
   }
+  {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
+    std::vector<uint8_t> tile_nz((size_t)S.Tn * S.Tn, 0);
+    for (int b = 0; b < S.nblk; ++b) {
+      // block (a,b'), a <= b' lands in rows 6b'..6b'+5, cols 6a..6a+5 of the lower triangle
+      const int r0 = 6 * blk_b[b] / 64, r1 = (6 * blk_b[b] + 5) / 64, c0 = 6 * blk_a[b] / 64, c1 = (6 * blk_a[b] + 5) / 64;
+      for (int r = r0; r <= r1; ++r) for (int c = c0; c <= c1; ++c) if (c <= r) tile_nz[(size_t)r * S.Tn + c] = 1;
+    }
+    int rc = chol_symbolic(ctx, S.n, tile_nz, &S.chol);
+    if (rc) return rc;
+  }
   auto blk_of = [&](int a, int b) {
     if (a > b) std::swap(a, b);
     const uint64_t key = (uint64_t)a * (uint64_t)nc + (uint64_t)b;
@@ -931,8 +942,8 @@ static int eval_at(Solver& S, const double* cams, const double* rho, const doubl
   if (rc) return rc;
   rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? S.tJ.p : nullptr, parts + 2 * np, &nt);
   if (rc) return rc;
-  sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 0, S.sc + cost_slot, 0);
-  sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 1, S.sc + cost_slot + 1, 0);
+  LAUNCH(sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 0, S.sc + cost_slot, 0));
+  LAUNCH(sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 1, S.sc + cost_slot + 1, 0));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -948,12 +959,12 @@ static BlockLists block_lists(Solver& S) {
 static int accumulate_landmarks(Solver& S) {
   cudaStream_t st = S.ctx->stream;
   if (S.nvp) {
-    lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p);
-    if (S.nsp) slot_accum_kernel<1, 2, 13><<<grid_for(S.nsp, 128), 128, 0, st>>>(S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p);
+    LAUNCH(lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
+    if (S.nsp) LAUNCH(slot_accum_kernel<1, 2, 13><<<grid_for(S.nsp, 128), 128, 0, st>>>(S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p));
   }
   if (S.nvt) {
-    lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p);
-    if (S.nst) slot_accum_kernel<3, 8, 15><<<grid_for(S.nst, 64), 64, 0, st>>>(S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p);
+    LAUNCH(lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    if (S.nst) LAUNCH(slot_accum_kernel<3, 8, 15><<<grid_for(S.nst, 64), 64, 0, st>>>(S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -964,21 +975,21 @@ static int compute_jacobi_scaling(Solver& S) {
   const int nc = S.nc;
   // unscaled column norms: cameras via the diagonal blocks' direct entries, landmarks via V with scale == 1
   if (nc) {
-    cam_colnorm_kernel<<<grid_for(nc * 32, 128), 128, 0, st>>>(nc, S.diag_blk.p, block_lists(S), S.pJ.p, S.tJ.p, S.colnorm_c.p);
+    LAUNCH(cam_colnorm_kernel<<<grid_for(nc * 32, 128), 128, 0, st>>>(nc, S.diag_blk.p, block_lists(S), S.pJ.p, S.tJ.p, S.colnorm_c.p));
     TSL_CHECK_LAUNCH();
     int rc = comm_allreduce_sum(S.ctx, S.colnorm_c.p, 6 * (size_t)nc);
     if (rc) return rc;
-    scale_from_norm_kernel<<<grid_for(6 * nc, 256), 256, 0, st>>>(6 * nc, S.colnorm_c.p, S.scale_c.p);
+    LAUNCH(scale_from_norm_kernel<<<grid_for(6 * nc, 256), 256, 0, st>>>(6 * nc, S.colnorm_c.p, S.scale_c.p));
   }
   if (S.nvp) {
-    fill_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.scale_vp.p, S.nvp, 1.0);
-    lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p);
-    lm_scale_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, S.scale_vp.p);
+    LAUNCH(fill_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.scale_vp.p, S.nvp, 1.0));
+    LAUNCH(lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
+    LAUNCH(lm_scale_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, S.scale_vp.p));
   }
   if (S.nvt) {
-    fill_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.scale_vt.p, 3 * S.nvt, 1.0);
-    lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p);
-    lm_scale_kernel<3><<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.nvt, S.Vt.p, S.scale_vt.p);
+    LAUNCH(fill_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.scale_vt.p, 3 * S.nvt, 1.0));
+    LAUNCH(lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    LAUNCH(lm_scale_kernel<3><<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.nvt, S.Vt.p, S.scale_vt.p));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -993,8 +1004,8 @@ static int compute_step(Solver& S, double radius) {
   mark(S, 1);  // landmark / Schur prep
   TSL_CUDA(cudaMemsetAsync(S.mx.p, 0, MX_N * sizeof(double), st));
   TSL_CUDA(cudaMemsetAsync(S.fail.p, 0, sizeof(int), st));
-  if (S.nvp) lm_vinv_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, inv_radius, S.Vinvp.p, S.mx.p);
-  if (S.nvt) lm_vinv_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.Vt.p, inv_radius, S.Vinvt.p, S.mx.p);
+  if (S.nvp) LAUNCH(lm_vinv_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, inv_radius, S.Vinvp.p, S.mx.p));
+  if (S.nvt) LAUNCH(lm_vinv_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.Vt.p, inv_radius, S.Vinvt.p, S.mx.p));
   mark(S, 2);  // reduced system build
   if (S.nblk) {
     BlockArgs B;
@@ -1003,7 +1014,7 @@ static int compute_step(Solver& S, double radius) {
     B.Ep = S.Ep.p; B.Vinvp = S.Vinvp.p; B.gp = S.gp.p; B.sp_lm = S.sp_lm.p;
     B.Et = S.Et.p; B.Vinvt = S.Vinvt.p; B.gt = S.gt.p; B.st_lm = S.st_lm.p;
     B.Sblk = S.Sblk; B.bvec = S.bvec; B.graw = S.graw; B.udiag = S.udiag;
-    schur_block_kernel<<<grid_for(S.nblk * 32, 128), 128, 0, st>>>(B);
+    LAUNCH(schur_block_kernel<<<grid_for(S.nblk * 32, 128), 128, 0, st>>>(B));
     TSL_CHECK_LAUNCH();
   }
   mark(S, 3);  // all-reduce
@@ -1016,23 +1027,23 @@ static int compute_step(Solver& S, double radius) {
     TSL_CUDA(cudaMemsetAsync(S.A.p, 0, (size_t)S.rows * S.ld * sizeof(double), st));
     ScatterArgs Sa{S.nblk, S.blk_a.p, S.blk_b.p, S.Sblk, S.bvec, S.udiag, inv_radius, S.A.p, S.ld, S.n, S.rows, S.Tn * 64};
     const int total = S.nblk * 36 + S.ld;
-    scatter_kernel<<<grid_for(total, 256), 256, 0, st>>>(Sa);
+    LAUNCH(scatter_kernel<<<grid_for(total, 256), 256, 0, st>>>(Sa));
     TSL_CHECK_LAUNCH();
-    int rc = chol_solve(ctx, S.A.p, S.n, S.ywork.p, S.yc.p, S.fail.p);
+    int rc = chol_solve(ctx, S.chol, S.A.p, S.ywork.p, S.yc.p, S.fail.p);
     if (rc) return rc;
-    copy_fail_kernel<<<1, 1, 0, st>>>(S.fail.p, S.mx.p);
+    LAUNCH(copy_fail_kernel<<<1, 1, 0, st>>>(S.fail.p, S.mx.p));
   }
   mark(S, 5);  // back-substitution + candidate
-  if (S.nvp) backsub_kernel<1><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p);
-  if (S.nvt) backsub_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p);
-  candidate_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0);
+  if (S.nvp) LAUNCH(backsub_kernel<1><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p));
+  if (S.nvt) LAUNCH(backsub_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p));
+  LAUNCH(candidate_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0));
   const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
   double* parts = S.parts.p;
-  if (S.nvp) candidate_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts);
-  if (S.nvt) candidate_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp);
+  if (S.nvp) LAUNCH(candidate_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts));
+  if (S.nvt) LAUNCH(candidate_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp));
   if (gvp + gvt) {
-    sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 0, S.sc + SC_STEP2, 1);
-    sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 1, S.sc + SC_CNORM2, 1);
+    LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 0, S.sc + SC_STEP2, 1));
+    LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 1, S.sc + SC_CNORM2, 1));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -1043,9 +1054,9 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
   mark(S, 6);  // model cost change + candidate cost
   const int gp = grid_for(S.lp, 256), gt = grid_for(S.lt, 256);
   double* parts = S.parts.p;
-  if (S.lp) model_cost_kernel<1, 2, 13><<<gp, 256, 0, st>>>(S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts);
-  if (S.lt) model_cost_kernel<3, 8, 15><<<gt, 256, 0, st>>>(S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp);
-  sum_parts_kernel<<<1, 256, 0, st>>>(parts, gp + gt, 1, 0, S.sc + SC_MCC, 0);
+  if (S.lp) LAUNCH(model_cost_kernel<1, 2, 13><<<gp, 256, 0, st>>>(S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts));
+  if (S.lt) LAUNCH(model_cost_kernel<3, 8, 15><<<gt, 256, 0, st>>>(S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp));
+  LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(parts, gp + gt, 1, 0, S.sc + SC_MCC, 0));
   TSL_CHECK_LAUNCH();
   int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, false, jac_mode, SC_CAND, S.cr_p.p, S.cr_t.p);
   if (rc) return rc;
@@ -1056,9 +1067,9 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
 static int gradient_max_norm(Solver& S) {
   cudaStream_t st = S.ctx->stream;
   // graw (cams) is produced by schur_block_kernel and already all-reduced; landmark gradients are local
-  gmax_cams_kernel<<<grid_for(S.K, 128), 128, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.graw, S.mx.p);
-  if (S.nvp) gmax_lm_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.gp.p, S.scale_vp.p, S.mx.p);
-  if (S.nvt) gmax_lm_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p);
+  LAUNCH(gmax_cams_kernel<<<grid_for(S.K, 128), 128, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.graw, S.mx.p));
+  if (S.nvp) LAUNCH(gmax_lm_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.gp.p, S.scale_vp.p, S.mx.p));
+  if (S.nvt) LAUNCH(gmax_lm_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -1091,11 +1102,11 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
   if ((rc = accumulate_landmarks(S))) return rc;
   // x_norm
   {
-    xnorm_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.sc + SC_XNORM2, ctx->rank == 0 ? 1.0 : 0.0);
+    LAUNCH(xnorm_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.sc + SC_XNORM2, ctx->rank == 0 ? 1.0 : 0.0));
     const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
-    if (S.nvp) xnorm_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.parts.p);
-    if (S.nvt) xnorm_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.parts.p + gvp);
-    if (gvp + gvt) sum_parts_kernel<<<1, 256, 0, st>>>(S.parts.p, gvp + gvt, 1, 0, S.sc + SC_XNORM2, 1);
+    if (S.nvp) LAUNCH(xnorm_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.parts.p));
+    if (S.nvt) LAUNCH(xnorm_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.parts.p + gvp));
+    if (gvp + gvt) LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(S.parts.p, gvp + gvt, 1, 0, S.sc + SC_XNORM2, 1));
     TSL_CHECK_LAUNCH();
   }
   double x_cost = 0, fixed_cost = 0, x_norm = 0, gmax = 0;
@@ -1232,8 +1243,8 @@ extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solv
     TSL_CUDA(orho.reserve(d.n_points)); TSL_CUDA(oth.reserve(3 * (size_t)d.n_planes));
     TSL_CUDA(cudaMemsetAsync(orho.p, 0, sizeof(double) * d.n_points, st));
     TSL_CUDA(cudaMemsetAsync(oth.p, 0, sizeof(double) * 3 * (size_t)d.n_planes, st));
-    if (S->nvp) export_lm_kernel<1><<<(S->nvp + 255) / 256, 256, 0, st>>>(S->nvp, S->vp_gl.p, d.rho.p, orho.p);
-    if (S->nvt) export_lm_kernel<3><<<(3 * S->nvt + 255) / 256, 256, 0, st>>>(S->nvt, S->vt_gl.p, d.theta.p, oth.p);
+    if (S->nvp) LAUNCH(export_lm_kernel<1><<<(S->nvp + 255) / 256, 256, 0, st>>>(S->nvp, S->vp_gl.p, d.rho.p, orho.p));
+    if (S->nvt) LAUNCH(export_lm_kernel<3><<<(3 * S->nvt + 255) / 256, 256, 0, st>>>(S->nvt, S->vt_gl.p, d.theta.p, oth.p));
     if ((rc = comm_allreduce_sum(ctx, orho.p, d.n_points))) return rc;
     if ((rc = comm_allreduce_sum(ctx, oth.p, 3 * (size_t)d.n_planes))) return rc;
     std::vector<double> hr(d.n_points), ht(3 * (size_t)d.n_planes);
@@ -1256,8 +1267,8 @@ extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solv
       DevBuf<double> fr;
       TSL_CUDA(fr.reserve(total));
       TSL_CUDA(cudaMemsetAsync(fr.p, 0, total * sizeof(double), st));
-      if (S->lp) scatter_rows_kernel<<<(2 * S->lp + 255) / 256, 256, 0, st>>>(S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p);
-      if (S->lt) scatter_rows_kernel<<<(8 * S->lt + 255) / 256, 256, 0, st>>>(S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs);
+      if (S->lp) LAUNCH(scatter_rows_kernel<<<(2 * S->lp + 255) / 256, 256, 0, st>>>(S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p));
+      if (S->lt) LAUNCH(scatter_rows_kernel<<<(8 * S->lt + 255) / 256, 256, 0, st>>>(S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs));
       if ((rc = comm_allreduce_sum(ctx, fr.p, total))) return rc;
       TSL_CUDA(cudaMemcpyAsync(final_residuals, fr.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
       TSL_CUDA(cudaStreamSynchronize(st));

@@ -7,6 +7,7 @@
 namespace tsl {
 
 thread_local std::string g_last_error;
+long long g_launches = 0;
 
 int set_error(int code, const char* fmt, ...) {
   char buf[1024];
@@ -120,6 +121,7 @@ extern "C" {
 
 const char* tslam_last_error(void) { return g_last_error.c_str(); }
 int tslam_version(void) { return 100; }
+long long tslam_launch_count(void) { return g_launches; }
 
 int tslam_ctx_create(int device_id, tslam_ctx** out) {
   if (!out) return set_error(TSLAM_ERR_ARG, "out == NULL");

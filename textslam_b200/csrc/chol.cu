@@ -1,4 +1,4 @@
-// Dense FP64 Cholesky solve of the reduced camera system S y = b on one B200 (sm_100a).
+// Dense-storage, tile-sparse FP64 Cholesky solve of the reduced camera system S y = b on one B200.
 //
 // Role in the reference: the linear solve inside ceres::Solve (src/optimizer.cc:1222,1602,1840) —
 // the reference leaves Ceres' default (sparse normal Cholesky of the full system); eliminating the
@@ -11,9 +11,15 @@
 // y = L^-1 b for free (forward substitution rides along with the panel TRSM), so only the backward
 // solve L^T x = y remains.
 //
-// Per 64-wide panel j: potrf (one CTA, shared memory) -> trsm (one CTA per 64-row tile below) ->
-// syrk/gemm trailing update with FP64 tensor-core MMA (mma.sync.m8n8k4.f64; tcgen05 has no FP64
-// kind, DMMA is the FP64 tensor path on sm_100a), one CTA per 64x64 lower tile.
+// Tile sparsity: the camera graph of a SLAM map is mostly banded (co-visibility), so most 64x64
+// tiles of S and of its factor are structurally zero. The host does a symbolic factorisation on the
+// Tn x Tn tile pattern once per problem (ChoSymbolic) and every panel step only touches the listed
+// non-zero tiles; a dense pattern degenerates to the classic right-looking blocked algorithm.
+//
+// Per 64-wide panel j: potrf (one CTA, rows in registers, Crout) -> trsm (one CTA per non-zero tile
+// below) -> syrk/gemm trailing update with FP64 tensor-core MMA (mma.sync.m8n8k4.f64 — tcgen05 has
+// no FP64 kind; DMMA is the FP64 tensor path on sm_100a), one CTA per non-zero 64x64 lower tile pair.
+#include <algorithm>
 #include "ctx.cuh"
 #include "solver.cuh"
 
@@ -23,95 +29,112 @@ constexpr int NB = 64;
 constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4 fragment loads
 
 // ---------------------------------------------------------------------------------------------
-// potrf: factor the 64x64 diagonal tile in shared memory (right-looking, column by column).
+// device tile routines (potrf / trsm / invert: 64 threads; gemm: 128 threads)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) potrf_tile_kernel(double* __restrict__ A, int ld, int j, int* __restrict__ fail) {
-  __shared__ double s[NB][NB + 1];
-  double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    s[r][c] = (c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
-  }
-  __syncthreads();
+
+// Crout Cholesky of a 64x64 tile: thread r (< 64) owns row r in registers; finished rows are
+// published to shared memory so that the dot products read row c as a broadcast.
+// sinv[c] = 1 / L[c][c] (kept for the TRSM / inverse so that no FP64 division sits on a critical path).
+__device__ __forceinline__ void potrf_tile(const double* __restrict__ Ajj, int ld, double* __restrict__ dst /*64x64 tight or null*/,
+                                           double (*sL)[NB + 1], double* sinv, int* fail) {
+  const int r = threadIdx.x;
+  double row[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) row[c] = (r < NB && c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
+#pragma unroll
   for (int c = 0; c < NB; ++c) {
-    const double piv = s[c][c];
-    if (!(piv > 0.0)) {  // not positive definite (or NaN): report and keep going with a harmless pivot
-      if (threadIdx.x == 0) atomicExch(fail, 1);
-    }
-    const double d = (piv > 0.0) ? sqrt(piv) : 1.0;
-    __syncthreads();
-    const double inv = 1.0 / d;
-    for (int r = c + threadIdx.x; r < NB; r += 256) s[r][c] = (r == c) ? d : s[r][c] * inv;
-    __syncthreads();
-    // trailing update: s[r][k] -= s[r][c]*s[k][c] for c < k <= r
-    const int m = NB - 1 - c;  // trailing dimension
-    for (int e = threadIdx.x; e < m * m; e += 256) {
-      const int rr = e / m, kk = e - rr * m;
-      if (kk <= rr) {
-        const int r = c + 1 + rr, k = c + 1 + kk;
-        s[r][k] -= s[r][c] * s[k][c];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (r < NB && r >= c) {
+#pragma unroll
+      for (int k = 0; k + 3 < c; k += 4) {
+        s0 += row[k] * sL[c][k]; s1 += row[k + 1] * sL[c][k + 1];
+        s2 += row[k + 2] * sL[c][k + 2]; s3 += row[k + 3] * sL[c][k + 3];
       }
+#pragma unroll
+      for (int k = c & ~3; k < c; ++k) s0 += row[k] * sL[c][k];
+    }
+    const double s = row[c] - ((s0 + s1) + (s2 + s3));
+    if (r == c) {
+      if (!(s > 0.0)) atomicExch(fail, 1);  // not positive definite (or NaN): report, continue with a harmless pivot
+      sinv[c] = (s > 0.0) ? rsqrt(s) : 1.0;
+    }
+    __syncthreads();
+    if (r < NB && r >= c) {
+      const double inv = sinv[c];
+      row[c] = s * inv;   // diagonal: s * rsqrt(s) = sqrt(s)
+      sL[r][c] = row[c];
     }
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    if (c <= r) Ajj[(size_t)r * ld + c] = s[r][c];
+  if (dst && r < NB) {
+#pragma unroll
+    for (int c = 0; c < NB; ++c) dst[r * NB + c] = (c <= r) ? row[c] : 0.0;
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// trsm: X L_jj^T = A_ij for every 64-row tile i > j (one thread per row, x kept in registers).
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB) trsm_tile_kernel(double* __restrict__ A, int ld, int j, int rows_valid_last) {
-  __shared__ double sL[NB][NB + 1];
-  const double* Ljj = A + (size_t)j * NB * ld + (size_t)j * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += NB) {
+// X L^T = A for one 64-row tile; sL holds L (lower, row-major). Thread r < 64 owns one row.
+__device__ __forceinline__ void trsm_tile(double* __restrict__ Aij, int ld, const double (*sL)[NB + 1], const double* sinv) {
+  const int r = threadIdx.x;
+  if (r >= NB) return;
+  double* rowp = Aij + (size_t)r * ld;
+  double x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(rowp + c); x[c] = v.x; x[c + 1] = v.y; }
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < c; k += 4) {
+      s0 += x[k] * sL[c][k]; s1 += x[k + 1] * sL[c][k + 1];
+      s2 += x[k + 2] * sL[c][k + 2]; s3 += x[k + 3] * sL[c][k + 3];
+    }
+#pragma unroll
+    for (int k = c & ~3; k < c; ++k) s0 += x[k] * sL[c][k];
+    x[c] = (x[c] - ((s0 + s1) + (s2 + s3))) * sinv[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(rowp + c) = make_double2(x[c], x[c + 1]);
+}
+
+// L^-1 tile: thread c (< 64) solves L z = e_c and stores column c: dst[r*64 + c] = (L^-1)[r][c]
+__device__ __forceinline__ void invert_tile(const double (*sL)[NB + 1], const double* sinv, double* __restrict__ dst) {
+  const int c = threadIdx.x;
+  if (c >= NB) return;
+  double z[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < r; k += 4) {
+      s0 += sL[r][k] * z[k]; s1 += sL[r][k + 1] * z[k + 1];
+      s2 += sL[r][k + 2] * z[k + 2]; s3 += sL[r][k + 3] * z[k + 3];
+    }
+#pragma unroll
+    for (int k = r & ~3; k < r; ++k) s0 += sL[r][k] * z[k];
+    // rows above the unit entry are exactly zero (z_k = 0 for k < c), so the sums vanish there
+    z[r] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - ((s0 + s1) + (s2 + s3))) * sinv[r];
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) dst[r * NB + c] = z[r];  // plain L^-1, row-major: coalesced over threads
+}
+
+__device__ __forceinline__ void load_L_tile(const double* __restrict__ Ljj, int ld, double (*sL)[NB + 1]) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
     const int r = e >> 6, c = e & 63;
     sL[r][c] = (c <= r) ? Ljj[(size_t)r * ld + c] : 0.0;
   }
-  __syncthreads();
-  const int i = j + 1 + blockIdx.x;
-  double* row = A + ((size_t)i * NB + threadIdx.x) * ld + (size_t)j * NB;
-  double x[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) x[c] = row[c];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    double s = x[c];
-#pragma unroll
-    for (int k = 0; k < c; ++k) s -= x[k] * sL[c][k];
-    x[c] = s / sL[c][c];
-  }
-#pragma unroll
-  for (int c = 0; c < NB; ++c) row[c] = x[c];
 }
 
-// ---------------------------------------------------------------------------------------------
-// syrk / gemm trailing update with DMMA: A_ik -= X_i X_k^T for j < k <= i.
-// CTA = 4 warps (2x2), warp tile 32x32 = 4x4 m8n8k4 tiles.
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) syrk_tile_kernel(double* __restrict__ A, int ld, int j, int nt /*tiles below j*/, int skip_last_diag) {
-  extern __shared__ double smem[];
-  double* sA = smem;               // X_i  [64][SPAD]
-  double* sB = smem + NB * SPAD;   // X_k  [64][SPAD]
-  // decode lower-triangular tile index -> (ti >= tk)
-  int t = blockIdx.x;
-  int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-  while (ti * (ti + 1) / 2 > t) --ti;
-  const int tk = t - ti * (ti + 1) / 2;
-  if (skip_last_diag && ti == nt - 1 && tk == nt - 1) return;  // (b-row, b-row) tile is never read
-  const int gi = j + 1 + ti, gk = j + 1 + tk;
-  const double* Xi = A + (size_t)gi * NB * ld + (size_t)j * NB;
-  const double* Xk = A + (size_t)gk * NB * ld + (size_t)j * NB;
-  for (int e = threadIdx.x; e < NB * NB / 2; e += 128) {  // double2 loads
+// C (64x64 at C, ld) -= Xi Xk^T with Xi, Xk 64x64 tiles (ld). 4 warps (2x2), warp tile 32x32.
+__device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, const double* __restrict__ Xk, double* __restrict__ C, int ld,
+                                             double* sA, double* sB) {
+  for (int e = threadIdx.x; e < NB * NB / 2; e += 128) {
     const int r = e >> 5, c2 = (e & 31) * 2;
     const double2 va = *reinterpret_cast<const double2*>(Xi + (size_t)r * ld + c2);
     const double2 vb = *reinterpret_cast<const double2*>(Xk + (size_t)r * ld + c2);
@@ -139,7 +162,6 @@ __global__ void __launch_bounds__(128) syrk_tile_kernel(double* __restrict__ A, 
 #pragma unroll
       for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
   }
-  double* C = A + (size_t)gi * NB * ld + (size_t)gk * NB;
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -153,44 +175,77 @@ __global__ void __launch_bounds__(128) syrk_tile_kernel(double* __restrict__ A, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward solve L^T x = y, right-looking over panels j = Tn-1 .. 0. y lives in `x` (in/out).
-// CTA k < j: t = L_jk^T x_j ; y_k -= t.  Every CTA first solves L_jj^T x_j = y_j redundantly;
-// CTA 0 (or the only CTA when j == 0) publishes x_j.
+// kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NB) backsolve_panel_kernel(const double* __restrict__ A, int ld, int j, double* __restrict__ x,
-                                                             double* __restrict__ xout) {
+// potrf of the diagonal tile fused with the TRSM of the non-zero tiles below it: every CTA factors
+// the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
+// this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
+// m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
+__global__ void __launch_bounds__(NB) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
+                                                        int* __restrict__ fail, double* __restrict__ LinvT) {
   __shared__ double sL[NB][NB + 1];
-  __shared__ double sx[NB];
-  const double* Ljj = A + (size_t)j * NB * ld + (size_t)j * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += NB) {
-    const int r = e >> 6, c = e & 63;
-    sL[r][c] = (c <= r) ? Ljj[(size_t)r * ld + c] : 0.0;
+  __shared__ double sinv[NB];
+  const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
+  potrf_tile(Ajj, ld, nullptr, sL, sinv, fail);
+  if (blockIdx.x == 0) {  // off the critical path: (L_jj^-1)^T for the backward solve
+    invert_tile(sL, sinv, LinvT + (size_t)j * NB * NB);
+    return;
   }
-  sx[threadIdx.x] = x[j * NB + threadIdx.x];
-  __syncthreads();
-  // column-oriented back substitution: x_c = y_c / L_cc ; y_r -= L_cr x_c (r < c)
-  for (int c = NB - 1; c >= 0; --c) {
-    if (threadIdx.x == c) sx[c] = sx[c] / sL[c][c];
-    __syncthreads();
-    if (threadIdx.x < c) sx[threadIdx.x] -= sL[c][threadIdx.x] * sx[c];
-    __syncthreads();
-  }
-  const int k = (int)blockIdx.x - 1;  // block 0 publishes x_j, blocks 1..j update y_{k}
-  if (k < 0) { xout[j * NB + threadIdx.x] = sx[threadIdx.x]; return; }
-  // t[col] = sum_r L_jk[r][col] * x_j[r]; thread = col -> coalesced row reads
-  const double* Ljk = A + (size_t)j * NB * ld + (size_t)k * NB;
-  double t = 0.0;
-#pragma unroll 8
-  for (int r = 0; r < NB; ++r) t += Ljk[(size_t)r * ld + threadIdx.x] * sx[r];
-  x[k * NB + threadIdx.x] -= t;
+  const int i = rows[blockIdx.x - 1];
+  trsm_tile(A + (size_t)i * NB * ld + (size_t)j * NB, ld, sL, sinv);
 }
 
-// gather y from the b row, scatter of x back handled by caller
+// trailing update: for each listed pair (i,k), i >= k > j: A_ik -= X_i X_k^T
+__global__ void __launch_bounds__(128) syrk_pairs_kernel(double* __restrict__ A, int ld, int j, const int2* __restrict__ pairs) {
+  extern __shared__ double smem[];
+  const int2 pr = pairs[blockIdx.x];
+  gemm_tile_nt(A + (size_t)pr.x * NB * ld + (size_t)j * NB, A + (size_t)pr.y * NB * ld + (size_t)j * NB,
+               A + (size_t)pr.x * NB * ld + (size_t)pr.y * NB, ld, smem, smem + NB * SPAD);
+}
+
+// backward solve L^T x = y, right-looking over panels j = Tn-1 .. 0. y lives in `x` (in/out).
+// x_j = L_jj^-T y_j is a 64x64 mat-vec with the stored (L_jj^-1)^T (no substitution chain); CTA 0
+// publishes x_j, CTA 1+m applies y_k -= L_jk^T x_j for the m-th non-zero tile (j,k), k < j.
+__global__ void __launch_bounds__(NB) backsolve_panel_kernel(const double* __restrict__ A, int ld, int j, const int* __restrict__ cols,
+                                                             const double* __restrict__ LinvT, double* __restrict__ x,
+                                                             double* __restrict__ xout) {
+  __shared__ double sy[NB];
+  __shared__ double sx[NB];
+  sy[threadIdx.x] = x[j * NB + threadIdx.x];
+  __syncthreads();
+  {
+    // x_c = sum_r (L^-1)[r][c] y_r : thread c walks column c, rows are contiguous across threads (coalesced)
+    const double* M = LinvT + (size_t)j * NB * NB;
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < NB; r += 2) {
+      t0 += M[r * NB + threadIdx.x] * sy[r];
+      t1 += M[(r + 1) * NB + threadIdx.x] * sy[r + 1];
+    }
+    sx[threadIdx.x] = t0 + t1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) { xout[j * NB + threadIdx.x] = sx[threadIdx.x]; return; }
+  const int k = cols[blockIdx.x - 1];
+  // t[col] = sum_r L_jk[r][col] * x_j[r]; thread = col -> coalesced row reads
+  const double* Ljk = A + (size_t)j * NB * ld + (size_t)k * NB;
+  double t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+  for (int r = 0; r < NB; r += 2) {
+    t0 += Ljk[(size_t)r * ld + threadIdx.x] * sx[r];
+    t1 += Ljk[(size_t)(r + 1) * ld + threadIdx.x] * sx[r + 1];
+  }
+  x[k * NB + threadIdx.x] -= t0 + t1;
+}
+
 __global__ void copy_row_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// host: symbolic tile factorisation + launch sequence
+// ---------------------------------------------------------------------------------------------
 int chol_workspace_dims(int n, int* ld, int* rows) {
   const int Tn = (n + NB - 1) / NB;
   *ld = Tn * NB;
@@ -198,26 +253,74 @@ int chol_workspace_dims(int n, int* ld, int* rows) {
   return Tn;
 }
 
-// Factor + solve. A: (Tn+1)*64 x ld as described above. ywork: ld doubles scratch. xout: ld doubles.
-int chol_solve(tslam_ctx* ctx, double* A, int n, double* ywork, double* xout, int* d_fail) {
+// tile_nz: Tn x Tn row-major flags of the lower-triangular tile pattern of S (diagonal always set).
+int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, CholSymbolic* sym) {
   int ld, rows;
   const int Tn = chol_workspace_dims(n, &ld, &rows);
+  sym->Tn = Tn; sym->n = n;
+  const int T1 = Tn + 1;  // + the b tile row (dense)
+  std::vector<uint8_t> P((size_t)T1 * T1, 0);
+  for (int i = 0; i < Tn; ++i)
+    for (int k = 0; k <= i; ++k) P[(size_t)i * T1 + k] = (i == k) || tile_nz[(size_t)i * Tn + k];
+  for (int k = 0; k < Tn; ++k) P[(size_t)Tn * T1 + k] = 1;
+  std::vector<int> rows_h, rows_ptr(Tn + 1, 0), cols_h, cols_ptr(Tn + 1, 0), pairs_ptr(Tn + 1, 0);
+  std::vector<int2> pairs_h;
+  std::vector<int> nzrows;
+  long long flop_tiles = 0;
+  for (int j = 0; j < Tn; ++j) {
+    nzrows.clear();
+    for (int i = j + 1; i < T1; ++i) if (P[(size_t)i * T1 + j]) nzrows.push_back(i);
+    for (int i : nzrows) rows_h.push_back(i);
+    rows_ptr[j + 1] = (int)rows_h.size();
+    for (size_t a = 0; a < nzrows.size(); ++a)
+      for (size_t b = 0; b <= a; ++b) {
+        const int i = nzrows[a], k = nzrows[b];
+        if (i == Tn && k == Tn) continue;  // (b row, b row) is never read
+        P[(size_t)i * T1 + k] = 1;         // fill
+        pairs_h.push_back(make_int2(i, k));
+      }
+    pairs_ptr[j + 1] = (int)pairs_h.size();
+    flop_tiles += (long long)(pairs_ptr[j + 1] - pairs_ptr[j]);
+  }
+  // backward solve: for panel j the non-zero tiles (j,k), k < j of the FACTOR
+  for (int j = 0; j < Tn; ++j) {
+    for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) cols_h.push_back(k);
+    cols_ptr[j + 1] = (int)cols_h.size();
+  }
+  sym->rows_ptr = rows_ptr; sym->pairs_ptr = pairs_ptr; sym->cols_ptr = cols_ptr;
+  sym->gemm_tiles = flop_tiles;
+  cudaStream_t s = ctx->stream;
+  TSL_CUDA(sym->rows.upload(rows_h.data(), rows_h.size(), s));
+  TSL_CUDA(sym->pairs.upload(pairs_h.data(), pairs_h.size(), s));
+  TSL_CUDA(sym->cols.upload(cols_h.data(), cols_h.size(), s));
+  TSL_CUDA(sym->Ldiag.reserve((size_t)(Tn ? Tn : 1) * NB * NB));
+  TSL_CUDA(cudaStreamSynchronize(s));
+  return TSLAM_OK;
+}
+
+// Factor + solve. A: (Tn+1)*64 x ld as described above. ywork: ld doubles scratch. xout: ld doubles.
+int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail) {
+  int ld, rows;
+  const int Tn = chol_workspace_dims(sym.n, &ld, &rows);
   static bool attr_set = false;
   const int smem = 2 * NB * SPAD * (int)sizeof(double);
   if (!attr_set) {
-    TSL_CUDA(cudaFuncSetAttribute(syrk_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TSL_CUDA(cudaFuncSetAttribute(syrk_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   cudaStream_t s = ctx->stream;
   for (int j = 0; j < Tn; ++j) {
-    potrf_tile_kernel<<<1, 256, 0, s>>>(A, ld, j, d_fail);
-    const int nt = Tn - j;  // row tiles below the diagonal one, including the b tile row
-    trsm_tile_kernel<<<nt, NB, 0, s>>>(A, ld, j, 0);
-    if (nt > 0) syrk_tile_kernel<<<nt * (nt + 1) / 2, 128, smem, s>>>(A, ld, j, nt, 1);
+    const int nrows = sym.rows_ptr[j + 1] - sym.rows_ptr[j];
+    const int npairs = sym.pairs_ptr[j + 1] - sym.pairs_ptr[j];
+    LAUNCH(potrf_trsm_kernel<<<1 + nrows, NB, 0, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
+    if (npairs > 0) LAUNCH(syrk_pairs_kernel<<<npairs, 128, smem, s>>>(A, ld, j, sym.pairs.p + sym.pairs_ptr[j]));
   }
   TSL_CHECK_LAUNCH();
-  copy_row_kernel<<<(ld + 255) / 256, 256, 0, s>>>(A + (size_t)Tn * NB * ld, ywork, ld);
-  for (int j = Tn - 1; j >= 0; --j) backsolve_panel_kernel<<<j + 1, NB, 0, s>>>(A, ld, j, ywork, xout);
+  LAUNCH(copy_row_kernel<<<(ld + 255) / 256, 256, 0, s>>>(A + (size_t)Tn * NB * ld, ywork, ld));
+  for (int j = Tn - 1; j >= 0; --j) {
+    const int ncols = sym.cols_ptr[j + 1] - sym.cols_ptr[j];
+    LAUNCH(backsolve_panel_kernel<<<1 + ncols, NB, 0, s>>>(A, ld, j, sym.cols.p + sym.cols_ptr[j], sym.Ldiag.p, ywork, xout));
+  }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }

@@ -10,6 +10,7 @@
 namespace tsl {
 
 extern thread_local std::string g_last_error;
+extern long long g_launches;
 int set_error(int code, const char* fmt, ...);
 
 #define TSL_CUDA(expr)                                                                                   \
@@ -18,6 +19,8 @@ int set_error(int code, const char* fmt, ...);
     if (_e != cudaSuccess) return tsl::set_error(TSLAM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
   } while (0)
 #define TSL_CHECK_LAUNCH() TSL_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through LAUNCH so that bench.py can report gpu_launches
+#define LAUNCH(...) do { ++tsl::g_launches; __VA_ARGS__; } while (0)
 
 template <typename T>
 struct DevBuf {  // simple RAII device buffer (grow-only)

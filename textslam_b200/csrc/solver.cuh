@@ -5,8 +5,17 @@
 namespace tsl {
 
 // chol.cu
+struct CholSymbolic {  // tile-level symbolic factorisation (per problem structure)
+  int Tn = 0, n = 0;
+  std::vector<int> rows_ptr, pairs_ptr, cols_ptr;  // per panel ranges into the device lists
+  DevBuf<int> rows, cols;
+  DevBuf<int2> pairs;
+  mutable DevBuf<double> Ldiag;                    // Tn factored diagonal tiles (64x64, tight)
+  long long gemm_tiles = 0;                        // number of 64x64x64 tile updates (2*64^3 flop each)
+};
 int chol_workspace_dims(int n, int* ld, int* rows);
-int chol_solve(tslam_ctx* ctx, double* A, int n, double* ywork, double* xout, int* d_fail);
+int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, CholSymbolic* sym);
+int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail);
 
 // ba_eval.cu (robustified evaluation used inside the LM loop)
 int launch_eval_points_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double* cams, const double* rho, const uint8_t* active,
