@@ -189,6 +189,9 @@ int tslam_orb_extract(tslam_orb* h, const uint8_t* const* imgs, int n_imgs, int 
  * last extract call (without border) into out (level_w x level_h, tight). */
 int tslam_orb_level_size(tslam_orb* h, int level, int* w, int* hgt);
 int tslam_orb_get_level(tslam_orb* h, int img, int level, uint8_t* out);
+/* Parity-test hook: read back an intermediate stage of the last extract call (0 FAST measure plane, 1 candidates
+ * of a level in vToDistributeKeys order, 2 quad-tree winners of a level; int32 count followed by (x,y,response) triplets). */
+int tslam_orb_debug_get(tslam_orb* h, int what, int img, int level, void* out, int out_bytes);
 /* Benchmark hook: images already resident in HBM; runs the full extractor `reps` times and returns
  * the mean ms per batch (CUDA events) and the total keypoints of the last batch. */
 int tslam_orb_dev_bench(tslam_orb* h, const uint8_t* const* imgs, int n_imgs, int w, int hgt, int stride,

@@ -12,8 +12,9 @@
 //  * DistributeOctTree sorts (size, node*) pairs (ORBextractor.cc:685): ties depend on heap addresses.
 //    Here ties are broken by node creation order (later-created node first), which is what a fresh
 //    heap gives; the GPU implementation uses the same rule.
-//  * cos/sin of the keypoint angle (ORBextractor.cc:112-113) are evaluated in double and rounded to
-//    float instead of calling the host libm's cosf/sinf.
+//  * cos/sin of the keypoint angle (ORBextractor.cc:112-113) are evaluated by a fixed double-precision
+//    operation sequence (textslam_b200/csrc/orb_math.h, shared with the GPU) and rounded to float
+//    instead of calling the host libm's cosf/sinf.
 //  * GaussianBlur taps: variant 0 = OpenCV >= 3.4 / 4.x fixed-point taps {18,34,48,56,48,34,18}/256
 //    (the only variant checkable here), variant 1 = OpenCV 3.3.1's round(k*256) taps {18,34,49,55,49,34,18}
 //    as recalled in SURVEY Appendix C (unverifiable here).
@@ -25,6 +26,7 @@
 #include <list>
 #include <algorithm>
 #include "../include/tslam_b200.h"
+#include "../textslam_b200/csrc/orb_math.h"
 
 namespace tso {
 
@@ -295,7 +297,9 @@ struct Extractor {
   void descriptor(const Img& im, float px, float py, float angle_deg, uint8_t* desc) const {  // ORBextractor.cc:108-147
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float angle = angle_deg * factorPI;
-    const float a = (float)std::cos((double)angle), b = (float)std::sin((double)angle);
+    double sd, cd;
+    tsl_det_sincos((double)angle, &sd, &cd);   // see orb_math.h (deviation from the host-libm cosf/sinf, documented above)
+    const float a = (float)cd, b = (float)sd;
     const uint8_t* center = im.row(cv_round(py)) + cv_round(px);
     const int step = im.w;
     const int8_t* pat = kPattern;
@@ -310,11 +314,14 @@ struct Extractor {
       desc[i] = (uint8_t)val;
     }
   }
+  std::vector<std::vector<DKey>> dbg_cand;
+  std::vector<std::vector<int>> dbg_sel;
   // ORBextractor.cc:766-854 + :1054-1116
   int extract(const uint8_t* img, int w, int h, int stride, int max_kp, tslam_keypoint* kp_out, uint8_t* desc_out) {
     compute_pyramid(img, w, h, stride);
     int total = 0;
     const float W = 30;
+    dbg_cand.assign(nlevels, {}); dbg_sel.assign(nlevels, {});
     for (int level = 0; level < nlevels; ++level) {
       const Img& im = pyr[level];
       const int minBX = EDGE_THRESHOLD - 3, minBY = minBX, maxBX = im.w - EDGE_THRESHOLD + 3, maxBY = im.h - EDGE_THRESHOLD + 3;
@@ -339,6 +346,7 @@ struct Extractor {
       std::vector<int> sel;
       if (!cand.empty()) sel = distribute_octtree(cand, minBX, maxBX, minBY, maxBY, perLevel[level]);
       const int scaledPatch = (int)(PATCH_SIZE * mvScale[level]);
+      dbg_cand[level] = cand; dbg_sel[level] = sel;
       if (sel.empty()) continue;
       Img blurred(im.w, im.h);
       gaussian7(im, blurred, blur_variant);
@@ -400,4 +408,37 @@ int tso_fast(const uint8_t* img, int w, int h, int threshold, int max_kp, int* x
 }
 float tso_fast_atan2(float y, float x) { return fast_atan2(y, x); }
 int tso_cv_round(double v) { return cv_round(v); }
+}
+
+extern "C" void tso_det_sincos(double x, double* s, double* c) { tsl_det_sincos(x, s, c); }
+
+// stage-by-stage read-back for the GPU parity tests: what = 0 FAST measure plane (max(m,0), 0 where m <= min_th),
+// 1 candidates of a level (vToDistributeKeys order), 2 quad-tree winners (list order). Returns the count.
+extern "C" int tso_orb_debug(const uint8_t* img, int w, int h, int nfeatures, float scale, int nlevels, int iniTh, int minTh, int what, int level,
+                             void* out, int max_items) {
+  Extractor E(nfeatures, scale, nlevels, iniTh, minTh, 0);
+  if (what == 0) {
+    E.compute_pyramid(img, w, h, w);
+    const Img& im = E.pyr[level];
+    uint8_t* o = (uint8_t*)out;
+    for (int y = 0; y < im.h; ++y) for (int x = 0; x < im.w; ++x) {
+      int m = 0;
+      if (x >= 3 && x < im.w - 3 && y >= 3 && y < im.h - 3) { m = fast_measure(im.row(y) + x, im.w); if (m <= minTh) m = 0; }
+      o[(size_t)y * im.w + x] = (uint8_t)std::min(255, std::max(0, m));
+    }
+    return im.w * im.h;
+  }
+  std::vector<tslam_keypoint> kp(nfeatures + 4 * nlevels + 64); std::vector<uint8_t> desc(kp.size() * 32);
+  E.extract(img, w, h, w, (int)kp.size(), kp.data(), desc.data());
+  int* o = (int*)out;
+  if (what == 1) {
+    const auto& c = E.dbg_cand[level];
+    const int n = std::min((int)c.size(), max_items);
+    for (int i = 0; i < n; ++i) { o[3 * i] = (int)c[i].x; o[3 * i + 1] = (int)c[i].y; o[3 * i + 2] = c[i].resp; }
+    return (int)c.size();
+  }
+  const auto& c = E.dbg_cand[level]; const auto& sl = E.dbg_sel[level];
+  const int n = std::min((int)sl.size(), max_items);
+  for (int i = 0; i < n; ++i) { o[3 * i] = (int)c[sl[i]].x; o[3 * i + 1] = (int)c[sl[i]].y; o[3 * i + 2] = c[sl[i]].resp; }
+  return (int)sl.size();
 }

@@ -141,3 +141,19 @@ def fast_atan2(y, x):
     f = lib().tso_fast_atan2
     f.restype = C.c_float
     return f(C.c_float(y), C.c_float(x))
+
+
+def orb_debug(img, what, level, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+    """Intermediate stages of the oracle extractor: 0 FAST measure plane, 1 candidates, 2 quad-tree winners."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    if what == 0:
+        lw, lh = orb_level_size(w, h, scale, nlevels, level)
+        out = np.zeros((lh, lw), dtype=np.uint8)
+        lib().tso_orb_debug(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(nfeatures), C.c_float(scale), C.c_int(nlevels),
+                            C.c_int(ini_th), C.c_int(min_th), C.c_int(0), C.c_int(level), out.ctypes.data_as(C.c_void_p), C.c_int(out.size))
+        return out
+    buf = np.zeros((140000, 3), dtype=np.int32)
+    n = lib().tso_orb_debug(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(nfeatures), C.c_float(scale), C.c_int(nlevels),
+                            C.c_int(ini_th), C.c_int(min_th), C.c_int(what), C.c_int(level), buf.ctypes.data_as(C.c_void_p), C.c_int(len(buf)))
+    return buf[:n].copy()

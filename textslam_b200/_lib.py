@@ -16,7 +16,7 @@ EXPORTS = [
     "tslam_ctx_init_comm", "tslam_eval_points", "tslam_eval_text", "tslam_solve", "tslam_dev_upload", "tslam_dev_free",
     "tslam_dev_eval_points", "tslam_dev_eval_text", "tslam_dev_lm_iterations", "tslam_dev_download_eval",
     "tslam_dev_download_params", "tslam_orb_create", "tslam_orb_destroy", "tslam_orb_extract", "tslam_orb_level_size",
-    "tslam_orb_get_level", "tslam_orb_dev_bench",
+    "tslam_orb_get_level", "tslam_orb_dev_bench", "tslam_orb_debug_get",
 ]
 
 

@@ -202,6 +202,17 @@ class ORBextractor:
         check(lib().tslam_orb_get_level(self._h, C.c_int(img), C.c_int(level), out.ctypes.data_as(c_bp)))
         return out
 
+    def debug_get(self, what, img, level):
+        """Intermediate stages of the last extract call (parity tests): 0 measure plane, 1 candidates, 2 winners."""
+        if what == 0:
+            w, h = self.level_size(level)
+            out = np.zeros((h, w), dtype=np.uint8)
+            check(lib().tslam_orb_debug_get(self._h, C.c_int(0), C.c_int(img), C.c_int(level), out.ctypes.data_as(C.c_void_p), C.c_int(out.nbytes)))
+            return out
+        buf = np.zeros(1 + 3 * 140000, dtype=np.int32)
+        check(lib().tslam_orb_debug_get(self._h, C.c_int(what), C.c_int(img), C.c_int(level), buf.ctypes.data_as(C.c_void_p), C.c_int(buf.nbytes)))
+        return buf[1:1 + 3 * buf[0]].reshape(-1, 3).copy()
+
     def dev_bench(self, imgs, reps=5):
         imgs, ptrs, n, h, w = self._ptrs(imgs)
         ms = C.c_float(); nk = C.c_int64()
