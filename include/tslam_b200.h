@@ -131,6 +131,9 @@ void tslam_ctx_destroy(tslam_ctx* ctx);
  * ncclUniqueId produced by tslam_nccl_unique_id() on rank 0 and broadcast by the host program
  * (torch.distributed / MPI / sockets). */
 int tslam_nccl_unique_id(uint8_t id_out[128]);
+/* The sharding rule: rank that owns an observation. An observation lives with its landmark when the
+ * landmark is free; observations of constant landmarks are dealt round-robin. Pure function, no GPU needed. */
+int tslam_shard_owner(int landmark_is_free, int landmark_index, int obs_index, int world);
 int tslam_ctx_init_comm(tslam_ctx* ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
 
 /* ---- residual + Jacobian evaluation (the metric kernel) --------------------------------------- */

@@ -13,7 +13,7 @@ _LIB = None
 # every symbol include/tslam_b200.h declares
 EXPORTS = [
     "tslam_last_error", "tslam_version", "tslam_launch_count", "tslam_ctx_create", "tslam_ctx_destroy", "tslam_nccl_unique_id",
-    "tslam_ctx_init_comm", "tslam_eval_points", "tslam_eval_text", "tslam_solve", "tslam_dev_upload", "tslam_dev_free",
+    "tslam_ctx_init_comm", "tslam_shard_owner", "tslam_eval_points", "tslam_eval_text", "tslam_solve", "tslam_dev_upload", "tslam_dev_free",
     "tslam_dev_eval_points", "tslam_dev_eval_text", "tslam_dev_lm_iterations", "tslam_dev_download_eval",
     "tslam_dev_download_params", "tslam_orb_create", "tslam_orb_destroy", "tslam_orb_extract", "tslam_orb_level_size",
     "tslam_orb_get_level", "tslam_orb_dev_bench", "tslam_orb_debug_get",

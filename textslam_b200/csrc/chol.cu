@@ -32,90 +32,70 @@ constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4
 // device tile routines (potrf / trsm / invert: 64 threads; gemm: 128 threads)
 // ---------------------------------------------------------------------------------------------
 
-// Crout Cholesky of a 64x64 tile: thread r (< 64) owns row r in registers; finished rows are
-// published to shared memory so that the dot products read row c as a broadcast.
-// sinv[c] = 1 / L[c][c] (kept for the TRSM / inverse so that no FP64 division sits on a critical path).
-__device__ __forceinline__ void potrf_tile(const double* __restrict__ Ajj, int ld, double* __restrict__ dst /*64x64 tight or null*/,
-                                           double (*sL)[NB + 1], double* sinv, int* fail) {
-  const int r = threadIdx.x;
-  double row[NB];
-#pragma unroll
-  for (int c = 0; c < NB; ++c) row[c] = (r < NB && c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
-#pragma unroll
+// All three 64x64 tile routines below run on 128 threads (two lanes of one warp per row / column) with the
+// tile in shared memory and short loops: a fully unrolled register version (2016 FMAs of straight-line code
+// per routine) measured 64 us per launch because it does not fit the instruction cache (profiles/r1).
+constexpr int LDT = NB + 1;  // smem leading dimension (doubles)
+
+// Crout Cholesky in place on sT (lower triangle). sinv[c] = 1 / L[c][c] so that no FP64 division sits on the
+// critical path of the TRSM / inverse.
+__device__ __forceinline__ void potrf_tile(double* sT, double* sinv, int* fail) {
+  const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
   for (int c = 0; c < NB; ++c) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (r < NB && r >= c) {
-#pragma unroll
-      for (int k = 0; k + 3 < c; k += 4) {
-        s0 += row[k] * sL[c][k]; s1 += row[k + 1] * sL[c][k + 1];
-        s2 += row[k + 2] * sL[c][k + 2]; s3 += row[k + 3] * sL[c][k + 3];
-      }
-#pragma unroll
-      for (int k = c & ~3; k < c; ++k) s0 += row[k] * sL[c][k];
+    double s0 = 0.0, s1 = 0.0;
+    if (r >= c) {
+      const double* a = sT + r * LDT; const double* b = sT + c * LDT;
+      int k = h;
+      for (; k + 2 < c; k += 4) { s0 += a[k] * b[k]; s1 += a[k + 2] * b[k + 2]; }
+      for (; k < c; k += 2) s0 += a[k] * b[k];
     }
-    const double s = row[c] - ((s0 + s1) + (s2 + s3));
-    if (r == c) {
-      if (!(s > 0.0)) atomicExch(fail, 1);  // not positive definite (or NaN): report, continue with a harmless pivot
-      sinv[c] = (s > 0.0) ? rsqrt(s) : 1.0;
-    }
-    __syncthreads();
-    if (r < NB && r >= c) {
-      const double inv = sinv[c];
-      row[c] = s * inv;   // diagonal: s * rsqrt(s) = sqrt(s)
-      sL[r][c] = row[c];
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const double val = sT[r * LDT + c] - s;
+    if (h == 0 && r == c) {
+      if (!(val > 0.0)) atomicExch(fail, 1);  // not positive definite (or NaN): report, continue with a harmless pivot
+      sinv[c] = (val > 0.0) ? rsqrt(val) : 1.0;
     }
     __syncthreads();
-  }
-  if (dst && r < NB) {
-#pragma unroll
-    for (int c = 0; c < NB; ++c) dst[r * NB + c] = (c <= r) ? row[c] : 0.0;
+    if (h == 0 && r >= c) sT[r * LDT + c] = val * sinv[c];   // diagonal: val * rsqrt(val) = sqrt(val)
+    __syncthreads();
   }
 }
 
-// X L^T = A for one 64-row tile; sL holds L (lower, row-major). Thread r < 64 owns one row.
-__device__ __forceinline__ void trsm_tile(double* __restrict__ Aij, int ld, const double (*sL)[NB + 1], const double* sinv) {
-  const int r = threadIdx.x;
-  if (r >= NB) return;
-  double* rowp = Aij + (size_t)r * ld;
-  double x[NB];
-#pragma unroll
-  for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(rowp + c); x[c] = v.x; x[c + 1] = v.y; }
-#pragma unroll
+// X L^T = A for one 64-row tile held in sX (in place). Rows are independent: lane pairs only need __syncwarp.
+__device__ __forceinline__ void trsm_tile(double* sX, const double* sT, const double* sinv) {
+  const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+  double* x = sX + r * LDT;
   for (int c = 0; c < NB; ++c) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int k = 0; k + 3 < c; k += 4) {
-      s0 += x[k] * sL[c][k]; s1 += x[k + 1] * sL[c][k + 1];
-      s2 += x[k + 2] * sL[c][k + 2]; s3 += x[k + 3] * sL[c][k + 3];
-    }
-#pragma unroll
-    for (int k = c & ~3; k < c; ++k) s0 += x[k] * sL[c][k];
-    x[c] = (x[c] - ((s0 + s1) + (s2 + s3))) * sinv[c];
+    const double* b = sT + c * LDT;
+    double s0 = 0.0, s1 = 0.0;
+    int k = h;
+    for (; k + 2 < c; k += 4) { s0 += x[k] * b[k]; s1 += x[k + 2] * b[k + 2]; }
+    for (; k < c; k += 2) s0 += x[k] * b[k];
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (h == 0) x[c] = (x[c] - s) * sinv[c];
+    __syncwarp();
   }
-#pragma unroll
-  for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(rowp + c) = make_double2(x[c], x[c + 1]);
 }
 
-// L^-1 tile: thread c (< 64) solves L z = e_c and stores column c: dst[r*64 + c] = (L^-1)[r][c]
-__device__ __forceinline__ void invert_tile(const double (*sL)[NB + 1], const double* sinv, double* __restrict__ dst) {
-  const int c = threadIdx.x;
-  if (c >= NB) return;
-  double z[NB];
-#pragma unroll
+// L^-1: lane pair c solves L z = e_c into sZ row c (z_r, r >= c); the caller stores dst[r*64 + c] = (L^-1)[r][c].
+__device__ __forceinline__ void invert_tile(double* sZ, const double* sT, const double* sinv) {
+  const int c = threadIdx.x >> 1, h = threadIdx.x & 1;
+  double* z = sZ + c * LDT;
   for (int r = 0; r < NB; ++r) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int k = 0; k + 3 < r; k += 4) {
-      s0 += sL[r][k] * z[k]; s1 += sL[r][k + 1] * z[k + 1];
-      s2 += sL[r][k + 2] * z[k + 2]; s3 += sL[r][k + 3] * z[k + 3];
+    double s0 = 0.0, s1 = 0.0;
+    if (r > c) {
+      const double* a = sT + r * LDT;
+      int k = c + h;
+      for (; k + 2 < r; k += 4) { s0 += a[k] * z[k]; s1 += a[k + 2] * z[k + 2]; }
+      for (; k < r; k += 2) s0 += a[k] * z[k];
     }
-#pragma unroll
-    for (int k = r & ~3; k < r; ++k) s0 += sL[r][k] * z[k];
-    // rows above the unit entry are exactly zero (z_k = 0 for k < c), so the sums vanish there
-    z[r] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - ((s0 + s1) + (s2 + s3))) * sinv[r];
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (h == 0) z[r] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - s) * sinv[r];
+    __syncwarp();
   }
-#pragma unroll
-  for (int r = 0; r < NB; ++r) dst[r * NB + c] = z[r];  // plain L^-1, row-major: coalesced over threads
 }
 
 __device__ __forceinline__ void load_L_tile(const double* __restrict__ Ljj, int ld, double (*sL)[NB + 1]) {
@@ -181,18 +161,31 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, cons
 // the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
 // this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
-__global__ void __launch_bounds__(NB) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
-                                                        int* __restrict__ fail, double* __restrict__ LinvT) {
-  __shared__ double sL[NB][NB + 1];
+__global__ void __launch_bounds__(128) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
+                                                         int* __restrict__ fail, double* __restrict__ Linv) {
+  extern __shared__ double smem[];
+  double* sT = smem;                 // 64 x LDT: diagonal tile -> L_jj
+  double* sX = smem + NB * LDT;      // 64 x LDT: row tile (TRSM) or inverse (CTA 0)
   __shared__ double sinv[NB];
   const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
-  potrf_tile(Ajj, ld, nullptr, sL, sinv, fail);
-  if (blockIdx.x == 0) {  // off the critical path: (L_jj^-1)^T for the backward solve
-    invert_tile(sL, sinv, LinvT + (size_t)j * NB * NB);
+  double* Aij = blockIdx.x == 0 ? nullptr : A + (size_t)rows[blockIdx.x - 1] * NB * ld + (size_t)j * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += 128) {
+    const int r = e >> 6, c = e & 63;
+    sT[r * LDT + c] = (c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
+    if (Aij) sX[r * LDT + c] = Aij[(size_t)r * ld + c];
+  }
+  __syncthreads();
+  potrf_tile(sT, sinv, fail);
+  if (blockIdx.x == 0) {   // off the critical path: L_jj^-1 for the backward solve
+    invert_tile(sX, sT, sinv);
+    __syncthreads();
+    double* dst = Linv + (size_t)j * NB * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += 128) { const int r = e >> 6, c = e & 63; dst[e] = sX[c * LDT + r]; }
     return;
   }
-  const int i = rows[blockIdx.x - 1];
-  trsm_tile(A + (size_t)i * NB * ld + (size_t)j * NB, ld, sL, sinv);
+  trsm_tile(sX, sT, sinv);
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += 128) { const int r = e >> 6, c = e & 63; Aij[(size_t)r * ld + c] = sX[r * LDT + c]; }
 }
 
 // trailing update: for each listed pair (i,k), i >= k > j: A_ik -= X_i X_k^T
@@ -304,15 +297,17 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   const int Tn = chol_workspace_dims(sym.n, &ld, &rows);
   static bool attr_set = false;
   const int smem = 2 * NB * SPAD * (int)sizeof(double);
+  const int smem_pt = 2 * NB * LDT * (int)sizeof(double);
   if (!attr_set) {
     TSL_CUDA(cudaFuncSetAttribute(syrk_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
     attr_set = true;
   }
   cudaStream_t s = ctx->stream;
   for (int j = 0; j < Tn; ++j) {
     const int nrows = sym.rows_ptr[j + 1] - sym.rows_ptr[j];
     const int npairs = sym.pairs_ptr[j + 1] - sym.pairs_ptr[j];
-    LAUNCH(potrf_trsm_kernel<<<1 + nrows, NB, 0, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
+    LAUNCH(potrf_trsm_kernel<<<1 + nrows, 128, smem_pt, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
     if (npairs > 0) LAUNCH(syrk_pairs_kernel<<<npairs, 128, smem, s>>>(A, ld, j, sym.pairs.p + sym.pairs_ptr[j]));
   }
   TSL_CHECK_LAUNCH();

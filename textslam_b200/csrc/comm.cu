@@ -73,6 +73,11 @@ using namespace tsl;
 
 extern "C" {
 
+int tslam_shard_owner(int landmark_is_free, int landmark_index, int obs_index, int world) {
+  if (world < 1) return set_error(TSLAM_ERR_ARG, "world < 1");
+  return obs_owner(landmark_is_free != 0, landmark_index, obs_index, world);
+}
+
 int tslam_nccl_unique_id(uint8_t id_out[128]) {
   if (!id_out) return set_error(TSLAM_ERR_ARG, "null argument");
   int rc = load_nccl();
