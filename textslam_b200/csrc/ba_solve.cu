@@ -746,8 +746,14 @@ static int analyze_and_upload(Solver& S) {
   // ---- global block structure: unique (a<=b) camslot pairs from every active observation / landmark ----
   // per landmark camslot sets (global), via sort of (landmark, camslot)
   std::vector<uint64_t> bkeys;
-  bkeys.reserve((size_t)(GP + GT) * 3);
-  auto add_key = [&](int a, int b) { if (a > b) std::swap(a, b); bkeys.push_back((uint64_t)a * (uint64_t)nc + (uint64_t)b); };
+  // dense (a,b) -> block id table when nc^2 is small enough (O(1) insert / lookup); sorted-key fallback otherwise
+  const bool dense_tab = (size_t)nc * (size_t)nc <= ((size_t)1 << 24);
+  std::vector<int> btab;
+  if (dense_tab) btab.assign((size_t)nc * nc, -1); else bkeys.reserve((size_t)(GP + GT) * 3);
+  auto add_key = [&](int a, int b) {
+    if (a > b) std::swap(a, b);
+    if (dense_tab) btab[(size_t)a * nc + b] = 0; else bkeys.push_back((uint64_t)a * (uint64_t)nc + (uint64_t)b);
+  };
   {
     // direct pairs
     for (int i = 0; i < GP; ++i) if (gp_active[i]) {
@@ -787,14 +793,21 @@ static int analyze_and_upload(Solver& S) {
     schur_pairs(GP, d->h_p_cam, d->h_p_host, d->h_p_lm, gp_active, S.lmfree_p_h, S.nl);
     schur_pairs(GT, d->h_t_cam, d->h_t_host, d->h_t_plane, gt_active, S.lmfree_t_h, S.npl);
   }
-  std::sort(bkeys.begin(), bkeys.end());
-  bkeys.erase(std::unique(bkeys.begin(), bkeys.end()), bkeys.end());
-  S.nblk = (int)bkeys.size();
-  std::vector<int> blk_a(S.nblk), blk_b(S.nblk), diag_blk(nc, -1);
-  for (int b = 0; b < S.nblk; ++b) {
-    blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); blk_b[b] = (int)(bkeys[b] % (uint64_t)nc);
-    if (blk_a[b] == blk_b[b]) diag_blk[blk_a[b]] = b;
+  std::vector<int> blk_a, blk_b, diag_blk(nc, -1);
+  if (dense_tab) {
+    int nb = 0;
+    for (int a = 0; a < nc; ++a)
+      for (int b = a; b < nc; ++b)
+        if (btab[(size_t)a * nc + b] == 0) { btab[(size_t)a * nc + b] = nb++; blk_a.push_back(a); blk_b.push_back(b); }
+    S.nblk = nb;
+  } else {
+    std::sort(bkeys.begin(), bkeys.end());
+    bkeys.erase(std::unique(bkeys.begin(), bkeys.end()), bkeys.end());
+    S.nblk = (int)bkeys.size();
+    blk_a.resize(S.nblk); blk_b.resize(S.nblk);
+    for (int b = 0; b < S.nblk; ++b) { blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); blk_b[b] = (int)(bkeys[b] % (uint64_t)nc); }
   }
+  for (int b = 0; b < S.nblk; ++b) if (blk_a[b] == blk_b[b]) diag_blk[blk_a[b]] = b;
   {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
     std::vector<uint8_t> tile_nz((size_t)S.Tn * S.Tn, 0);
     for (int b = 0; b < S.nblk; ++b) {
@@ -807,6 +820,7 @@ static int analyze_and_upload(Solver& S) {
   }
   auto blk_of = [&](int a, int b) {
     if (a > b) std::swap(a, b);
+    if (dense_tab) return btab[(size_t)a * nc + b];
     const uint64_t key = (uint64_t)a * (uint64_t)nc + (uint64_t)b;
     return (int)(std::lower_bound(bkeys.begin(), bkeys.end(), key) - bkeys.begin());
   };

@@ -32,71 +32,73 @@ constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4
 // device tile routines (potrf / trsm / invert: 64 threads; gemm: 128 threads)
 // ---------------------------------------------------------------------------------------------
 
-// All three 64x64 tile routines below run on 128 threads (two lanes of one warp per row / column) with the
-// tile in shared memory and short loops: a fully unrolled register version (2016 FMAs of straight-line code
-// per routine) measured 64 us per launch because it does not fit the instruction cache (profiles/r1).
-constexpr int LDT = NB + 1;  // smem leading dimension (doubles)
+// The three 64x64 tile routines keep the tile in shared memory and are written column-oriented
+// (right-looking) so that every step is a batch of INDEPENDENT FMAs: measured alternatives were a fully
+// unrolled register version (64 us per launch: 3 x 2016 FMAs of straight-line code miss the instruction
+// cache) and a left-looking dot-product version (101 us: serial LDS->DFMA chains) — profiles/r1_notes.md.
+constexpr int LDT = NB + 1;       // smem leading dimension (doubles)
+constexpr int PT_THREADS = 256;   // CTA size of potrf_trsm_kernel
 
-// Crout Cholesky in place on sT (lower triangle). sinv[c] = 1 / L[c][c] so that no FP64 division sits on the
-// critical path of the TRSM / inverse.
-__device__ __forceinline__ void potrf_tile(double* sT, double* sinv, int* fail) {
-  const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+// Right-looking Cholesky in place on sT (lower triangle), 256 threads as a 16x16 grid, each owning the
+// elements (r, k) with r = ty + 16 i, k = tx + 16 j. sinv[c] = 1 / L[c][c]; col[] is a scaled copy of the
+// current column so that the rank-1 update needs no read-after-write hazard handling.
+__device__ __forceinline__ void potrf_tile(double* sT, double* sinv, double* col, int* fail) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   for (int c = 0; c < NB; ++c) {
-    double s0 = 0.0, s1 = 0.0;
-    if (r >= c) {
-      const double* a = sT + r * LDT; const double* b = sT + c * LDT;
-      int k = h;
-      for (; k + 2 < c; k += 4) { s0 += a[k] * b[k]; s1 += a[k + 2] * b[k + 2]; }
-      for (; k < c; k += 2) s0 += a[k] * b[k];
-    }
-    double s = s0 + s1;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    const double val = sT[r * LDT + c] - s;
-    if (h == 0 && r == c) {
-      if (!(val > 0.0)) atomicExch(fail, 1);  // not positive definite (or NaN): report, continue with a harmless pivot
-      sinv[c] = (val > 0.0) ? rsqrt(val) : 1.0;
+    const double piv = sT[c * LDT + c];                   // broadcast read; every thread derives the same inverse
+    const double inv = (piv > 0.0) ? rsqrt(piv) : 1.0;
+    if (threadIdx.x < NB) {
+      const int r = threadIdx.x;
+      if (r == c) { sinv[c] = inv; if (!(piv > 0.0)) atomicExch(fail, 1); }   // not SPD / NaN: report, harmless pivot
+      if (r >= c) col[r] = sT[r * LDT + c] * inv;          // sT itself is written after the barrier (others still read sT[c][c])
     }
     __syncthreads();
-    if (h == 0 && r >= c) sT[r * LDT + c] = val * sinv[c];   // diagonal: val * rsqrt(val) = sqrt(val)
+    if (threadIdx.x < NB && threadIdx.x >= c) sT[threadIdx.x * LDT + c] = col[threadIdx.x];
+    // trailing update A[r][k] -= l_r l_k for c < k <= r. All loads are staged in registers before any store so
+    // that the 16 updates are independent (sT / col may alias as far as the compiler knows).
+    const int k0 = c + 1;
+    double lr[4], lk[4], a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { lr[i] = col[ty + 16 * i]; lk[i] = col[tx + 16 * i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = ty + 16 * i, k = tx + 16 * j;
+        a[i][j] = (k >= k0 && k <= r) ? sT[r * LDT + k] : 0.0;
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = ty + 16 * i, k = tx + 16 * j;
+        if (k >= k0 && k <= r) sT[r * LDT + k] = a[i][j] - lr[i] * lk[j];
+      }
     __syncthreads();
   }
 }
 
-// X L^T = A for one 64-row tile held in sX (in place). Rows are independent: lane pairs only need __syncwarp.
+// X L^T = A for one 64-row tile held in sX (in place), column-oriented: x_c *= inv_c, then x_k -= x_c L[k][c]
+// for k > c. Four lanes of one warp share a row (k = q + 4 m); rows are independent, so only __syncwarp is needed.
 __device__ __forceinline__ void trsm_tile(double* sX, const double* sT, const double* sinv) {
-  const int r = threadIdx.x >> 1, h = threadIdx.x & 1;
+  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
   double* x = sX + r * LDT;
   for (int c = 0; c < NB; ++c) {
-    const double* b = sT + c * LDT;
-    double s0 = 0.0, s1 = 0.0;
-    int k = h;
-    for (; k + 2 < c; k += 4) { s0 += x[k] * b[k]; s1 += x[k + 2] * b[k + 2]; }
-    for (; k < c; k += 2) s0 += x[k] * b[k];
-    double s = s0 + s1;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (h == 0) x[c] = (x[c] - s) * sinv[c];
+    const double xc = x[c] * sinv[c];
+    __syncwarp();
+    if (q == (c & 3)) x[c] = xc;
+    const int kb = c + 1 + ((q - (c + 1)) & 3);
+    double xv[16], lv[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { const int k = kb + 4 * m; xv[m] = (k < NB) ? x[k] : 0.0; lv[m] = (k < NB) ? sT[k * LDT + c] : 0.0; }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) { const int k = kb + 4 * m; if (k < NB) x[k] = xv[m] - xc * lv[m]; }
     __syncwarp();
   }
 }
 
-// L^-1: lane pair c solves L z = e_c into sZ row c (z_r, r >= c); the caller stores dst[r*64 + c] = (L^-1)[r][c].
-__device__ __forceinline__ void invert_tile(double* sZ, const double* sT, const double* sinv) {
-  const int c = threadIdx.x >> 1, h = threadIdx.x & 1;
-  double* z = sZ + c * LDT;
-  for (int r = 0; r < NB; ++r) {
-    double s0 = 0.0, s1 = 0.0;
-    if (r > c) {
-      const double* a = sT + r * LDT;
-      int k = c + h;
-      for (; k + 2 < r; k += 4) { s0 += a[k] * z[k]; s1 += a[k + 2] * z[k + 2]; }
-      for (; k < r; k += 2) s0 += a[k] * z[k];
-    }
-    double s = s0 + s1;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (h == 0) z[r] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - s) * sinv[r];
-    __syncwarp();
-  }
-}
+// L^-1 for the backward solve comes from the same routine: CTA 0 runs trsm_tile on an identity tile
+// (X L^T = I  ->  X = L^-T) and stores the transpose.
 
 __device__ __forceinline__ void load_L_tile(const double* __restrict__ Ljj, int ld, double (*sL)[NB + 1]) {
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
@@ -114,12 +116,22 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // C (64x64 at C, ld) -= Xi Xk^T with Xi, Xk 64x64 tiles (ld). 4 warps (2x2), warp tile 32x32.
 __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, const double* __restrict__ Xk, double* __restrict__ C, int ld,
                                              double* sA, double* sB) {
-  for (int e = threadIdx.x; e < NB * NB / 2; e += 128) {
-    const int r = e >> 5, c2 = (e & 31) * 2;
-    const double2 va = *reinterpret_cast<const double2*>(Xi + (size_t)r * ld + c2);
-    const double2 vb = *reinterpret_cast<const double2*>(Xk + (size_t)r * ld + c2);
-    sA[r * SPAD + c2] = va.x; sA[r * SPAD + c2 + 1] = va.y;
-    sB[r * SPAD + c2] = vb.x; sB[r * SPAD + c2 + 1] = vb.y;
+  // 2 x 32 KB tile loads: all 16-byte loads of a batch are issued before the first shared-memory store
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    double2 va[8], vb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = threadIdx.x + 128 * (8 * half + u), r = e >> 5, c2 = (e & 31) * 2;
+      va[u] = *reinterpret_cast<const double2*>(Xi + (size_t)r * ld + c2);
+      vb[u] = *reinterpret_cast<const double2*>(Xk + (size_t)r * ld + c2);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = threadIdx.x + 128 * (8 * half + u), r = e >> 5, c2 = (e & 31) * 2;
+      sA[r * SPAD + c2] = va[u].x; sA[r * SPAD + c2 + 1] = va[u].y;
+      sB[r * SPAD + c2] = vb[u].x; sB[r * SPAD + c2 + 1] = vb[u].y;
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,31 +173,39 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, cons
 // the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
 // this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
-__global__ void __launch_bounds__(128) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
-                                                         int* __restrict__ fail, double* __restrict__ Linv) {
+__global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
+                                                                int* __restrict__ fail, double* __restrict__ Linv) {
   extern __shared__ double smem[];
   double* sT = smem;                 // 64 x LDT: diagonal tile -> L_jj
-  double* sX = smem + NB * LDT;      // 64 x LDT: row tile (TRSM) or inverse (CTA 0)
+  double* sX = smem + NB * LDT;      // 64 x LDT: row tile (TRSM) or identity -> L_jj^-T (CTA 0)
   __shared__ double sinv[NB];
+  __shared__ double col[NB];
   const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
   double* Aij = blockIdx.x == 0 ? nullptr : A + (size_t)rows[blockIdx.x - 1] * NB * ld + (size_t)j * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += 128) {
-    const int r = e >> 6, c = e & 63;
-    sT[r * LDT + c] = (c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
-    if (Aij) sX[r * LDT + c] = Aij[(size_t)r * ld + c];
+  {
+    double vt[16], vx[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = threadIdx.x + PT_THREADS * u, r = e >> 6, c = e & 63;
+      vt[u] = (c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
+      vx[u] = Aij ? Aij[(size_t)r * ld + c] : ((r == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = threadIdx.x + PT_THREADS * u, r = e >> 6, c = e & 63;
+      sT[r * LDT + c] = vt[u]; sX[r * LDT + c] = vx[u];
+    }
   }
   __syncthreads();
-  potrf_tile(sT, sinv, fail);
-  if (blockIdx.x == 0) {   // off the critical path: L_jj^-1 for the backward solve
-    invert_tile(sX, sT, sinv);
-    __syncthreads();
+  potrf_tile(sT, sinv, col, fail);
+  trsm_tile(sX, sT, sinv);           // CTA 0: X L^T = I  ->  X = L^-T
+  __syncthreads();
+  if (blockIdx.x == 0) {             // off the critical path: store L_jj^-1 = X^T for the backward solve
     double* dst = Linv + (size_t)j * NB * NB;
-    for (int e = threadIdx.x; e < NB * NB; e += 128) { const int r = e >> 6, c = e & 63; dst[e] = sX[c * LDT + r]; }
+    for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; dst[e] = sX[c * LDT + r]; }
     return;
   }
-  trsm_tile(sX, sT, sinv);
-  __syncthreads();
-  for (int e = threadIdx.x; e < NB * NB; e += 128) { const int r = e >> 6, c = e & 63; Aij[(size_t)r * ld + c] = sX[r * LDT + c]; }
+  for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; Aij[(size_t)r * ld + c] = sX[r * LDT + c]; }
 }
 
 // trailing update: for each listed pair (i,k), i >= k > j: A_ik -= X_i X_k^T
@@ -307,7 +327,7 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   for (int j = 0; j < Tn; ++j) {
     const int nrows = sym.rows_ptr[j + 1] - sym.rows_ptr[j];
     const int npairs = sym.pairs_ptr[j + 1] - sym.pairs_ptr[j];
-    LAUNCH(potrf_trsm_kernel<<<1 + nrows, 128, smem_pt, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
+    LAUNCH(potrf_trsm_kernel<<<1 + nrows, PT_THREADS, smem_pt, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
     if (npairs > 0) LAUNCH(syrk_pairs_kernel<<<npairs, 128, smem, s>>>(A, ld, j, sym.pairs.p + sym.pairs_ptr[j]));
   }
   TSL_CHECK_LAUNCH();
