@@ -149,6 +149,12 @@ int tslam_ctx_create(int device_id, tslam_ctx** out) {
     delete c;
     return set_error(TSLAM_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a kernels only", device_id, prop.major, prop.minor);
   }
+  {
+    cudaMemPool_t pool;
+    TSL_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_id));
+    unsigned long long keep = ~0ull;
+    TSL_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   c->sm_count = prop.multiProcessorCount;
   c->l2_bytes = (size_t)prop.l2CacheSize;
   TSL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -16,6 +16,9 @@
 // Tn x Tn tile pattern once per problem (ChoSymbolic) and every panel step only touches the listed
 // non-zero tiles; a dense pattern degenerates to the classic right-looking blocked algorithm.
 //
+// Tile routines: fully unrolled, rows in registers (Crout). Measured alternatives (profiles/r1_notes.md): shared-memory
+// left-looking loops (2.1x slower), shared-memory right-looking rank-1 updates on 256 threads (1.6x slower); the
+// unrolled version is instruction-fetch bound (ncu: stall_no_instruction dominant, 70 % I-cache hit rate).
 // Per 64-wide panel j: potrf (one CTA, rows in registers, Crout) -> trsm (one CTA per non-zero tile
 // below) -> syrk/gemm trailing update with FP64 tensor-core MMA (mma.sync.m8n8k4.f64 — tcgen05 has
 // no FP64 kind; DMMA is the FP64 tensor path on sm_100a), one CTA per non-zero 64x64 lower tile pair.
@@ -32,73 +35,91 @@ constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4
 // device tile routines (potrf / trsm / invert: 64 threads; gemm: 128 threads)
 // ---------------------------------------------------------------------------------------------
 
-// The three 64x64 tile routines keep the tile in shared memory and are written column-oriented
-// (right-looking) so that every step is a batch of INDEPENDENT FMAs: measured alternatives were a fully
-// unrolled register version (64 us per launch: 3 x 2016 FMAs of straight-line code miss the instruction
-// cache) and a left-looking dot-product version (101 us: serial LDS->DFMA chains) — profiles/r1_notes.md.
-constexpr int LDT = NB + 1;       // smem leading dimension (doubles)
-constexpr int PT_THREADS = 256;   // CTA size of potrf_trsm_kernel
-
-// Right-looking Cholesky in place on sT (lower triangle), 256 threads as a 16x16 grid, each owning the
-// elements (r, k) with r = ty + 16 i, k = tx + 16 j. sinv[c] = 1 / L[c][c]; col[] is a scaled copy of the
-// current column so that the rank-1 update needs no read-after-write hazard handling.
-__device__ __forceinline__ void potrf_tile(double* sT, double* sinv, double* col, int* fail) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+// Crout Cholesky of a 64x64 tile: thread r (< 64) owns row r in registers; finished rows are
+// published to shared memory so that the dot products read row c as a broadcast.
+// sinv[c] = 1 / L[c][c] (kept for the TRSM / inverse so that no FP64 division sits on a critical path).
+__device__ __forceinline__ void potrf_tile(const double* __restrict__ Ajj, int ld, double* __restrict__ dst /*64x64 tight or null*/,
+                                           double (*sL)[NB + 1], double* sinv, int* fail) {
+  const int r = threadIdx.x;
+  double row[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) row[c] = (r < NB && c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
+#pragma unroll
   for (int c = 0; c < NB; ++c) {
-    const double piv = sT[c * LDT + c];                   // broadcast read; every thread derives the same inverse
-    const double inv = (piv > 0.0) ? rsqrt(piv) : 1.0;
-    if (threadIdx.x < NB) {
-      const int r = threadIdx.x;
-      if (r == c) { sinv[c] = inv; if (!(piv > 0.0)) atomicExch(fail, 1); }   // not SPD / NaN: report, harmless pivot
-      if (r >= c) col[r] = sT[r * LDT + c] * inv;          // sT itself is written after the barrier (others still read sT[c][c])
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (r < NB && r >= c) {
+#pragma unroll
+      for (int k = 0; k + 3 < c; k += 4) {
+        s0 += row[k] * sL[c][k]; s1 += row[k + 1] * sL[c][k + 1];
+        s2 += row[k + 2] * sL[c][k + 2]; s3 += row[k + 3] * sL[c][k + 3];
+      }
+#pragma unroll
+      for (int k = c & ~3; k < c; ++k) s0 += row[k] * sL[c][k];
+    }
+    const double s = row[c] - ((s0 + s1) + (s2 + s3));
+    if (r == c) {
+      if (!(s > 0.0)) atomicExch(fail, 1);  // not positive definite (or NaN): report, continue with a harmless pivot
+      sinv[c] = (s > 0.0) ? rsqrt(s) : 1.0;
     }
     __syncthreads();
-    if (threadIdx.x < NB && threadIdx.x >= c) sT[threadIdx.x * LDT + c] = col[threadIdx.x];
-    // trailing update A[r][k] -= l_r l_k for c < k <= r. All loads are staged in registers before any store so
-    // that the 16 updates are independent (sT / col may alias as far as the compiler knows).
-    const int k0 = c + 1;
-    double lr[4], lk[4], a[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { lr[i] = col[ty + 16 * i]; lk[i] = col[tx + 16 * i]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = ty + 16 * i, k = tx + 16 * j;
-        a[i][j] = (k >= k0 && k <= r) ? sT[r * LDT + k] : 0.0;
-      }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = ty + 16 * i, k = tx + 16 * j;
-        if (k >= k0 && k <= r) sT[r * LDT + k] = a[i][j] - lr[i] * lk[j];
-      }
+    if (r < NB && r >= c) {
+      const double inv = sinv[c];
+      row[c] = s * inv;   // diagonal: s * rsqrt(s) = sqrt(s)
+      sL[r][c] = row[c];
+    }
     __syncthreads();
   }
-}
-
-// X L^T = A for one 64-row tile held in sX (in place), column-oriented: x_c *= inv_c, then x_k -= x_c L[k][c]
-// for k > c. Four lanes of one warp share a row (k = q + 4 m); rows are independent, so only __syncwarp is needed.
-__device__ __forceinline__ void trsm_tile(double* sX, const double* sT, const double* sinv) {
-  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
-  double* x = sX + r * LDT;
-  for (int c = 0; c < NB; ++c) {
-    const double xc = x[c] * sinv[c];
-    __syncwarp();
-    if (q == (c & 3)) x[c] = xc;
-    const int kb = c + 1 + ((q - (c + 1)) & 3);
-    double xv[16], lv[16];
+  if (dst && r < NB) {
 #pragma unroll
-    for (int m = 0; m < 16; ++m) { const int k = kb + 4 * m; xv[m] = (k < NB) ? x[k] : 0.0; lv[m] = (k < NB) ? sT[k * LDT + c] : 0.0; }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) { const int k = kb + 4 * m; if (k < NB) x[k] = xv[m] - xc * lv[m]; }
-    __syncwarp();
+    for (int c = 0; c < NB; ++c) dst[r * NB + c] = (c <= r) ? row[c] : 0.0;
   }
 }
 
-// L^-1 for the backward solve comes from the same routine: CTA 0 runs trsm_tile on an identity tile
-// (X L^T = I  ->  X = L^-T) and stores the transpose.
+// X L^T = A for one 64-row tile; sL holds L (lower, row-major). Thread r < 64 owns one row.
+__device__ __forceinline__ void trsm_tile(double* __restrict__ Aij, int ld, const double (*sL)[NB + 1], const double* sinv) {
+  const int r = threadIdx.x;
+  if (r >= NB) return;
+  double* rowp = Aij + (size_t)r * ld;
+  double x[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(rowp + c); x[c] = v.x; x[c + 1] = v.y; }
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < c; k += 4) {
+      s0 += x[k] * sL[c][k]; s1 += x[k + 1] * sL[c][k + 1];
+      s2 += x[k + 2] * sL[c][k + 2]; s3 += x[k + 3] * sL[c][k + 3];
+    }
+#pragma unroll
+    for (int k = c & ~3; k < c; ++k) s0 += x[k] * sL[c][k];
+    x[c] = (x[c] - ((s0 + s1) + (s2 + s3))) * sinv[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(rowp + c) = make_double2(x[c], x[c + 1]);
+}
+
+// L^-1 tile: thread c (< 64) solves L z = e_c and stores column c: dst[r*64 + c] = (L^-1)[r][c]
+__device__ __forceinline__ void invert_tile(const double (*sL)[NB + 1], const double* sinv, double* __restrict__ dst) {
+  const int c = threadIdx.x;
+  if (c >= NB) return;
+  double z[NB];
+#pragma unroll
+  for (int r = 0; r < NB; ++r) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 3 < r; k += 4) {
+      s0 += sL[r][k] * z[k]; s1 += sL[r][k + 1] * z[k + 1];
+      s2 += sL[r][k + 2] * z[k + 2]; s3 += sL[r][k + 3] * z[k + 3];
+    }
+#pragma unroll
+    for (int k = r & ~3; k < r; ++k) s0 += sL[r][k] * z[k];
+    // rows above the unit entry are exactly zero (z_k = 0 for k < c), so the sums vanish there
+    z[r] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - ((s0 + s1) + (s2 + s3))) * sinv[r];
+  }
+#pragma unroll
+  for (int r = 0; r < NB; ++r) dst[r * NB + c] = z[r];  // plain L^-1, row-major: coalesced over threads
+}
 
 __device__ __forceinline__ void load_L_tile(const double* __restrict__ Ljj, int ld, double (*sL)[NB + 1]) {
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
@@ -173,39 +194,18 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, cons
 // the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
 // this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
-__global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
-                                                                int* __restrict__ fail, double* __restrict__ Linv) {
-  extern __shared__ double smem[];
-  double* sT = smem;                 // 64 x LDT: diagonal tile -> L_jj
-  double* sX = smem + NB * LDT;      // 64 x LDT: row tile (TRSM) or identity -> L_jj^-T (CTA 0)
+__global__ void __launch_bounds__(NB) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
+                                                        int* __restrict__ fail, double* __restrict__ LinvT) {
+  __shared__ double sL[NB][NB + 1];
   __shared__ double sinv[NB];
-  __shared__ double col[NB];
   const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
-  double* Aij = blockIdx.x == 0 ? nullptr : A + (size_t)rows[blockIdx.x - 1] * NB * ld + (size_t)j * NB;
-  {
-    double vt[16], vx[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = threadIdx.x + PT_THREADS * u, r = e >> 6, c = e & 63;
-      vt[u] = (c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
-      vx[u] = Aij ? Aij[(size_t)r * ld + c] : ((r == c) ? 1.0 : 0.0);
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int e = threadIdx.x + PT_THREADS * u, r = e >> 6, c = e & 63;
-      sT[r * LDT + c] = vt[u]; sX[r * LDT + c] = vx[u];
-    }
-  }
-  __syncthreads();
-  potrf_tile(sT, sinv, col, fail);
-  trsm_tile(sX, sT, sinv);           // CTA 0: X L^T = I  ->  X = L^-T
-  __syncthreads();
-  if (blockIdx.x == 0) {             // off the critical path: store L_jj^-1 = X^T for the backward solve
-    double* dst = Linv + (size_t)j * NB * NB;
-    for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; dst[e] = sX[c * LDT + r]; }
+  potrf_tile(Ajj, ld, nullptr, sL, sinv, fail);
+  if (blockIdx.x == 0) {  // off the critical path: (L_jj^-1)^T for the backward solve
+    invert_tile(sL, sinv, LinvT + (size_t)j * NB * NB);
     return;
   }
-  for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; Aij[(size_t)r * ld + c] = sX[r * LDT + c]; }
+  const int i = rows[blockIdx.x - 1];
+  trsm_tile(A + (size_t)i * NB * ld + (size_t)j * NB, ld, sL, sinv);
 }
 
 // trailing update: for each listed pair (i,k), i >= k > j: A_ik -= X_i X_k^T
@@ -317,17 +317,15 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   const int Tn = chol_workspace_dims(sym.n, &ld, &rows);
   static bool attr_set = false;
   const int smem = 2 * NB * SPAD * (int)sizeof(double);
-  const int smem_pt = 2 * NB * LDT * (int)sizeof(double);
   if (!attr_set) {
     TSL_CUDA(cudaFuncSetAttribute(syrk_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
     attr_set = true;
   }
   cudaStream_t s = ctx->stream;
   for (int j = 0; j < Tn; ++j) {
     const int nrows = sym.rows_ptr[j + 1] - sym.rows_ptr[j];
     const int npairs = sym.pairs_ptr[j + 1] - sym.pairs_ptr[j];
-    LAUNCH(potrf_trsm_kernel<<<1 + nrows, PT_THREADS, smem_pt, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
+    LAUNCH(potrf_trsm_kernel<<<1 + nrows, NB, 0, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
     if (npairs > 0) LAUNCH(syrk_pairs_kernel<<<npairs, 128, smem, s>>>(A, ld, j, sym.pairs.p + sym.pairs_ptr[j]));
   }
   TSL_CHECK_LAUNCH();

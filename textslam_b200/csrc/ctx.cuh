@@ -26,15 +26,18 @@ template <typename T>
 struct DevBuf {  // simple RAII device buffer (grow-only)
   T* p = nullptr;
   size_t cap = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, cudaStreamPerThread); }   // back to the (never trimmed) default pool: next solve reuses it
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   cudaError_t reserve(size_t n) {
     if (p && n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, cudaStreamPerThread);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    // stream-ordered allocation from the device's default memory pool (release threshold raised in tslam_ctx_create):
+    // repeated tslam_solve calls recycle their buffers instead of paying cudaMalloc/cudaFree every time
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T), cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
     if (e == cudaSuccess) cap = n;
     return e;
   }
