@@ -82,6 +82,44 @@ def test_medium_global_ba(ctx, oracle):
     _compare(ctx, oracle, prob, 8)
 
 
+def test_dense_camera_graph_and_loop_closure_links(ctx, oracle):
+    # (a) every keyframe pair co-observes landmarks -> dense reduced matrix, the tile level schedule degenerates to a chain
+    prob = synth.make_ba_problem(seed=61, n_kf=150, n_lm=4000, obs_per_lm=4, band=150, fixed_cams=(0, 1), w_point=1.0)
+    so, sg = _compare(ctx, oracle, prob, 6)
+    assert sg["reduced_dim"] == 6 * 148
+    # (b) banded graph plus long-range "loop closure" landmarks -> fill outside the band under the nested-dissection order
+    prob = synth.c5_global_ba(seed=62, n_kf=260, n_lm=9000)
+    rng = np.random.default_rng(62)
+    extra = 40
+    lm0 = len(prob.rho)
+    host = rng.integers(0, 30, extra); cam = rng.integers(220, 260, extra)
+    import copy
+    q = copy.deepcopy(prob)
+    # re-observe existing landmarks hosted in the first 30 keyframes from the last 40 (observation = current projection + noise)
+    hosted = [np.nonzero((prob.p_host == h))[0] for h in host]
+    new_rows = [(int(rng.choice(ix)), int(c)) for ix, c in zip(hosted, cam) if len(ix)]
+    from textslam_b200._abi import PT_BA_NW
+    tmp = copy.deepcopy(prob)
+    tmp.p_cam = np.ascontiguousarray([c for _, c in new_rows], dtype=np.int32)
+    tmp.p_host = np.ascontiguousarray(prob.p_host[[i for i, _ in new_rows]], dtype=np.int32)
+    tmp.p_lm = np.ascontiguousarray(prob.p_lm[[i for i, _ in new_rows]], dtype=np.int32)
+    tmp.p_ray = np.ascontiguousarray(prob.p_ray[[i for i, _ in new_rows]])
+    tmp.p_uv = np.zeros((len(new_rows), 2))
+    r, _ = oracle.eval_points(tmp, PT_BA_NW, want_J=False)      # r = projection - 0  -> projected pixel
+    tmp.p_uv = np.ascontiguousarray(r + rng.normal(0, 1.0, r.shape))
+    q.p_uv = np.concatenate([prob.p_uv, tmp.p_uv]); q.p_ray = np.concatenate([prob.p_ray, tmp.p_ray])
+    q.p_cam = np.concatenate([prob.p_cam, tmp.p_cam]).astype(np.int32); q.p_host = np.concatenate([prob.p_host, tmp.p_host]).astype(np.int32)
+    q.p_lm = np.concatenate([prob.p_lm, tmp.p_lm]).astype(np.int32)
+    assert lm0 == len(q.rho)
+    _compare(ctx, oracle, q, 6)
+
+
+def test_global_ba_text_on(ctx, oracle):
+    # the reference's (disabled) text branch of PyrGlobalBA, w_T = 1 (src/optimizer.cc:1813)
+    prob = synth.c5_global_ba(seed=63, n_kf=120, n_lm=5000, n_planes=150, text_kf_stride=4)
+    _compare(ctx, oracle, prob, 6)
+
+
 def test_global_ba_c5_full_size(ctx, oracle):
     prob = synth.c5_global_ba(seed=0)
     so, sg = _compare(ctx, oracle, prob, 5)

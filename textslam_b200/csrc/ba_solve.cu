@@ -742,6 +742,39 @@ static int analyze_and_upload(Solver& S) {
   const int nc = S.nc;
   S.n = 6 * nc;
   S.Tn = chol_workspace_dims(S.n, &S.ld, &S.rows);
+  // ---- nested-dissection order of the free cameras (keyframes are temporally ordered, co-visibility is banded) ----
+  // Units of U cameras (U = multiple of 32 cameras = 3 tiles of 64 columns, at least the co-visibility bandwidth) are
+  // ordered leaves-first / separators-last so that the tile elimination DAG of chol.cu has ~log depth instead of being
+  // a chain; any order is valid, this one only shortens the critical path of the reduced-system factorisation.
+  if (nc >= 128) {
+    std::vector<int> dist;
+    dist.reserve((size_t)GP + GT);
+    for (int i = 0; i < GP; ++i) if (gp_active[i]) { const int a = S.camslot[d->h_p_cam[i]], b = S.camslot[d->h_p_host[i]]; if (a >= 0 && b >= 0) dist.push_back(std::abs(a - b)); }
+    for (int i = 0; i < GT; ++i) if (gt_active[i]) { const int a = S.camslot[d->h_t_cam[i]], b = S.camslot[d->h_t_host[i]]; if (a >= 0 && b >= 0) dist.push_back(std::abs(a - b)); }
+    int bw = 0;
+    if (!dist.empty()) { const size_t q = (size_t)(0.98 * (dist.size() - 1)); std::nth_element(dist.begin(), dist.begin() + q, dist.end()); bw = 2 * dist[q]; }
+    const int U = 32 * ((bw + 1 + 31) / 32);
+    const int nfull = nc / U;
+    if (nfull >= 4) {
+      std::vector<int> unit_order;
+      std::vector<std::pair<int, int>> stack;  // recursive bisection written iteratively (post-order: left, right, separator)
+      struct Frame { int lo, hi, stage; };
+      std::vector<Frame> st; st.push_back({0, nfull, 0});
+      while (!st.empty()) {
+        Frame f = st.back(); st.pop_back();
+        if (f.hi - f.lo <= 0) continue;
+        if (f.hi - f.lo <= 2) { for (int u = f.lo; u < f.hi; ++u) unit_order.push_back(u); continue; }
+        const int mid = (f.lo + f.hi) / 2;
+        if (f.stage == 0) { st.push_back({f.lo, f.hi, 1}); st.push_back({mid + 1, f.hi, 0}); st.push_back({f.lo, mid, 0}); }
+        else unit_order.push_back(mid);
+      }
+      std::vector<int> new_of_old(nc, -1);
+      int next = 0;
+      for (int u : unit_order) for (int c = u * U; c < (u + 1) * U; ++c) new_of_old[c] = next++;
+      for (int c = nfull * U; c < nc; ++c) new_of_old[c] = next++;   // the partial unit goes last (keeps units tile-aligned)
+      for (int k = 0; k < K; ++k) if (S.camslot[k] >= 0) S.camslot[k] = new_of_old[S.camslot[k]];
+    }
+  }
 
   // ---- global block structure: unique (a<=b) camslot pairs from every active observation / landmark ----
   // per landmark camslot sets (global), via sort of (landmark, camslot)

@@ -194,61 +194,128 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, cons
 // the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
 // this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
-__global__ void __launch_bounds__(NB) potrf_trsm_kernel(double* __restrict__ A, int ld, int j, const int* __restrict__ rows,
+__global__ void __launch_bounds__(NB) potrf_trsm_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
                                                         int* __restrict__ fail, double* __restrict__ LinvT) {
+  // one CTA per (panel j, row tile i) item of the current wave; i < 0 marks the CTA that stores L_jj^-1
   __shared__ double sL[NB][NB + 1];
   __shared__ double sinv[NB];
+  const int2 it = items[blockIdx.x];
+  const int j = it.x;
   const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
   potrf_tile(Ajj, ld, nullptr, sL, sinv, fail);
-  if (blockIdx.x == 0) {  // off the critical path: (L_jj^-1)^T for the backward solve
+  if (it.y < 0) {  // off the critical path: L_jj^-1 for the backward solve
     invert_tile(sL, sinv, LinvT + (size_t)j * NB * NB);
     return;
   }
-  const int i = rows[blockIdx.x - 1];
-  trsm_tile(A + (size_t)i * NB * ld + (size_t)j * NB, ld, sL, sinv);
+  trsm_tile(A + (size_t)it.y * NB * ld + (size_t)j * NB, ld, sL, sinv);
 }
 
-// trailing update: for each listed pair (i,k), i >= k > j: A_ik -= X_i X_k^T
-__global__ void __launch_bounds__(128) syrk_pairs_kernel(double* __restrict__ A, int ld, int j, const int2* __restrict__ pairs) {
+// trailing update of one wave: one CTA per target tile (i,k); it sums the contributions X_i^(j) X_k^(j)^T of every
+// source panel j of this wave (no two CTAs touch the same tile, so no atomics and a fixed summation order).
+__global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, int ld, const int2* __restrict__ targets,
+                                                        const int* __restrict__ src_ptr, const int* __restrict__ src) {
   extern __shared__ double smem[];
-  const int2 pr = pairs[blockIdx.x];
-  gemm_tile_nt(A + (size_t)pr.x * NB * ld + (size_t)j * NB, A + (size_t)pr.y * NB * ld + (size_t)j * NB,
-               A + (size_t)pr.x * NB * ld + (size_t)pr.y * NB, ld, smem, smem + NB * SPAD);
+  double* sA = smem;
+  double* sB = smem + NB * SPAD;
+  const int2 tg = targets[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+  const int g = lane >> 2, tgi = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int e = src_ptr[blockIdx.x]; e < src_ptr[blockIdx.x + 1]; ++e) {
+    const int j = src[e];
+    const double* Xi = A + (size_t)tg.x * NB * ld + (size_t)j * NB;
+    const double* Xk = A + (size_t)tg.y * NB * ld + (size_t)j * NB;
+    __syncthreads();   // previous source fully consumed
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double2 va[8], vb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ee = threadIdx.x + 128 * (8 * half + u), r = ee >> 5, c2 = (ee & 31) * 2;
+        va[u] = *reinterpret_cast<const double2*>(Xi + (size_t)r * ld + c2);
+        vb[u] = *reinterpret_cast<const double2*>(Xk + (size_t)r * ld + c2);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ee = threadIdx.x + 128 * (8 * half + u), r = ee >> 5, c2 = (ee & 31) * 2;
+        sA[r * SPAD + c2] = va[u].x; sA[r * SPAD + c2 + 1] = va[u].y;
+        sB[r * SPAD + c2] = vb[u].x; sB[r * SPAD + c2 + 1] = vb[u].y;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k0 = 0; k0 < NB; k0 += 4) {
+      double fa[4], fb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) fa[a] = sA[(wr + 8 * a + g) * SPAD + k0 + tgi];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) fb[b] = sB[(wc + 8 * b + g) * SPAD + k0 + tgi];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+    }
+  }
+  double* C = A + (size_t)tg.x * NB * ld + (size_t)tg.y * NB;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = wr + 8 * a + g, c = wc + 8 * b + 2 * tgi;
+      double2* p = reinterpret_cast<double2*>(C + (size_t)r * ld + c);
+      double2 v = *p;
+      v.x -= acc[a][b][0]; v.y -= acc[a][b][1];
+      *p = v;
+    }
 }
 
-// backward solve L^T x = y, right-looking over panels j = Tn-1 .. 0. y lives in `x` (in/out).
-// x_j = L_jj^-T y_j is a 64x64 mat-vec with the stored (L_jj^-1)^T (no substitution chain); CTA 0
-// publishes x_j, CTA 1+m applies y_k -= L_jk^T x_j for the m-th non-zero tile (j,k), k < j.
-__global__ void __launch_bounds__(NB) backsolve_panel_kernel(const double* __restrict__ A, int ld, int j, const int* __restrict__ cols,
-                                                             const double* __restrict__ LinvT, double* __restrict__ x,
-                                                             double* __restrict__ xout) {
-  __shared__ double sy[NB];
-  __shared__ double sx[NB];
-  sy[threadIdx.x] = x[j * NB + threadIdx.x];
-  __syncthreads();
-  {
-    // x_c = sum_r (L^-1)[r][c] y_r : thread c walks column c, rows are contiguous across threads (coalesced)
-    const double* M = LinvT + (size_t)j * NB * NB;
-    double t0 = 0.0, t1 = 0.0;
+// backward solve L^T x = y by waves in reverse order, gather form: for panel j of the wave
+//   t = y_j - sum_{i > j, L_ij != 0} L_ij^T x_i   (x_i final: they belong to later waves)      x_j = L_jj^-T t
+// x holds y on entry and is overwritten panel by panel. One CTA (64 threads = columns) per panel.
+__global__ void __launch_bounds__(256) backsolve_wave_kernel(const double* __restrict__ A, int ld, const int* __restrict__ panels,
+                                                             const int* __restrict__ below_ptr, const int* __restrict__ below,
+                                                             const double* __restrict__ Linv, double* __restrict__ x) {
+  // 256 threads = 4 groups x 64 columns; group g takes the tiles e = g (mod 4) of the list, partial sums meet in smem
+  __shared__ double sx[4][NB];
+  __shared__ double st[4][NB];
+  __shared__ double stt[NB];
+  const int j = panels[blockIdx.x];
+  const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+  double t0 = 0.0, t1 = 0.0;
+  const int e0 = below_ptr[blockIdx.x], e1 = below_ptr[blockIdx.x + 1];
+  for (int e = e0 + g; e < e1; e += 4) {
+    const int i = below[e];
+    sx[g][c] = x[i * NB + c];
+    __syncwarp();                                  // a group is 2 warps: make the tile's x visible with a named barrier
+    asm volatile("bar.sync %0, 64;" ::"r"(g + 1));
+    const double* Lij = A + (size_t)i * NB * ld + (size_t)j * NB + c;
 #pragma unroll 8
     for (int r = 0; r < NB; r += 2) {
-      t0 += M[r * NB + threadIdx.x] * sy[r];
-      t1 += M[(r + 1) * NB + threadIdx.x] * sy[r + 1];
+      t0 -= Lij[(size_t)r * ld] * sx[g][r];
+      t1 -= Lij[(size_t)(r + 1) * ld] * sx[g][r + 1];
     }
-    sx[threadIdx.x] = t0 + t1;
+    asm volatile("bar.sync %0, 64;" ::"r"(g + 1));  // everyone done with sx[g] before it is overwritten
   }
+  st[g][c] = t0 + t1;
   __syncthreads();
-  if (blockIdx.x == 0) { xout[j * NB + threadIdx.x] = sx[threadIdx.x]; return; }
-  const int k = cols[blockIdx.x - 1];
-  // t[col] = sum_r L_jk[r][col] * x_j[r]; thread = col -> coalesced row reads
-  const double* Ljk = A + (size_t)j * NB * ld + (size_t)k * NB;
-  double t0 = 0.0, t1 = 0.0;
+  if (g == 0) stt[c] = x[j * NB + c] + ((st[0][c] + st[1][c]) + (st[2][c] + st[3][c]));
+  __syncthreads();
+  // x_c = sum_r (L^-1)[r][c] t_r, rows split over the 4 groups
+  const double* M = Linv + (size_t)j * NB * NB;
+  double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
-  for (int r = 0; r < NB; r += 2) {
-    t0 += Ljk[(size_t)r * ld + threadIdx.x] * sx[r];
-    t1 += Ljk[(size_t)(r + 1) * ld + threadIdx.x] * sx[r + 1];
+  for (int r = 16 * g; r < 16 * g + 16; r += 2) {
+    a0 += M[r * NB + c] * stt[r];
+    a1 += M[(r + 1) * NB + c] * stt[r + 1];
   }
-  x[k * NB + threadIdx.x] -= t0 + t1;
+  st[g][c] = a0 + a1;
+  __syncthreads();
+  if (g == 0) x[j * NB + c] = (st[0][c] + st[1][c]) + (st[2][c] + st[3][c]);
 }
 
 __global__ void copy_row_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
@@ -267,6 +334,10 @@ int chol_workspace_dims(int n, int* ld, int* rows) {
 }
 
 // tile_nz: Tn x Tn row-major flags of the lower-triangular tile pattern of S (diagonal always set).
+// Besides the fill pattern this computes a LEVEL SCHEDULE of the tile elimination DAG: panel j can start once every
+// panel k < j with L[j][k] != 0 is finished; panels of one wave are mutually independent, so a wave is three
+// launches (factor+solve, update, and later the backward solve) however many panels it holds. With the nested-
+// dissection camera order chosen by the solver a banded problem needs ~15 waves instead of T = 47 panel steps.
 int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, CholSymbolic* sym) {
   int ld, rows;
   const int Tn = chol_workspace_dims(n, &ld, &rows);
@@ -276,63 +347,92 @@ int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, Ch
   for (int i = 0; i < Tn; ++i)
     for (int k = 0; k <= i; ++k) P[(size_t)i * T1 + k] = (i == k) || tile_nz[(size_t)i * Tn + k];
   for (int k = 0; k < Tn; ++k) P[(size_t)Tn * T1 + k] = 1;
-  std::vector<int> rows_h, rows_ptr(Tn + 1, 0), cols_h, cols_ptr(Tn + 1, 0), pairs_ptr(Tn + 1, 0);
-  std::vector<int2> pairs_h;
-  std::vector<int> nzrows;
-  long long flop_tiles = 0;
+  // symbolic factorisation (fill)
+  std::vector<std::vector<int>> below(Tn);
   for (int j = 0; j < Tn; ++j) {
-    nzrows.clear();
-    for (int i = j + 1; i < T1; ++i) if (P[(size_t)i * T1 + j]) nzrows.push_back(i);
-    for (int i : nzrows) rows_h.push_back(i);
-    rows_ptr[j + 1] = (int)rows_h.size();
-    for (size_t a = 0; a < nzrows.size(); ++a)
-      for (size_t b = 0; b <= a; ++b) {
-        const int i = nzrows[a], k = nzrows[b];
-        if (i == Tn && k == Tn) continue;  // (b row, b row) is never read
-        P[(size_t)i * T1 + k] = 1;         // fill
-        pairs_h.push_back(make_int2(i, k));
-      }
-    pairs_ptr[j + 1] = (int)pairs_h.size();
-    flop_tiles += (long long)(pairs_ptr[j + 1] - pairs_ptr[j]);
+    std::vector<int>& nz = below[j];
+    for (int i = j + 1; i < T1; ++i) if (P[(size_t)i * T1 + j]) nz.push_back(i);
+    for (size_t a = 0; a < nz.size(); ++a)
+      for (size_t b = 0; b <= a; ++b) P[(size_t)nz[a] * T1 + nz[b]] = 1;
   }
-  // backward solve: for panel j the non-zero tiles (j,k), k < j of the FACTOR
+  // level schedule
+  std::vector<int> wave(Tn, 0);
+  int nwaves = 0;
   for (int j = 0; j < Tn; ++j) {
-    for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) cols_h.push_back(k);
-    cols_ptr[j + 1] = (int)cols_h.size();
+    int w = 0;
+    for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, wave[k] + 1);
+    wave[j] = w; nwaves = std::max(nwaves, w + 1);
   }
-  sym->rows_ptr = rows_ptr; sym->pairs_ptr = pairs_ptr; sym->cols_ptr = cols_ptr;
-  sym->gemm_tiles = flop_tiles;
+  sym->nwaves = nwaves;
+  std::vector<std::vector<int>> wave_panels(nwaves);
+  for (int j = 0; j < Tn; ++j) wave_panels[wave[j]].push_back(j);
+  std::vector<int2> items, targets; std::vector<int> src_ptr, src, panels, below_ptr, below_l;
+  sym->item_ptr.assign(nwaves + 1, 0); sym->target_ptr.assign(nwaves + 1, 0); sym->panel_ptr.assign(nwaves + 1, 0);
+  src_ptr.push_back(0); below_ptr.push_back(0);
+  long long gemm_tiles = 0;
+  std::vector<int> tgt_index((size_t)T1 * T1, -1);
+  for (int w = 0; w < nwaves; ++w) {
+    const size_t t_begin = targets.size();
+    std::vector<std::vector<int>> tsrc;
+    for (int j : wave_panels[w]) {
+      items.push_back(make_int2(j, -1));
+      for (int i : below[j]) items.push_back(make_int2(j, i));
+      const std::vector<int>& nz = below[j];
+      for (size_t a = 0; a < nz.size(); ++a)
+        for (size_t b = 0; b <= a; ++b) {
+          const int i = nz[a], k = nz[b];
+          if (i == Tn && k == Tn) continue;   // (b row, b row) is never read
+          int& ti = tgt_index[(size_t)i * T1 + k];
+          if (ti < (int)t_begin) { ti = (int)targets.size(); targets.push_back(make_int2(i, k)); tsrc.emplace_back(); }
+          tsrc[ti - t_begin].push_back(j);
+          ++gemm_tiles;
+        }
+      // backward solve: tiles (i, j) of the factor below the diagonal, excluding the b row
+      panels.push_back(j);
+      for (int i : below[j]) if (i < Tn) below_l.push_back(i);
+      below_ptr.push_back((int)below_l.size());
+    }
+    for (auto& v : tsrc) { for (int j : v) src.push_back(j); src_ptr.push_back((int)src.size()); }
+    for (size_t t = t_begin; t < targets.size(); ++t) tgt_index[(size_t)targets[t].x * T1 + targets[t].y] = -1;
+    sym->item_ptr[w + 1] = (int)items.size(); sym->target_ptr[w + 1] = (int)targets.size(); sym->panel_ptr[w + 1] = (int)panels.size();
+  }
+  sym->gemm_tiles = gemm_tiles;
   cudaStream_t s = ctx->stream;
-  TSL_CUDA(sym->rows.upload(rows_h.data(), rows_h.size(), s));
-  TSL_CUDA(sym->pairs.upload(pairs_h.data(), pairs_h.size(), s));
-  TSL_CUDA(sym->cols.upload(cols_h.data(), cols_h.size(), s));
+  TSL_CUDA(sym->items.upload(items.data(), items.size(), s));
+  TSL_CUDA(sym->targets.upload(targets.data(), targets.size(), s));
+  TSL_CUDA(sym->src_ptr.upload(src_ptr.data(), src_ptr.size(), s));
+  TSL_CUDA(sym->src.upload(src.data(), src.size(), s));
+  TSL_CUDA(sym->panels.upload(panels.data(), panels.size(), s));
+  TSL_CUDA(sym->below_ptr.upload(below_ptr.data(), below_ptr.size(), s));
+  TSL_CUDA(sym->below.upload(below_l.data(), below_l.size(), s));
   TSL_CUDA(sym->Ldiag.reserve((size_t)(Tn ? Tn : 1) * NB * NB));
   TSL_CUDA(cudaStreamSynchronize(s));
   return TSLAM_OK;
 }
 
-// Factor + solve. A: (Tn+1)*64 x ld as described above. ywork: ld doubles scratch. xout: ld doubles.
+// Factor + solve. A: (Tn+1)*64 x ld as described above. xout: ld doubles (receives y, then x).
 int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail) {
+  (void)ywork;
   int ld, rows;
   const int Tn = chol_workspace_dims(sym.n, &ld, &rows);
   static bool attr_set = false;
   const int smem = 2 * NB * SPAD * (int)sizeof(double);
   if (!attr_set) {
-    TSL_CUDA(cudaFuncSetAttribute(syrk_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TSL_CUDA(cudaFuncSetAttribute(syrk_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   cudaStream_t s = ctx->stream;
-  for (int j = 0; j < Tn; ++j) {
-    const int nrows = sym.rows_ptr[j + 1] - sym.rows_ptr[j];
-    const int npairs = sym.pairs_ptr[j + 1] - sym.pairs_ptr[j];
-    LAUNCH(potrf_trsm_kernel<<<1 + nrows, NB, 0, s>>>(A, ld, j, sym.rows.p + sym.rows_ptr[j], d_fail, sym.Ldiag.p));
-    if (npairs > 0) LAUNCH(syrk_pairs_kernel<<<npairs, 128, smem, s>>>(A, ld, j, sym.pairs.p + sym.pairs_ptr[j]));
+  for (int w = 0; w < sym.nwaves; ++w) {
+    const int ni = sym.item_ptr[w + 1] - sym.item_ptr[w], nt = sym.target_ptr[w + 1] - sym.target_ptr[w];
+    LAUNCH(potrf_trsm_kernel<<<ni, NB, 0, s>>>(A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+    if (nt > 0) LAUNCH(syrk_wave_kernel<<<nt, 128, smem, s>>>(A, ld, sym.targets.p + sym.target_ptr[w], sym.src_ptr.p + sym.target_ptr[w], sym.src.p));
   }
   TSL_CHECK_LAUNCH();
-  LAUNCH(copy_row_kernel<<<(ld + 255) / 256, 256, 0, s>>>(A + (size_t)Tn * NB * ld, ywork, ld));
-  for (int j = Tn - 1; j >= 0; --j) {
-    const int ncols = sym.cols_ptr[j + 1] - sym.cols_ptr[j];
-    LAUNCH(backsolve_panel_kernel<<<1 + ncols, NB, 0, s>>>(A, ld, j, sym.cols.p + sym.cols_ptr[j], sym.Ldiag.p, ywork, xout));
+  LAUNCH(copy_row_kernel<<<(ld + 255) / 256, 256, 0, s>>>(A + (size_t)Tn * NB * ld, xout, ld));
+  for (int w = sym.nwaves - 1; w >= 0; --w) {
+    const int np = sym.panel_ptr[w + 1] - sym.panel_ptr[w];
+    LAUNCH(backsolve_wave_kernel<<<np, 256, 0, s>>>(A, ld, sym.panels.p + sym.panel_ptr[w], sym.below_ptr.p + sym.panel_ptr[w], sym.below.p,
+                                                    sym.Ldiag.p, xout));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;

@@ -5,13 +5,14 @@
 namespace tsl {
 
 // chol.cu
-struct CholSymbolic {  // tile-level symbolic factorisation (per problem structure)
-  int Tn = 0, n = 0;
-  std::vector<int> rows_ptr, pairs_ptr, cols_ptr;  // per panel ranges into the device lists
-  DevBuf<int> rows, cols;
-  DevBuf<int2> pairs;
-  mutable DevBuf<double> Ldiag;                    // Tn factored diagonal tiles (64x64, tight)
-  long long gemm_tiles = 0;                        // number of 64x64x64 tile updates (2*64^3 flop each)
+struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (per problem structure)
+  int Tn = 0, n = 0, nwaves = 0;
+  std::vector<int> item_ptr, target_ptr, panel_ptr;   // per wave ranges into the device lists
+  DevBuf<int2> items, targets;                        // (panel, row tile | -1), (target tile i, k)
+  DevBuf<int> src_ptr, src;                           // per target: source panels of its wave
+  DevBuf<int> panels, below_ptr, below;               // backward solve: panels per wave and their non-zero tiles below
+  mutable DevBuf<double> Ldiag;                       // Tn inverse diagonal factors L_jj^-1 (64x64, tight)
+  long long gemm_tiles = 0;                           // number of 64x64x64 tile updates (2*64^3 flop each)
 };
 int chol_workspace_dims(int n, int* ld, int* rows);
 int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, CholSymbolic* sym);
