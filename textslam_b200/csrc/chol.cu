@@ -32,29 +32,35 @@ constexpr int NB = 64;
 constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4 fragment loads
 
 // ---------------------------------------------------------------------------------------------
-// device tile routines (potrf / trsm / invert: 64 threads; gemm: 128 threads)
+// device tile routines for the 64x64 diagonal tile (CTA = 128 threads, tile and right-hand side in shared memory).
+// The factorisation is recursive over 32x32 blocks: the sequential part (32-column Crout / substitution with the
+// row held in registers, fully unrolled) exists ONCE as a __noinline__ function and is called twice, the coupling
+// between the halves is a small register-tiled GEMM. A flat 64-column unrolled version measured 64 us per launch
+// because 3 x 2016 FMAs of straight-line code miss the instruction cache (profiles/r1_notes.md).
 // ---------------------------------------------------------------------------------------------
+constexpr int HB = 32;             // half block
+constexpr int LDT = NB + 1;        // smem leading dimension (doubles)
+constexpr int PT_THREADS = 128;    // CTA size of potrf_trsm_kernel
 
-// Crout Cholesky of a 64x64 tile: thread r (< 64) owns row r in registers; finished rows are
-// published to shared memory so that the dot products read row c as a broadcast.
-// sinv[c] = 1 / L[c][c] (kept for the TRSM / inverse so that no FP64 division sits on a critical path).
-__device__ __forceinline__ void potrf_tile(const double* __restrict__ Ajj, int ld, double* __restrict__ dst /*64x64 tight or null*/,
-                                           double (*sL)[NB + 1], double* sinv, int* fail) {
+// Crout Cholesky of the 32x32 block at M (lower, in place). Threads 0..31 own one row each (registers); finished
+// entries are published to M so that row c is read as a broadcast. sinv[c] = 1 / L[c][c]. All CTA threads call it.
+__device__ __noinline__ void potrf32(double* M, double* sinv, int* fail) {
   const int r = threadIdx.x;
-  double row[NB];
+  const bool owner = r < HB;
+  double row[HB];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) row[c] = (r < NB && c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
+  for (int c = 0; c < HB; ++c) row[c] = (owner && c <= r) ? M[r * LDT + c] : 0.0;
 #pragma unroll
-  for (int c = 0; c < NB; ++c) {
+  for (int c = 0; c < HB; ++c) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (r < NB && r >= c) {
+    if (owner && r >= c) {
 #pragma unroll
       for (int k = 0; k + 3 < c; k += 4) {
-        s0 += row[k] * sL[c][k]; s1 += row[k + 1] * sL[c][k + 1];
-        s2 += row[k + 2] * sL[c][k + 2]; s3 += row[k + 3] * sL[c][k + 3];
+        s0 += row[k] * M[c * LDT + k]; s1 += row[k + 1] * M[c * LDT + k + 1];
+        s2 += row[k + 2] * M[c * LDT + k + 2]; s3 += row[k + 3] * M[c * LDT + k + 3];
       }
 #pragma unroll
-      for (int k = c & ~3; k < c; ++k) s0 += row[k] * sL[c][k];
+      for (int k = c & ~3; k < c; ++k) s0 += row[k] * M[c * LDT + k];
     }
     const double s = row[c] - ((s0 + s1) + (s2 + s3));
     if (r == c) {
@@ -62,70 +68,87 @@ __device__ __forceinline__ void potrf_tile(const double* __restrict__ Ajj, int l
       sinv[c] = (s > 0.0) ? rsqrt(s) : 1.0;
     }
     __syncthreads();
-    if (r < NB && r >= c) {
-      const double inv = sinv[c];
-      row[c] = s * inv;   // diagonal: s * rsqrt(s) = sqrt(s)
-      sL[r][c] = row[c];
-    }
+    if (owner && r >= c) { row[c] = s * sinv[c]; M[r * LDT + c] = row[c]; }   // diagonal: s * rsqrt(s) = sqrt(s)
     __syncthreads();
-  }
-  if (dst && r < NB) {
-#pragma unroll
-    for (int c = 0; c < NB; ++c) dst[r * NB + c] = (c <= r) ? row[c] : 0.0;
   }
 }
 
-// X L^T = A for one 64-row tile; sL holds L (lower, row-major). Thread r < 64 owns one row.
-__device__ __forceinline__ void trsm_tile(double* __restrict__ Aij, int ld, const double (*sL)[NB + 1], const double* sinv) {
+// X L^T = B for `nrows` (<= 64) rows and a 32x32 lower block L (both in shared memory, in place on X).
+// Thread r owns row r in registers; rows are independent, no barrier inside.
+__device__ __noinline__ void trsm32(double* X, int nrows, const double* L, const double* sinv) {
   const int r = threadIdx.x;
-  if (r >= NB) return;
-  double* rowp = Aij + (size_t)r * ld;
-  double x[NB];
+  if (r >= nrows) return;
+  double x[HB];
 #pragma unroll
-  for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(rowp + c); x[c] = v.x; x[c + 1] = v.y; }
+  for (int c = 0; c < HB; ++c) x[c] = X[r * LDT + c];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) {
+  for (int c = 0; c < HB; ++c) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int k = 0; k + 3 < c; k += 4) {
-      s0 += x[k] * sL[c][k]; s1 += x[k + 1] * sL[c][k + 1];
-      s2 += x[k + 2] * sL[c][k + 2]; s3 += x[k + 3] * sL[c][k + 3];
+      s0 += x[k] * L[c * LDT + k]; s1 += x[k + 1] * L[c * LDT + k + 1];
+      s2 += x[k + 2] * L[c * LDT + k + 2]; s3 += x[k + 3] * L[c * LDT + k + 3];
     }
 #pragma unroll
-    for (int k = c & ~3; k < c; ++k) s0 += x[k] * sL[c][k];
+    for (int k = c & ~3; k < c; ++k) s0 += x[k] * L[c * LDT + k];
     x[c] = (x[c] - ((s0 + s1) + (s2 + s3))) * sinv[c];
   }
 #pragma unroll
-  for (int c = 0; c < NB; c += 2) *reinterpret_cast<double2*>(rowp + c) = make_double2(x[c], x[c + 1]);
+  for (int c = 0; c < HB; ++c) X[r * LDT + c] = x[c];
 }
 
-// L^-1 tile: thread c (< 64) solves L z = e_c and stores column c: dst[r*64 + c] = (L^-1)[r][c]
-__device__ __forceinline__ void invert_tile(const double (*sL)[NB + 1], const double* sinv, double* __restrict__ dst) {
-  const int c = threadIdx.x;
-  if (c >= NB) return;
-  double z[NB];
+// C[m x 32] -= A[m x 32] B[32 x 32]^T, everything in shared memory (ld LDT), 4x4 register tiles, m in {32, 64}.
+__device__ __noinline__ void gemm_nt32(double* C, const double* A, const double* B, int m) {
+  const int nb = (m / 4) * (HB / 4);
+  for (int blk = threadIdx.x; blk < nb; blk += PT_THREADS) {
+    const int bi = blk / (HB / 4), bj = blk - bi * (HB / 4);
+    const double* a = A + 4 * bi * LDT; const double* b = B + 4 * bj * LDT;
+    double acc[4][4];
 #pragma unroll
-  for (int r = 0; r < NB; ++r) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k + 3 < r; k += 4) {
-      s0 += sL[r][k] * z[k]; s1 += sL[r][k + 1] * z[k + 1];
-      s2 += sL[r][k + 2] * z[k + 2]; s3 += sL[r][k + 3] * z[k + 3];
+      for (int jj = 0; jj < 4; ++jj) acc[i][jj] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < HB; ++k) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = a[i * LDT + k]; bv[i] = b[i * LDT + k]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] += av[i] * bv[jj];
     }
+    double cv[4][4];
 #pragma unroll
-    for (int k = r & ~3; k < r; ++k) s0 += sL[r][k] * z[k];
-    // rows above the unit entry are exactly zero (z_k = 0 for k < c), so the sums vanish there
-    z[r] = (r < c) ? 0.0 : (((r == c) ? 1.0 : 0.0) - ((s0 + s1) + (s2 + s3))) * sinv[r];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) cv[i][jj] = C[(4 * bi + i) * LDT + 4 * bj + jj];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) C[(4 * bi + i) * LDT + 4 * bj + jj] = cv[i][jj] - acc[i][jj];
   }
-#pragma unroll
-  for (int r = 0; r < NB; ++r) dst[r * NB + c] = z[r];  // plain L^-1, row-major: coalesced over threads
 }
 
-__device__ __forceinline__ void load_L_tile(const double* __restrict__ Ljj, int ld, double (*sL)[NB + 1]) {
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e >> 6, c = e & 63;
-    sL[r][c] = (c <= r) ? Ljj[(size_t)r * ld + c] : 0.0;
-  }
+// 64x64 Cholesky in place on sT (lower):  L11 = chol(A11); L21 = A21 L11^-T; A22 -= L21 L21^T; L22 = chol(A22)
+__device__ __forceinline__ void potrf_tile(double* sT, double* sinv, int* fail) {
+  potrf32(sT, sinv, fail);
+  trsm32(sT + HB * LDT, HB, sT, sinv);
+  __syncthreads();
+  gemm_nt32(sT + HB * LDT + HB, sT + HB * LDT, sT + HB * LDT, HB);
+  __syncthreads();
+  potrf32(sT + HB * LDT + HB, sinv + HB, fail);
+}
+
+// X L^T = B for a 64-row tile sX (in place) against the factored sT:
+//   X1 = B1 L11^-T ;  B2 -= X1 L21^T ;  X2 = B2 L22^-T
+__device__ __forceinline__ void trsm_tile(double* sX, const double* sT, const double* sinv) {
+  trsm32(sX, NB, sT, sinv);
+  __syncthreads();
+  gemm_nt32(sX + HB, sX, sT + HB * LDT, NB);
+  __syncthreads();
+  trsm32(sX + HB, NB, sT + HB * LDT + HB, sinv + HB);
+  __syncthreads();
 }
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -194,20 +217,43 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, cons
 // the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
 // this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
-__global__ void __launch_bounds__(NB) potrf_trsm_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
-                                                        int* __restrict__ fail, double* __restrict__ LinvT) {
-  // one CTA per (panel j, row tile i) item of the current wave; i < 0 marks the CTA that stores L_jj^-1
-  __shared__ double sL[NB][NB + 1];
+__global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
+                                                                int* __restrict__ fail, double* __restrict__ Linv) {
+  // one CTA per (panel j, row tile i) item of the current wave; i < 0 marks the CTA that stores L_jj^-1.
+  // Every CTA factors the (small) diagonal tile redundantly straight from A: nobody writes A_jj in this launch.
+  extern __shared__ double smem[];
+  double* sT = smem;                 // 64 x LDT: diagonal tile -> L_jj
+  double* sX = smem + NB * LDT;      // 64 x LDT: row tile, or identity -> L_jj^-T
   __shared__ double sinv[NB];
   const int2 it = items[blockIdx.x];
   const int j = it.x;
   const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
-  potrf_tile(Ajj, ld, nullptr, sL, sinv, fail);
-  if (it.y < 0) {  // off the critical path: L_jj^-1 for the backward solve
-    invert_tile(sL, sinv, LinvT + (size_t)j * NB * NB);
+  double* Aij = it.y < 0 ? nullptr : A + (size_t)it.y * NB * ld + (size_t)j * NB;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {   // all global loads of a batch are issued before the first shared-memory store
+    double vt[16], vx[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = threadIdx.x + PT_THREADS * (16 * half + u), r = e >> 6, c = e & 63;
+      vt[u] = (c <= r) ? Ajj[(size_t)r * ld + c] : 0.0;
+      vx[u] = Aij ? Aij[(size_t)r * ld + c] : ((r == c) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = threadIdx.x + PT_THREADS * (16 * half + u), r = e >> 6, c = e & 63;
+      sT[r * LDT + c] = vt[u]; sX[r * LDT + c] = vx[u];
+    }
+  }
+  __syncthreads();
+  potrf_tile(sT, sinv, fail);
+  __syncthreads();
+  trsm_tile(sX, sT, sinv);             // row tile: X = A_ij L^-T ;  identity: X = L^-T
+  if (!Aij) {                          // off the critical path: store L_jj^-1 = X^T (row-major) for the backward solve
+    double* dst = Linv + (size_t)j * NB * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; dst[e] = sX[c * LDT + r]; }
     return;
   }
-  trsm_tile(A + (size_t)it.y * NB * ld + (size_t)j * NB, ld, sL, sinv);
+  for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; Aij[(size_t)r * ld + c] = sX[r * LDT + c]; }
 }
 
 // trailing update of one wave: one CTA per target tile (i,k); it sums the contributions X_i^(j) X_k^(j)^T of every
@@ -417,14 +463,16 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   const int Tn = chol_workspace_dims(sym.n, &ld, &rows);
   static bool attr_set = false;
   const int smem = 2 * NB * SPAD * (int)sizeof(double);
+  const int smem_pt = 2 * NB * LDT * (int)sizeof(double);
   if (!attr_set) {
     TSL_CUDA(cudaFuncSetAttribute(syrk_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
     attr_set = true;
   }
   cudaStream_t s = ctx->stream;
   for (int w = 0; w < sym.nwaves; ++w) {
     const int ni = sym.item_ptr[w + 1] - sym.item_ptr[w], nt = sym.target_ptr[w + 1] - sym.target_ptr[w];
-    LAUNCH(potrf_trsm_kernel<<<ni, NB, 0, s>>>(A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+    LAUNCH(potrf_trsm_kernel<<<ni, PT_THREADS, smem_pt, s>>>(A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
     if (nt > 0) LAUNCH(syrk_wave_kernel<<<nt, 128, smem, s>>>(A, ld, sym.targets.p + sym.target_ptr[w], sym.src_ptr.p + sym.target_ptr[w], sym.src.p));
   }
   TSL_CHECK_LAUNCH();
