@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 GLOBAL_BA_ITERS = 20  # src/optimizer.cc:411-414
 POINT_EVAL_BYTES = 268  # 44 B in + 224 B out per auto_BAScene(NW) evaluation
+# dram__bytes_read.sum + dram__bytes_write.sum of one x16 launch from the committed ncu --set full capture
+# (profiles/r1_ncu_point_eval_x16.txt: 76.1 MB + 298.2 MB; part of the 358 MB output is still in L2 at kernel end)
+NCU_TRAFFIC_X16 = 374.3e6
 WORKLOAD = "C5 global BA: 500 KF x 100k auto_BASceneNW obs (25k landmarks x 4 obs, band +-10, text off as src/optimizer.cc:1707), <=20 LM its"
 
 
@@ -188,7 +191,7 @@ def main():
     line = {"metric": "ba_resjac_mevals_per_s", "value": value, "unit": "M-evals/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "every step rewrites >126 MB (71 MB dense reduced matrix memset + factor, 21 MB J) between passes over the inputs",
+            "config": {"workload": WORKLOAD, "l2": "each LM iteration rewrites the 71 MB dense reduced matrix + 21 MB of J between passes over the inputs; the stand-alone kernel timings flush L2 or exceed it (see roofline)",
                        "landmark_sharding": f"landmark % {world}" if world > 1 else "none"},
             "lm_iter_ms": dev_ms / max(1, its), "lm_iterations_per_step": its / K, "wall_ms_per_step": wall_ms / K,
             "gpu_launches": int(launches), "clocks": clk}
@@ -196,22 +199,30 @@ def main():
     line["lm_phase_ms_per_iter"] = {n: float(phases_acc[i] / max(1, its)) for i, n in enumerate(phase_names)}
 
     if rank == 0 and not args.no_extras and world == 1:
-        # ---- the residual+Jacobian kernel alone (north_star roofline target), inputs in HBM, L2 flushed between launches
-        ms = dev.eval_points(T.PT_BA_NW, reps=20, flush_l2=True)
-        ach = POINT_EVAL_BYTES * prob.n_pobs / (ms * 1e-3) / 1e9
-        line["roofline"] = {"kernel": "point_eval_kernel<0,13,J,plain> (auto_BASceneNW residual+Jacobian), C5 = 100k evals/launch",
-                            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                            "traffic": None, "peak_source": peak_src, "ms_per_launch": ms,
-                            "mevals_per_s": prob.n_pobs / (ms * 1e-3) / 1e6}
+        # ---- the residual+Jacobian kernel alone (north_star roofline target), inputs resident in HBM.
+        # Primary roofline: a launch whose footprint (429 MB) exceeds L2 (C5 x16 replica, same structure); the C5-sized
+        # launch (26.8 MB, L2 flushed with a write+read sweep of 2x L2 between launches) is reported beside it.
         big = synth.make_ba_problem(seed=1, n_kf=500, n_lm=400000, obs_per_lm=4, band=10, fixed_cams=(0, 1), w_point=1.0, perturb=False)
         dbig = ctx.upload(big)
         dbig.eval_points(T.PT_BA_NW, reps=3)
         msb = dbig.eval_points(T.PT_BA_NW, reps=10, flush_l2=True)
         achb = POINT_EVAL_BYTES * big.n_pobs / (msb * 1e-3) / 1e9
-        line["roofline_x16"] = {"kernel": "same kernel, C5 x16 replica (1.6M evals/launch, 429 MB > L2)", "bound": "hbm", "achieved": achb,
-                                "peak": hbm_peak, "unit": "GB/s", "frac": achb / hbm_peak, "ms_per_launch": msb,
-                                "mevals_per_s": big.n_pobs / (msb * 1e-3) / 1e6}
+        line["roofline"] = {"kernel": "point_eval_kernel<0,13,J> (auto_BASceneNW residual+Jacobian), C5 x16 replica = 1.6M evals / launch (429 MB > L2)",
+                            "bound": "hbm", "achieved": achb, "peak": hbm_peak, "unit": "GB/s", "frac": achb / hbm_peak,
+                            "traffic": NCU_TRAFFIC_X16, "peak_source": peak_src, "ms_per_launch": msb,
+                            "mevals_per_s": big.n_pobs / (msb * 1e-3) / 1e6,
+                            "algorithmic_bytes_per_launch": POINT_EVAL_BYTES * big.n_pobs}
         dbig.free()
+        dev.eval_points(T.PT_BA_NW, reps=5, flush_l2=True)
+        ms = dev.eval_points(T.PT_BA_NW, reps=20, flush_l2=True)
+        ach = POINT_EVAL_BYTES * prob.n_pobs / (ms * 1e-3) / 1e9
+        line["roofline_c5"] = {"kernel": "same kernel at the C5 size (100k evals, 26.8 MB / launch, L2 flushed between launches)", "bound": "hbm",
+                               "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "ms_per_launch": ms,
+                               "mevals_per_s": prob.n_pobs / (ms * 1e-3) / 1e6,
+                               "note": "one partial wave (782 CTAs on 148 SMs): launch/latency bound, see DESIGN.md"}
+        line["dominant_kernel"] = {"name": "potrf_trsm_kernel (64x64 tile factor + triangular solve of the reduced camera system)",
+                                   "share_of_lm_iteration": "largest single kernel of the step (profiles/r1_launches_lm.txt)",
+                                   "bound": "latency (sequential column eliminations); FP64 tensor work of the step is syrk_wave_kernel"}
         # ---- end to end through the public C-ABI with host buffers
         e2e_t, e2e_evals = 0.0, 0
         fr_bytes = 8 * (2 * prob.n_pobs + 8 * prob.n_tobs)
@@ -236,6 +247,7 @@ def main():
         line["cpu_baseline"] = {"value": jac_evals(summ, prob) / dt / 1e6, "unit": "M-evals/s", "cores": threads, "kind": "port",
                                 "sample": "first 2 LM iterations of the same C5 solve (oracle/ba_lm.cpp)",
                                 "lm_iter_ms": 1e3 * dt / max(1, summ["iterations"])}
+        line["small_problems"] = small_problem_bench(ctx, T, synth, po, threads)
         try:
             line["orb"] = orb_bench(ctx, T, synth)
         except Exception as e:  # ORB is reported beside the BA metric; its absence must not hide the BA line
@@ -247,6 +259,24 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_problem_bench(ctx, T, synth, po, threads):
+    """C3 pose-only and C4 local BA (BASELINE.json configs 2-3): 10 LM iterations per call, host buffers, vs the oracle."""
+    out = {}
+    for name, prob in (("c3_pose_only_2k_pts_250_text", synth.c3_pose_only(seed=0)), ("c4_local_ba_10kf_3k_pts_750_text", synth.c4_local_ba(seed=0))):
+        for _ in range(2):
+            ctx.solve(prob.copy(), 10, want_trace=False)
+        t0 = time.perf_counter(); n = 10
+        for _ in range(n):
+            summ, _, _ = ctx.solve(prob.copy(), 10, want_trace=False)
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / n
+        t0 = time.perf_counter()
+        so, _, _ = po.solve(prob.copy(), 10, n_threads=1, want_trace=False)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        out[name] = {"gpu_ms_per_solve_e2e": gpu_ms, "lm_iterations": summ["iterations"], "oracle_1thread_ms_per_solve": cpu_ms,
+                     "oracle_iterations": so["iterations"]}
+    return out
 
 
 def orb_bench(ctx, T, synth):

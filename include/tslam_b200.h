@@ -200,6 +200,16 @@ int tslam_orb_debug_get(tslam_orb* h, int what, int img, int level, void* out, i
 int tslam_orb_dev_bench(tslam_orb* h, const uint8_t* const* imgs, int n_imgs, int w, int hgt, int stride,
                         int reps, float* ms_mean, int64_t* n_kp);
 
+/* ---- direct-method frame pyramid ------------------------------------------------ */
+/* Replaces frame::GetPyrMat (src/frame.cc:178-202): cv::pyrDown chain, cv::Sobel (CV_8U) in x / y, addWeighted(0.5, 0.5).
+ * what: 0 = vFrameImg[level], 1 = vFrameGrad, 2 = vFrameGradX, 3 = vFrameGradY (tight u8 planes). */
+typedef struct tslam_frame_pyr tslam_frame_pyr;
+int tslam_frame_pyr_create(tslam_ctx* ctx, int nlevels, tslam_frame_pyr** out);
+void tslam_frame_pyr_destroy(tslam_frame_pyr* p);
+int tslam_frame_pyr_build(tslam_frame_pyr* p, const uint8_t* const* imgs, int n_imgs, int w, int hgt, int stride);
+int tslam_frame_pyr_level_size(tslam_frame_pyr* p, int level, int* w, int* hgt);
+int tslam_frame_pyr_get(tslam_frame_pyr* p, int img, int level, int what, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

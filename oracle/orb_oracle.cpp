@@ -442,3 +442,57 @@ extern "C" int tso_orb_debug(const uint8_t* img, int w, int h, int nfeatures, fl
   for (int i = 0; i < n; ++i) { o[3 * i] = (int)c[sl[i]].x; o[3 * i + 1] = (int)c[sl[i]].y; o[3 * i + 2] = c[sl[i]].resp; }
   return (int)sl.size();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Direct-method frame pyramid: frame::GetPyrMat (/root/reference/src/frame.cc:178-202) —
+// cv::pyrDown chain, cv::Sobel(ddepth = CV_8U, ksize 3, BORDER_DEFAULT) in x and y, cv::addWeighted(0.5, 0.5).
+// OpenCV rules pinned against cv2 in tests/test_oracle_orb.py: pyrDown = separable
+// [1 4 6 4 1], REFLECT_101, (V + 128) >> 8, size ((w+1)/2, (h+1)/2); Sobel into CV_8U saturates (negative
+// derivatives become 0); addWeighted rounds half to even.
+// ---------------------------------------------------------------------------------------------------------
+namespace tso {
+static void pyr_down(const Img& src, Img& dst) {
+  static const int K[5] = {1, 4, 6, 4, 1};
+  for (int y = 0; y < dst.h; ++y)
+    for (int x = 0; x < dst.w; ++x) {
+      int s = 0;
+      for (int j = 0; j < 5; ++j) {
+        const uint8_t* row = src.row(reflect101(2 * y + j - 2, src.h));
+        int rs = 0;
+        for (int i = 0; i < 5; ++i) rs += K[i] * row[reflect101(2 * x + i - 2, src.w)];
+        s += K[j] * rs;
+      }
+      dst.row(y)[x] = (uint8_t)((s + 128) >> 8);
+    }
+}
+static void sobel_u8(const Img& src, Img& gx, Img& gy, Img& g) {
+  for (int y = 0; y < src.h; ++y) {
+    const uint8_t* r0 = src.row(reflect101(y - 1, src.h)); const uint8_t* r1 = src.row(y); const uint8_t* r2 = src.row(reflect101(y + 1, src.h));
+    for (int x = 0; x < src.w; ++x) {
+      const int xm = reflect101(x - 1, src.w), xp = reflect101(x + 1, src.w);
+      const int dx = (r0[xp] - r0[xm]) + 2 * (r1[xp] - r1[xm]) + (r2[xp] - r2[xm]);
+      const int dy = (r2[xm] - r0[xm]) + 2 * (r2[x] - r0[x]) + (r2[xp] - r0[xp]);
+      const int a = std::min(255, std::max(0, dx)), b = std::min(255, std::max(0, dy));
+      gx.row(y)[x] = (uint8_t)a; gy.row(y)[x] = (uint8_t)b;
+      g.row(y)[x] = (uint8_t)std::min(255, cv_round(a * 0.5 + b * 0.5));
+    }
+  }
+}
+}  // namespace tso
+
+// what: 0 image level, 1 grad (addWeighted), 2 grad_x, 3 grad_y. Returns level width * height.
+extern "C" int tso_frame_pyramid(const uint8_t* img, int w, int h, int stride, int nlevels, int level, int what, uint8_t* out, int* lw, int* lh) {
+  using namespace tso;
+  Img cur(w, h);
+  for (int y = 0; y < h; ++y) std::memcpy(cur.row(y), img + (size_t)y * stride, w);
+  for (int l = 1; l <= level; ++l) { Img nxt((cur.w + 1) / 2, (cur.h + 1) / 2); pyr_down(cur, nxt); cur = nxt; }
+  (void)nlevels;
+  *lw = cur.w; *lh = cur.h;
+  if (!out) return cur.w * cur.h;
+  if (what == 0) { std::memcpy(out, cur.d.data(), cur.d.size()); return cur.w * cur.h; }
+  Img gx(cur.w, cur.h), gy(cur.w, cur.h), g(cur.w, cur.h);
+  sobel_u8(cur, gx, gy, g);
+  const Img& o = what == 1 ? g : (what == 2 ? gx : gy);
+  std::memcpy(out, o.d.data(), o.d.size());
+  return cur.w * cur.h;
+}

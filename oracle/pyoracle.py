@@ -157,3 +157,16 @@ def orb_debug(img, what, level, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20,
     n = lib().tso_orb_debug(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(nfeatures), C.c_float(scale), C.c_int(nlevels),
                             C.c_int(ini_th), C.c_int(min_th), C.c_int(what), C.c_int(level), buf.ctypes.data_as(C.c_void_p), C.c_int(len(buf)))
     return buf[:n].copy()
+
+
+def frame_pyramid(img, level, what):
+    """frame::GetPyrMat restatement: what = 0 level image, 1 grad, 2 grad_x, 3 grad_y."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    lw, lh = C.c_int(), C.c_int()
+    lib().tso_frame_pyramid(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(8), C.c_int(level), C.c_int(what), None,
+                            C.byref(lw), C.byref(lh))
+    out = np.zeros((lh.value, lw.value), dtype=np.uint8)
+    lib().tso_frame_pyramid(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(8), C.c_int(level), C.c_int(what),
+                            out.ctypes.data_as(C.c_void_p), C.byref(lw), C.byref(lh))
+    return out

@@ -27,5 +27,12 @@ out["atan2_out"] = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in yx], 
 vals = np.concatenate([np.arange(-8, 8) + 0.5, rng.normal(0, 30, 200)])
 out["round_in"] = vals
 out["round_out"] = np.array([int(np.rint(v)) for v in vals], dtype=np.int32)  # cvRound == rint (round-half-even)
+small = img[:120, :160].copy()
+pd = cv2.pyrDown(small)
+out["n2_src"] = small
+out["n2_pyrdown"] = pd
+out["n2_sobel_x"] = cv2.Sobel(small, cv2.CV_8U, 1, 0, ksize=3, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+out["n2_sobel_y"] = cv2.Sobel(small, cv2.CV_8U, 0, 1, ksize=3, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+out["n2_grad"] = cv2.addWeighted(out["n2_sobel_x"], 0.5, out["n2_sobel_y"], 0.5, 0)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "orb_cv2_golden.npz"), **out)
 print("wrote", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})

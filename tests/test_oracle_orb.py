@@ -83,3 +83,25 @@ def test_flat_and_tiny_inputs(oracle):
     few[200:230, 300:340] = 200   # one rectangle: a handful of corners, far fewer than requested
     kp, desc = oracle.orb_extract(few)
     assert 0 < len(kp) < 200
+
+
+def test_golden_frame_pyramid(oracle):
+    src = G["n2_src"]
+    assert np.array_equal(oracle.frame_pyramid(src, 1, 0), G["n2_pyrdown"])
+    assert np.array_equal(oracle.frame_pyramid(src, 0, 2), G["n2_sobel_x"])
+    assert np.array_equal(oracle.frame_pyramid(src, 0, 3), G["n2_sobel_y"])
+    assert np.array_equal(oracle.frame_pyramid(src, 0, 1), G["n2_grad"])
+
+
+def test_live_cv2_frame_pyramid(oracle):
+    cv2 = pytest.importorskip("cv2")
+    img = synth.orb_images(seed=9, n=1, w=645, h=487)[0]
+    cur = img
+    for l in range(6):
+        if l > 0:
+            cur = cv2.pyrDown(cur)
+        assert np.array_equal(oracle.frame_pyramid(img, l, 0), cur), l
+        gx = cv2.Sobel(cur, cv2.CV_8U, 1, 0, ksize=3, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+        gy = cv2.Sobel(cur, cv2.CV_8U, 0, 1, ksize=3, scale=1, delta=0, borderType=cv2.BORDER_DEFAULT)
+        assert np.array_equal(oracle.frame_pyramid(img, l, 2), gx) and np.array_equal(oracle.frame_pyramid(img, l, 3), gy)
+        assert np.array_equal(oracle.frame_pyramid(img, l, 1), cv2.addWeighted(gx, 0.5, gy, 0.5, 0))

@@ -16,7 +16,8 @@ EXPORTS = [
     "tslam_ctx_init_comm", "tslam_shard_owner", "tslam_eval_points", "tslam_eval_text", "tslam_solve", "tslam_dev_upload", "tslam_dev_free",
     "tslam_dev_eval_points", "tslam_dev_eval_text", "tslam_dev_lm_iterations", "tslam_dev_download_eval",
     "tslam_dev_download_params", "tslam_orb_create", "tslam_orb_destroy", "tslam_orb_extract", "tslam_orb_level_size",
-    "tslam_orb_get_level", "tslam_orb_dev_bench", "tslam_orb_debug_get",
+    "tslam_orb_get_level", "tslam_orb_dev_bench", "tslam_orb_debug_get", "tslam_frame_pyr_create", "tslam_frame_pyr_destroy", "tslam_frame_pyr_build",
+    "tslam_frame_pyr_level_size", "tslam_frame_pyr_get",
 ]
 
 
@@ -33,10 +34,10 @@ def lib():
         _LIB = C.CDLL(LIB_PATH)
         _LIB.tslam_last_error.restype = C.c_char_p
         for name in EXPORTS:
-            if name not in ("tslam_last_error", "tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy"):
+            if name not in ("tslam_last_error", "tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy", "tslam_frame_pyr_destroy"):
                 getattr(_LIB, name).restype = C.c_int
         _LIB.tslam_launch_count.restype = C.c_longlong
-        for name in ("tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy"):
+        for name in ("tslam_ctx_destroy", "tslam_dev_free", "tslam_orb_destroy", "tslam_frame_pyr_destroy"):
             getattr(_LIB, name).restype = None
     return _LIB
 

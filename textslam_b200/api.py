@@ -219,3 +219,39 @@ class ORBextractor:
         check(lib().tslam_orb_dev_bench(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(reps),
                                         C.byref(ms), C.byref(nk)))
         return ms.value, nk.value
+
+
+class FramePyramid:
+    """Mirror of frame::GetPyrMat (src/frame.cc:178-202): vFrameImg / vFrameGrad / vFrameGradX / vFrameGradY per level."""
+    IMG, GRAD, GRAD_X, GRAD_Y = 0, 1, 2, 3
+
+    def __init__(self, ctx, nlevels=8):
+        self.ctx, self.nlevels = ctx, nlevels
+        self._h = C.c_void_p()
+        check(lib().tslam_frame_pyr_create(ctx._h, C.c_int(nlevels), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().tslam_frame_pyr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build(self, imgs):
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        n, h, w = imgs.shape
+        ptrs = (C.c_void_p * n)(*[imgs[i].ctypes.data for i in range(n)])
+        check(lib().tslam_frame_pyr_build(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w)))
+
+    def get(self, img, level, what=0):
+        w, h = C.c_int(), C.c_int()
+        check(lib().tslam_frame_pyr_level_size(self._h, C.c_int(level), C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), dtype=np.uint8)
+        check(lib().tslam_frame_pyr_get(self._h, C.c_int(img), C.c_int(level), C.c_int(what), out.ctypes.data_as(c_bp)))
+        return out

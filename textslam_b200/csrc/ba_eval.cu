@@ -30,8 +30,8 @@ struct PointArgs {
 };
 
 // COL0 = first tangent column exported, NCOLS = number of columns (13: BA, 6: pose, 1 @12: rho)
-template <int COL0, int NCOLS, bool WANT_J, bool ROBUST>
-__global__ void __launch_bounds__(kEvalThreads) point_eval_kernel(PointArgs a, double2* __restrict__ r_out, double* __restrict__ J_out) {
+template <int COL0, int NCOLS, bool WANT_J, bool ROBUST, int MINB = 6>
+__global__ void __launch_bounds__(kEvalThreads, MINB) point_eval_kernel(PointArgs a, double2* __restrict__ r_out, double* __restrict__ J_out) {
   constexpr int ROW = 2 * NCOLS;
   constexpr int STRIDE = (ROW % 2 == 0) ? ROW + 1 : ROW;  // odd stride in doubles: conflict-free 64-bit smem access
   __shared__ double sJ[WANT_J ? kEvalThreads * STRIDE : 1];
@@ -225,7 +225,12 @@ int launch_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, bool want
   const int grid = (d->n_pobs + kEvalThreads - 1) / kEvalThreads;
   double2* r = reinterpret_cast<double2*>(d->pr.p);
   if (!want_J) LAUNCH(point_eval_kernel<0, 13, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr));
-  else if (ncols == 13) LAUNCH(point_eval_kernel<0, 13, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+  else if (ncols == 13) {
+    // occupancy variant: 8 CTAs/SM (64 registers, ~48 B of L1-resident spills) vs 6 CTAs/SM (79 registers)
+    static const bool occ8 = getenv("TSLAM_EVAL_OCC6") == nullptr;
+    if (occ8) LAUNCH(point_eval_kernel<0, 13, true, false, 8><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+    else LAUNCH(point_eval_kernel<0, 13, true, false, 6><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+  }
   else if (ncols == 6) LAUNCH(point_eval_kernel<0, 6, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
   else LAUNCH(point_eval_kernel<12, 1, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
   TSL_CHECK_LAUNCH();
