@@ -210,6 +210,20 @@ int tslam_frame_pyr_build(tslam_frame_pyr* p, const uint8_t* const* imgs, int n_
 int tslam_frame_pyr_level_size(tslam_frame_pyr* p, int level, int* w, int* hgt);
 int tslam_frame_pyr_get(tslam_frame_pyr* p, int img, int level, int what, uint8_t* out);
 
+/* ---- plane covariance ------------------------------------------------------------- */
+/* Replaces the ceres::Covariance block of PyrThetaOptim (src/optimizer.cc:2219-2238): cov_out[n_planes x 9] =
+ * (J_theta' J_theta)^-1 per plane from its text blocks (loss-corrected Jacobian); singular blocks give zeros and are
+ * counted in *n_singular (may be NULL). */
+int tslam_theta_covariance(tslam_ctx* ctx, const tslam_ba_problem* p, int jac_mode, double* cov_out, int32_t* n_singular);
+
+/* ---- projection-guided descriptor matching core ------------------------------------ */
+/* Inner loop of tracking::SearchFrom3D* (src/tracking.cc:1161-1175,1241-1256,1310-1325) with
+ * tracking::DescriptorDistance (:2762-2778): per query the first candidate (list order) of minimum Hamming distance.
+ * Descriptors are 32 bytes; candidates in CSR form (cand_ptr[n_query+1], cand_idx into train). Empty list -> idx -1,
+ * dist INT_MAX. second_dist (may be NULL) = distance of the runner-up candidate. */
+int tslam_match_hamming(tslam_ctx* ctx, const uint8_t* query_desc, int n_query, const uint8_t* train_desc, int n_train,
+                        const int32_t* cand_ptr, const int32_t* cand_idx, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -602,3 +602,22 @@ extern "C" int tso_point_ambient(const double* cam, const double* host, double r
   return 0;
 }
 extern "C" void tso_quat_plus(const double* x, const double* d, double* out) { quat_plus(x, d, out); }
+
+// ceres::Covariance of the theta blocks (src/optimizer.cc:2219-2238): (J_theta' J_theta)^-1 per plane, loss-corrected Jacobian.
+extern "C" int tso_theta_covariance(const tslam_ba_problem* p, int jac_mode, double* cov) {
+  std::vector<double> V(9 * (size_t)p->n_planes, 0.0);
+  for (int i = 0; i < p->n_tobs; ++i) {
+    TextBlockConst c = text_const(*p, i);
+    const double* cam = p->cams + 7 * (size_t)p->t_cam[i]; const double* host = p->cams + 7 * (size_t)p->t_host[i];
+    const double* th = p->theta + 3 * (size_t)p->t_plane[i];
+    double r[8], J[120];
+    if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) text_eval_numeric(cam, host, th, c, 7u, r, J); else text_eval_analytic(cam, host, th, c, r, J);
+    double s = 0; for (int k = 0; k < 8; ++k) s += r[k] * r[k];
+    double rho[3]; huber(p->huber_text, s, rho);
+    double* Vp = &V[9 * (size_t)p->t_plane[i]];
+    for (int k = 0; k < 8; ++k) for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) Vp[3 * a + b] += rho[1] * J[15 * k + 12 + a] * J[15 * k + 12 + b];
+  }
+  int singular = 0;
+  for (int k = 0; k < p->n_planes; ++k) { if (!inv3_spd(&V[9 * (size_t)k], cov + 9 * (size_t)k)) { for (int a = 0; a < 9; ++a) cov[9 * (size_t)k + a] = 0; ++singular; } }
+  return singular;
+}

@@ -170,3 +170,28 @@ def frame_pyramid(img, level, what):
     lib().tso_frame_pyramid(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(8), C.c_int(level), C.c_int(what),
                             out.ctypes.data_as(C.c_void_p), C.byref(lw), C.byref(lh))
     return out
+
+
+def match_hamming(query_desc, train_desc, cand_ptr, cand_idx):
+    """tracking::SearchFrom3D inner loop (src/tracking.cc:1161-1175) with DescriptorDistance (:2762-2778), restated in numpy:
+    sequential scan, strict `dist < bestDist` keeps the FIRST minimum. Returns (best_idx, best_dist, second_dist)."""
+    q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train_desc, dtype=np.uint8).reshape(-1, 32)
+    nq = len(q); INT_MAX = 2147483647
+    bi = np.full(nq, -1, dtype=np.int32); bd = np.full(nq, INT_MAX, dtype=np.int32); sd = np.full(nq, INT_MAX, dtype=np.int32)
+    for i in range(nq):
+        c = np.asarray(cand_idx[cand_ptr[i]:cand_ptr[i + 1]], dtype=np.int64)
+        if len(c) == 0:
+            continue
+        d = np.unpackbits(q[i][None, :] ^ t[c], axis=1).sum(1).astype(np.int64)
+        k = int(np.argmin(d))   # first minimum
+        bi[i] = c[k]; bd[i] = d[k]
+        if len(c) > 1:
+            sd[i] = np.delete(d, k).min()
+    return bi, bd, sd
+
+
+def theta_covariance(prob, jac_mode=0):
+    cov = np.zeros((len(prob.theta), 3, 3))
+    pc = prob.as_c()
+    ns = lib().tso_theta_covariance(C.byref(pc), C.c_int(jac_mode), _dp(cov))
+    return cov, ns

@@ -137,3 +137,14 @@ def test_device_resident_lm_matches_solve(ctx, oracle):
     assert np.allclose(cams, q.cams, rtol=1e-12, atol=1e-14) and np.allclose(rho, q.rho, rtol=1e-12, atol=1e-14)
     assert phases[7] > 0
     d.free()
+
+
+def test_theta_covariance(ctx, oracle):
+    # PyrThetaOptim shape: every camera constant, planes free, no loss, unweighted (src/optimizer.cc:2170-2242)
+    prob = synth.make_ba_problem(seed=64, n_kf=5, n_lm=10, obs_per_lm=2, band=5, fixed_cams=(0, 1, 2, 3, 4), n_planes=12, w_text=1.0, huber_text=0.0)
+    ctx.solve(prob, 15)
+    cg, ng = ctx.theta_covariance(prob)
+    co, no = oracle.theta_covariance(prob)
+    assert ng == no == 0
+    assert np.allclose(cg, co, rtol=1e-8, atol=1e-300)
+    assert np.all(np.linalg.eigvalsh(cg) > 0)

@@ -74,6 +74,13 @@ class Context:
         check(lib().tslam_solve(self._h, C.byref(pc), C.byref(opt), C.byref(summ), _dp(fr), _dp(tr) if want_trace else None))
         return summ.as_dict(), fr, tr
 
+    def theta_covariance(self, prob, jac_mode=JAC_ANALYTIC):
+        """ceres::Covariance of every theta block (src/optimizer.cc:2219-2238). Returns (cov (n_planes,3,3), n_singular)."""
+        cov = np.zeros((len(prob.theta), 3, 3)); ns = C.c_int32(0)
+        pc = prob.as_c()
+        check(lib().tslam_theta_covariance(self._h, C.byref(pc), C.c_int(jac_mode), _dp(cov), C.byref(ns)))
+        return cov, ns.value
+
     # ---- device-resident handles (benchmarks) --------------------------------------------------
     def upload(self, prob):
         return DeviceProblem(self, prob)
@@ -219,6 +226,19 @@ class ORBextractor:
         check(lib().tslam_orb_dev_bench(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(reps),
                                         C.byref(ms), C.byref(nk)))
         return ms.value, nk.value
+
+
+def match_hamming(ctx, query_desc, train_desc, cand_ptr, cand_idx):
+    """Core of tracking::SearchFrom3D*: per query the first minimum-Hamming-distance candidate. Returns (idx, dist, second)."""
+    q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(train_desc, dtype=np.uint8).reshape(-1, 32)
+    cp = np.ascontiguousarray(cand_ptr, dtype=np.int32); ci = np.ascontiguousarray(cand_idx, dtype=np.int32)
+    nq = len(q)
+    bi = np.zeros(nq, dtype=np.int32); bd = np.zeros(nq, dtype=np.int32); sd = np.zeros(nq, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    check(lib().tslam_match_hamming(ctx._h, q.ctypes.data_as(c_bp), C.c_int(nq), t.ctypes.data_as(c_bp), C.c_int(len(t)), ip(cp),
+                                    ip(ci) if len(ci) else None, ip(bi), ip(bd), ip(sd)))
+    return bi, bd, sd
 
 
 class FramePyramid:
