@@ -10,4 +10,5 @@ python tools/prof_orb.py 64
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_lm_$R.csv python tools/prof_lm.py 2 > gpurun_out/prof_lm.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_orb_$R.csv python tools/prof_orb.py 64 > gpurun_out/prof_orb.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:point_eval_kernel -s 0 -c 2 -o gpurun_out/prof_point_eval_x16_$R -f python tools/prof_eval_x16.py > gpurun_out/prof_eval_x16.log 2>&1
+python tools/prof_eval_x16.py 2>&1 | tail -1; TSLAM_EVAL_OCC6=1 python tools/prof_eval_x16.py 2>&1 | tail -1
 ls -la gpurun_out
