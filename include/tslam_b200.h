@@ -210,6 +210,13 @@ int tslam_frame_pyr_build(tslam_frame_pyr* p, const uint8_t* const* imgs, int n_
 int tslam_frame_pyr_level_size(tslam_frame_pyr* p, int level, int* w, int* hgt);
 int tslam_frame_pyr_get(tslam_frame_pyr* p, int img, int level, int what, uint8_t* out);
 
+/* ---- mu / sigma of projected text quads ------------------------------------------- */
+/* Replaces tool::CalTextinfo + CalStatistics (src/tool.cc:1178-1262) for a batch of quads: quads = n_quads x 8 doubles
+ * (x0 y0 .. x3 y3, image pixels, the projected text box), quad_img = image index of each quad, imgs = n_imgs x h x w u8.
+ * ok_out[i] = the function's bool result (0: empty mask or sigma == 0). */
+int tslam_text_info(tslam_ctx* ctx, const uint8_t* imgs, int n_imgs, int w, int h, const double* quads, const int32_t* quad_img, int n_quads,
+                    double* mu_out, double* sigma_out, int32_t* ok_out);
+
 /* ---- plane covariance ------------------------------------------------------------- */
 /* Replaces the ceres::Covariance block of PyrThetaOptim (src/optimizer.cc:2219-2238): cov_out[n_planes x 9] =
  * (J_theta' J_theta)^-1 per plane from its text blocks (loss-corrected Jacobian); singular blocks give zeros and are

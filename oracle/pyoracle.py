@@ -195,3 +195,15 @@ def theta_covariance(prob, jac_mode=0):
     pc = prob.as_c()
     ns = lib().tso_theta_covariance(C.byref(pc), C.c_int(jac_mode), _dp(cov))
     return cov, ns
+
+
+def text_info(img, quad, want_mask=False):
+    """tool::CalTextinfo restatement: (ok, mu, sigma[, fillPoly mask]) for one quad (4x2 doubles) on a u8 image."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    q = np.ascontiguousarray(quad, dtype=np.float64).reshape(8)
+    mu, sg = C.c_double(), C.c_double()
+    mask = np.zeros((h, w), dtype=np.uint8) if want_mask else None
+    ok = lib().tso_text_info(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), _dp(q), C.byref(mu), C.byref(sg),
+                             mask.ctypes.data_as(C.c_void_p) if want_mask else None)
+    return (bool(ok), mu.value, sg.value, mask) if want_mask else (bool(ok), mu.value, sg.value)

@@ -228,6 +228,20 @@ class ORBextractor:
         return ms.value, nk.value
 
 
+def text_info(ctx, imgs, quads, quad_img):
+    """tool::CalTextinfo for a batch of projected text quads: returns (ok, mu, sigma) arrays."""
+    imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+    if imgs.ndim == 2:
+        imgs = imgs[None]
+    n, h, w = imgs.shape
+    q = np.ascontiguousarray(quads, dtype=np.float64).reshape(-1, 8)
+    qi = np.ascontiguousarray(quad_img, dtype=np.int32)
+    mu = np.zeros(len(q)); sg = np.zeros(len(q)); ok = np.zeros(len(q), dtype=np.int32)
+    check(lib().tslam_text_info(ctx._h, imgs.ctypes.data_as(c_bp), C.c_int(n), C.c_int(w), C.c_int(h), _dp(q), qi.ctypes.data_as(C.POINTER(C.c_int32)),
+                                C.c_int(len(q)), _dp(mu), _dp(sg), ok.ctypes.data_as(C.POINTER(C.c_int32))))
+    return ok.astype(bool), mu, sg
+
+
 def match_hamming(ctx, query_desc, train_desc, cand_ptr, cand_idx):
     """Core of tracking::SearchFrom3D*: per query the first minimum-Hamming-distance candidate. Returns (idx, dist, second)."""
     q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32)

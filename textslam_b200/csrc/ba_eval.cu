@@ -227,7 +227,7 @@ int launch_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, bool want
   if (!want_J) LAUNCH(point_eval_kernel<0, 13, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr));
   else if (ncols == 13) {
     // occupancy variant: 8 CTAs/SM (64 registers, ~48 B of L1-resident spills) vs 6 CTAs/SM (79 registers)
-    static const bool occ8 = getenv("TSLAM_EVAL_OCC6") == nullptr;
+    static const bool occ8 = getenv("TSLAM_EVAL_OCC8") != nullptr;   // measured: 8 CTAs/SM is slower (0.67 vs 0.81 of HBM peak, profiles/r1_notes.md)
     if (occ8) LAUNCH(point_eval_kernel<0, 13, true, false, 8><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
     else LAUNCH(point_eval_kernel<0, 13, true, false, 6><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
   }
