@@ -136,6 +136,22 @@ int tslam_nccl_unique_id(uint8_t id_out[128]);
 int tslam_shard_owner(int landmark_is_free, int landmark_index, int obs_index, int world);
 int tslam_ctx_init_comm(tslam_ctx* ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
 
+/* ---- structure analysis (host only, no GPU needed) -------------------------------------------------- */
+/* What tslam_solve derives from the index arrays before the first kernel: free parameter blocks, the reduced camera
+ * system (6 x 6 blocks), the landmark -> camera incidence of this rank's shard and the tile schedule of the
+ * factorisation. The counterpart of ceres::Problem / Solver::Summary's num_*_reduced fields. */
+typedef struct tslam_structure_info {
+  int32_t n_free_cams, n_free_points, n_free_planes, reduced_dim;
+  int32_t n_blocks;             /* non-zero 6x6 blocks of the upper triangle of the reduced camera matrix            */
+  int32_t n_local_pobs, n_local_tobs;   /* observations owned by `rank`                                             */
+  int32_t n_owned_points, n_owned_planes, n_slots_point, n_slots_text;   /* landmarks / (landmark, camera) pairs owned */
+  int32_t n_tiles, n_waves;     /* 64 x 64 tile rows of the factorisation; length of its level schedule              */
+  int64_t n_tile_updates;       /* 64^3 tile multiply-adds of one factorisation                                      */
+  int64_t n_schur_entries, n_direct_entries;   /* gather-list lengths on this rank                                   */
+  double analysis_ms;
+} tslam_structure_info;
+int tslam_analyze_structure(const tslam_ba_problem* p, int rank, int world, tslam_structure_info* out);
+
 /* ---- residual + Jacobian evaluation (the metric kernel) --------------------------------------- */
 /* Replaces ceres::AutoDiffCostFunction<...>::Evaluate + QuaternionParameterization projection for
  * every residual block of the given kind.  r: n_pobs x 2.  J: n_pobs x 2 x ncols (ncols 13/6/1),

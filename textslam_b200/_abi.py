@@ -54,6 +54,20 @@ class SolveSummaryC(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class StructureInfoC(C.Structure):
+    _fields_ = [
+        ("n_free_cams", C.c_int32), ("n_free_points", C.c_int32), ("n_free_planes", C.c_int32), ("reduced_dim", C.c_int32),
+        ("n_blocks", C.c_int32), ("n_local_pobs", C.c_int32), ("n_local_tobs", C.c_int32),
+        ("n_owned_points", C.c_int32), ("n_owned_planes", C.c_int32), ("n_slots_point", C.c_int32), ("n_slots_text", C.c_int32),
+        ("n_tiles", C.c_int32), ("n_waves", C.c_int32),
+        ("n_tile_updates", C.c_int64), ("n_schur_entries", C.c_int64), ("n_direct_entries", C.c_int64),
+        ("analysis_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class KeyPointC(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
                 ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]

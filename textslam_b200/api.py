@@ -228,6 +228,15 @@ class ORBextractor:
         return ms.value, nk.value
 
 
+def analyze_structure(prob, rank=0, world=1):
+    """Host-only structure analysis of a problem (no GPU needed): what tslam_solve derives before its first kernel."""
+    from ._abi import StructureInfoC
+    info = StructureInfoC()
+    pc = prob.as_c()
+    check(lib().tslam_analyze_structure(C.byref(pc), C.c_int(rank), C.c_int(world), C.byref(info)))
+    return info.as_dict()
+
+
 def text_info(ctx, imgs, quads, quad_img):
     """tool::CalTextinfo for a batch of projected text quads: returns (ok, mu, sigma) arrays."""
     imgs = np.ascontiguousarray(imgs, dtype=np.uint8)

@@ -1,0 +1,483 @@
+// Structure analysis of a BA problem on the host — see analysis.hpp.
+#include "analysis.hpp"
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <atomic>
+#include <functional>
+#include <thread>
+
+namespace tsl {
+
+namespace {
+
+constexpr int NB = 64;   // Cholesky tile (chol.cu)
+
+// Worker pool that lives for one analyze_structure call: nt - 1 threads spin (then yield) on a generation counter, so a
+// parallel region costs a few microseconds instead of a thread start per region.
+class Pool {
+ public:
+  explicit Pool(int nt) : nt_(nt) {
+    for (int t = 1; t < nt_; ++t) th_.emplace_back([this, t] { worker(t); });
+  }
+  ~Pool() {
+    stop_ = true;
+    gen_.fetch_add(1, std::memory_order_release);
+    for (auto& x : th_) x.join();
+  }
+  int threads() const { return nt_; }
+  void set_serial() { serial_ = true; }
+  // f(tid, begin, end) over nt contiguous ranges of [0, n); the calling thread takes range 0. Ranges are ordered by tid,
+  // which the counting sorts below rely on to keep the serial (generation) order inside every bucket.
+  template <class F>
+  void ranges(int n, F&& f) {
+    if (nt_ <= 1 || serial_ || n < 2 * nt_) { f(0, 0, n); return; }
+    job_ = [&f, n, this](int t) { f(t, (int)((long long)n * t / nt_), (int)((long long)n * (t + 1) / nt_)); };
+    done_.store(0, std::memory_order_relaxed);
+    gen_.fetch_add(1, std::memory_order_release);
+    job_(0);
+    int spins = 0;
+    while (done_.load(std::memory_order_acquire) != nt_ - 1) if (++spins > 256) std::this_thread::yield();
+  }
+  int ranges_threads(int n) const { return (nt_ <= 1 || serial_ || n < 2 * nt_) ? 1 : nt_; }
+
+ private:
+  void worker(int t) {
+    int seen = 0;
+    for (;;) {
+      int spins = 0;
+      while (gen_.load(std::memory_order_acquire) == seen) if (++spins > 4096) std::this_thread::yield();
+      ++seen;
+      if (stop_) return;
+      job_(t);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  int nt_;
+  bool serial_ = false;
+  std::vector<std::thread> th_;
+  std::function<void(int)> job_;
+  std::atomic<int> gen_{0}, done_{0};
+  std::atomic<bool> stop_{false};
+};
+
+int host_threads(size_t work_items) {
+  static const int hw = [] {
+    if (const char* e = getenv("TSLAM_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned h = std::thread::hardware_concurrency();
+    return (int)std::min(8u, std::max(1u, h));
+  }();
+  return work_items < 20000 ? 1 : hw;   // thread start-up (~20 us each) only pays on the large problems
+}
+
+// One pass over the observations of one landmark type. lm_of_obs[i] = dense index (0..nv) of the landmark of local
+// observation i when that landmark is free and the observation active, else -1.
+void landmark_pass(Pool& pool, int n_obs, const int* cs, const int* hs, const int* lm_of_obs, int nv, LmSide& S) {
+  S.obs_ptr.assign((size_t)nv + 1, 0);
+  std::vector<int> ent_off((size_t)nv + 1, 0);
+  for (int i = 0; i < n_obs; ++i) {
+    const int v = lm_of_obs[i];
+    if (v < 0) continue;
+    S.obs_ptr[v + 1]++;
+    ent_off[v + 1] += (cs[i] >= 0) + (hs[i] >= 0);
+  }
+  for (int v = 0; v < nv; ++v) { S.obs_ptr[v + 1] += S.obs_ptr[v]; ent_off[v + 1] += ent_off[v]; }
+  const size_t n_ent = (size_t)ent_off[nv];
+  S.obs.resize((size_t)S.obs_ptr[nv]);
+  {
+    std::vector<int> cur(S.obs_ptr.begin(), S.obs_ptr.end() - 1);
+    for (int i = 0; i < n_obs; ++i) { const int v = lm_of_obs[i]; if (v >= 0) S.obs[cur[v]++] = i; }
+  }
+  // phase 1: per landmark, the (camera slot, obs << 1 | role) keys sorted; count the distinct camera slots
+  std::vector<uint64_t> keys(n_ent);
+  S.slot_ptr.assign((size_t)nv + 1, 0);
+  pool.ranges(nv, [&](int, int v0, int v1) {
+    for (int v = v0; v < v1; ++v) {
+      uint64_t* key = keys.data() + ent_off[v];
+      int m = 0;
+      for (int e = S.obs_ptr[v]; e < S.obs_ptr[v + 1]; ++e) {
+        const int i = S.obs[e];
+        if (cs[i] >= 0) key[m++] = ((uint64_t)cs[i] << 32) | (uint32_t)((i << 1) | 0);
+        if (hs[i] >= 0) key[m++] = ((uint64_t)hs[i] << 32) | (uint32_t)((i << 1) | 1);
+      }
+      if (m <= 24) {
+        for (int a = 1; a < m; ++a) { const uint64_t k = key[a]; int b = a - 1; while (b >= 0 && key[b] > k) { key[b + 1] = key[b]; --b; } key[b + 1] = k; }
+      } else std::sort(key, key + m);
+      int ns = 0;
+      for (int k = 0; k < m; ++k) ns += (k == 0 || (key[k] >> 32) != (key[k - 1] >> 32));
+      S.slot_ptr[v + 1] = ns;
+    }
+  });
+  for (int v = 0; v < nv; ++v) S.slot_ptr[v + 1] += S.slot_ptr[v];
+  const size_t n_slots = (size_t)S.slot_ptr[nv];
+  S.slot_cam.resize(n_slots); S.slot_lm.resize(n_slots); S.ent.resize(n_ent); S.ent_ptr.resize(n_slots + 1);
+  // phase 2: emit slots and their entry ranges (entries of a landmark are contiguous, slots ascending)
+  pool.ranges(nv, [&](int, int v0, int v1) {
+    for (int v = v0; v < v1; ++v) {
+      const uint64_t* key = keys.data() + ent_off[v];
+      const int m = ent_off[v + 1] - ent_off[v];
+      int s = S.slot_ptr[v] - 1;
+      for (int k = 0; k < m; ++k) {
+        if (k == 0 || (key[k] >> 32) != (key[k - 1] >> 32)) { ++s; S.slot_cam[s] = (int)(key[k] >> 32); S.slot_lm[s] = v; S.ent_ptr[s] = ent_off[v] + k; }
+        S.ent[(size_t)ent_off[v] + k] = (int)(uint32_t)key[k];
+      }
+    }
+  });
+  S.ent_ptr[n_slots] = (int)n_ent;
+}
+
+// Dense owned-landmark numbering: landmarks that are free (lmfree >= 0) and appear in an active local observation,
+// in ascending global order. Fills S.v_gl, S.obs_ls.
+int owned_landmarks(int n_obs, const int32_t* lm, const uint8_t* act, const std::vector<int>& lmfree, LmSide& S) {
+  const int n_lm = (int)lmfree.size();
+  std::vector<int> local_of((size_t)n_lm, -1);
+  for (int i = 0; i < n_obs; ++i) if (act[i] && lmfree[lm[i]] >= 0) local_of[lm[i]] = 0;
+  S.v_gl.clear();
+  for (int l = 0; l < n_lm; ++l) if (local_of[l] == 0) { local_of[l] = (int)S.v_gl.size(); S.v_gl.push_back(l); }
+  S.obs_ls.resize((size_t)n_obs);
+  for (int i = 0; i < n_obs; ++i) S.obs_ls[i] = (act[i] && lmfree[lm[i]] >= 0) ? local_of[lm[i]] : -1;
+  return (int)S.v_gl.size();
+}
+
+struct Laps {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), tl = t0;
+  double lap() { auto now = std::chrono::steady_clock::now(); const double ms = std::chrono::duration<double, std::milli>(now - tl).count(); tl = now; return ms; }
+  double total() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+}  // namespace
+
+int chol_workspace_dims(int n, int* ld, int* rows) {
+  const int Tn = (n + NB - 1) / NB;
+  *ld = Tn * NB;
+  *rows = (Tn + 1) * NB;
+  return Tn;
+}
+
+// tile_nz: Tn x Tn row-major flags of the lower-triangular tile pattern of S (diagonal always set).
+// Besides the fill pattern this computes a LEVEL SCHEDULE of the tile elimination DAG: panel j can start once every
+// panel k < j with L[j][k] != 0 is finished; panels of one wave are mutually independent, so a wave is three
+// launches (factor+solve, update, and later the backward solve) however many panels it holds. With the nested-
+// dissection camera order chosen below a banded problem needs ~15 waves instead of T = 47 panel steps.
+void chol_symbolic_host(int n, const std::vector<uint8_t>& tile_nz, CholHost& H) {
+  int ld, rows;
+  const int Tn = chol_workspace_dims(n, &ld, &rows);
+  H = CholHost();
+  H.Tn = Tn; H.n = n;
+  const int T1 = Tn + 1;  // + the b tile row (dense)
+  std::vector<uint8_t> P((size_t)T1 * T1, 0);
+  for (int i = 0; i < Tn; ++i)
+    for (int k = 0; k <= i; ++k) P[(size_t)i * T1 + k] = (i == k) || tile_nz[(size_t)i * Tn + k];
+  for (int k = 0; k < Tn; ++k) P[(size_t)Tn * T1 + k] = 1;
+  std::vector<std::vector<int>> below(Tn);
+  for (int j = 0; j < Tn; ++j) {   // symbolic factorisation (fill)
+    std::vector<int>& nz = below[j];
+    for (int i = j + 1; i < T1; ++i) if (P[(size_t)i * T1 + j]) nz.push_back(i);
+    for (size_t a = 0; a < nz.size(); ++a)
+      for (size_t b = 0; b <= a; ++b) P[(size_t)nz[a] * T1 + nz[b]] = 1;
+  }
+  std::vector<int> wave(Tn, 0);
+  int nwaves = 0;
+  for (int j = 0; j < Tn; ++j) {
+    int w = 0;
+    for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, wave[k] + 1);
+    wave[j] = w; nwaves = std::max(nwaves, w + 1);
+  }
+  H.nwaves = nwaves;
+  std::vector<std::vector<int>> wave_panels(nwaves);
+  for (int j = 0; j < Tn; ++j) wave_panels[wave[j]].push_back(j);
+  H.item_ptr.assign(nwaves + 1, 0); H.target_ptr.assign(nwaves + 1, 0); H.panel_ptr.assign(nwaves + 1, 0);
+  H.src_ptr.push_back(0); H.below_ptr.push_back(0);
+  std::vector<int> tgt_index((size_t)T1 * T1, -1);
+  for (int w = 0; w < nwaves; ++w) {
+    const size_t t_begin = H.targets.size();
+    std::vector<std::vector<int>> tsrc;
+    for (int j : wave_panels[w]) {
+      H.items.push_back(I2{j, -1});
+      for (int i : below[j]) H.items.push_back(I2{j, i});
+      const std::vector<int>& nz = below[j];
+      for (size_t a = 0; a < nz.size(); ++a)
+        for (size_t b = 0; b <= a; ++b) {
+          const int i = nz[a], k = nz[b];
+          if (i == Tn && k == Tn) continue;   // (b row, b row) is never read
+          int& ti = tgt_index[(size_t)i * T1 + k];
+          if (ti < (int)t_begin) { ti = (int)H.targets.size(); H.targets.push_back(I2{i, k}); tsrc.emplace_back(); }
+          tsrc[ti - t_begin].push_back(j);
+          ++H.gemm_tiles;
+        }
+      H.panels.push_back(j);   // backward solve: tiles (i, j) of the factor below the diagonal, excluding the b row
+      for (int i : below[j]) if (i < Tn) H.below.push_back(i);
+      H.below_ptr.push_back((int)H.below.size());
+    }
+    for (auto& v : tsrc) { for (int j : v) H.src.push_back(j); H.src_ptr.push_back((int)H.src.size()); }
+    for (size_t t = t_begin; t < H.targets.size(); ++t) tgt_index[(size_t)H.targets[t].x * T1 + H.targets[t].y] = -1;
+    H.item_ptr[w + 1] = (int)H.items.size(); H.target_ptr[w + 1] = (int)H.targets.size(); H.panel_ptr[w + 1] = (int)H.panels.size();
+  }
+}
+
+void analyze_structure(const IndexView& V, Analysis& A) {
+  Laps T;
+  const int K = V.n_cams, GP = V.g_pobs, GT = V.g_tobs;
+  Pool pool(host_threads((size_t)GP + 8 * (size_t)GT));
+  A.K = K;
+  auto cf = [&](int k) { return V.cam_fixed[k] != 0; };
+  // ---- global layout (same on every rank) ----
+  std::vector<uint8_t> cu(K, 0), lu(V.n_points, 0), pu(V.n_planes, 0);
+  std::vector<uint8_t> gp_active(GP), gt_active(GT);
+  for (int i = 0; i < GP; ++i) {
+    const int c = V.p_cam[i], h = V.p_host[i], l = V.p_lm[i];
+    const bool act = !cf(c) || !cf(h) || !V.rho_fixed[l];
+    gp_active[i] = act;
+    if (act) { cu[c] = cu[h] = 1; lu[l] = 1; }
+  }
+  for (int i = 0; i < GT; ++i) {
+    const int c = V.t_cam[i], h = V.t_host[i], l = V.t_plane[i];
+    const bool act = !cf(c) || !cf(h) || !V.theta_fixed[l];
+    gt_active[i] = act;
+    if (act) { cu[c] = cu[h] = 1; pu[l] = 1; }
+  }
+  A.camslot.assign(K, -1); A.nc = 0;
+  for (int k = 0; k < K; ++k) if (cu[k] && !cf(k)) A.camslot[k] = A.nc++;
+  A.lmfree_p.assign(V.n_points, -1); A.nl = 0;
+  for (int k = 0; k < V.n_points; ++k) if (lu[k] && !V.rho_fixed[k]) A.lmfree_p[k] = A.nl++;
+  A.lmfree_t.assign(V.n_planes, -1); A.npl = 0;
+  for (int k = 0; k < V.n_planes; ++k) if (pu[k] && !V.theta_fixed[k]) A.lmfree_t[k] = A.npl++;
+  const int nc = A.nc;
+  A.n = 6 * nc;
+  A.Tn = chol_workspace_dims(A.n, &A.ld, &A.rows);
+  // ---- nested-dissection order of the free cameras (keyframes are temporally ordered, co-visibility is banded) ----
+  // Units of U cameras (U = multiple of 32 cameras = 3 tiles of 64 columns, at least the co-visibility bandwidth) are
+  // ordered leaves-first / separators-last so that the tile elimination DAG of chol.cu has ~log depth instead of being
+  // a chain; any order is valid, this one only shortens the critical path of the reduced-system factorisation.
+  if (nc >= 128) {
+    std::vector<int> hist((size_t)nc, 0);   // histogram of |slot(cam) - slot(host)| over the active observations
+    size_t nd = 0;
+    for (int i = 0; i < GP; ++i) if (gp_active[i]) { const int a = A.camslot[V.p_cam[i]], b = A.camslot[V.p_host[i]]; if (a >= 0 && b >= 0) { hist[std::abs(a - b)]++; ++nd; } }
+    for (int i = 0; i < GT; ++i) if (gt_active[i]) { const int a = A.camslot[V.t_cam[i]], b = A.camslot[V.t_host[i]]; if (a >= 0 && b >= 0) { hist[std::abs(a - b)]++; ++nd; } }
+    int bw = 0;
+    if (nd) {   // 98th percentile of the distances (index floor(0.98 (nd-1)) of the sorted list)
+      const size_t q = (size_t)(0.98 * (double)(nd - 1));
+      size_t acc = 0; int dq = 0;
+      for (int dd = 0; dd < nc; ++dd) { acc += hist[dd]; if (acc > q) { dq = dd; break; } }
+      bw = 2 * dq;
+    }
+    const int U = 32 * ((bw + 1 + 31) / 32);
+    const int nfull = nc / U;
+    if (nfull >= 4) {
+      std::vector<int> unit_order;
+      struct Frame { int lo, hi, stage; };   // recursive bisection written iteratively (post-order: left, right, separator)
+      std::vector<Frame> st; st.push_back({0, nfull, 0});
+      while (!st.empty()) {
+        Frame f = st.back(); st.pop_back();
+        if (f.hi - f.lo <= 0) continue;
+        if (f.hi - f.lo <= 2) { for (int u = f.lo; u < f.hi; ++u) unit_order.push_back(u); continue; }
+        const int mid = (f.lo + f.hi) / 2;
+        if (f.stage == 0) { st.push_back({f.lo, f.hi, 1}); st.push_back({mid + 1, f.hi, 0}); st.push_back({f.lo, mid, 0}); }
+        else unit_order.push_back(mid);
+      }
+      std::vector<int> new_of_old(nc, -1);
+      int next = 0;
+      for (int u : unit_order) for (int c = u * U; c < (u + 1) * U; ++c) new_of_old[c] = next++;
+      for (int c = nfull * U; c < nc; ++c) new_of_old[c] = next++;   // the partial unit goes last (keeps units tile-aligned)
+      for (int k = 0; k < K; ++k) if (A.camslot[k] >= 0) A.camslot[k] = new_of_old[A.camslot[k]];
+    }
+  }
+  // camera slots of every global observation
+  std::vector<int> gp_cs(GP), gp_hs(GP), gt_cs(GT), gt_hs(GT);
+  for (int i = 0; i < GP; ++i) { gp_cs[i] = A.camslot[V.p_cam[i]]; gp_hs[i] = A.camslot[V.p_host[i]]; }
+  for (int i = 0; i < GT; ++i) { gt_cs[i] = A.camslot[V.t_cam[i]]; gt_hs[i] = A.camslot[V.t_host[i]]; }
+  A.lap_ms[0] = T.lap();
+
+  // ---- local observations + landmark side ----
+  const bool sharded = V.gsel_p != nullptr || V.gsel_t != nullptr;
+  const int lp = V.lp, lt = V.lt; A.lp = lp; A.lt = lt;
+  std::vector<int32_t> lp_lm, lt_lm;
+  const int32_t *l_p_lm = V.p_lm, *l_t_lm = V.t_plane;
+  if (!sharded) {
+    A.p_cs = gp_cs; A.p_hs = gp_hs; A.p_act = gp_active; A.t_cs = gt_cs; A.t_hs = gt_hs; A.t_act = gt_active;
+  } else {
+    A.p_cs.resize(lp); A.p_hs.resize(lp); A.p_act.resize(lp); lp_lm.resize(lp);
+    for (int i = 0; i < lp; ++i) { const int g = V.gsel_p[i]; A.p_cs[i] = gp_cs[g]; A.p_hs[i] = gp_hs[g]; A.p_act[i] = gp_active[g]; lp_lm[i] = V.p_lm[g]; }
+    A.t_cs.resize(lt); A.t_hs.resize(lt); A.t_act.resize(lt); lt_lm.resize(lt);
+    for (int i = 0; i < lt; ++i) { const int g = V.gsel_t[i]; A.t_cs[i] = gt_cs[g]; A.t_hs[i] = gt_hs[g]; A.t_act[i] = gt_active[g]; lt_lm[i] = V.t_plane[g]; }
+    l_p_lm = lp_lm.data(); l_t_lm = lt_lm.data();
+  }
+  A.t_fm.resize(lt);
+  for (int i = 0; i < lt; ++i) A.t_fm[i] = (uint8_t)((A.t_cs[i] >= 0 ? 1 : 0) | (A.t_hs[i] >= 0 ? 2 : 0) | (A.lmfree_t[l_t_lm[i]] >= 0 ? 4 : 0));
+  A.nvp = owned_landmarks(lp, l_p_lm, A.p_act.data(), A.lmfree_p, A.LP);
+  A.nvt = owned_landmarks(lt, l_t_lm, A.t_act.data(), A.lmfree_t, A.LT);
+  landmark_pass(pool, lp, A.p_cs.data(), A.p_hs.data(), A.LP.obs_ls.data(), A.nvp, A.LP);
+  landmark_pass(pool, lt, A.t_cs.data(), A.t_hs.data(), A.LT.obs_ls.data(), A.nvt, A.LT);
+  A.nsp = (int)A.LP.slot_cam.size(); A.nst = (int)A.LT.slot_cam.size();
+  // the block structure needs the slot sets of ALL free landmarks (every rank builds the same reduced matrix layout)
+  LmSide GLP, GLT;
+  const LmSide *SP = &A.LP, *ST = &A.LT;
+  if (sharded) {
+    owned_landmarks(GP, V.p_lm, gp_active.data(), A.lmfree_p, GLP);
+    owned_landmarks(GT, V.t_plane, gt_active.data(), A.lmfree_t, GLT);
+    landmark_pass(pool, GP, gp_cs.data(), gp_hs.data(), GLP.obs_ls.data(), (int)GLP.v_gl.size(), GLP);
+    landmark_pass(pool, GT, gt_cs.data(), gt_hs.data(), GLT.obs_ls.data(), (int)GLT.v_gl.size(), GLT);
+    SP = &GLP; ST = &GLT;
+  }
+  A.lap_ms[1] = T.lap();
+
+  // ---- global block structure: unique (a <= b) camera-slot pairs from every active observation / landmark ----
+  // dense (a,b) -> block id table when nc^2 is small enough (O(1) insert / lookup); sorted-key fallback otherwise
+  const bool dense_tab = (size_t)nc * (size_t)nc <= ((size_t)1 << 24);
+  std::vector<int> btab;
+  std::vector<uint64_t> bkeys;
+  if (dense_tab) btab.assign((size_t)nc * nc, -1);
+  if (dense_tab) {
+    // every thread stores the same value (0) into the table: relaxed atomic stores, no ordering needed before the join
+    auto mark = [&](int a, int b) { __atomic_store_n(&btab[(size_t)a * nc + b], 0, __ATOMIC_RELAXED); };
+    auto direct_keys = [&](int n_obs, const int* cs, const int* hs, const uint8_t* act) {
+      pool.ranges(n_obs, [&](int, int i0, int i1) {
+        for (int i = i0; i < i1; ++i) if (act[i]) {
+          const int c = cs[i], h = hs[i];
+          if (c >= 0) mark(c, c);
+          if (h >= 0) mark(h, h);
+          if (c >= 0 && h >= 0 && c != h) mark(std::min(c, h), std::max(c, h));
+        }
+      });
+    };
+    direct_keys(GP, gp_cs.data(), gp_hs.data(), gp_active.data());
+    direct_keys(GT, gt_cs.data(), gt_hs.data(), gt_active.data());
+    auto schur_keys = [&](const LmSide& L) {
+      pool.ranges((int)L.slot_ptr.size() - 1, [&](int, int v0, int v1) {
+        for (int v = v0; v < v1; ++v)
+          for (int x = L.slot_ptr[v]; x < L.slot_ptr[v + 1]; ++x)
+            for (int y = x; y < L.slot_ptr[v + 1]; ++y) mark(L.slot_cam[x], L.slot_cam[y]);
+      });
+    };
+    schur_keys(*SP); schur_keys(*ST);
+  } else {
+    auto add_key = [&](int a, int b) { bkeys.push_back((uint64_t)a * (uint64_t)nc + (uint64_t)b); };   // a <= b
+    auto direct_keys = [&](int n_obs, const int* cs, const int* hs, const uint8_t* act) {
+      for (int i = 0; i < n_obs; ++i) if (act[i]) {
+        const int c = cs[i], h = hs[i];
+        if (c >= 0) add_key(c, c);
+        if (h >= 0) add_key(h, h);
+        if (c >= 0 && h >= 0 && c != h) add_key(std::min(c, h), std::max(c, h));
+      }
+    };
+    direct_keys(GP, gp_cs.data(), gp_hs.data(), gp_active.data());
+    direct_keys(GT, gt_cs.data(), gt_hs.data(), gt_active.data());
+    auto schur_keys = [&](const LmSide& L) {
+      const int nv = (int)L.slot_ptr.size() - 1;
+      for (int v = 0; v < nv; ++v)
+        for (int x = L.slot_ptr[v]; x < L.slot_ptr[v + 1]; ++x)
+          for (int y = x; y < L.slot_ptr[v + 1]; ++y) add_key(L.slot_cam[x], L.slot_cam[y]);
+    };
+    schur_keys(*SP); schur_keys(*ST);
+  }
+  A.blk_a.clear(); A.blk_b.clear(); A.diag_blk.assign(nc, -1);
+  if (dense_tab) {
+    int nb = 0;
+    for (int a = 0; a < nc; ++a)
+      for (int b = a; b < nc; ++b)
+        if (btab[(size_t)a * nc + b] == 0) { btab[(size_t)a * nc + b] = nb++; A.blk_a.push_back(a); A.blk_b.push_back(b); }
+    A.nblk = nb;
+  } else {
+    std::sort(bkeys.begin(), bkeys.end());
+    bkeys.erase(std::unique(bkeys.begin(), bkeys.end()), bkeys.end());
+    A.nblk = (int)bkeys.size();
+    A.blk_a.resize(A.nblk); A.blk_b.resize(A.nblk);
+    for (int b = 0; b < A.nblk; ++b) { A.blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); A.blk_b[b] = (int)(bkeys[b] % (uint64_t)nc); }
+  }
+  for (int b = 0; b < A.nblk; ++b) if (A.blk_a[b] == A.blk_b[b]) A.diag_blk[A.blk_a[b]] = b;
+  A.lap_ms[2] = T.lap();
+  {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
+    std::vector<uint8_t> tile_nz((size_t)A.Tn * A.Tn, 0);
+    for (int b = 0; b < A.nblk; ++b) {
+      // block (a,b'), a <= b' lands in rows 6b'..6b'+5, cols 6a..6a+5 of the lower triangle
+      const int r0 = 6 * A.blk_b[b] / NB, r1 = (6 * A.blk_b[b] + 5) / NB, c0 = 6 * A.blk_a[b] / NB, c1 = (6 * A.blk_a[b] + 5) / NB;
+      for (int r = r0; r <= r1; ++r) for (int c = c0; c <= c1; ++c) if (c <= r) tile_nz[(size_t)r * A.Tn + c] = 1;
+    }
+    chol_symbolic_host(A.n, tile_nz, A.chol);
+  }
+  A.lap_ms[3] = T.lap();
+  auto blk_of = [&](int a, int b) {   // a <= b
+    if (dense_tab) return btab[(size_t)a * nc + b];
+    const uint64_t key = (uint64_t)a * (uint64_t)nc + (uint64_t)b;
+    return (int)(std::lower_bound(bkeys.begin(), bkeys.end(), key) - bkeys.begin());
+  };
+
+  // ---- local gather lists per block: counting sort by block, order inside a block = generation order. Parallel form:
+  // thread t counts its (ordered) range into its own histogram, bucket b then starts at ptr[b] + sum_{t' < t} hist[t'][b].
+  if ((size_t)pool.threads() * (size_t)A.nblk > ((size_t)1 << 22)) pool.set_serial();
+  const int nt = pool.threads();
+  std::vector<int> hist((size_t)nt * ((size_t)A.nblk + 1));
+  auto offsets_from_hist = [&](std::vector<int>& ptr) {   // hist[t][b] (counts) -> hist[t][b] (start offsets), ptr = CSR
+    ptr.assign((size_t)A.nblk + 1, 0);
+    int run = 0;
+    for (int b = 0; b < A.nblk; ++b) {
+      ptr[b] = run;
+      for (int t = 0; t < nt; ++t) { int& h = hist[(size_t)t * (A.nblk + 1) + b]; const int c = h; h = run; run += c; }
+    }
+    ptr[A.nblk] = run;
+    return run;
+  };
+  auto direct_lists = [&](int n_obs, const int* cs, const int* hs, const uint8_t* act, std::vector<int>& ptr, std::vector<int>& out) {
+    // codes: 0 = J_cam^T J_cam on the diagonal block of the observing camera, 1 = same for the host, 2 / 3 = the
+    // off-diagonal block (2: observing slot < host slot, 3: host slot < observing slot)
+    std::vector<int> key(3 * (size_t)n_obs);
+    std::fill(hist.begin(), hist.end(), 0);
+    pool.ranges(n_obs, [&](int t, int i0, int i1) {
+      int* h_ = &hist[(size_t)t * (A.nblk + 1)];
+      for (int i = i0; i < i1; ++i) {
+        int* k = &key[3 * (size_t)i];
+        k[0] = k[1] = k[2] = -1;
+        if (!act[i]) continue;
+        const int c = cs[i], h = hs[i];
+        if (c >= 0) { k[0] = A.diag_blk[c]; h_[k[0]]++; }
+        if (h >= 0) { k[1] = A.diag_blk[h]; h_[k[1]]++; }
+        if (c >= 0 && h >= 0) { k[2] = c < h ? blk_of(c, h) : (h < c ? blk_of(h, c) : A.diag_blk[c]); h_[k[2]] += (c == h) ? 2 : 1; }
+      }
+    });
+    out.resize((size_t)offsets_from_hist(ptr));
+    pool.ranges(n_obs, [&](int t, int i0, int i1) {
+      int* cur = &hist[(size_t)t * (A.nblk + 1)];
+      for (int i = i0; i < i1; ++i) {
+        const int* k = &key[3 * (size_t)i];
+        if (k[0] >= 0) out[cur[k[0]]++] = (i << 2) | 0;
+        if (k[1] >= 0) out[cur[k[1]]++] = (i << 2) | 1;
+        if (k[2] >= 0) {
+          const int c = cs[i], h = hs[i];
+          if (c < h) out[cur[k[2]]++] = (i << 2) | 2;
+          else if (h < c) out[cur[k[2]]++] = (i << 2) | 3;
+          else { out[cur[k[2]]++] = (i << 2) | 2; out[cur[k[2]]++] = (i << 2) | 3; }   // cam == host never happens in the reference (src/optimizer.cc:1397)
+        }
+      }
+    });
+  };
+  direct_lists(lp, A.p_cs.data(), A.p_hs.data(), A.p_act.data(), A.bdp_ptr, A.bdp);
+  direct_lists(lt, A.t_cs.data(), A.t_hs.data(), A.t_act.data(), A.bdt_ptr, A.bdt);
+  auto schur_lists = [&](const LmSide& L, std::vector<int>& ptr, std::vector<I2>& out) {
+    const int nv = (int)L.slot_ptr.size() - 1;
+    std::vector<size_t> pair_off((size_t)nv + 1, 0);
+    for (int v = 0; v < nv; ++v) { const size_t m = (size_t)(L.slot_ptr[v + 1] - L.slot_ptr[v]); pair_off[v + 1] = pair_off[v] + m * (m + 1) / 2; }
+    std::vector<int> key(pair_off[nv]);
+    std::fill(hist.begin(), hist.end(), 0);
+    pool.ranges(nv, [&](int t, int v0, int v1) {
+      int* h_ = &hist[(size_t)t * (A.nblk + 1)];
+      size_t e = pair_off[v0];
+      for (int v = v0; v < v1; ++v)
+        for (int x = L.slot_ptr[v]; x < L.slot_ptr[v + 1]; ++x)
+          for (int y = x; y < L.slot_ptr[v + 1]; ++y) { const int b = blk_of(L.slot_cam[x], L.slot_cam[y]); key[e++] = b; h_[b]++; }
+    });
+    out.resize((size_t)offsets_from_hist(ptr));
+    pool.ranges(nv, [&](int t, int v0, int v1) {
+      int* cur = &hist[(size_t)t * (A.nblk + 1)];
+      size_t e = pair_off[v0];
+      for (int v = v0; v < v1; ++v)
+        for (int x = L.slot_ptr[v]; x < L.slot_ptr[v + 1]; ++x)
+          for (int y = x; y < L.slot_ptr[v + 1]; ++y) out[cur[key[e++]]++] = I2{x, y};
+    });
+  };
+  schur_lists(A.LP, A.bsp_ptr, A.bsp);
+  schur_lists(A.LT, A.bst_ptr, A.bst);
+  A.lap_ms[4] = T.lap();
+  A.lap_ms[5] = T.total();
+}
+
+}  // namespace tsl

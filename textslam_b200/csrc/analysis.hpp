@@ -1,0 +1,57 @@
+// Host-side structure analysis of a BA problem (pure C++, no CUDA): which parameter blocks are free, the camera
+// ordering, the landmark -> (camera slot) incidence, the non-zero 6x6 blocks of the reduced camera system with their
+// gather lists, and the tile-level symbolic Cholesky. This is the work ceres::Problem / Program / the Schur ordering
+// do when the reference calls ceres::Solve on a freshly built problem (src/optimizer.cc:1222,1602,1840,1982,2209);
+// it runs once per tslam_solve call and sits inside the end-to-end time, so it is written as counting sorts over
+// flat arrays (no per-element allocation) rather than as containers.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace tsl {
+
+struct I2 { int x, y; };   // layout-compatible with CUDA's int2
+
+struct IndexView {          // index arrays of the GLOBAL problem + the locally owned observations
+  int n_cams = 0, n_points = 0, n_planes = 0, g_pobs = 0, g_tobs = 0;
+  const uint8_t *cam_fixed = nullptr, *rho_fixed = nullptr, *theta_fixed = nullptr;
+  const int32_t *p_cam = nullptr, *p_host = nullptr, *p_lm = nullptr, *t_cam = nullptr, *t_host = nullptr, *t_plane = nullptr;
+  int lp = 0, lt = 0;                                   // local observation counts
+  const int32_t *gsel_p = nullptr, *gsel_t = nullptr;   // global index of each local observation; NULL = identity (not sharded)
+};
+
+struct LmSide {   // landmark-side structure of one landmark type (inverse depths or planes) for the locally owned landmarks
+  std::vector<int> v_gl;               // owned landmark -> global landmark index (ascending)
+  std::vector<int> obs_ptr, obs;       // CSR: local observations of each owned landmark (ascending)
+  std::vector<int> obs_ls;             // per local observation: owned landmark or -1
+  std::vector<int> slot_ptr, slot_cam, slot_lm;   // CSR: distinct camera slots touching each landmark (ascending)
+  std::vector<int> ent_ptr, ent;       // CSR per slot: (obs << 1 | role) entries, role 0 = observing camera, 1 = host camera
+};
+
+struct CholHost {  // tile-level symbolic factorisation + level schedule (see chol.cu)
+  int Tn = 0, n = 0, nwaves = 0;
+  long long gemm_tiles = 0;
+  std::vector<int> item_ptr, target_ptr, panel_ptr;
+  std::vector<I2> items, targets;
+  std::vector<int> src_ptr, src, panels, below_ptr, below;
+};
+
+struct Analysis {
+  int K = 0, nc = 0, nl = 0, npl = 0, lp = 0, lt = 0, nvp = 0, nvt = 0, nsp = 0, nst = 0, nblk = 0;
+  int n = 0, ld = 0, rows = 0, Tn = 0;
+  std::vector<int> camslot, lmfree_p, lmfree_t;
+  std::vector<int> p_cs, p_hs, t_cs, t_hs;             // per local observation: camera slots (or -1)
+  std::vector<uint8_t> p_act, t_act, t_fm;
+  LmSide LP, LT;
+  std::vector<int> blk_a, blk_b, diag_blk;
+  std::vector<int> bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr;
+  std::vector<I2> bsp, bst;
+  CholHost chol;
+  double lap_ms[6] = {0, 0, 0, 0, 0, 0};   // layout+ordering, landmark side, block structure, symbolic, entry lists, total
+};
+
+int chol_workspace_dims(int n, int* ld, int* rows);
+void chol_symbolic_host(int n, const std::vector<uint8_t>& tile_nz, CholHost& H);
+void analyze_structure(const IndexView& V, Analysis& A);
+
+}  // namespace tsl

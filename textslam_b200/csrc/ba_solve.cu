@@ -24,6 +24,7 @@
 #include <numeric>
 #include "ctx.cuh"
 #include "solver.cuh"
+#include "analysis.hpp"
 #include "ba_device.cuh"
 
 namespace tsl {
@@ -643,304 +644,49 @@ struct Solver {
 template <typename T>
 static cudaError_t up(DevBuf<T>& b, const std::vector<T>& h, cudaStream_t s) { return b.upload(h.data(), h.size(), s); }
 
-// counting-sort based CSR builder: keys in [0, nkeys)
-static void build_csr(int nkeys, const std::vector<int>& keys, std::vector<int>& ptr, std::vector<int>& order) {
-  ptr.assign(nkeys + 1, 0);
-  for (int k : keys) ptr[k + 1]++;
-  for (int i = 0; i < nkeys; ++i) ptr[i + 1] += ptr[i];
-  order.resize(keys.size());
-  std::vector<int> cur(ptr.begin(), ptr.end() - 1);
-  for (size_t i = 0; i < keys.size(); ++i) order[cur[keys[i]]++] = (int)i;
+template <typename T, typename H>
+static cudaError_t up_as(DevBuf<T>& b, const std::vector<H>& h, cudaStream_t s) {
+  static_assert(sizeof(T) == sizeof(H), "layout-compatible element types expected");
+  return b.upload(reinterpret_cast<const T*>(h.data()), h.size(), s);
 }
 
-struct LmStruct {  // landmark-side structure for one landmark type (points or planes)
-  std::vector<int> v_gl, obs_ptr, obs, slot_ptr, slot_cam, slot_lm, ent_ptr, ent;
-  std::vector<int> obs_ls;  // per local observation: owned landmark index or -1
-  // per landmark list of (global) camslots, for ALL free landmarks of this type (global block structure)
-};
-
-// Builds slot structure for the locally owned landmarks from local observations.
-//  free_gl[l] >= 0  iff landmark l is free & used (global); local obs arrays index global landmarks.
-static void build_landmark_side(int n_obs, const int* o_lm, const std::vector<int>& o_cs, const std::vector<int>& o_hs,
-                                const std::vector<uint8_t>& o_active, const std::vector<int>& lmslot_gl, int n_lm_total, LmStruct& S) {
-  // owned landmarks = free landmarks that appear in local active observations (ownership rule guarantees all their obs are local)
-  std::vector<int> local_of(n_lm_total, -1);
-  S.v_gl.clear();
-  S.obs_ls.assign(n_obs, -1);
-  for (int i = 0; i < n_obs; ++i) {
-    const int l = o_lm[i];
-    if (!o_active[i] || lmslot_gl[l] < 0) continue;
-    if (local_of[l] < 0) { local_of[l] = (int)S.v_gl.size(); S.v_gl.push_back(l); }
-  }
-  // keep owned landmarks in ascending global order (deterministic, independent of obs order)
-  std::sort(S.v_gl.begin(), S.v_gl.end());
-  for (size_t v = 0; v < S.v_gl.size(); ++v) local_of[S.v_gl[v]] = (int)v;
-  const int nv = (int)S.v_gl.size();
-  std::vector<int> keys; std::vector<int> idx;
-  for (int i = 0; i < n_obs; ++i) {
-    const int l = o_lm[i];
-    if (!o_active[i] || lmslot_gl[l] < 0) continue;
-    S.obs_ls[i] = local_of[l];
-    keys.push_back(local_of[l]); idx.push_back(i);
-  }
-  std::vector<int> order;
-  build_csr(nv, keys, S.obs_ptr, order);
-  S.obs.resize(order.size());
-  for (size_t k = 0; k < order.size(); ++k) S.obs[k] = idx[order[k]];
-  // slots: per landmark, distinct camslots (ascending) among cam / host of its observations
-  S.slot_ptr.assign(nv + 1, 0); S.slot_cam.clear(); S.slot_lm.clear(); S.ent_ptr.clear(); S.ent.clear();
-  S.ent_ptr.push_back(0);
-  std::vector<std::pair<int, int>> tmp;  // (camslot, obs<<1|role)
-  for (int v = 0; v < nv; ++v) {
-    tmp.clear();
-    for (int e = S.obs_ptr[v]; e < S.obs_ptr[v + 1]; ++e) {
-      const int i = S.obs[e];
-      if (o_cs[i] >= 0) tmp.emplace_back(o_cs[i], (i << 1) | 0);
-      if (o_hs[i] >= 0) tmp.emplace_back(o_hs[i], (i << 1) | 1);
-    }
-    std::sort(tmp.begin(), tmp.end());
-    for (size_t k = 0; k < tmp.size(); ++k) {
-      if (k == 0 || tmp[k].first != tmp[k - 1].first) {
-        if (k != 0) S.ent_ptr.push_back((int)S.ent.size());
-        S.slot_cam.push_back(tmp[k].first); S.slot_lm.push_back(v);
-      }
-      S.ent.push_back(tmp[k].second);
-    }
-    if (!tmp.empty()) S.ent_ptr.push_back((int)S.ent.size());
-    S.slot_ptr[v + 1] = (int)S.slot_cam.size();
-  }
-}
-
+// Structure analysis (analysis.cpp, host) + upload of the index structures + allocation of the value buffers.
 static int analyze_and_upload(Solver& S) {
   auto T0 = std::chrono::steady_clock::now();
+  static const bool trace_setup = getenv("TSLAM_SETUP_TRACE") != nullptr;
   tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
   cudaStream_t st = ctx->stream;
-  const int K = d->n_cams; S.K = K;
-  const int GP = d->g_pobs, GT = d->g_tobs;
-  auto cf = [&](int k) { return d->h_cam_fixed[k] != 0; };
-  // ---- global layout (same on every rank) ----
-  std::vector<uint8_t> cu(K, 0), lu(d->n_points, 0), pu(d->n_planes, 0);
-  std::vector<uint8_t> gp_active(GP), gt_active(GT);
-  for (int i = 0; i < GP; ++i) {
-    const int c = d->h_p_cam[i], h = d->h_p_host[i], l = d->h_p_lm[i];
-    const bool act = !cf(c) || !cf(h) || !d->h_rho_fixed[l];
-    gp_active[i] = act;
-    if (act) { cu[c] = cu[h] = 1; lu[l] = 1; }
-  }
-  for (int i = 0; i < GT; ++i) {
-    const int c = d->h_t_cam[i], h = d->h_t_host[i], l = d->h_t_plane[i];
-    const bool act = !cf(c) || !cf(h) || !d->h_theta_fixed[l];
-    gt_active[i] = act;
-    if (act) { cu[c] = cu[h] = 1; pu[l] = 1; }
-  }
-  S.camslot.assign(K, -1); S.nc = 0;
-  for (int k = 0; k < K; ++k) if (cu[k] && !cf(k)) S.camslot[k] = S.nc++;
-  S.lmfree_p_h.assign(d->n_points, -1); S.nl = 0;
-  for (int k = 0; k < d->n_points; ++k) if (lu[k] && !d->h_rho_fixed[k]) S.lmfree_p_h[k] = S.nl++;
-  S.lmfree_t_h.assign(d->n_planes, -1); S.npl = 0;
-  for (int k = 0; k < d->n_planes; ++k) if (pu[k] && !d->h_theta_fixed[k]) S.lmfree_t_h[k] = S.npl++;
-  const int nc = S.nc;
-  S.n = 6 * nc;
-  S.Tn = chol_workspace_dims(S.n, &S.ld, &S.rows);
-  // ---- nested-dissection order of the free cameras (keyframes are temporally ordered, co-visibility is banded) ----
-  // Units of U cameras (U = multiple of 32 cameras = 3 tiles of 64 columns, at least the co-visibility bandwidth) are
-  // ordered leaves-first / separators-last so that the tile elimination DAG of chol.cu has ~log depth instead of being
-  // a chain; any order is valid, this one only shortens the critical path of the reduced-system factorisation.
-  if (nc >= 128) {
-    std::vector<int> dist;
-    dist.reserve((size_t)GP + GT);
-    for (int i = 0; i < GP; ++i) if (gp_active[i]) { const int a = S.camslot[d->h_p_cam[i]], b = S.camslot[d->h_p_host[i]]; if (a >= 0 && b >= 0) dist.push_back(std::abs(a - b)); }
-    for (int i = 0; i < GT; ++i) if (gt_active[i]) { const int a = S.camslot[d->h_t_cam[i]], b = S.camslot[d->h_t_host[i]]; if (a >= 0 && b >= 0) dist.push_back(std::abs(a - b)); }
-    int bw = 0;
-    if (!dist.empty()) { const size_t q = (size_t)(0.98 * (dist.size() - 1)); std::nth_element(dist.begin(), dist.begin() + q, dist.end()); bw = 2 * dist[q]; }
-    const int U = 32 * ((bw + 1 + 31) / 32);
-    const int nfull = nc / U;
-    if (nfull >= 4) {
-      std::vector<int> unit_order;
-      std::vector<std::pair<int, int>> stack;  // recursive bisection written iteratively (post-order: left, right, separator)
-      struct Frame { int lo, hi, stage; };
-      std::vector<Frame> st; st.push_back({0, nfull, 0});
-      while (!st.empty()) {
-        Frame f = st.back(); st.pop_back();
-        if (f.hi - f.lo <= 0) continue;
-        if (f.hi - f.lo <= 2) { for (int u = f.lo; u < f.hi; ++u) unit_order.push_back(u); continue; }
-        const int mid = (f.lo + f.hi) / 2;
-        if (f.stage == 0) { st.push_back({f.lo, f.hi, 1}); st.push_back({mid + 1, f.hi, 0}); st.push_back({f.lo, mid, 0}); }
-        else unit_order.push_back(mid);
-      }
-      std::vector<int> new_of_old(nc, -1);
-      int next = 0;
-      for (int u : unit_order) for (int c = u * U; c < (u + 1) * U; ++c) new_of_old[c] = next++;
-      for (int c = nfull * U; c < nc; ++c) new_of_old[c] = next++;   // the partial unit goes last (keeps units tile-aligned)
-      for (int k = 0; k < K; ++k) if (S.camslot[k] >= 0) S.camslot[k] = new_of_old[S.camslot[k]];
-    }
-  }
-
-  // ---- global block structure: unique (a<=b) camslot pairs from every active observation / landmark ----
-  // per landmark camslot sets (global), via sort of (landmark, camslot)
-  std::vector<uint64_t> bkeys;
-  // dense (a,b) -> block id table when nc^2 is small enough (O(1) insert / lookup); sorted-key fallback otherwise
-  const bool dense_tab = (size_t)nc * (size_t)nc <= ((size_t)1 << 24);
-  std::vector<int> btab;
-  if (dense_tab) btab.assign((size_t)nc * nc, -1); else bkeys.reserve((size_t)(GP + GT) * 3);
-  auto add_key = [&](int a, int b) {
-    if (a > b) std::swap(a, b);
-    if (dense_tab) btab[(size_t)a * nc + b] = 0; else bkeys.push_back((uint64_t)a * (uint64_t)nc + (uint64_t)b);
-  };
-  {
-    // direct pairs
-    for (int i = 0; i < GP; ++i) if (gp_active[i]) {
-      const int cs = S.camslot[d->h_p_cam[i]], hs = S.camslot[d->h_p_host[i]];
-      if (cs >= 0) add_key(cs, cs);
-      if (hs >= 0) add_key(hs, hs);
-      if (cs >= 0 && hs >= 0 && cs != hs) add_key(cs, hs);
-    }
-    for (int i = 0; i < GT; ++i) if (gt_active[i]) {
-      const int cs = S.camslot[d->h_t_cam[i]], hs = S.camslot[d->h_t_host[i]];
-      if (cs >= 0) add_key(cs, cs);
-      if (hs >= 0) add_key(hs, hs);
-      if (cs >= 0 && hs >= 0 && cs != hs) add_key(cs, hs);
-    }
-    // schur pairs: all pairs of distinct camslots touching the same free landmark
-    auto schur_pairs = [&](int n_obs, const std::vector<int32_t>& ocam, const std::vector<int32_t>& ohost, const std::vector<int32_t>& olm,
-                           const std::vector<uint8_t>& act, const std::vector<int>& lmfree, int nlm) {
-      std::vector<int> keys; std::vector<int> cams;
-      for (int i = 0; i < n_obs; ++i) {
-        if (!act[i] || lmfree[olm[i]] < 0) continue;
-        const int cs = S.camslot[ocam[i]], hs = S.camslot[ohost[i]];
-        if (cs >= 0) { keys.push_back(lmfree[olm[i]]); cams.push_back(cs); }
-        if (hs >= 0) { keys.push_back(lmfree[olm[i]]); cams.push_back(hs); }
-      }
-      std::vector<int> ptr, order;
-      build_csr(nlm, keys, ptr, order);
-      std::vector<int> set;
-      for (int l = 0; l < nlm; ++l) {
-        set.clear();
-        for (int e = ptr[l]; e < ptr[l + 1]; ++e) set.push_back(cams[order[e]]);
-        std::sort(set.begin(), set.end());
-        set.erase(std::unique(set.begin(), set.end()), set.end());
-        for (size_t x = 0; x < set.size(); ++x)
-          for (size_t y = x; y < set.size(); ++y) add_key(set[x], set[y]);
-      }
-    };
-    schur_pairs(GP, d->h_p_cam, d->h_p_host, d->h_p_lm, gp_active, S.lmfree_p_h, S.nl);
-    schur_pairs(GT, d->h_t_cam, d->h_t_host, d->h_t_plane, gt_active, S.lmfree_t_h, S.npl);
-  }
-  std::vector<int> blk_a, blk_b, diag_blk(nc, -1);
-  if (dense_tab) {
-    int nb = 0;
-    for (int a = 0; a < nc; ++a)
-      for (int b = a; b < nc; ++b)
-        if (btab[(size_t)a * nc + b] == 0) { btab[(size_t)a * nc + b] = nb++; blk_a.push_back(a); blk_b.push_back(b); }
-    S.nblk = nb;
-  } else {
-    std::sort(bkeys.begin(), bkeys.end());
-    bkeys.erase(std::unique(bkeys.begin(), bkeys.end()), bkeys.end());
-    S.nblk = (int)bkeys.size();
-    blk_a.resize(S.nblk); blk_b.resize(S.nblk);
-    for (int b = 0; b < S.nblk; ++b) { blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); blk_b[b] = (int)(bkeys[b] % (uint64_t)nc); }
-  }
-  for (int b = 0; b < S.nblk; ++b) if (blk_a[b] == blk_b[b]) diag_blk[blk_a[b]] = b;
-  {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
-    std::vector<uint8_t> tile_nz((size_t)S.Tn * S.Tn, 0);
-    for (int b = 0; b < S.nblk; ++b) {
-      // block (a,b'), a <= b' lands in rows 6b'..6b'+5, cols 6a..6a+5 of the lower triangle
-      const int r0 = 6 * blk_b[b] / 64, r1 = (6 * blk_b[b] + 5) / 64, c0 = 6 * blk_a[b] / 64, c1 = (6 * blk_a[b] + 5) / 64;
-      for (int r = r0; r <= r1; ++r) for (int c = c0; c <= c1; ++c) if (c <= r) tile_nz[(size_t)r * S.Tn + c] = 1;
-    }
-    int rc = chol_symbolic(ctx, S.n, tile_nz, &S.chol);
-    if (rc) return rc;
-  }
-  auto blk_of = [&](int a, int b) {
-    if (a > b) std::swap(a, b);
-    if (dense_tab) return btab[(size_t)a * nc + b];
-    const uint64_t key = (uint64_t)a * (uint64_t)nc + (uint64_t)b;
-    return (int)(std::lower_bound(bkeys.begin(), bkeys.end(), key) - bkeys.begin());
-  };
-
-  // ---- local observations ----
-  const int lp = d->n_pobs, lt = d->n_tobs; S.lp = lp; S.lt = lt;
-  auto gidx_p = [&](int i) { return d->sharded ? d->gsel_p[i] : i; };
-  auto gidx_t = [&](int i) { return d->sharded ? d->gsel_t[i] : i; };
-  std::vector<int> p_cs(lp), p_hs(lp), t_cs(lt), t_hs(lt);
-  std::vector<uint8_t> p_act(lp), t_act(lt), t_fm(lt);
-  std::vector<int32_t> lp_lm(lp), lt_lm(lt);
-  for (int i = 0; i < lp; ++i) {
-    const int g = gidx_p(i);
-    p_cs[i] = S.camslot[d->h_p_cam[g]]; p_hs[i] = S.camslot[d->h_p_host[g]]; lp_lm[i] = d->h_p_lm[g]; p_act[i] = gp_active[g];
-  }
-  for (int i = 0; i < lt; ++i) {
-    const int g = gidx_t(i);
-    t_cs[i] = S.camslot[d->h_t_cam[g]]; t_hs[i] = S.camslot[d->h_t_host[g]]; lt_lm[i] = d->h_t_plane[g]; t_act[i] = gt_active[g];
-    t_fm[i] = (uint8_t)((t_cs[i] >= 0 ? 1 : 0) | (t_hs[i] >= 0 ? 2 : 0) | (S.lmfree_t_h[lt_lm[i]] >= 0 ? 4 : 0));
-  }
-  LmStruct LP, LT;
-  build_landmark_side(lp, lp_lm.data(), p_cs, p_hs, p_act, S.lmfree_p_h, d->n_points, LP);
-  build_landmark_side(lt, lt_lm.data(), t_cs, t_hs, t_act, S.lmfree_t_h, d->n_planes, LT);
-  S.nvp = (int)LP.v_gl.size(); S.nvt = (int)LT.v_gl.size();
-  S.nsp = (int)LP.slot_cam.size(); S.nst = (int)LT.slot_cam.size();
-  S.vp_gl_h = LP.v_gl; S.vt_gl_h = LT.v_gl;
-
-  // ---- local entry lists per block ----
-  std::vector<int> kdp, vdp, kdt, vdt, ksp, kst;
-  std::vector<int2> vsp, vst;
-  auto direct = [&](int n_obs, const std::vector<int>& cs, const std::vector<int>& hs, const std::vector<uint8_t>& act,
-                    std::vector<int>& keys, std::vector<int>& vals) {
-    for (int i = 0; i < n_obs; ++i) {
-      if (!act[i]) continue;
-      const int c = cs[i], h = hs[i];
-      if (c >= 0) { keys.push_back(diag_blk[c]); vals.push_back((i << 2) | 0); }
-      if (h >= 0) { keys.push_back(diag_blk[h]); vals.push_back((i << 2) | 1); }
-      if (c >= 0 && h >= 0) {
-        if (c < h) { keys.push_back(blk_of(c, h)); vals.push_back((i << 2) | 2); }
-        else if (h < c) { keys.push_back(blk_of(h, c)); vals.push_back((i << 2) | 3); }
-        else {  // cam == host never happens in the reference (src/optimizer.cc:1397); keep the maths right anyway
-          keys.push_back(diag_blk[c]); vals.push_back((i << 2) | 2);
-          keys.push_back(diag_blk[c]); vals.push_back((i << 2) | 3);
-        }
-      }
-    }
-  };
-  direct(lp, p_cs, p_hs, p_act, kdp, vdp);
-  direct(lt, t_cs, t_hs, t_act, kdt, vdt);
-  auto schur = [&](const LmStruct& L, std::vector<int>& keys, std::vector<int2>& vals) {
-    const int nv = (int)L.v_gl.size();
-    for (int v = 0; v < nv; ++v)
-      for (int x = L.slot_ptr[v]; x < L.slot_ptr[v + 1]; ++x)
-        for (int y = x; y < L.slot_ptr[v + 1]; ++y) { keys.push_back(blk_of(L.slot_cam[x], L.slot_cam[y])); vals.push_back(make_int2(x, y)); }
-  };
-  schur(LP, ksp, vsp);
-  schur(LT, kst, vst);
-  auto csr_i = [&](const std::vector<int>& keys, const std::vector<int>& vals, std::vector<int>& ptr, std::vector<int>& out) {
-    std::vector<int> order; build_csr(S.nblk, keys, ptr, order);
-    out.resize(order.size());
-    for (size_t k = 0; k < order.size(); ++k) out[k] = vals[order[k]];
-  };
-  auto csr_2 = [&](const std::vector<int>& keys, const std::vector<int2>& vals, std::vector<int>& ptr, std::vector<int2>& out) {
-    std::vector<int> order; build_csr(S.nblk, keys, ptr, order);
-    out.resize(order.size());
-    for (size_t k = 0; k < order.size(); ++k) out[k] = vals[order[k]];
-  };
-  std::vector<int> bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr;
-  std::vector<int2> bsp, bst;
-  csr_i(kdp, vdp, bdp_ptr, bdp); csr_i(kdt, vdt, bdt_ptr, bdt);
-  csr_2(ksp, vsp, bsp_ptr, bsp); csr_2(kst, vst, bst_ptr, bst);
-
+  IndexView V;
+  V.n_cams = d->n_cams; V.n_points = d->n_points; V.n_planes = d->n_planes; V.g_pobs = d->g_pobs; V.g_tobs = d->g_tobs;
+  V.cam_fixed = d->h_cam_fixed.data(); V.rho_fixed = d->h_rho_fixed.data(); V.theta_fixed = d->h_theta_fixed.data();
+  V.p_cam = d->h_p_cam.data(); V.p_host = d->h_p_host.data(); V.p_lm = d->h_p_lm.data();
+  V.t_cam = d->h_t_cam.data(); V.t_host = d->h_t_host.data(); V.t_plane = d->h_t_plane.data();
+  V.lp = d->n_pobs; V.lt = d->n_tobs;
+  V.gsel_p = d->sharded ? d->gsel_p.data() : nullptr; V.gsel_t = d->sharded ? d->gsel_t.data() : nullptr;
+  Analysis A;
+  analyze_structure(V, A);
+  S.K = A.K; S.nc = A.nc; S.nl = A.nl; S.npl = A.npl; S.lp = A.lp; S.lt = A.lt;
+  S.nvp = A.nvp; S.nvt = A.nvt; S.nsp = A.nsp; S.nst = A.nst; S.nblk = A.nblk;
+  S.n = A.n; S.ld = A.ld; S.rows = A.rows; S.Tn = A.Tn;
+  const int K = A.K, nc = A.nc, lp = A.lp, lt = A.lt;
+  auto T1 = std::chrono::steady_clock::now();
   // ---- upload ----
-  TSL_CUDA(up(S.camslot_d, S.camslot, st));
-  TSL_CUDA(up(S.p_cs, p_cs, st)); TSL_CUDA(up(S.p_hs, p_hs, st)); TSL_CUDA(up(S.p_ls, LP.obs_ls, st));
-  TSL_CUDA(up(S.t_cs, t_cs, st)); TSL_CUDA(up(S.t_hs, t_hs, st)); TSL_CUDA(up(S.t_ls, LT.obs_ls, st));
-  TSL_CUDA(up(S.p_active, p_act, st)); TSL_CUDA(up(S.t_active, t_act, st)); TSL_CUDA(up(S.t_fmask, t_fm, st));
-  TSL_CUDA(up(S.vp_gl, LP.v_gl, st)); TSL_CUDA(up(S.vt_gl, LT.v_gl, st));
-  TSL_CUDA(up(S.vp_obs_ptr, LP.obs_ptr, st)); TSL_CUDA(up(S.vp_obs, LP.obs, st));
-  TSL_CUDA(up(S.vt_obs_ptr, LT.obs_ptr, st)); TSL_CUDA(up(S.vt_obs, LT.obs, st));
-  TSL_CUDA(up(S.sp_ptr, LP.slot_ptr, st)); TSL_CUDA(up(S.sp_cam, LP.slot_cam, st)); TSL_CUDA(up(S.sp_lm, LP.slot_lm, st));
-  TSL_CUDA(up(S.spe_ptr, LP.ent_ptr, st)); TSL_CUDA(up(S.spe, LP.ent, st));
-  TSL_CUDA(up(S.st_ptr, LT.slot_ptr, st)); TSL_CUDA(up(S.st_cam, LT.slot_cam, st)); TSL_CUDA(up(S.st_lm, LT.slot_lm, st));
-  TSL_CUDA(up(S.ste_ptr, LT.ent_ptr, st)); TSL_CUDA(up(S.ste, LT.ent, st));
-  TSL_CUDA(up(S.blk_a, blk_a, st)); TSL_CUDA(up(S.blk_b, blk_b, st)); TSL_CUDA(up(S.diag_blk, diag_blk, st));
-  TSL_CUDA(up(S.bdp_ptr, bdp_ptr, st)); TSL_CUDA(up(S.bdp, bdp, st)); TSL_CUDA(up(S.bdt_ptr, bdt_ptr, st)); TSL_CUDA(up(S.bdt, bdt, st));
-  TSL_CUDA(up(S.bsp_ptr, bsp_ptr, st)); TSL_CUDA(up(S.bsp, bsp, st)); TSL_CUDA(up(S.bst_ptr, bst_ptr, st)); TSL_CUDA(up(S.bst, bst, st));
+  int rc = chol_upload(ctx, A.chol, &S.chol);
+  if (rc) return rc;
+  TSL_CUDA(up(S.camslot_d, A.camslot, st));
+  TSL_CUDA(up(S.p_cs, A.p_cs, st)); TSL_CUDA(up(S.p_hs, A.p_hs, st)); TSL_CUDA(up(S.p_ls, A.LP.obs_ls, st));
+  TSL_CUDA(up(S.t_cs, A.t_cs, st)); TSL_CUDA(up(S.t_hs, A.t_hs, st)); TSL_CUDA(up(S.t_ls, A.LT.obs_ls, st));
+  TSL_CUDA(up(S.p_active, A.p_act, st)); TSL_CUDA(up(S.t_active, A.t_act, st)); TSL_CUDA(up(S.t_fmask, A.t_fm, st));
+  TSL_CUDA(up(S.vp_gl, A.LP.v_gl, st)); TSL_CUDA(up(S.vt_gl, A.LT.v_gl, st));
+  TSL_CUDA(up(S.vp_obs_ptr, A.LP.obs_ptr, st)); TSL_CUDA(up(S.vp_obs, A.LP.obs, st));
+  TSL_CUDA(up(S.vt_obs_ptr, A.LT.obs_ptr, st)); TSL_CUDA(up(S.vt_obs, A.LT.obs, st));
+  TSL_CUDA(up(S.sp_ptr, A.LP.slot_ptr, st)); TSL_CUDA(up(S.sp_cam, A.LP.slot_cam, st)); TSL_CUDA(up(S.sp_lm, A.LP.slot_lm, st));
+  TSL_CUDA(up(S.spe_ptr, A.LP.ent_ptr, st)); TSL_CUDA(up(S.spe, A.LP.ent, st));
+  TSL_CUDA(up(S.st_ptr, A.LT.slot_ptr, st)); TSL_CUDA(up(S.st_cam, A.LT.slot_cam, st)); TSL_CUDA(up(S.st_lm, A.LT.slot_lm, st));
+  TSL_CUDA(up(S.ste_ptr, A.LT.ent_ptr, st)); TSL_CUDA(up(S.ste, A.LT.ent, st));
+  TSL_CUDA(up(S.blk_a, A.blk_a, st)); TSL_CUDA(up(S.blk_b, A.blk_b, st)); TSL_CUDA(up(S.diag_blk, A.diag_blk, st));
+  TSL_CUDA(up(S.bdp_ptr, A.bdp_ptr, st)); TSL_CUDA(up(S.bdp, A.bdp, st)); TSL_CUDA(up(S.bdt_ptr, A.bdt_ptr, st)); TSL_CUDA(up(S.bdt, A.bdt, st));
+  TSL_CUDA(up(S.bsp_ptr, A.bsp_ptr, st)); TSL_CUDA(up_as(S.bsp, A.bsp, st)); TSL_CUDA(up(S.bst_ptr, A.bst_ptr, st)); TSL_CUDA(up_as(S.bst, A.bst, st));
   if (d->sharded) { TSL_CUDA(up(S.gsel_p, d->gsel_p, st)); TSL_CUDA(up(S.gsel_t, d->gsel_t, st)); }
   // ---- value buffers ----
   TSL_CUDA(S.xc_cams.reserve(7 * (size_t)K)); TSL_CUDA(S.xc_rho.reserve(d->n_points)); TSL_CUDA(S.xc_theta.reserve(3 * (size_t)d->n_planes));
@@ -964,8 +710,15 @@ static int analyze_and_upload(Solver& S) {
   const size_t nparts = 2 * ((size_t)(lp + 127) / 128 + (size_t)(8 * (size_t)lt + 127) / 128) + 2 * ((size_t)(S.nvp + 255) / 256 + (size_t)(S.nvt + 255) / 256) + 64;
   TSL_CUDA(S.parts.reserve(nparts));
   TSL_CUDA(S.fail.reserve(1));
-  TSL_CUDA(cudaStreamSynchronize(st));
-  S.setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+  TSL_CUDA(cudaStreamSynchronize(st));   // the host vectors of A go out of scope on return
+  S.camslot = std::move(A.camslot); S.vp_gl_h = std::move(A.LP.v_gl); S.vt_gl_h = std::move(A.LT.v_gl);
+  S.lmfree_p_h = std::move(A.lmfree_p); S.lmfree_t_h = std::move(A.lmfree_t);
+  auto T2 = std::chrono::steady_clock::now();
+  S.setup_ms = std::chrono::duration<double, std::milli>(T2 - T0).count();
+  if (trace_setup)
+    fprintf(stderr, "[tslam setup] host analysis %.3f ms (layout+order %.3f, landmark side %.3f, block structure %.3f, symbolic %.3f, gather lists %.3f); "
+            "index upload + buffers %.3f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), A.lap_ms[0], A.lap_ms[1], A.lap_ms[2], A.lap_ms[3],
+            A.lap_ms[4], std::chrono::duration<double, std::milli>(T2 - T1).count());
   return TSLAM_OK;
 }
 
@@ -1276,12 +1029,14 @@ extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solv
   tslam_dev_problem d;
   int rc = upload_problem(ctx, p, &d, /*shard=*/true);
   if (rc) return rc;
+  auto Tu = std::chrono::steady_clock::now();
   struct Guard { tslam_dev_problem* d; ~Guard() { free_solver(d); } } guard{&d};
   Solver* S = nullptr;
   if ((rc = get_solver(ctx, &d, &S))) return rc;
   auto T1 = std::chrono::steady_clock::now();
   tslam_solve_summary sum{};
   if ((rc = run_lm(*S, opt, opt->max_iters, &sum, trace))) return rc;
+  auto Tlm = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
   // ---- results back to the caller's arrays ----
   if (ctx->world > 1) {
@@ -1326,6 +1081,10 @@ extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solv
   }
   TSL_CUDA(cudaStreamSynchronize(st));
   auto T2 = std::chrono::steady_clock::now();
+  if (getenv("TSLAM_SETUP_TRACE"))
+    fprintf(stderr, "[tslam solve] upload %.3f ms, analysis %.3f ms, lm %.3f ms, download %.3f ms\n", std::chrono::duration<double, std::milli>(Tu - T0).count(),
+            std::chrono::duration<double, std::milli>(T1 - Tu).count(), std::chrono::duration<double, std::milli>(Tlm - T1).count(),
+            std::chrono::duration<double, std::milli>(T2 - Tlm).count());
   sum.setup_ms = std::chrono::duration<double, std::milli>(T1 - T0).count();
   sum.total_ms = std::chrono::duration<double, std::milli>(T2 - T0).count();
   if (summary) *summary = sum;

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <chrono>
 #include "ctx.cuh"
+#include "analysis.hpp"
 
 namespace tsl {
 
@@ -132,6 +133,40 @@ extern "C" {
 const char* tslam_last_error(void) { return g_last_error.c_str(); }
 int tslam_version(void) { return 100; }
 long long tslam_launch_count(void) { return g_launches; }
+
+int tslam_analyze_structure(const tslam_ba_problem* p, int rank, int world, tslam_structure_info* out) {
+  if (!p || !out) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return set_error(TSLAM_ERR_ARG, "bad rank/world %d/%d", rank, world);
+  if (p->n_cams <= 0) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
+  for (int i = 0; i < p->n_pobs; ++i)
+    if ((unsigned)p->p_cam[i] >= (unsigned)p->n_cams || (unsigned)p->p_host[i] >= (unsigned)p->n_cams || (unsigned)p->p_lm[i] >= (unsigned)p->n_points)
+      return set_error(TSLAM_ERR_ARG, "point observation %d has an index out of range", i);
+  for (int i = 0; i < p->n_tobs; ++i)
+    if ((unsigned)p->t_cam[i] >= (unsigned)p->n_cams || (unsigned)p->t_host[i] >= (unsigned)p->n_cams || (unsigned)p->t_plane[i] >= (unsigned)p->n_planes)
+      return set_error(TSLAM_ERR_ARG, "text block %d has an index out of range", i);
+  std::vector<uint8_t> zc(p->n_cams, 0), zr(p->n_points, 0), zt(p->n_planes, 0);
+  IndexView V;
+  V.n_cams = p->n_cams; V.n_points = p->n_points; V.n_planes = p->n_planes; V.g_pobs = p->n_pobs; V.g_tobs = p->n_tobs;
+  V.cam_fixed = p->cam_fixed ? p->cam_fixed : zc.data(); V.rho_fixed = p->rho_fixed ? p->rho_fixed : zr.data();
+  V.theta_fixed = p->theta_fixed ? p->theta_fixed : zt.data();
+  V.p_cam = p->p_cam; V.p_host = p->p_host; V.p_lm = p->p_lm; V.t_cam = p->t_cam; V.t_host = p->t_host; V.t_plane = p->t_plane;
+  std::vector<int32_t> gp, gt;
+  if (world > 1) {
+    for (int i = 0; i < p->n_pobs; ++i) if (obs_owner(!V.rho_fixed[p->p_lm[i]], p->p_lm[i], i, world) == rank) gp.push_back(i);
+    for (int i = 0; i < p->n_tobs; ++i) if (obs_owner(!V.theta_fixed[p->t_plane[i]], p->t_plane[i], i, world) == rank) gt.push_back(i);
+    V.lp = (int)gp.size(); V.lt = (int)gt.size(); V.gsel_p = gp.data(); V.gsel_t = gt.data();
+    if (!V.gsel_p) V.gsel_p = &rank; if (!V.gsel_t) V.gsel_t = &rank;   // empty shard: any non-null pointer marks "sharded"
+  } else { V.lp = p->n_pobs; V.lt = p->n_tobs; }
+  Analysis A;
+  analyze_structure(V, A);
+  memset(out, 0, sizeof(*out));
+  out->n_free_cams = A.nc; out->n_free_points = A.nl; out->n_free_planes = A.npl; out->reduced_dim = A.n; out->n_blocks = A.nblk;
+  out->n_local_pobs = A.lp; out->n_local_tobs = A.lt; out->n_owned_points = A.nvp; out->n_owned_planes = A.nvt;
+  out->n_slots_point = A.nsp; out->n_slots_text = A.nst; out->n_tiles = A.Tn; out->n_waves = A.chol.nwaves; out->n_tile_updates = A.chol.gemm_tiles;
+  out->n_schur_entries = (int64_t)A.bsp.size() + (int64_t)A.bst.size(); out->n_direct_entries = (int64_t)A.bdp.size() + (int64_t)A.bdt.size();
+  out->analysis_ms = A.lap_ms[5];
+  return TSLAM_OK;
+}
 
 int tslam_ctx_create(int device_id, tslam_ctx** out) {
   if (!out) return set_error(TSLAM_ERR_ARG, "out == NULL");

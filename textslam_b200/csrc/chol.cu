@@ -13,7 +13,7 @@
 //
 // Tile sparsity: the camera graph of a SLAM map is mostly banded (co-visibility), so most 64x64
 // tiles of S and of its factor are structurally zero. The host does a symbolic factorisation on the
-// Tn x Tn tile pattern once per problem (ChoSymbolic) and every panel step only touches the listed
+// Tn x Tn tile pattern once per problem (analysis.cpp: chol_symbolic_host) and every panel step only touches the listed
 // non-zero tiles; a dense pattern degenerates to the classic right-looking blocked algorithm.
 //
 // Tile routines: fully unrolled, rows in registers (Crout). Measured alternatives (profiles/r1_notes.md): shared-memory
@@ -372,88 +372,23 @@ __global__ void copy_row_kernel(const double* __restrict__ src, double* __restri
 // ---------------------------------------------------------------------------------------------
 // host: symbolic tile factorisation + launch sequence
 // ---------------------------------------------------------------------------------------------
-int chol_workspace_dims(int n, int* ld, int* rows) {
-  const int Tn = (n + NB - 1) / NB;
-  *ld = Tn * NB;
-  *rows = (Tn + 1) * NB;
-  return Tn;
-}
-
-// tile_nz: Tn x Tn row-major flags of the lower-triangular tile pattern of S (diagonal always set).
-// Besides the fill pattern this computes a LEVEL SCHEDULE of the tile elimination DAG: panel j can start once every
-// panel k < j with L[j][k] != 0 is finished; panels of one wave are mutually independent, so a wave is three
-// launches (factor+solve, update, and later the backward solve) however many panels it holds. With the nested-
-// dissection camera order chosen by the solver a banded problem needs ~15 waves instead of T = 47 panel steps.
-int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, CholSymbolic* sym) {
-  int ld, rows;
-  const int Tn = chol_workspace_dims(n, &ld, &rows);
-  sym->Tn = Tn; sym->n = n;
-  const int T1 = Tn + 1;  // + the b tile row (dense)
-  std::vector<uint8_t> P((size_t)T1 * T1, 0);
-  for (int i = 0; i < Tn; ++i)
-    for (int k = 0; k <= i; ++k) P[(size_t)i * T1 + k] = (i == k) || tile_nz[(size_t)i * Tn + k];
-  for (int k = 0; k < Tn; ++k) P[(size_t)Tn * T1 + k] = 1;
-  // symbolic factorisation (fill)
-  std::vector<std::vector<int>> below(Tn);
-  for (int j = 0; j < Tn; ++j) {
-    std::vector<int>& nz = below[j];
-    for (int i = j + 1; i < T1; ++i) if (P[(size_t)i * T1 + j]) nz.push_back(i);
-    for (size_t a = 0; a < nz.size(); ++a)
-      for (size_t b = 0; b <= a; ++b) P[(size_t)nz[a] * T1 + nz[b]] = 1;
-  }
-  // level schedule
-  std::vector<int> wave(Tn, 0);
-  int nwaves = 0;
-  for (int j = 0; j < Tn; ++j) {
-    int w = 0;
-    for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, wave[k] + 1);
-    wave[j] = w; nwaves = std::max(nwaves, w + 1);
-  }
-  sym->nwaves = nwaves;
-  std::vector<std::vector<int>> wave_panels(nwaves);
-  for (int j = 0; j < Tn; ++j) wave_panels[wave[j]].push_back(j);
-  std::vector<int2> items, targets; std::vector<int> src_ptr, src, panels, below_ptr, below_l;
-  sym->item_ptr.assign(nwaves + 1, 0); sym->target_ptr.assign(nwaves + 1, 0); sym->panel_ptr.assign(nwaves + 1, 0);
-  src_ptr.push_back(0); below_ptr.push_back(0);
-  long long gemm_tiles = 0;
-  std::vector<int> tgt_index((size_t)T1 * T1, -1);
-  for (int w = 0; w < nwaves; ++w) {
-    const size_t t_begin = targets.size();
-    std::vector<std::vector<int>> tsrc;
-    for (int j : wave_panels[w]) {
-      items.push_back(make_int2(j, -1));
-      for (int i : below[j]) items.push_back(make_int2(j, i));
-      const std::vector<int>& nz = below[j];
-      for (size_t a = 0; a < nz.size(); ++a)
-        for (size_t b = 0; b <= a; ++b) {
-          const int i = nz[a], k = nz[b];
-          if (i == Tn && k == Tn) continue;   // (b row, b row) is never read
-          int& ti = tgt_index[(size_t)i * T1 + k];
-          if (ti < (int)t_begin) { ti = (int)targets.size(); targets.push_back(make_int2(i, k)); tsrc.emplace_back(); }
-          tsrc[ti - t_begin].push_back(j);
-          ++gemm_tiles;
-        }
-      // backward solve: tiles (i, j) of the factor below the diagonal, excluding the b row
-      panels.push_back(j);
-      for (int i : below[j]) if (i < Tn) below_l.push_back(i);
-      below_ptr.push_back((int)below_l.size());
-    }
-    for (auto& v : tsrc) { for (int j : v) src.push_back(j); src_ptr.push_back((int)src.size()); }
-    for (size_t t = t_begin; t < targets.size(); ++t) tgt_index[(size_t)targets[t].x * T1 + targets[t].y] = -1;
-    sym->item_ptr[w + 1] = (int)items.size(); sym->target_ptr[w + 1] = (int)targets.size(); sym->panel_ptr[w + 1] = (int)panels.size();
-  }
-  sym->gemm_tiles = gemm_tiles;
+// Device copy of the tile-level symbolic factorisation + level schedule computed on the host (analysis.cpp:
+// chol_symbolic_host): per wave the (panel, row tile) items of potrf_trsm_kernel, the target tiles of syrk_wave_kernel
+// with their source panels, and the panel / below lists of the backward solve.
+int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
+  sym->Tn = H.Tn; sym->n = H.n; sym->nwaves = H.nwaves; sym->gemm_tiles = H.gemm_tiles;
+  sym->item_ptr = H.item_ptr; sym->target_ptr = H.target_ptr; sym->panel_ptr = H.panel_ptr;
   cudaStream_t s = ctx->stream;
-  TSL_CUDA(sym->items.upload(items.data(), items.size(), s));
-  TSL_CUDA(sym->targets.upload(targets.data(), targets.size(), s));
-  TSL_CUDA(sym->src_ptr.upload(src_ptr.data(), src_ptr.size(), s));
-  TSL_CUDA(sym->src.upload(src.data(), src.size(), s));
-  TSL_CUDA(sym->panels.upload(panels.data(), panels.size(), s));
-  TSL_CUDA(sym->below_ptr.upload(below_ptr.data(), below_ptr.size(), s));
-  TSL_CUDA(sym->below.upload(below_l.data(), below_l.size(), s));
-  TSL_CUDA(sym->Ldiag.reserve((size_t)(Tn ? Tn : 1) * NB * NB));
-  TSL_CUDA(cudaStreamSynchronize(s));
-  return TSLAM_OK;
+  static_assert(sizeof(I2) == sizeof(int2), "I2 must match int2");
+  TSL_CUDA(sym->items.upload(reinterpret_cast<const int2*>(H.items.data()), H.items.size(), s));
+  TSL_CUDA(sym->targets.upload(reinterpret_cast<const int2*>(H.targets.data()), H.targets.size(), s));
+  TSL_CUDA(sym->src_ptr.upload(H.src_ptr.data(), H.src_ptr.size(), s));
+  TSL_CUDA(sym->src.upload(H.src.data(), H.src.size(), s));
+  TSL_CUDA(sym->panels.upload(H.panels.data(), H.panels.size(), s));
+  TSL_CUDA(sym->below_ptr.upload(H.below_ptr.data(), H.below_ptr.size(), s));
+  TSL_CUDA(sym->below.upload(H.below.data(), H.below.size(), s));
+  TSL_CUDA(sym->Ldiag.reserve((size_t)(H.Tn ? H.Tn : 1) * NB * NB));
+  return TSLAM_OK;   // the caller synchronises the stream before H goes away
 }
 
 // Factor + solve. A: (Tn+1)*64 x ld as described above. xout: ld doubles (receives y, then x).

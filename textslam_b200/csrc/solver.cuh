@@ -1,6 +1,7 @@
 // Internal interfaces between the solver translation units.
 #pragma once
 #include "ctx.cuh"
+#include "analysis.hpp"
 
 namespace tsl {
 
@@ -14,8 +15,7 @@ struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (pe
   mutable DevBuf<double> Ldiag;                       // Tn inverse diagonal factors L_jj^-1 (64x64, tight)
   long long gemm_tiles = 0;                           // number of 64x64x64 tile updates (2*64^3 flop each)
 };
-int chol_workspace_dims(int n, int* ld, int* rows);
-int chol_symbolic(tslam_ctx* ctx, int n, const std::vector<uint8_t>& tile_nz, CholSymbolic* sym);
+int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);   // device copy of the host symbolic factorisation (analysis.cpp)
 int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail);
 
 // ba_eval.cu (robustified evaluation used inside the LM loop)
