@@ -13,6 +13,8 @@ struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (pe
   DevBuf<int> src_ptr, src;                           // per target: source panels of its wave
   DevBuf<int> panels, below_ptr, below;               // backward solve: panels per wave and their non-zero tiles below
   mutable DevBuf<double> Ldiag;                       // Tn inverse diagonal factors L_jj^-1 (64x64, tight)
+  mutable DevBuf<int> flags;                          // backward solve: flags[j] == epoch <=> x_j final in the current call
+  mutable int epoch = 0;
   long long gemm_tiles = 0;                           // number of 64x64x64 tile updates (2*64^3 flop each)
 };
 int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);   // device copy of the host symbolic factorisation (analysis.cpp)
