@@ -384,7 +384,8 @@ void analyze_structure(const IndexView& V, Analysis& A) {
     A.blk_a.resize(A.nblk); A.blk_b.resize(A.nblk);
     for (int b = 0; b < A.nblk; ++b) { A.blk_a[b] = (int)(bkeys[b] / (uint64_t)nc); A.blk_b[b] = (int)(bkeys[b] % (uint64_t)nc); }
   }
-  for (int b = 0; b < A.nblk; ++b) if (A.blk_a[b] == A.blk_b[b]) A.diag_blk[A.blk_a[b]] = b;
+  A.offdiag_blk.clear();
+  for (int b = 0; b < A.nblk; ++b) { if (A.blk_a[b] == A.blk_b[b]) A.diag_blk[A.blk_a[b]] = b; else A.offdiag_blk.push_back(b); }
   A.lap_ms[2] = T.lap();
   {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
     std::vector<uint8_t> tile_nz((size_t)A.Tn * A.Tn, 0);

@@ -43,7 +43,7 @@ struct Analysis {
   std::vector<int> p_cs, p_hs, t_cs, t_hs;             // per local observation: camera slots (or -1)
   std::vector<uint8_t> p_act, t_act, t_fm;
   LmSide LP, LT;
-  std::vector<int> blk_a, blk_b, diag_blk;
+  std::vector<int> blk_a, blk_b, diag_blk, offdiag_blk;   // diag_blk[c] = block (c,c); offdiag_blk = ids of the blocks with a < b
   std::vector<int> bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr;
   std::vector<I2> bsp, bst;
   CholHost chol;

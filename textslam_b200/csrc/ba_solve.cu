@@ -239,9 +239,14 @@ struct BlockArgs {
   double* udiag;  // 6 nc : diagonal of the scaled J_c'J_c (the LM damping term is built from it after the reduce)
 };
 
-__global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
-  const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (blk >= A.nblk) return;
+// G lanes per block (G = 32 for the diagonal blocks, which carry ~650 gather entries each on the global-BA shape;
+// G = 8 for the off-diagonal ones with ~35): the fixed cost of a block is the butterfly reduction of its 36 partial
+// sums (36 x log2(G) 64-bit shuffles), which dominated when every block had a whole warp.
+template <int G>
+__global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int* __restrict__ list, int nlist) {
+  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x & (G - 1);
+  const bool valid = gi < nlist;           // lanes of an empty group still take part in the full-warp shuffles
+  const int blk = valid ? list[gi] : 0;
   const int a = A.blk_a[blk], b = A.blk_b[blk];
   const bool diag = a == b;
   double sa[6], sb[6];
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) gr[k] = 0.0;
   // ---- direct J_a' J_b terms (scaled on load) ----
-  for (int e = A.L.dp_ptr[blk] + lane; e < A.L.dp_ptr[blk + 1]; e += 32) {
+  for (int e = A.L.dp_ptr[blk] + lane, e1 = valid ? A.L.dp_ptr[blk + 1] : 0; e < e1; e += G) {
     const int code = A.L.dp[e]; int ox, oy; code_offsets(code & 3, ox, oy);
     const int i = code >> 2;
     const double* Ji = A.pJ + (size_t)i * 26;
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
       }
     }
   }
-  for (int e = A.L.dt_ptr[blk] + lane; e < A.L.dt_ptr[blk + 1]; e += 32) {
+  for (int e = A.L.dt_ptr[blk] + lane, e1 = valid ? A.L.dt_ptr[blk + 1] : 0; e < e1; e += G) {
     const int code = A.L.dt[e]; int ox, oy; code_offsets(code & 3, ox, oy);
     const int i = code >> 2;
     const double* Ji = A.tJ + (size_t)i * 120;
@@ -292,24 +297,11 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
       }
     }
   }
+  double dd[6], bred[6];   // diagonal of the direct part (LM damping is built from it), Schur part of the right-hand side
 #pragma unroll
-  for (int k = 0; k < 36; ++k)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-  double bred[6];
-  if (diag) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gr[k] += __shfl_xor_sync(0xffffffffu, gr[k], o);
-      bred[k] = 0.0;
-    }
-  }
-  // ---- Schur terms: - E_i V^-1 E_j' (and - E_i V^-1 g for the right-hand side) ----
-  double sch[36];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) sch[k] = 0.0;
-  for (int e = A.L.sp_ptr[blk] + lane; e < A.L.sp_ptr[blk + 1]; e += 32) {
+  for (int k = 0; k < 6; ++k) { dd[k] = acc[7 * k]; bred[k] = 0.0; }
+  // ---- Schur terms: - E_i V^-1 E_j' (and - E_i V^-1 g for the right-hand side), subtracted in place ----
+  for (int e = A.L.sp_ptr[blk] + lane, e1 = valid ? A.L.sp_ptr[blk + 1] : 0; e < e1; e += G) {
     const int2 sl = A.L.sp[e];
     const double* Ei = A.Ep + (size_t)sl.x * 6;
     const double* Ej = A.Ep + (size_t)sl.y * 6;
@@ -321,14 +313,14 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
 #pragma unroll
     for (int p = 0; p < 6; ++p)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) sch[p * 6 + q] += ei[p] * Ej[q];
+      for (int q = 0; q < 6; ++q) acc[p * 6 + q] -= ei[p] * Ej[q];
     if (diag && sl.x == sl.y) {
       const double gl = A.gp[lm];
 #pragma unroll
       for (int p = 0; p < 6; ++p) bred[p] += ei[p] * gl;
     }
   }
-  for (int e = A.L.st_ptr[blk] + lane; e < A.L.st_ptr[blk + 1]; e += 32) {
+  for (int e = A.L.st_ptr[blk] + lane, e1 = valid ? A.L.st_ptr[blk + 1] : 0; e < e1; e += G) {
     const int2 sl = A.L.st[e];
     const double* Ei = A.Et + (size_t)sl.x * 18;
     const double* Ej = A.Et + (size_t)sl.y * 18;
@@ -342,38 +334,37 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A) {
 #pragma unroll
     for (int p = 0; p < 6; ++p)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) sch[p * 6 + q] += ev[p * 3] * Ej[q * 3] + ev[p * 3 + 1] * Ej[q * 3 + 1] + ev[p * 3 + 2] * Ej[q * 3 + 2];
+      for (int q = 0; q < 6; ++q) acc[p * 6 + q] -= ev[p * 3] * Ej[q * 3] + ev[p * 3 + 1] * Ej[q * 3 + 1] + ev[p * 3 + 2] * Ej[q * 3 + 2];
     if (diag && sl.x == sl.y) {
       const double* gl = A.gt + (size_t)lm * 3;
 #pragma unroll
       for (int p = 0; p < 6; ++p) bred[p] += ev[p * 3] * gl[0] + ev[p * 3 + 1] * gl[1] + ev[p * 3 + 2] * gl[2];
     }
   }
+  // ---- reduce over the G lanes of the group (butterfly: every lane ends with the total) ----
 #pragma unroll
   for (int k = 0; k < 36; ++k)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sch[k] += __shfl_xor_sync(0xffffffffu, sch[k], o);
-  if (diag) {
+    for (int o = G / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  if (G == 32 ? diag : __any_sync(0xffffffffu, diag)) {   // G == 32: the branch is warp-uniform
 #pragma unroll
     for (int k = 0; k < 6; ++k)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) bred[k] += __shfl_xor_sync(0xffffffffu, bred[k], o);
+      for (int o = G / 2; o > 0; o >>= 1) {
+        gr[k] += __shfl_xor_sync(0xffffffffu, gr[k], o);
+        dd[k] += __shfl_xor_sync(0xffffffffu, dd[k], o);
+        bred[k] += __shfl_xor_sync(0xffffffffu, bred[k], o);
+      }
   }
-  if (diag) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (lane == k) A.udiag[6 * a + k] = acc[7 * k];
-  }
-#pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] -= sch[k];
+  if (!valid) return;
   double* out = A.Sblk + (size_t)blk * 36;
 #pragma unroll
   for (int k = 0; k < 36; ++k)
-    if ((k & 31) == lane) out[k] = acc[k];
+    if ((k % G) == lane) out[k] = acc[k];
   if (diag) {
 #pragma unroll
     for (int k = 0; k < 6; ++k)
-      if (lane == k) { A.bvec[6 * a + k] = gr[k] - bred[k]; A.graw[6 * a + k] = gr[k] / sa[k]; }
+      if (lane == k) { A.udiag[6 * a + k] = dd[k]; A.bvec[6 * a + k] = gr[k] - bred[k]; A.graw[6 * a + k] = gr[k] / sa[k]; }
   }
 }
 
@@ -615,6 +606,7 @@ struct Solver {
   DevBuf<uint8_t> p_active, t_active, t_fmask;
   DevBuf<int> vp_gl, vt_gl, vp_obs_ptr, vp_obs, vt_obs_ptr, vt_obs;
   DevBuf<int> sp_ptr, sp_cam, sp_lm, spe_ptr, spe, st_ptr, st_cam, st_lm, ste_ptr, ste;
+  DevBuf<int> offdiag_blk; int noff = 0;
   DevBuf<int> blk_a, blk_b, diag_blk, bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr, gsel_p, gsel_t;
   DevBuf<int2> bsp, bst;
   // values
@@ -685,6 +677,7 @@ static int analyze_and_upload(Solver& S) {
   TSL_CUDA(up(S.st_ptr, A.LT.slot_ptr, st)); TSL_CUDA(up(S.st_cam, A.LT.slot_cam, st)); TSL_CUDA(up(S.st_lm, A.LT.slot_lm, st));
   TSL_CUDA(up(S.ste_ptr, A.LT.ent_ptr, st)); TSL_CUDA(up(S.ste, A.LT.ent, st));
   TSL_CUDA(up(S.blk_a, A.blk_a, st)); TSL_CUDA(up(S.blk_b, A.blk_b, st)); TSL_CUDA(up(S.diag_blk, A.diag_blk, st));
+  TSL_CUDA(up(S.offdiag_blk, A.offdiag_blk, st)); S.noff = (int)A.offdiag_blk.size();
   TSL_CUDA(up(S.bdp_ptr, A.bdp_ptr, st)); TSL_CUDA(up(S.bdp, A.bdp, st)); TSL_CUDA(up(S.bdt_ptr, A.bdt_ptr, st)); TSL_CUDA(up(S.bdt, A.bdt, st));
   TSL_CUDA(up(S.bsp_ptr, A.bsp_ptr, st)); TSL_CUDA(up_as(S.bsp, A.bsp, st)); TSL_CUDA(up(S.bst_ptr, A.bst_ptr, st)); TSL_CUDA(up_as(S.bst, A.bst, st));
   if (d->sharded) { TSL_CUDA(up(S.gsel_p, d->gsel_p, st)); TSL_CUDA(up(S.gsel_t, d->gsel_t, st)); }
@@ -814,7 +807,9 @@ static int compute_step(Solver& S, double radius) {
     B.Ep = S.Ep.p; B.Vinvp = S.Vinvp.p; B.gp = S.gp.p; B.sp_lm = S.sp_lm.p;
     B.Et = S.Et.p; B.Vinvt = S.Vinvt.p; B.gt = S.gt.p; B.st_lm = S.st_lm.p;
     B.Sblk = S.Sblk; B.bvec = S.bvec; B.graw = S.graw; B.udiag = S.udiag;
-    LAUNCH(schur_block_kernel<<<grid_for(S.nblk * 32, 128), 128, 0, st>>>(B));
+    // diagonal blocks (heavy gather lists) get a warp each, off-diagonal blocks 8 lanes
+    LAUNCH(schur_block_kernel<32><<<grid_for(S.nc * 32, 128), 128, 0, st>>>(B, S.diag_blk.p, S.nc));
+    if (S.noff) LAUNCH(schur_block_kernel<8><<<grid_for(S.noff * 8, 128), 128, 0, st>>>(B, S.offdiag_blk.p, S.noff));
     TSL_CHECK_LAUNCH();
   }
   mark(S, 3);  // all-reduce
@@ -824,7 +819,7 @@ static int compute_step(Solver& S, double radius) {
   }
   mark(S, 4);  // Cholesky
   if (nc) {
-    TSL_CUDA(cudaMemsetAsync(S.A.p, 0, (size_t)S.rows * S.ld * sizeof(double), st));
+    { int rc = chol_clear(ctx, S.chol, S.A.p); if (rc) return rc; }
     ScatterArgs Sa{S.nblk, S.blk_a.p, S.blk_b.p, S.Sblk, S.bvec, S.udiag, inv_radius, S.A.p, S.ld, S.n, S.rows, S.Tn * 64};
     const int total = S.nblk * 36 + S.ld;
     LAUNCH(scatter_kernel<<<grid_for(total, 256), 256, 0, st>>>(Sa));

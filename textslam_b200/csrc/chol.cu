@@ -222,6 +222,14 @@ __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict
   if (threadIdx.x == 0) { __threadfence(); *reinterpret_cast<volatile int*>(flags + j) = epoch; }
 }
 
+// Zero the tiles of the factor pattern (one CTA per (panel, row tile) item = one 64x64 tile) before the reduced system is
+// scattered into them: the dense workspace is 10x larger than its structurally non-zero part on a SLAM camera graph.
+__global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items) {
+  const int2 it = items[blockIdx.x];
+  double* T = A + (size_t)(it.y < 0 ? it.x : it.y) * NB * ld + (size_t)it.x * NB;
+  for (int e = threadIdx.x; e < NB * NB / 2; e += 256) { const int r = e >> 5, c = (e & 31) * 2; *reinterpret_cast<double2*>(T + (size_t)r * ld + c) = make_double2(0.0, 0.0); }
+}
+
 __global__ void copy_row_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -250,6 +258,16 @@ int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
   TSL_CUDA(cudaMemsetAsync(sym->flags.p, 0, sizeof(int) * (size_t)(H.Tn ? H.Tn : 1), s));
   sym->epoch = 0;
   return TSLAM_OK;   // the caller synchronises the stream before H goes away
+}
+
+// Clears every tile the factorisation reads or writes (pattern of L incl. the b row); everything else is never touched.
+int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A) {
+  int ld, rows;
+  chol_workspace_dims(sym.n, &ld, &rows);
+  const int ni = sym.item_ptr[sym.nwaves];
+  if (ni > 0) LAUNCH(zero_tiles_kernel<<<ni, 256, 0, ctx->stream>>>(A, ld, sym.items.p));
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
 }
 
 // Factor + solve. A: (Tn+1)*64 x ld as described above. xout: ld doubles (receives y, then x).

@@ -300,15 +300,17 @@ __device__ __noinline__ void gemm_nt32_il(double* C, const double* A, const doub
     for (int j = 0; j < 4; ++j) C[(rg + nrg * i) * LD2 + cg + 8 * j] -= acc[i][j];
 }
 
-// Factor the 64x64 diagonal tile in sT (lower, LD2) and solve X L^T = B for the 64 rows of sX, with the warps of a
-// 128-thread CTA working on different parts of the dependency graph:
+// Factor the 64x64 diagonal tile in sT (lower, LD2) and solve X L^T = B for the 64 rows of sX (128-thread CTA):
 //   phase 1  warp 0: L11 = chol(A11)
-//   phase 2  warp 0: L21 = A21 L11^-T            | warps 2,3: X1 = B1 L11^-T
-//   phase 3  all   : A22 -= L21 L21^T
-//   phase 4  warp 0: L22 = chol(A22)             | warps 2,3: B2 -= X1 L21^T
+//   phase 2  warp 0: L21 = A21 L11^-T            | warps 2,3: X1 = B1 L11^-T        (same code on both sides)
+//   phase 3  all   : A22 -= L21 L21^T ;  B2 -= X1 L21^T
+//   phase 4  warp 0: L22 = chol(A22)
 //   phase 5  warps 0,1: X2 = B2 L22^-T
-// sLt receives L11^T and L22^T (diagonal blocks only). STAMPS: optional clock64() trace for the micro-benchmark.
-template <bool STAMPS, int EXPERIMENT = 0>
+// sLt receives L11^T and L22^T (diagonal blocks only). Measured (tools/ubench/chol_tile_bench.cu): running the B2 update
+// on warps 2,3 WHILE warp 0 factors A22 is 3x slower than doing them one after the other (30.2k vs 7.2k + 2.5k cycles):
+// two different unrolled instruction streams on one SM evict each other from the instruction cache, so phases only
+// ever overlap identical code. STAMPS: optional clock64() trace for the micro-benchmark.
+template <bool STAMPS>
 __device__ __forceinline__ void factor_solve_tile(double* sT, double* sX, double* sLt, double* sinv, int* fail, long long* stamps) {
   const int tid = threadIdx.x, warp = tid >> 5;
 #define TSL_STAMP(k) do { if (STAMPS && tid == 0) stamps[k] = clock64(); } while (0)
@@ -320,20 +322,10 @@ __device__ __forceinline__ void factor_solve_tile(double* sT, double* sX, double
   __syncthreads();
   TSL_STAMP(3);
   gemm_nt32_il<2>(sT + HB * LD2 + HB, sT + HB * LD2, sT + HB * LD2, HB, tid);
+  gemm_nt32_il<4>(sX + HB, sX, sT + HB * LD2, NB, tid);
   __syncthreads();
   TSL_STAMP(4);
-  if (EXPERIMENT == 0) {
-    if (warp == 0) potrf32_rl(sT + HB * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB, fail);
-    else if (warp >= 2) gemm_nt32_il<8>(sX + HB, sX, sT + HB * LD2, NB, tid - 64);
-  } else if (EXPERIMENT == 1) {   // micro-benchmark only: factorisation alone
-    if (warp == 0) potrf32_rl(sT + HB * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB, fail);
-  } else if (EXPERIMENT == 2) {   // micro-benchmark only: X2 update alone
-    if (warp >= 2) gemm_nt32_il<8>(sX + HB, sX, sT + HB * LD2, NB, tid - 64);
-  } else {                        // micro-benchmark only: one after the other, X2 update on all four warps
-    if (warp == 0) potrf32_rl(sT + HB * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB, fail);
-    __syncthreads();
-    gemm_nt32_il<4>(sX + HB, sX, sT + HB * LD2, NB, tid);
-  }
+  if (warp == 0) potrf32_rl(sT + HB * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB, fail);
   __syncthreads();
   TSL_STAMP(5);
   if (warp < 2) trsm32_row(sX + tid * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB);

@@ -18,6 +18,7 @@ struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (pe
   long long gemm_tiles = 0;                           // number of 64x64x64 tile updates (2*64^3 flop each)
 };
 int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);   // device copy of the host symbolic factorisation (analysis.cpp)
+int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A);
 int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail);
 
 // ba_eval.cu (robustified evaluation used inside the LM loop)
