@@ -4,7 +4,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 
 namespace tsl {
@@ -13,44 +15,66 @@ namespace {
 
 constexpr int NB = 64;   // Cholesky tile (chol.cu)
 
-// Worker pool that lives for one analyze_structure call: nt - 1 threads spin (then yield) on a generation counter, so a
-// parallel region costs a few microseconds instead of a thread start per region.
+// Persistent worker pool: nt - 1 threads created once per process. Between analyses they sleep on a condition variable;
+// activate() wakes them and for the ~2 ms of an analysis they spin (then yield) on a generation counter, so a parallel
+// region costs a few microseconds instead of a thread start.
 class Pool {
  public:
   explicit Pool(int nt) : nt_(nt) {
     for (int t = 1; t < nt_; ++t) th_.emplace_back([this, t] { worker(t); });
   }
   ~Pool() {
-    stop_ = true;
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; active_ = true; }
+    cv_.notify_all();
     gen_.fetch_add(1, std::memory_order_release);
     for (auto& x : th_) x.join();
   }
-  int threads() const { return nt_; }
-  void set_serial() { serial_ = true; }
+  int threads() const { return serial_ ? 1 : nt_; }
+  void activate(bool serial) {
+    serial_ = serial || nt_ <= 1;
+    if (serial_) return;
+    { std::lock_guard<std::mutex> lk(mu_); active_ = true; }
+    cv_.notify_all();
+  }
+  void deactivate() {
+    if (serial_) return;
+    { std::lock_guard<std::mutex> lk(mu_); active_ = false; }
+    gen_.fetch_add(1, std::memory_order_release);   // release the spinners into the sleep path (job_ is empty)
+  }
+  void set_serial() { serial_ = true; }   // rest of this analysis on the calling thread only (workers keep spinning idle)
   // f(tid, begin, end) over nt contiguous ranges of [0, n); the calling thread takes range 0. Ranges are ordered by tid,
   // which the counting sorts below rely on to keep the serial (generation) order inside every bucket.
   template <class F>
   void ranges(int n, F&& f) {
-    if (nt_ <= 1 || serial_ || n < 2 * nt_) { f(0, 0, n); return; }
+    if (serial_ || n < 2 * nt_) { f(0, 0, n); return; }
     job_ = [&f, n, this](int t) { f(t, (int)((long long)n * t / nt_), (int)((long long)n * (t + 1) / nt_)); };
     done_.store(0, std::memory_order_relaxed);
+    has_job_.store(true, std::memory_order_relaxed);
     gen_.fetch_add(1, std::memory_order_release);
     job_(0);
     int spins = 0;
     while (done_.load(std::memory_order_acquire) != nt_ - 1) if (++spins > 256) std::this_thread::yield();
+    has_job_.store(false, std::memory_order_relaxed);
   }
-  int ranges_threads(int n) const { return (nt_ <= 1 || serial_ || n < 2 * nt_) ? 1 : nt_; }
 
  private:
   void worker(int t) {
-    int seen = 0;
+    int seen = 0;   // gen_'s value at construction: a worker that starts late must not miss the first job
     for (;;) {
-      int spins = 0;
-      while (gen_.load(std::memory_order_acquire) == seen) if (++spins > 4096) std::this_thread::yield();
-      ++seen;
-      if (stop_) return;
-      job_(t);
-      done_.fetch_add(1, std::memory_order_release);
+      {   // sleep while no analysis is running
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return active_; });
+        if (stop_) return;
+      }
+      for (;;) {   // spin phase
+        int spins = 0, g;
+        while ((g = gen_.load(std::memory_order_acquire)) == seen) if (++spins > 4096) std::this_thread::yield();
+        seen = g;
+        bool act;
+        { std::lock_guard<std::mutex> lk(mu_); act = active_; if (stop_) return; }
+        if (!act) break;
+        if (has_job_.load(std::memory_order_relaxed)) { job_(t); done_.fetch_add(1, std::memory_order_release); }
+      }
     }
   }
   int nt_;
@@ -58,38 +82,57 @@ class Pool {
   std::vector<std::thread> th_;
   std::function<void(int)> job_;
   std::atomic<int> gen_{0}, done_{0};
-  std::atomic<bool> stop_{false};
+  std::atomic<bool> has_job_{false};
+  std::mutex mu_;
+  std::condition_variable cv_;
+  bool active_ = false, stop_ = false;
 };
 
-int host_threads(size_t work_items) {
-  static const int hw = [] {
+Pool& global_pool() {
+  static Pool pool([] {
     if (const char* e = getenv("TSLAM_HOST_THREADS")) return std::max(1, atoi(e));
     const unsigned h = std::thread::hardware_concurrency();
     return (int)std::min(8u, std::max(1u, h));
-  }();
-  return work_items < 20000 ? 1 : hw;   // thread start-up (~20 us each) only pays on the large problems
+  }());
+  return pool;
 }
+
+thread_local Arena* g_arena = nullptr;
 
 // One pass over the observations of one landmark type. lm_of_obs[i] = dense index (0..nv) of the landmark of local
 // observation i when that landmark is free and the observation active, else -1.
 void landmark_pass(Pool& pool, int n_obs, const int* cs, const int* hs, const int* lm_of_obs, int nv, LmSide& S) {
+  // counting sort of the observations by landmark; thread t counts its (ordered) observation range into its own
+  // histogram, so that observations keep their ascending order inside every landmark
+  const int nt = pool.threads();
+  AVec<int> cnt((size_t)nt * ((size_t)nv + 1), 0), entc((size_t)nt * ((size_t)nv + 1), 0);
+  pool.ranges(n_obs, [&](int t, int i0, int i1) {
+    int* c_ = &cnt[(size_t)t * (nv + 1)]; int* e_ = &entc[(size_t)t * (nv + 1)];
+    for (int i = i0; i < i1; ++i) {
+      const int v = lm_of_obs[i];
+      if (v < 0) continue;
+      c_[v]++;
+      e_[v] += (cs[i] >= 0) + (hs[i] >= 0);
+    }
+  });
   S.obs_ptr.assign((size_t)nv + 1, 0);
-  std::vector<int> ent_off((size_t)nv + 1, 0);
-  for (int i = 0; i < n_obs; ++i) {
-    const int v = lm_of_obs[i];
-    if (v < 0) continue;
-    S.obs_ptr[v + 1]++;
-    ent_off[v + 1] += (cs[i] >= 0) + (hs[i] >= 0);
+  AVec<int> ent_off((size_t)nv + 1, 0);
+  {
+    int run = 0, erun = 0;
+    for (int v = 0; v < nv; ++v) {
+      S.obs_ptr[v] = run; ent_off[v] = erun;
+      for (int t = 0; t < nt; ++t) { int& c = cnt[(size_t)t * (nv + 1) + v]; const int k = c; c = run; run += k; erun += entc[(size_t)t * (nv + 1) + v]; }
+    }
+    S.obs_ptr[nv] = run; ent_off[nv] = erun;
   }
-  for (int v = 0; v < nv; ++v) { S.obs_ptr[v + 1] += S.obs_ptr[v]; ent_off[v + 1] += ent_off[v]; }
   const size_t n_ent = (size_t)ent_off[nv];
   S.obs.resize((size_t)S.obs_ptr[nv]);
-  {
-    std::vector<int> cur(S.obs_ptr.begin(), S.obs_ptr.end() - 1);
-    for (int i = 0; i < n_obs; ++i) { const int v = lm_of_obs[i]; if (v >= 0) S.obs[cur[v]++] = i; }
-  }
+  pool.ranges(n_obs, [&](int t, int i0, int i1) {
+    int* cur = &cnt[(size_t)t * (nv + 1)];
+    for (int i = i0; i < i1; ++i) { const int v = lm_of_obs[i]; if (v >= 0) S.obs[cur[v]++] = i; }
+  });
   // phase 1: per landmark, the (camera slot, obs << 1 | role) keys sorted; count the distinct camera slots
-  std::vector<uint64_t> keys(n_ent);
+  AVec<uint64_t> keys(n_ent);
   S.slot_ptr.assign((size_t)nv + 1, 0);
   pool.ranges(nv, [&](int, int v0, int v1) {
     for (int v = v0; v < v1; ++v) {
@@ -128,14 +171,18 @@ void landmark_pass(Pool& pool, int n_obs, const int* cs, const int* hs, const in
 
 // Dense owned-landmark numbering: landmarks that are free (lmfree >= 0) and appear in an active local observation,
 // in ascending global order. Fills S.v_gl, S.obs_ls.
-int owned_landmarks(int n_obs, const int32_t* lm, const uint8_t* act, const std::vector<int>& lmfree, LmSide& S) {
+int owned_landmarks(Pool& pool, int n_obs, const int32_t* lm, const uint8_t* act, const AVec<int>& lmfree, LmSide& S) {
   const int n_lm = (int)lmfree.size();
-  std::vector<int> local_of((size_t)n_lm, -1);
-  for (int i = 0; i < n_obs; ++i) if (act[i] && lmfree[lm[i]] >= 0) local_of[lm[i]] = 0;
+  AVec<int> local_of((size_t)n_lm, -1);
+  pool.ranges(n_obs, [&](int, int i0, int i1) {   // every thread stores the same value: relaxed atomic stores
+    for (int i = i0; i < i1; ++i) if (act[i] && lmfree[lm[i]] >= 0) __atomic_store_n(&local_of[lm[i]], 0, __ATOMIC_RELAXED);
+  });
   S.v_gl.clear();
   for (int l = 0; l < n_lm; ++l) if (local_of[l] == 0) { local_of[l] = (int)S.v_gl.size(); S.v_gl.push_back(l); }
   S.obs_ls.resize((size_t)n_obs);
-  for (int i = 0; i < n_obs; ++i) S.obs_ls[i] = (act[i] && lmfree[lm[i]] >= 0) ? local_of[lm[i]] : -1;
+  pool.ranges(n_obs, [&](int, int i0, int i1) {
+    for (int i = i0; i < i1; ++i) S.obs_ls[i] = (act[i] && lmfree[lm[i]] >= 0) ? local_of[lm[i]] : -1;
+  });
   return (int)S.v_gl.size();
 }
 
@@ -146,6 +193,24 @@ struct Laps {
 };
 
 }  // namespace
+
+Arena* current_arena() { return g_arena; }
+
+void* Arena::allocate(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;   // 256-byte granules: every vector starts on a DMA / cache-line friendly boundary
+  if (bytes == 0) bytes = 256;
+  while (cur_ < chunks_.size() && off_ + bytes > chunks_[cur_].cap) { ++cur_; off_ = 0; }
+  if (cur_ == chunks_.size()) {
+    const size_t cap = std::max(bytes, (size_t)32 << 20);
+    void* p = alloc_(cap);
+    if (!p) throw std::bad_alloc();
+    chunks_.push_back(Chunk{static_cast<char*>(p), cap});
+    off_ = 0;
+  }
+  void* r = chunks_[cur_].p + off_;
+  off_ += bytes;
+  return r;
+}
 
 int chol_workspace_dims(int n, int* ld, int* rows) {
   const int Tn = (n + NB - 1) / NB;
@@ -159,24 +224,24 @@ int chol_workspace_dims(int n, int* ld, int* rows) {
 // panel k < j with L[j][k] != 0 is finished; panels of one wave are mutually independent, so a wave is three
 // launches (factor+solve, update, and later the backward solve) however many panels it holds. With the nested-
 // dissection camera order chosen below a banded problem needs ~15 waves instead of T = 47 panel steps.
-void chol_symbolic_host(int n, const std::vector<uint8_t>& tile_nz, CholHost& H) {
+void chol_symbolic_host(int n, const AVec<uint8_t>& tile_nz, CholHost& H) {
   int ld, rows;
   const int Tn = chol_workspace_dims(n, &ld, &rows);
   H = CholHost();
   H.Tn = Tn; H.n = n;
   const int T1 = Tn + 1;  // + the b tile row (dense)
-  std::vector<uint8_t> P((size_t)T1 * T1, 0);
+  AVec<uint8_t> P((size_t)T1 * T1, 0);
   for (int i = 0; i < Tn; ++i)
     for (int k = 0; k <= i; ++k) P[(size_t)i * T1 + k] = (i == k) || tile_nz[(size_t)i * Tn + k];
   for (int k = 0; k < Tn; ++k) P[(size_t)Tn * T1 + k] = 1;
-  std::vector<std::vector<int>> below(Tn);
+  AVec<AVec<int>> below(Tn);
   for (int j = 0; j < Tn; ++j) {   // symbolic factorisation (fill)
-    std::vector<int>& nz = below[j];
+    AVec<int>& nz = below[j];
     for (int i = j + 1; i < T1; ++i) if (P[(size_t)i * T1 + j]) nz.push_back(i);
     for (size_t a = 0; a < nz.size(); ++a)
       for (size_t b = 0; b <= a; ++b) P[(size_t)nz[a] * T1 + nz[b]] = 1;
   }
-  std::vector<int> wave(Tn, 0);
+  AVec<int> wave(Tn, 0);
   int nwaves = 0;
   for (int j = 0; j < Tn; ++j) {
     int w = 0;
@@ -184,18 +249,18 @@ void chol_symbolic_host(int n, const std::vector<uint8_t>& tile_nz, CholHost& H)
     wave[j] = w; nwaves = std::max(nwaves, w + 1);
   }
   H.nwaves = nwaves;
-  std::vector<std::vector<int>> wave_panels(nwaves);
+  AVec<AVec<int>> wave_panels(nwaves);
   for (int j = 0; j < Tn; ++j) wave_panels[wave[j]].push_back(j);
   H.item_ptr.assign(nwaves + 1, 0); H.target_ptr.assign(nwaves + 1, 0); H.panel_ptr.assign(nwaves + 1, 0);
   H.src_ptr.push_back(0); H.below_ptr.push_back(0);
-  std::vector<int> tgt_index((size_t)T1 * T1, -1);
+  AVec<int> tgt_index((size_t)T1 * T1, -1);
   for (int w = 0; w < nwaves; ++w) {
     const size_t t_begin = H.targets.size();
-    std::vector<std::vector<int>> tsrc;
+    AVec<AVec<int>> tsrc;
     for (int j : wave_panels[w]) {
       H.items.push_back(I2{j, -1});
       for (int i : below[j]) H.items.push_back(I2{j, i});
-      const std::vector<int>& nz = below[j];
+      const AVec<int>& nz = below[j];
       for (size_t a = 0; a < nz.size(); ++a)
         for (size_t b = 0; b <= a; ++b) {
           const int i = nz[a], k = nz[b];
@@ -215,27 +280,51 @@ void chol_symbolic_host(int n, const std::vector<uint8_t>& tile_nz, CholHost& H)
   }
 }
 
-void analyze_structure(const IndexView& V, Analysis& A) {
+namespace {
+struct ArenaScope {   // makes `a` the calling thread's arena for the lifetime of the scope
+  Arena* prev;
+  explicit ArenaScope(Arena* a) : prev(g_arena) { g_arena = a; }
+  ~ArenaScope() { g_arena = prev; }
+};
+struct PoolScope {
+  Pool& p;
+  PoolScope(Pool& pool, bool serial) : p(pool) { p.activate(serial); }
+  ~PoolScope() { p.deactivate(); }
+};
+std::mutex g_analysis_mutex;   // one analysis at a time per process (the pool and its job slot are shared)
+}  // namespace
+
+void analyze_structure(const IndexView& V, Analysis& A, Arena& arena) {
+  std::lock_guard<std::mutex> serialise(g_analysis_mutex);
   Laps T;
+  arena.reset();
+  ArenaScope arena_scope(&arena);
+  A = Analysis();
   const int K = V.n_cams, GP = V.g_pobs, GT = V.g_tobs;
-  Pool pool(host_threads((size_t)GP + 8 * (size_t)GT));
+  Pool& pool = global_pool();
+  PoolScope pool_scope(pool, (size_t)GP + 8 * (size_t)GT < 20000);   // waking the workers only pays on the large problems
   A.K = K;
   auto cf = [&](int k) { return V.cam_fixed[k] != 0; };
   // ---- global layout (same on every rank) ----
-  std::vector<uint8_t> cu(K, 0), lu(V.n_points, 0), pu(V.n_planes, 0);
-  std::vector<uint8_t> gp_active(GP), gt_active(GT);
-  for (int i = 0; i < GP; ++i) {
-    const int c = V.p_cam[i], h = V.p_host[i], l = V.p_lm[i];
-    const bool act = !cf(c) || !cf(h) || !V.rho_fixed[l];
-    gp_active[i] = act;
-    if (act) { cu[c] = cu[h] = 1; lu[l] = 1; }
-  }
-  for (int i = 0; i < GT; ++i) {
-    const int c = V.t_cam[i], h = V.t_host[i], l = V.t_plane[i];
-    const bool act = !cf(c) || !cf(h) || !V.theta_fixed[l];
-    gt_active[i] = act;
-    if (act) { cu[c] = cu[h] = 1; pu[l] = 1; }
-  }
+  AVec<uint8_t> cu(K, 0), lu(V.n_points, 0), pu(V.n_planes, 0);
+  AVec<uint8_t> gp_active(GP), gt_active(GT);
+  auto mark1 = [](uint8_t& f) { __atomic_store_n(&f, (uint8_t)1, __ATOMIC_RELAXED); };   // same value from every thread
+  pool.ranges(GP, [&](int, int i0, int i1) {
+    for (int i = i0; i < i1; ++i) {
+      const int c = V.p_cam[i], h = V.p_host[i], l = V.p_lm[i];
+      const bool act = !cf(c) || !cf(h) || !V.rho_fixed[l];
+      gp_active[i] = act;
+      if (act) { mark1(cu[c]); mark1(cu[h]); mark1(lu[l]); }
+    }
+  });
+  pool.ranges(GT, [&](int, int i0, int i1) {
+    for (int i = i0; i < i1; ++i) {
+      const int c = V.t_cam[i], h = V.t_host[i], l = V.t_plane[i];
+      const bool act = !cf(c) || !cf(h) || !V.theta_fixed[l];
+      gt_active[i] = act;
+      if (act) { mark1(cu[c]); mark1(cu[h]); mark1(pu[l]); }
+    }
+  });
   A.camslot.assign(K, -1); A.nc = 0;
   for (int k = 0; k < K; ++k) if (cu[k] && !cf(k)) A.camslot[k] = A.nc++;
   A.lmfree_p.assign(V.n_points, -1); A.nl = 0;
@@ -250,7 +339,7 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   // ordered leaves-first / separators-last so that the tile elimination DAG of chol.cu has ~log depth instead of being
   // a chain; any order is valid, this one only shortens the critical path of the reduced-system factorisation.
   if (nc >= 128) {
-    std::vector<int> hist((size_t)nc, 0);   // histogram of |slot(cam) - slot(host)| over the active observations
+    AVec<int> hist((size_t)nc, 0);   // histogram of |slot(cam) - slot(host)| over the active observations
     size_t nd = 0;
     for (int i = 0; i < GP; ++i) if (gp_active[i]) { const int a = A.camslot[V.p_cam[i]], b = A.camslot[V.p_host[i]]; if (a >= 0 && b >= 0) { hist[std::abs(a - b)]++; ++nd; } }
     for (int i = 0; i < GT; ++i) if (gt_active[i]) { const int a = A.camslot[V.t_cam[i]], b = A.camslot[V.t_host[i]]; if (a >= 0 && b >= 0) { hist[std::abs(a - b)]++; ++nd; } }
@@ -264,9 +353,9 @@ void analyze_structure(const IndexView& V, Analysis& A) {
     const int U = 32 * ((bw + 1 + 31) / 32);
     const int nfull = nc / U;
     if (nfull >= 4) {
-      std::vector<int> unit_order;
+      AVec<int> unit_order;
       struct Frame { int lo, hi, stage; };   // recursive bisection written iteratively (post-order: left, right, separator)
-      std::vector<Frame> st; st.push_back({0, nfull, 0});
+      AVec<Frame> st; st.push_back({0, nfull, 0});
       while (!st.empty()) {
         Frame f = st.back(); st.pop_back();
         if (f.hi - f.lo <= 0) continue;
@@ -275,7 +364,7 @@ void analyze_structure(const IndexView& V, Analysis& A) {
         if (f.stage == 0) { st.push_back({f.lo, f.hi, 1}); st.push_back({mid + 1, f.hi, 0}); st.push_back({f.lo, mid, 0}); }
         else unit_order.push_back(mid);
       }
-      std::vector<int> new_of_old(nc, -1);
+      AVec<int> new_of_old(nc, -1);
       int next = 0;
       for (int u : unit_order) for (int c = u * U; c < (u + 1) * U; ++c) new_of_old[c] = next++;
       for (int c = nfull * U; c < nc; ++c) new_of_old[c] = next++;   // the partial unit goes last (keeps units tile-aligned)
@@ -283,15 +372,15 @@ void analyze_structure(const IndexView& V, Analysis& A) {
     }
   }
   // camera slots of every global observation
-  std::vector<int> gp_cs(GP), gp_hs(GP), gt_cs(GT), gt_hs(GT);
-  for (int i = 0; i < GP; ++i) { gp_cs[i] = A.camslot[V.p_cam[i]]; gp_hs[i] = A.camslot[V.p_host[i]]; }
-  for (int i = 0; i < GT; ++i) { gt_cs[i] = A.camslot[V.t_cam[i]]; gt_hs[i] = A.camslot[V.t_host[i]]; }
+  AVec<int> gp_cs(GP), gp_hs(GP), gt_cs(GT), gt_hs(GT);
+  pool.ranges(GP, [&](int, int i0, int i1) { for (int i = i0; i < i1; ++i) { gp_cs[i] = A.camslot[V.p_cam[i]]; gp_hs[i] = A.camslot[V.p_host[i]]; } });
+  pool.ranges(GT, [&](int, int i0, int i1) { for (int i = i0; i < i1; ++i) { gt_cs[i] = A.camslot[V.t_cam[i]]; gt_hs[i] = A.camslot[V.t_host[i]]; } });
   A.lap_ms[0] = T.lap();
 
   // ---- local observations + landmark side ----
   const bool sharded = V.gsel_p != nullptr || V.gsel_t != nullptr;
   const int lp = V.lp, lt = V.lt; A.lp = lp; A.lt = lt;
-  std::vector<int32_t> lp_lm, lt_lm;
+  AVec<int32_t> lp_lm, lt_lm;
   const int32_t *l_p_lm = V.p_lm, *l_t_lm = V.t_plane;
   if (!sharded) {
     A.p_cs = gp_cs; A.p_hs = gp_hs; A.p_act = gp_active; A.t_cs = gt_cs; A.t_hs = gt_hs; A.t_act = gt_active;
@@ -304,8 +393,8 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   }
   A.t_fm.resize(lt);
   for (int i = 0; i < lt; ++i) A.t_fm[i] = (uint8_t)((A.t_cs[i] >= 0 ? 1 : 0) | (A.t_hs[i] >= 0 ? 2 : 0) | (A.lmfree_t[l_t_lm[i]] >= 0 ? 4 : 0));
-  A.nvp = owned_landmarks(lp, l_p_lm, A.p_act.data(), A.lmfree_p, A.LP);
-  A.nvt = owned_landmarks(lt, l_t_lm, A.t_act.data(), A.lmfree_t, A.LT);
+  A.nvp = owned_landmarks(pool, lp, l_p_lm, A.p_act.data(), A.lmfree_p, A.LP);
+  A.nvt = owned_landmarks(pool, lt, l_t_lm, A.t_act.data(), A.lmfree_t, A.LT);
   landmark_pass(pool, lp, A.p_cs.data(), A.p_hs.data(), A.LP.obs_ls.data(), A.nvp, A.LP);
   landmark_pass(pool, lt, A.t_cs.data(), A.t_hs.data(), A.LT.obs_ls.data(), A.nvt, A.LT);
   A.nsp = (int)A.LP.slot_cam.size(); A.nst = (int)A.LT.slot_cam.size();
@@ -313,8 +402,8 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   LmSide GLP, GLT;
   const LmSide *SP = &A.LP, *ST = &A.LT;
   if (sharded) {
-    owned_landmarks(GP, V.p_lm, gp_active.data(), A.lmfree_p, GLP);
-    owned_landmarks(GT, V.t_plane, gt_active.data(), A.lmfree_t, GLT);
+    owned_landmarks(pool, GP, V.p_lm, gp_active.data(), A.lmfree_p, GLP);
+    owned_landmarks(pool, GT, V.t_plane, gt_active.data(), A.lmfree_t, GLT);
     landmark_pass(pool, GP, gp_cs.data(), gp_hs.data(), GLP.obs_ls.data(), (int)GLP.v_gl.size(), GLP);
     landmark_pass(pool, GT, gt_cs.data(), gt_hs.data(), GLT.obs_ls.data(), (int)GLT.v_gl.size(), GLT);
     SP = &GLP; ST = &GLT;
@@ -324,8 +413,8 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   // ---- global block structure: unique (a <= b) camera-slot pairs from every active observation / landmark ----
   // dense (a,b) -> block id table when nc^2 is small enough (O(1) insert / lookup); sorted-key fallback otherwise
   const bool dense_tab = (size_t)nc * (size_t)nc <= ((size_t)1 << 24);
-  std::vector<int> btab;
-  std::vector<uint64_t> bkeys;
+  AVec<int> btab;
+  AVec<uint64_t> bkeys;
   if (dense_tab) btab.assign((size_t)nc * nc, -1);
   if (dense_tab) {
     // every thread stores the same value (0) into the table: relaxed atomic stores, no ordering needed before the join
@@ -388,7 +477,7 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   for (int b = 0; b < A.nblk; ++b) { if (A.blk_a[b] == A.blk_b[b]) A.diag_blk[A.blk_a[b]] = b; else A.offdiag_blk.push_back(b); }
   A.lap_ms[2] = T.lap();
   {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
-    std::vector<uint8_t> tile_nz((size_t)A.Tn * A.Tn, 0);
+    AVec<uint8_t> tile_nz((size_t)A.Tn * A.Tn, 0);
     for (int b = 0; b < A.nblk; ++b) {
       // block (a,b'), a <= b' lands in rows 6b'..6b'+5, cols 6a..6a+5 of the lower triangle
       const int r0 = 6 * A.blk_b[b] / NB, r1 = (6 * A.blk_b[b] + 5) / NB, c0 = 6 * A.blk_a[b] / NB, c1 = (6 * A.blk_a[b] + 5) / NB;
@@ -407,8 +496,8 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   // thread t counts its (ordered) range into its own histogram, bucket b then starts at ptr[b] + sum_{t' < t} hist[t'][b].
   if ((size_t)pool.threads() * (size_t)A.nblk > ((size_t)1 << 22)) pool.set_serial();
   const int nt = pool.threads();
-  std::vector<int> hist((size_t)nt * ((size_t)A.nblk + 1));
-  auto offsets_from_hist = [&](std::vector<int>& ptr) {   // hist[t][b] (counts) -> hist[t][b] (start offsets), ptr = CSR
+  AVec<int> hist((size_t)nt * ((size_t)A.nblk + 1));
+  auto offsets_from_hist = [&](AVec<int>& ptr) {   // hist[t][b] (counts) -> hist[t][b] (start offsets), ptr = CSR
     ptr.assign((size_t)A.nblk + 1, 0);
     int run = 0;
     for (int b = 0; b < A.nblk; ++b) {
@@ -418,10 +507,10 @@ void analyze_structure(const IndexView& V, Analysis& A) {
     ptr[A.nblk] = run;
     return run;
   };
-  auto direct_lists = [&](int n_obs, const int* cs, const int* hs, const uint8_t* act, std::vector<int>& ptr, std::vector<int>& out) {
+  auto direct_lists = [&](int n_obs, const int* cs, const int* hs, const uint8_t* act, AVec<int>& ptr, AVec<int>& out) {
     // codes: 0 = J_cam^T J_cam on the diagonal block of the observing camera, 1 = same for the host, 2 / 3 = the
     // off-diagonal block (2: observing slot < host slot, 3: host slot < observing slot)
-    std::vector<int> key(3 * (size_t)n_obs);
+    AVec<int> key(3 * (size_t)n_obs);
     std::fill(hist.begin(), hist.end(), 0);
     pool.ranges(n_obs, [&](int t, int i0, int i1) {
       int* h_ = &hist[(size_t)t * (A.nblk + 1)];
@@ -453,11 +542,11 @@ void analyze_structure(const IndexView& V, Analysis& A) {
   };
   direct_lists(lp, A.p_cs.data(), A.p_hs.data(), A.p_act.data(), A.bdp_ptr, A.bdp);
   direct_lists(lt, A.t_cs.data(), A.t_hs.data(), A.t_act.data(), A.bdt_ptr, A.bdt);
-  auto schur_lists = [&](const LmSide& L, std::vector<int>& ptr, std::vector<I2>& out) {
+  auto schur_lists = [&](const LmSide& L, AVec<int>& ptr, AVec<I2>& out) {
     const int nv = (int)L.slot_ptr.size() - 1;
-    std::vector<size_t> pair_off((size_t)nv + 1, 0);
+    AVec<size_t> pair_off((size_t)nv + 1, 0);
     for (int v = 0; v < nv; ++v) { const size_t m = (size_t)(L.slot_ptr[v + 1] - L.slot_ptr[v]); pair_off[v + 1] = pair_off[v] + m * (m + 1) / 2; }
-    std::vector<int> key(pair_off[nv]);
+    AVec<int> key(pair_off[nv]);
     std::fill(hist.begin(), hist.end(), 0);
     pool.ranges(nv, [&](int t, int v0, int v1) {
       int* h_ = &hist[(size_t)t * (A.nblk + 1)];

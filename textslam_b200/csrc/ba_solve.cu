@@ -633,12 +633,12 @@ struct Solver {
   ~Solver() { for (auto e : ev) cudaEventDestroy(e); }
 };
 
-template <typename T>
-static cudaError_t up(DevBuf<T>& b, const std::vector<T>& h, cudaStream_t s) { return b.upload(h.data(), h.size(), s); }
+template <typename T, typename Vec>
+static cudaError_t up(DevBuf<T>& b, const Vec& h, cudaStream_t s) { return b.upload(h.data(), h.size(), s); }
 
-template <typename T, typename H>
-static cudaError_t up_as(DevBuf<T>& b, const std::vector<H>& h, cudaStream_t s) {
-  static_assert(sizeof(T) == sizeof(H), "layout-compatible element types expected");
+template <typename T, typename Vec>
+static cudaError_t up_as(DevBuf<T>& b, const Vec& h, cudaStream_t s) {
+  static_assert(sizeof(T) == sizeof(typename Vec::value_type), "layout-compatible element types expected");
   return b.upload(reinterpret_cast<const T*>(h.data()), h.size(), s);
 }
 
@@ -655,8 +655,11 @@ static int analyze_and_upload(Solver& S) {
   V.t_cam = d->h_t_cam.data(); V.t_host = d->h_t_host.data(); V.t_plane = d->h_t_plane.data();
   V.lp = d->n_pobs; V.lt = d->n_tobs;
   V.gsel_p = d->sharded ? d->gsel_p.data() : nullptr; V.gsel_t = d->sharded ? d->gsel_t.data() : nullptr;
+  if (!ctx->host_arena)
+    ctx->host_arena = new Arena([](size_t n) -> void* { void* q = nullptr; return cudaHostAlloc(&q, n, cudaHostAllocDefault) == cudaSuccess ? q : nullptr; },
+                                [](void* q) { cudaFreeHost(q); });
   Analysis A;
-  analyze_structure(V, A);
+  try { analyze_structure(V, A, *ctx->host_arena); } catch (const std::exception& e) { return set_error(TSLAM_ERR_CUDA, "structure analysis failed: %s", e.what()); }
   S.K = A.K; S.nc = A.nc; S.nl = A.nl; S.npl = A.npl; S.lp = A.lp; S.lt = A.lt;
   S.nvp = A.nvp; S.nvt = A.nvt; S.nsp = A.nsp; S.nst = A.nst; S.nblk = A.nblk;
   S.n = A.n; S.ld = A.ld; S.rows = A.rows; S.Tn = A.Tn;
@@ -704,8 +707,9 @@ static int analyze_and_upload(Solver& S) {
   TSL_CUDA(S.parts.reserve(nparts));
   TSL_CUDA(S.fail.reserve(1));
   TSL_CUDA(cudaStreamSynchronize(st));   // the host vectors of A go out of scope on return
-  S.camslot = std::move(A.camslot); S.vp_gl_h = std::move(A.LP.v_gl); S.vt_gl_h = std::move(A.LT.v_gl);
-  S.lmfree_p_h = std::move(A.lmfree_p); S.lmfree_t_h = std::move(A.lmfree_t);
+  // host copies the solver keeps (the arena is recycled by the next analysis on this context)
+  S.camslot.assign(A.camslot.begin(), A.camslot.end()); S.vp_gl_h.assign(A.LP.v_gl.begin(), A.LP.v_gl.end()); S.vt_gl_h.assign(A.LT.v_gl.begin(), A.LT.v_gl.end());
+  S.lmfree_p_h.assign(A.lmfree_p.begin(), A.lmfree_p.end()); S.lmfree_t_h.assign(A.lmfree_t.begin(), A.lmfree_t.end());
   auto T2 = std::chrono::steady_clock::now();
   S.setup_ms = std::chrono::duration<double, std::milli>(T2 - T0).count();
   if (trace_setup)

@@ -157,8 +157,9 @@ int tslam_analyze_structure(const tslam_ba_problem* p, int rank, int world, tsla
     V.lp = (int)gp.size(); V.lt = (int)gt.size(); V.gsel_p = gp.data(); V.gsel_t = gt.data();
     if (!V.gsel_p) V.gsel_p = &rank; if (!V.gsel_t) V.gsel_t = &rank;   // empty shard: any non-null pointer marks "sharded"
   } else { V.lp = p->n_pobs; V.lt = p->n_tobs; }
+  Arena arena([](size_t n) { return malloc(n); }, [](void* q) { free(q); });   // pageable: nothing is uploaded here
   Analysis A;
-  analyze_structure(V, A);
+  try { analyze_structure(V, A, arena); } catch (const std::exception& e) { return set_error(TSLAM_ERR_ARG, "structure analysis failed: %s", e.what()); }
   memset(out, 0, sizeof(*out));
   out->n_free_cams = A.nc; out->n_free_points = A.nl; out->n_free_planes = A.npl; out->reduced_dim = A.n; out->n_blocks = A.nblk;
   out->n_local_pobs = A.lp; out->n_local_tobs = A.lt; out->n_owned_points = A.nvp; out->n_owned_planes = A.nvt;
@@ -210,6 +211,7 @@ void tslam_ctx_destroy(tslam_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  delete c->host_arena;
   delete c;
 }
 

@@ -243,7 +243,8 @@ __global__ void copy_row_kernel(const double* __restrict__ src, double* __restri
 // with their source panels, and the panel / below lists of the backward solve.
 int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
   sym->Tn = H.Tn; sym->n = H.n; sym->nwaves = H.nwaves; sym->gemm_tiles = H.gemm_tiles;
-  sym->item_ptr = H.item_ptr; sym->target_ptr = H.target_ptr; sym->panel_ptr = H.panel_ptr;
+  sym->item_ptr.assign(H.item_ptr.begin(), H.item_ptr.end()); sym->target_ptr.assign(H.target_ptr.begin(), H.target_ptr.end());
+  sym->panel_ptr.assign(H.panel_ptr.begin(), H.panel_ptr.end());
   cudaStream_t s = ctx->stream;
   static_assert(sizeof(I2) == sizeof(int2), "I2 must match int2");
   TSL_CUDA(sym->items.upload(reinterpret_cast<const int2*>(H.items.data()), H.items.size(), s));

@@ -1,5 +1,6 @@
 // Context, error handling and the device-resident problem (HBM layout) of libtslam_b200.
 #pragma once
+#include "analysis.hpp"
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -65,6 +66,8 @@ struct tslam_ctx {
   void* nccl_comm = nullptr;
   // pinned staging for scalars
   double* h_scalars = nullptr;  // cudaHostAlloc, 64 doubles
+  // page-locked arena behind the host-side structure analysis (analysis.hpp); recycled by every solve on this context
+  tsl::Arena* host_arena = nullptr;
 };
 
 // Device-resident problem: everything the kernels read, SoA, FP64 / int32 / u8.
