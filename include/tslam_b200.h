@@ -152,6 +152,10 @@ typedef struct tslam_structure_info {
 } tslam_structure_info;
 int tslam_analyze_structure(const tslam_ba_problem* p, int rank, int world, tslam_structure_info* out);
 
+/* Test hook: runs the structure analysis on the device (the path tslam_solve takes for an unsharded problem) and on the host
+ * (the multi-GPU path) and writes the space-separated names of every index array that differs to `report` ("" = identical). */
+int tslam_debug_compare_analysis(tslam_ctx* ctx, const tslam_ba_problem* p, char* report, int report_len);
+
 /* ---- residual + Jacobian evaluation (the metric kernel) --------------------------------------- */
 /* Replaces ceres::AutoDiffCostFunction<...>::Evaluate + QuaternionParameterization projection for
  * every residual block of the given kind.  r: n_pobs x 2.  J: n_pobs x 2 x ncols (ncols 13/6/1),

@@ -81,6 +81,13 @@ class Context:
         check(lib().tslam_theta_covariance(self._h, C.byref(pc), C.c_int(jac_mode), _dp(cov), C.byref(ns)))
         return cov, ns.value
 
+    def compare_analysis(self, prob):
+        """Test hook: names of the index arrays on which the device-side structure analysis differs from the host one."""
+        buf = C.create_string_buffer(4096)
+        pc = prob.as_c()
+        check(lib().tslam_debug_compare_analysis(self._h, C.byref(pc), buf, C.c_int(4096)))
+        return buf.value.decode().split()
+
     # ---- device-resident handles (benchmarks) --------------------------------------------------
     def upload(self, prob):
         return DeviceProblem(self, prob)

@@ -294,6 +294,16 @@ struct PoolScope {
 std::mutex g_analysis_mutex;   // one analysis at a time per process (the pool and its job slot are shared)
 }  // namespace
 
+void chol_symbolic_in_arena(int n, const uint8_t* tile_nz, Arena& arena, CholHost& H) {
+  std::lock_guard<std::mutex> serialise(g_analysis_mutex);
+  arena.reset();
+  ArenaScope arena_scope(&arena);
+  int ld, rows;
+  const int Tn = chol_workspace_dims(n, &ld, &rows);
+  AVec<uint8_t> tz(tile_nz, tile_nz + (size_t)Tn * Tn);
+  chol_symbolic_host(n, tz, H);
+}
+
 void analyze_structure(const IndexView& V, Analysis& A, Arena& arena) {
   std::lock_guard<std::mutex> serialise(g_analysis_mutex);
   Laps T;

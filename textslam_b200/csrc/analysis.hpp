@@ -88,6 +88,8 @@ struct Analysis {
 
 int chol_workspace_dims(int n, int* ld, int* rows);
 void chol_symbolic_host(int n, const AVec<uint8_t>& tile_nz, CholHost& H);   // needs a current arena (called by analyze_structure)
+// tile-level symbolic factorisation alone (device analysis path): tile_nz = Tn x Tn row-major flags; resets `arena`.
+void chol_symbolic_in_arena(int n, const uint8_t* tile_nz, Arena& arena, CholHost& H);
 // All vectors of A live in `arena` (reset here first): they stay valid until the next analyze_structure on that arena.
 void analyze_structure(const IndexView& V, Analysis& A, Arena& arena);
 

@@ -591,24 +591,9 @@ __global__ void export_lm_kernel(int nv, const int* __restrict__ v_gl, const dou
 // ================================================================================================
 // host side
 // ================================================================================================
-struct Solver {
+struct Solver : SolverIndex {
   tslam_ctx* ctx = nullptr;
   tslam_dev_problem* d = nullptr;
-  int K = 0, nc = 0, nl = 0, npl = 0;         // global free counts
-  int lp = 0, lt = 0;                         // local observations
-  int nvp = 0, nvt = 0, nsp = 0, nst = 0;     // owned landmarks / slots
-  int nblk = 0;
-  int n = 0, ld = 0, rows = 0, Tn = 0;        // reduced system dims
-  std::vector<int> camslot;
-  std::vector<int> vp_gl_h, vt_gl_h, lmfree_p_h, lmfree_t_h;
-  // device index structures
-  DevBuf<int> camslot_d, p_cs, p_hs, p_ls, t_cs, t_hs, t_ls;
-  DevBuf<uint8_t> p_active, t_active, t_fmask;
-  DevBuf<int> vp_gl, vt_gl, vp_obs_ptr, vp_obs, vt_obs_ptr, vt_obs;
-  DevBuf<int> sp_ptr, sp_cam, sp_lm, spe_ptr, spe, st_ptr, st_cam, st_lm, ste_ptr, ste;
-  DevBuf<int> offdiag_blk; int noff = 0;
-  DevBuf<int> blk_a, blk_b, diag_blk, bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr, gsel_p, gsel_t;
-  DevBuf<int2> bsp, bst;
   // values
   DevBuf<double> xc_cams, xc_rho, xc_theta;
   DevBuf<double> pr, pJ, tr, tJ, cr_p, cr_t;   // cr_*: candidate residual scratch
@@ -619,7 +604,6 @@ struct Solver {
   DevBuf<double> mx;         // max-reduced scalars
   DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts;
   DevBuf<int> fail;
-  CholSymbolic chol;
   size_t red_n = 0;
   double *Sblk = nullptr, *bvec = nullptr, *graw = nullptr, *udiag = nullptr, *sc = nullptr;
   double* x_cams = nullptr; double* x_rho = nullptr; double* x_theta = nullptr;   // current (alias d-> buffers or xc)
@@ -642,10 +626,8 @@ static cudaError_t up_as(DevBuf<T>& b, const Vec& h, cudaStream_t s) {
   return b.upload(reinterpret_cast<const T*>(h.data()), h.size(), s);
 }
 
-// Structure analysis (analysis.cpp, host) + upload of the index structures + allocation of the value buffers.
-static int analyze_and_upload(Solver& S) {
-  auto T0 = std::chrono::steady_clock::now();
-  static const bool trace_setup = getenv("TSLAM_SETUP_TRACE") != nullptr;
+// Host path (sharded / multi-GPU problems, or TSLAM_HOST_ANALYSIS=1): analysis.cpp + upload of the index structures.
+static int analyze_on_host_and_upload(Solver& S, Analysis& A, std::chrono::steady_clock::time_point& T1) {
   tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
   cudaStream_t st = ctx->stream;
   IndexView V;
@@ -658,13 +640,11 @@ static int analyze_and_upload(Solver& S) {
   if (!ctx->host_arena)
     ctx->host_arena = new Arena([](size_t n) -> void* { void* q = nullptr; return cudaHostAlloc(&q, n, cudaHostAllocDefault) == cudaSuccess ? q : nullptr; },
                                 [](void* q) { cudaFreeHost(q); });
-  Analysis A;
   try { analyze_structure(V, A, *ctx->host_arena); } catch (const std::exception& e) { return set_error(TSLAM_ERR_CUDA, "structure analysis failed: %s", e.what()); }
   S.K = A.K; S.nc = A.nc; S.nl = A.nl; S.npl = A.npl; S.lp = A.lp; S.lt = A.lt;
   S.nvp = A.nvp; S.nvt = A.nvt; S.nsp = A.nsp; S.nst = A.nst; S.nblk = A.nblk;
   S.n = A.n; S.ld = A.ld; S.rows = A.rows; S.Tn = A.Tn;
-  const int K = A.K, nc = A.nc, lp = A.lp, lt = A.lt;
-  auto T1 = std::chrono::steady_clock::now();
+  T1 = std::chrono::steady_clock::now();
   // ---- upload ----
   int rc = chol_upload(ctx, A.chol, &S.chol);
   if (rc) return rc;
@@ -684,6 +664,29 @@ static int analyze_and_upload(Solver& S) {
   TSL_CUDA(up(S.bdp_ptr, A.bdp_ptr, st)); TSL_CUDA(up(S.bdp, A.bdp, st)); TSL_CUDA(up(S.bdt_ptr, A.bdt_ptr, st)); TSL_CUDA(up(S.bdt, A.bdt, st));
   TSL_CUDA(up(S.bsp_ptr, A.bsp_ptr, st)); TSL_CUDA(up_as(S.bsp, A.bsp, st)); TSL_CUDA(up(S.bst_ptr, A.bst_ptr, st)); TSL_CUDA(up_as(S.bst, A.bst, st));
   if (d->sharded) { TSL_CUDA(up(S.gsel_p, d->gsel_p, st)); TSL_CUDA(up(S.gsel_t, d->gsel_t, st)); }
+  return TSLAM_OK;
+}
+
+// Structure analysis (device or host) + allocation of the value buffers.
+static int analyze_and_upload(Solver& S) {
+  auto T0 = std::chrono::steady_clock::now();
+  static const bool trace_setup = getenv("TSLAM_SETUP_TRACE") != nullptr;
+  tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
+  cudaStream_t st = ctx->stream;
+  double dev_laps[4] = {0, 0, 0, 0};
+  const bool on_device = device_analysis_supported(ctx, d);
+  Analysis A;
+  auto T1 = T0;
+  if (on_device) {
+    // unsharded problem: the index structures are built where the observation arrays already are (analysis_dev.cu)
+    int rc = analyze_structure_device(ctx, d, S, dev_laps);
+    if (rc) return rc;
+    T1 = std::chrono::steady_clock::now();
+  } else {
+    int rc = analyze_on_host_and_upload(S, A, T1);
+    if (rc) return rc;
+  }
+  const int K = S.K, nc = S.nc, lp = S.lp, lt = S.lt;
   // ---- value buffers ----
   TSL_CUDA(S.xc_cams.reserve(7 * (size_t)K)); TSL_CUDA(S.xc_rho.reserve(d->n_points)); TSL_CUDA(S.xc_theta.reserve(3 * (size_t)d->n_planes));
   TSL_CUDA(S.pr.reserve(2 * (size_t)lp)); TSL_CUDA(S.pJ.reserve(26 * (size_t)lp)); TSL_CUDA(S.cr_p.reserve(2 * (size_t)lp));
@@ -712,7 +715,10 @@ static int analyze_and_upload(Solver& S) {
   S.lmfree_p_h.assign(A.lmfree_p.begin(), A.lmfree_p.end()); S.lmfree_t_h.assign(A.lmfree_t.begin(), A.lmfree_t.end());
   auto T2 = std::chrono::steady_clock::now();
   S.setup_ms = std::chrono::duration<double, std::milli>(T2 - T0).count();
-  if (trace_setup)
+  if (trace_setup && on_device)
+    fprintf(stderr, "[tslam setup] device analysis %.3f ms (layout+slots+block table+round trip %.3f, symbolic+upload %.3f, block arrays+gather lists %.3f); "
+            "value buffers %.3f ms\n", dev_laps[3], dev_laps[0], dev_laps[1], dev_laps[2], std::chrono::duration<double, std::milli>(T2 - T1).count());
+  else if (trace_setup)
     fprintf(stderr, "[tslam setup] host analysis %.3f ms (layout+order %.3f, landmark side %.3f, block structure %.3f, symbolic %.3f, gather lists %.3f); "
             "index upload + buffers %.3f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), A.lap_ms[0], A.lap_ms[1], A.lap_ms[2], A.lap_ms[3],
             A.lap_ms[4], std::chrono::duration<double, std::milli>(T2 - T1).count());

@@ -21,6 +21,29 @@ int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);   // devi
 int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A);
 int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail);
 
+// Index structures of one problem on the device (what the structure analysis produces; analysis.cpp on the host or
+// analysis_dev.cu on the GPU) — the LM kernels of ba_solve.cu only ever read these.
+struct SolverIndex {
+  int K = 0, nc = 0, nl = 0, npl = 0;         // cameras; free cameras / inverse depths / planes (global)
+  int lp = 0, lt = 0;                         // local observations
+  int nvp = 0, nvt = 0, nsp = 0, nst = 0;     // owned landmarks / (landmark, camera) slots
+  int nblk = 0, noff = 0;                     // non-zero 6x6 blocks (a <= b), of which off-diagonal
+  int n = 0, ld = 0, rows = 0, Tn = 0;        // reduced system dims
+  std::vector<int> camslot;                   // host copies (multi-GPU result merge only)
+  std::vector<int> vp_gl_h, vt_gl_h, lmfree_p_h, lmfree_t_h;
+  DevBuf<int> camslot_d, p_cs, p_hs, p_ls, t_cs, t_hs, t_ls;
+  DevBuf<uint8_t> p_active, t_active, t_fmask;
+  DevBuf<int> vp_gl, vt_gl, vp_obs_ptr, vp_obs, vt_obs_ptr, vt_obs;
+  DevBuf<int> sp_ptr, sp_cam, sp_lm, spe_ptr, spe, st_ptr, st_cam, st_lm, ste_ptr, ste;
+  DevBuf<int> blk_a, blk_b, diag_blk, offdiag_blk, bdp_ptr, bdp, bdt_ptr, bdt, bsp_ptr, bst_ptr, gsel_p, gsel_t;
+  DevBuf<int2> bsp, bst;
+  CholSymbolic chol;
+};
+// analysis_dev.cu: the same analysis as analyze_structure(), for an unsharded problem, entirely on the device (radix sorts
+// and scans instead of counting sorts); returns TSLAM_ERR_ARG + "unsupported" when the problem exceeds its packing limits.
+bool device_analysis_supported(const tslam_ctx* ctx, const tslam_dev_problem* d);
+int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& X, double* lap_ms /*[4]*/);
+
 // ba_eval.cu (robustified evaluation used inside the LM loop)
 int launch_eval_points_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double* cams, const double* rho, const uint8_t* active,
                               double* r, double* J, double* cost_part, int* n_parts);
