@@ -53,6 +53,21 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const double* __restrict
   if (threadIdx.x == 0) *out = accumulate ? *out + s[0] : s[0];
 }
 
+// two interleaved series (stride 2) -> two scalars in one launch: CTA b sums parts[2 i + b]; same order as sum_parts_kernel
+__global__ void __launch_bounds__(256) sum_parts_pair_kernel(const double* __restrict__ parts, int n, double* out0, double* out1, int accumulate) {
+  __shared__ double s[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += parts[(size_t)i * 2 + blockIdx.x];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  double* out = blockIdx.x ? out1 : out0;
+  if (threadIdx.x == 0) *out = accumulate ? *out + s[0] : s[0];
+}
+
 __device__ __forceinline__ double block_sum_256(double v, double* s) {
   s[threadIdx.x] = v;
   __syncthreads();
@@ -244,6 +259,8 @@ struct BlockArgs {
 // sums (36 x log2(G) 64-bit shuffles), which dominated when every block had a whole warp.
 template <int G>
 __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int* __restrict__ list, int nlist) {
+  static_assert(G == 8 || G == 32 || G == 128, "group size");
+  __shared__ double xs[G == 128 ? 4 * 54 : 1];   // G == 128 (one CTA per block): cross-warp stage of the reduction
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x & (G - 1);
   const bool valid = gi < nlist;           // lanes of an empty group still take part in the full-warp shuffles
   const int blk = valid ? list[gi] : 0;
@@ -342,19 +359,44 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int
     }
   }
   // ---- reduce over the G lanes of the group (butterfly: every lane ends with the total) ----
+  constexpr int GW = G > 32 ? 32 : G;
 #pragma unroll
   for (int k = 0; k < 36; ++k)
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-  if (G == 32 ? diag : __any_sync(0xffffffffu, diag)) {   // G == 32: the branch is warp-uniform
+    for (int o = GW / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  if (G >= 32 ? diag : __any_sync(0xffffffffu, diag)) {   // G >= 32: the branch is warp-uniform
 #pragma unroll
     for (int k = 0; k < 6; ++k)
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
+      for (int o = GW / 2; o > 0; o >>= 1) {
         gr[k] += __shfl_xor_sync(0xffffffffu, gr[k], o);
         dd[k] += __shfl_xor_sync(0xffffffffu, dd[k], o);
         bred[k] += __shfl_xor_sync(0xffffffffu, bred[k], o);
       }
+  }
+  if (G == 128) {   // four warp totals -> one, in warp order; thread k (< 54) then owns value k
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 36; ++k) xs[w * 54 + k] = acc[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { xs[w * 54 + 36 + k] = gr[k]; xs[w * 54 + 42 + k] = dd[k]; xs[w * 54 + 48 + k] = bred[k]; }
+    }
+    __syncthreads();
+    if (!valid || threadIdx.x >= 54) return;
+    const int k = threadIdx.x;
+    const double v = (xs[k] + xs[54 + k]) + (xs[108 + k] + xs[162 + k]);
+    if (k < 36) A.Sblk[(size_t)blk * 36 + k] = v;
+    if (diag) {   // gr, dd, bred of the same index live in threads 36+k, 42+k, 48+k: thread 36+k gathers its triple from smem
+      if (k >= 36 && k < 42) {
+        const int q = k - 36;
+        const double g_ = v;
+        const double d_ = (xs[42 + q] + xs[54 + 42 + q]) + (xs[108 + 42 + q] + xs[162 + 42 + q]);
+        const double b_ = (xs[48 + q] + xs[54 + 48 + q]) + (xs[108 + 48 + q] + xs[162 + 48 + q]);
+        A.udiag[6 * a + q] = d_; A.bvec[6 * a + q] = g_ - b_; A.graw[6 * a + q] = g_ / A.scale_c[6 * a + q];
+      }
+    }
+    return;
   }
   if (!valid) return;
   double* out = A.Sblk + (size_t)blk * 36;
@@ -566,8 +608,11 @@ __global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, co
 }
 __global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  atomic_max_nonneg(mx + MX_GMAX, fabs(g_scaled[i] / scale[i]));
+  // max over the bit patterns (what the atomic does; keeps a NaN visible), one atomic per warp instead of per landmark
+  unsigned long long m = i < n ? (unsigned long long)__double_as_longlong(fabs(g_scaled[i] / scale[i])) : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(mx + MX_GMAX), m);
 }
 
 __global__ void copy_fail_kernel(const int* fail, double* mx) {
@@ -745,8 +790,7 @@ static int eval_at(Solver& S, const double* cams, const double* rho, const doubl
   if (rc) return rc;
   rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? S.tJ.p : nullptr, parts + 2 * np, &nt);
   if (rc) return rc;
-  LAUNCH(sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 0, S.sc + cost_slot, 0));
-  LAUNCH(sum_parts_kernel<<<1, 256, 0, ctx->stream>>>(parts, np + nt, 2, 1, S.sc + cost_slot + 1, 0));
+  LAUNCH(sum_parts_pair_kernel<<<2, 256, 0, ctx->stream>>>(parts, np + nt, S.sc + cost_slot, S.sc + cost_slot + 1, 0));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -817,8 +861,8 @@ static int compute_step(Solver& S, double radius) {
     B.Ep = S.Ep.p; B.Vinvp = S.Vinvp.p; B.gp = S.gp.p; B.sp_lm = S.sp_lm.p;
     B.Et = S.Et.p; B.Vinvt = S.Vinvt.p; B.gt = S.gt.p; B.st_lm = S.st_lm.p;
     B.Sblk = S.Sblk; B.bvec = S.bvec; B.graw = S.graw; B.udiag = S.udiag;
-    // diagonal blocks (heavy gather lists) get a warp each, off-diagonal blocks 8 lanes
-    LAUNCH(schur_block_kernel<32><<<grid_for(S.nc * 32, 128), 128, 0, st>>>(B, S.diag_blk.p, S.nc));
+    // diagonal blocks (heavy gather lists, ~650 entries on the global-BA shape) get a CTA each, off-diagonal blocks 8 lanes
+    LAUNCH(schur_block_kernel<128><<<S.nc, 128, 0, st>>>(B, S.diag_blk.p, S.nc));
     if (S.noff) LAUNCH(schur_block_kernel<8><<<grid_for(S.noff * 8, 128), 128, 0, st>>>(B, S.offdiag_blk.p, S.noff));
     TSL_CHECK_LAUNCH();
   }
@@ -847,8 +891,7 @@ static int compute_step(Solver& S, double radius) {
   if (S.nvp) LAUNCH(candidate_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts));
   if (S.nvt) LAUNCH(candidate_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp));
   if (gvp + gvt) {
-    LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 0, S.sc + SC_STEP2, 1));
-    LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(parts, gvp + gvt, 2, 1, S.sc + SC_CNORM2, 1));
+    LAUNCH(sum_parts_pair_kernel<<<2, 256, 0, st>>>(parts, gvp + gvt, S.sc + SC_STEP2, S.sc + SC_CNORM2, 1));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
 // registers. x holds y on entry and is overwritten panel by panel. flags[j] == epoch marks x_j final for this call.
 __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict__ A, int ld, int npanels, const int* __restrict__ panels,
                                                         const int* __restrict__ below_ptr, const int* __restrict__ below,
-                                                        const double* __restrict__ Linv, double* x, int* flags, int epoch) {
+                                                        const double* __restrict__ Linv, const double* __restrict__ y, double* x, int* flags, int epoch) {
   // 256 threads = 4 groups x 64 columns; group g takes the tiles e = g (mod 4) of the list, partial sums meet in smem
   __shared__ double sx[4][NB];
   __shared__ double st[4][NB];
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict
 #pragma unroll
     for (int r = 0; r < 16; ++r) minv[r] = M[(16 * g + r) * NB + c];
   }
-  const double yj = (g == 0) ? x[j * NB + c] : 0.0;   // y_j: written before this launch
+  const double yj = (g == 0) ? y[j * NB + c] : 0.0;   // y_j = (L^-1 b)_j: the b row of the factorised workspace
   // ---- wait for the panels below ----
   for (int e = e0 + (int)threadIdx.x; e < e1; e += 256) {
     const volatile int* f = flags + below[e];
@@ -298,12 +298,10 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
     mark(1);
   }
   TSL_CHECK_LAUNCH();
-  LAUNCH(copy_row_kernel<<<(ld + 255) / 256, 256, 0, s>>>(A + (size_t)Tn * NB * ld, xout, ld));
-  mark(2);
   {
     const int np = sym.panel_ptr[sym.nwaves];
     const int epoch = ++sym.epoch;
-    LAUNCH(backsolve_kernel<<<np, 256, 0, s>>>(A, ld, np, sym.panels.p, sym.below_ptr.p, sym.below.p, sym.Ldiag.p, xout, sym.flags.p, epoch));
+    LAUNCH(backsolve_kernel<<<np, 256, 0, s>>>(A, ld, np, sym.panels.p, sym.below_ptr.p, sym.below.p, sym.Ldiag.p, A + (size_t)Tn * NB * ld, xout, sym.flags.p, epoch));
     mark(3);
   }
   if (trace) {
