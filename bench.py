@@ -191,7 +191,7 @@ def main():
     line = {"metric": "ba_resjac_mevals_per_s", "value": value, "unit": "M-evals/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "each LM iteration rewrites the 71 MB dense reduced matrix + 21 MB of J between passes over the inputs; the stand-alone kernel timings flush L2 or exceed it (see roofline)",
+            "config": {"workload": WORKLOAD, "l2": "the solve is not L2-flushed between iterations (its working set, 21 MB of J + 8 MB of factor tiles + index lists, is what a real solve keeps in L2); the stand-alone kernel timings of `roofline` flush L2 or exceed it",
                        "landmark_sharding": f"landmark % {world}" if world > 1 else "none"},
             "lm_iter_ms": dev_ms / max(1, its), "lm_iterations_per_step": its / K, "wall_ms_per_step": wall_ms / K,
             "gpu_launches": int(launches), "clocks": clk}
@@ -221,8 +221,8 @@ def main():
                                "mevals_per_s": prob.n_pobs / (ms * 1e-3) / 1e6,
                                "note": "one partial wave (782 CTAs on 148 SMs): launch/latency bound, see DESIGN.md"}
         line["dominant_kernel"] = {"name": "potrf_trsm_kernel (64x64 tile factor + triangular solve of the reduced camera system)",
-                                   "share_of_lm_iteration": "largest single kernel of the step (profiles/r1_launches_lm.txt)",
-                                   "bound": "latency (sequential column eliminations); FP64 tensor work of the step is syrk_wave_kernel"}
+                                   "share_of_lm_iteration": "largest single kernel of the step (profiles/r1_launches_lm.txt); 14 dependent waves per factorisation",
+                                   "bound": "latency: 64 dependent pivots per tile (rsqrt -> scale -> update -> broadcast, ~185 cycles each, tools/ubench/chol_tile_bench.cu); FP64 tensor work of the step is syrk_wave_kernel"}
         # ---- end to end through the public C-ABI with host buffers
         e2e_t, e2e_evals = 0.0, 0
         fr_bytes = 8 * (2 * prob.n_pobs + 8 * prob.n_tobs)
@@ -235,7 +235,7 @@ def main():
                 e2e_t += dt; e2e_evals += jac_evals(summ, prob)
         line["e2e"] = {"value": e2e_evals / e2e_t / 1e6, "unit": "M-evals/s", "h2d_bytes_per_step": problem_bytes(prob),
                        "d2h_bytes_per_step": int(prob.cams.nbytes + prob.rho.nbytes + prob.theta.nbytes + fr_bytes),
-                       "ms_per_step": 1e3 * e2e_t / K, "call": "tslam_solve (host buffers, pageable)"}
+                       "ms_per_step": 1e3 * e2e_t / K, "call": "tslam_solve (caller-owned pageable host buffers: upload, device-side structure analysis, LM loop, download)"}
         # ---- CPU baseline beside it: oracle port, bounded sample
         from oracle import pyoracle as po
         po.build()
