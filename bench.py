@@ -42,17 +42,29 @@ def read_peaks():
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def wait_running(self, timeout=3.0):
+        """Blocks until the sampler has produced its first line (nvidia-smi takes ~0.1 s to start)."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return True
+            time.sleep(0.01)
+        return False
+
+    def stop(self, t_begin=None, t_end=None):
+        """Samples inside [t_begin, t_end] (time.time() of the timed region) are used; if the region was shorter than the
+        sampling period, all samples taken since the sampler started (warm-up + timed region, GPU under load) are."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -63,20 +75,31 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 7:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
+                row = [float(c[0]), float(c[1]), c[3:7], None]
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+            if len(c) >= 8:
+                try:
+                    row[3] = datetime.datetime.strptime(c[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    pass
+            rows.append(row)
+        inside = [r for r in rows if r[3] is not None and t_begin is not None and t_begin - 0.02 <= r[3] <= t_end + 0.02]
+        used = inside if inside else rows
+        reasons = set()
+        for r in used:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if used:
+            out.update(sm_mhz=float(np.median([r[0] for r in used])), sm_max_mhz=float(max(r[1] for r in used)), reasons=sorted(reasons), samples=len(used),
+                       window="timed region" if inside else "warm-up + timed region (region shorter than the sampling period)")
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -164,11 +187,14 @@ def main():
     n_obs = prob.n_pobs + prob.n_tobs
     dev = ctx.upload(prob)
     W, K = max(args.warmup, 3), args.steps
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.wait_running()
     for _ in range(W):
         dev.lm_iterations(GLOBAL_BA_ITERS)
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib().tslam_launch_count()
     barrier()
+    t_region0 = time.time()
     t_wall0 = time.perf_counter()
     dev_ms, evals, its = 0.0, 0, 0
     phases_acc = np.zeros(8)
@@ -180,7 +206,7 @@ def main():
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
     launches = lib().tslam_launch_count() - launches0
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_region0, time.time()) if clocks else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

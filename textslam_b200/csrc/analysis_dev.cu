@@ -68,43 +68,63 @@ __global__ void dist_hist_kernel(int n, const int* __restrict__ cam, const int* 
   if (a >= 0 && b >= 0) atomicAdd(&hist[abs(a - b)], 1);
 }
 
-// Nested-dissection order of the free cameras — the serial logic of analysis.cpp (analyze_structure) on one thread:
-// the inputs are a histogram and the outputs a permutation of <= 2^14 cameras.
-__global__ void nd_order_kernel(int K, int* camslot, const int* __restrict__ hist, const Counts* cnt, int* new_of_old, int* unit_order) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// Nested-dissection order of the free cameras — the logic of analysis.cpp (analyze_structure) on one warp: the inputs are
+// a histogram and the outputs a permutation of <= 2^14 cameras; the scans over it are lane-parallel, the (tiny) recursive
+// bisection runs on lane 0.
+__global__ void __launch_bounds__(32) nd_order_kernel(int K, int* camslot, const int* __restrict__ hist, const Counts* cnt, int* new_of_old, int* unit_order) {
+  const int lane = threadIdx.x;
   const int nc = cnt->nc;
   if (nc < 128) return;
   unsigned long long nd = 0;
-  for (int d = 0; d < nc; ++d) nd += (unsigned long long)hist[d];
+  for (int d = lane; d < nc; d += 32) nd += (unsigned long long)hist[d];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
   int bw = 0;
-  if (nd) {
+  if (nd) {   // 98th percentile of the |slot(cam) - slot(host)| distances: first d with cumulative count > q
     const unsigned long long q = (unsigned long long)(0.98 * (double)(nd - 1));
     unsigned long long acc = 0; int dq = 0;
-    for (int d = 0; d < nc; ++d) { acc += (unsigned long long)hist[d]; if (acc > q) { dq = d; break; } }
+    for (int d0 = 0; d0 < nc; d0 += 32) {
+      const int d = d0 + lane;
+      unsigned long long inc = d < nc ? (unsigned long long)hist[d] : 0ull;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      const unsigned hit = __ballot_sync(0xffffffffu, d < nc && acc + inc > q);
+      if (hit) { dq = d0 + __ffs(hit) - 1; break; }
+      acc += __shfl_sync(0xffffffffu, inc, 31);
+    }
     bw = 2 * dq;
   }
   const int U = 32 * ((bw + 1 + 31) / 32);
   const int nfull = nc / U;
   if (nfull < 4) return;
   int n_order = 0;
-  int lo_s[64], hi_s[64], st_s[64]; int sp = 0;   // recursive bisection, post-order: left, right, separator
-  lo_s[0] = 0; hi_s[0] = nfull; st_s[0] = 0; sp = 1;
-  while (sp > 0) {
-    --sp;
-    const int lo = lo_s[sp], hi = hi_s[sp], stage = st_s[sp];
-    if (hi - lo <= 0) continue;
-    if (hi - lo <= 2) { for (int u = lo; u < hi; ++u) unit_order[n_order++] = u; continue; }
-    const int mid = (lo + hi) / 2;
-    if (stage == 0) {
-      lo_s[sp] = lo; hi_s[sp] = hi; st_s[sp] = 1; ++sp;
-      lo_s[sp] = mid + 1; hi_s[sp] = hi; st_s[sp] = 0; ++sp;
-      lo_s[sp] = lo; hi_s[sp] = mid; st_s[sp] = 0; ++sp;
-    } else unit_order[n_order++] = mid;
+  if (lane == 0) {
+    int lo_s[64], hi_s[64], st_s[64]; int sp = 0;   // recursive bisection, post-order: left, right, separator
+    lo_s[0] = 0; hi_s[0] = nfull; st_s[0] = 0; sp = 1;
+    while (sp > 0) {
+      --sp;
+      const int lo = lo_s[sp], hi = hi_s[sp], stage = st_s[sp];
+      if (hi - lo <= 0) continue;
+      if (hi - lo <= 2) { for (int u = lo; u < hi; ++u) unit_order[n_order++] = u; continue; }
+      const int mid = (lo + hi) / 2;
+      if (stage == 0) {
+        lo_s[sp] = lo; hi_s[sp] = hi; st_s[sp] = 1; ++sp;
+        lo_s[sp] = mid + 1; hi_s[sp] = hi; st_s[sp] = 0; ++sp;
+        lo_s[sp] = lo; hi_s[sp] = mid; st_s[sp] = 0; ++sp;
+      } else unit_order[n_order++] = mid;
+    }
+    __threadfence_block();
   }
-  int next = 0;
-  for (int k = 0; k < n_order; ++k) { const int u = unit_order[k]; for (int c = u * U; c < (u + 1) * U; ++c) new_of_old[c] = next++; }
-  for (int c = nfull * U; c < nc; ++c) new_of_old[c] = next++;   // the partial unit goes last (keeps units tile-aligned)
-  for (int k = 0; k < K; ++k) if (camslot[k] >= 0) camslot[k] = new_of_old[camslot[k]];
+  n_order = __shfl_sync(0xffffffffu, n_order, 0);
+  __syncwarp();
+  for (int k = 0; k < n_order; ++k) {
+    const int u = unit_order[k];
+    for (int c = lane; c < U; c += 32) new_of_old[u * U + c] = k * U + c;
+  }
+  for (int c = nfull * U + lane; c < nc; c += 32) new_of_old[c] = n_order * U + (c - nfull * U);   // the partial unit goes last (keeps units tile-aligned)
+  __threadfence_block();
+  __syncwarp();
+  for (int k = lane; k < K; k += 32) if (camslot[k] >= 0) camslot[k] = new_of_old[camslot[k]];
 }
 
 __global__ void lm_flag_kernel(int n, const int* __restrict__ lu, const uint8_t* __restrict__ lf, int* __restrict__ f) {
