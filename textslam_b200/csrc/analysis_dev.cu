@@ -426,6 +426,7 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   TSL_CUDA(cudaStreamSynchronize(st));
   auto T1 = std::chrono::steady_clock::now();
   X.nc = hc.nc; X.nl = hc.nl; X.npl = hc.npl; X.nvp = hc.nl; X.nvt = hc.npl; X.nsp = hc.nsp; X.nst = hc.nst; X.nblk = hc.nblk; X.noff = hc.nblk - hc.nc;
+  X.est_entries = (long long)hc.npairs_p + hc.npairs_t + 3LL * ((long long)np + nt);
   X.n = 6 * X.nc;
   X.Tn = chol_workspace_dims(X.n, &X.ld, &X.rows);
   {   // tile-level symbolic factorisation + level schedule on the host (Tn^2 flags), uploaded like on the host path

@@ -155,6 +155,89 @@ __global__ void slot_accum_kernel(int ns, const int* __restrict__ ent_ptr, const
   }
 }
 
+// Same sums with one WARP per landmark (lanes over the (observation, residual row) pairs, butterfly at the end): the text
+// planes are few (tens) with hundreds of residual rows each — a thread per plane left the GPU idle behind 30 serial loops
+// (local BA C4: 94 us per call, profiles/r1_notes.md).
+template <int D, int ROWS, int JC>
+__global__ void __launch_bounds__(128) lm_accum_warp_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
+                                                            const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
+                                                            double* __restrict__ g) {
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (v >= nv) return;   // warp-uniform
+  double Vv[D * D], gv[D];
+#pragma unroll
+  for (int k = 0; k < D * D; ++k) Vv[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) gv[k] = 0.0;
+  const int e0 = obs_ptr[v], n_items = (obs_ptr[v + 1] - e0) * ROWS;
+  for (int t = lane; t < n_items; t += 32) {
+    const int i = obs[e0 + t / ROWS], row = t % ROWS;
+    const double* Ji = J + (size_t)i * ROWS * JC + row * JC + 12;
+    const double rr = r[(size_t)i * ROWS + row];
+    double jl[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) jl[a] = Ji[a];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      gv[a] += jl[a] * rr;
+#pragma unroll
+      for (int b = 0; b < D; ++b) Vv[a * D + b] += jl[a] * jl[b];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < D * D; ++k) Vv[k] += __shfl_xor_sync(0xffffffffu, Vv[k], o);
+#pragma unroll
+    for (int k = 0; k < D; ++k) gv[k] += __shfl_xor_sync(0xffffffffu, gv[k], o);
+  }
+  if (lane == 0) {
+    double s[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) s[a] = scale[v * D + a];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      g[v * D + a] = gv[a] * s[a];
+#pragma unroll
+      for (int b = 0; b < D; ++b) V[(size_t)v * D * D + a * D + b] = Vv[a * D + b] * s[a] * s[b];
+    }
+  }
+}
+
+template <int D, int ROWS, int JC>
+__global__ void __launch_bounds__(128) slot_accum_warp_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
+                                                              const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
+                                                              const double* __restrict__ scale_l, double* __restrict__ E) {
+  const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (sidx >= ns) return;   // warp-uniform
+  double Ev[6 * D];
+#pragma unroll
+  for (int k = 0; k < 6 * D; ++k) Ev[k] = 0.0;
+  const int e0 = ent_ptr[sidx], n_items = (ent_ptr[sidx + 1] - e0) * ROWS;
+  for (int t = lane; t < n_items; t += 32) {
+    const int code = ent[e0 + t / ROWS], row = t % ROWS;
+    const int i = code >> 1, off = (code & 1) * 6;
+    const double* Ji = J + (size_t)i * ROWS * JC + row * JC;
+    double jl[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) jl[a] = Ji[12 + a];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double jc = Ji[off + c];
+#pragma unroll
+      for (int a = 0; a < D; ++a) Ev[c * D + a] += jc * jl[a];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 6 * D; ++k) Ev[k] += __shfl_xor_sync(0xffffffffu, Ev[k], o);
+  const int cam = slot_cam[sidx], lm = slot_lm[sidx];
+#pragma unroll
+  for (int k = 0; k < 6 * D; ++k)
+    if (lane == k) E[(size_t)sidx * 6 * D + k] = Ev[k] * scale_c[6 * cam + k / D] * scale_l[lm * D + k % D];
+}
+
 __device__ __forceinline__ double lm_damp(double d, double inv_radius) { return fmin(fmax(d, 1e-6), 1e32) * inv_radius; }
 
 // ---- (V + D^2)^-1 for the current trust-region radius ----------------------------------------------
@@ -263,7 +346,7 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int
   __shared__ double xs[G == 128 ? 4 * 54 : 1];   // G == 128 (one CTA per block): cross-warp stage of the reduction
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x & (G - 1);
   const bool valid = gi < nlist;           // lanes of an empty group still take part in the full-warp shuffles
-  const int blk = valid ? list[gi] : 0;
+  const int blk = valid ? (list ? list[gi] : gi) : 0;   // list == NULL: every block, in order
   const int a = A.blk_a[blk], b = A.blk_b[blk];
   const bool diag = a == b;
   double sa[6], sb[6];
@@ -706,6 +789,7 @@ static int analyze_on_host_and_upload(Solver& S, Analysis& A, std::chrono::stead
   TSL_CUDA(up(S.ste_ptr, A.LT.ent_ptr, st)); TSL_CUDA(up(S.ste, A.LT.ent, st));
   TSL_CUDA(up(S.blk_a, A.blk_a, st)); TSL_CUDA(up(S.blk_b, A.blk_b, st)); TSL_CUDA(up(S.diag_blk, A.diag_blk, st));
   TSL_CUDA(up(S.offdiag_blk, A.offdiag_blk, st)); S.noff = (int)A.offdiag_blk.size();
+  S.est_entries = (long long)A.bdp.size() + (long long)A.bdt.size() + (long long)A.bsp.size() + (long long)A.bst.size();
   TSL_CUDA(up(S.bdp_ptr, A.bdp_ptr, st)); TSL_CUDA(up(S.bdp, A.bdp, st)); TSL_CUDA(up(S.bdt_ptr, A.bdt_ptr, st)); TSL_CUDA(up(S.bdt, A.bdt, st));
   TSL_CUDA(up(S.bsp_ptr, A.bsp_ptr, st)); TSL_CUDA(up_as(S.bsp, A.bsp, st)); TSL_CUDA(up(S.bst_ptr, A.bst_ptr, st)); TSL_CUDA(up_as(S.bst, A.bst, st));
   if (d->sharded) { TSL_CUDA(up(S.gsel_p, d->gsel_p, st)); TSL_CUDA(up(S.gsel_t, d->gsel_t, st)); }
@@ -810,8 +894,8 @@ static int accumulate_landmarks(Solver& S) {
     if (S.nsp) LAUNCH(slot_accum_kernel<1, 2, 13><<<grid_for(S.nsp, 128), 128, 0, st>>>(S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p));
   }
   if (S.nvt) {
-    LAUNCH(lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
-    if (S.nst) LAUNCH(slot_accum_kernel<3, 8, 15><<<grid_for(S.nst, 64), 64, 0, st>>>(S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p));
+    LAUNCH(lm_accum_warp_kernel<3, 8, 15><<<grid_for(S.nvt * 32, 128), 128, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    if (S.nst) LAUNCH(slot_accum_warp_kernel<3, 8, 15><<<grid_for(S.nst * 32, 128), 128, 0, st>>>(S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -835,7 +919,7 @@ static int compute_jacobi_scaling(Solver& S) {
   }
   if (S.nvt) {
     LAUNCH(fill_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.scale_vt.p, 3 * S.nvt, 1.0));
-    LAUNCH(lm_accum_kernel<3, 8, 15><<<grid_for(S.nvt, 64), 64, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    LAUNCH(lm_accum_warp_kernel<3, 8, 15><<<grid_for(S.nvt * 32, 128), 128, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
     LAUNCH(lm_scale_kernel<3><<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.nvt, S.Vt.p, S.scale_vt.p));
   }
   TSL_CHECK_LAUNCH();
@@ -861,9 +945,14 @@ static int compute_step(Solver& S, double radius) {
     B.Ep = S.Ep.p; B.Vinvp = S.Vinvp.p; B.gp = S.gp.p; B.sp_lm = S.sp_lm.p;
     B.Et = S.Et.p; B.Vinvt = S.Vinvt.p; B.gt = S.gt.p; B.st_lm = S.st_lm.p;
     B.Sblk = S.Sblk; B.bvec = S.bvec; B.graw = S.graw; B.udiag = S.udiag;
-    // diagonal blocks (heavy gather lists, ~650 entries on the global-BA shape) get a CTA each, off-diagonal blocks 8 lanes
-    LAUNCH(schur_block_kernel<128><<<S.nc, 128, 0, st>>>(B, S.diag_blk.p, S.nc));
-    if (S.noff) LAUNCH(schur_block_kernel<8><<<grid_for(S.noff * 8, 128), 128, 0, st>>>(B, S.offdiag_blk.p, S.noff));
+    // diagonal blocks (heavy gather lists, ~650 entries on the global-BA shape) get a CTA each, off-diagonal blocks 8 lanes —
+    // unless the camera graph is small and dense (local BA: 7 cameras, 28 blocks, ~600 entries each): then every block gets a CTA
+    if (S.est_entries > 96 * (long long)S.nblk) {
+      LAUNCH(schur_block_kernel<128><<<S.nblk, 128, 0, st>>>(B, nullptr, S.nblk));
+    } else {
+      LAUNCH(schur_block_kernel<128><<<S.nc, 128, 0, st>>>(B, S.diag_blk.p, S.nc));
+      if (S.noff) LAUNCH(schur_block_kernel<8><<<grid_for(S.noff * 8, 128), 128, 0, st>>>(B, S.offdiag_blk.p, S.noff));
+    }
     TSL_CHECK_LAUNCH();
   }
   mark(S, 3);  // all-reduce

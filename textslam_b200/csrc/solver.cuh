@@ -28,6 +28,7 @@ struct SolverIndex {
   int lp = 0, lt = 0;                         // local observations
   int nvp = 0, nvt = 0, nsp = 0, nst = 0;     // owned landmarks / (landmark, camera) slots
   int nblk = 0, noff = 0;                     // non-zero 6x6 blocks (a <= b), of which off-diagonal
+  long long est_entries = 0;                  // gather-list entries over all blocks (an upper estimate on the device path)
   int n = 0, ld = 0, rows = 0, Tn = 0;        // reduced system dims
   std::vector<int> camslot;                   // host copies (multi-GPU result merge only)
   std::vector<int> vp_gl_h, vt_gl_h, lmfree_p_h, lmfree_t_h;
