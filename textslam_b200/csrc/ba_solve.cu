@@ -1054,7 +1054,7 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
   while (true) {
     if (iter >= max_iters) { term = TSLAM_TERM_NO_CONVERGENCE; break; }
     if (radius <= min_radius) { term = TSLAM_TERM_NO_CONVERGENCE; break; }
-    if (S.nc + S.nl + S.npl == 0) break;
+    if (S.nc + S.nl + S.npl == 0) { term = TSLAM_TERM_GRADIENT_TOL; break; }   // nothing to optimise: the (empty) gradient passes Ceres' first test
     // ---- linear solve + candidate (speculative: the gradient test for THIS iteration is read back with it) ----
     if ((rc = compute_step(S, radius))) return rc;
     if ((rc = gradient_max_norm(S))) return rc;
@@ -1121,6 +1121,19 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
     }
   }
   TSL_CUDA(cudaStreamSynchronize(st));
+  if (!have_cost) {   // left before the first read-back (no free parameter block, or max_iters == 0): the costs of iteration 0 are still wanted
+    const double* sc_src = S.sc;
+    if (ctx->world > 1) {
+      TSL_CUDA(cudaMemcpyAsync(S.scr.p, S.sc, SC_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if ((rc = comm_allreduce_sum(ctx, S.scr.p, SC_N))) return rc;
+      sc_src = S.scr.p;
+    }
+    TSL_CUDA(cudaMemcpyAsync(h, sc_src, SC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TSL_CUDA(cudaStreamSynchronize(st));
+    x_cost = h[SC_COST]; fixed_cost = h[SC_FIXED];
+    sum.initial_cost = x_cost + fixed_cost; sum.fixed_cost = fixed_cost;
+    if (trace) { trace[0] = x_cost + fixed_cost; trace[1] = radius; trace[2] = 0; trace[3] = 1; }
+  }
   // make d->cams / rho / theta hold the solution
   if (S.x_cams != d->cams.p) {
     TSL_CUDA(cudaMemcpyAsync(d->cams.p, S.x_cams, sizeof(double) * 7 * (size_t)S.K, cudaMemcpyDeviceToDevice, st));
