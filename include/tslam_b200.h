@@ -243,6 +243,40 @@ int tslam_text_info(tslam_ctx* ctx, const uint8_t* imgs, int n_imgs, int w, int 
  * counted in *n_singular (may be NULL). */
 int tslam_theta_covariance(tslam_ctx* ctx, const tslam_ba_problem* p, int jac_mode, double* cov_out, int32_t* n_singular);
 
+/* ---- post-solve chi^2 gates ------------------------------------------------------ */
+/* Replaces the outlier loops that follow Problem::Evaluate in PyrPoseOptim (src/optimizer.cc:1236-1302) and PyrBA
+ * (:1616-1684) on the loss-corrected final residuals (2*n_pobs point values followed by 8*n_tobs text values, insertion order):
+ *   point observation i bad  <=>  (r[2i]/w_x)^2 > chi2  ||  (r[2i+1]/w_y)^2 > chi2, chi2 = chi2_mono (+ relax_amount when
+ *                                 n_tobs < relax_below_text_blocks: ":1240-1241, :1620-1622");
+ *   text block j bad         <=>  any of its 8 |r/w_text| > chi2_text (:1264-1281);
+ *   text object o bad        <=>  (double)bad_blocks(o) / (double)obj_size[o] > text_ratio (:1286-1294).
+ * t_obj[j] = object of block j (vIdx2vTextsGood / vIdx2IdxTexts), obj_size[o] = vSizeEachObj[o]; the reference adds the
+ * blocks of an object contiguously, and the number of blocks naming an object must equal obj_size[o] (TSLAM_ERR_ARG
+ * otherwise; objects of size 0 are never flagged). Outputs are 0/1 bytes (1 = the reference sets the Good flag to false);
+ * the caller keeps applying them to its vObvGood* vectors through its own index maps. counts_out (may be NULL) =
+ * {nBadS, bad text blocks, nBadT}. */
+typedef struct tslam_gate_options {
+  int32_t gate_points;              /* SCENEOutlier */
+  int32_t gate_text;                /* TEXTOutlier  */
+  double w_point[2];                /* weight_S_x, weight_S_y the residuals carry   */
+  double chi2_mono;                 /* 12.25                                        */
+  int32_t relax_below_text_blocks;  /* 50 (0 disables the relaxation)               */
+  double relax_amount;              /* 4                                            */
+  double w_text;                    /* weight_T                                     */
+  double chi2_text;                 /* 0.5 / 0.95 (pose), 0.5..0.8 (BA)             */
+  double text_ratio;                /* 0.99                                         */
+} tslam_gate_options;
+/* residuals in caller-owned host memory (any solve, any source) */
+int tslam_gate_residuals(tslam_ctx* ctx, const double* final_residuals, int n_pobs, int n_tobs, const int32_t* t_obj,
+                         const int32_t* obj_size, int n_obj, const tslam_gate_options* gate,
+                         uint8_t* pt_bad, uint8_t* tf_bad, uint8_t* obj_bad, int32_t counts_out[3]);
+/* tslam_solve followed by the gates on the residuals while they are still in HBM (no second upload): one call per
+ * pyramid level of PoseOptim / LocalBundleAdjustment. final_residuals and trace may be NULL. */
+int tslam_solve_gated(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, const tslam_gate_options* gate,
+                      const int32_t* t_obj, const int32_t* obj_size, int n_obj,
+                      tslam_solve_summary* summary, double* final_residuals, double* trace,
+                      uint8_t* pt_bad, uint8_t* tf_bad, uint8_t* obj_bad, int32_t counts_out[3]);
+
 /* ---- projection-guided descriptor matching core ------------------------------------ */
 /* Inner loop of tracking::SearchFrom3D* (src/tracking.cc:1161-1175,1241-1256,1310-1325) with
  * tracking::DescriptorDistance (:2762-2778): per query the first candidate (list order) of minimum Hamming distance.

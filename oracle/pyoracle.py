@@ -190,6 +190,22 @@ def match_hamming(query_desc, train_desc, cand_ptr, cand_idx):
     return bi, bd, sd
 
 
+def gate_residuals(final_residuals, n_pobs, n_tobs, gate, t_obj=None, obj_size=None):
+    """The reference's outlier loops (src/optimizer.cc:1236-1302, 1616-1684) on a final residual vector.
+    Returns (pt_bad, tf_bad, obj_bad, (nBadS, nBadFeat, nBadT)); raises if the reference's asserts would fire."""
+    fr = np.ascontiguousarray(final_residuals, dtype=np.float64)
+    t_obj = np.ascontiguousarray(t_obj if t_obj is not None else np.zeros(n_tobs), dtype=np.int32)
+    obj_size = np.ascontiguousarray(obj_size if obj_size is not None else [], dtype=np.int32)
+    pb, tb, ob = np.zeros(n_pobs, np.uint8), np.zeros(n_tobs, np.uint8), np.zeros(len(obj_size), np.uint8)
+    cnt = (C.c_int32 * 3)()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().tso_gate_residuals(_dp(fr), C.c_int(n_pobs), C.c_int(n_tobs), vp(t_obj), vp(obj_size), C.c_int(len(obj_size)),
+                                  C.byref(gate), vp(pb), vp(tb), vp(ob), cnt)
+    if rc != 0:
+        raise ValueError(f"tso_gate_residuals: inconsistent object bookkeeping ({rc})")
+    return pb, tb, ob, tuple(cnt)
+
+
 def theta_covariance(prob, jac_mode=0):
     cov = np.zeros((len(prob.theta), 3, 3))
     pc = prob.as_c()

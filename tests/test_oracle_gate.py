@@ -1,0 +1,129 @@
+"""CPU tests: the oracle restatement of the post-solve chi^2 loops (src/optimizer.cc:1236-1302, 1616-1684) against
+hand-computed cases and an independent vectorised derivation, the Good-flag bookkeeping of the pyramid loop
+(textslam_b200.api.run_pyramid) driven by the oracle, and the ctypes layout of tslam_gate_options."""
+import os
+import subprocess
+import numpy as np
+import pytest
+import textslam_b200 as T
+from textslam_b200 import synth
+from textslam_b200.api import PyramidLevel, run_pyramid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def random_gate_case(seed, n_p=500, n_obj=7, max_feats=30, scale_p=3.0, scale_t=0.4):
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(0, max_feats, n_obj)
+    t_obj = np.repeat(np.arange(n_obj), sizes)
+    n_t = int(sizes.sum())
+    fr = np.concatenate([rng.normal(0, scale_p, 2 * n_p), rng.normal(0, scale_t, 8 * n_t)])
+    return fr, n_p, n_t, t_obj.astype(np.int32), sizes.astype(np.int32)
+
+
+def numpy_gate(fr, n_p, n_t, t_obj, sizes, g):
+    rp = fr[:2 * n_p].reshape(-1, 2); rt = fr[2 * n_p:].reshape(-1, 8)
+    chi2 = g.chi2_mono + (g.relax_amount if 0 < g.relax_below_text_blocks and n_t < g.relax_below_text_blocks else 0.0)
+    qx, qy = rp[:, 0] / g.w_point[0], rp[:, 1] / g.w_point[1]
+    pb = ((qx * qx > chi2) | (qy * qy > chi2)).astype(np.uint8)
+    tb = (np.abs(rt / g.w_text) > g.chi2_text).any(1).astype(np.uint8)
+    bad = np.bincount(t_obj, weights=tb, minlength=len(sizes))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ob = np.where(sizes > 0, bad / sizes.astype(np.float64) > g.text_ratio, False).astype(np.uint8)
+    return pb, tb, ob, (int(pb.sum()), int(tb.sum()), int(ob.sum()))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_gate_matches_vectorised(oracle, seed):
+    fr, n_p, n_t, t_obj, sizes = random_gate_case(seed)
+    for g in (T.gate_options(), T.gate_options(chi2_text=0.95, chi2_mono=5.991, w_point=(1.0, 1.0), w_text=1.0, text_ratio=0.3),
+              T.gate_options(relax_below_text_blocks=10 ** 6)):
+        got = oracle.gate_residuals(fr, n_p, n_t, g, t_obj, sizes)
+        want = numpy_gate(fr, n_p, n_t, t_obj, sizes, g)
+        for a, b in zip(got[:3], want[:3]):
+            assert np.array_equal(a, b)
+        assert got[3] == want[3]
+
+
+def test_oracle_gate_hand_cases(oracle):
+    w = 1.0 / 1.2
+    g = T.gate_options()                       # chi2 12.25 (+4 because there are < 50 text blocks), |r/w_T| > 0.5, ratio 0.99
+    lim = np.sqrt(16.25) * w
+    fr = np.array([lim * 0.999, 0.0, 0.0, -lim * 1.001, 0.0, 0.0], dtype=np.float64)
+    pb, _, _, cnt = oracle.gate_residuals(fr, 3, 0, g)
+    assert pb.tolist() == [0, 1, 0] and cnt == (1, 0, 0)
+    g2 = T.gate_options(relax_below_text_blocks=0)   # no relaxation: 12.25
+    lim2 = 3.5 * w
+    fr = np.array([lim2 * 1.0001, 0.0, lim2 * 0.9999, 0.0])
+    assert oracle.gate_residuals(fr, 2, 0, g2)[0].tolist() == [1, 0]
+    # 100 blocks in one object: 99 bad -> ratio 0.99 is NOT > 0.99; 100 bad -> object dropped. One pixel over the limit flags a block.
+    for n_bad, want in ((99, 0), (100, 1)):
+        rt = np.zeros((100, 8)); rt[:n_bad, 3] = 0.5 * 5.0 * 1.01
+        fr = rt.ravel()
+        _, tb, ob, cnt = oracle.gate_residuals(fr, 0, 100, g, np.zeros(100, np.int32), np.array([100], np.int32))
+        assert int(tb.sum()) == n_bad and ob.tolist() == [want] and cnt == (0, n_bad, want)
+    # an object of size 0 is never touched; inconsistent bookkeeping trips the reference's assert
+    _, _, ob, _ = oracle.gate_residuals(np.zeros(16), 0, 2, g, np.array([1, 1], np.int32), np.array([0, 2], np.int32))
+    assert ob.tolist() == [0, 0]
+    with pytest.raises(ValueError):
+        oracle.gate_residuals(np.zeros(8), 0, 1, g, np.array([0], np.int32), np.array([0], np.int32))   # FeatNum_tmp > vSizeEachObj
+
+
+def test_gate_options_layout_matches_c(tmp_path):
+    import ctypes as C
+    from textslam_b200._abi import GateOptionsC
+    src = tmp_path / "g.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tslam_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",sizeof(tslam_gate_options),'
+                   'offsetof(tslam_gate_options,w_point),offsetof(tslam_gate_options,relax_below_text_blocks),offsetof(tslam_gate_options,relax_amount),'
+                   'offsetof(tslam_gate_options,text_ratio));return 0;}')
+    exe = tmp_path / "g"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(GateOptionsC), GateOptionsC.w_point.offset, GateOptionsC.relax_below_text_blocks.offset, GateOptionsC.relax_amount.offset,
+            GateOptionsC.text_ratio.offset]
+    assert got == want
+
+
+def oracle_solve_gated(oracle):
+    def f(prob, gate, t_obj, obj_size, max_iters):
+        summ, fr, tr = oracle.solve(prob, max_iters, want_trace=False)
+        pb, tb, ob, cnt = oracle.gate_residuals(fr, prob.n_pobs, prob.n_tobs, gate, t_obj, obj_size)
+        return summ, fr, tr, pb, tb, ob, cnt
+    return f
+
+
+def pose_levels(seed, n_pobs=300, n_planes=4, levels=(2, 1, 0)):
+    """Three PyrPoseOptim inputs: the same 2-D point observations at every level (SceneUse0Pyr, src/optimizer.cc:1072), text
+    blocks of `n_planes` objects x 25 features rendered at each pyramid level."""
+    out = []
+    for lv in levels:
+        p = synth.c3_pose_only(seed=seed, level=lv, n_pobs=n_pobs, n_planes=n_planes)
+        feats = np.tile(np.arange(25), n_planes)
+        out.append(PyramidLevel(p, t_obj=p.t_plane.copy(), t_feat=feats))
+    for l in out[1:]:
+        assert np.array_equal(l.prob.p_uv, out[0].prob.p_uv)
+    return out
+
+
+def test_pyramid_loop_bookkeeping(oracle):
+    levels = pose_levels(seed=11)
+    n_p, n_obj = levels[0].prob.n_pobs, 4
+    pts_good = np.ones(n_p, bool); texts_good = np.ones(n_obj, bool); feats_good = np.ones((n_obj, 25), bool)
+    res = run_pyramid(oracle_solve_gated(oracle), levels, (12.25,) * 3, (0.5, 0.5, 0.95), (10,) * 3, pts_good, texts_good, feats_good)
+    assert len(res) == 3
+    # blocks removed by a level never come back, and every level assembles exactly the blocks that are still good
+    assert res[0]["n_point_blocks"] == n_p and res[1]["n_point_blocks"] == n_p - res[0]["bad"][0]
+    assert res[2]["n_point_blocks"] == res[1]["n_point_blocks"] - res[1]["bad"][0] == int(pts_good.sum()) + res[2]["bad"][0]
+    assert res[1]["n_text_blocks"] <= res[0]["n_text_blocks"] == 100
+    # the generator plants 5 % gross outliers (+-20 px): the gates must have removed most of them and few inliers
+    assert 0.03 * n_p <= n_p - pts_good.sum() <= 0.12 * n_p
+    # the pose estimate is carried from level to level and written back to every level's problem
+    gt = levels[0].prob.gt[0][0]
+    est = levels[0].prob.cams[0]
+    assert np.abs(est - gt).max() < 5e-3
+    assert all(np.array_equal(l.prob.cams, levels[0].prob.cams) for l in levels)
+    # rapid mode: gates off, flags untouched
+    levels = pose_levels(seed=11)
+    pg = np.ones(n_p, bool); tg = np.ones(n_obj, bool); fg = np.ones((n_obj, 25), bool)
+    res = run_pyramid(oracle_solve_gated(oracle), levels, (12.25,) * 3, (0.5, 0.5, 0.95), (10,) * 3, pg, tg, fg, rapid=True)
+    assert pg.all() and tg.all() and fg.all() and all(r["bad"] == (0, 0, 0) for r in res)

@@ -148,6 +148,19 @@ class BAProblem:
     def params(self):
         return self.cams.copy(), self.rho.copy(), self.theta.copy()
 
+    def subset(self, sel_p=None, sel_t=None):
+        """The same problem restricted to the selected residual blocks (boolean masks, insertion order kept) — what the
+        reference's `if(!vPtsGood[..]) continue;` / `if(!vTextFeatsGood[..][..]) continue;` filters do while the ceres::Problem
+        is assembled (src/optimizer.cc:1128-1130, 1168-1169, 1188-1189). Parameter blocks and images are shared by value."""
+        sp = np.ones(self.n_pobs, bool) if sel_p is None else np.asarray(sel_p, bool)
+        st = np.ones(self.n_tobs, bool) if sel_t is None else np.asarray(sel_t, bool)
+        assert sp.shape == (self.n_pobs,) and st.shape == (self.n_tobs,)
+        return BAProblem(self.cams, self.cam_fixed, self.rho, self.rho_fixed, self.theta, self.theta_fixed,
+                         self.p_uv[sp], self.p_ray[sp], self.p_cam[sp], self.p_host[sp], self.p_lm[sp],
+                         self.K_point, self.w_point, self.huber_point,
+                         self.t_rays[st], self.t_iref[st], self.t_musigma[st], self.t_cam[st], self.t_host[st], self.t_plane[st],
+                         self.t_img[st], self.imgs, self.K_text, self.w_text, self.huber_text)
+
     def set_params(self, cams, rho, theta):
         self.cams[...] = cams
         self.rho[...] = rho
@@ -193,3 +206,23 @@ def solve_options(max_iters=10, text_jac_mode=JAC_ANALYTIC, n_threads=1, dense_f
     o.function_tolerance, o.gradient_tolerance = function_tolerance, gradient_tolerance
     o.parameter_tolerance, o.initial_radius = parameter_tolerance, initial_radius
     return o
+
+
+class GateOptionsC(C.Structure):
+    """tslam_gate_options (include/tslam_b200.h)."""
+    _fields_ = [
+        ("gate_points", C.c_int32), ("gate_text", C.c_int32), ("w_point", C.c_double * 2), ("chi2_mono", C.c_double),
+        ("relax_below_text_blocks", C.c_int32), ("relax_amount", C.c_double), ("w_text", C.c_double), ("chi2_text", C.c_double),
+        ("text_ratio", C.c_double),
+    ]
+
+
+def gate_options(w_point=(1.0 / 1.2, 1.0 / 1.2), chi2_mono=12.25, w_text=1.0 / 0.2, chi2_text=0.5, text_ratio=0.99,
+                 relax_below_text_blocks=50, relax_amount=4.0, gate_points=True, gate_text=True):
+    """Defaults = the constants of PyrPoseOptim / PyrBA (src/optimizer.cc:175-176, 1082-1087, 1240-1241)."""
+    g = GateOptionsC()
+    g.gate_points, g.gate_text = int(gate_points), int(gate_text)
+    g.w_point = (C.c_double * 2)(*[float(v) for v in w_point])
+    g.chi2_mono, g.relax_below_text_blocks, g.relax_amount = float(chi2_mono), int(relax_below_text_blocks), float(relax_amount)
+    g.w_text, g.chi2_text, g.text_ratio = float(w_text), float(chi2_text), float(text_ratio)
+    return g

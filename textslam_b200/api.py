@@ -8,8 +8,8 @@ import ctypes as C
 import numpy as np
 from ._lib import lib, check, TslamError  # noqa: F401
 from ._abi import (BAProblem, SolveSummaryC, KeyPointC, KP_DTYPE, PT_NCOLS, TX_NCOLS, TRACE_COLS, solve_options,
-                   c_dp, c_bp, PT_BA, PT_BA_NW, PT_POSE, PT_RHO, TX_BA, TX_POSE, TX_THETA, JAC_ANALYTIC,
-                   JAC_CENTRAL_DIFF)
+                   c_dp, c_bp, c_ip, PT_BA, PT_BA_NW, PT_POSE, PT_RHO, TX_BA, TX_POSE, TX_THETA, JAC_ANALYTIC,
+                   JAC_CENTRAL_DIFF, GateOptionsC, gate_options)
 
 
 def _dp(a):
@@ -64,15 +64,54 @@ class Context:
         return r, J
 
     # ---- solve ---------------------------------------------------------------------------------
-    def solve(self, prob, max_iters=10, text_jac_mode=JAC_ANALYTIC, want_trace=True, **kw):
-        """ceres::Solve + Problem::Evaluate replacement; updates `prob` parameters in place."""
+    def solve(self, prob, max_iters=10, text_jac_mode=JAC_ANALYTIC, want_trace=True, final_residuals=None, **kw):
+        """ceres::Solve + Problem::Evaluate replacement; updates `prob` parameters in place.
+        `final_residuals`: optional caller-owned float64 buffer of 2*n_pobs + 8*n_tobs (e.g. page-locked) to receive the residuals."""
         opt = solve_options(max_iters, text_jac_mode, **kw)
         summ = SolveSummaryC()
-        fr = np.zeros(2 * prob.n_pobs + 8 * prob.n_tobs)
+        nfr = 2 * prob.n_pobs + 8 * prob.n_tobs
+        if final_residuals is not None:
+            fr = final_residuals
+            assert fr.dtype == np.float64 and fr.size == nfr and fr.flags.c_contiguous
+        else:
+            fr = np.zeros(nfr)
         tr = np.full((max_iters + 1, TRACE_COLS), np.nan)
         pc = prob.as_c()
         check(lib().tslam_solve(self._h, C.byref(pc), C.byref(opt), C.byref(summ), _dp(fr), _dp(tr) if want_trace else None))
         return summ.as_dict(), fr, tr
+
+    # ---- chi^2 gates (src/optimizer.cc:1236-1302, 1616-1684) ------------------------------------
+    @staticmethod
+    def _gate_buffers(n_pobs, n_tobs, t_obj, obj_size):
+        t_obj = np.ascontiguousarray(t_obj if t_obj is not None else np.zeros(n_tobs), dtype=np.int32)
+        obj_size = np.ascontiguousarray(obj_size if obj_size is not None else [], dtype=np.int32)
+        assert len(t_obj) == n_tobs
+        return t_obj, obj_size, np.zeros(n_pobs, np.uint8), np.zeros(n_tobs, np.uint8), np.zeros(len(obj_size), np.uint8), (C.c_int32 * 3)()
+
+    def gate_residuals(self, final_residuals, n_pobs, n_tobs, gate, t_obj=None, obj_size=None):
+        """Outlier flags from the final residual vector. Returns (pt_bad, tf_bad, obj_bad, (nBadS, nBadFeat, nBadT))."""
+        fr = np.ascontiguousarray(final_residuals, dtype=np.float64)
+        assert fr.size == 2 * n_pobs + 8 * n_tobs
+        t_obj, obj_size, pb, tb, ob, cnt = self._gate_buffers(n_pobs, n_tobs, t_obj, obj_size)
+        check(lib().tslam_gate_residuals(self._h, _dp(fr), C.c_int(n_pobs), C.c_int(n_tobs), t_obj.ctypes.data_as(c_ip),
+                                         obj_size.ctypes.data_as(c_ip), C.c_int(len(obj_size)), C.byref(gate),
+                                         pb.ctypes.data_as(c_bp), tb.ctypes.data_as(c_bp), ob.ctypes.data_as(c_bp), cnt))
+        return pb, tb, ob, tuple(cnt)
+
+    def solve_gated(self, prob, gate, t_obj=None, obj_size=None, max_iters=10, text_jac_mode=JAC_ANALYTIC, want_trace=True, **kw):
+        """One pyramid level of PoseOptim / LocalBundleAdjustment: ceres::Solve + Problem::Evaluate + the chi^2 loops in one call.
+        Returns (summary, final_residuals, trace, pt_bad, tf_bad, obj_bad, counts)."""
+        opt = solve_options(max_iters, text_jac_mode, **kw)
+        summ = SolveSummaryC()
+        fr = np.zeros(2 * prob.n_pobs + 8 * prob.n_tobs)
+        tr = np.full((max_iters + 1, TRACE_COLS), np.nan)
+        t_obj, obj_size, pb, tb, ob, cnt = self._gate_buffers(prob.n_pobs, prob.n_tobs, t_obj, obj_size)
+        pc = prob.as_c()
+        check(lib().tslam_solve_gated(self._h, C.byref(pc), C.byref(opt), C.byref(gate), t_obj.ctypes.data_as(c_ip),
+                                      obj_size.ctypes.data_as(c_ip), C.c_int(len(obj_size)), C.byref(summ), _dp(fr),
+                                      _dp(tr) if want_trace else None, pb.ctypes.data_as(c_bp), tb.ctypes.data_as(c_bp),
+                                      ob.ctypes.data_as(c_bp), cnt))
+        return summ.as_dict(), fr, tr, pb, tb, ob, tuple(cnt)
 
     def theta_covariance(self, prob, jac_mode=JAC_ANALYTIC):
         """ceres::Covariance of every theta block (src/optimizer.cc:2219-2238). Returns (cov (n_planes,3,3), n_singular)."""
@@ -143,17 +182,81 @@ class DeviceProblem:
         return cams, rho, theta
 
 
+class PyramidLevel:
+    """The candidate residual blocks of ONE PyrPoseOptim / PyrBA invocation (one pyramid level), before the Good-flag filter,
+    with the reference's index maps back to the observation-quality vectors:
+    p_raw[i]  -> entry of vObvGoodPts the point block i clears (vIdx2vPtsGood, src/optimizer.cc:1145, 1433);
+    t_obj[j]  -> text object of block j (vIdx2vTextsGood :1201);  t_feat[j] -> its feature index (vIdx2vTextFeatsGood :1202)."""
+
+    def __init__(self, prob, p_raw=None, t_obj=None, t_feat=None):
+        self.prob = prob
+        self.p_raw = np.arange(prob.n_pobs) if p_raw is None else np.asarray(p_raw, np.int64)
+        self.t_obj = np.zeros(prob.n_tobs, np.int64) if t_obj is None else np.asarray(t_obj, np.int64)
+        self.t_feat = np.arange(prob.n_tobs) if t_feat is None else np.asarray(t_feat, np.int64)
+        assert len(self.p_raw) == prob.n_pobs and len(self.t_obj) == prob.n_tobs and len(self.t_feat) == prob.n_tobs
+
+
+def run_pyramid(solve_gated, levels, chi2_mono, chi2_text, its, pts_good, texts_good, feats_good, rapid=False, on_level=None):
+    """The level loop of optimizer::PoseOptim (src/optimizer.cc:172-186) / LocalBundleAdjustment (:282-289): per level, assemble
+    the problem from the blocks whose Good flags are still set, solve, evaluate, gate, clear flags, carry the parameters on.
+    `solve_gated(prob, gate, t_obj, obj_size, max_iters)` -> (summary, final_residuals, trace, pt_bad, tf_bad, obj_bad, counts) is
+    Context.solve_gated for the product; the parity tests pass the CPU oracle's equivalent. Flags are modified in place.
+    rapid (bFlag_rapid): gates off (src/optimizer.cc:1077-1080, 1343-1346). Returns the per-level summaries."""
+    carried, out = None, []
+    for li, lvl in enumerate(levels):
+        sel_p = pts_good[lvl.p_raw]
+        sel_t = texts_good[lvl.t_obj] & feats_good[lvl.t_obj, lvl.t_feat] if lvl.prob.n_tobs else np.zeros(0, bool)
+        sub = lvl.prob.subset(sel_p, sel_t)
+        if carried is not None:
+            sub.set_params(*carried)
+        if on_level is not None:
+            on_level(li, sub)   # e.g. refresh mu / sigma with text_info() at the carried pose (src/optimizer.cc:1179-1184)
+        t_obj = lvl.t_obj[sel_t]
+        obj_size = np.bincount(t_obj, minlength=len(texts_good)).astype(np.int32)   # vSizeEachObj
+        gate = gate_options(w_point=sub.w_point, chi2_mono=chi2_mono[li], w_text=sub.w_text, chi2_text=chi2_text[li],
+                            gate_points=not rapid, gate_text=not rapid)
+        summ, fr, _, pb, tb, ob, cnt = solve_gated(sub, gate, t_obj, obj_size, its[li])
+        if not rapid:
+            pts_good[lvl.p_raw[sel_p][pb == 1]] = False
+            feats_good[t_obj[tb == 1], lvl.t_feat[sel_t][tb == 1]] = False
+            texts_good[np.nonzero(ob == 1)[0]] = False
+        carried = sub.params()
+        out.append({"summary": summ, "n_point_blocks": sub.n_pobs, "n_text_blocks": sub.n_tobs, "bad": cnt, "final_residuals": fr})
+    if carried is not None:
+        for lvl in levels:
+            lvl.prob.set_params(*carried)
+    return out
+
+
 class Optimizer:
     """Mirror of TextSLAM::optimizer's solve entry points (src/optimizer.h:57-70) on flattened problems.
-    Iteration counts are the reference's: 10 (pose, local BA; src/optimizer.cc:180,286), 20 (global BA, :413)."""
+    Iteration counts are the reference's: 10 (pose, local BA; src/optimizer.cc:180,286), 20 (global BA, :413).
+    PoseOptim / LocalBundleAdjustment accept either one flattened problem (a single ceres::Solve) or the list of
+    PyramidLevel inputs of the reference's coarse-to-fine loop together with the Good-flag arrays it maintains."""
+    CHI2_MONO = (12.25, 12.25, 12.25, 12.25)   # src/optimizer.cc:175, 285
+    CHI2_TEXT = (0.5, 0.5, 0.5, 0.95)          # :176, 286
 
-    def __init__(self, ctx, text_jac_mode=JAC_ANALYTIC):
-        self.ctx, self.text_jac_mode = ctx, text_jac_mode
+    def __init__(self, ctx, text_jac_mode=JAC_ANALYTIC, rapid=False):
+        self.ctx, self.text_jac_mode, self.rapid = ctx, text_jac_mode, rapid
 
-    def PoseOptim(self, prob, its=10):
+    def _solve_gated(self, prob, gate, t_obj, obj_size, max_iters):
+        return self.ctx.solve_gated(prob, gate, t_obj, obj_size, max_iters, self.text_jac_mode, want_trace=False)
+
+    def _pyramid(self, levels, pts_good, texts_good, feats_good, its, on_level):
+        # the reference runs pyramid levels 2, 1, 0 (and 3 first when bFlag_rapid): the last len(levels) table entries
+        n = len(levels)
+        assert 1 <= n <= 4
+        return run_pyramid(self._solve_gated, levels, self.CHI2_MONO[4 - n:], self.CHI2_TEXT[4 - n:], [its] * n,
+                           pts_good, texts_good, feats_good, rapid=self.rapid, on_level=on_level)
+
+    def PoseOptim(self, prob, its=10, pts_good=None, texts_good=None, feats_good=None, on_level=None):
+        if isinstance(prob, (list, tuple)):
+            return self._pyramid(prob, pts_good, texts_good, feats_good, its, on_level)
         return self.ctx.solve(prob, its, self.text_jac_mode)
 
-    def LocalBundleAdjustment(self, prob, its=10):
+    def LocalBundleAdjustment(self, prob, its=10, pts_good=None, texts_good=None, feats_good=None, on_level=None):
+        if isinstance(prob, (list, tuple)):
+            return self._pyramid(prob, pts_good, texts_good, feats_good, its, on_level)
         return self.ctx.solve(prob, its, self.text_jac_mode)
 
     def GlobalBA(self, prob, its=20):

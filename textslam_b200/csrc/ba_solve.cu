@@ -1170,8 +1170,18 @@ static int get_solver(tslam_ctx* ctx, tslam_dev_problem* d, Solver** out) {
 
 using namespace tsl;
 
-extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, tslam_solve_summary* summary,
-                           double* final_residuals, double* trace) {
+namespace tsl {
+int gate_device(tslam_ctx* ctx, const double* d_rp, const double* d_rt, int n_pobs, int n_tobs, const int32_t* t_obj,
+                const int32_t* obj_size, int n_obj, const tslam_gate_options* g, uint8_t* pt_bad, uint8_t* tf_bad, uint8_t* obj_bad,
+                int32_t* counts_out);   // gate.cu
+struct GateArgs {
+  const tslam_gate_options* opt; const int32_t* t_obj; const int32_t* obj_size; int n_obj;
+  uint8_t *pt_bad, *tf_bad, *obj_bad; int32_t* counts;
+};
+}  // namespace tsl
+
+static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, tslam_solve_summary* summary,
+                      double* final_residuals, double* trace, const GateArgs* gate) {
   if (!ctx || !p || !opt) return set_error(TSLAM_ERR_ARG, "null argument");
   if (opt->max_iters < 0) return set_error(TSLAM_ERR_ARG, "max_iters < 0");
   auto T0 = std::chrono::steady_clock::now();
@@ -1211,22 +1221,28 @@ extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solv
     if (d.n_points) TSL_CUDA(cudaMemcpyAsync(p->rho, d.rho.p, sizeof(double) * d.n_points, cudaMemcpyDeviceToHost, st));
     if (d.n_planes) TSL_CUDA(cudaMemcpyAsync(p->theta, d.theta.p, sizeof(double) * 3 * (size_t)d.n_planes, cudaMemcpyDeviceToHost, st));
   }
-  if (final_residuals) {
+  DevBuf<double> fr;   // world > 1: the global residual vector, replicated after the all-reduce
+  if (final_residuals || gate) {
     // Problem::Evaluate: loss-corrected residuals of every block, insertion order (Appendix A.6)
     if ((rc = eval_at(*S, d.cams.p, d.rho.p, d.theta.p, false, opt->text_jac_mode, SC_CAND, S->cr_p.p, S->cr_t.p))) return rc;
     const size_t total = 2 * (size_t)d.g_pobs + 8 * (size_t)d.g_tobs;
     if (ctx->world > 1) {
-      DevBuf<double> fr;
       TSL_CUDA(fr.reserve(total));
       TSL_CUDA(cudaMemsetAsync(fr.p, 0, total * sizeof(double), st));
       if (S->lp) LAUNCH(scatter_rows_kernel<<<(2 * S->lp + 255) / 256, 256, 0, st>>>(S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p));
       if (S->lt) LAUNCH(scatter_rows_kernel<<<(8 * S->lt + 255) / 256, 256, 0, st>>>(S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs));
       if ((rc = comm_allreduce_sum(ctx, fr.p, total))) return rc;
-      TSL_CUDA(cudaMemcpyAsync(final_residuals, fr.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (final_residuals) TSL_CUDA(cudaMemcpyAsync(final_residuals, fr.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
       TSL_CUDA(cudaStreamSynchronize(st));
-    } else {
+    } else if (final_residuals) {
       if (S->lp) TSL_CUDA(cudaMemcpyAsync(final_residuals, S->cr_p.p, 2 * (size_t)S->lp * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (S->lt) TSL_CUDA(cudaMemcpyAsync(final_residuals + 2 * (size_t)d.g_pobs, S->cr_t.p, 8 * (size_t)S->lt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (gate) {   // chi^2 gates on the residuals where they are (src/optimizer.cc:1236-1302, 1616-1684)
+      const double* rp = ctx->world > 1 ? fr.p : S->cr_p.p;
+      const double* rt = ctx->world > 1 ? fr.p + 2 * (size_t)d.g_pobs : S->cr_t.p;
+      if ((rc = gate_device(ctx, rp, rt, d.g_pobs, d.g_tobs, gate->t_obj, gate->obj_size, gate->n_obj, gate->opt, gate->pt_bad, gate->tf_bad,
+                            gate->obj_bad, gate->counts))) return rc;
     }
   }
   TSL_CUDA(cudaStreamSynchronize(st));
@@ -1239,6 +1255,21 @@ extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solv
   sum.total_ms = std::chrono::duration<double, std::milli>(T2 - T0).count();
   if (summary) *summary = sum;
   return TSLAM_OK;
+}
+
+extern "C" int tslam_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, tslam_solve_summary* summary,
+                           double* final_residuals, double* trace) {
+  return solve_impl(ctx, p, opt, summary, final_residuals, trace, nullptr);
+}
+
+extern "C" int tslam_solve_gated(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, const tslam_gate_options* gate,
+                                 const int32_t* t_obj, const int32_t* obj_size, int n_obj, tslam_solve_summary* summary,
+                                 double* final_residuals, double* trace, uint8_t* pt_bad, uint8_t* tf_bad, uint8_t* obj_bad,
+                                 int32_t counts_out[3]) {
+  if (!gate) return set_error(TSLAM_ERR_ARG, "gate options missing");
+  if (counts_out) counts_out[0] = counts_out[1] = counts_out[2] = 0;
+  GateArgs g{gate, t_obj, obj_size, n_obj, pt_bad, tf_bad, obj_bad, counts_out};
+  return solve_impl(ctx, p, opt, summary, final_residuals, trace, &g);
 }
 
 extern "C" int tslam_dev_lm_iterations(tslam_ctx* ctx, tslam_dev_problem* d, const tslam_solve_options* opt, int iters, float* phase_ms,
