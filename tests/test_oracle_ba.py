@@ -114,3 +114,29 @@ def test_huber_corrected_final_residuals(oracle):
     a = prob.huber_point
     scale = np.where(sn <= a * a, 1.0, np.sqrt(a / np.sqrt(np.maximum(sn, 1e-300))))
     assert np.allclose(fr[: 2 * prob.n_pobs].reshape(-1, 2), r * scale[:, None], rtol=1e-12, atol=1e-14)
+
+
+def test_init_ba_functor_is_ba_nw_with_identity_host(oracle):
+    """auto_IniBAScene (include/auto_IniBAScene.h:28-60) = rotate ray/rho by the second frame's pose, project, unweighted.
+    With the host camera held at identity the auto_BASceneNW path must give the same residuals, so InitBA needs no extra kernel."""
+    rng = np.random.default_rng(5)
+    n = 200
+    q = rng.normal(size=4); q /= np.linalg.norm(q) * 0.9     # deliberately not unit: QuaternionRotatePoint normalises
+    q = np.array([1.0, 0.02, -0.03, 0.01]) * 1.1
+    t = np.array([0.2, -0.1, 0.05])
+    cams = np.stack([np.array([1.0, 0, 0, 0, 0, 0, 0]), np.concatenate([q, t])])
+    ray = rng.uniform(-0.5, 0.5, (n, 2)); rho = rng.uniform(0.1, 1.0, n); uv = rng.uniform(0, 480, (n, 2))
+    from textslam_b200 import BAProblem
+    prob = BAProblem(cams, [1, 0], rho, None, None, None, uv, ray, np.ones(n, np.int32), np.zeros(n, np.int32), np.arange(n, dtype=np.int32),
+                     w_point=(1.0, 1.0))
+    r, _ = oracle.eval_points(prob, PT_BA_NW)
+    fx, fy, cx, cy = prob.K_point
+    un = q / np.linalg.norm(q)
+    w, x, y, z = un
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    p = np.concatenate([ray, np.ones((n, 1))], 1) / rho[:, None]
+    qp = p @ R.T + t
+    want = np.stack([fx * qp[:, 0] / qp[:, 2] + cx - uv[:, 0], fy * qp[:, 1] / qp[:, 2] + cy - uv[:, 1]], 1)
+    assert np.allclose(r, want, rtol=1e-12, atol=1e-9)
