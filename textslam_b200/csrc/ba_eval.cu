@@ -32,6 +32,7 @@ struct PointArgs {
 // COL0 = first tangent column exported, NCOLS = number of columns (13: BA, 6: pose, 1 @12: rho)
 template <int COL0, int NCOLS, bool WANT_J, bool ROBUST, int MINB = 6>
 __global__ void __launch_bounds__(kEvalThreads, MINB) point_eval_kernel(PointArgs a, double2* __restrict__ r_out, double* __restrict__ J_out) {
+  PDL_PROLOGUE();
   constexpr int ROW = 2 * NCOLS;
   constexpr int STRIDE = (ROW % 2 == 0) ? ROW + 1 : ROW;  // odd stride in doubles: conflict-free 64-bit smem access
   __shared__ double sJ[WANT_J ? kEvalThreads * STRIDE : 1];
@@ -112,6 +113,7 @@ struct TextArgs {
 // One lane per pattern pixel: 4 text blocks per warp, 16 per CTA.
 template <int COL0, int NCOLS, int MODE, bool WANT_J, bool ROBUST>
 __global__ void __launch_bounds__(kEvalThreads) text_eval_kernel(TextArgs a, double* __restrict__ r_out, double* __restrict__ J_out) {
+  PDL_PROLOGUE();
   constexpr int STRIDE = (NCOLS % 2 == 0) ? NCOLS + 1 : NCOLS;
   __shared__ double sJ[WANT_J ? kEvalThreads * STRIDE : 1];
   __shared__ double sred[ROBUST ? 2 * (kEvalThreads / 32) : 1];
@@ -224,24 +226,24 @@ int launch_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, bool want
   PointArgs a = make_point_args(d, kind == TSLAM_PT_BA_NW || kind == TSLAM_PT_RHO);
   const int grid = (d->n_pobs + kEvalThreads - 1) / kEvalThreads;
   double2* r = reinterpret_cast<double2*>(d->pr.p);
-  if (!want_J) LAUNCH(point_eval_kernel<0, 13, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr));
+  if (!want_J) LAUNCH(launch_k(point_eval_kernel<0, 13, false, false>, grid, kEvalThreads, 0, ctx->stream, a, r, nullptr));
   else if (ncols == 13) {
     // occupancy variant: 8 CTAs/SM (64 registers, ~48 B of L1-resident spills) vs 6 CTAs/SM (79 registers)
     static const bool occ8 = getenv("TSLAM_EVAL_OCC8") != nullptr;   // measured: 8 CTAs/SM is slower (0.67 vs 0.81 of HBM peak, profiles/r1_notes.md)
-    if (occ8) LAUNCH(point_eval_kernel<0, 13, true, false, 8><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
-    else LAUNCH(point_eval_kernel<0, 13, true, false, 6><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+    if (occ8) LAUNCH(launch_k(point_eval_kernel<0, 13, true, false, 8>, grid, kEvalThreads, 0, ctx->stream, a, r, d->pJ.p));
+    else LAUNCH(launch_k(point_eval_kernel<0, 13, true, false, 6>, grid, kEvalThreads, 0, ctx->stream, a, r, d->pJ.p));
   }
-  else if (ncols == 6) LAUNCH(point_eval_kernel<0, 6, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
-  else LAUNCH(point_eval_kernel<12, 1, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, d->pJ.p));
+  else if (ncols == 6) LAUNCH(launch_k(point_eval_kernel<0, 6, true, false>, grid, kEvalThreads, 0, ctx->stream, a, r, d->pJ.p));
+  else LAUNCH(launch_k(point_eval_kernel<12, 1, true, false>, grid, kEvalThreads, 0, ctx->stream, a, r, d->pJ.p));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
 
 template <int MODE>
 static void launch_text_mode(tslam_ctx* ctx, tslam_dev_problem* d, int kind, const TextArgs& a, int grid) {
-  if (kind == TSLAM_TX_BA) LAUNCH(text_eval_kernel<0, 15, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p));
-  else if (kind == TSLAM_TX_POSE) LAUNCH(text_eval_kernel<0, 6, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p));
-  else LAUNCH(text_eval_kernel<12, 3, MODE, true, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, d->tJ.p));
+  if (kind == TSLAM_TX_BA) LAUNCH(launch_k(text_eval_kernel<0, 15, MODE, true, false>, grid, kEvalThreads, 0, ctx->stream, a, d->tr.p, d->tJ.p));
+  else if (kind == TSLAM_TX_POSE) LAUNCH(launch_k(text_eval_kernel<0, 6, MODE, true, false>, grid, kEvalThreads, 0, ctx->stream, a, d->tr.p, d->tJ.p));
+  else LAUNCH(launch_k(text_eval_kernel<12, 3, MODE, true, false>, grid, kEvalThreads, 0, ctx->stream, a, d->tr.p, d->tJ.p));
 }
 
 int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, bool want_J) {
@@ -252,7 +254,7 @@ int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mod
   TextArgs a = make_text_args(d, kind == TSLAM_TX_THETA);
   a.free_mask = kind == TSLAM_TX_BA ? 7u : (kind == TSLAM_TX_POSE ? 1u : 4u);
   const int grid = (8 * d->n_tobs + kEvalThreads - 1) / kEvalThreads;
-  if (!want_J) LAUNCH(text_eval_kernel<0, 15, 0, false, false><<<grid, kEvalThreads, 0, ctx->stream>>>(a, d->tr.p, nullptr));
+  if (!want_J) LAUNCH(launch_k(text_eval_kernel<0, 15, 0, false, false>, grid, kEvalThreads, 0, ctx->stream, a, d->tr.p, nullptr));
   else if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) launch_text_mode<TSLAM_JAC_CENTRAL_DIFF>(ctx, d, kind, a, grid);
   else launch_text_mode<TSLAM_JAC_ANALYTIC>(ctx, d, kind, a, grid);
   TSL_CHECK_LAUNCH();
@@ -268,8 +270,8 @@ int launch_eval_points_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double
   a.cams = cams; a.rho = rho; a.huber = d->huber_point; a.active = active; a.cost_part = cost_part;
   const int grid = (d->n_pobs + kEvalThreads - 1) / kEvalThreads;
   *n_parts = grid;
-  if (J) LAUNCH(point_eval_kernel<0, 13, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, reinterpret_cast<double2*>(r), J));
-  else LAUNCH(point_eval_kernel<0, 13, false, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, reinterpret_cast<double2*>(r), nullptr));
+  if (J) LAUNCH(launch_k(point_eval_kernel<0, 13, true, true>, grid, kEvalThreads, 0, ctx->stream, a, reinterpret_cast<double2*>(r), J));
+  else LAUNCH(launch_k(point_eval_kernel<0, 13, false, true>, grid, kEvalThreads, 0, ctx->stream, a, reinterpret_cast<double2*>(r), nullptr));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -281,9 +283,9 @@ int launch_eval_text_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double* 
   a.cams = cams; a.theta = theta; a.huber = d->huber_text; a.active = active; a.cost_part = cost_part; a.free_masks = free_masks;
   const int grid = (8 * d->n_tobs + kEvalThreads - 1) / kEvalThreads;
   *n_parts = grid;
-  if (!J) LAUNCH(text_eval_kernel<0, 15, 0, false, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, nullptr));
-  else if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) LAUNCH(text_eval_kernel<0, 15, TSLAM_JAC_CENTRAL_DIFF, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, J));
-  else LAUNCH(text_eval_kernel<0, 15, TSLAM_JAC_ANALYTIC, true, true><<<grid, kEvalThreads, 0, ctx->stream>>>(a, r, J));
+  if (!J) LAUNCH(launch_k(text_eval_kernel<0, 15, 0, false, true>, grid, kEvalThreads, 0, ctx->stream, a, r, nullptr));
+  else if (jac_mode == TSLAM_JAC_CENTRAL_DIFF) LAUNCH(launch_k(text_eval_kernel<0, 15, TSLAM_JAC_CENTRAL_DIFF, true, true>, grid, kEvalThreads, 0, ctx->stream, a, r, J));
+  else LAUNCH(launch_k(text_eval_kernel<0, 15, TSLAM_JAC_ANALYTIC, true, true>, grid, kEvalThreads, 0, ctx->stream, a, r, J));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }

@@ -41,6 +41,7 @@ enum { MX_GMAX = 0, MX_FAIL = 1, MX_N = 2 };
 
 // deterministic two-level sum: parts[0..n) (stride 1) -> *out (+= if accumulate)
 __global__ void __launch_bounds__(256) sum_parts_kernel(const double* __restrict__ parts, int n, int stride, int offset, double* out, int accumulate) {
+  PDL_PROLOGUE();
   __shared__ double s[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) a += parts[(size_t)i * stride + offset];
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const double* __restrict
 
 // two interleaved series (stride 2) -> two scalars in one launch: CTA b sums parts[2 i + b]; same order as sum_parts_kernel
 __global__ void __launch_bounds__(256) sum_parts_pair_kernel(const double* __restrict__ parts, int n, double* out0, double* out1, int accumulate) {
+  PDL_PROLOGUE();
   __shared__ double s[256];
   double a = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) a += parts[(size_t)i * 2 + blockIdx.x];
@@ -83,6 +85,7 @@ template <int D, int ROWS, int JC>
 __global__ void lm_accum_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
                                 const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
                                 double* __restrict__ g) {
+  PDL_PROLOGUE();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   double Vv[D * D], gv[D];
@@ -124,6 +127,7 @@ template <int D, int ROWS, int JC>
 __global__ void slot_accum_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
                                   const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
                                   const double* __restrict__ scale_l, double* __restrict__ E) {
+  PDL_PROLOGUE();
   const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx >= ns) return;
   double Ev[6 * D];
@@ -162,6 +166,7 @@ template <int D, int ROWS, int JC>
 __global__ void __launch_bounds__(128) lm_accum_warp_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
                                                             const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
                                                             double* __restrict__ g) {
+  PDL_PROLOGUE();
   const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (v >= nv) return;   // warp-uniform
   double Vv[D * D], gv[D];
@@ -208,6 +213,7 @@ template <int D, int ROWS, int JC>
 __global__ void __launch_bounds__(128) slot_accum_warp_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
                                                               const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
                                                               const double* __restrict__ scale_l, double* __restrict__ E) {
+  PDL_PROLOGUE();
   const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (sidx >= ns) return;   // warp-uniform
   double Ev[6 * D];
@@ -243,6 +249,7 @@ __device__ __forceinline__ double lm_damp(double d, double inv_radius) { return 
 // ---- (V + D^2)^-1 for the current trust-region radius ----------------------------------------------
 template <int D>
 __global__ void lm_vinv_kernel(int nv, const double* __restrict__ V, double inv_radius, double* __restrict__ Vinv, double* __restrict__ mx) {
+  PDL_PROLOGUE();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   if (D == 1) {
@@ -280,6 +287,7 @@ __device__ __forceinline__ void code_offsets(int code, int& ox, int& oy) {
 
 __global__ void cam_colnorm_kernel(int nc, const int* __restrict__ diag_blk, BlockLists L, const double* __restrict__ pJ,
                                    const double* __restrict__ tJ, double* __restrict__ out /*6nc*/) {
+  PDL_PROLOGUE();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nc) return;
   const int blk = diag_blk[warp];
@@ -308,18 +316,21 @@ __global__ void cam_colnorm_kernel(int nc, const int* __restrict__ diag_blk, Blo
 }
 
 __global__ void scale_from_norm_kernel(int n, const double* __restrict__ d2, double* __restrict__ scale) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) scale[i] = 1.0 / (1.0 + sqrt(d2[i]));
 }
 // landmark scales from the diagonal of the (unscaled, scale == 1) V
 template <int D>
 __global__ void lm_scale_kernel(int nv, const double* __restrict__ V, double* __restrict__ scale) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nv * D) return;
   const int v = i / D, a = i - v * D;
   scale[i] = 1.0 / (1.0 + sqrt(V[(size_t)v * D * D + a * D + a]));
 }
 __global__ void fill_kernel(double* p, int n, double v) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -342,6 +353,7 @@ struct BlockArgs {
 // sums (36 x log2(G) 64-bit shuffles), which dominated when every block had a whole warp.
 template <int G>
 __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int* __restrict__ list, int nlist) {
+  PDL_PROLOGUE();
   static_assert(G == 8 || G == 32 || G == 128, "group size");
   __shared__ double xs[G == 128 ? 4 * 54 : 1];   // G == 128 (one CTA per block): cross-warp stage of the reduction
   const int gi = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x & (G - 1);
@@ -500,6 +512,7 @@ struct ScatterArgs {
   double* A; int ld; int n; int rows_total; int Rb;
 };
 __global__ void scatter_kernel(ScatterArgs S) {
+  PDL_PROLOGUE();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int nb36 = S.nblk * 36;
   if (t < nb36) {
@@ -522,6 +535,7 @@ template <int D>
 __global__ void backsub_kernel(int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
                                const double* __restrict__ Vinv, const double* __restrict__ g, const double* __restrict__ yc,
                                const double* __restrict__ scale_l, double* __restrict__ delta_l) {
+  PDL_PROLOGUE();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   double t[D];
@@ -549,6 +563,7 @@ __global__ void __launch_bounds__(256) candidate_cams_kernel(int n_cams, const i
                                                              const double* __restrict__ yc, const double* __restrict__ scale_c,
                                                              double* __restrict__ delta_c, double* __restrict__ xc,
                                                              double* __restrict__ sc, double norm_weight) {
+  PDL_PROLOGUE();
   __shared__ double sred[256];
   double step2 = 0.0, cn2 = 0.0;
   for (int k = threadIdx.x; k < n_cams; k += 256) {
@@ -591,6 +606,7 @@ template <int D>
 __global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
                                                            const double* __restrict__ delta_l, double* __restrict__ xc,
                                                            double* __restrict__ parts /*2 per block*/) {
+  PDL_PROLOGUE();
   __shared__ double sred[256];
   const int v = blockIdx.x * 256 + threadIdx.x;
   double step2 = 0.0, cn2 = 0.0;
@@ -612,6 +628,7 @@ __global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __
 
 // squared norm of the free ambient parameters (x_norm at start)
 __global__ void __launch_bounds__(256) xnorm_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, double* out, double w) {
+  PDL_PROLOGUE();
   __shared__ double sred[256];
   double a = 0.0;
   for (int k = threadIdx.x; k < n_cams; k += 256)
@@ -622,6 +639,7 @@ __global__ void __launch_bounds__(256) xnorm_cams_kernel(int n_cams, const int* 
 }
 template <int D>
 __global__ void __launch_bounds__(256) xnorm_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x, double* parts) {
+  PDL_PROLOGUE();
   __shared__ double sred[256];
   const int v = blockIdx.x * 256 + threadIdx.x;
   double a = 0.0;
@@ -637,6 +655,7 @@ __global__ void __launch_bounds__(256) model_cost_kernel(int n, const int* __res
                                                          const double* __restrict__ J, const double* __restrict__ r,
                                                          const double* __restrict__ delta_c, const double* __restrict__ delta_l,
                                                          double* __restrict__ parts) {
+  PDL_PROLOGUE();
   __shared__ double sred[256];
   const int i = blockIdx.x * 256 + threadIdx.x;
   double acc = 0.0;
@@ -668,6 +687,7 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 }
 __global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, const double* __restrict__ graw,
                                  double* __restrict__ mx) {
+  PDL_PROLOGUE();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_cams) return;
   const int s = camslot[k];
@@ -690,6 +710,7 @@ __global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, co
   atomic_max_nonneg(mx + MX_GMAX, m);
 }
 __global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   // max over the bit patterns (what the atomic does; keeps a NaN visible), one atomic per warp instead of per landmark
   unsigned long long m = i < n ? (unsigned long long)__double_as_longlong(fabs(g_scaled[i] / scale[i])) : 0ull;
@@ -699,10 +720,12 @@ __global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const
 }
 
 __global__ void copy_fail_kernel(const int* fail, double* mx) {
+  PDL_PROLOGUE();
   if (*fail) atomic_max_nonneg(mx + MX_FAIL, 1.0);
 }
 // final residual scatter into the global residual vector (multi-GPU: other ranks' entries stay 0)
 __global__ void scatter_rows_kernel(int n, int width, const int* __restrict__ gsel, const double* __restrict__ src, double* __restrict__ dst) {
+  PDL_PROLOGUE();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * width) return;
   const int i = t / width, k = t - i * width;
@@ -710,6 +733,7 @@ __global__ void scatter_rows_kernel(int n, int width, const int* __restrict__ gs
 }
 template <int D>
 __global__ void export_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x, double* __restrict__ out) {
+  PDL_PROLOGUE();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nv * D) return;
   const int v = t / D, a = t - v * D;
@@ -874,7 +898,7 @@ static int eval_at(Solver& S, const double* cams, const double* rho, const doubl
   if (rc) return rc;
   rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? S.tJ.p : nullptr, parts + 2 * np, &nt);
   if (rc) return rc;
-  LAUNCH(sum_parts_pair_kernel<<<2, 256, 0, ctx->stream>>>(parts, np + nt, S.sc + cost_slot, S.sc + cost_slot + 1, 0));
+  LAUNCH(launch_k(sum_parts_pair_kernel, 2, 256, 0, ctx->stream, parts, np + nt, S.sc + cost_slot, S.sc + cost_slot + 1, 0));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -890,12 +914,12 @@ static BlockLists block_lists(Solver& S) {
 static int accumulate_landmarks(Solver& S) {
   cudaStream_t st = S.ctx->stream;
   if (S.nvp) {
-    LAUNCH(lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
-    if (S.nsp) LAUNCH(slot_accum_kernel<1, 2, 13><<<grid_for(S.nsp, 128), 128, 0, st>>>(S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p));
+    LAUNCH(launch_k(lm_accum_kernel<1, 2, 13>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
+    if (S.nsp) LAUNCH(launch_k(slot_accum_kernel<1, 2, 13>, grid_for(S.nsp, 128), 128, 0, st, S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p));
   }
   if (S.nvt) {
-    LAUNCH(lm_accum_warp_kernel<3, 8, 15><<<grid_for(S.nvt * 32, 128), 128, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
-    if (S.nst) LAUNCH(slot_accum_warp_kernel<3, 8, 15><<<grid_for(S.nst * 32, 128), 128, 0, st>>>(S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p));
+    LAUNCH(launch_k(lm_accum_warp_kernel<3, 8, 15>, grid_for(S.nvt * 32, 128), 128, 0, st, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    if (S.nst) LAUNCH(launch_k(slot_accum_warp_kernel<3, 8, 15>, grid_for(S.nst * 32, 128), 128, 0, st, S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -906,21 +930,21 @@ static int compute_jacobi_scaling(Solver& S) {
   const int nc = S.nc;
   // unscaled column norms: cameras via the diagonal blocks' direct entries, landmarks via V with scale == 1
   if (nc) {
-    LAUNCH(cam_colnorm_kernel<<<grid_for(nc * 32, 128), 128, 0, st>>>(nc, S.diag_blk.p, block_lists(S), S.pJ.p, S.tJ.p, S.colnorm_c.p));
+    LAUNCH(launch_k(cam_colnorm_kernel, grid_for(nc * 32, 128), 128, 0, st, nc, S.diag_blk.p, block_lists(S), S.pJ.p, S.tJ.p, S.colnorm_c.p));
     TSL_CHECK_LAUNCH();
     int rc = comm_allreduce_sum(S.ctx, S.colnorm_c.p, 6 * (size_t)nc);
     if (rc) return rc;
-    LAUNCH(scale_from_norm_kernel<<<grid_for(6 * nc, 256), 256, 0, st>>>(6 * nc, S.colnorm_c.p, S.scale_c.p));
+    LAUNCH(launch_k(scale_from_norm_kernel, grid_for(6 * nc, 256), 256, 0, st, 6 * nc, S.colnorm_c.p, S.scale_c.p));
   }
   if (S.nvp) {
-    LAUNCH(fill_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.scale_vp.p, S.nvp, 1.0));
-    LAUNCH(lm_accum_kernel<1, 2, 13><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
-    LAUNCH(lm_scale_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, S.scale_vp.p));
+    LAUNCH(launch_k(fill_kernel, grid_for(S.nvp, 256), 256, 0, st, S.scale_vp.p, S.nvp, 1.0));
+    LAUNCH(launch_k(lm_accum_kernel<1, 2, 13>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
+    LAUNCH(launch_k(lm_scale_kernel<1>, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.Vp.p, S.scale_vp.p));
   }
   if (S.nvt) {
-    LAUNCH(fill_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.scale_vt.p, 3 * S.nvt, 1.0));
-    LAUNCH(lm_accum_warp_kernel<3, 8, 15><<<grid_for(S.nvt * 32, 128), 128, 0, st>>>(S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
-    LAUNCH(lm_scale_kernel<3><<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(S.nvt, S.Vt.p, S.scale_vt.p));
+    LAUNCH(launch_k(fill_kernel, grid_for(3 * S.nvt, 256), 256, 0, st, S.scale_vt.p, 3 * S.nvt, 1.0));
+    LAUNCH(launch_k(lm_accum_warp_kernel<3, 8, 15>, grid_for(S.nvt * 32, 128), 128, 0, st, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    LAUNCH(launch_k(lm_scale_kernel<3>, grid_for(3 * S.nvt, 256), 256, 0, st, S.nvt, S.Vt.p, S.scale_vt.p));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -935,8 +959,8 @@ static int compute_step(Solver& S, double radius) {
   mark(S, 1);  // landmark / Schur prep
   TSL_CUDA(cudaMemsetAsync(S.mx.p, 0, MX_N * sizeof(double), st));
   TSL_CUDA(cudaMemsetAsync(S.fail.p, 0, sizeof(int), st));
-  if (S.nvp) LAUNCH(lm_vinv_kernel<1><<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.Vp.p, inv_radius, S.Vinvp.p, S.mx.p));
-  if (S.nvt) LAUNCH(lm_vinv_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.Vt.p, inv_radius, S.Vinvt.p, S.mx.p));
+  if (S.nvp) LAUNCH(launch_k(lm_vinv_kernel<1>, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.Vp.p, inv_radius, S.Vinvp.p, S.mx.p));
+  if (S.nvt) LAUNCH(launch_k(lm_vinv_kernel<3>, grid_for(S.nvt, 128), 128, 0, st, S.nvt, S.Vt.p, inv_radius, S.Vinvt.p, S.mx.p));
   mark(S, 2);  // reduced system build
   if (S.nblk) {
     BlockArgs B;
@@ -948,10 +972,10 @@ static int compute_step(Solver& S, double radius) {
     // diagonal blocks (heavy gather lists, ~650 entries on the global-BA shape) get a CTA each, off-diagonal blocks 8 lanes —
     // unless the camera graph is small and dense (local BA: 7 cameras, 28 blocks, ~600 entries each): then every block gets a CTA
     if (S.est_entries > 96 * (long long)S.nblk) {
-      LAUNCH(schur_block_kernel<128><<<S.nblk, 128, 0, st>>>(B, nullptr, S.nblk));
+      LAUNCH(launch_k(schur_block_kernel<128>, S.nblk, 128, 0, st, B, nullptr, S.nblk));
     } else {
-      LAUNCH(schur_block_kernel<128><<<S.nc, 128, 0, st>>>(B, S.diag_blk.p, S.nc));
-      if (S.noff) LAUNCH(schur_block_kernel<8><<<grid_for(S.noff * 8, 128), 128, 0, st>>>(B, S.offdiag_blk.p, S.noff));
+      LAUNCH(launch_k(schur_block_kernel<128>, S.nc, 128, 0, st, B, S.diag_blk.p, S.nc));
+      if (S.noff) LAUNCH(launch_k(schur_block_kernel<8>, grid_for(S.noff * 8, 128), 128, 0, st, B, S.offdiag_blk.p, S.noff));
     }
     TSL_CHECK_LAUNCH();
   }
@@ -965,22 +989,22 @@ static int compute_step(Solver& S, double radius) {
     { int rc = chol_clear(ctx, S.chol, S.A.p); if (rc) return rc; }
     ScatterArgs Sa{S.nblk, S.blk_a.p, S.blk_b.p, S.Sblk, S.bvec, S.udiag, inv_radius, S.A.p, S.ld, S.n, S.rows, S.Tn * 64};
     const int total = S.nblk * 36 + S.ld;
-    LAUNCH(scatter_kernel<<<grid_for(total, 256), 256, 0, st>>>(Sa));
+    LAUNCH(launch_k(scatter_kernel, grid_for(total, 256), 256, 0, st, Sa));
     TSL_CHECK_LAUNCH();
     int rc = chol_solve(ctx, S.chol, S.A.p, S.ywork.p, S.yc.p, S.fail.p);
     if (rc) return rc;
-    LAUNCH(copy_fail_kernel<<<1, 1, 0, st>>>(S.fail.p, S.mx.p));
+    LAUNCH(launch_k(copy_fail_kernel, 1, 1, 0, st, S.fail.p, S.mx.p));
   }
   mark(S, 5);  // back-substitution + candidate
-  if (S.nvp) LAUNCH(backsub_kernel<1><<<grid_for(S.nvp, 128), 128, 0, st>>>(S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p));
-  if (S.nvt) LAUNCH(backsub_kernel<3><<<grid_for(S.nvt, 128), 128, 0, st>>>(S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p));
-  LAUNCH(candidate_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0));
+  if (S.nvp) LAUNCH(launch_k(backsub_kernel<1>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p));
+  if (S.nvt) LAUNCH(launch_k(backsub_kernel<3>, grid_for(S.nvt, 128), 128, 0, st, S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p));
+  LAUNCH(launch_k(candidate_cams_kernel, 1, 256, 0, st, S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0));
   const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
   double* parts = S.parts.p;
-  if (S.nvp) LAUNCH(candidate_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts));
-  if (S.nvt) LAUNCH(candidate_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp));
+  if (S.nvp) LAUNCH(launch_k(candidate_lm_kernel<1>, gvp, 256, 0, st, S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts));
+  if (S.nvt) LAUNCH(launch_k(candidate_lm_kernel<3>, gvt, 256, 0, st, S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp));
   if (gvp + gvt) {
-    LAUNCH(sum_parts_pair_kernel<<<2, 256, 0, st>>>(parts, gvp + gvt, S.sc + SC_STEP2, S.sc + SC_CNORM2, 1));
+    LAUNCH(launch_k(sum_parts_pair_kernel, 2, 256, 0, st, parts, gvp + gvt, S.sc + SC_STEP2, S.sc + SC_CNORM2, 1));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -991,9 +1015,9 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
   mark(S, 6);  // model cost change + candidate cost
   const int gp = grid_for(S.lp, 256), gt = grid_for(S.lt, 256);
   double* parts = S.parts.p;
-  if (S.lp) LAUNCH(model_cost_kernel<1, 2, 13><<<gp, 256, 0, st>>>(S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts));
-  if (S.lt) LAUNCH(model_cost_kernel<3, 8, 15><<<gt, 256, 0, st>>>(S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp));
-  LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(parts, gp + gt, 1, 0, S.sc + SC_MCC, 0));
+  if (S.lp) LAUNCH(launch_k(model_cost_kernel<1, 2, 13>, gp, 256, 0, st, S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts));
+  if (S.lt) LAUNCH(launch_k(model_cost_kernel<3, 8, 15>, gt, 256, 0, st, S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp));
+  LAUNCH(launch_k(sum_parts_kernel, 1, 256, 0, st, parts, gp + gt, 1, 0, S.sc + SC_MCC, 0));
   TSL_CHECK_LAUNCH();
   int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, false, jac_mode, SC_CAND, S.cr_p.p, S.cr_t.p);
   if (rc) return rc;
@@ -1004,9 +1028,9 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
 static int gradient_max_norm(Solver& S) {
   cudaStream_t st = S.ctx->stream;
   // graw (cams) is produced by schur_block_kernel and already all-reduced; landmark gradients are local
-  LAUNCH(gmax_cams_kernel<<<grid_for(S.K, 128), 128, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.graw, S.mx.p));
-  if (S.nvp) LAUNCH(gmax_lm_kernel<<<grid_for(S.nvp, 256), 256, 0, st>>>(S.nvp, S.gp.p, S.scale_vp.p, S.mx.p));
-  if (S.nvt) LAUNCH(gmax_lm_kernel<<<grid_for(3 * S.nvt, 256), 256, 0, st>>>(3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p));
+  LAUNCH(launch_k(gmax_cams_kernel, grid_for(S.K, 128), 128, 0, st, S.K, S.camslot_d.p, S.x_cams, S.graw, S.mx.p));
+  if (S.nvp) LAUNCH(launch_k(gmax_lm_kernel, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.gp.p, S.scale_vp.p, S.mx.p));
+  if (S.nvt) LAUNCH(launch_k(gmax_lm_kernel, grid_for(3 * S.nvt, 256), 256, 0, st, 3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -1039,11 +1063,11 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
   if ((rc = accumulate_landmarks(S))) return rc;
   // x_norm
   {
-    LAUNCH(xnorm_cams_kernel<<<1, 256, 0, st>>>(S.K, S.camslot_d.p, S.x_cams, S.sc + SC_XNORM2, ctx->rank == 0 ? 1.0 : 0.0));
+    LAUNCH(launch_k(xnorm_cams_kernel, 1, 256, 0, st, S.K, S.camslot_d.p, S.x_cams, S.sc + SC_XNORM2, ctx->rank == 0 ? 1.0 : 0.0));
     const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
-    if (S.nvp) LAUNCH(xnorm_lm_kernel<1><<<gvp, 256, 0, st>>>(S.nvp, S.vp_gl.p, S.x_rho, S.parts.p));
-    if (S.nvt) LAUNCH(xnorm_lm_kernel<3><<<gvt, 256, 0, st>>>(S.nvt, S.vt_gl.p, S.x_theta, S.parts.p + gvp));
-    if (gvp + gvt) LAUNCH(sum_parts_kernel<<<1, 256, 0, st>>>(S.parts.p, gvp + gvt, 1, 0, S.sc + SC_XNORM2, 1));
+    if (S.nvp) LAUNCH(launch_k(xnorm_lm_kernel<1>, gvp, 256, 0, st, S.nvp, S.vp_gl.p, S.x_rho, S.parts.p));
+    if (S.nvt) LAUNCH(launch_k(xnorm_lm_kernel<3>, gvt, 256, 0, st, S.nvt, S.vt_gl.p, S.x_theta, S.parts.p + gvp));
+    if (gvp + gvt) LAUNCH(launch_k(sum_parts_kernel, 1, 256, 0, st, S.parts.p, gvp + gvt, 1, 0, S.sc + SC_XNORM2, 1));
     TSL_CHECK_LAUNCH();
   }
   double x_cost = 0, fixed_cost = 0, x_norm = 0, gmax = 0;
@@ -1205,8 +1229,8 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
     TSL_CUDA(orho.reserve(d.n_points)); TSL_CUDA(oth.reserve(3 * (size_t)d.n_planes));
     TSL_CUDA(cudaMemsetAsync(orho.p, 0, sizeof(double) * d.n_points, st));
     TSL_CUDA(cudaMemsetAsync(oth.p, 0, sizeof(double) * 3 * (size_t)d.n_planes, st));
-    if (S->nvp) LAUNCH(export_lm_kernel<1><<<(S->nvp + 255) / 256, 256, 0, st>>>(S->nvp, S->vp_gl.p, d.rho.p, orho.p));
-    if (S->nvt) LAUNCH(export_lm_kernel<3><<<(3 * S->nvt + 255) / 256, 256, 0, st>>>(S->nvt, S->vt_gl.p, d.theta.p, oth.p));
+    if (S->nvp) LAUNCH(launch_k(export_lm_kernel<1>, (S->nvp + 255) / 256, 256, 0, st, S->nvp, S->vp_gl.p, d.rho.p, orho.p));
+    if (S->nvt) LAUNCH(launch_k(export_lm_kernel<3>, (3 * S->nvt + 255) / 256, 256, 0, st, S->nvt, S->vt_gl.p, d.theta.p, oth.p));
     if ((rc = comm_allreduce_sum(ctx, orho.p, d.n_points))) return rc;
     if ((rc = comm_allreduce_sum(ctx, oth.p, 3 * (size_t)d.n_planes))) return rc;
     std::vector<double> hr(d.n_points), ht(3 * (size_t)d.n_planes);
@@ -1229,8 +1253,8 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
     if (ctx->world > 1) {
       TSL_CUDA(fr.reserve(total));
       TSL_CUDA(cudaMemsetAsync(fr.p, 0, total * sizeof(double), st));
-      if (S->lp) LAUNCH(scatter_rows_kernel<<<(2 * S->lp + 255) / 256, 256, 0, st>>>(S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p));
-      if (S->lt) LAUNCH(scatter_rows_kernel<<<(8 * S->lt + 255) / 256, 256, 0, st>>>(S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs));
+      if (S->lp) LAUNCH(launch_k(scatter_rows_kernel, (2 * S->lp + 255) / 256, 256, 0, st, S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p));
+      if (S->lt) LAUNCH(launch_k(scatter_rows_kernel, (8 * S->lt + 255) / 256, 256, 0, st, S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs));
       if ((rc = comm_allreduce_sum(ctx, fr.p, total))) return rc;
       if (final_residuals) TSL_CUDA(cudaMemcpyAsync(final_residuals, fr.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
       TSL_CUDA(cudaStreamSynchronize(st));

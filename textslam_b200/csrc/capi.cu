@@ -9,6 +9,10 @@ namespace tsl {
 
 thread_local std::string g_last_error;
 long long g_launches = 0;
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("TSLAM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 int set_error(int code, const char* fmt, ...) {
   char buf[1024];

@@ -38,6 +38,7 @@ namespace tsl {
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
 __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
                                                                 int* __restrict__ fail, double* __restrict__ Linv) {
+  PDL_PROLOGUE();
   // one CTA per (panel j, row tile i) item of the current wave; i < 0 marks the CTA that stores L_jj^-1.
   // Every CTA factors the (small) diagonal tile redundantly straight from A: nobody writes A_jj in this launch.
   extern __shared__ __align__(16) double smem[];
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restri
 constexpr int QB = 32;
 __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, int ld, const int2* __restrict__ targets,
                                                         const int* __restrict__ src_ptr, const int* __restrict__ src) {
+  PDL_PROLOGUE();
   extern __shared__ double smem[];
   double* sA = smem;               // 32 x SPAD: rows of X_i
   double* sB = smem + QB * SPAD;   // 32 x SPAD: rows of X_k
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
 __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict__ A, int ld, int npanels, const int* __restrict__ panels,
                                                         const int* __restrict__ below_ptr, const int* __restrict__ below,
                                                         const double* __restrict__ Linv, const double* __restrict__ y, double* x, int* flags, int epoch) {
+  PDL_PROLOGUE();
   // 256 threads = 4 groups x 64 columns; group g takes the tiles e = g (mod 4) of the list, partial sums meet in smem
   __shared__ double sx[4][NB];
   __shared__ double st[4][NB];
@@ -225,12 +228,14 @@ __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict
 // Zero the tiles of the factor pattern (one CTA per (panel, row tile) item = one 64x64 tile) before the reduced system is
 // scattered into them: the dense workspace is 10x larger than its structurally non-zero part on a SLAM camera graph.
 __global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items) {
+  PDL_PROLOGUE();
   const int2 it = items[blockIdx.x];
   double* T = A + (size_t)(it.y < 0 ? it.x : it.y) * NB * ld + (size_t)it.x * NB;
   for (int e = threadIdx.x; e < NB * NB / 2; e += 256) { const int r = e >> 5, c = (e & 31) * 2; *reinterpret_cast<double2*>(T + (size_t)r * ld + c) = make_double2(0.0, 0.0); }
 }
 
 __global__ void copy_row_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
+  PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
@@ -266,7 +271,7 @@ int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A) {
   int ld, rows;
   chol_workspace_dims(sym.n, &ld, &rows);
   const int ni = sym.item_ptr[sym.nwaves];
-  if (ni > 0) LAUNCH(zero_tiles_kernel<<<ni, 256, 0, ctx->stream>>>(A, ld, sym.items.p));
+  if (ni > 0) LAUNCH(launch_k(zero_tiles_kernel, ni, 256, 0, ctx->stream, A, ld, sym.items.p));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -292,16 +297,16 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   mark(-1);
   for (int w = 0; w < sym.nwaves; ++w) {
     const int ni = sym.item_ptr[w + 1] - sym.item_ptr[w], nt = sym.target_ptr[w + 1] - sym.target_ptr[w];
-    LAUNCH(potrf_trsm_kernel<<<ni, PT_THREADS, smem_pt, s>>>(A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+    LAUNCH(launch_k(potrf_trsm_kernel, ni, PT_THREADS, smem_pt, s, A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
     mark(0);
-    if (nt > 0) LAUNCH(syrk_wave_kernel<<<4 * nt, 128, smem, s>>>(A, ld, sym.targets.p + sym.target_ptr[w], sym.src_ptr.p + sym.target_ptr[w], sym.src.p));
+    if (nt > 0) LAUNCH(launch_k(syrk_wave_kernel, 4 * nt, 128, smem, s, A, ld, sym.targets.p + sym.target_ptr[w], sym.src_ptr.p + sym.target_ptr[w], sym.src.p));
     mark(1);
   }
   TSL_CHECK_LAUNCH();
   {
     const int np = sym.panel_ptr[sym.nwaves];
     const int epoch = ++sym.epoch;
-    LAUNCH(backsolve_kernel<<<np, 256, 0, s>>>(A, ld, np, sym.panels.p, sym.below_ptr.p, sym.below.p, sym.Ldiag.p, A + (size_t)Tn * NB * ld, xout, sym.flags.p, epoch));
+    LAUNCH(launch_k(backsolve_kernel, np, 256, 0, s, A, ld, np, sym.panels.p, sym.below_ptr.p, sym.below.p, sym.Ldiag.p, A + (size_t)Tn * NB * ld, xout, sym.flags.p, epoch));
     mark(3);
   }
   if (trace) {

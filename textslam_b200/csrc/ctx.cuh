@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/tslam_b200.h"
 
@@ -22,6 +23,32 @@ int set_error(int code, const char* fmt, ...);
 #define TSL_CHECK_LAUNCH() TSL_CUDA(cudaGetLastError())
 // every kernel launch of this library goes through LAUNCH so that bench.py can report gpu_launches
 #define LAUNCH(...) do { ++tsl::g_launches; __VA_ARGS__; } while (0)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// An LM iteration is ~50 short dependent kernels (29 of them the wave-scheduled Cholesky); between two of them the GPU
+// otherwise drains, then fetches and schedules the next grid. Every solver kernel starts with PDL_PROLOGUE():
+// `griddepcontrol.launch_dependents` lets the next kernel of the stream be scheduled as soon as all CTAs of this one have
+// started, `griddepcontrol.wait` then blocks until the previous kernel has completed and its writes are visible — so
+// the data dependencies are exactly those of plain stream order, only the launch latency overlaps the predecessor's tail.
+// Both instructions are no-ops for a kernel launched without the attribute (TSLAM_PDL=0, or launch through <<<>>>).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#define PDL_PROLOGUE() tsl::pdl_prologue()
+bool pdl_enabled();   // capi.cu: TSLAM_PDL != "0"
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through TSL_CHECK_LAUNCH (cudaGetLastError)
+}
+#endif
 
 template <typename T>
 struct DevBuf {  // simple RAII device buffer (grow-only)
