@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <atomic>
 #include "ctx.cuh"
 #include "solver.cuh"
 #include "analysis.hpp"
@@ -719,9 +720,54 @@ __global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(mx + MX_GMAX), m);
 }
 
-__global__ void copy_fail_kernel(const int* fail, double* mx) {
+// ---- end of an LM iteration's device work --------------------------------------------------------------------------
+// ONE launch finishes the three two-level sums of the iteration (step / candidate norms, model cost change, candidate cost;
+// same summation order as sum_parts(_pair)_kernel), folds the factorisation's failure flag into mx[], and — single GPU —
+// publishes the 10 scalars the host's accept / reject logic needs straight into page-locked host memory, followed by a
+// sequence number the host spins on (no copy-engine round trip, no stream synchronisation). It also re-arms mx[] and the
+// failure flag for the next iteration. Multi-GPU: host == nullptr here, the scalars are all-reduced first and
+// publish_scalars_kernel does the publishing.
+struct TailArgs {
+  const double* parts_step; int n_step;   // interleaved (step^2, candidate-norm^2) partial pairs of candidate_lm_kernel
+  const double* parts_mcc; int n_mcc;     // model_cost_kernel partials
+  const double* parts_cand; int n_cand;   // interleaved (cost, fixed cost) partial pairs of the candidate evaluation
+  double* sc; double* mx; int* fail;
+  double* host; double seq;
+};
+constexpr int H_SEQ = 63;                 // slot of the sequence number in tslam_ctx::h_scalars (64 doubles)
+
+__device__ __forceinline__ double strided_sum_256(const double* __restrict__ p, int n, int stride, int off, double* s) {
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) a += p[(size_t)i * stride + off];
+  __syncthreads();   // s[] may still be read by the previous reduction
+  return block_sum_256(a, s);
+}
+__device__ __forceinline__ void publish_to_host(const double* sc, double* mx, int* fail, double* host, double seq) {
+  // one thread, program order: 10 payload stores, system-scope fence, then the sequence number
+  for (int k = 0; k < SC_N; ++k) host[k] = sc[k];
+  for (int k = 0; k < MX_N; ++k) { host[SC_N + k] = mx[k]; mx[k] = 0.0; }
+  *fail = 0;
+  __threadfence_system();
+  *reinterpret_cast<volatile double*>(host + H_SEQ) = seq;
+}
+__global__ void __launch_bounds__(256) iteration_tail_kernel(TailArgs a) {
   PDL_PROLOGUE();
-  if (*fail) atomic_max_nonneg(mx + MX_FAIL, 1.0);
+  __shared__ double s[256];
+  const double step2 = strided_sum_256(a.parts_step, a.n_step, 2, 0, s);
+  const double cn2 = strided_sum_256(a.parts_step, a.n_step, 2, 1, s);
+  const double mcc = strided_sum_256(a.parts_mcc, a.n_mcc, 1, 0, s);
+  const double cand = strided_sum_256(a.parts_cand, a.n_cand, 2, 0, s);
+  const double cand_fixed = strided_sum_256(a.parts_cand, a.n_cand, 2, 1, s);
+  if (threadIdx.x == 0) {
+    a.sc[SC_STEP2] += step2; a.sc[SC_CNORM2] += cn2;   // candidate_cams_kernel wrote the camera part
+    a.sc[SC_MCC] = mcc; a.sc[SC_CAND] = cand; a.sc[SC_CAND_FIXED] = cand_fixed;
+    if (*a.fail) a.mx[MX_FAIL] = fmax(a.mx[MX_FAIL], 1.0);
+    if (a.host) publish_to_host(a.sc, a.mx, a.fail, a.host, a.seq);
+  }
+}
+__global__ void publish_scalars_kernel(const double* sc, double* mx, int* fail, double* host, double seq) {
+  PDL_PROLOGUE();
+  if (threadIdx.x == 0 && blockIdx.x == 0) publish_to_host(sc, mx, fail, host, seq);
 }
 // final residual scatter into the global residual vector (multi-GPU: other ranks' entries stay 0)
 __global__ void scatter_rows_kernel(int n, int width, const int* __restrict__ gsel, const double* __restrict__ src, double* __restrict__ dst) {
@@ -754,7 +800,8 @@ struct Solver : SolverIndex {
   DevBuf<double> red;        // [Sblk | b | graw | udiag]  (one all-reduce)
   DevBuf<double> scl, scr;   // local scalars / reduced copy
   DevBuf<double> mx;         // max-reduced scalars
-  DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts;
+  DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts, parts_step, parts_mcc;
+  int tail_n_cand = 0;   // partial pairs of the deferred candidate-cost sum (iteration_tail_kernel)
   DevBuf<int> fail;
   size_t red_n = 0;
   double *Sblk = nullptr, *bvec = nullptr, *graw = nullptr, *udiag = nullptr, *sc = nullptr;
@@ -861,6 +908,8 @@ static int analyze_and_upload(Solver& S) {
   TSL_CUDA(S.delta_c.reserve(6 * (size_t)nc)); TSL_CUDA(S.delta_vp.reserve(S.nvp)); TSL_CUDA(S.delta_vt.reserve(3 * (size_t)S.nvt));
   const size_t nparts = 2 * ((size_t)(lp + 127) / 128 + (size_t)(8 * (size_t)lt + 127) / 128) + 2 * ((size_t)(S.nvp + 255) / 256 + (size_t)(S.nvt + 255) / 256) + 64;
   TSL_CUDA(S.parts.reserve(nparts));
+  TSL_CUDA(S.parts_step.reserve(2 * ((size_t)(S.nvp + 255) / 256 + (size_t)(S.nvt + 255) / 256) + 2));
+  TSL_CUDA(S.parts_mcc.reserve((size_t)(lp + 255) / 256 + (size_t)(lt + 255) / 256 + 2));
   TSL_CUDA(S.fail.reserve(1));
   TSL_CUDA(cudaStreamSynchronize(st));   // the host vectors of A go out of scope on return
   // host copies the solver keeps (the arena is recycled by the next analysis on this context)
@@ -890,7 +939,7 @@ static inline int grid_for(int n, int b) { return n > 0 ? (n + b - 1) / b : 0; }
 
 // Evaluate residuals (+ Jacobians) at (cams, rho, theta); cost -> sc[cost_slot], sc[cost_slot+1]
 static int eval_at(Solver& S, const double* cams, const double* rho, const double* theta, bool want_J, int jac_mode, int cost_slot,
-                   double* pr, double* tr) {
+                   double* pr, double* tr, bool defer_sum = false) {
   tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
   int np = 0, nt = 0;
   double* parts = S.parts.p;
@@ -898,7 +947,8 @@ static int eval_at(Solver& S, const double* cams, const double* rho, const doubl
   if (rc) return rc;
   rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? S.tJ.p : nullptr, parts + 2 * np, &nt);
   if (rc) return rc;
-  LAUNCH(launch_k(sum_parts_pair_kernel, 2, 256, 0, ctx->stream, parts, np + nt, S.sc + cost_slot, S.sc + cost_slot + 1, 0));
+  S.tail_n_cand = np + nt;
+  if (!defer_sum) LAUNCH(launch_k(sum_parts_pair_kernel, 2, 256, 0, ctx->stream, parts, np + nt, S.sc + cost_slot, S.sc + cost_slot + 1, 0));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -957,8 +1007,7 @@ static int compute_step(Solver& S, double radius) {
   const double inv_radius = 1.0 / radius;
   const int nc = S.nc;
   mark(S, 1);  // landmark / Schur prep
-  TSL_CUDA(cudaMemsetAsync(S.mx.p, 0, MX_N * sizeof(double), st));
-  TSL_CUDA(cudaMemsetAsync(S.fail.p, 0, sizeof(int), st));
+  // mx[] and the failure flag are zero here: cleared by run_lm before the first iteration, re-armed by every publish
   if (S.nvp) LAUNCH(launch_k(lm_vinv_kernel<1>, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.Vp.p, inv_radius, S.Vinvp.p, S.mx.p));
   if (S.nvt) LAUNCH(launch_k(lm_vinv_kernel<3>, grid_for(S.nvt, 128), 128, 0, st, S.nvt, S.Vt.p, inv_radius, S.Vinvt.p, S.mx.p));
   mark(S, 2);  // reduced system build
@@ -993,19 +1042,15 @@ static int compute_step(Solver& S, double radius) {
     TSL_CHECK_LAUNCH();
     int rc = chol_solve(ctx, S.chol, S.A.p, S.ywork.p, S.yc.p, S.fail.p);
     if (rc) return rc;
-    LAUNCH(launch_k(copy_fail_kernel, 1, 1, 0, st, S.fail.p, S.mx.p));
   }
   mark(S, 5);  // back-substitution + candidate
   if (S.nvp) LAUNCH(launch_k(backsub_kernel<1>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p));
   if (S.nvt) LAUNCH(launch_k(backsub_kernel<3>, grid_for(S.nvt, 128), 128, 0, st, S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p));
   LAUNCH(launch_k(candidate_cams_kernel, 1, 256, 0, st, S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0));
   const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
-  double* parts = S.parts.p;
+  double* parts = S.parts_step.p;   // summed onto sc[SC_STEP2], sc[SC_CNORM2] by iteration_tail_kernel
   if (S.nvp) LAUNCH(launch_k(candidate_lm_kernel<1>, gvp, 256, 0, st, S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts));
   if (S.nvt) LAUNCH(launch_k(candidate_lm_kernel<3>, gvt, 256, 0, st, S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp));
-  if (gvp + gvt) {
-    LAUNCH(launch_k(sum_parts_pair_kernel, 2, 256, 0, st, parts, gvp + gvt, S.sc + SC_STEP2, S.sc + SC_CNORM2, 1));
-  }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -1014,13 +1059,19 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
   cudaStream_t st = S.ctx->stream;
   mark(S, 6);  // model cost change + candidate cost
   const int gp = grid_for(S.lp, 256), gt = grid_for(S.lt, 256);
-  double* parts = S.parts.p;
+  double* parts = S.parts_mcc.p;
   if (S.lp) LAUNCH(launch_k(model_cost_kernel<1, 2, 13>, gp, 256, 0, st, S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts));
   if (S.lt) LAUNCH(launch_k(model_cost_kernel<3, 8, 15>, gt, 256, 0, st, S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp));
-  LAUNCH(launch_k(sum_parts_kernel, 1, 256, 0, st, parts, gp + gt, 1, 0, S.sc + SC_MCC, 0));
   TSL_CHECK_LAUNCH();
-  int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, false, jac_mode, SC_CAND, S.cr_p.p, S.cr_t.p);
+  int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, false, jac_mode, SC_CAND, S.cr_p.p, S.cr_t.p, /*defer_sum=*/true);
   if (rc) return rc;
+  // the three sums of this iteration (+ the publish on one GPU) in one launch
+  tslam_ctx* ctx = S.ctx;
+  const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
+  TailArgs ta{S.parts_step.p, gvp + gvt, S.parts_mcc.p, gp + gt, S.parts.p, S.tail_n_cand, S.sc, S.mx.p, S.fail.p,
+              ctx->world > 1 ? nullptr : ctx->h_scalars_dev, ctx->world > 1 ? 0.0 : ++ctx->h_seq};
+  LAUNCH(launch_k(iteration_tail_kernel, 1, 256, 0, st, ta));
+  TSL_CHECK_LAUNCH();
   mark(S, 7);  // end of the iteration's device work
   return TSLAM_OK;
 }
@@ -1032,6 +1083,28 @@ static int gradient_max_norm(Solver& S) {
   if (S.nvp) LAUNCH(launch_k(gmax_lm_kernel, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.gp.p, S.scale_vp.p, S.mx.p));
   if (S.nvt) LAUNCH(launch_k(gmax_lm_kernel, grid_for(3 * S.nvt, 256), 256, 0, st, 3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p));
   TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
+}
+
+// Spins on the sequence number the device writes after the iteration's scalars (page-locked, device-mapped host memory);
+// the stream is queried now and then so that a failed launch or a sticky error ends the wait instead of hanging it.
+static int wait_published(tslam_ctx* ctx) {
+  volatile double* flag = ctx->h_scalars + H_SEQ;
+  const double seq = ctx->h_seq;
+  for (unsigned spins = 1;; ++spins) {
+    if (*flag == seq) break;
+    if ((spins & 0x1fffu) == 0) {
+      const cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaErrorNotReady) continue;
+      if (e != cudaSuccess) return set_error(TSLAM_ERR_CUDA, "LM iteration failed on the device: %s", cudaGetErrorString(e));
+      if (*flag == seq) break;
+      return set_error(TSLAM_ERR_CUDA, "LM iteration finished without publishing its scalars");
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   return TSLAM_OK;
 }
 
@@ -1055,6 +1128,8 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
   TSL_CUDA(cudaMemcpyAsync(S.c_rho, S.x_rho, sizeof(double) * d->n_points, cudaMemcpyDeviceToDevice, st));
   TSL_CUDA(cudaMemcpyAsync(S.c_theta, S.x_theta, sizeof(double) * 3 * (size_t)d->n_planes, cudaMemcpyDeviceToDevice, st));
 
+  TSL_CUDA(cudaMemsetAsync(S.mx.p, 0, MX_N * sizeof(double), st));
+  TSL_CUDA(cudaMemsetAsync(S.fail.p, 0, sizeof(int), st));
   // ---- iteration 0 ----
   mark(S, 0);
   int rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.pr.p, S.tr.p);
@@ -1083,16 +1158,14 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
     if ((rc = compute_step(S, radius))) return rc;
     if ((rc = gradient_max_norm(S))) return rc;
     if ((rc = model_and_candidate_cost(S, jac_mode))) return rc;
-    const double* sc_src = S.sc;
     if (ctx->world > 1) {  // reduce a COPY: the local slots (cost at x, x-norm) persist across iterations
       TSL_CUDA(cudaMemcpyAsync(S.scr.p, S.sc, SC_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
       if ((rc = comm_allreduce_sum(ctx, S.scr.p, SC_N))) return rc;
       if ((rc = comm_allreduce_max(ctx, S.mx.p, MX_N))) return rc;
-      sc_src = S.scr.p;
+      LAUNCH(launch_k(publish_scalars_kernel, 1, 32, 0, st, S.scr.p, S.mx.p, S.fail.p, ctx->h_scalars_dev, ++ctx->h_seq));
+      TSL_CHECK_LAUNCH();
     }
-    TSL_CUDA(cudaMemcpyAsync(h, sc_src, SC_N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    TSL_CUDA(cudaMemcpyAsync(h + SC_N, S.mx.p, MX_N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    TSL_CUDA(cudaStreamSynchronize(st));
+    if ((rc = wait_published(ctx))) return rc;   // iteration_tail_kernel / publish_scalars_kernel wrote h[] and the sequence number
     if (!have_cost) {
       x_cost = h[SC_COST]; fixed_cost = h[SC_FIXED]; x_norm = std::sqrt(h[SC_XNORM2]); have_cost = true;
       sum.initial_cost = x_cost + fixed_cost; sum.fixed_cost = fixed_cost;
@@ -1125,10 +1198,9 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
     }
     const double rel = cost_change / mcc;
     if (rel > min_rel_dec) {
+      // both buffers carry the untouched (fixed / non-owned) landmark entries since the copy before iteration 0, and
+      // candidate_lm_kernel rewrites every owned free entry each iteration: a pointer swap is all an accepted step needs
       std::swap(S.x_cams, S.c_cams); std::swap(S.x_rho, S.c_rho); std::swap(S.x_theta, S.c_theta);
-      // the candidate buffers must carry the untouched (fixed / non-owned) entries too
-      TSL_CUDA(cudaMemcpyAsync(S.c_rho, S.x_rho, sizeof(double) * d->n_points, cudaMemcpyDeviceToDevice, st));
-      TSL_CUDA(cudaMemcpyAsync(S.c_theta, S.x_theta, sizeof(double) * 3 * (size_t)d->n_planes, cudaMemcpyDeviceToDevice, st));
       x_norm = std::sqrt(h[SC_CNORM2]);
       mark(S, 0);  // eval + J (the next iteration's linearisation point)
       if ((rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.pr.p, S.tr.p))) return rc;

@@ -200,7 +200,9 @@ int tslam_ctx_create(int device_id, tslam_ctx** out) {
   TSL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   TSL_CUDA(cudaEventCreate(&c->ev0));
   TSL_CUDA(cudaEventCreate(&c->ev1));
-  TSL_CUDA(cudaHostAlloc(&c->h_scalars, 64 * sizeof(double), cudaHostAllocDefault));
+  TSL_CUDA(cudaHostAlloc(&c->h_scalars, 64 * sizeof(double), cudaHostAllocMapped));
+  memset(c->h_scalars, 0, 64 * sizeof(double));
+  TSL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->h_scalars_dev), c->h_scalars, 0));
   *out = c;
   return TSLAM_OK;
 }

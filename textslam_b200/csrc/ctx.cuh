@@ -92,7 +92,9 @@ struct tslam_ctx {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
   // pinned staging for scalars
-  double* h_scalars = nullptr;  // cudaHostAlloc, 64 doubles
+  double* h_scalars = nullptr;  // cudaHostAlloc (mapped), 64 doubles: [0..9] iteration scalars, [63] sequence number written last by the device
+  double* h_scalars_dev = nullptr;   // device-side address of h_scalars
+  double h_seq = 0.0;                // last sequence number handed to a publishing kernel
   // page-locked arena behind the host-side structure analysis (analysis.hpp); recycled by every solve on this context
   tsl::Arena* host_arena = nullptr;
 };
