@@ -83,11 +83,10 @@ __device__ __forceinline__ double block_sum_256(double v, double* s) {
 
 // ---- per-landmark accumulation: V (DxD), g (D), both in the Jacobi-scaled system ------------------
 template <int D, int ROWS, int JC>
-__global__ void lm_accum_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
+__device__ __forceinline__ void lm_accum_body(const unsigned bid, int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
                                 const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
                                 double* __restrict__ g) {
-  PDL_PROLOGUE();
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = bid * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   double Vv[D * D], gv[D];
 #pragma unroll
@@ -122,14 +121,20 @@ __global__ void lm_accum_kernel(int nv, const int* __restrict__ obs_ptr, const i
     for (int b = 0; b < D; ++b) V[(size_t)v * D * D + a * D + b] = Vv[a * D + b] * s[a] * s[b];
   }
 }
+template <int D, int ROWS, int JC>
+__global__ void lm_accum_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
+                                const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
+                                double* __restrict__ g) {
+  PDL_PROLOGUE();
+  lm_accum_body<D, ROWS, JC>(blockIdx.x, nv, obs_ptr, obs, J, r, scale, V, g);
+}
 
 // ---- per (landmark, camera) slot: E = S_c J_c' J_l S_l  (6 x D) ----------------------------------------
 template <int D, int ROWS, int JC>
-__global__ void slot_accum_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
+__device__ __forceinline__ void slot_accum_body(const unsigned bid, int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
                                   const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
                                   const double* __restrict__ scale_l, double* __restrict__ E) {
-  PDL_PROLOGUE();
-  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sidx = bid * blockDim.x + threadIdx.x;
   if (sidx >= ns) return;
   double Ev[6 * D];
 #pragma unroll
@@ -159,16 +164,22 @@ __global__ void slot_accum_kernel(int ns, const int* __restrict__ ent_ptr, const
     for (int a = 0; a < D; ++a) E[(size_t)sidx * 6 * D + c * D + a] = Ev[c * D + a] * sc * scale_l[lm * D + a];
   }
 }
+template <int D, int ROWS, int JC>
+__global__ void slot_accum_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
+                                  const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
+                                  const double* __restrict__ scale_l, double* __restrict__ E) {
+  PDL_PROLOGUE();
+  slot_accum_body<D, ROWS, JC>(blockIdx.x, ns, ent_ptr, ent, slot_cam, slot_lm, J, scale_c, scale_l, E);
+}
 
 // Same sums with one WARP per landmark (lanes over the (observation, residual row) pairs, butterfly at the end): the text
 // planes are few (tens) with hundreds of residual rows each — a thread per plane left the GPU idle behind 30 serial loops
 // (local BA C4: 94 us per call, profiles/r1_notes.md).
 template <int D, int ROWS, int JC>
-__global__ void __launch_bounds__(128) lm_accum_warp_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
+__device__ __forceinline__ void lm_accum_warp_body(const unsigned bid, int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
                                                             const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
                                                             double* __restrict__ g) {
-  PDL_PROLOGUE();
-  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int v = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (v >= nv) return;   // warp-uniform
   double Vv[D * D], gv[D];
 #pragma unroll
@@ -209,13 +220,19 @@ __global__ void __launch_bounds__(128) lm_accum_warp_kernel(int nv, const int* _
     }
   }
 }
+template <int D, int ROWS, int JC>
+__global__ void __launch_bounds__(128) lm_accum_warp_kernel(int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs, const double* __restrict__ J,
+                                                            const double* __restrict__ r, const double* __restrict__ scale, double* __restrict__ V,
+                                                            double* __restrict__ g) {
+  PDL_PROLOGUE();
+  lm_accum_warp_body<D, ROWS, JC>(blockIdx.x, nv, obs_ptr, obs, J, r, scale, V, g);
+}
 
 template <int D, int ROWS, int JC>
-__global__ void __launch_bounds__(128) slot_accum_warp_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
+__device__ __forceinline__ void slot_accum_warp_body(const unsigned bid, int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
                                                               const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
                                                               const double* __restrict__ scale_l, double* __restrict__ E) {
-  PDL_PROLOGUE();
-  const int sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int sidx = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (sidx >= ns) return;   // warp-uniform
   double Ev[6 * D];
 #pragma unroll
@@ -243,6 +260,31 @@ __global__ void __launch_bounds__(128) slot_accum_warp_kernel(int ns, const int*
 #pragma unroll
   for (int k = 0; k < 6 * D; ++k)
     if (lane == k) E[(size_t)sidx * 6 * D + k] = Ev[k] * scale_c[6 * cam + k / D] * scale_l[lm * D + k % D];
+}
+template <int D, int ROWS, int JC>
+__global__ void __launch_bounds__(128) slot_accum_warp_kernel(int ns, const int* __restrict__ ent_ptr, const int* __restrict__ ent, const int* __restrict__ slot_cam,
+                                                              const int* __restrict__ slot_lm, const double* __restrict__ J, const double* __restrict__ scale_c,
+                                                              const double* __restrict__ scale_l, double* __restrict__ E) {
+  PDL_PROLOGUE();
+  slot_accum_warp_body<D, ROWS, JC>(blockIdx.x, ns, ent_ptr, ent, slot_cam, slot_lm, J, scale_c, scale_l, E);
+}
+
+// V, g per landmark and E per (landmark, camera) slot are independent sums over the same Jacobian: one launch, the first
+// g_lm CTAs run the landmark bodies, the rest the slot bodies (two dependent-in-stream launches would run back to back).
+template <int D, int ROWS, int JC, bool WARP>
+__global__ void __launch_bounds__(128) accum_merged_kernel(int g_lm, int nv, const int* __restrict__ obs_ptr, const int* __restrict__ obs,
+                                                           const double* __restrict__ J, const double* __restrict__ r, const double* __restrict__ scale_l,
+                                                           double* __restrict__ V, double* __restrict__ g, int ns, const int* __restrict__ ent_ptr,
+                                                           const int* __restrict__ ent, const int* __restrict__ slot_cam, const int* __restrict__ slot_lm,
+                                                           const double* __restrict__ scale_c, double* __restrict__ E) {
+  PDL_PROLOGUE();
+  if ((int)blockIdx.x < g_lm) {
+    if (WARP) lm_accum_warp_body<D, ROWS, JC>(blockIdx.x, nv, obs_ptr, obs, J, r, scale_l, V, g);
+    else lm_accum_body<D, ROWS, JC>(blockIdx.x, nv, obs_ptr, obs, J, r, scale_l, V, g);
+  } else {
+    if (WARP) slot_accum_warp_body<D, ROWS, JC>(blockIdx.x - g_lm, ns, ent_ptr, ent, slot_cam, slot_lm, J, scale_c, scale_l, E);
+    else slot_accum_body<D, ROWS, JC>(blockIdx.x - g_lm, ns, ent_ptr, ent, slot_cam, slot_lm, J, scale_c, scale_l, E);
+  }
 }
 
 __device__ __forceinline__ double lm_damp(double d, double inv_radius) { return fmin(fmax(d, 1e-6), 1e32) * inv_radius; }
@@ -353,11 +395,10 @@ struct BlockArgs {
 // G = 8 for the off-diagonal ones with ~35): the fixed cost of a block is the butterfly reduction of its 36 partial
 // sums (36 x log2(G) 64-bit shuffles), which dominated when every block had a whole warp.
 template <int G>
-__global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int* __restrict__ list, int nlist) {
-  PDL_PROLOGUE();
+__device__ __forceinline__ void schur_block_body(const unsigned bid, BlockArgs A, const int* __restrict__ list, int nlist) {
   static_assert(G == 8 || G == 32 || G == 128, "group size");
   __shared__ double xs[G == 128 ? 4 * 54 : 1];   // G == 128 (one CTA per block): cross-warp stage of the reduction
-  const int gi = (blockIdx.x * blockDim.x + threadIdx.x) / G, lane = threadIdx.x & (G - 1);
+  const int gi = (bid * blockDim.x + threadIdx.x) / G, lane = threadIdx.x & (G - 1);
   const bool valid = gi < nlist;           // lanes of an empty group still take part in the full-warp shuffles
   const int blk = valid ? (list ? list[gi] : gi) : 0;   // list == NULL: every block, in order
   const int a = A.blk_a[blk], b = A.blk_b[blk];
@@ -505,6 +546,19 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int
       if (lane == k) { A.udiag[6 * a + k] = dd[k]; A.bvec[6 * a + k] = gr[k] - bred[k]; A.graw[6 * a + k] = gr[k] / sa[k]; }
   }
 }
+template <int G>
+__global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int* __restrict__ list, int nlist) {
+  PDL_PROLOGUE();
+  schur_block_body<G>(blockIdx.x, A, list, nlist);
+}
+
+// Diagonal blocks (a CTA each) and off-diagonal blocks (8 lanes each) in ONE launch: CTAs [0, n_diag) take the diagonal list.
+__global__ void __launch_bounds__(128) schur_merged_kernel(BlockArgs A, const int* __restrict__ diag_list, int n_diag,
+                                                           const int* __restrict__ off_list, int n_off) {
+  PDL_PROLOGUE();
+  if ((int)blockIdx.x < n_diag) schur_block_body<128>(blockIdx.x, A, diag_list, n_diag);
+  else schur_block_body<8>(blockIdx.x - n_diag, A, off_list, n_off);
+}
 
 // The LM damping term clamp(diag(J'J))/radius must see the GLOBAL diagonal: ranks exchange un-damped
 // blocks plus udiag, and the damping is added while scattering into the dense matrix.
@@ -533,11 +587,10 @@ __global__ void scatter_kernel(ScatterArgs S) {
 
 // ---- landmark back-substitution, steps and candidate parameters ---------------------------------------
 template <int D>
-__global__ void backsub_kernel(int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
+__device__ __forceinline__ void backsub_body(const unsigned bid, int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
                                const double* __restrict__ Vinv, const double* __restrict__ g, const double* __restrict__ yc,
                                const double* __restrict__ scale_l, double* __restrict__ delta_l) {
-  PDL_PROLOGUE();
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = bid * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   double t[D];
 #pragma unroll
@@ -558,13 +611,19 @@ __global__ void backsub_kernel(int nv, const int* __restrict__ slot_ptr, const i
     delta_l[v * D + a] = -y * scale_l[v * D + a];
   }
 }
+template <int D>
+__global__ void backsub_kernel(int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
+                               const double* __restrict__ Vinv, const double* __restrict__ g, const double* __restrict__ yc,
+                               const double* __restrict__ scale_l, double* __restrict__ delta_l) {
+  PDL_PROLOGUE();
+  backsub_body<D>(blockIdx.x, nv, slot_ptr, slot_cam, E, Vinv, g, yc, scale_l, delta_l);
+}
 
 // cameras: delta_c = -y_c * scale ; x_c = Plus(x, delta); partial norms (one block, cams are few)
-__global__ void __launch_bounds__(256) candidate_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x,
+__device__ __forceinline__ void candidate_cams_body(const unsigned bid, int n_cams, const int* __restrict__ camslot, const double* __restrict__ x,
                                                              const double* __restrict__ yc, const double* __restrict__ scale_c,
                                                              double* __restrict__ delta_c, double* __restrict__ xc,
                                                              double* __restrict__ sc, double norm_weight) {
-  PDL_PROLOGUE();
   __shared__ double sred[256];
   double step2 = 0.0, cn2 = 0.0;
   for (int k = threadIdx.x; k < n_cams; k += 256) {
@@ -602,14 +661,20 @@ __global__ void __launch_bounds__(256) candidate_cams_kernel(int n_cams, const i
   const double b = block_sum_256(cn2, sred);
   if (threadIdx.x == 0) { sc[SC_STEP2] = a * norm_weight; sc[SC_CNORM2] = b * norm_weight; }
 }
+__global__ void __launch_bounds__(256) candidate_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x,
+                                                             const double* __restrict__ yc, const double* __restrict__ scale_c,
+                                                             double* __restrict__ delta_c, double* __restrict__ xc,
+                                                             double* __restrict__ sc, double norm_weight) {
+  PDL_PROLOGUE();
+  candidate_cams_body(blockIdx.x, n_cams, camslot, x, yc, scale_c, delta_c, xc, sc, norm_weight);
+}
 
 template <int D>
-__global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
+__device__ __forceinline__ void candidate_lm_body(const unsigned bid, int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
                                                            const double* __restrict__ delta_l, double* __restrict__ xc,
                                                            double* __restrict__ parts /*2 per block*/) {
-  PDL_PROLOGUE();
   __shared__ double sred[256];
-  const int v = blockIdx.x * 256 + threadIdx.x;
+  const int v = bid * 256 + threadIdx.x;
   double step2 = 0.0, cn2 = 0.0;
   if (v < nv) {
     const int gidx = v_gl[v];
@@ -624,7 +689,14 @@ __global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __
   const double a = block_sum_256(step2, sred);
   __syncthreads();
   const double b = block_sum_256(cn2, sred);
-  if (threadIdx.x == 0) { parts[2 * blockIdx.x] = a; parts[2 * blockIdx.x + 1] = b; }
+  if (threadIdx.x == 0) { parts[2 * bid] = a; parts[2 * bid + 1] = b; }
+}
+template <int D>
+__global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
+                                                           const double* __restrict__ delta_l, double* __restrict__ xc,
+                                                           double* __restrict__ parts /*2 per block*/) {
+  PDL_PROLOGUE();
+  candidate_lm_body<D>(blockIdx.x, nv, v_gl, x, delta_l, xc, parts);
 }
 
 // squared norm of the free ambient parameters (x_norm at start)
@@ -686,10 +758,9 @@ __global__ void __launch_bounds__(256) model_cost_kernel(int n, const int* __res
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
   atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
-__global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, const double* __restrict__ graw,
+__device__ __forceinline__ void gmax_cams_body(const unsigned bid, int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, const double* __restrict__ graw,
                                  double* __restrict__ mx) {
-  PDL_PROLOGUE();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = bid * blockDim.x + threadIdx.x;
   if (k >= n_cams) return;
   const int s = camslot[k];
   if (s < 0) return;
@@ -710,14 +781,89 @@ __global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, co
   for (int c = 3; c < 6; ++c) m = fmax(m, fabs(graw[6 * s + c]));
   atomic_max_nonneg(mx + MX_GMAX, m);
 }
-__global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
+__global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, const double* __restrict__ graw,
+                                 double* __restrict__ mx) {
   PDL_PROLOGUE();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  gmax_cams_body(blockIdx.x, n_cams, camslot, x, graw, mx);
+}
+__device__ __forceinline__ void gmax_lm_body(const unsigned bid, int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
+  const int i = bid * blockDim.x + threadIdx.x;
   // max over the bit patterns (what the atomic does; keeps a NaN visible), one atomic per warp instead of per landmark
   unsigned long long m = i < n ? (unsigned long long)__double_as_longlong(fabs(g_scaled[i] / scale[i])) : 0ull;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(mx + MX_GMAX), m);
+}
+__global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
+  PDL_PROLOGUE();
+  gmax_lm_body(blockIdx.x, n, g_scaled, scale, mx);
+}
+
+// ---- everything between the reduced-system solve and the candidate evaluation, in ONE launch ---------------------------
+// CTA ranges: landmark back-substitution fused with the candidate landmark values and their norm partials (points, then
+// planes), the candidate cameras (one CTA), and the gradient max-norm pieces (cameras, points, planes) — six launches before.
+template <int D>
+__device__ __forceinline__ void backsub_candidate_body(const unsigned bid, int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam,
+                                                       const double* __restrict__ E, const double* __restrict__ Vinv, const double* __restrict__ g,
+                                                       const double* __restrict__ yc, const double* __restrict__ scale_l, double* __restrict__ delta_l,
+                                                       const int* __restrict__ v_gl, const double* __restrict__ x, double* __restrict__ xc,
+                                                       double* __restrict__ parts) {
+  __shared__ double sred[256];
+  const int v = bid * 256 + threadIdx.x;
+  double step2 = 0.0, cn2 = 0.0;
+  if (v < nv) {
+    double t[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) t[a] = g[v * D + a];
+    for (int s = slot_ptr[v]; s < slot_ptr[v + 1]; ++s) {
+      const double* y = yc + 6 * slot_cam[s];
+      const double* Es = E + (size_t)s * 6 * D;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int a = 0; a < D; ++a) t[a] -= Es[c * D + a] * y[c];
+    }
+    const int gidx = v_gl[v];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double y = 0.0;
+#pragma unroll
+      for (int b = 0; b < D; ++b) y += Vinv[(size_t)v * D * D + a * D + b] * t[b];
+      const double d = -y * scale_l[v * D + a];
+      delta_l[v * D + a] = d;
+      const double val = x[(size_t)gidx * D + a] + d;
+      xc[(size_t)gidx * D + a] = val;
+      step2 += d * d; cn2 += val * val;
+    }
+  }
+  const double a = block_sum_256(step2, sred);
+  __syncthreads();
+  const double b = block_sum_256(cn2, sred);
+  if (threadIdx.x == 0) { parts[2 * bid] = a; parts[2 * bid + 1] = b; }
+}
+
+struct PostArgs {
+  int nvp; const int* sp_ptr; const int* sp_cam; const double* Ep; const double* Vinvp; const double* gp; const double* scale_vp; double* delta_vp;
+  const int* vp_gl; const double* x_rho; double* c_rho;
+  int nvt; const int* st_ptr; const int* st_cam; const double* Et; const double* Vinvt; const double* gt; const double* scale_vt; double* delta_vt;
+  const int* vt_gl; const double* x_theta; double* c_theta;
+  const double* yc; double* parts_step;
+  int K; const int* camslot; const double* x_cams; const double* scale_c; double* delta_c; double* c_cams; double* sc; double norm_weight;
+  const double* graw; double* mx;
+  int b_p, b_t, b_cam, b_gc, b_gp;   // CTA range ends: points | planes | candidate cameras | gmax cameras | gmax points | (rest) gmax planes
+};
+__global__ void __launch_bounds__(256) post_solve_kernel(PostArgs a) {
+  PDL_PROLOGUE();
+  const int b = blockIdx.x;
+  if (b < a.b_p)
+    backsub_candidate_body<1>(b, a.nvp, a.sp_ptr, a.sp_cam, a.Ep, a.Vinvp, a.gp, a.yc, a.scale_vp, a.delta_vp, a.vp_gl, a.x_rho, a.c_rho, a.parts_step);
+  else if (b < a.b_t)
+    backsub_candidate_body<3>(b - a.b_p, a.nvt, a.st_ptr, a.st_cam, a.Et, a.Vinvt, a.gt, a.yc, a.scale_vt, a.delta_vt, a.vt_gl, a.x_theta, a.c_theta,
+                              a.parts_step + 2 * a.b_p);
+  else if (b < a.b_cam) candidate_cams_body(0, a.K, a.camslot, a.x_cams, a.yc, a.scale_c, a.delta_c, a.c_cams, a.sc, a.norm_weight);
+  else if (b < a.b_gc) gmax_cams_body(b - a.b_cam, a.K, a.camslot, a.x_cams, a.graw, a.mx);
+  else if (b < a.b_gp) gmax_lm_body(b - a.b_gc, a.nvp, a.gp, a.scale_vp, a.mx);
+  else gmax_lm_body(b - a.b_gp, 3 * a.nvt, a.gt, a.scale_vt, a.mx);
 }
 
 // ---- end of an LM iteration's device work --------------------------------------------------------------------------
@@ -964,12 +1110,14 @@ static BlockLists block_lists(Solver& S) {
 static int accumulate_landmarks(Solver& S) {
   cudaStream_t st = S.ctx->stream;
   if (S.nvp) {
-    LAUNCH(launch_k(lm_accum_kernel<1, 2, 13>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
-    if (S.nsp) LAUNCH(launch_k(slot_accum_kernel<1, 2, 13>, grid_for(S.nsp, 128), 128, 0, st, S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.pJ.p, S.scale_c.p, S.scale_vp.p, S.Ep.p));
+    const int g1 = grid_for(S.nvp, 128), g2 = grid_for(S.nsp, 128);
+    LAUNCH(launch_k(accum_merged_kernel<1, 2, 13, false>, g1 + g2, 128, 0, st, g1, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p,
+                    S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.scale_c.p, S.Ep.p));
   }
   if (S.nvt) {
-    LAUNCH(launch_k(lm_accum_warp_kernel<3, 8, 15>, grid_for(S.nvt * 32, 128), 128, 0, st, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
-    if (S.nst) LAUNCH(launch_k(slot_accum_warp_kernel<3, 8, 15>, grid_for(S.nst * 32, 128), 128, 0, st, S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.tJ.p, S.scale_c.p, S.scale_vt.p, S.Et.p));
+    const int g1 = grid_for(S.nvt * 32, 128), g2 = grid_for(S.nst * 32, 128);
+    LAUNCH(launch_k(accum_merged_kernel<3, 8, 15, true>, g1 + g2, 128, 0, st, g1, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p,
+                    S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.scale_c.p, S.Et.p));
   }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
@@ -1023,8 +1171,7 @@ static int compute_step(Solver& S, double radius) {
     if (S.est_entries > 96 * (long long)S.nblk) {
       LAUNCH(launch_k(schur_block_kernel<128>, S.nblk, 128, 0, st, B, nullptr, S.nblk));
     } else {
-      LAUNCH(launch_k(schur_block_kernel<128>, S.nc, 128, 0, st, B, S.diag_blk.p, S.nc));
-      if (S.noff) LAUNCH(launch_k(schur_block_kernel<8>, grid_for(S.noff * 8, 128), 128, 0, st, B, S.offdiag_blk.p, S.noff));
+      LAUNCH(launch_k(schur_merged_kernel, S.nc + grid_for(S.noff * 8, 128), 128, 0, st, B, S.diag_blk.p, S.nc, S.offdiag_blk.p, S.noff));
     }
     TSL_CHECK_LAUNCH();
   }
@@ -1044,13 +1191,21 @@ static int compute_step(Solver& S, double radius) {
     if (rc) return rc;
   }
   mark(S, 5);  // back-substitution + candidate
-  if (S.nvp) LAUNCH(launch_k(backsub_kernel<1>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.sp_ptr.p, S.sp_cam.p, S.Ep.p, S.Vinvp.p, S.gp.p, S.yc.p, S.scale_vp.p, S.delta_vp.p));
-  if (S.nvt) LAUNCH(launch_k(backsub_kernel<3>, grid_for(S.nvt, 128), 128, 0, st, S.nvt, S.st_ptr.p, S.st_cam.p, S.Et.p, S.Vinvt.p, S.gt.p, S.yc.p, S.scale_vt.p, S.delta_vt.p));
-  LAUNCH(launch_k(candidate_cams_kernel, 1, 256, 0, st, S.K, S.camslot_d.p, S.x_cams, S.yc.p, S.scale_c.p, S.delta_c.p, S.c_cams, S.sc, ctx->rank == 0 ? 1.0 : 0.0));
-  const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
-  double* parts = S.parts_step.p;   // summed onto sc[SC_STEP2], sc[SC_CNORM2] by iteration_tail_kernel
-  if (S.nvp) LAUNCH(launch_k(candidate_lm_kernel<1>, gvp, 256, 0, st, S.nvp, S.vp_gl.p, S.x_rho, S.delta_vp.p, S.c_rho, parts));
-  if (S.nvt) LAUNCH(launch_k(candidate_lm_kernel<3>, gvt, 256, 0, st, S.nvt, S.vt_gl.p, S.x_theta, S.delta_vt.p, S.c_theta, parts + 2 * gvp));
+  {
+    const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
+    PostArgs a;
+    a.nvp = S.nvp; a.sp_ptr = S.sp_ptr.p; a.sp_cam = S.sp_cam.p; a.Ep = S.Ep.p; a.Vinvp = S.Vinvp.p; a.gp = S.gp.p; a.scale_vp = S.scale_vp.p;
+    a.delta_vp = S.delta_vp.p; a.vp_gl = S.vp_gl.p; a.x_rho = S.x_rho; a.c_rho = S.c_rho;
+    a.nvt = S.nvt; a.st_ptr = S.st_ptr.p; a.st_cam = S.st_cam.p; a.Et = S.Et.p; a.Vinvt = S.Vinvt.p; a.gt = S.gt.p; a.scale_vt = S.scale_vt.p;
+    a.delta_vt = S.delta_vt.p; a.vt_gl = S.vt_gl.p; a.x_theta = S.x_theta; a.c_theta = S.c_theta;
+    a.yc = S.yc.p; a.parts_step = S.parts_step.p;   // pairs summed onto sc[SC_STEP2], sc[SC_CNORM2] by iteration_tail_kernel
+    a.K = S.K; a.camslot = S.camslot_d.p; a.x_cams = S.x_cams; a.scale_c = S.scale_c.p; a.delta_c = S.delta_c.p; a.c_cams = S.c_cams; a.sc = S.sc;
+    a.norm_weight = ctx->rank == 0 ? 1.0 : 0.0;
+    a.graw = S.graw; a.mx = S.mx.p;   // graw (cams) comes from the reduced-system build and is already all-reduced; landmark gradients are local
+    a.b_p = gvp; a.b_t = a.b_p + gvt; a.b_cam = a.b_t + 1; a.b_gc = a.b_cam + grid_for(S.K, 256); a.b_gp = a.b_gc + grid_for(S.nvp, 256);
+    const int grid = a.b_gp + grid_for(3 * S.nvt, 256);
+    LAUNCH(launch_k(post_solve_kernel, grid, 256, 0, st, a));
+  }
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -1076,15 +1231,6 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
   return TSLAM_OK;
 }
 
-static int gradient_max_norm(Solver& S) {
-  cudaStream_t st = S.ctx->stream;
-  // graw (cams) is produced by schur_block_kernel and already all-reduced; landmark gradients are local
-  LAUNCH(launch_k(gmax_cams_kernel, grid_for(S.K, 128), 128, 0, st, S.K, S.camslot_d.p, S.x_cams, S.graw, S.mx.p));
-  if (S.nvp) LAUNCH(launch_k(gmax_lm_kernel, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.gp.p, S.scale_vp.p, S.mx.p));
-  if (S.nvt) LAUNCH(launch_k(gmax_lm_kernel, grid_for(3 * S.nvt, 256), 256, 0, st, 3 * S.nvt, S.gt.p, S.scale_vt.p, S.mx.p));
-  TSL_CHECK_LAUNCH();
-  return TSLAM_OK;
-}
 
 // Spins on the sequence number the device writes after the iteration's scalars (page-locked, device-mapped host memory);
 // the stream is queried now and then so that a failed launch or a sticky error ends the wait instead of hanging it.
@@ -1156,7 +1302,7 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
     if (S.nc + S.nl + S.npl == 0) { term = TSLAM_TERM_GRADIENT_TOL; break; }   // nothing to optimise: the (empty) gradient passes Ceres' first test
     // ---- linear solve + candidate (speculative: the gradient test for THIS iteration is read back with it) ----
     if ((rc = compute_step(S, radius))) return rc;
-    if ((rc = gradient_max_norm(S))) return rc;
+    // (the gradient max-norm pieces run inside post_solve_kernel)
     if ((rc = model_and_candidate_cost(S, jac_mode))) return rc;
     if (ctx->world > 1) {  // reduce a COPY: the local slots (cost at x, x-norm) persist across iterations
       TSL_CUDA(cudaMemcpyAsync(S.scr.p, S.sc, SC_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
