@@ -940,7 +940,10 @@ struct Solver : SolverIndex {
   tslam_dev_problem* d = nullptr;
   // values
   DevBuf<double> xc_cams, xc_rho, xc_theta;
-  DevBuf<double> pr, pJ, tr, tJ, cr_p, cr_t;   // cr_*: candidate residual scratch
+  DevBuf<double> pr, pJ, tr, tJ, cr_p, cr_t, pJ2, tJ2;   // two (residual, Jacobian) sets: linearisation point and candidate
+  double *rp = nullptr, *Jp = nullptr, *rt = nullptr, *Jt = nullptr;        // current linearisation point
+  double *rp2 = nullptr, *Jp2 = nullptr, *rt2 = nullptr, *Jt2 = nullptr;    // candidate (swapped in when a step is accepted)
+  bool spec_J = false;   // evaluate the Jacobian together with the candidate cost (saves the re-evaluation after an accepted step)
   DevBuf<double> scale_c, scale_vp, scale_vt, colnorm_c;
   DevBuf<double> Vp, gp, Vinvp, Vt, gt, Vinvt, Ep, Et;
   DevBuf<double> red;        // [Sblk | b | graw | udiag]  (one all-reduce)
@@ -1035,8 +1038,8 @@ static int analyze_and_upload(Solver& S) {
   const int K = S.K, nc = S.nc, lp = S.lp, lt = S.lt;
   // ---- value buffers ----
   TSL_CUDA(S.xc_cams.reserve(7 * (size_t)K)); TSL_CUDA(S.xc_rho.reserve(d->n_points)); TSL_CUDA(S.xc_theta.reserve(3 * (size_t)d->n_planes));
-  TSL_CUDA(S.pr.reserve(2 * (size_t)lp)); TSL_CUDA(S.pJ.reserve(26 * (size_t)lp)); TSL_CUDA(S.cr_p.reserve(2 * (size_t)lp));
-  TSL_CUDA(S.tr.reserve(8 * (size_t)lt)); TSL_CUDA(S.tJ.reserve(120 * (size_t)lt)); TSL_CUDA(S.cr_t.reserve(8 * (size_t)lt));
+  TSL_CUDA(S.pr.reserve(2 * (size_t)lp)); TSL_CUDA(S.pJ.reserve(26 * (size_t)lp)); TSL_CUDA(S.cr_p.reserve(2 * (size_t)lp)); TSL_CUDA(S.pJ2.reserve(26 * (size_t)lp));
+  TSL_CUDA(S.tr.reserve(8 * (size_t)lt)); TSL_CUDA(S.tJ.reserve(120 * (size_t)lt)); TSL_CUDA(S.cr_t.reserve(8 * (size_t)lt)); TSL_CUDA(S.tJ2.reserve(120 * (size_t)lt));
   TSL_CUDA(S.scale_c.reserve(6 * (size_t)nc)); TSL_CUDA(S.colnorm_c.reserve(6 * (size_t)nc));
   TSL_CUDA(S.scale_vp.reserve(S.nvp)); TSL_CUDA(S.scale_vt.reserve(3 * (size_t)S.nvt));
   TSL_CUDA(S.Vp.reserve(S.nvp)); TSL_CUDA(S.gp.reserve(S.nvp)); TSL_CUDA(S.Vinvp.reserve(S.nvp));
@@ -1085,13 +1088,13 @@ static inline int grid_for(int n, int b) { return n > 0 ? (n + b - 1) / b : 0; }
 
 // Evaluate residuals (+ Jacobians) at (cams, rho, theta); cost -> sc[cost_slot], sc[cost_slot+1]
 static int eval_at(Solver& S, const double* cams, const double* rho, const double* theta, bool want_J, int jac_mode, int cost_slot,
-                   double* pr, double* tr, bool defer_sum = false) {
+                   double* pr, double* tr, double* pJ, double* tJ, bool defer_sum = false) {
   tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
   int np = 0, nt = 0;
   double* parts = S.parts.p;
-  int rc = launch_eval_points_robust(ctx, d, cams, rho, S.p_active.p, pr, want_J ? S.pJ.p : nullptr, parts, &np);
+  int rc = launch_eval_points_robust(ctx, d, cams, rho, S.p_active.p, pr, want_J ? pJ : nullptr, parts, &np);
   if (rc) return rc;
-  rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? S.tJ.p : nullptr, parts + 2 * np, &nt);
+  rc = launch_eval_text_robust(ctx, d, cams, theta, S.t_active.p, S.t_fmask.p, jac_mode, tr, want_J ? tJ : nullptr, parts + 2 * np, &nt);
   if (rc) return rc;
   S.tail_n_cand = np + nt;
   if (!defer_sum) LAUNCH(launch_k(sum_parts_pair_kernel, 2, 256, 0, ctx->stream, parts, np + nt, S.sc + cost_slot, S.sc + cost_slot + 1, 0));
@@ -1111,12 +1114,12 @@ static int accumulate_landmarks(Solver& S) {
   cudaStream_t st = S.ctx->stream;
   if (S.nvp) {
     const int g1 = grid_for(S.nvp, 128), g2 = grid_for(S.nsp, 128);
-    LAUNCH(launch_k(accum_merged_kernel<1, 2, 13, false>, g1 + g2, 128, 0, st, g1, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p,
+    LAUNCH(launch_k(accum_merged_kernel<1, 2, 13, false>, g1 + g2, 128, 0, st, g1, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.Jp, S.rp, S.scale_vp.p, S.Vp.p, S.gp.p,
                     S.nsp, S.spe_ptr.p, S.spe.p, S.sp_cam.p, S.sp_lm.p, S.scale_c.p, S.Ep.p));
   }
   if (S.nvt) {
     const int g1 = grid_for(S.nvt * 32, 128), g2 = grid_for(S.nst * 32, 128);
-    LAUNCH(launch_k(accum_merged_kernel<3, 8, 15, true>, g1 + g2, 128, 0, st, g1, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p,
+    LAUNCH(launch_k(accum_merged_kernel<3, 8, 15, true>, g1 + g2, 128, 0, st, g1, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.Jt, S.rt, S.scale_vt.p, S.Vt.p, S.gt.p,
                     S.nst, S.ste_ptr.p, S.ste.p, S.st_cam.p, S.st_lm.p, S.scale_c.p, S.Et.p));
   }
   TSL_CHECK_LAUNCH();
@@ -1128,7 +1131,7 @@ static int compute_jacobi_scaling(Solver& S) {
   const int nc = S.nc;
   // unscaled column norms: cameras via the diagonal blocks' direct entries, landmarks via V with scale == 1
   if (nc) {
-    LAUNCH(launch_k(cam_colnorm_kernel, grid_for(nc * 32, 128), 128, 0, st, nc, S.diag_blk.p, block_lists(S), S.pJ.p, S.tJ.p, S.colnorm_c.p));
+    LAUNCH(launch_k(cam_colnorm_kernel, grid_for(nc * 32, 128), 128, 0, st, nc, S.diag_blk.p, block_lists(S), S.Jp, S.Jt, S.colnorm_c.p));
     TSL_CHECK_LAUNCH();
     int rc = comm_allreduce_sum(S.ctx, S.colnorm_c.p, 6 * (size_t)nc);
     if (rc) return rc;
@@ -1136,12 +1139,12 @@ static int compute_jacobi_scaling(Solver& S) {
   }
   if (S.nvp) {
     LAUNCH(launch_k(fill_kernel, grid_for(S.nvp, 256), 256, 0, st, S.scale_vp.p, S.nvp, 1.0));
-    LAUNCH(launch_k(lm_accum_kernel<1, 2, 13>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.pJ.p, S.pr.p, S.scale_vp.p, S.Vp.p, S.gp.p));
+    LAUNCH(launch_k(lm_accum_kernel<1, 2, 13>, grid_for(S.nvp, 128), 128, 0, st, S.nvp, S.vp_obs_ptr.p, S.vp_obs.p, S.Jp, S.rp, S.scale_vp.p, S.Vp.p, S.gp.p));
     LAUNCH(launch_k(lm_scale_kernel<1>, grid_for(S.nvp, 256), 256, 0, st, S.nvp, S.Vp.p, S.scale_vp.p));
   }
   if (S.nvt) {
     LAUNCH(launch_k(fill_kernel, grid_for(3 * S.nvt, 256), 256, 0, st, S.scale_vt.p, 3 * S.nvt, 1.0));
-    LAUNCH(launch_k(lm_accum_warp_kernel<3, 8, 15>, grid_for(S.nvt * 32, 128), 128, 0, st, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.tJ.p, S.tr.p, S.scale_vt.p, S.Vt.p, S.gt.p));
+    LAUNCH(launch_k(lm_accum_warp_kernel<3, 8, 15>, grid_for(S.nvt * 32, 128), 128, 0, st, S.nvt, S.vt_obs_ptr.p, S.vt_obs.p, S.Jt, S.rt, S.scale_vt.p, S.Vt.p, S.gt.p));
     LAUNCH(launch_k(lm_scale_kernel<3>, grid_for(3 * S.nvt, 256), 256, 0, st, S.nvt, S.Vt.p, S.scale_vt.p));
   }
   TSL_CHECK_LAUNCH();
@@ -1162,7 +1165,7 @@ static int compute_step(Solver& S, double radius) {
   if (S.nblk) {
     BlockArgs B;
     B.nblk = S.nblk; B.blk_a = S.blk_a.p; B.blk_b = S.blk_b.p; B.L = block_lists(S);
-    B.pJ = S.pJ.p; B.pr = S.pr.p; B.tJ = S.tJ.p; B.tr = S.tr.p; B.scale_c = S.scale_c.p;
+    B.pJ = S.Jp; B.pr = S.rp; B.tJ = S.Jt; B.tr = S.rt; B.scale_c = S.scale_c.p;
     B.Ep = S.Ep.p; B.Vinvp = S.Vinvp.p; B.gp = S.gp.p; B.sp_lm = S.sp_lm.p;
     B.Et = S.Et.p; B.Vinvt = S.Vinvt.p; B.gt = S.gt.p; B.st_lm = S.st_lm.p;
     B.Sblk = S.Sblk; B.bvec = S.bvec; B.graw = S.graw; B.udiag = S.udiag;
@@ -1215,10 +1218,10 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
   mark(S, 6);  // model cost change + candidate cost
   const int gp = grid_for(S.lp, 256), gt = grid_for(S.lt, 256);
   double* parts = S.parts_mcc.p;
-  if (S.lp) LAUNCH(launch_k(model_cost_kernel<1, 2, 13>, gp, 256, 0, st, S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.pJ.p, S.pr.p, S.delta_c.p, S.delta_vp.p, parts));
-  if (S.lt) LAUNCH(launch_k(model_cost_kernel<3, 8, 15>, gt, 256, 0, st, S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.tJ.p, S.tr.p, S.delta_c.p, S.delta_vt.p, parts + gp));
+  if (S.lp) LAUNCH(launch_k(model_cost_kernel<1, 2, 13>, gp, 256, 0, st, S.lp, S.p_cs.p, S.p_hs.p, S.p_ls.p, S.Jp, S.rp, S.delta_c.p, S.delta_vp.p, parts));
+  if (S.lt) LAUNCH(launch_k(model_cost_kernel<3, 8, 15>, gt, 256, 0, st, S.lt, S.t_cs.p, S.t_hs.p, S.t_ls.p, S.Jt, S.rt, S.delta_c.p, S.delta_vt.p, parts + gp));
   TSL_CHECK_LAUNCH();
-  int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, false, jac_mode, SC_CAND, S.cr_p.p, S.cr_t.p, /*defer_sum=*/true);
+  int rc = eval_at(S, S.c_cams, S.c_rho, S.c_theta, S.spec_J, jac_mode, SC_CAND, S.rp2, S.rt2, S.Jp2, S.Jt2, /*defer_sum=*/true);
   if (rc) return rc;
   // the three sums of this iteration (+ the publish on one GPU) in one launch
   tslam_ctx* ctx = S.ctx;
@@ -1276,9 +1279,16 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
 
   TSL_CUDA(cudaMemsetAsync(S.mx.p, 0, MX_N * sizeof(double), st));
   TSL_CUDA(cudaMemsetAsync(S.fail.p, 0, sizeof(int), st));
+  S.rp = S.pr.p; S.Jp = S.pJ.p; S.rt = S.tr.p; S.Jt = S.tJ.p; S.rp2 = S.cr_p.p; S.Jp2 = S.pJ2.p; S.rt2 = S.cr_t.p; S.Jt2 = S.tJ2.p;
+  // Speculative Jacobian: worth it when a Jacobian costs about as much as a residual pass (closed forms); with Ceres-style
+  // central differences (35 functor calls per text block) a rejected step would waste far more than an accepted one saves.
+  {
+    static const bool spec_env = [] { const char* e = getenv("TSLAM_SPEC_J"); return !(e && e[0] == '0'); }();
+    S.spec_J = spec_env && (S.lt == 0 || jac_mode == TSLAM_JAC_ANALYTIC);
+  }
   // ---- iteration 0 ----
   mark(S, 0);
-  int rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.pr.p, S.tr.p);
+  int rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.rp, S.rt, S.Jp, S.Jt);
   if (rc) return rc;
   if ((rc = compute_jacobi_scaling(S))) return rc;
   if ((rc = accumulate_landmarks(S))) return rc;
@@ -1349,7 +1359,9 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
       std::swap(S.x_cams, S.c_cams); std::swap(S.x_rho, S.c_rho); std::swap(S.x_theta, S.c_theta);
       x_norm = std::sqrt(h[SC_CNORM2]);
       mark(S, 0);  // eval + J (the next iteration's linearisation point)
-      if ((rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.pr.p, S.tr.p))) return rc;
+      if (S.spec_J) {   // residuals and Jacobian of the accepted point were produced by the candidate evaluation
+        std::swap(S.rp, S.rp2); std::swap(S.Jp, S.Jp2); std::swap(S.rt, S.rt2); std::swap(S.Jt, S.Jt2);
+      } else if ((rc = eval_at(S, S.x_cams, S.x_rho, S.x_theta, true, jac_mode, SC_COST, S.rp, S.rt, S.Jp, S.Jt, /*defer_sum=*/true))) return rc;
       if ((rc = accumulate_landmarks(S))) return rc;
       x_cost = cand_cost;  // identical evaluation point; the device value is re-read next iteration for the trace only
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
@@ -1466,23 +1478,23 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
   DevBuf<double> fr;   // world > 1: the global residual vector, replicated after the all-reduce
   if (final_residuals || gate) {
     // Problem::Evaluate: loss-corrected residuals of every block, insertion order (Appendix A.6)
-    if ((rc = eval_at(*S, d.cams.p, d.rho.p, d.theta.p, false, opt->text_jac_mode, SC_CAND, S->cr_p.p, S->cr_t.p))) return rc;
+    if ((rc = eval_at(*S, d.cams.p, d.rho.p, d.theta.p, false, opt->text_jac_mode, SC_CAND, S->rp2, S->rt2, nullptr, nullptr))) return rc;
     const size_t total = 2 * (size_t)d.g_pobs + 8 * (size_t)d.g_tobs;
     if (ctx->world > 1) {
       TSL_CUDA(fr.reserve(total));
       TSL_CUDA(cudaMemsetAsync(fr.p, 0, total * sizeof(double), st));
-      if (S->lp) LAUNCH(launch_k(scatter_rows_kernel, (2 * S->lp + 255) / 256, 256, 0, st, S->lp, 2, S->gsel_p.p, S->cr_p.p, fr.p));
-      if (S->lt) LAUNCH(launch_k(scatter_rows_kernel, (8 * S->lt + 255) / 256, 256, 0, st, S->lt, 8, S->gsel_t.p, S->cr_t.p, fr.p + 2 * (size_t)d.g_pobs));
+      if (S->lp) LAUNCH(launch_k(scatter_rows_kernel, (2 * S->lp + 255) / 256, 256, 0, st, S->lp, 2, S->gsel_p.p, S->rp2, fr.p));
+      if (S->lt) LAUNCH(launch_k(scatter_rows_kernel, (8 * S->lt + 255) / 256, 256, 0, st, S->lt, 8, S->gsel_t.p, S->rt2, fr.p + 2 * (size_t)d.g_pobs));
       if ((rc = comm_allreduce_sum(ctx, fr.p, total))) return rc;
       if (final_residuals) TSL_CUDA(cudaMemcpyAsync(final_residuals, fr.p, total * sizeof(double), cudaMemcpyDeviceToHost, st));
       TSL_CUDA(cudaStreamSynchronize(st));
     } else if (final_residuals) {
-      if (S->lp) TSL_CUDA(cudaMemcpyAsync(final_residuals, S->cr_p.p, 2 * (size_t)S->lp * sizeof(double), cudaMemcpyDeviceToHost, st));
-      if (S->lt) TSL_CUDA(cudaMemcpyAsync(final_residuals + 2 * (size_t)d.g_pobs, S->cr_t.p, 8 * (size_t)S->lt * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (S->lp) TSL_CUDA(cudaMemcpyAsync(final_residuals, S->rp2, 2 * (size_t)S->lp * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (S->lt) TSL_CUDA(cudaMemcpyAsync(final_residuals + 2 * (size_t)d.g_pobs, S->rt2, 8 * (size_t)S->lt * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     if (gate) {   // chi^2 gates on the residuals where they are (src/optimizer.cc:1236-1302, 1616-1684)
-      const double* rp = ctx->world > 1 ? fr.p : S->cr_p.p;
-      const double* rt = ctx->world > 1 ? fr.p + 2 * (size_t)d.g_pobs : S->cr_t.p;
+      const double* rp = ctx->world > 1 ? fr.p : S->rp2;
+      const double* rt = ctx->world > 1 ? fr.p + 2 * (size_t)d.g_pobs : S->rt2;
       if ((rc = gate_device(ctx, rp, rt, d.g_pobs, d.g_tobs, gate->t_obj, gate->obj_size, gate->n_obj, gate->opt, gate->pt_bad, gate->tf_bad,
                             gate->obj_bad, gate->counts))) return rc;
     }
