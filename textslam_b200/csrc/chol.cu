@@ -38,7 +38,7 @@ namespace tsl {
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
 __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
                                                                 int* __restrict__ fail, double* __restrict__ Linv) {
-  PDL_PROLOGUE();
+  PDL_TRIGGER();
   // one CTA per (panel j, row tile i) item of the current wave; i < 0 marks the CTA that stores L_jj^-1.
   // Every CTA factors the (small) diagonal tile redundantly straight from A: nobody writes A_jj in this launch.
   extern __shared__ __align__(16) double smem[];
@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restri
   double* sX = smem + NB * LD2;        // 64 x LD2: row tile, or identity -> L_jj^-T
   double* sLt = smem + 2 * NB * LD2;   // 64 x LD2: transposes of the two 32x32 diagonal blocks of L_jj
   __shared__ double sinv[NB];
-  const int2 it = items[blockIdx.x];
+  const int2 it = items[blockIdx.x];   // schedule of the symbolic factorisation: constant, read before the dependency wait
+  PDL_WAIT();
   const int j = it.x;
   const double* Ajj = A + (size_t)j * NB * ld + (size_t)j * NB;
   double* Aij = it.y < 0 ? nullptr : A + (size_t)it.y * NB * ld + (size_t)j * NB;
@@ -86,12 +87,15 @@ __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restri
 constexpr int QB = 32;
 __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, int ld, const int2* __restrict__ targets,
                                                         const int* __restrict__ src_ptr, const int* __restrict__ src) {
-  PDL_PROLOGUE();
+  PDL_TRIGGER();
   extern __shared__ double smem[];
   double* sA = smem;               // 32 x SPAD: rows of X_i
   double* sB = smem + QB * SPAD;   // 32 x SPAD: rows of X_k
   const int t = blockIdx.x >> 2, qi = (blockIdx.x >> 1) & 1, qk = blockIdx.x & 1;
   const int2 tg = targets[t];
+  const int e_begin = src_ptr[t], e_end = src_ptr[t + 1];
+  int j_next = e_begin < e_end ? src[e_begin] : 0;   // the schedule is constant: read it before the dependency wait
+  PDL_WAIT();
   if (tg.x == tg.y && qk > qi) return;   // the upper-right quadrant of a diagonal tile is never read
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wr = (warp >> 1) * 16, wc = (warp & 1) * 16;
@@ -101,8 +105,17 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  for (int e = src_ptr[t]; e < src_ptr[t + 1]; ++e) {
-    const int j = src[e];
+  // the target quadrant is read now so that its latency hides behind the source loads and the MMA loop (no other CTA of
+  // this launch writes it, and the previous launch has completed)
+  double* C = A + ((size_t)tg.x * NB + QB * qi) * ld + (size_t)tg.y * NB + QB * qk;
+  double2 cv[2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) cv[a][b] = *reinterpret_cast<const double2*>(C + (size_t)(wr + 8 * a + g) * ld + wc + 8 * b + 2 * tgi);
+  for (int e = e_begin; e < e_end; ++e) {
+    const int j = j_next;
+    if (e + 1 < e_end) j_next = src[e + 1];
     const double* Xi = A + ((size_t)tg.x * NB + QB * qi) * ld + (size_t)j * NB;
     const double* Xk = A + ((size_t)tg.y * NB + QB * qk) * ld + (size_t)j * NB;
     __syncthreads();   // previous source fully consumed
@@ -133,16 +146,14 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
         for (int b = 0; b < 2; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
     }
   }
-  double* C = A + ((size_t)tg.x * NB + QB * qi) * ld + (size_t)tg.y * NB + QB * qk;
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int r = wr + 8 * a + g, c = wc + 8 * b + 2 * tgi;
-      double2* p = reinterpret_cast<double2*>(C + (size_t)r * ld + c);
-      double2 v = *p;
+      double2 v = cv[a][b];
       v.x -= acc[a][b][0]; v.y -= acc[a][b][1];
-      *p = v;
+      *reinterpret_cast<double2*>(C + (size_t)r * ld + c) = v;
     }
 }
 
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
 __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict__ A, int ld, int npanels, const int* __restrict__ panels,
                                                         const int* __restrict__ below_ptr, const int* __restrict__ below,
                                                         const double* __restrict__ Linv, const double* __restrict__ y, double* x, int* flags, int epoch) {
-  PDL_PROLOGUE();
+  PDL_TRIGGER();
   // 256 threads = 4 groups x 64 columns; group g takes the tiles e = g (mod 4) of the list, partial sums meet in smem
   __shared__ double sx[4][NB];
   __shared__ double st[4][NB];
@@ -164,11 +175,13 @@ __global__ void __launch_bounds__(256) backsolve_kernel(const double* __restrict
   const int j = panels[p];
   const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
   const int e0 = below_ptr[p], e1 = below_ptr[p + 1];
+  const int first_below = e0 + g < e1 ? below[e0 + g] : 0;   // schedule reads (constant) before the dependency wait
+  PDL_WAIT();
   // ---- prefetch what does not depend on other panels ----
   double lfirst[NB];
   const bool has_first = e0 + g < e1;
   if (has_first) {
-    const double* Lij = A + (size_t)below[e0 + g] * NB * ld + (size_t)j * NB + c;
+    const double* Lij = A + (size_t)first_below * NB * ld + (size_t)j * NB + c;
 #pragma unroll
     for (int r = 0; r < NB; ++r) lfirst[r] = Lij[(size_t)r * ld];
   }

@@ -37,6 +37,12 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 #define PDL_PROLOGUE() tsl::pdl_prologue()
+// Split form for kernels that can read launch-invariant index structures (uploaded once per problem, never written by a
+// kernel) before they have to wait for their predecessor: PDL_TRIGGER(); <index loads>; PDL_WAIT(); <everything else>.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define PDL_TRIGGER() tsl::pdl_trigger()
+#define PDL_WAIT() tsl::pdl_wait()
 bool pdl_enabled();   // capi.cu: TSLAM_PDL != "0"
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
