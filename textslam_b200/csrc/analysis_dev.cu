@@ -8,7 +8,14 @@
 // (47 x 47 tiles) stays on the host.
 //
 // Packing limits (device_analysis_supported): 2^24 free landmarks, 2^14 free cameras with nc^2 <= 2^24, 2^25 observations
-// per type; larger or sharded problems take the host path.
+// per type; larger problems take the host path.
+//
+// Landmark-sharded problems (multi-GPU global BA): a rank holds only the observations it owns, but the camera layout, the
+// camera order and the block numbering of the reduced system must be the same on every rank (the packed block buffer is
+// all-reduced element by element). Three small integer tables carry everything global — cameras in use (K), the
+// co-visibility distance histogram (K) and the K x K block flags — and are summed across the ranks with NCCL right after
+// the local passes that fill them; everything derived from them is then identical everywhere, the landmark side
+// (numbering, slots, gather lists) stays local by construction (an observation lives with its landmark).
 #include <cub/cub.cuh>
 #include <chrono>
 #include "ctx.cuh"
@@ -288,6 +295,7 @@ __global__ void schur_keys_kernel(int nq, const int* n_lm, const int* __restrict
     }
 }
 __global__ void zero_int_kernel(int* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 0; }
+__global__ void clamp01_kernel(int* p, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = p[i] != 0; }
 
 inline int grid(size_t n, int b) { return n > 0 ? (int)((n + b - 1) / b) : 1; }
 
@@ -295,7 +303,7 @@ inline int grid(size_t n, int b) { return n > 0 ? (int)((n + b - 1) / b) : 1; }
 
 bool device_analysis_supported(const tslam_ctx* ctx, const tslam_dev_problem* d) {
   static const bool force_host = getenv("TSLAM_HOST_ANALYSIS") != nullptr;
-  if (force_host || d->sharded || ctx->world > 1) return false;
+  if (force_host) return false;
   if ((size_t)d->n_cams * d->n_cams > ((size_t)1 << 24) || d->n_cams >= (1 << CAM_BITS)) return false;
   if (d->n_points >= (1 << 24) || d->n_planes >= (1 << 24)) return false;
   if (d->n_pobs >= (1 << 25) || d->n_tobs >= (1 << 25)) return false;
@@ -341,9 +349,13 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   TSL_CUDA(X.camslot_d.reserve(K));
   if (np) LAUNCH(flags_kernel<<<grid(np, 256), 256, 0, st>>>(np, d->p_cam.p, d->p_host.p, d->p_lm.p, d->cam_fixed.p, d->rho_fixed.p, X.p_active.p, cu.p, BP.lu.p));
   if (nt) LAUNCH(flags_kernel<<<grid(nt, 256), 256, 0, st>>>(nt, d->t_cam.p, d->t_host.p, d->t_plane.p, d->cam_fixed.p, d->theta_fixed.p, X.t_active.p, cu.p, BT.lu.p));
+  const bool multi = ctx->world > 1;
+  int rc;
+  if (multi && (rc = comm_allreduce_sum_i32(ctx, cu.p, K))) return rc;        // cameras used by anybody's active observations
   LAUNCH(cam_layout_kernel<<<1, 1024, 0, st>>>(K, cu.p, d->cam_fixed.p, X.camslot_d.p, cnt.p));
   if (np) LAUNCH(dist_hist_kernel<<<grid(np, 256), 256, 0, st>>>(np, d->p_cam.p, d->p_host.p, X.p_active.p, X.camslot_d.p, hist.p));
   if (nt) LAUNCH(dist_hist_kernel<<<grid(nt, 256), 256, 0, st>>>(nt, d->t_cam.p, d->t_host.p, X.t_active.p, X.camslot_d.p, hist.p));
+  if (multi && (rc = comm_allreduce_sum_i32(ctx, hist.p, K))) return rc;      // global co-visibility distances -> same camera order
   LAUNCH(nd_order_kernel<<<1, 32, 0, st>>>(K, X.camslot_d.p, hist.p, cnt.p, new_of_old.p, unit_order.p));
   TSL_CHECK_LAUNCH();
 
@@ -393,7 +405,6 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
     return TSLAM_OK;
   };
   Counts* C = cnt.p;
-  int rc;
   TypeIn inP{np, NP, d->p_cam.p, d->p_host.p, d->p_lm.p, d->rho_fixed.p}, inT{nt, NL, d->t_cam.p, d->t_host.p, d->t_plane.p, d->theta_fixed.p};
   if ((rc = type_pass(inP, BP, X.p_active.p, &C->nl, &C->n_ent_p, &C->nsp, &C->npairs_p, X.p_cs, X.p_hs, X.p_ls, nullptr, X.vp_gl, X.vp_obs_ptr, X.vp_obs,
                       X.sp_ptr, X.sp_cam, X.sp_lm, X.spe_ptr, X.spe))) return rc;
@@ -412,6 +423,10 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   if (nt) LAUNCH(mark_direct_kernel<<<grid(nt, 256), 256, 0, st>>>(nt, X.t_cs.p, X.t_hs.p, X.t_active.p, C, flag.p));
   if (np && NP) LAUNCH(mark_schur_kernel<<<grid(NP, 128), 128, 0, st>>>(NP, &C->nl, X.sp_ptr.p, X.sp_cam.p, C, flag.p));
   if (nt && NL) LAUNCH(mark_schur_kernel<<<grid(NL, 128), 128, 0, st>>>(NL, &C->npl, X.st_ptr.p, X.st_cam.p, C, flag.p));
+  if (multi) {   // global block pattern
+    if ((rc = comm_allreduce_sum_i32(ctx, flag.p, K2))) return rc;
+    LAUNCH(clamp01_kernel<<<grid(K2, 256), 256, 0, st>>>(flag.p, (int)K2));
+  }
   {
     size_t tb = temp_bytes;
     TSL_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, flag.p, pre.p, (int)K2, st)); ++g_launches;
@@ -419,13 +434,22 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   LAUNCH(block_count_kernel<<<grid(K2, 256), 256, 0, st>>>((int)K2, flag.p, pre.p, C, tile_nz_d.p, tn_cap));
   TSL_CHECK_LAUNCH();
   // ---- the one round trip: counts + tile pattern ----
+  DevBuf<int> gfree;   // multi-GPU: global number of free landmarks of each type (summary + termination test need the global count)
+  int gfree_h[2] = {0, 0};
+  if (multi) {
+    TSL_CUDA(gfree.reserve(2));
+    TSL_CUDA(cudaMemcpyAsync(gfree.p, &C->nl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    TSL_CUDA(cudaMemcpyAsync(gfree.p + 1, &C->npl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if ((rc = comm_allreduce_sum_i32(ctx, gfree.p, 2))) return rc;
+    TSL_CUDA(cudaMemcpyAsync(gfree_h, gfree.p, sizeof(gfree_h), cudaMemcpyDeviceToHost, st));
+  }
   Counts hc;
   std::vector<uint8_t> tile_h((size_t)tn_cap * tn_cap);
   TSL_CUDA(cudaMemcpyAsync(&hc, C, sizeof(Counts), cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaMemcpyAsync(tile_h.data(), tile_nz_d.p, tile_h.size(), cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaStreamSynchronize(st));
   auto T1 = std::chrono::steady_clock::now();
-  X.nc = hc.nc; X.nl = hc.nl; X.npl = hc.npl; X.nvp = hc.nl; X.nvt = hc.npl; X.nsp = hc.nsp; X.nst = hc.nst; X.nblk = hc.nblk; X.noff = hc.nblk - hc.nc;
+  X.nc = hc.nc; X.nl = multi ? gfree_h[0] : hc.nl; X.npl = multi ? gfree_h[1] : hc.npl; X.nvp = hc.nl; X.nvt = hc.npl; X.nsp = hc.nsp; X.nst = hc.nst; X.nblk = hc.nblk; X.noff = hc.nblk - hc.nc;
   X.est_entries = (long long)hc.npairs_p + hc.npairs_t + 3LL * ((long long)np + nt);
   X.n = 6 * X.nc;
   X.Tn = chol_workspace_dims(X.n, &X.ld, &X.rows);
@@ -476,6 +500,9 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   if ((rc = schur_lists(hc.npairs_p, NP, &C->nl, X.sp_ptr, X.sp_cam, BP.pair_off, X.bsp_ptr, X.bsp))) return rc;
   if ((rc = schur_lists(hc.npairs_t, NL, &C->npl, X.st_ptr, X.st_cam, BT.pair_off, X.bst_ptr, X.bst))) return rc;
   TSL_CHECK_LAUNCH();
+  if (d->sharded) {   // global observation index of each local one (final residual scatter)
+    TSL_CUDA(X.gsel_p.upload(d->gsel_p.data(), d->gsel_p.size(), st)); TSL_CUDA(X.gsel_t.upload(d->gsel_t.data(), d->gsel_t.size(), st));
+  }
   TSL_CUDA(cudaStreamSynchronize(st));   // the scratch buffers of this function are released on return
   auto T3 = std::chrono::steady_clock::now();
   if (lap_ms) {

@@ -924,12 +924,21 @@ __global__ void scatter_rows_kernel(int n, int width, const int* __restrict__ gs
   dst[(size_t)(gsel ? gsel[i] : i) * width + k] = src[t];
 }
 template <int D>
-__global__ void export_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x, double* __restrict__ out) {
+__global__ void export_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x, double* __restrict__ out, double* __restrict__ owners) {
   PDL_PROLOGUE();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nv * D) return;
   const int v = t / D, a = t - v * D;
   out[(size_t)v_gl[v] * D + a] = x[(size_t)v_gl[v] * D + a];
+  if (a == 0) owners[v_gl[v]] = 1.0;
+}
+// after the all-reduce: landmarks somebody owns take the reduced value, all others keep what the caller passed in
+template <int D>
+__global__ void merge_lm_kernel(int n, const double* __restrict__ reduced, const double* __restrict__ owners, double* __restrict__ x) {
+  PDL_PROLOGUE();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * D) return;
+  if (owners[t / D] > 0.0) x[t] = reduced[t];
 }
 
 // ================================================================================================
@@ -1454,22 +1463,23 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
   cudaStream_t st = ctx->stream;
   // ---- results back to the caller's arrays ----
   if (ctx->world > 1) {
-    // every rank owns a subset of the landmarks: zero the others, sum across ranks, keep originals where nobody owns
-    DevBuf<double> orho, oth;
-    TSL_CUDA(orho.reserve(d.n_points)); TSL_CUDA(oth.reserve(3 * (size_t)d.n_planes));
-    TSL_CUDA(cudaMemsetAsync(orho.p, 0, sizeof(double) * d.n_points, st));
-    TSL_CUDA(cudaMemsetAsync(oth.p, 0, sizeof(double) * 3 * (size_t)d.n_planes, st));
-    if (S->nvp) LAUNCH(launch_k(export_lm_kernel<1>, (S->nvp + 255) / 256, 256, 0, st, S->nvp, S->vp_gl.p, d.rho.p, orho.p));
-    if (S->nvt) LAUNCH(launch_k(export_lm_kernel<3>, (3 * S->nvt + 255) / 256, 256, 0, st, S->nvt, S->vt_gl.p, d.theta.p, oth.p));
-    if ((rc = comm_allreduce_sum(ctx, orho.p, d.n_points))) return rc;
-    if ((rc = comm_allreduce_sum(ctx, oth.p, 3 * (size_t)d.n_planes))) return rc;
-    std::vector<double> hr(d.n_points), ht(3 * (size_t)d.n_planes);
-    TSL_CUDA(cudaMemcpyAsync(hr.data(), orho.p, sizeof(double) * d.n_points, cudaMemcpyDeviceToHost, st));
-    TSL_CUDA(cudaMemcpyAsync(ht.data(), oth.p, sizeof(double) * 3 * (size_t)d.n_planes, cudaMemcpyDeviceToHost, st));
+    // every rank owns a subset of the landmarks: one packed buffer [rho | theta | owner count per point | per plane], zero where
+    // not owned, summed across the ranks; landmarks nobody owns (constant / unobserved) keep the caller's values
+    const size_t nP = (size_t)d.n_points, nT = (size_t)d.n_planes, total = 2 * nP + 4 * nT;
+    DevBuf<double> ob;
+    TSL_CUDA(ob.reserve(total));
+    TSL_CUDA(cudaMemsetAsync(ob.p, 0, sizeof(double) * (total ? total : 1), st));
+    double *orho = ob.p, *oth = ob.p + nP, *ownP = ob.p + nP + 3 * nT, *ownT = ownP + nP;
+    if (S->nvp) LAUNCH(launch_k(export_lm_kernel<1>, (S->nvp + 255) / 256, 256, 0, st, S->nvp, S->vp_gl.p, d.rho.p, orho, ownP));
+    if (S->nvt) LAUNCH(launch_k(export_lm_kernel<3>, (3 * S->nvt + 255) / 256, 256, 0, st, S->nvt, S->vt_gl.p, d.theta.p, oth, ownT));
+    if ((rc = comm_allreduce_sum(ctx, ob.p, total))) return rc;
+    if (nP) LAUNCH(launch_k(merge_lm_kernel<1>, (int)((nP + 255) / 256), 256, 0, st, (int)nP, orho, ownP, d.rho.p));
+    if (nT) LAUNCH(launch_k(merge_lm_kernel<3>, (int)((3 * nT + 255) / 256), 256, 0, st, (int)nT, oth, ownT, d.theta.p));
+    TSL_CHECK_LAUNCH();
     TSL_CUDA(cudaMemcpyAsync(p->cams, d.cams.p, sizeof(double) * 7 * (size_t)d.n_cams, cudaMemcpyDeviceToHost, st));
+    if (nP) TSL_CUDA(cudaMemcpyAsync(p->rho, d.rho.p, sizeof(double) * nP, cudaMemcpyDeviceToHost, st));
+    if (nT) TSL_CUDA(cudaMemcpyAsync(p->theta, d.theta.p, sizeof(double) * 3 * nT, cudaMemcpyDeviceToHost, st));
     TSL_CUDA(cudaStreamSynchronize(st));
-    for (int k = 0; k < d.n_points; ++k) if (S->lmfree_p_h[k] >= 0) p->rho[k] = hr[k];
-    for (int k = 0; k < d.n_planes; ++k) if (S->lmfree_t_h[k] >= 0) for (int a = 0; a < 3; ++a) p->theta[3 * k + a] = ht[3 * (size_t)k + a];
   } else {
     TSL_CUDA(cudaMemcpyAsync(p->cams, d.cams.p, sizeof(double) * 7 * (size_t)d.n_cams, cudaMemcpyDeviceToHost, st));
     if (d.n_points) TSL_CUDA(cudaMemcpyAsync(p->rho, d.rho.p, sizeof(double) * d.n_points, cudaMemcpyDeviceToHost, st));

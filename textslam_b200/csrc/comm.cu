@@ -65,6 +65,13 @@ static int allreduce(tslam_ctx* ctx, double* buf, size_t n, int op) {
   return TSLAM_OK;
 }
 int comm_allreduce_sum(tslam_ctx* ctx, double* buf, size_t n) { return allreduce(ctx, buf, n, 0); }
+// ncclInt32 = 2: flag / count tables of the sharded structure analysis (analysis_dev.cu)
+int comm_allreduce_sum_i32(tslam_ctx* ctx, int* buf, size_t n) {
+  if (ctx->world <= 1 || n == 0) return TSLAM_OK;
+  if (!ctx->nccl_comm) return set_error(TSLAM_ERR_NCCL, "world=%d but tslam_ctx_init_comm was not called", ctx->world);
+  TSL_NCCL(g_nccl.AllReduce(buf, buf, n, 2, 0, (ncclComm_p)ctx->nccl_comm, ctx->stream));
+  return TSLAM_OK;
+}
 int comm_allreduce_max(tslam_ctx* ctx, double* buf, size_t n) { return allreduce(ctx, buf, n, 2); }
 
 }  // namespace tsl

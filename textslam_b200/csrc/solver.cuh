@@ -54,5 +54,6 @@ int launch_eval_text_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double* 
 // comm.cu
 int comm_allreduce_sum(tslam_ctx* ctx, double* buf, size_t n);
 int comm_allreduce_max(tslam_ctx* ctx, double* buf, size_t n);
+int comm_allreduce_sum_i32(tslam_ctx* ctx, int* buf, size_t n);
 
 }  // namespace tsl
