@@ -879,6 +879,7 @@ struct TailArgs {
   const double* parts_cand; int n_cand;   // interleaved (cost, fixed cost) partial pairs of the candidate evaluation
   double* sc; double* mx; int* fail;
   double* host; double seq;
+  double* gather; int rank, world;        // multi-GPU: world x (SC_N + MX_N) slots, this rank fills its own and zeroes the others
 };
 constexpr int H_SEQ = 63;                 // slot of the sequence number in tslam_ctx::h_scalars (64 doubles)
 
@@ -909,11 +910,33 @@ __global__ void __launch_bounds__(256) iteration_tail_kernel(TailArgs a) {
     a.sc[SC_MCC] = mcc; a.sc[SC_CAND] = cand; a.sc[SC_CAND_FIXED] = cand_fixed;
     if (*a.fail) a.mx[MX_FAIL] = fmax(a.mx[MX_FAIL], 1.0);
     if (a.host) publish_to_host(a.sc, a.mx, a.fail, a.host, a.seq);
+    if (a.gather)
+      for (int r = 0; r < a.world; ++r) {
+        double* slot = a.gather + (size_t)r * (SC_N + MX_N);
+        for (int k = 0; k < SC_N; ++k) slot[k] = r == a.rank ? a.sc[k] : 0.0;
+        for (int k = 0; k < MX_N; ++k) slot[SC_N + k] = r == a.rank ? a.mx[k] : 0.0;
+      }
   }
 }
-__global__ void publish_scalars_kernel(const double* sc, double* mx, int* fail, double* host, double seq) {
+// Multi-GPU: `gather` has been summed across the ranks (every slot was non-zero on exactly one rank, so the sum is an
+// all-gather): sums in rank order and maxima over the ranks — identical on every rank — then the publish as on one GPU.
+__global__ void publish_gathered_kernel(const double* gather, int world, double* mx, int* fail, double* host, double seq) {
   PDL_PROLOGUE();
-  if (threadIdx.x == 0 && blockIdx.x == 0) publish_to_host(sc, mx, fail, host, seq);
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int k = 0; k < SC_N; ++k) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += gather[(size_t)r * (SC_N + MX_N) + k];
+    host[k] = s;
+  }
+  for (int k = 0; k < MX_N; ++k) {
+    unsigned long long m = 0ull;   // non-negative doubles: order of the bit patterns (keeps a NaN visible, like the atomics that fill mx[])
+    for (int r = 0; r < world; ++r) { const unsigned long long v = (unsigned long long)__double_as_longlong(gather[(size_t)r * (SC_N + MX_N) + SC_N + k]); m = v > m ? v : m; }
+    host[SC_N + k] = __longlong_as_double((long long)m);
+    mx[k] = 0.0;
+  }
+  *fail = 0;
+  __threadfence_system();
+  *reinterpret_cast<volatile double*>(host + H_SEQ) = seq;
 }
 // final residual scatter into the global residual vector (multi-GPU: other ranks' entries stay 0)
 __global__ void scatter_rows_kernel(int n, int width, const int* __restrict__ gsel, const double* __restrict__ src, double* __restrict__ dst) {
@@ -958,7 +981,7 @@ struct Solver : SolverIndex {
   DevBuf<double> red;        // [Sblk | b | graw | udiag]  (one all-reduce)
   DevBuf<double> scl, scr;   // local scalars / reduced copy
   DevBuf<double> mx;         // max-reduced scalars
-  DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts, parts_step, parts_mcc;
+  DevBuf<double> A, ywork, yc, delta_c, delta_vp, delta_vt, parts, parts_step, parts_mcc, gat;
   int tail_n_cand = 0;   // partial pairs of the deferred candidate-cost sum (iteration_tail_kernel)
   DevBuf<int> fail;
   size_t red_n = 0;
@@ -987,6 +1010,7 @@ static cudaError_t up_as(DevBuf<T>& b, const Vec& h, cudaStream_t s) {
 static int analyze_on_host_and_upload(Solver& S, Analysis& A, std::chrono::steady_clock::time_point& T1) {
   tslam_ctx* ctx = S.ctx; tslam_dev_problem* d = S.d;
   cudaStream_t st = ctx->stream;
+  if (!d->have_host_index) return set_error(TSLAM_ERR_ARG, "host structure analysis requested but the index copies were not kept");
   IndexView V;
   V.n_cams = d->n_cams; V.n_points = d->n_points; V.n_planes = d->n_planes; V.g_pobs = d->g_pobs; V.g_tobs = d->g_tobs;
   V.cam_fixed = d->h_cam_fixed.data(); V.rho_fixed = d->h_rho_fixed.data(); V.theta_fixed = d->h_theta_fixed.data();
@@ -1069,6 +1093,7 @@ static int analyze_and_upload(Solver& S) {
   TSL_CUDA(S.parts_step.reserve(2 * ((size_t)(S.nvp + 255) / 256 + (size_t)(S.nvt + 255) / 256) + 2));
   TSL_CUDA(S.parts_mcc.reserve((size_t)(lp + 255) / 256 + (size_t)(lt + 255) / 256 + 2));
   TSL_CUDA(S.fail.reserve(1));
+  TSL_CUDA(S.gat.reserve((size_t)(ctx->world > 1 ? ctx->world : 1) * (SC_N + MX_N)));
   TSL_CUDA(cudaStreamSynchronize(st));   // the host vectors of A go out of scope on return
   // host copies the solver keeps (the arena is recycled by the next analysis on this context)
   S.camslot.assign(A.camslot.begin(), A.camslot.end()); S.vp_gl_h.assign(A.LP.v_gl.begin(), A.LP.v_gl.end()); S.vt_gl_h.assign(A.LT.v_gl.begin(), A.LT.v_gl.end());
@@ -1236,7 +1261,8 @@ static int model_and_candidate_cost(Solver& S, int jac_mode) {
   tslam_ctx* ctx = S.ctx;
   const int gvp = grid_for(S.nvp, 256), gvt = grid_for(S.nvt, 256);
   TailArgs ta{S.parts_step.p, gvp + gvt, S.parts_mcc.p, gp + gt, S.parts.p, S.tail_n_cand, S.sc, S.mx.p, S.fail.p,
-              ctx->world > 1 ? nullptr : ctx->h_scalars_dev, ctx->world > 1 ? 0.0 : ++ctx->h_seq};
+              ctx->world > 1 ? nullptr : ctx->h_scalars_dev, ctx->world > 1 ? 0.0 : ++ctx->h_seq,
+              ctx->world > 1 ? S.gat.p : nullptr, ctx->rank, ctx->world};
   LAUNCH(launch_k(iteration_tail_kernel, 1, 256, 0, st, ta));
   TSL_CHECK_LAUNCH();
   mark(S, 7);  // end of the iteration's device work
@@ -1323,11 +1349,9 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
     if ((rc = compute_step(S, radius))) return rc;
     // (the gradient max-norm pieces run inside post_solve_kernel)
     if ((rc = model_and_candidate_cost(S, jac_mode))) return rc;
-    if (ctx->world > 1) {  // reduce a COPY: the local slots (cost at x, x-norm) persist across iterations
-      TSL_CUDA(cudaMemcpyAsync(S.scr.p, S.sc, SC_N * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      if ((rc = comm_allreduce_sum(ctx, S.scr.p, SC_N))) return rc;
-      if ((rc = comm_allreduce_max(ctx, S.mx.p, MX_N))) return rc;
-      LAUNCH(launch_k(publish_scalars_kernel, 1, 32, 0, st, S.scr.p, S.mx.p, S.fail.p, ctx->h_scalars_dev, ++ctx->h_seq));
+    if (ctx->world > 1) {  // ONE small collective per iteration for the 8 sums and 2 maxima (iteration_tail_kernel filled this rank's slot)
+      if ((rc = comm_allreduce_sum(ctx, S.gat.p, (size_t)ctx->world * (SC_N + MX_N)))) return rc;
+      LAUNCH(launch_k(publish_gathered_kernel, 1, 32, 0, st, S.gat.p, ctx->world, S.mx.p, S.fail.p, ctx->h_scalars_dev, ++ctx->h_seq));
       TSL_CHECK_LAUNCH();
     }
     if ((rc = wait_published(ctx))) return rc;   // iteration_tail_kernel / publish_scalars_kernel wrote h[] and the sequence number
@@ -1449,8 +1473,9 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
   if (opt->max_iters < 0) return set_error(TSLAM_ERR_ARG, "max_iters < 0");
   auto T0 = std::chrono::steady_clock::now();
   TSL_CUDA(cudaSetDevice(ctx->device));
+  AllocStreamScope alloc_scope(ctx->stream);   // declared before every device buffer of this call: released after them, on the same stream
   tslam_dev_problem d;
-  int rc = upload_problem(ctx, p, &d, /*shard=*/true);
+  int rc = upload_problem(ctx, p, &d, /*shard=*/true, /*need_host_index=*/false);
   if (rc) return rc;
   auto Tu = std::chrono::steady_clock::now();
   struct Guard { tslam_dev_problem* d; ~Guard() { free_solver(d); } } guard{&d};

@@ -9,6 +9,7 @@ namespace tsl {
 
 thread_local std::string g_last_error;
 long long g_launches = 0;
+thread_local cudaStream_t g_alloc_stream = nullptr;
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("TSLAM_PDL"); return !(e && e[0] == '0'); }();
   return on;
@@ -42,14 +43,27 @@ int flush_l2(tslam_ctx* ctx) {
   return TSLAM_OK;
 }
 
+// dst[i] = src[sel[i]] for rows of `width` elements: the sharded upload copies the caller's arrays as they are and selects
+// this rank's observations on the device (no per-rank host staging copies)
 template <typename T>
-static std::vector<T> gather_rows(const T* src, const std::vector<int32_t>& sel, int width) {
-  std::vector<T> out(sel.size() * (size_t)width);
-  for (size_t i = 0; i < sel.size(); ++i) memcpy(&out[i * width], src + (size_t)sel[i] * width, sizeof(T) * width);
-  return out;
+__global__ void gather_rows_kernel(const T* __restrict__ src, const int32_t* __restrict__ sel, size_t n, int width, T* __restrict__ dst) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const size_t i = t / width; const int k = (int)(t - i * width);
+  dst[t] = src[(size_t)sel[i] * width + k];
+}
+template <typename T>
+static int upload_selected(DevBuf<T>& dst, DevBuf<T>& scratch, const T* src, size_t n_all, const DevBuf<int32_t>& sel, size_t n_sel, int width, cudaStream_t s) {
+  TSL_CUDA(dst.reserve(n_sel * width));
+  if (n_sel == 0) return TSLAM_OK;
+  TSL_CUDA(scratch.upload(src, n_all * width, s));
+  const size_t total = n_sel * width;
+  LAUNCH(gather_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(scratch.p, sel.p, n_sel, width, dst.p));
+  TSL_CHECK_LAUNCH();
+  return TSLAM_OK;
 }
 
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard) {
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool need_host_index) {
   if (!p) return set_error(TSLAM_ERR_ARG, "null problem");
   if (p->n_cams <= 0 || !p->cams) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
   for (int i = 0; i < p->n_pobs; ++i) {
@@ -72,10 +86,16 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
   d->h_cam_fixed.assign(p->cam_fixed ? p->cam_fixed : zc.data(), (p->cam_fixed ? p->cam_fixed : zc.data()) + p->n_cams);
   d->h_rho_fixed.assign(p->rho_fixed ? p->rho_fixed : zr.data(), (p->rho_fixed ? p->rho_fixed : zr.data()) + p->n_points);
   d->h_theta_fixed.assign(p->theta_fixed ? p->theta_fixed : zt.data(), (p->theta_fixed ? p->theta_fixed : zt.data()) + p->n_planes);
-  d->h_p_cam.assign(p->p_cam, p->p_cam + p->n_pobs); d->h_p_host.assign(p->p_host, p->p_host + p->n_pobs);
-  d->h_p_lm.assign(p->p_lm, p->p_lm + p->n_pobs);
-  d->h_t_cam.assign(p->t_cam, p->t_cam + p->n_tobs); d->h_t_host.assign(p->t_host, p->t_host + p->n_tobs);
-  d->h_t_plane.assign(p->t_plane, p->t_plane + p->n_tobs);
+  d->n_pobs = p->n_pobs; d->n_tobs = p->n_tobs;   // (local counts are set below for a sharded upload)
+  if (need_host_index || !device_analysis_supported(ctx, d)) {   // index copies for the host-side structure analysis
+    d->h_p_cam.assign(p->p_cam, p->p_cam + p->n_pobs); d->h_p_host.assign(p->p_host, p->p_host + p->n_pobs);
+    d->h_p_lm.assign(p->p_lm, p->p_lm + p->n_pobs);
+    d->h_t_cam.assign(p->t_cam, p->t_cam + p->n_tobs); d->h_t_host.assign(p->t_host, p->t_host + p->n_tobs);
+    d->h_t_plane.assign(p->t_plane, p->t_plane + p->n_tobs);
+    d->have_host_index = true;
+  } else {
+    d->have_host_index = false;
+  }
   TSL_CUDA(d->cams.upload(p->cams, 7 * (size_t)p->n_cams, s));
   TSL_CUDA(d->cams0.upload(p->cams, 7 * (size_t)p->n_cams, s));
   TSL_CUDA(d->rho.upload(p->rho, p->n_points, s));
@@ -112,18 +132,24 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
     if (obs_owner(!d->h_theta_fixed[p->t_plane[i]], p->t_plane[i], i, ctx->world) == ctx->rank) d->gsel_t.push_back(i);
   d->n_pobs = (int)d->gsel_p.size(); d->n_tobs = (int)d->gsel_t.size();
   {
-    auto uv = gather_rows(p->p_uv, d->gsel_p, 2); auto ray = gather_rows(p->p_ray, d->gsel_p, 2);
-    auto c = gather_rows(p->p_cam, d->gsel_p, 1); auto h = gather_rows(p->p_host, d->gsel_p, 1); auto l = gather_rows(p->p_lm, d->gsel_p, 1);
-    auto tr = gather_rows(p->t_rays, d->gsel_t, 16); auto ti = gather_rows(p->t_iref, d->gsel_t, 8); auto tm = gather_rows(p->t_musigma, d->gsel_t, 2);
-    auto tc = gather_rows(p->t_cam, d->gsel_t, 1); auto th = gather_rows(p->t_host, d->gsel_t, 1); auto tp = gather_rows(p->t_plane, d->gsel_t, 1);
-    auto tg = gather_rows(p->t_img, d->gsel_t, 1);
-    TSL_CUDA(d->p_uv.upload(uv.data(), uv.size(), s)); TSL_CUDA(d->p_ray.upload(ray.data(), ray.size(), s));
-    TSL_CUDA(d->p_cam.upload(c.data(), c.size(), s)); TSL_CUDA(d->p_host.upload(h.data(), h.size(), s)); TSL_CUDA(d->p_lm.upload(l.data(), l.size(), s));
-    TSL_CUDA(d->t_rays.upload(tr.data(), tr.size(), s)); TSL_CUDA(d->t_iref.upload(ti.data(), ti.size(), s));
-    TSL_CUDA(d->t_musigma.upload(tm.data(), tm.size(), s));
-    TSL_CUDA(d->t_cam.upload(tc.data(), tc.size(), s)); TSL_CUDA(d->t_host.upload(th.data(), th.size(), s));
-    TSL_CUDA(d->t_plane.upload(tp.data(), tp.size(), s)); TSL_CUDA(d->t_img.upload(tg.data(), tg.size(), s));
-    TSL_CUDA(cudaStreamSynchronize(s));
+    DevBuf<int32_t> selp, selt, si[7];
+    DevBuf<double> sd[5];
+    TSL_CUDA(selp.upload(d->gsel_p.data(), d->gsel_p.size(), s)); TSL_CUDA(selt.upload(d->gsel_t.data(), d->gsel_t.size(), s));
+    const size_t NPo = (size_t)p->n_pobs, NTo = (size_t)p->n_tobs, lp = d->gsel_p.size(), lt = d->gsel_t.size();
+    int rc;
+    if ((rc = upload_selected(d->p_uv, sd[0], p->p_uv, NPo, selp, lp, 2, s))) return rc;
+    if ((rc = upload_selected(d->p_ray, sd[1], p->p_ray, NPo, selp, lp, 2, s))) return rc;
+    if ((rc = upload_selected(d->p_cam, si[0], p->p_cam, NPo, selp, lp, 1, s))) return rc;
+    if ((rc = upload_selected(d->p_host, si[1], p->p_host, NPo, selp, lp, 1, s))) return rc;
+    if ((rc = upload_selected(d->p_lm, si[2], p->p_lm, NPo, selp, lp, 1, s))) return rc;
+    if ((rc = upload_selected(d->t_rays, sd[2], p->t_rays, NTo, selt, lt, 16, s))) return rc;
+    if ((rc = upload_selected(d->t_iref, sd[3], p->t_iref, NTo, selt, lt, 8, s))) return rc;
+    if ((rc = upload_selected(d->t_musigma, sd[4], p->t_musigma, NTo, selt, lt, 2, s))) return rc;
+    if ((rc = upload_selected(d->t_cam, si[3], p->t_cam, NTo, selt, lt, 1, s))) return rc;
+    if ((rc = upload_selected(d->t_host, si[4], p->t_host, NTo, selt, lt, 1, s))) return rc;
+    if ((rc = upload_selected(d->t_plane, si[5], p->t_plane, NTo, selt, lt, 1, s))) return rc;
+    if ((rc = upload_selected(d->t_img, si[6], p->t_img, NTo, selt, lt, 1, s))) return rc;
+    TSL_CUDA(cudaStreamSynchronize(s));   // the scratch copies are released on return; host arrays are caller-owned
   }
   return TSLAM_OK;
 }

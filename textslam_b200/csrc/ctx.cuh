@@ -56,22 +56,35 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 #endif
 
+// Stream the calling entry point wants its device buffers allocated (and released) on. tslam_solve sets it to the context
+// stream for the duration of the call: every use of those buffers is on that stream, so stream order alone makes the
+// ~130 allocations of a solve safe and none of them needs a host synchronisation (0.6 ms per call on the global-BA shape).
+// nullptr (default): allocate on the per-thread stream and synchronise, the buffer may then be used on any stream.
+extern thread_local cudaStream_t g_alloc_stream;
+struct AllocStreamScope {
+  cudaStream_t prev;
+  explicit AllocStreamScope(cudaStream_t s) : prev(g_alloc_stream) { g_alloc_stream = s; }
+  ~AllocStreamScope() { g_alloc_stream = prev; }
+};
+
 template <typename T>
 struct DevBuf {  // simple RAII device buffer (grow-only)
   T* p = nullptr;
   size_t cap = 0;
-  ~DevBuf() { if (p) cudaFreeAsync(p, cudaStreamPerThread); }   // back to the (never trimmed) default pool: next solve reuses it
+  // back to the (never trimmed) default pool: the next solve reuses it
+  ~DevBuf() { if (p) cudaFreeAsync(p, g_alloc_stream ? g_alloc_stream : cudaStreamPerThread); }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   cudaError_t reserve(size_t n) {
     if (p && n <= cap) return cudaSuccess;
-    if (p) cudaFreeAsync(p, cudaStreamPerThread);
+    cudaStream_t as = g_alloc_stream;
+    if (p) cudaFreeAsync(p, as ? as : cudaStreamPerThread);
     p = nullptr; cap = 0;
     // stream-ordered allocation from the device's default memory pool (release threshold raised in tslam_ctx_create):
     // repeated tslam_solve calls recycle their buffers instead of paying cudaMalloc/cudaFree every time
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T), cudaStreamPerThread);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), (n ? n : 1) * sizeof(T), as ? as : cudaStreamPerThread);
+    if (e == cudaSuccess && !as) e = cudaStreamSynchronize(cudaStreamPerThread);
     if (e == cudaSuccess) cap = n;
     return e;
   }
@@ -126,12 +139,16 @@ struct tslam_dev_problem {
   std::vector<uint8_t> h_cam_fixed, h_rho_fixed, h_theta_fixed;
   std::vector<int32_t> gsel_p, gsel_t;              // global index of each local observation (sharded upload)
   bool sharded = false;
+  bool have_host_index = true;   // h_p_* / h_t_* filled (needed by the host-side structure analysis only)
   void* solver = nullptr;  // tsl::Solver*, owned (ba_solve.cu)
 };
 
 namespace tsl {
 // shard = true: keep only the observations this rank owns (multi-GPU global BA, ctx->world > 1)
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false);
+// need_host_index = false (one-shot tslam_solve): the host copies of the observation index arrays are only made when the
+// structure analysis will run on the host
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false, bool need_host_index = true);
+bool device_analysis_supported(const tslam_ctx* ctx, const tslam_dev_problem* d);
 // observation ownership rule shared by upload and the solver's structure analysis
 inline int obs_owner(bool lm_free, int lm_index, int obs_index, int world) { return (lm_free ? lm_index : obs_index) % world; }
 int flush_l2(tslam_ctx* ctx);
