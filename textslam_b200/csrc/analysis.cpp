@@ -1,5 +1,6 @@
 // Structure analysis of a BA problem on the host — see analysis.hpp.
 #include "analysis.hpp"
+#include "nd_layout.h"
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -343,11 +344,12 @@ void analyze_structure(const IndexView& V, Analysis& A, Arena& arena) {
   for (int k = 0; k < V.n_planes; ++k) if (pu[k] && !V.theta_fixed[k]) A.lmfree_t[k] = A.npl++;
   const int nc = A.nc;
   A.n = 6 * nc;
-  A.Tn = chol_workspace_dims(A.n, &A.ld, &A.rows);
-  // ---- nested-dissection order of the free cameras (keyframes are temporally ordered, co-visibility is banded) ----
-  // Units of U cameras (U = multiple of 32 cameras = 3 tiles of 64 columns, at least the co-visibility bandwidth) are
-  // ordered leaves-first / separators-last so that the tile elimination DAG of chol.cu has ~log depth instead of being
-  // a chain; any order is valid, this one only shortens the critical path of the reduced-system factorisation.
+  // ---- camera order + tile-aligned layout (nd_layout.h): leaves first, then the separators by height; every node starts on
+  // a tile boundary of the dense reduced matrix. Any order is valid, this one only shortens the critical path of the
+  // reduced-system factorisation (keyframes are temporally ordered, co-visibility is banded).
+  A.doff.assign(nc, 0);
+  for (int s = 0; s < nc; ++s) A.doff[s] = 6 * s;
+  A.npad = A.n;
   if (nc >= 128) {
     AVec<int> hist((size_t)nc, 0);   // histogram of |slot(cam) - slot(host)| over the active observations
     size_t nd = 0;
@@ -360,27 +362,21 @@ void analyze_structure(const IndexView& V, Analysis& A, Arena& arena) {
       for (int dd = 0; dd < nc; ++dd) { acc += hist[dd]; if (acc > q) { dq = dd; break; } }
       bw = 2 * dq;
     }
-    const int U = 32 * ((bw + 1 + 31) / 32);
-    const int nfull = nc / U;
-    if (nfull >= 4) {
-      AVec<int> unit_order;
-      struct Frame { int lo, hi, stage; };   // recursive bisection written iteratively (post-order: left, right, separator)
-      AVec<Frame> st; st.push_back({0, nfull, 0});
-      while (!st.empty()) {
-        Frame f = st.back(); st.pop_back();
-        if (f.hi - f.lo <= 0) continue;
-        if (f.hi - f.lo <= 2) { for (int u = f.lo; u < f.hi; ++u) unit_order.push_back(u); continue; }
-        const int mid = (f.lo + f.hi) / 2;
-        if (f.stage == 0) { st.push_back({f.lo, f.hi, 1}); st.push_back({mid + 1, f.hi, 0}); st.push_back({f.lo, mid, 0}); }
-        else unit_order.push_back(mid);
-      }
+    const NdPlan P = nd_plan(nc, bw);
+    if (P.levels > 0) {
       AVec<int> new_of_old(nc, -1);
-      int next = 0;
-      for (int u : unit_order) for (int c = u * U; c < (u + 1) * U; ++c) new_of_old[c] = next++;
-      for (int c = nfull * U; c < nc; ++c) new_of_old[c] = next++;   // the partial unit goes last (keeps units tile-aligned)
+      int slot = 0, d = 0;
+      for (int k = 0; k < nd_node_count(P); ++k) {
+        int s0, sz;
+        nd_node(P, k, &s0, &sz);
+        d = (d + NB - 1) / NB * NB;
+        for (int c = s0; c < s0 + sz; ++c) { new_of_old[c] = slot; A.doff[slot] = d; ++slot; d += 6; }
+      }
+      A.npad = d;
       for (int k = 0; k < K; ++k) if (A.camslot[k] >= 0) A.camslot[k] = new_of_old[A.camslot[k]];
     }
   }
+  A.Tn = chol_workspace_dims(A.npad, &A.ld, &A.rows);
   // camera slots of every global observation
   AVec<int> gp_cs(GP), gp_hs(GP), gt_cs(GT), gt_hs(GT);
   pool.ranges(GP, [&](int, int i0, int i1) { for (int i = i0; i < i1; ++i) { gp_cs[i] = A.camslot[V.p_cam[i]]; gp_hs[i] = A.camslot[V.p_host[i]]; } });
@@ -489,11 +485,11 @@ void analyze_structure(const IndexView& V, Analysis& A, Arena& arena) {
   {  // tile pattern of the reduced matrix -> symbolic tile Cholesky
     AVec<uint8_t> tile_nz((size_t)A.Tn * A.Tn, 0);
     for (int b = 0; b < A.nblk; ++b) {
-      // block (a,b'), a <= b' lands in rows 6b'..6b'+5, cols 6a..6a+5 of the lower triangle
-      const int r0 = 6 * A.blk_b[b] / NB, r1 = (6 * A.blk_b[b] + 5) / NB, c0 = 6 * A.blk_a[b] / NB, c1 = (6 * A.blk_a[b] + 5) / NB;
+      // block (a,b'), a <= b' lands in rows doff[b']..+5, cols doff[a]..+5 of the lower triangle
+      const int r0 = A.doff[A.blk_b[b]] / NB, r1 = (A.doff[A.blk_b[b]] + 5) / NB, c0 = A.doff[A.blk_a[b]] / NB, c1 = (A.doff[A.blk_a[b]] + 5) / NB;
       for (int r = r0; r <= r1; ++r) for (int c = c0; c <= c1; ++c) if (c <= r) tile_nz[(size_t)r * A.Tn + c] = 1;
     }
-    chol_symbolic_host(A.n, tile_nz, A.chol);
+    chol_symbolic_host(A.npad, tile_nz, A.chol);
   }
   A.lap_ms[3] = T.lap();
   auto blk_of = [&](int a, int b) {   // a <= b

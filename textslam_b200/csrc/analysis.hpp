@@ -74,8 +74,9 @@ struct CholHost {  // tile-level symbolic factorisation + level schedule (see ch
 
 struct Analysis {
   int K = 0, nc = 0, nl = 0, npl = 0, lp = 0, lt = 0, nvp = 0, nvt = 0, nsp = 0, nst = 0, nblk = 0;
-  int n = 0, ld = 0, rows = 0, Tn = 0;
+  int n = 0, npad = 0, ld = 0, rows = 0, Tn = 0;   // n = 6 nc unknowns; npad = columns of the tile-aligned layout (>= n)
   AVec<int> camslot, lmfree_p, lmfree_t;
+  AVec<int> doff;                               // first column of each camera slot in the dense reduced matrix (nd_layout.h)
   AVec<int> p_cs, p_hs, t_cs, t_hs;             // per local observation: camera slots (or -1)
   AVec<uint8_t> p_act, t_act, t_fm;
   LmSide LP, LT;

@@ -20,6 +20,7 @@
 #include <chrono>
 #include "ctx.cuh"
 #include "solver.cuh"
+#include "nd_layout.h"
 
 namespace tsl {
 namespace {
@@ -33,6 +34,7 @@ struct Counts {   // device-side scalars, copied to the host once
   int n_ent_p, n_ent_t, nsp, nst, nblk;
   int npairs_p, npairs_t;
   int overflow;
+  int npad;   // columns of the tile-aligned camera layout (nd_layout.h)
 };
 
 static int bits_for(unsigned long long max_value) { int b = 1; while (b < 64 && (max_value >> b)) ++b; return b; }
@@ -78,10 +80,11 @@ __global__ void dist_hist_kernel(int n, const int* __restrict__ cam, const int* 
 // Nested-dissection order of the free cameras — the logic of analysis.cpp (analyze_structure) on one warp: the inputs are
 // a histogram and the outputs a permutation of <= 2^14 cameras; the scans over it are lane-parallel, the (tiny) recursive
 // bisection runs on lane 0.
-__global__ void __launch_bounds__(32) nd_order_kernel(int K, int* camslot, const int* __restrict__ hist, const Counts* cnt, int* new_of_old, int* unit_order) {
+__global__ void __launch_bounds__(32) nd_order_kernel(int K, int* camslot, const int* __restrict__ hist, Counts* cnt, int* new_of_old, int* doff) {
   const int lane = threadIdx.x;
   const int nc = cnt->nc;
-  if (nc < 128) return;
+  for (int s0 = lane; s0 < nc; s0 += 32) doff[s0] = 6 * s0;   // default: natural order, no padding
+  if (nc < 128) { if (lane == 0) cnt->npad = 6 * nc; return; }
   unsigned long long nd = 0;
   for (int d = lane; d < nc; d += 32) nd += (unsigned long long)hist[d];
 #pragma unroll
@@ -101,34 +104,30 @@ __global__ void __launch_bounds__(32) nd_order_kernel(int K, int* camslot, const
     }
     bw = 2 * dq;
   }
-  const int U = 32 * ((bw + 1 + 31) / 32);
-  const int nfull = nc / U;
-  if (nfull < 4) return;
-  int n_order = 0;
+  // node table of the plan (nd_layout.h) on lane 0, then the lanes fill the permutation and the column offsets
+  __shared__ int s_nat[128], s_size[128], s_slot[128], s_col[128];
+  __shared__ int s_nodes, s_npad;
   if (lane == 0) {
-    int lo_s[64], hi_s[64], st_s[64]; int sp = 0;   // recursive bisection, post-order: left, right, separator
-    lo_s[0] = 0; hi_s[0] = nfull; st_s[0] = 0; sp = 1;
-    while (sp > 0) {
-      --sp;
-      const int lo = lo_s[sp], hi = hi_s[sp], stage = st_s[sp];
-      if (hi - lo <= 0) continue;
-      if (hi - lo <= 2) { for (int u = lo; u < hi; ++u) unit_order[n_order++] = u; continue; }
-      const int mid = (lo + hi) / 2;
-      if (stage == 0) {
-        lo_s[sp] = lo; hi_s[sp] = hi; st_s[sp] = 1; ++sp;
-        lo_s[sp] = mid + 1; hi_s[sp] = hi; st_s[sp] = 0; ++sp;
-        lo_s[sp] = lo; hi_s[sp] = mid; st_s[sp] = 0; ++sp;
-      } else unit_order[n_order++] = mid;
+    const NdPlan P = nd_plan(nc, bw);
+    int nn = 0, slot = 0, d = 0;
+    if (P.levels > 0) {
+      nn = nd_node_count(P);
+      for (int k = 0; k < nn; ++k) {
+        int s0, sz;
+        nd_node(P, k, &s0, &sz);
+        d = (d + 63) / 64 * 64;
+        s_nat[k] = s0; s_size[k] = sz; s_slot[k] = slot; s_col[k] = d;
+        slot += sz; d += 6 * sz;
+      }
     }
-    __threadfence_block();
+    s_nodes = nn; s_npad = nn ? d : 6 * nc;
   }
-  n_order = __shfl_sync(0xffffffffu, n_order, 0);
   __syncwarp();
-  for (int k = 0; k < n_order; ++k) {
-    const int u = unit_order[k];
-    for (int c = lane; c < U; c += 32) new_of_old[u * U + c] = k * U + c;
-  }
-  for (int c = nfull * U + lane; c < nc; c += 32) new_of_old[c] = n_order * U + (c - nfull * U);   // the partial unit goes last (keeps units tile-aligned)
+  const int nn = s_nodes;
+  if (lane == 0) cnt->npad = s_npad;
+  if (nn == 0) return;   // natural order: doff = 6 s (filled by the caller's default), camslot unchanged
+  for (int k = 0; k < nn; ++k)
+    for (int c = lane; c < s_size[k]; c += 32) { new_of_old[s_nat[k] + c] = s_slot[k] + c; doff[s_slot[k] + c] = s_col[k] + 6 * c; }
   __threadfence_block();
   __syncwarp();
   for (int k = lane; k < K; k += 32) if (camslot[k] >= 0) camslot[k] = new_of_old[camslot[k]];
@@ -232,16 +231,16 @@ __global__ void mark_schur_kernel(int nq, const int* n_lm, const int* __restrict
   for (int x = slot_ptr[v]; x < slot_ptr[v + 1]; ++x)
     for (int y = x; y < slot_ptr[v + 1]; ++y) flag[(size_t)slot_cam[x] * nc + slot_cam[y]] = 1;
 }
-__global__ void block_count_kernel(int ncap2, const int* __restrict__ flag, const int* __restrict__ pre, Counts* cnt, uint8_t* __restrict__ tile_nz, int tn_cap) {
-  // nblk, and the 64x64 tile pattern of the lower triangle (block (a,b), a <= b: rows 6b.., cols 6a..)
+__global__ void block_count_kernel(int ncap2, const int* __restrict__ flag, const int* __restrict__ pre, Counts* cnt, const int* __restrict__ doff, uint8_t* __restrict__ tile_nz, int tn_cap) {
+  // nblk, and the 64x64 tile pattern of the lower triangle (block (a,b), a <= b: rows doff[b].., cols doff[a]..)
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nc = cnt->nc;
   const size_t nc2 = (size_t)nc * nc;
   if (t == 0) cnt->nblk = nc2 ? pre[nc2 - 1] + flag[nc2 - 1] : 0;
   if (t >= nc2 || !flag[t]) return;
   const int a = (int)(t / nc), b = (int)(t % nc);
-  const int Tn = (6 * nc + 63) / 64;
-  const int r0 = 6 * b / 64, r1 = (6 * b + 5) / 64, c0 = 6 * a / 64, c1 = (6 * a + 5) / 64;
+  const int Tn = (cnt->npad + 63) / 64;
+  const int r0 = doff[b] / 64, r1 = (doff[b] + 5) / 64, c0 = doff[a] / 64, c1 = (doff[a] + 5) / 64;
   for (int r = r0; r <= r1; ++r) for (int c = c0; c <= c1; ++c) if (c <= r) tile_nz[(size_t)r * Tn + c] = 1;
   (void)ncap2; (void)tn_cap;
 }
@@ -339,8 +338,8 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   TSL_CUDA(cnt.reserve(1));
   TSL_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(Counts), st));
   // ---- flags, camera layout, nested-dissection order ----
-  DevBuf<int> cu, hist, new_of_old, unit_order;
-  TSL_CUDA(cu.reserve(K)); TSL_CUDA(hist.reserve(K)); TSL_CUDA(new_of_old.reserve(K)); TSL_CUDA(unit_order.reserve(K / 32 + 2));
+  DevBuf<int> cu, hist, new_of_old;
+  TSL_CUDA(cu.reserve(K)); TSL_CUDA(hist.reserve(K)); TSL_CUDA(new_of_old.reserve(K)); TSL_CUDA(X.doff.reserve(K));
   TSL_CUDA(cudaMemsetAsync(cu.p, 0, sizeof(int) * K, st)); TSL_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(int) * K, st));
   TypeBufs BP, BT;
   TSL_CUDA(BP.lu.reserve(NP)); TSL_CUDA(BT.lu.reserve(NL));
@@ -356,7 +355,7 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   if (np) LAUNCH(dist_hist_kernel<<<grid(np, 256), 256, 0, st>>>(np, d->p_cam.p, d->p_host.p, X.p_active.p, X.camslot_d.p, hist.p));
   if (nt) LAUNCH(dist_hist_kernel<<<grid(nt, 256), 256, 0, st>>>(nt, d->t_cam.p, d->t_host.p, X.t_active.p, X.camslot_d.p, hist.p));
   if (multi && (rc = comm_allreduce_sum_i32(ctx, hist.p, K))) return rc;      // global co-visibility distances -> same camera order
-  LAUNCH(nd_order_kernel<<<1, 32, 0, st>>>(K, X.camslot_d.p, hist.p, cnt.p, new_of_old.p, unit_order.p));
+  LAUNCH(nd_order_kernel<<<1, 32, 0, st>>>(K, X.camslot_d.p, hist.p, cnt.p, new_of_old.p, X.doff.p));
   TSL_CHECK_LAUNCH();
 
   // ---- per landmark type: free numbering, observation CSR, slots ----
@@ -413,7 +412,7 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
 
   // ---- non-zero blocks: dense (a, b) flag table -> ids in (a, b) order ----
   const size_t K2 = (size_t)K * K;
-  const int tn_cap = (6 * K + 63) / 64;
+  const int tn_cap = (6 * K + 63) / 64 + 128;   // + one padding tile per node of the layout at most
   DevBuf<int> flag, pre;
   DevBuf<uint8_t> tile_nz_d;
   TSL_CUDA(flag.reserve(K2)); TSL_CUDA(pre.reserve(K2)); TSL_CUDA(tile_nz_d.reserve((size_t)tn_cap * tn_cap));
@@ -431,7 +430,7 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
     size_t tb = temp_bytes;
     TSL_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, flag.p, pre.p, (int)K2, st)); ++g_launches;
   }
-  LAUNCH(block_count_kernel<<<grid(K2, 256), 256, 0, st>>>((int)K2, flag.p, pre.p, C, tile_nz_d.p, tn_cap));
+  LAUNCH(block_count_kernel<<<grid(K2, 256), 256, 0, st>>>((int)K2, flag.p, pre.p, C, X.doff.p, tile_nz_d.p, tn_cap));
   TSL_CHECK_LAUNCH();
   // ---- the one round trip: counts + tile pattern ----
   DevBuf<int> gfree;   // multi-GPU: global number of free landmarks of each type (summary + termination test need the global count)
@@ -451,14 +450,14 @@ int analyze_structure_device(tslam_ctx* ctx, tslam_dev_problem* d, SolverIndex& 
   auto T1 = std::chrono::steady_clock::now();
   X.nc = hc.nc; X.nl = multi ? gfree_h[0] : hc.nl; X.npl = multi ? gfree_h[1] : hc.npl; X.nvp = hc.nl; X.nvt = hc.npl; X.nsp = hc.nsp; X.nst = hc.nst; X.nblk = hc.nblk; X.noff = hc.nblk - hc.nc;
   X.est_entries = (long long)hc.npairs_p + hc.npairs_t + 3LL * ((long long)np + nt);
-  X.n = 6 * X.nc;
-  X.Tn = chol_workspace_dims(X.n, &X.ld, &X.rows);
+  X.n = 6 * X.nc; X.npad = hc.npad;
+  X.Tn = chol_workspace_dims(X.npad, &X.ld, &X.rows);
   {   // tile-level symbolic factorisation + level schedule on the host (Tn^2 flags), uploaded like on the host path
     if (!ctx->host_arena)
       ctx->host_arena = new Arena([](size_t n) -> void* { void* q = nullptr; return cudaHostAlloc(&q, n, cudaHostAllocDefault) == cudaSuccess ? q : nullptr; },
                                   [](void* q) { cudaFreeHost(q); });
     CholHost H;
-    try { chol_symbolic_in_arena(X.n, tile_h.data(), *ctx->host_arena, H); } catch (const std::exception& e) { return set_error(TSLAM_ERR_CUDA, "symbolic factorisation failed: %s", e.what()); }
+    try { chol_symbolic_in_arena(X.npad, tile_h.data(), *ctx->host_arena, H); } catch (const std::exception& e) { return set_error(TSLAM_ERR_CUDA, "symbolic factorisation failed: %s", e.what()); }
     if ((rc = chol_upload(ctx, H, &X.chol))) return rc;
     TSL_CUDA(cudaStreamSynchronize(st));   // H lives in the arena only until the next analysis
   }
@@ -559,7 +558,8 @@ extern "C" int tslam_debug_compare_analysis(tslam_ctx* ctx, const tslam_ba_probl
   std::string bad;
   auto chk = [&](bool ok, const char* name) { if (!ok) { bad += name; bad += ' '; } };
   chk(X.K == A.K && X.nc == A.nc && X.nl == A.nl && X.npl == A.npl && X.lp == A.lp && X.lt == A.lt && X.nvp == A.nvp && X.nvt == A.nvt && X.nsp == A.nsp &&
-      X.nst == A.nst && X.nblk == A.nblk && X.noff == (int)A.offdiag_blk.size() && X.n == A.n && X.ld == A.ld && X.rows == A.rows && X.Tn == A.Tn, "counts");
+      X.nst == A.nst && X.nblk == A.nblk && X.noff == (int)A.offdiag_blk.size() && X.n == A.n && X.npad == A.npad && X.ld == A.ld && X.rows == A.rows && X.Tn == A.Tn, "counts");
+  chk(same_as_host(X.doff, A.doff, A.nc, st), "doff");
   chk(same_as_host(X.camslot_d, A.camslot, A.K, st), "camslot");
   chk(same_as_host(X.p_cs, A.p_cs, A.lp, st), "p_cs"); chk(same_as_host(X.p_hs, A.p_hs, A.lp, st), "p_hs"); chk(same_as_host(X.p_ls, A.LP.obs_ls, A.lp, st), "p_ls");
   chk(same_as_host(X.t_cs, A.t_cs, A.lt, st), "t_cs"); chk(same_as_host(X.t_hs, A.t_hs, A.lt, st), "t_hs"); chk(same_as_host(X.t_ls, A.LT.obs_ls, A.lt, st), "t_ls");

@@ -565,6 +565,8 @@ __global__ void __launch_bounds__(128) schur_merged_kernel(BlockArgs A, const in
 struct ScatterArgs {
   int nblk; const int* blk_a; const int* blk_b; const double* Sblk; const double* bvec; const double* udiag; double inv_radius;
   double* A; int ld; int n; int rows_total; int Rb;
+  const int* doff;   // first column of each camera slot in the tile-aligned layout (nd_layout.h); padding columns keep the
+                     // unit diagonal zero_tiles_kernel wrote
 };
 __global__ void scatter_kernel(ScatterArgs S) {
   PDL_PROLOGUE();
@@ -576,52 +578,18 @@ __global__ void scatter_kernel(ScatterArgs S) {
     double v = S.Sblk[t];
     if (a == b && p == q) v += lm_damp(S.udiag[6 * a + p], S.inv_radius);
     // block (a,b), a <= b, holds rows a / cols b; the lower triangle wants rows b / cols a
-    const int R = 6 * b + q, Cc = 6 * a + p;
+    const int R = S.doff[b] + q, Cc = S.doff[a] + p;
     if (a != b || R >= Cc) S.A[(size_t)R * S.ld + Cc] = v;
   } else {
     const int u = t - nb36;
-    if (u < S.n) S.A[(size_t)S.Rb * S.ld + u] = S.bvec[u];                       // b row
-    else if (u < S.ld) S.A[(size_t)u * S.ld + u] = 1.0;                          // identity padding
+    if (u < S.n) S.A[(size_t)S.Rb * S.ld + S.doff[u / 6] + u % 6] = S.bvec[u];   // b row
   }
 }
 
 // ---- landmark back-substitution, steps and candidate parameters ---------------------------------------
-template <int D>
-__device__ __forceinline__ void backsub_body(const unsigned bid, int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
-                               const double* __restrict__ Vinv, const double* __restrict__ g, const double* __restrict__ yc,
-                               const double* __restrict__ scale_l, double* __restrict__ delta_l) {
-  const int v = bid * blockDim.x + threadIdx.x;
-  if (v >= nv) return;
-  double t[D];
-#pragma unroll
-  for (int a = 0; a < D; ++a) t[a] = g[v * D + a];
-  for (int s = slot_ptr[v]; s < slot_ptr[v + 1]; ++s) {
-    const double* y = yc + 6 * slot_cam[s];
-    const double* Es = E + (size_t)s * 6 * D;
-#pragma unroll
-    for (int c = 0; c < 6; ++c)
-#pragma unroll
-      for (int a = 0; a < D; ++a) t[a] -= Es[c * D + a] * y[c];
-  }
-#pragma unroll
-  for (int a = 0; a < D; ++a) {
-    double y = 0.0;
-#pragma unroll
-    for (int b = 0; b < D; ++b) y += Vinv[(size_t)v * D * D + a * D + b] * t[b];
-    delta_l[v * D + a] = -y * scale_l[v * D + a];
-  }
-}
-template <int D>
-__global__ void backsub_kernel(int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam, const double* __restrict__ E,
-                               const double* __restrict__ Vinv, const double* __restrict__ g, const double* __restrict__ yc,
-                               const double* __restrict__ scale_l, double* __restrict__ delta_l) {
-  PDL_PROLOGUE();
-  backsub_body<D>(blockIdx.x, nv, slot_ptr, slot_cam, E, Vinv, g, yc, scale_l, delta_l);
-}
-
 // cameras: delta_c = -y_c * scale ; x_c = Plus(x, delta); partial norms (one block, cams are few)
-__device__ __forceinline__ void candidate_cams_body(const unsigned bid, int n_cams, const int* __restrict__ camslot, const double* __restrict__ x,
-                                                             const double* __restrict__ yc, const double* __restrict__ scale_c,
+__device__ __forceinline__ void candidate_cams_body(const unsigned bid, int n_cams, const int* __restrict__ camslot, const int* __restrict__ doff,
+                                                             const double* __restrict__ x, const double* __restrict__ yc, const double* __restrict__ scale_c,
                                                              double* __restrict__ delta_c, double* __restrict__ xc,
                                                              double* __restrict__ sc, double norm_weight) {
   __shared__ double sred[256];
@@ -637,7 +605,7 @@ __device__ __forceinline__ void candidate_cams_body(const unsigned bid, int n_ca
     }
     double d[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { d[c] = -yc[6 * s + c] * scale_c[6 * s + c]; delta_c[6 * s + c] = d[c]; }
+    for (int c = 0; c < 6; ++c) { d[c] = -yc[doff[s] + c] * scale_c[6 * s + c]; delta_c[6 * s + c] = d[c]; }
     // ceres::QuaternionParameterization::Plus
     const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     double q[4];
@@ -661,44 +629,6 @@ __device__ __forceinline__ void candidate_cams_body(const unsigned bid, int n_ca
   const double b = block_sum_256(cn2, sred);
   if (threadIdx.x == 0) { sc[SC_STEP2] = a * norm_weight; sc[SC_CNORM2] = b * norm_weight; }
 }
-__global__ void __launch_bounds__(256) candidate_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x,
-                                                             const double* __restrict__ yc, const double* __restrict__ scale_c,
-                                                             double* __restrict__ delta_c, double* __restrict__ xc,
-                                                             double* __restrict__ sc, double norm_weight) {
-  PDL_PROLOGUE();
-  candidate_cams_body(blockIdx.x, n_cams, camslot, x, yc, scale_c, delta_c, xc, sc, norm_weight);
-}
-
-template <int D>
-__device__ __forceinline__ void candidate_lm_body(const unsigned bid, int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
-                                                           const double* __restrict__ delta_l, double* __restrict__ xc,
-                                                           double* __restrict__ parts /*2 per block*/) {
-  __shared__ double sred[256];
-  const int v = bid * 256 + threadIdx.x;
-  double step2 = 0.0, cn2 = 0.0;
-  if (v < nv) {
-    const int gidx = v_gl[v];
-#pragma unroll
-    for (int a = 0; a < D; ++a) {
-      const double d = delta_l[v * D + a];
-      const double val = x[(size_t)gidx * D + a] + d;
-      xc[(size_t)gidx * D + a] = val;
-      step2 += d * d; cn2 += val * val;
-    }
-  }
-  const double a = block_sum_256(step2, sred);
-  __syncthreads();
-  const double b = block_sum_256(cn2, sred);
-  if (threadIdx.x == 0) { parts[2 * bid] = a; parts[2 * bid + 1] = b; }
-}
-template <int D>
-__global__ void __launch_bounds__(256) candidate_lm_kernel(int nv, const int* __restrict__ v_gl, const double* __restrict__ x,
-                                                           const double* __restrict__ delta_l, double* __restrict__ xc,
-                                                           double* __restrict__ parts /*2 per block*/) {
-  PDL_PROLOGUE();
-  candidate_lm_body<D>(blockIdx.x, nv, v_gl, x, delta_l, xc, parts);
-}
-
 // squared norm of the free ambient parameters (x_norm at start)
 __global__ void __launch_bounds__(256) xnorm_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, double* out, double w) {
   PDL_PROLOGUE();
@@ -781,11 +711,6 @@ __device__ __forceinline__ void gmax_cams_body(const unsigned bid, int n_cams, c
   for (int c = 3; c < 6; ++c) m = fmax(m, fabs(graw[6 * s + c]));
   atomic_max_nonneg(mx + MX_GMAX, m);
 }
-__global__ void gmax_cams_kernel(int n_cams, const int* __restrict__ camslot, const double* __restrict__ x, const double* __restrict__ graw,
-                                 double* __restrict__ mx) {
-  PDL_PROLOGUE();
-  gmax_cams_body(blockIdx.x, n_cams, camslot, x, graw, mx);
-}
 __device__ __forceinline__ void gmax_lm_body(const unsigned bid, int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
   const int i = bid * blockDim.x + threadIdx.x;
   // max over the bit patterns (what the atomic does; keeps a NaN visible), one atomic per warp instead of per landmark
@@ -794,20 +719,15 @@ __device__ __forceinline__ void gmax_lm_body(const unsigned bid, int n, const do
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(mx + MX_GMAX), m);
 }
-__global__ void gmax_lm_kernel(int n, const double* __restrict__ g_scaled, const double* __restrict__ scale, double* __restrict__ mx) {
-  PDL_PROLOGUE();
-  gmax_lm_body(blockIdx.x, n, g_scaled, scale, mx);
-}
-
 // ---- everything between the reduced-system solve and the candidate evaluation, in ONE launch ---------------------------
 // CTA ranges: landmark back-substitution fused with the candidate landmark values and their norm partials (points, then
 // planes), the candidate cameras (one CTA), and the gradient max-norm pieces (cameras, points, planes) — six launches before.
 template <int D>
 __device__ __forceinline__ void backsub_candidate_body(const unsigned bid, int nv, const int* __restrict__ slot_ptr, const int* __restrict__ slot_cam,
                                                        const double* __restrict__ E, const double* __restrict__ Vinv, const double* __restrict__ g,
-                                                       const double* __restrict__ yc, const double* __restrict__ scale_l, double* __restrict__ delta_l,
-                                                       const int* __restrict__ v_gl, const double* __restrict__ x, double* __restrict__ xc,
-                                                       double* __restrict__ parts) {
+                                                       const double* __restrict__ yc, const int* __restrict__ doff, const double* __restrict__ scale_l,
+                                                       double* __restrict__ delta_l, const int* __restrict__ v_gl, const double* __restrict__ x,
+                                                       double* __restrict__ xc, double* __restrict__ parts) {
   __shared__ double sred[256];
   const int v = bid * 256 + threadIdx.x;
   double step2 = 0.0, cn2 = 0.0;
@@ -816,7 +736,7 @@ __device__ __forceinline__ void backsub_candidate_body(const unsigned bid, int n
 #pragma unroll
     for (int a = 0; a < D; ++a) t[a] = g[v * D + a];
     for (int s = slot_ptr[v]; s < slot_ptr[v + 1]; ++s) {
-      const double* y = yc + 6 * slot_cam[s];
+      const double* y = yc + doff[slot_cam[s]];
       const double* Es = E + (size_t)s * 6 * D;
 #pragma unroll
       for (int c = 0; c < 6; ++c)
@@ -847,7 +767,7 @@ struct PostArgs {
   const int* vp_gl; const double* x_rho; double* c_rho;
   int nvt; const int* st_ptr; const int* st_cam; const double* Et; const double* Vinvt; const double* gt; const double* scale_vt; double* delta_vt;
   const int* vt_gl; const double* x_theta; double* c_theta;
-  const double* yc; double* parts_step;
+  const double* yc; const int* doff; double* parts_step;
   int K; const int* camslot; const double* x_cams; const double* scale_c; double* delta_c; double* c_cams; double* sc; double norm_weight;
   const double* graw; double* mx;
   int b_p, b_t, b_cam, b_gc, b_gp;   // CTA range ends: points | planes | candidate cameras | gmax cameras | gmax points | (rest) gmax planes
@@ -856,11 +776,11 @@ __global__ void __launch_bounds__(256) post_solve_kernel(PostArgs a) {
   PDL_PROLOGUE();
   const int b = blockIdx.x;
   if (b < a.b_p)
-    backsub_candidate_body<1>(b, a.nvp, a.sp_ptr, a.sp_cam, a.Ep, a.Vinvp, a.gp, a.yc, a.scale_vp, a.delta_vp, a.vp_gl, a.x_rho, a.c_rho, a.parts_step);
+    backsub_candidate_body<1>(b, a.nvp, a.sp_ptr, a.sp_cam, a.Ep, a.Vinvp, a.gp, a.yc, a.doff, a.scale_vp, a.delta_vp, a.vp_gl, a.x_rho, a.c_rho, a.parts_step);
   else if (b < a.b_t)
-    backsub_candidate_body<3>(b - a.b_p, a.nvt, a.st_ptr, a.st_cam, a.Et, a.Vinvt, a.gt, a.yc, a.scale_vt, a.delta_vt, a.vt_gl, a.x_theta, a.c_theta,
+    backsub_candidate_body<3>(b - a.b_p, a.nvt, a.st_ptr, a.st_cam, a.Et, a.Vinvt, a.gt, a.yc, a.doff, a.scale_vt, a.delta_vt, a.vt_gl, a.x_theta, a.c_theta,
                               a.parts_step + 2 * a.b_p);
-  else if (b < a.b_cam) candidate_cams_body(0, a.K, a.camslot, a.x_cams, a.yc, a.scale_c, a.delta_c, a.c_cams, a.sc, a.norm_weight);
+  else if (b < a.b_cam) candidate_cams_body(0, a.K, a.camslot, a.doff, a.x_cams, a.yc, a.scale_c, a.delta_c, a.c_cams, a.sc, a.norm_weight);
   else if (b < a.b_gc) gmax_cams_body(b - a.b_cam, a.K, a.camslot, a.x_cams, a.graw, a.mx);
   else if (b < a.b_gp) gmax_lm_body(b - a.b_gc, a.nvp, a.gp, a.scale_vp, a.mx);
   else gmax_lm_body(b - a.b_gp, 3 * a.nvt, a.gt, a.scale_vt, a.mx);
@@ -874,7 +794,7 @@ __global__ void __launch_bounds__(256) post_solve_kernel(PostArgs a) {
 // failure flag for the next iteration. Multi-GPU: host == nullptr here, the scalars are all-reduced first and
 // publish_scalars_kernel does the publishing.
 struct TailArgs {
-  const double* parts_step; int n_step;   // interleaved (step^2, candidate-norm^2) partial pairs of candidate_lm_kernel
+  const double* parts_step; int n_step;   // interleaved (step^2, candidate-norm^2) partial pairs of post_solve_kernel's landmark CTAs
   const double* parts_mcc; int n_mcc;     // model_cost_kernel partials
   const double* parts_cand; int n_cand;   // interleaved (cost, fixed cost) partial pairs of the candidate evaluation
   double* sc; double* mx; int* fail;
@@ -906,7 +826,7 @@ __global__ void __launch_bounds__(256) iteration_tail_kernel(TailArgs a) {
   const double cand = strided_sum_256(a.parts_cand, a.n_cand, 2, 0, s);
   const double cand_fixed = strided_sum_256(a.parts_cand, a.n_cand, 2, 1, s);
   if (threadIdx.x == 0) {
-    a.sc[SC_STEP2] += step2; a.sc[SC_CNORM2] += cn2;   // candidate_cams_kernel wrote the camera part
+    a.sc[SC_STEP2] += step2; a.sc[SC_CNORM2] += cn2;   // the candidate-camera CTA of post_solve_kernel wrote the camera part
     a.sc[SC_MCC] = mcc; a.sc[SC_CAND] = cand; a.sc[SC_CAND_FIXED] = cand_fixed;
     if (*a.fail) a.mx[MX_FAIL] = fmax(a.mx[MX_FAIL], 1.0);
     if (a.host) publish_to_host(a.sc, a.mx, a.fail, a.host, a.seq);
@@ -1024,12 +944,12 @@ static int analyze_on_host_and_upload(Solver& S, Analysis& A, std::chrono::stead
   try { analyze_structure(V, A, *ctx->host_arena); } catch (const std::exception& e) { return set_error(TSLAM_ERR_CUDA, "structure analysis failed: %s", e.what()); }
   S.K = A.K; S.nc = A.nc; S.nl = A.nl; S.npl = A.npl; S.lp = A.lp; S.lt = A.lt;
   S.nvp = A.nvp; S.nvt = A.nvt; S.nsp = A.nsp; S.nst = A.nst; S.nblk = A.nblk;
-  S.n = A.n; S.ld = A.ld; S.rows = A.rows; S.Tn = A.Tn;
+  S.n = A.n; S.npad = A.npad; S.ld = A.ld; S.rows = A.rows; S.Tn = A.Tn;
   T1 = std::chrono::steady_clock::now();
   // ---- upload ----
   int rc = chol_upload(ctx, A.chol, &S.chol);
   if (rc) return rc;
-  TSL_CUDA(up(S.camslot_d, A.camslot, st));
+  TSL_CUDA(up(S.camslot_d, A.camslot, st)); TSL_CUDA(up(S.doff, A.doff, st));
   TSL_CUDA(up(S.p_cs, A.p_cs, st)); TSL_CUDA(up(S.p_hs, A.p_hs, st)); TSL_CUDA(up(S.p_ls, A.LP.obs_ls, st));
   TSL_CUDA(up(S.t_cs, A.t_cs, st)); TSL_CUDA(up(S.t_hs, A.t_hs, st)); TSL_CUDA(up(S.t_ls, A.LT.obs_ls, st));
   TSL_CUDA(up(S.p_active, A.p_act, st)); TSL_CUDA(up(S.t_active, A.t_act, st)); TSL_CUDA(up(S.t_fmask, A.t_fm, st));
@@ -1220,8 +1140,8 @@ static int compute_step(Solver& S, double radius) {
   mark(S, 4);  // Cholesky
   if (nc) {
     { int rc = chol_clear(ctx, S.chol, S.A.p); if (rc) return rc; }
-    ScatterArgs Sa{S.nblk, S.blk_a.p, S.blk_b.p, S.Sblk, S.bvec, S.udiag, inv_radius, S.A.p, S.ld, S.n, S.rows, S.Tn * 64};
-    const int total = S.nblk * 36 + S.ld;
+    ScatterArgs Sa{S.nblk, S.blk_a.p, S.blk_b.p, S.Sblk, S.bvec, S.udiag, inv_radius, S.A.p, S.ld, S.n, S.rows, S.Tn * 64, S.doff.p};
+    const int total = S.nblk * 36 + S.n;
     LAUNCH(launch_k(scatter_kernel, grid_for(total, 256), 256, 0, st, Sa));
     TSL_CHECK_LAUNCH();
     int rc = chol_solve(ctx, S.chol, S.A.p, S.ywork.p, S.yc.p, S.fail.p);
@@ -1235,7 +1155,7 @@ static int compute_step(Solver& S, double radius) {
     a.delta_vp = S.delta_vp.p; a.vp_gl = S.vp_gl.p; a.x_rho = S.x_rho; a.c_rho = S.c_rho;
     a.nvt = S.nvt; a.st_ptr = S.st_ptr.p; a.st_cam = S.st_cam.p; a.Et = S.Et.p; a.Vinvt = S.Vinvt.p; a.gt = S.gt.p; a.scale_vt = S.scale_vt.p;
     a.delta_vt = S.delta_vt.p; a.vt_gl = S.vt_gl.p; a.x_theta = S.x_theta; a.c_theta = S.c_theta;
-    a.yc = S.yc.p; a.parts_step = S.parts_step.p;   // pairs summed onto sc[SC_STEP2], sc[SC_CNORM2] by iteration_tail_kernel
+    a.yc = S.yc.p; a.doff = S.doff.p; a.parts_step = S.parts_step.p;   // pairs summed onto sc[SC_STEP2], sc[SC_CNORM2] by iteration_tail_kernel
     a.K = S.K; a.camslot = S.camslot_d.p; a.x_cams = S.x_cams; a.scale_c = S.scale_c.p; a.delta_c = S.delta_c.p; a.c_cams = S.c_cams; a.sc = S.sc;
     a.norm_weight = ctx->rank == 0 ? 1.0 : 0.0;
     a.graw = S.graw; a.mx = S.mx.p;   // graw (cams) comes from the reduced-system build and is already all-reduced; landmark gradients are local
@@ -1388,7 +1308,7 @@ static int run_lm(Solver& S, const tslam_solve_options* opt, int max_iters, tsla
     const double rel = cost_change / mcc;
     if (rel > min_rel_dec) {
       // both buffers carry the untouched (fixed / non-owned) landmark entries since the copy before iteration 0, and
-      // candidate_lm_kernel rewrites every owned free entry each iteration: a pointer swap is all an accepted step needs
+      // post_solve_kernel rewrites every owned free landmark entry each iteration: a pointer swap is all an accepted step needs
       std::swap(S.x_cams, S.c_cams); std::swap(S.x_rho, S.c_rho); std::swap(S.x_theta, S.c_theta);
       x_norm = std::sqrt(h[SC_CNORM2]);
       mark(S, 0);  // eval + J (the next iteration's linearisation point)

@@ -244,7 +244,13 @@ __global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ A,
   PDL_PROLOGUE();
   const int2 it = items[blockIdx.x];
   double* T = A + (size_t)(it.y < 0 ? it.x : it.y) * NB * ld + (size_t)it.x * NB;
-  for (int e = threadIdx.x; e < NB * NB / 2; e += 256) { const int r = e >> 5, c = (e & 31) * 2; *reinterpret_cast<double2*>(T + (size_t)r * ld + c) = make_double2(0.0, 0.0); }
+  // diagonal tiles get a unit diagonal: the columns no camera owns (padding of the tile-aligned layout, nd_layout.h) stay
+  // decoupled identity rows, the real diagonal entries are overwritten by scatter_kernel
+  const bool dg = it.y < 0;
+  for (int e = threadIdx.x; e < NB * NB / 2; e += 256) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(T + (size_t)r * ld + c) = make_double2(dg && r == c ? 1.0 : 0.0, dg && r == c + 1 ? 1.0 : 0.0);
+  }
 }
 
 __global__ void copy_row_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {

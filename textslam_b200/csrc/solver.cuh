@@ -29,9 +29,10 @@ struct SolverIndex {
   int nvp = 0, nvt = 0, nsp = 0, nst = 0;     // owned landmarks / (landmark, camera) slots
   int nblk = 0, noff = 0;                     // non-zero 6x6 blocks (a <= b), of which off-diagonal
   long long est_entries = 0;                  // gather-list entries over all blocks (an upper estimate on the device path)
-  int n = 0, ld = 0, rows = 0, Tn = 0;        // reduced system dims
+  int n = 0, npad = 0, ld = 0, rows = 0, Tn = 0;   // reduced system: 6 nc unknowns, columns of the tile-aligned layout, workspace dims
   std::vector<int> camslot;                   // host copies (multi-GPU result merge only)
   std::vector<int> vp_gl_h, vt_gl_h, lmfree_p_h, lmfree_t_h;
+  DevBuf<int> doff;                           // first column of each camera slot in the dense reduced matrix (nd_layout.h)
   DevBuf<int> camslot_d, p_cs, p_hs, p_ls, t_cs, t_hs, t_ls;
   DevBuf<uint8_t> p_active, t_active, t_fmask;
   DevBuf<int> vp_gl, vt_gl, vp_obs_ptr, vp_obs, vt_obs_ptr, vt_obs;
