@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 GLOBAL_BA_ITERS = 20  # src/optimizer.cc:411-414
 POINT_EVAL_BYTES = 268  # 44 B in + 224 B out per auto_BAScene(NW) evaluation
 # dram__bytes_read.sum + dram__bytes_write.sum of one x16 launch from the committed ncu --set full capture
-# (profiles/r1_ncu_point_eval_x16.txt: 76.1 MB + 298.2 MB; part of the 358 MB output is still in L2 at kernel end)
-NCU_TRAFFIC_X16 = 374.3e6
+# (profiles/r1_ncu_point_eval_x16_end.txt: 76.1 MB + 299.3 MB; part of the 358 MB output is still in L2 at kernel end)
+NCU_TRAFFIC_X16 = 375.4e6
 WORKLOAD = "C5 global BA: 500 KF x 100k auto_BASceneNW obs (25k landmarks x 4 obs, band +-10, text off as src/optimizer.cc:1707), <=20 LM its"
 
 
@@ -334,7 +334,7 @@ def main():
                                "mevals_per_s": prob.n_pobs / (ms * 1e-3) / 1e6,
                                "note": "one partial wave (782 CTAs on 148 SMs): launch/latency bound, see DESIGN.md"}
         line["dominant_kernel"] = {"name": "potrf_trsm_kernel (64x64 tile factor + triangular solve of the reduced camera system)",
-                                   "share_of_lm_iteration": "largest single kernel of the step (profiles/r1_launches_lm.txt); 14 dependent waves per factorisation",
+                                   "share_of_lm_iteration": f"largest single kernel of the step (profiles/r1_launches_lm_end.txt); {T.analyze_structure(prob)['n_waves']} dependent waves per factorisation",
                                    "bound": "latency: 64 dependent pivots per tile (rsqrt -> scale -> update -> broadcast, ~185 cycles each, tools/ubench/chol_tile_bench.cu); FP64 tensor work of the step is syrk_wave_kernel"}
         # ---- CPU baseline beside it: oracle port, bounded sample
         from oracle import pyoracle as po
