@@ -42,3 +42,23 @@ def test_pdl_on_and_off_are_bit_identical():
     on, off = _run("1"), _run("0")
     assert on == off
     assert on["gba"]["iterations"] >= 3
+
+
+def test_two_tile_panels_match_single_tile_schedule():
+    """TSLAM_CHOL_PAIR=1 factors the two tiles of a layout node in one CTA (potrf2_trsm2_kernel): same iteration sequence,
+    results equal to rounding (the trailing updates are summed in a different order)."""
+    base = _run("1")
+    env = dict(os.environ, TSLAM_CHOL_PAIR="1")
+    p = subprocess.run([sys.executable, "-c", CHILD.replace('"final_cost": summ["final_cost"].hex()', '"final_cost": summ["final_cost"].hex(), "cams": prob.cams.tolist()') % ROOT],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    pair = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    p0 = subprocess.run([sys.executable, "-c", CHILD.replace('"final_cost": summ["final_cost"].hex()', '"final_cost": summ["final_cost"].hex(), "cams": prob.cams.tolist()') % ROOT],
+                        env=dict(os.environ, TSLAM_CHOL_PAIR="0"), capture_output=True, text=True, timeout=300)
+    single = json.loads([l for l in p0.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    for name in ("c4", "gba"):
+        assert pair[name]["iterations"] == single[name]["iterations"] == base[name]["iterations"]
+        a, b = np.array(pair[name]["cams"]), np.array(single[name]["cams"])
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+        fa, fb = float.fromhex(pair[name]["final_cost"]), float.fromhex(single[name]["final_cost"])
+        assert abs(fa - fb) <= 1e-10 * abs(fb)

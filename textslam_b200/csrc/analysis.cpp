@@ -242,42 +242,93 @@ void chol_symbolic_host(int n, const AVec<uint8_t>& tile_nz, CholHost& H) {
     for (size_t a = 0; a < nz.size(); ++a)
       for (size_t b = 0; b <= a; ++b) P[(size_t)nz[a] * T1 + nz[b]] = 1;
   }
-  AVec<int> wave(Tn, 0);
-  int nwaves = 0;
+  // ---- units of the schedule: single tiles, or PAIRS of consecutive coupled tiles (a, a+1) that one CTA factors together
+  // (potrf2_trsm2_kernel: L_aa, L_ba, the update of A_bb and L_bb without leaving the SM). In the tile-aligned camera layout
+  // (nd_layout.h) every node is two tiles wide, so a pair is a node and a tree level costs one launch pair instead of two.
+  // A pair is formed when the second tile has no dependency that finishes later than the first tile's own dependencies.
+  AVec<int> wave(Tn, 0);   // per-tile level of the plain (unpaired) schedule, used for the pairing test only
   for (int j = 0; j < Tn; ++j) {
     int w = 0;
     for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, wave[k] + 1);
-    wave[j] = w; nwaves = std::max(nwaves, w + 1);
+    wave[j] = w;
+  }
+  // Measured on the 500-keyframe global BA (profiles/r1_notes.md): 5 waves instead of 10, but a pair CTA runs its two 64-pivot
+  // chains back to back (38 us per launch against 2 x 19 us), so the factorisation time is unchanged (283 vs 279 us) — the
+  // schedule is kept behind TSLAM_CHOL_PAIR=1 until the pair kernel overlaps the row-tile work with the second chain.
+  static const bool pairing = [] { const char* e = getenv("TSLAM_CHOL_PAIR"); return e && e[0] == '1'; }();
+  AVec<int> unit_of(Tn, -1), unit_first, unit_size;
+  for (int j = 0; j < Tn;) {
+    bool pair = pairing && j + 1 < Tn && P[(size_t)(j + 1) * T1 + j];
+    if (pair)
+      for (int k = 0; k < j; ++k) if (P[(size_t)(j + 1) * T1 + k] && wave[k] >= wave[j]) { pair = false; break; }
+    unit_of[j] = (int)unit_first.size();
+    if (pair) unit_of[j + 1] = (int)unit_first.size();
+    unit_first.push_back(j); unit_size.push_back(pair ? 2 : 1);
+    j += pair ? 2 : 1;
+  }
+  const int nunits = (int)unit_first.size();
+  AVec<int> uwave(nunits, 0);
+  int nwaves = 0;
+  for (int u = 0; u < nunits; ++u) {
+    int w = 0;
+    for (int t = 0; t < unit_size[u]; ++t) {
+      const int j = unit_first[u] + t;
+      for (int k = 0; k < unit_first[u]; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, uwave[unit_of[k]] + 1);
+    }
+    uwave[u] = w; nwaves = std::max(nwaves, w + 1);
   }
   H.nwaves = nwaves;
-  AVec<AVec<int>> wave_panels(nwaves);
-  for (int j = 0; j < Tn; ++j) wave_panels[wave[j]].push_back(j);
-  H.item_ptr.assign(nwaves + 1, 0); H.target_ptr.assign(nwaves + 1, 0); H.panel_ptr.assign(nwaves + 1, 0);
+  AVec<AVec<int>> wave_units(nwaves);
+  for (int u = 0; u < nunits; ++u) wave_units[uwave[u]].push_back(u);
+  H.item_ptr.assign(nwaves + 1, 0); H.item2_ptr.assign(nwaves + 1, 0); H.target_ptr.assign(nwaves + 1, 0); H.panel_ptr.assign(nwaves + 1, 0);
   H.src_ptr.push_back(0); H.below_ptr.push_back(0);
+  for (int j = 0; j < Tn; ++j) {   // every tile of the factor pattern (cleared before the reduced system is scattered)
+    H.clear_items.push_back(I2{j, -1});
+    for (int i : below[j]) H.clear_items.push_back(I2{j, i});
+  }
   AVec<int> tgt_index((size_t)T1 * T1, -1);
   for (int w = 0; w < nwaves; ++w) {
     const size_t t_begin = H.targets.size();
     AVec<AVec<int>> tsrc;
-    for (int j : wave_panels[w]) {
-      H.items.push_back(I2{j, -1});
-      for (int i : below[j]) H.items.push_back(I2{j, i});
+    auto add_updates = [&](int j, int skip_tile) {   // trailing updates of panel j; targets in column skip_tile are done inside the pair kernel
       const AVec<int>& nz = below[j];
       for (size_t a = 0; a < nz.size(); ++a)
         for (size_t b = 0; b <= a; ++b) {
           const int i = nz[a], k = nz[b];
           if (i == Tn && k == Tn) continue;   // (b row, b row) is never read
+          if (k == skip_tile) continue;
           int& ti = tgt_index[(size_t)i * T1 + k];
           if (ti < (int)t_begin) { ti = (int)H.targets.size(); H.targets.push_back(I2{i, k}); tsrc.emplace_back(); }
           tsrc[ti - t_begin].push_back(j);
           ++H.gemm_tiles;
         }
-      H.panels.push_back(j);   // backward solve: tiles (i, j) of the factor below the diagonal, excluding the b row
-      for (int i : below[j]) if (i < Tn) H.below.push_back(i);
-      H.below_ptr.push_back((int)H.below.size());
+    };
+    for (int u : wave_units[w]) {
+      const int j = unit_first[u];
+      if (unit_size[u] == 1) {
+        H.items.push_back(I2{j, -1});
+        for (int i : below[j]) H.items.push_back(I2{j, i});
+        add_updates(j, -1);
+      } else {
+        // pair (j, j+1): one CTA per row tile of column j+1 (+ one for the diagonal); x carries bit 30 when the row tile is
+        // structurally absent from column j
+        H.items2.push_back(I2{j, -1});
+        for (int i : below[j + 1]) H.items2.push_back(I2{P[(size_t)i * T1 + j] ? j : (j | (1 << 30)), i});
+        add_updates(j, j + 1);
+        add_updates(j + 1, -1);
+        H.gemm_tiles += 2 * (long long)below[j + 1].size() + 1;   // the in-kernel updates of A_bb and of the row tiles of column j+1
+      }
+      for (int t = 0; t < unit_size[u]; ++t) {   // backward solve: tiles (i, j) of the factor below the diagonal, excluding the b row
+        const int jj = j + t;
+        H.panels.push_back(jj);
+        for (int i : below[jj]) if (i < Tn) H.below.push_back(i);
+        H.below_ptr.push_back((int)H.below.size());
+      }
     }
     for (auto& v : tsrc) { for (int j : v) H.src.push_back(j); H.src_ptr.push_back((int)H.src.size()); }
     for (size_t t = t_begin; t < H.targets.size(); ++t) tgt_index[(size_t)H.targets[t].x * T1 + H.targets[t].y] = -1;
-    H.item_ptr[w + 1] = (int)H.items.size(); H.target_ptr[w + 1] = (int)H.targets.size(); H.panel_ptr[w + 1] = (int)H.panels.size();
+    H.item_ptr[w + 1] = (int)H.items.size(); H.item2_ptr[w + 1] = (int)H.items2.size();
+    H.target_ptr[w + 1] = (int)H.targets.size(); H.panel_ptr[w + 1] = (int)H.panels.size();
   }
 }
 

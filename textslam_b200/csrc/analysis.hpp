@@ -67,8 +67,8 @@ struct LmSide {   // landmark-side structure of one landmark type (inverse depth
 struct CholHost {  // tile-level symbolic factorisation + level schedule (see chol.cu)
   int Tn = 0, n = 0, nwaves = 0;
   long long gemm_tiles = 0;
-  AVec<int> item_ptr, target_ptr, panel_ptr;
-  AVec<I2> items, targets;
+  AVec<int> item_ptr, item2_ptr, target_ptr, panel_ptr;   // per wave ranges
+  AVec<I2> items, items2, targets, clear_items;           // single-tile panels, two-tile panels (see analysis.cpp), update targets, all pattern tiles
   AVec<int> src_ptr, src, panels, below_ptr, below;
 };
 

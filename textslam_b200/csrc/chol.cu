@@ -80,6 +80,93 @@ __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restri
   }
 }
 
+// Two-tile panel (a, b = a + 1): what two potrf_trsm launches and the update launch between them did for the tiles of one node
+// of the camera layout, in ONE CTA per row tile (+ one for the diagonal):
+//   L_aa = chol(A_aa);  L_ba = A_ba L_aa^-T;  X_a = B_a L_aa^-T          (factor_solve_tile2<2>)
+//   A_bb -= L_ba L_ba^T;  B_b -= X_a L_ba^T                               (FP64 tensor MMAs, one team each)
+//   L_bb = chol(A_bb);  X_b = B_b L_bb^-T                                  (factor_solve_tile2<1>)
+// Every CTA redoes the (small) diagonal work straight from A: nobody writes A_aa, A_ba or A_bb in this launch. The diagonal
+// CTA stores L_aa^-1, L_bb^-1 (backward solve) and parks L_ba in `Lpair` — copy_pair_tiles_kernel moves it into the factor
+// once every CTA of the launch has read A_ba. Bit 30 of item.x: the row tile is structurally absent from column a.
+__global__ void __launch_bounds__(P2_THREADS) potrf2_trsm2_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
+                                                                  int* __restrict__ fail, double* __restrict__ Linv, double* __restrict__ Lpair) {
+  PDL_TRIGGER();
+  extern __shared__ __align__(16) double smem[];
+  double* sTa = smem;
+  double* sXba = smem + 1 * NB * LD2;
+  double* sXia = smem + 2 * NB * LD2;
+  double* sTb = smem + 3 * NB * LD2;
+  double* sXib = smem + 4 * NB * LD2;
+  double* sLt = smem + 5 * NB * LD2;
+  __shared__ double sinv[2 * NB];
+  const int2 it = items[blockIdx.x];   // schedule of the symbolic factorisation: constant, read before the dependency wait
+  PDL_WAIT();
+  const int a = it.x & 0x3fffffff, b = a + 1, i = it.y;
+  const bool has_a = (it.x & (1 << 30)) == 0, dg = i < 0;
+  const double* Aaa = A + (size_t)a * NB * ld + (size_t)a * NB;
+  const double* Aba = A + (size_t)b * NB * ld + (size_t)a * NB;
+  const double* Abb = A + (size_t)b * NB * ld + (size_t)b * NB;
+  double* Bia = dg ? nullptr : A + (size_t)i * NB * ld + (size_t)a * NB;
+  double* Bib = dg ? nullptr : A + (size_t)i * NB * ld + (size_t)b * NB;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {   // all global loads of a batch are issued before the first shared-memory store
+    double2 v0[4], v1[4], v2[4], v3[4], v4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = threadIdx.x + P2_THREADS * (4 * q + u), r = e >> 5, c = (e & 31) * 2;
+      const double2 idn = make_double2(r == c ? 1.0 : 0.0, r == c + 1 ? 1.0 : 0.0);
+      v0[u] = *reinterpret_cast<const double2*>(Aaa + (size_t)r * ld + c);
+      v1[u] = *reinterpret_cast<const double2*>(Aba + (size_t)r * ld + c);
+      v2[u] = *reinterpret_cast<const double2*>(Abb + (size_t)r * ld + c);
+      v3[u] = dg ? idn : (has_a ? *reinterpret_cast<const double2*>(Bia + (size_t)r * ld + c) : make_double2(0.0, 0.0));
+      v4[u] = dg ? idn : *reinterpret_cast<const double2*>(Bib + (size_t)r * ld + c);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = threadIdx.x + P2_THREADS * (4 * q + u), r = e >> 5, c = (e & 31) * 2;
+      *reinterpret_cast<double2*>(sTa + r * LD2 + c) = make_double2(c <= r ? v0[u].x : 0.0, c + 1 <= r ? v0[u].y : 0.0);
+      *reinterpret_cast<double2*>(sXba + r * LD2 + c) = v1[u];
+      *reinterpret_cast<double2*>(sTb + r * LD2 + c) = make_double2(c <= r ? v2[u].x : 0.0, c + 1 <= r ? v2[u].y : 0.0);
+      *reinterpret_cast<double2*>(sXia + r * LD2 + c) = v3[u];
+      *reinterpret_cast<double2*>(sXib + r * LD2 + c) = v4[u];
+    }
+  }
+  __syncthreads();
+  factor_solve_tile2<2>(sTa, sXba, sXia, sLt, sinv, fail);
+  if (threadIdx.x < 128) smem_gemm64_nt_dmma(sTb, sXba, sXba, threadIdx.x);
+  else if (!dg && has_a) smem_gemm64_nt_dmma(sXib, sXia, sXba, threadIdx.x - 128);
+  __syncthreads();
+  factor_solve_tile2<1>(sTb, sXib, nullptr, sLt, sinv + NB, fail);
+  if (dg) {   // off the critical path: L_aa^-1 = X_a^T, L_bb^-1 = X_b^T (row-major) for the backward solve, L_ba for the factor
+    double* da = Linv + (size_t)a * NB * NB;
+    double* db = Linv + (size_t)b * NB * NB;
+    double* dp = Lpair + (size_t)a * NB * NB;
+    for (int e = threadIdx.x; e < NB * NB; e += P2_THREADS) {
+      const int r = e >> 6, c = e & 63;
+      da[e] = sXia[c * LD2 + r]; db[e] = sXib[c * LD2 + r]; dp[e] = sXba[r * LD2 + c];
+    }
+    return;
+  }
+  for (int e = threadIdx.x; e < NB * NB / 2; e += P2_THREADS) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    if (has_a) *reinterpret_cast<double2*>(Bia + (size_t)r * ld + c) = *reinterpret_cast<const double2*>(sXia + r * LD2 + c);
+    *reinterpret_cast<double2*>(Bib + (size_t)r * ld + c) = *reinterpret_cast<const double2*>(sXib + r * LD2 + c);
+  }
+}
+
+// L_ba of every two-tile panel from its parking buffer into tile (a + 1, a) of the factor (read by the backward solve).
+__global__ void __launch_bounds__(256) copy_pair_tiles_kernel(double* __restrict__ A, int ld, const int* __restrict__ pair_a, const double* __restrict__ Lpair) {
+  PDL_TRIGGER();
+  const int a = pair_a[blockIdx.x];
+  PDL_WAIT();
+  const double* src = Lpair + (size_t)a * NB * NB;
+  double* dst = A + (size_t)(a + 1) * NB * ld + (size_t)a * NB;
+  for (int e = threadIdx.x; e < NB * NB / 2; e += 256) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    *reinterpret_cast<double2*>(dst + (size_t)r * ld + c) = *reinterpret_cast<const double2*>(src + r * NB + c);
+  }
+}
+
 // trailing update of one wave: four CTAs per target tile (i,k), one per 32x32 quadrant; each sums the contributions
 // X_i^(j) X_k^(j)^T of every source panel j of this wave (no two CTAs touch the same element, so no atomics and a fixed
 // summation order). A wave has at most ~100 target tiles with 1-2 sources each, so a whole-tile CTA (64^3 FMAs = 2.2 us
@@ -268,10 +355,13 @@ __global__ void copy_row_kernel(const double* __restrict__ src, double* __restri
 int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
   sym->Tn = H.Tn; sym->n = H.n; sym->nwaves = H.nwaves; sym->gemm_tiles = H.gemm_tiles;
   sym->item_ptr.assign(H.item_ptr.begin(), H.item_ptr.end()); sym->target_ptr.assign(H.target_ptr.begin(), H.target_ptr.end());
+  sym->item2_ptr.assign(H.item2_ptr.begin(), H.item2_ptr.end()); sym->n_clear = (int)H.clear_items.size();
   sym->panel_ptr.assign(H.panel_ptr.begin(), H.panel_ptr.end());
   cudaStream_t s = ctx->stream;
   static_assert(sizeof(I2) == sizeof(int2), "I2 must match int2");
   TSL_CUDA(sym->items.upload(reinterpret_cast<const int2*>(H.items.data()), H.items.size(), s));
+  TSL_CUDA(sym->items2.upload(reinterpret_cast<const int2*>(H.items2.data()), H.items2.size(), s));
+  TSL_CUDA(sym->clear_items.upload(reinterpret_cast<const int2*>(H.clear_items.data()), H.clear_items.size(), s));
   TSL_CUDA(sym->targets.upload(reinterpret_cast<const int2*>(H.targets.data()), H.targets.size(), s));
   TSL_CUDA(sym->src_ptr.upload(H.src_ptr.data(), H.src_ptr.size(), s));
   TSL_CUDA(sym->src.upload(H.src.data(), H.src.size(), s));
@@ -279,6 +369,14 @@ int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
   TSL_CUDA(sym->below_ptr.upload(H.below_ptr.data(), H.below_ptr.size(), s));
   TSL_CUDA(sym->below.upload(H.below.data(), H.below.size(), s));
   TSL_CUDA(sym->Ldiag.reserve((size_t)(H.Tn ? H.Tn : 1) * NB * NB));
+  {
+    std::vector<int> pa;
+    for (const I2& it : H.items2) if (it.y < 0) pa.push_back(it.x);
+    sym->n_pairs = (int)pa.size();
+    TSL_CUDA(sym->pair_a.upload(pa.data(), pa.size(), s));
+    TSL_CUDA(cudaStreamSynchronize(s));   // pa is a local
+    if (sym->n_pairs) TSL_CUDA(sym->Lpair.reserve((size_t)H.Tn * NB * NB));
+  }
   TSL_CUDA(sym->flags.reserve((size_t)(H.Tn ? H.Tn : 1)));
   TSL_CUDA(cudaMemsetAsync(sym->flags.p, 0, sizeof(int) * (size_t)(H.Tn ? H.Tn : 1), s));
   sym->epoch = 0;
@@ -289,8 +387,8 @@ int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
 int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A) {
   int ld, rows;
   chol_workspace_dims(sym.n, &ld, &rows);
-  const int ni = sym.item_ptr[sym.nwaves];
-  if (ni > 0) LAUNCH(launch_k(zero_tiles_kernel, ni, 256, 0, ctx->stream, A, ld, sym.items.p));
+  const int ni = sym.n_clear;
+  if (ni > 0) LAUNCH(launch_k(zero_tiles_kernel, ni, 256, 0, ctx->stream, A, ld, sym.clear_items.p));
   TSL_CHECK_LAUNCH();
   return TSLAM_OK;
 }
@@ -303,7 +401,9 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   static bool attr_set = false;
   const int smem = 2 * QB * SPAD * (int)sizeof(double);
   const int smem_pt = 3 * NB * LD2 * (int)sizeof(double);
+  const int smem_p2 = 6 * NB * LD2 * (int)sizeof(double);
   if (!attr_set) {
+    TSL_CUDA(cudaFuncSetAttribute(potrf2_trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p2));
     TSL_CUDA(cudaFuncSetAttribute(syrk_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
     attr_set = true;
@@ -315,13 +415,15 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   auto mark = [&](int c) { if (!trace) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); cls.push_back(c); };
   mark(-1);
   for (int w = 0; w < sym.nwaves; ++w) {
-    const int ni = sym.item_ptr[w + 1] - sym.item_ptr[w], nt = sym.target_ptr[w + 1] - sym.target_ptr[w];
-    LAUNCH(launch_k(potrf_trsm_kernel, ni, PT_THREADS, smem_pt, s, A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+    const int ni = sym.item_ptr[w + 1] - sym.item_ptr[w], ni2 = sym.item2_ptr[w + 1] - sym.item2_ptr[w], nt = sym.target_ptr[w + 1] - sym.target_ptr[w];
+    if (ni2 > 0) LAUNCH(launch_k(potrf2_trsm2_kernel, ni2, P2_THREADS, smem_p2, s, A, ld, sym.items2.p + sym.item2_ptr[w], d_fail, sym.Ldiag.p, sym.Lpair.p));
+    if (ni > 0) LAUNCH(launch_k(potrf_trsm_kernel, ni, PT_THREADS, smem_pt, s, A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
     mark(0);
     if (nt > 0) LAUNCH(launch_k(syrk_wave_kernel, 4 * nt, 128, smem, s, A, ld, sym.targets.p + sym.target_ptr[w], sym.src_ptr.p + sym.target_ptr[w], sym.src.p));
     mark(1);
   }
   TSL_CHECK_LAUNCH();
+  if (sym.n_pairs > 0) LAUNCH(launch_k(copy_pair_tiles_kernel, sym.n_pairs, 256, 0, s, A, ld, sym.pair_a.p, sym.Lpair.p));
   {
     const int np = sym.panel_ptr[sym.nwaves];
     const int epoch = ++sym.epoch;

@@ -334,4 +334,68 @@ __device__ __forceinline__ void factor_solve_tile(double* sT, double* sX, double
 #undef TSL_STAMP
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-tile panels (potrf2_trsm2_kernel, 256-thread CTA = two teams of 4 warps).
+// ---------------------------------------------------------------------------------------------
+constexpr int P2_THREADS = 256;
+
+// C (64 x 64) -= A (64 x 64) B (64 x 64)^T, everything in shared memory (leading dimension LD2), by ONE team of 4 warps
+// (tid in [0, 128)) with FP64 tensor MMAs; fragment layout as in gemm_tile_nt (warp tile 32 x 32).
+__device__ __forceinline__ void smem_gemm64_nt_dmma(double* C, const double* A, const double* B, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+  const int g = lane >> 2, tg = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < NB; k0 += 4) {
+    double fa[4], fb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) fa[a] = A[(wr + 8 * a + g) * LD2 + k0 + tg];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) fb[b] = B[(wc + 8 * b + g) * LD2 + k0 + tg];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double2* p = reinterpret_cast<double2*>(C + (wr + 8 * a + g) * LD2 + wc + 8 * b + 2 * tg);
+      double2 v = *p;
+      v.x -= acc[a][b][0]; v.y -= acc[a][b][1];
+      *p = v;
+    }
+}
+
+// factor_solve_tile for a 256-thread CTA and NX (1 or 2) row tiles: the second row tile rides on warps 4-5 / 2-3 of the
+// same phases (identical instruction streams side by side), its rank-32 update on the second team.
+template <int NX>
+__device__ __forceinline__ void factor_solve_tile2(double* sT, double* sX0, double* sX1, double* sLt, double* sinv, int* fail) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) potrf32_rl(sT, sLt, sinv, fail);
+  __syncthreads();
+  if (warp == 0) trsm32_row(sT + (HB + tid) * LD2, sLt, sinv);
+  else if (warp == 2 || warp == 3) trsm32_row(sX0 + (tid - 64) * LD2, sLt, sinv);
+  else if (NX == 2 && (warp == 4 || warp == 5)) trsm32_row(sX1 + (tid - 128) * LD2, sLt, sinv);
+  __syncthreads();
+  if (tid < 128) {
+    gemm_nt32_il<2>(sT + HB * LD2 + HB, sT + HB * LD2, sT + HB * LD2, HB, tid);
+    gemm_nt32_il<4>(sX0 + HB, sX0, sT + HB * LD2, NB, tid);
+  } else if (NX == 2) {
+    gemm_nt32_il<4>(sX1 + HB, sX1, sT + HB * LD2, NB, tid - 128);
+  }
+  __syncthreads();
+  if (warp == 0) potrf32_rl(sT + HB * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB, fail);
+  __syncthreads();
+  if (warp < 2) trsm32_row(sX0 + tid * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB);
+  else if (NX == 2 && warp < 4) trsm32_row(sX1 + (tid - 64) * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB);
+  __syncthreads();
+}
+
 }  // namespace tsl

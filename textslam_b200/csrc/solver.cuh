@@ -8,10 +8,13 @@ namespace tsl {
 // chol.cu
 struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (per problem structure)
   int Tn = 0, n = 0, nwaves = 0;
-  std::vector<int> item_ptr, target_ptr, panel_ptr;   // per wave ranges into the device lists
-  DevBuf<int2> items, targets;                        // (panel, row tile | -1), (target tile i, k)
+  std::vector<int> item_ptr, item2_ptr, target_ptr, panel_ptr;   // per wave ranges into the device lists
+  DevBuf<int2> items, items2, targets, clear_items;   // single-tile panels (panel, row tile | -1), two-tile panels, (target tile i, k), all pattern tiles
+  int n_clear = 0;
   DevBuf<int> src_ptr, src;                           // per target: source panels of its wave
   DevBuf<int> panels, below_ptr, below;               // backward solve: panels per wave and their non-zero tiles below
+  DevBuf<int> pair_a; int n_pairs = 0;                // first tiles of the two-tile panels
+  mutable DevBuf<double> Lpair;                       // per two-tile panel: L_ba parked until every CTA of its launch has read A_ba
   mutable DevBuf<double> Ldiag;                       // Tn inverse diagonal factors L_jj^-1 (64x64, tight)
   mutable DevBuf<int> flags;                          // backward solve: flags[j] == epoch <=> x_j final in the current call
   mutable int epoch = 0;
