@@ -142,6 +142,41 @@ __device__ __forceinline__ int fast_measure_bisect(const uint8_t* p, int stride,
   return lo + 1;
 }
 
+// The same measure in closed form: m = max(m_bright, m_dark), m_bright = max over the 16 arcs of the minimum of (c_k - p) over the
+// arc's 9 pixels (m_dark with p - c_k). The 16 sliding-window minima over the circular ring come from a doubling ladder
+// (windows of 2, 4, 8, then 8 + 1): 4 x 16 integer min per polarity instead of 8 bisection steps x 32 comparisons.
+// corner at t <=> m > t, so the bisection's result (largest corner threshold + 1) is m itself, 0 when m <= min_th.
+__device__ __forceinline__ int ring_max_of_window9_min(const int (&d)[16]) {
+  int w2[16], w4[16], w8[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w2[k] = min(d[k], d[(k + 1) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w4[k] = min(w2[k], w2[(k + 2) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w8[k] = min(w4[k], w4[(k + 4) & 15]);
+  int best = -256;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) best = max(best, min(w8[k], d[(k + 8) & 15]));
+  return best;
+}
+__device__ __forceinline__ int fast_measure_ladder(const uint8_t* p, int stride, int min_th) {
+  const int v = p[0];
+  int ring[16];
+  ring[0] = p[3 * stride]; ring[8] = p[-3 * stride]; ring[4] = p[3]; ring[12] = p[-3];
+  // every arc of 9 contains pixel 0 or 8, and pixel 4 or 12: most pixels are rejected after 5 loads
+  if ((abs(ring[0] - v) <= min_th && abs(ring[8] - v) <= min_th) || (abs(ring[4] - v) <= min_th && abs(ring[12] - v) <= min_th)) return 0;
+  ring[1] = p[3 * stride + 1]; ring[2] = p[2 * stride + 2]; ring[3] = p[stride + 3];
+  ring[5] = p[-stride + 3]; ring[6] = p[-2 * stride + 2]; ring[7] = p[-3 * stride + 1];
+  ring[9] = p[-3 * stride - 1]; ring[10] = p[-2 * stride - 2]; ring[11] = p[-stride - 3];
+  ring[13] = p[stride - 3]; ring[14] = p[2 * stride - 2]; ring[15] = p[3 * stride - 1];
+  int db[16], dd[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { db[k] = ring[k] - v; dd[k] = v - ring[k]; }
+  const int m = max(ring_max_of_window9_min(db), ring_max_of_window9_min(dd));
+  return m > min_th ? m : 0;
+}
+
+template <bool LADDER>
 __global__ void fast_score_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ score, size_t img_bytes, size_t off, int w, int h, int min_th) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= w) return;
@@ -149,7 +184,7 @@ __global__ void fast_score_kernel(const uint8_t* __restrict__ pyr, uint8_t* __re
   int m = 0;
   if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
     const uint8_t* p = pyr + base + (size_t)y * w + x;
-    m = fast_measure_bisect(p, w, min_th);
+    m = LADDER ? fast_measure_ladder(p, w, min_th) : fast_measure_bisect(p, w, min_th);
   }
   score[base + (size_t)y * w + x] = (uint8_t)min(max(m, 0), 255);
 }
@@ -688,7 +723,9 @@ static int orb_run(tslam_orb* o, int n) {
   for (int l = 0; l < o->nlevels; ++l) {
     const LevelInfo& li = o->L[l];
     dim3 grid((li.w + 127) / 128, li.h, n);
-    LAUNCH(fast_score_kernel<<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
+    static const bool bisect = getenv("TSLAM_FAST_BISECT") != nullptr;   // the first (bisection) formulation, kept for A/B runs
+    if (bisect) LAUNCH(fast_score_kernel<false><<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
+    else LAUNCH(fast_score_kernel<true><<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
     LAUNCH(cell_nms_kernel<<<dim3(li.ncells, n), 128, 0, st>>>(o->score.p, o->img_bytes, o->Ld.p, l, o->cells.p, o->total_cells, o->iniTh, o->minTh,
                                                                  o->slots.p, o->cell_count.p, o->err.p));
     dim3 bgrid((li.w + 31) / 32, (li.h + 7) / 8, n);
