@@ -819,12 +819,25 @@ __device__ __forceinline__ void publish_to_host(const double* sc, double* mx, in
 }
 __global__ void __launch_bounds__(256) iteration_tail_kernel(TailArgs a) {
   PDL_PROLOGUE();
-  __shared__ double s[256];
-  const double step2 = strided_sum_256(a.parts_step, a.n_step, 2, 0, s);
-  const double cn2 = strided_sum_256(a.parts_step, a.n_step, 2, 1, s);
-  const double mcc = strided_sum_256(a.parts_mcc, a.n_mcc, 1, 0, s);
-  const double cand = strided_sum_256(a.parts_cand, a.n_cand, 2, 0, s);
-  const double cand_fixed = strided_sum_256(a.parts_cand, a.n_cand, 2, 1, s);
+  // five sums at once: per-thread strided partials (all loads independent), then ONE tree over the five columns — the same
+  // pairing of additions as five sum_parts(_pair)_kernel launches, with 8 barriers instead of 45
+  __shared__ double s[5][256];
+  {
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
+    for (int i = threadIdx.x; i < a.n_step; i += 256) { p0 += a.parts_step[2 * (size_t)i]; p1 += a.parts_step[2 * (size_t)i + 1]; }
+    for (int i = threadIdx.x; i < a.n_mcc; i += 256) p2 += a.parts_mcc[i];
+    for (int i = threadIdx.x; i < a.n_cand; i += 256) { p3 += a.parts_cand[2 * (size_t)i]; p4 += a.parts_cand[2 * (size_t)i + 1]; }
+    s[0][threadIdx.x] = p0; s[1][threadIdx.x] = p1; s[2][threadIdx.x] = p2; s[3][threadIdx.x] = p3; s[4][threadIdx.x] = p4;
+  }
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const double step2 = s[0][0], cn2 = s[1][0], mcc = s[2][0], cand = s[3][0], cand_fixed = s[4][0];
   if (threadIdx.x == 0) {
     a.sc[SC_STEP2] += step2; a.sc[SC_CNORM2] += cn2;   // the candidate-camera CTA of post_solve_kernel wrote the camera part
     a.sc[SC_MCC] = mcc; a.sc[SC_CAND] = cand; a.sc[SC_CAND_FIXED] = cand_fixed;

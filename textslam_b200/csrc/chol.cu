@@ -200,19 +200,22 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) cv[a][b] = *reinterpret_cast<const double2*>(C + (size_t)(wr + 8 * a + g) * ld + wc + 8 * b + 2 * tgi);
-  for (int e = e_begin; e < e_end; ++e) {
-    const int j = j_next;
-    if (e + 1 < e_end) j_next = src[e + 1];
+  // software pipeline over the source panels: the 2 x 16 KB of source e + 1 are in flight (registers) while source e is
+  // multiplied out of shared memory
+  double2 va[8], vb[8];
+  auto fetch = [&](int j) {
     const double* Xi = A + ((size_t)tg.x * NB + QB * qi) * ld + (size_t)j * NB;
     const double* Xk = A + ((size_t)tg.y * NB + QB * qk) * ld + (size_t)j * NB;
-    __syncthreads();   // previous source fully consumed
-    double2 va[8], vb[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {   // 2 x 16 KB: every load is issued before the first shared-memory store
+    for (int u = 0; u < 8; ++u) {
       const int ee = threadIdx.x + 128 * u, r = ee >> 5, c2 = (ee & 31) * 2;
       va[u] = *reinterpret_cast<const double2*>(Xi + (size_t)r * ld + c2);
       vb[u] = *reinterpret_cast<const double2*>(Xk + (size_t)r * ld + c2);
     }
+  };
+  if (e_begin < e_end) fetch(j_next);
+  for (int e = e_begin; e < e_end; ++e) {
+    __syncthreads();   // previous source fully consumed
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int ee = threadIdx.x + 128 * u, r = ee >> 5, c2 = (ee & 31) * 2;
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(128) syrk_wave_kernel(double* __restrict__ A, 
       *reinterpret_cast<double2*>(sB + r * SPAD + c2) = vb[u];
     }
     __syncthreads();
+    if (e + 1 < e_end) fetch(src[e + 1]);
 #pragma unroll 4
     for (int k0 = 0; k0 < NB; k0 += 4) {
       double fa[2], fb[2];
