@@ -75,3 +75,20 @@ def test_structure_rejects_bad_indices():
     prob.p_lm = prob.p_lm.copy(); prob.p_lm[3] = len(prob.rho) + 7
     with pytest.raises(T.TslamError):
         T.analyze_structure(prob)
+
+
+def test_banded_problems_get_a_shallow_tile_elimination_tree():
+    """nd_layout.h: on a banded keyframe graph the tile-aligned nested-dissection layout must turn the chain of T panel steps into
+    L * tiles(separator) + tiles(leaf) waves (C5 shape: 498 free cameras, band 20 -> 4 levels of 2-tile separators + 2-tile leaves)."""
+    import textslam_b200 as T
+    info = T.analyze_structure(synth.c5_global_ba(seed=0))
+    assert info["n_free_cams"] == 498 and info["reduced_dim"] == 2988
+    assert info["n_tiles"] == 62 and info["n_waves"] == 10     # 15 separators x 2 tiles + 16 leaves x 2 tiles; natural order: 47 waves
+    small = T.analyze_structure(synth.c5_global_ba(seed=3, n_kf=100, n_lm=3000))   # < 128 free cameras: natural order, no padding
+    assert small["n_tiles"] == (6 * small["n_free_cams"] + 63) // 64
+    big = T.analyze_structure(synth.make_ba_problem(seed=8, n_kf=1000, n_lm=12000, obs_per_lm=4, band=10, fixed_cams=(0, 1), w_point=1.0))
+    assert big["n_waves"] <= 12 < big["n_tiles"]
+    # sharded analysis sees the same global structure on every rank
+    a, b = T.analyze_structure(synth.c5_global_ba(seed=0), rank=0, world=2), T.analyze_structure(synth.c5_global_ba(seed=0), rank=1, world=2)
+    for k in ("n_free_cams", "n_blocks", "n_tiles", "n_waves", "n_tile_updates"):
+        assert a[k] == b[k] == info[k]
