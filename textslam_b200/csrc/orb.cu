@@ -276,7 +276,34 @@ struct DistSmem {
   unsigned short order[MAXID], order2[MAXID], vsize[MAXID], vprev[MAXID], freelist[MAXID];
   int cell_off[MAXCELLS + 1];
   int ctl[8];
+  int wsum[3][8];                 // per-warp totals of the block scans
 };
+
+// exclusive scan of up to three counters over the 256 threads of the CTA (warp shuffles + one shared-memory hop);
+// tot[k] = block totals. Ends with a barrier, so wsum is reusable right away.
+template <int NV>
+__device__ __forceinline__ void block_exscan(const int (&v)[NV], int (&e)[NV], int (&tot)[NV], int (*wsum)[8]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) inc[k] = v[k];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { const int t = __shfl_up_sync(0xffffffffu, inc[k], o); if (lane >= o) inc[k] += t; }
+  if (lane == 31)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) wsum[k][w] = inc[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    int b = 0, t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int x = wsum[k][j]; if (j < w) b += x; t += x; }
+    e[k] = b + inc[k] - v[k]; tot[k] = t;
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ int quadrant_of(float x, float y, int mx, int my) {
   if (x < (float)mx) return (y < (float)my) ? 0 : 2;
@@ -395,8 +422,61 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
       }
     })
     __syncthreads();
-    // 3. sequential list surgery (thread 0)
-    if (tid == 0) {
+    // 3. list surgery. Coarse mode (every dividable node splits): all threads, three block scans over the list give each
+    // node its creation rank (children are numbered in list order, quadrant order), the slot of its big children in vsize
+    // and the slot of an untouched node in the kept list — the same lists the sequential walk of the reference builds.
+    if (mode == 0) {
+      const int nfree0 = S.ctl[0], seqc0 = S.ctl[1], live0 = S.ctl[2];
+      int* created = reinterpret_cast<int*>(S.best);   // scratch (best[] is only used at the very end)
+      int base_n = 0, base_big = 0, base_kept = 0;
+      for (int c0 = 0; c0 < live0; c0 += 256) {
+        const int i = c0 + tid;
+        int id = 0; bool sel = false;
+        int v[3] = {0, 0, 0}, e[3], tot[3];
+        if (i < live0) {
+          id = S.order[i]; sel = (S.flags[id] & 4) != 0;
+          if (sel) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int cc = S.childcnt[id][q]; v[0] += cc > 0; v[1] += cc > 1; }
+          } else v[2] = 1;
+        }
+        block_exscan<3>(v, e, tot, S.wsum);
+        if (i < live0) {
+          if (sel) {
+            int r = base_n + e[0], vb = base_big + e[1];
+            const int halfX = (int)ceilf((float)(S.urx[id] - S.ulx[id]) / 2), halfY = (int)ceilf((float)(S.bly[id] - S.uly[id]) / 2);
+            const int mx = S.ulx[id] + halfX, my = S.uly[id] + halfY;
+            for (int q = 0; q < 4; ++q) {
+              const int cc = S.childcnt[id][q];
+              S.childid[id][q] = 0xFFFF;
+              if (cc == 0) continue;
+              if (r >= nfree0) { S.ctl[6] = 3; ++r; continue; }
+              const int ch = S.freelist[nfree0 - 1 - r];
+              S.ulx[ch] = (short)((q & 1) ? mx : S.ulx[id]); S.urx[ch] = (short)((q & 1) ? S.urx[id] : mx);
+              S.uly[ch] = (short)((q & 2) ? my : S.uly[id]); S.bly[ch] = (short)((q & 2) ? S.bly[id] : my);
+              S.cnt[ch] = cc; S.seq[ch] = seqc0 + r + 1; S.flags[ch] = (unsigned char)(1 | (cc == 1 ? 2 : 0));
+              S.childid[id][q] = (unsigned short)ch;
+              created[r] = ch;
+              if (cc > 1) S.vsize[vb++] = (unsigned short)ch;
+              ++r;
+            }
+          } else S.order2[base_kept + e[2]] = (unsigned short)id;
+        }
+        base_n += tot[0]; base_big += tot[1]; base_kept += tot[2];
+      }
+      __syncthreads();
+      const int ncreated = min(base_n, nfree0);
+      // new list = children in reverse creation order, then the untouched (noMore) nodes in their old order
+      for (int p = tid; p < ncreated; p += nthreads) S.order[p] = (unsigned short)created[ncreated - 1 - p];
+      for (int p = tid; p < base_kept; p += nthreads) S.order[ncreated + p] = S.order2[p];
+      __syncthreads();
+      if (tid == 0) {
+        const int live = ncreated + base_kept;
+        S.ctl[0] = nfree0 - ncreated; S.ctl[1] = seqc0 + ncreated; S.ctl[2] = live; S.ctl[5] = base_big;
+        if (live >= N || live == live0) S.ctl[3] = 1;
+        else if (live + base_big * 3 > N) S.ctl[4] = 1;
+      }
+    } else if (tid == 0) {   // fine mode (near the feature limit): sequential, the largest nodes first until the limit is reached
       int nfree = S.ctl[0], seqc = S.ctl[1], live = S.ctl[2];
       auto make_children = [&](int id, int* created, int& ncreated, int* nToExpand, int& nvs) {
         const int halfX = (int)ceilf((float)(S.urx[id] - S.ulx[id]) / 2), halfY = (int)ceilf((float)(S.bly[id] - S.uly[id]) / 2);
@@ -417,23 +497,7 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
       };
       int* created = reinterpret_cast<int*>(S.best);   // scratch (best[] is only used at the very end)
       int ncreated = 0, nvs = 0;
-      if (mode == 0) {
-        const int prevSize = live;
-        int nToExpand = 0, nkept = 0;
-        for (int i = 0; i < live; ++i) {
-          const int id = S.order[i];
-          if (S.flags[id] & 4) make_children(id, created, ncreated, &nToExpand, nvs);
-          else S.order2[nkept++] = (unsigned short)id;
-        }
-        // new list = children in reverse creation order, then the untouched (noMore) nodes in their old order
-        int p = 0;
-        for (int i = ncreated - 1; i >= 0; --i) S.order[p++] = (unsigned short)created[i];
-        for (int i = 0; i < nkept; ++i) S.order[p++] = S.order2[i];
-        live = p;
-        S.ctl[5] = nvs;
-        if (live >= N || live == prevSize) S.ctl[3] = 1;
-        else if (live + nToExpand * 3 > N) S.ctl[4] = 1;
-      } else {
+      {
         const int prevSize = live;
         const int nv = S.ctl[5];
         int processed_from = nv;   // vprev[processed_from .. nv) were divided
@@ -469,16 +533,23 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
       if ((fl & 4) && (mode == 0 || (fl & 8))) nof[kidx] = S.childid[nid][kqq[kidx]];
     })
     __syncthreads();
-    if (tid == 0) {
+    {   // recycle the divided parents: ordered compaction of their ids onto the free list (ascending id, like a serial walk)
       int nfree = S.ctl[0];
-      for (int i = 0; i < MAXID; ++i) {
+      __syncthreads();
+      for (int c0 = 0; c0 < MAXID; c0 += 256) {
+        const int i = c0 + tid;
         const int fl = S.flags[i];
-        if ((fl & 4) && (mode == 0 || (fl & 8))) { S.flags[i] = 0; S.freelist[nfree++] = (unsigned short)i; }
+        const bool fr = (fl & 4) && (mode == 0 || (fl & 8));
+        if (fr) S.flags[i] = 0;
         else if (fl & 4) S.flags[i] = (unsigned char)(fl & ~4);
+        int v[1] = {fr ? 1 : 0}, e[1], tot[1];
+        block_exscan<1>(v, e, tot, S.wsum);
+        if (fr) S.freelist[nfree + e[0]] = (unsigned short)i;
+        nfree += tot[0];
       }
-      S.ctl[0] = nfree;
+      if (tid == 0) S.ctl[0] = nfree;
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (S.ctl[6] && tid == 0) atomicExch(err, 3);
   // ---- best candidate per live node: max response, first in insertion order on ties ----
