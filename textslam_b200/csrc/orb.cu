@@ -328,10 +328,16 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
   uint32_t* out = sel + ((size_t)img * nlevels + level) * sel_cap;
   const int ncells = li.ncells;
   // candidate index = cell_off[cell] + slot  (vToDistributeKeys order)
-  if (tid == 0) {
-    int acc = 0;
-    for (int c = 0; c < ncells; ++c) { S.cell_off[c] = acc; acc += ccount[c]; }
-    S.cell_off[ncells] = acc;
+  {   // exclusive scan of the per-cell counts (block scan; a serial walk was ~300 dependent global loads on one thread)
+    int base = 0;
+    for (int c0 = 0; c0 < ncells; c0 += 256) {
+      const int c = c0 + tid;
+      int v[1] = {c < ncells ? ccount[c] : 0}, e[1], tot[1];
+      block_exscan<1>(v, e, tot, S.wsum);
+      if (c < ncells) S.cell_off[c] = base + e[0];
+      base += tot[0];
+    }
+    if (tid == 0) S.cell_off[ncells] = base;
   }
   __syncthreads();
   const int M = S.cell_off[ncells];
@@ -347,11 +353,10 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
       S.ulx[i] = (short)(int)(hX * (float)i); S.uly[i] = 0; S.urx[i] = (short)(int)(hX * (float)(i + 1)); S.bly[i] = (short)Hd;
       S.seq[i] = -i; S.flags[i] = 1;
     }
-    int nf = 0;
-    for (int i = MAXID - 1; i >= nIni; --i) S.freelist[nf++] = (unsigned short)i;   // pop from the end -> ids nIni, nIni+1, ...
-    S.ctl[0] = nf;      // free list size
-    S.ctl[1] = 0;       // creation counter
+    S.ctl[0] = MAXID - nIni;   // free list size
+    S.ctl[1] = 0;              // creation counter
   }
+  for (int k = tid; k < MAXID - nIni; k += nthreads) S.freelist[k] = (unsigned short)(MAXID - 1 - k);   // pop from the end -> ids nIni, nIni+1, ...
   __syncthreads();
 #define FOR_EACH_KP(...)                                                        \
   for (int c = warp; c < ncells; c += nwarps) {                                  \
