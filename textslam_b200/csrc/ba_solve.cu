@@ -803,12 +803,6 @@ struct TailArgs {
 };
 constexpr int H_SEQ = 63;                 // slot of the sequence number in tslam_ctx::h_scalars (64 doubles)
 
-__device__ __forceinline__ double strided_sum_256(const double* __restrict__ p, int n, int stride, int off, double* s) {
-  double a = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) a += p[(size_t)i * stride + off];
-  __syncthreads();   // s[] may still be read by the previous reduction
-  return block_sum_256(a, s);
-}
 __device__ __forceinline__ void publish_to_host(const double* sc, double* mx, int* fail, double* host, double seq) {
   // one thread, program order: 10 payload stores, system-scope fence, then the sequence number
   for (int k = 0; k < SC_N; ++k) host[k] = sc[k];

@@ -5,9 +5,9 @@
 // landmark blocks first and factoring the reduced camera matrix exactly is the same LM step
 // (SURVEY Appendix A.7).
 //
-// Layout: A is row-major with leading dimension ld = Tn*64 (Tn = ceil(n/64)); rows [0,n) hold the
-// lower triangle of S, rows [n, Tn*64) are identity padding, and one extra tile row starting at
-// Rb = Tn*64 carries b in its first row. Factoring [S; b^T] panel by panel turns that row into
+// Layout: A is row-major with leading dimension ld = Tn*64 (Tn = tiles of the tile-aligned camera layout, nd_layout.h); camera
+// slot s owns rows / columns doff[s] .. doff[s]+5 of the lower triangle of S, every other row is identity padding (unit diagonal
+// written by zero_tiles_kernel), and one extra tile row starting at Rb = Tn*64 carries b in its first row. Factoring [S; b^T] panel by panel turns that row into
 // y = L^-1 b for free (forward substitution rides along with the panel TRSM), so only the backward
 // solve L^T x = y remains.
 //
@@ -16,12 +16,12 @@
 // Tn x Tn tile pattern once per problem (analysis.cpp: chol_symbolic_host) and every panel step only touches the listed
 // non-zero tiles; a dense pattern degenerates to the classic right-looking blocked algorithm.
 //
-// Tile routines: fully unrolled, rows in registers (Crout). Measured alternatives (profiles/r1_notes.md): shared-memory
-// left-looking loops (2.1x slower), shared-memory right-looking rank-1 updates on 256 threads (1.6x slower); the
-// unrolled version is instruction-fetch bound (ncu: stall_no_instruction dominant, 70 % I-cache hit rate).
-// Per 64-wide panel j: potrf (one CTA, rows in registers, Crout) -> trsm (one CTA per non-zero tile
-// below) -> syrk/gemm trailing update with FP64 tensor-core MMA (mma.sync.m8n8k4.f64 — tcgen05 has
-// no FP64 kind; DMMA is the FP64 tensor path on sm_100a), one CTA per non-zero 64x64 lower tile pair.
+// Per 64-wide panel j of a wave: potrf_trsm_kernel (one CTA per non-zero tile below the diagonal + one for L_jj^-1; every CTA
+// re-factors the small diagonal tile, chol_tile.cuh: right-looking 32x32 factorisation inside one warp, rows in registers) ->
+// syrk_wave_kernel, the trailing update with FP64 tensor-core MMA (mma.sync.m8n8k4.f64 — tcgen05 has no FP64 kind; DMMA is
+// the FP64 tensor path on sm_100a), four CTAs per target tile. Waves come from the level schedule of the symbolic
+// factorisation on the tile-aligned camera layout (nd_layout.h). potrf2_trsm2_kernel is the two-tile-panel variant
+// (TSLAM_CHOL_PAIR=1). Measured alternatives and dead ends: profiles/r1_notes.md.
 #include <algorithm>
 #include "ctx.cuh"
 #include "solver.cuh"
