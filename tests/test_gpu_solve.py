@@ -148,3 +148,35 @@ def test_theta_covariance(ctx, oracle):
     assert ng == no == 0
     assert np.allclose(cg, co, rtol=1e-8, atol=1e-300)
     assert np.all(np.linalg.eigvalsh(cg) > 0)
+
+
+def test_optimizer_surface_wrappers(ctx, oracle):
+    """The remaining entry points of src/optimizer.h:57-70 on flattened problems: InitBA (two views, first one fixed at the identity),
+    OptimizeLandmarker (poses constant), ThetaOptimMultiFs (planes + covariance) — each against the oracle's solve of the same problem."""
+    import textslam_b200 as T
+    opt = T.Optimizer(ctx)
+    # InitBA: keyframe 0 = identity (fixed), keyframe 1 free, unweighted points, no loss
+    prob = synth.make_ba_problem(seed=71, n_kf=2, n_lm=400, obs_per_lm=1, band=2, fixed_cams=(0,), w_point=1.0, huber_point=0.0)
+    prob.cams[0] = [1, 0, 0, 0, 0, 0, 0]   # the initialiser's reference frame; keyframe 1 (free) absorbs the relative pose
+    a, b = prob.copy(), prob.copy()
+    sg, _, _ = opt.InitBA(a, 10)
+    so, _, _ = oracle.solve(b, 10)
+    assert sg["iterations"] == so["iterations"] and np.abs(a.cams - b.cams).max() <= 1e-5 * np.abs(b.cams).max()
+    assert np.abs(a.rho - b.rho).max() <= 1e-5 * np.abs(b.rho).max()
+    with pytest.raises(AssertionError):
+        opt.InitBA(synth.c4_local_ba(seed=1), 1)           # keyframe 0 is not the identity frame there
+    # OptimizeLandmarker: all poses constant
+    prob = synth.make_ba_problem(seed=72, n_kf=6, n_lm=300, obs_per_lm=3, band=6, fixed_cams=(0, 1, 2, 3, 4, 5), n_planes=4, w_point=1.0, w_text=1.0, huber_text=2.0)
+    a, b = prob.copy(), prob.copy()
+    sg, _, _ = opt.OptimizeLandmarker(a, 50)
+    so, _, _ = oracle.solve(b, 50)
+    assert sg["iterations"] == so["iterations"] and sg["n_free_cams"] == 0
+    assert np.abs(a.rho - b.rho).max() <= 1e-5 * np.abs(b.rho).max() and np.abs(a.theta - b.theta).max() <= 1e-5 * np.abs(b.theta).max()
+    # ThetaOptimMultiFs: planes only, covariance of every plane
+    prob = synth.make_ba_problem(seed=73, n_kf=5, n_lm=10, obs_per_lm=2, band=5, fixed_cams=(0, 1, 2, 3, 4), n_planes=8, w_text=1.0, huber_text=0.0)
+    prob.rho_fixed[:] = 1
+    a, b = prob.copy(), prob.copy()
+    sg, _, _, cov, ok = opt.ThetaOptimMultiFs(a, 10)
+    so, _, _ = oracle.solve(b, 10)
+    co, _ = oracle.theta_covariance(b)
+    assert ok and sg["iterations"] == so["iterations"] and np.allclose(cov, co, rtol=1e-6, atol=1e-300)

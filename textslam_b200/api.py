@@ -262,6 +262,30 @@ class Optimizer:
     def GlobalBA(self, prob, its=20):
         return self.ctx.solve(prob, its, self.text_jac_mode)
 
+    def InitBA(self, prob, its=10):
+        """optimizer::InitBA (src/optimizer.cc:56-133): the two-view problem of the initialiser. The auto_IniBAScene / nume_IniBAText
+        functors are the BA functors with the first keyframe held at the identity pose, so the flattened problem must carry that
+        keyframe as a constant camera (checked here) and unit point weights."""
+        assert prob.cam_fixed[0] == 1 and np.allclose(prob.cams[0], [1, 0, 0, 0, 0, 0, 0]), "InitBA: keyframe 0 is the fixed identity frame"
+        assert prob.w_point == (1.0, 1.0), "auto_IniBAScene is unweighted (ScaleScene = 1)"
+        return self.ctx.solve(prob, its, self.text_jac_mode)
+
+    def OptimizeLandmarker(self, prob, its=50):
+        """optimizer::OptimizeLandmarker / PyrLandmarkers (src/optimizer.cc:456-562, 1853-2168): every pose constant, inverse
+        depths (auto_RhoScene) and planes (nume_thetaText) free, 50 iterations per level."""
+        assert prob.cam_fixed.all(), "OptimizeLandmarker keeps every keyframe pose constant"
+        return self.ctx.solve(prob, its, self.text_jac_mode)
+
+    def ThetaOptimMultiFs(self, prob, its=10):
+        """optimizer::ThetaOptimMultiFs / PyrThetaOptim (src/optimizer.cc:2170-2242): plane parameters of text objects from several
+        frames with constant poses, followed by the 3x3 covariance of every plane (ceres::Covariance). Returns
+        (summary, final_residuals, trace, covariances (n_planes, 3, 3), flag) with flag = False when a covariance is singular —
+        the reference then reports failure for the object."""
+        assert prob.cam_fixed.all(), "ThetaOptimMultiFs keeps every pose constant"
+        summ, fr, tr = self.ctx.solve(prob, its, self.text_jac_mode)
+        cov, n_singular = self.ctx.theta_covariance(prob, self.text_jac_mode)
+        return summ, fr, tr, cov, n_singular == 0
+
 
 class ORBextractor:
     """Mirror of TextSLAM::ORBextractor (src/ORBextractor.h:45-114): ctor args and operator()."""
