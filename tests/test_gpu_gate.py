@@ -86,3 +86,30 @@ def test_pose_pyramid_matches_oracle(ctx, oracle):
     for x, y in zip(fg, fo):
         assert np.array_equal(x, y)
     assert np.abs(lg[0].prob.cams - lo[0].prob.cams).max() <= 1e-5 * np.abs(lo[0].prob.cams).max()
+
+
+def test_local_ba_pyramid_matches_oracle(ctx, oracle):
+    """optimizer::LocalBundleAdjustment's three PyrBA levels (src/optimizer.cc:282-289) through the Optimizer mirror vs the oracle:
+    same blocks assembled per level, same flags cleared, poses / inverse depths within the north-star tolerance."""
+    from textslam_b200.api import PyramidLevel
+    n_obj = 6
+
+    def levels():
+        out = []
+        for lv in (2, 1, 0):
+            p = synth.c4_local_ba(seed=33, level=lv, n_lm=300, n_planes=n_obj)
+            out.append(PyramidLevel(p, t_obj=p.t_plane.copy(), t_feat=np.tile(np.arange(25), n_obj)))
+        return out
+
+    lg, lo = levels(), levels()
+    flags = lambda n: (np.ones(n, bool), np.ones(n_obj, bool), np.ones((n_obj, 25), bool))
+    fg, fo = flags(lg[0].prob.n_pobs), flags(lo[0].prob.n_pobs)
+    rg = T.Optimizer(ctx).LocalBundleAdjustment(lg, 10, *fg)
+    ro = run_pyramid(oracle_solve_gated(oracle), lo, (12.25,) * 3, (0.5, 0.5, 0.95), (10,) * 3, *fo)
+    for a, b in zip(rg, ro):
+        assert a["summary"]["iterations"] == b["summary"]["iterations"] and a["bad"] == b["bad"]
+        assert a["n_point_blocks"] == b["n_point_blocks"] and a["n_text_blocks"] == b["n_text_blocks"]
+    for x, y in zip(fg, fo):
+        assert np.array_equal(x, y)
+    assert np.abs(lg[0].prob.cams - lo[0].prob.cams).max() <= 1e-5 * np.abs(lo[0].prob.cams).max()
+    assert np.abs(lg[0].prob.rho - lo[0].prob.rho).max() <= 1e-5 * np.abs(lo[0].prob.rho).max()
