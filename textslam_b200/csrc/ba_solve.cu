@@ -1402,7 +1402,7 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
   TSL_CUDA(cudaSetDevice(ctx->device));
   AllocStreamScope alloc_scope(ctx->stream);   // declared before every device buffer of this call: released after them, on the same stream
   tslam_dev_problem d;
-  int rc = upload_problem(ctx, p, &d, /*shard=*/true, /*need_host_index=*/false);
+  int rc = upload_problem(ctx, p, &d, /*shard=*/true, /*persistent=*/false);
   if (rc) return rc;
   auto Tu = std::chrono::steady_clock::now();
   struct Guard { tslam_dev_problem* d; ~Guard() { free_solver(d); } } guard{&d};

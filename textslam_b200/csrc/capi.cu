@@ -63,7 +63,7 @@ static int upload_selected(DevBuf<T>& dst, DevBuf<T>& scratch, const T* src, siz
   return TSLAM_OK;
 }
 
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool need_host_index) {
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool persistent) {
   if (!p) return set_error(TSLAM_ERR_ARG, "null problem");
   if (p->n_cams <= 0 || !p->cams) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
   for (int i = 0; i < p->n_pobs; ++i) {
@@ -87,7 +87,7 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
   d->h_rho_fixed.assign(p->rho_fixed ? p->rho_fixed : zr.data(), (p->rho_fixed ? p->rho_fixed : zr.data()) + p->n_points);
   d->h_theta_fixed.assign(p->theta_fixed ? p->theta_fixed : zt.data(), (p->theta_fixed ? p->theta_fixed : zt.data()) + p->n_planes);
   d->n_pobs = p->n_pobs; d->n_tobs = p->n_tobs;   // (local counts are set below for a sharded upload)
-  if (need_host_index || !device_analysis_supported(ctx, d)) {   // index copies for the host-side structure analysis
+  if (persistent || !device_analysis_supported(ctx, d)) {   // index copies for the host-side structure analysis
     d->h_p_cam.assign(p->p_cam, p->p_cam + p->n_pobs); d->h_p_host.assign(p->p_host, p->p_host + p->n_pobs);
     d->h_p_lm.assign(p->p_lm, p->p_lm + p->n_pobs);
     d->h_t_cam.assign(p->t_cam, p->t_cam + p->n_tobs); d->h_t_host.assign(p->t_host, p->t_host + p->n_tobs);
@@ -97,11 +97,11 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
     d->have_host_index = false;
   }
   TSL_CUDA(d->cams.upload(p->cams, 7 * (size_t)p->n_cams, s));
-  TSL_CUDA(d->cams0.upload(p->cams, 7 * (size_t)p->n_cams, s));
+  if (persistent) TSL_CUDA(d->cams0.upload(p->cams, 7 * (size_t)p->n_cams, s));   // reset copies: device-resident handles only
   TSL_CUDA(d->rho.upload(p->rho, p->n_points, s));
-  TSL_CUDA(d->rho0.upload(p->rho, p->n_points, s));
+  if (persistent) TSL_CUDA(d->rho0.upload(p->rho, p->n_points, s));
   TSL_CUDA(d->theta.upload(p->theta, 3 * (size_t)p->n_planes, s));
-  TSL_CUDA(d->theta0.upload(p->theta, 3 * (size_t)p->n_planes, s));
+  if (persistent) TSL_CUDA(d->theta0.upload(p->theta, 3 * (size_t)p->n_planes, s));
   TSL_CUDA(d->cam_fixed.upload(d->h_cam_fixed.data(), p->n_cams, s));
   TSL_CUDA(d->rho_fixed.upload(d->h_rho_fixed.data(), p->n_points, s));
   TSL_CUDA(d->theta_fixed.upload(d->h_theta_fixed.data(), p->n_planes, s));
@@ -122,7 +122,9 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
     TSL_CUDA(d->t_host.upload(p->t_host, p->n_tobs, s));
     TSL_CUDA(d->t_plane.upload(p->t_plane, p->n_tobs, s));
     TSL_CUDA(d->t_img.upload(p->t_img, p->n_tobs, s));
-    TSL_CUDA(cudaStreamSynchronize(s));  // host arrays are caller-owned and may change after return
+    // host arrays are caller-owned and may change after return; inside a one-shot tslam_solve the caller is blocked until the
+    // call ends, so the copies may still be in flight while the structure analysis is being enqueued behind them
+    if (persistent) TSL_CUDA(cudaStreamSynchronize(s));
     return TSLAM_OK;
   }
   // landmark-sharded upload: an observation lives with its landmark

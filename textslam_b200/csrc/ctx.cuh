@@ -145,9 +145,10 @@ struct tslam_dev_problem {
 
 namespace tsl {
 // shard = true: keep only the observations this rank owns (multi-GPU global BA, ctx->world > 1)
-// need_host_index = false (one-shot tslam_solve): the host copies of the observation index arrays are only made when the
-// structure analysis will run on the host
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false, bool need_host_index = true);
+// persistent = false (one-shot tslam_solve, the caller is blocked until the call ends): no reset copies of the parameters, host
+// copies of the observation index arrays only when the structure analysis will run on the host, and the uploads may still be in
+// flight on return (everything that follows is ordered behind them on the context stream)
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false, bool persistent = true);
 bool device_analysis_supported(const tslam_ctx* ctx, const tslam_dev_problem* d);
 // observation ownership rule shared by upload and the solver's structure analysis
 inline int obs_owner(bool lm_free, int lm_index, int obs_index, int world) { return (lm_free ? lm_index : obs_index) % world; }
