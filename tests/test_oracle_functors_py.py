@@ -10,7 +10,7 @@ from textslam_b200._abi import PT_BA, PT_BA_NW, PT_POSE, PT_RHO, TX_BA, JAC_ANAL
 
 
 def quat_to_R(q):
-    w, x, y, z = q / np.linalg.norm(q)     # QuaternionRotatePoint / Eigen::Quaterniond::normalized
+    w, x, y, z = q / np.sqrt((q * q).sum())     # QuaternionRotatePoint / Eigen::Quaterniond::normalized (no conjugate: complex-step safe)
     return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
@@ -60,8 +60,8 @@ def text_residual(cam, host, theta, rays, iref, mu, sigma, img, K, wT):
 
 def plus(cam, d):
     """ceres::QuaternionParameterization::Plus on the quaternion (delta on the LEFT: q' = exp(d) (x) q), identity on the translation."""
-    n = np.linalg.norm(d[:3])
-    if n > 0:
+    n = np.sqrt((d[:3] * d[:3]).sum())      # complex-step safe (analytic continuation, no conjugate)
+    if n != 0:
         s = np.sin(n) / n
         e = np.array([np.cos(n), s * d[0], s * d[1], s * d[2]])
     else:
