@@ -89,3 +89,81 @@ def test_pose_only_trace_matches_second_reading(oracle, seed, rot_noise):
     if rot_noise >= 0.5:   # the hard start ends with three rejected steps in a row: radius / 2, / 4, / 8 (decrease_factor doubling)
         assert tr[-3:, 3].tolist() == [0, 0, 0] and len(tr) == 11
         assert np.allclose(tr[-3:, 1] / tr[-4:-1, 1], [0.5, 0.25, 0.125], rtol=1e-12)
+
+
+def dense_ceres_lm_ba(prob, max_iters):
+    """The same loop for a small bundle adjustment: free cameras (6 tangent columns each, applied through Plus) and free inverse depths
+    (plain additive), one dense Jacobian, no Schur complement. The C++ oracle eliminates the landmarks first (an exact
+    reformulation, Appendix A.7), so its trace must still agree."""
+    K, w, delta = prob.K_point, prob.w_point, prob.huber_point
+    cams, rho = prob.cams.copy(), prob.rho.copy()
+    fc = [int(c) for c in np.nonzero(prob.cam_fixed == 0)[0]]
+    fl = [int(l) for l in np.nonzero(prob.rho_fixed == 0)[0]]
+    n = 6 * len(fc) + len(fl)
+
+    def residuals(cams_, rho_):
+        return np.array([point_residual(cams_[prob.p_cam[i]], cams_[prob.p_host[i]], rho_[prob.p_lm[i]], prob.p_ray[i], prob.p_uv[i], K, w) for i in range(prob.n_pobs)])
+
+    def apply(cams_, rho_, step):
+        c2, r2 = cams_.astype(step.dtype if np.iscomplexobj(step) else float), rho_.astype(step.dtype if np.iscomplexobj(step) else float)
+        for k, c in enumerate(fc):
+            c2[c] = plus(c2[c], step[6 * k:6 * k + 6])
+        for k, l in enumerate(fl):
+            r2[l] = r2[l] + step[6 * len(fc) + k]
+        return c2, r2
+
+    def jacobian(cams_, rho_, h=1e-30):
+        J = np.zeros((prob.n_pobs, 2, n))
+        for k in range(n):
+            d = np.zeros(n, dtype=complex); d[k] = 1j * h
+            J[:, :, k] = residuals(*apply(cams_, rho_, d)).imag / h
+        return J
+
+    def robustify(r):
+        s = (r ** 2).sum(1)
+        out = s > delta * delta
+        rho_l = np.where(out, 2 * delta * np.sqrt(np.maximum(s, 1e-300)) - delta * delta, s)
+        return 0.5 * rho_l.sum(), np.where(out, np.sqrt(delta / np.sqrt(np.maximum(s, 1e-300))), 1.0)
+
+    def xnorm(cams_, rho_):
+        return np.sqrt(sum((cams_[c] ** 2).sum() for c in fc) + sum(rho_[l] ** 2 for l in fl))
+
+    r = residuals(cams, rho); cost, sq = robustify(r)
+    Jm = (jacobian(cams, rho) * sq[:, None, None]).reshape(-1, n); rc = (r * sq[:, None]).reshape(-1)
+    scale = 1.0 / (1.0 + np.sqrt((Jm ** 2).sum(0)))
+    radius, decrease_factor = 1e4, 2.0
+    trace = [(cost, radius, 0.0, 1)]
+    for _ in range(max_iters):
+        Js = Jm * scale
+        H, g = Js.T @ Js, Js.T @ rc
+        step = np.linalg.solve(H + np.diag(np.clip(np.diag(H), 1e-6, 1e32) / radius), -g) * scale
+        Jd = Jm @ step
+        model_change = -(Jd @ (rc + 0.5 * Jd))
+        c_new, r_new_p = apply(cams, rho, step)
+        res_new = residuals(c_new, r_new_p); cost_new, sq_new = robustify(res_new)
+        if not model_change > 0:
+            radius /= decrease_factor; decrease_factor *= 2; trace.append((cost, radius, 0.0, -1)); continue
+        step_norm = np.sqrt(sum(((c_new[c] - cams[c]) ** 2).sum() for c in fc) + sum((r_new_p[l] - rho[l]) ** 2 for l in fl))
+        if step_norm <= 1e-8 * (xnorm(cams, rho) + 1e-8) or abs(cost - cost_new) <= 1e-6 * cost:
+            trace.append((cost, radius, 0.0, 0)); break
+        rel = (cost - cost_new) / model_change
+        if rel > 1e-3:
+            cams, rho, r, cost, sq = c_new, r_new_p, res_new, cost_new, sq_new
+            Jm = (jacobian(cams, rho) * sq[:, None, None]).reshape(-1, n); rc = (r * sq[:, None]).reshape(-1)
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rel - 1.0) ** 3)); decrease_factor = 2.0
+            trace.append((cost, radius, rel, 1))
+        else:
+            radius /= decrease_factor; decrease_factor *= 2; trace.append((cost_new, radius, rel, 0))
+    return np.array(trace), cams, rho
+
+
+@pytest.mark.parametrize("seed", [12, 13])
+def test_small_ba_trace_matches_second_reading(oracle, seed):
+    prob = synth.make_ba_problem(seed=seed, n_kf=4, n_lm=24, obs_per_lm=3, band=4, fixed_cams=(0, 1), rot_noise=3e-2, trans_noise=3e-2, rho_noise=0.1)
+    tr_py, cams_py, rho_py = dense_ceres_lm_ba(prob, 10)
+    a = prob.copy()
+    _, _, tr = oracle.solve(a, 10)
+    tr = tr[~np.isnan(tr[:, 0])]
+    assert len(tr) == len(tr_py) and np.array_equal(tr[:, 3], tr_py[:, 3])
+    assert np.allclose(tr[:, 0], tr_py[:, 0], rtol=1e-7) and np.allclose(tr[:, 1], tr_py[:, 1], rtol=1e-4)
+    assert np.abs(a.cams - cams_py).max() < 1e-7 and np.abs(a.rho - rho_py).max() < 1e-7
