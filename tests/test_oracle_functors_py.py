@@ -130,3 +130,36 @@ def test_text_functor_matches_numpy_restatement(oracle, level):
         ok = np.abs(J - Ja[j]) <= 5e-4 * scale
         assert ok.mean() >= 0.95, (j, np.abs(J - Ja[j]).max() / scale)     # rows whose sample sits on a pixel boundary may differ
         assert np.abs(Jc[j] - Ja[j]).max() <= 0.2 * scale                  # Ceres' step (1e-6 relative) straddles cell borders more often
+
+
+def ceres_central_numeric_jacobian(fun, x):
+    """ceres::NumericDiffCostFunction<CENTRAL> with default options (SURVEY Appendix A.3): h_j = max(|x_j| 1e-6, sqrt(DBL_EPSILON))."""
+    J = np.zeros((8, len(x)))
+    for j in range(len(x)):
+        h = max(abs(x[j]) * 1e-6, np.sqrt(np.finfo(float).eps))
+        xp, xm = x.copy(), x.copy()
+        xp[j] += h; xm[j] -= h
+        J[:, j] = (fun(xp) - fun(xm)) / (2 * h)
+    return J
+
+
+def quaternion_plus_jacobian(q):
+    """d Plus(q, delta) / d delta at delta = 0 for ceres::QuaternionParameterization (4 x 3, Appendix A.1)."""
+    x0, x1, x2, x3 = q
+    return np.array([[-x1, -x2, -x3], [x0, x3, -x2], [-x3, x0, x1], [x2, -x1, x0]])
+
+
+def test_numeric_diff_mode_is_ceres_step_rule_plus_local_parameterization(oracle):
+    """The oracle's TSLAM_JAC_CENTRAL_DIFF Jacobian = Ceres' central differences on the 17 AMBIENT parameters of nume_BAText (4+3+4+3+3),
+    quaternion blocks then multiplied by the 4x3 Plus Jacobian: identical arithmetic, so agreement is at rounding level."""
+    prob = synth.c4_local_ba(seed=23, n_lm=30, n_planes=5)
+    _, Jc = oracle.eval_text(prob, TX_BA, JAC_CENTRAL_DIFF)
+    for j in range(0, prob.n_tobs, 9):
+        cam, host, th = prob.cams[prob.t_cam[j]].copy(), prob.cams[prob.t_host[j]].copy(), prob.theta[prob.t_plane[j]].copy()
+        args = (prob.t_rays[j], prob.t_iref[j], prob.t_musigma[j, 0], prob.t_musigma[j, 1], prob.imgs[prob.t_img[j]], prob.K_text, prob.w_text)
+        x = np.concatenate([cam, host, th])
+        fun = lambda v: text_residual(v[:7], v[7:14], v[14:], *args)
+        Ja = ceres_central_numeric_jacobian(fun, x)                       # 8 x 17 ambient
+        J = np.concatenate([Ja[:, 0:4] @ quaternion_plus_jacobian(cam[:4]), Ja[:, 4:7],
+                            Ja[:, 7:11] @ quaternion_plus_jacobian(host[:4]), Ja[:, 11:14], Ja[:, 14:17]], axis=1)
+        assert np.allclose(J, Jc[j], rtol=1e-6, atol=1e-6 * (np.abs(Jc[j]).max() + 1e-12)), j
