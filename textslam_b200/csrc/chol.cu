@@ -36,6 +36,7 @@ namespace tsl {
 // the (tiny) diagonal tile redundantly into shared memory straight from A (nobody writes A_jj in
 // this launch), CTA 0 stores the factor to Ldiag[j] (read by the backward solve), CTA 1+m solves the
 // m-th non-zero row tile. Saves one launch + one grid-wide dependency per panel.
+template <bool MMA_UPDATE>
 __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restrict__ A, int ld, const int2* __restrict__ items,
                                                                 int* __restrict__ fail, double* __restrict__ Linv) {
   PDL_TRIGGER();
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(PT_THREADS) potrf_trsm_kernel(double* __restri
     }
   }
   __syncthreads();
-  factor_solve_tile<false>(sT, sX, sLt, sinv, fail, nullptr);   // row tile: X = A_ij L^-T ;  identity: X = L^-T
+  factor_solve_tile<false, MMA_UPDATE>(sT, sX, sLt, sinv, fail, nullptr);   // row tile: X = A_ij L^-T ;  identity: X = L^-T
   if (!Aij) {                          // off the critical path: store L_jj^-1 = X^T (row-major) for the backward solve
     double* dst = Linv + (size_t)j * NB * NB;
     for (int e = threadIdx.x; e < NB * NB; e += PT_THREADS) { const int r = e >> 6, c = e & 63; dst[e] = sX[c * LD2 + r]; }
@@ -409,19 +410,25 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
   if (!attr_set) {
     TSL_CUDA(cudaFuncSetAttribute(potrf2_trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p2));
     TSL_CUDA(cudaFuncSetAttribute(syrk_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
+    TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
+    TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
     attr_set = true;
   }
   cudaStream_t s = ctx->stream;
   // TSLAM_CHOL_TRACE=1: per-kernel-class device time of this call (CUDA events between launches; debugging aid only)
   static const bool trace = getenv("TSLAM_CHOL_TRACE") != nullptr;
+  // in-tile rank-32 updates of the panel kernel on the FP64 tensor pipe (TSLAM_POTRF_FMA=1: the register-tiled FMA version)
+  static const bool mma_update = getenv("TSLAM_POTRF_FMA") == nullptr;
   std::vector<cudaEvent_t> ev; std::vector<int> cls;
   auto mark = [&](int c) { if (!trace) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); cls.push_back(c); };
   mark(-1);
   for (int w = 0; w < sym.nwaves; ++w) {
     const int ni = sym.item_ptr[w + 1] - sym.item_ptr[w], ni2 = sym.item2_ptr[w + 1] - sym.item2_ptr[w], nt = sym.target_ptr[w + 1] - sym.target_ptr[w];
     if (ni2 > 0) LAUNCH(launch_k(potrf2_trsm2_kernel, ni2, P2_THREADS, smem_p2, s, A, ld, sym.items2.p + sym.item2_ptr[w], d_fail, sym.Ldiag.p, sym.Lpair.p));
-    if (ni > 0) LAUNCH(launch_k(potrf_trsm_kernel, ni, PT_THREADS, smem_pt, s, A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+    if (ni > 0) {
+      if (mma_update) LAUNCH(launch_k(potrf_trsm_kernel<true>, ni, PT_THREADS, smem_pt, s, A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+      else LAUNCH(launch_k(potrf_trsm_kernel<false>, ni, PT_THREADS, smem_pt, s, A, ld, sym.items.p + sym.item_ptr[w], d_fail, sym.Ldiag.p));
+    }
     mark(0);
     if (nt > 0) LAUNCH(launch_k(syrk_wave_kernel, 4 * nt, 128, smem, s, A, ld, sym.targets.p + sym.target_ptr[w], sym.src_ptr.p + sym.target_ptr[w], sym.src.p));
     mark(1);

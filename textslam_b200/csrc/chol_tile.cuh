@@ -300,6 +300,36 @@ __device__ __noinline__ void gemm_nt32_il(double* C, const double* A, const doub
     for (int j = 0; j < 4; ++j) C[(rg + nrg * i) * LD2 + cg + 8 * j] -= acc[i][j];
 }
 
+// Phase 3 of factor_solve_tile on the FP64 tensor pipe: A22 (32 x 32) -= L21 L21^T and X2 (64 x 32) -= X1 L21^T as twelve
+// 8-row strips (4 of A22, 8 of X2), three per warp; each strip is 4 column tiles x 8 k-steps of mma.m8n8k4 (fragment layout
+// as in gemm_tile_nt). The register-tiled FMA version (gemm_nt32_il) spent 4.1k cycles here, bound by shared-memory bandwidth
+// (one 128-bit load per 4 FMAs); the MMA fragments need one 64-bit load per 64 FMAs.
+__device__ __forceinline__ void update_phase_dmma(double* sT, double* sX, int tid) {
+  const int w = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const double* B = sT + HB * LD2;                       // L21: rows 32..63, columns 0..31
+#pragma unroll 1
+  for (int t = w; t < 12; t += 4) {
+    const double* A = t < 4 ? sT + (HB + 8 * t) * LD2 : sX + 8 * (t - 4) * LD2;   // strip of L21 / of X1 (columns 0..31)
+    double* C = (t < 4 ? sT + (HB + 8 * t) * LD2 : sX + 8 * (t - 4) * LD2) + HB; // same rows, columns 32..63
+    double acc[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c][0] = acc[c][1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < HB; k0 += 4) {
+      const double fa = A[g * LD2 + k0 + tg];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dmma_m8n8k4(acc[c][0], acc[c][1], fa, B[(8 * c + g) * LD2 + k0 + tg]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double2* p = reinterpret_cast<double2*>(C + g * LD2 + 8 * c + 2 * tg);
+      double2 v = *p;
+      v.x -= acc[c][0]; v.y -= acc[c][1];
+      *p = v;
+    }
+  }
+}
+
 // Factor the 64x64 diagonal tile in sT (lower, LD2) and solve X L^T = B for the 64 rows of sX (128-thread CTA):
 //   phase 1  warp 0: L11 = chol(A11)
 //   phase 2  warp 0: L21 = A21 L11^-T            | warps 2,3: X1 = B1 L11^-T        (same code on both sides)
@@ -310,7 +340,7 @@ __device__ __noinline__ void gemm_nt32_il(double* C, const double* A, const doub
 // on warps 2,3 WHILE warp 0 factors A22 is 3x slower than doing them one after the other (30.2k vs 7.2k + 2.5k cycles):
 // two different unrolled instruction streams on one SM evict each other from the instruction cache, so phases only
 // ever overlap identical code. STAMPS: optional clock64() trace for the micro-benchmark.
-template <bool STAMPS>
+template <bool STAMPS, bool MMA_UPDATE = false>
 __device__ __forceinline__ void factor_solve_tile(double* sT, double* sX, double* sLt, double* sinv, int* fail, long long* stamps) {
   const int tid = threadIdx.x, warp = tid >> 5;
 #define TSL_STAMP(k) do { if (STAMPS && tid == 0) stamps[k] = clock64(); } while (0)
@@ -321,8 +351,11 @@ __device__ __forceinline__ void factor_solve_tile(double* sT, double* sX, double
   else if (warp >= 2) trsm32_row(sX + (tid - 64) * LD2, sLt, sinv);
   __syncthreads();
   TSL_STAMP(3);
-  gemm_nt32_il<2>(sT + HB * LD2 + HB, sT + HB * LD2, sT + HB * LD2, HB, tid);
-  gemm_nt32_il<4>(sX + HB, sX, sT + HB * LD2, NB, tid);
+  if (MMA_UPDATE) update_phase_dmma(sT, sX, tid);
+  else {
+    gemm_nt32_il<2>(sT + HB * LD2 + HB, sT + HB * LD2, sT + HB * LD2, HB, tid);
+    gemm_nt32_il<4>(sX + HB, sX, sT + HB * LD2, NB, tid);
+  }
   __syncthreads();
   TSL_STAMP(4);
   if (warp == 0) potrf32_rl(sT + HB * LD2 + HB, sLt + HB * LD2 + HB, sinv + HB, fail);
