@@ -1,4 +1,7 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see ba_math.hpp header). PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ba_math.hpp header). PARITY UNPINNED against a real Ceres build; cross-checked
+// instead against two independent re-implementations: a dense numpy reading of the same loop whose trace (accept / reject
+// sequence, cost and radius of every iteration) it reproduces (tests/test_oracle_lm_py.py), and scipy.optimize.least_squares
+// on the same robustified objective, which reaches the same optimum (tests/test_oracle_scipy.py).
 //
 // CPU restatement of what `ceres::Solve` does for the problems TextSLAM builds
 // (/root/reference/src/optimizer.cc:1037-1044,1215-1222,1595-1602,1833-1840: TRUST_REGION +

@@ -7,7 +7,9 @@
 // Eigen and OpenCV, none of which are present in this image. This file restates
 // the reference functors operation-for-operation in plain C++17 (double), with a forward-mode
 // dual-number type standing in for ceres::Jet and a central-difference evaluator following
-// Ceres' published NumericDiff step rule.
+// Ceres' published NumericDiff step rule. A second restatement written from the same headers in plain numpy
+// (tests/test_oracle_functors_py.py) agrees with it: residuals to 1e-11, Jacobians with central / complex-step derivatives
+// through the quaternion Plus, the NumericDiff mode with Ceres' step rule applied to the ambient parameters.
 //
 // Reference anchors (all under /root/reference):
 //   include/rotation.h:524-573         UnitQuaternionRotatePoint / QuaternionRotatePoint / QuaternionProduct

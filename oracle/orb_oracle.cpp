@@ -5,8 +5,9 @@
 // with non-max suppression, INTER_LINEAR u8 resize, 7x7 sigma=2 GaussianBlur, fastAtan2, cvRound) are
 // checked bit-for-bit against Python cv2 4.13 in tests/test_oracle_orb.py and against committed golden
 // vectors produced by cv2 (tests/golden/, script tests/golden/make_orb_golden.py); the orchestration
-// above them (cells, quad-tree, orientation, steered BRIEF) has nothing to be pinned against but the
-// reference text, cited per function below.
+// above them (cells, quad-tree, orientation, steered BRIEF) is pinned against a second, independent
+// restatement in plain Python on the real cv2 primitives (tests/test_oracle_orb_py.py): candidates,
+// quad-tree winners, output order, angles and every descriptor byte agree exactly.
 //
 // Deliberate, documented deviations (SURVEY §7 hard part 2, Appendix C):
 //  * DistributeOctTree sorts (size, node*) pairs (ORBextractor.cc:685): ties depend on heap addresses.
