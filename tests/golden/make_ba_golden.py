@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 from textslam_b200 import synth                                                   # noqa: E402
-from test_oracle_functors_py import point_residual, plus                          # noqa: E402
+from test_oracle_functors_py import point_residual, text_residual, plus           # noqa: E402
 from test_oracle_lm_py import dense_ceres_lm, dense_ceres_lm_ba                   # noqa: E402
 
 FIELDS = ("cams", "cam_fixed", "rho", "rho_fixed", "p_uv", "p_ray", "p_cam", "p_host", "p_lm")
@@ -49,6 +49,15 @@ def main():
     pack("b_", prob, out)
     tr, cams, rho = dense_ceres_lm_ba(prob, 10)
     out["b_trace"], out["b_out_cams"], out["b_out_rho"] = tr, cams, rho
+    # (4) nume_BAText residuals on quarter-resolution images (level 2: 160 x 120), four planes
+    prob = synth.make_ba_problem(seed=55, n_kf=4, n_lm=8, obs_per_lm=2, band=4, fixed_cams=(0,), n_planes=4, feats_per_plane=9, level=2)
+    pack("t_", prob, out)
+    for f in ("theta", "theta_fixed", "t_rays", "t_iref", "t_musigma", "t_cam", "t_host", "t_plane", "t_img", "imgs"):
+        out["t_" + f] = getattr(prob, f)
+    out["t_Kt"], out["t_wt"] = np.array(prob.K_text), np.array(prob.w_text)
+    out["t_r"] = np.array([text_residual(prob.cams[prob.t_cam[j]], prob.cams[prob.t_host[j]], prob.theta[prob.t_plane[j]], prob.t_rays[j], prob.t_iref[j],
+                                         prob.t_musigma[j, 0], prob.t_musigma[j, 1], prob.imgs[prob.t_img[j]], prob.K_text, prob.w_text)
+                           for j in range(prob.n_tobs)])
     np.savez_compressed(os.path.join(HERE, "ba_numpy_golden.npz"), **out)
     print("written", {k: v.shape for k, v in out.items() if k.endswith(("trace", "_r", "_J"))})
 
