@@ -127,3 +127,30 @@ def test_pyramid_loop_bookkeeping(oracle):
     pg = np.ones(n_p, bool); tg = np.ones(n_obj, bool); fg = np.ones((n_obj, 25), bool)
     res = run_pyramid(oracle_solve_gated(oracle), levels, (12.25,) * 3, (0.5, 0.5, 0.95), (10,) * 3, pg, tg, fg, rapid=True)
     assert pg.all() and tg.all() and fg.all() and all(r["bad"] == (0, 0, 0) for r in res)
+
+
+def test_pyramid_loop_edge_cases(oracle):
+    """Host logic of the level loop: objects that are already bad contribute no blocks (vSizeEachObj = 0 and they are never re-flagged),
+    a level without any text still gates the points with the relaxed threshold, and an empty level list is a no-op."""
+    levels = pose_levels(seed=12, n_pobs=120, n_planes=3)
+    n_p = levels[0].prob.n_pobs
+    pts_good = np.ones(n_p, bool); texts_good = np.array([True, False, True]); feats_good = np.ones((3, 25), bool)
+    feats_good[2, :20] = False                                   # object 2 keeps 5 features
+    seen = []
+
+    def spy(prob, gate, t_obj, obj_size, max_iters):
+        seen.append((prob.n_pobs, prob.n_tobs, obj_size.tolist(), gate.gate_points, gate.gate_text))
+        return oracle_solve_gated(oracle)(prob, gate, t_obj, obj_size, max_iters)
+
+    res = run_pyramid(spy, levels, (12.25,) * 3, (0.5, 0.5, 0.95), (10,) * 3, pts_good, texts_good, feats_good)
+    assert seen[0][1] == 30 and seen[0][2] == [25, 0, 5]         # 25 + 5 blocks at the first level, none from the bad object
+    assert not texts_good[1] and res[0]["n_text_blocks"] == 30
+    for (_, n_t, sizes, gp, gt), r in zip(seen, res):
+        assert sum(sizes) == n_t == r["n_text_blocks"] and sizes[1] == 0 and gp and gt
+    # points only: the text gate has nothing to do, the point gate uses chi2 + 4 (fewer than 50 text blocks)
+    p_only = [PyramidLevel(synth.c3_pose_only(seed=12, n_pobs=120, n_planes=0))]
+    pg = np.ones(120, bool)
+    r = run_pyramid(oracle_solve_gated(oracle), p_only, (12.25,), (0.5,), (10,), pg, np.zeros(0, bool), np.zeros((0, 25), bool))
+    fr = r[0]["final_residuals"].reshape(-1, 2) / np.array(p_only[0].prob.w_point)
+    assert np.array_equal(~pg, ((fr ** 2) > 16.25).any(1))
+    assert run_pyramid(oracle_solve_gated(oracle), [], (), (), (), pg, np.zeros(0, bool), np.zeros((0, 25), bool)) == []
