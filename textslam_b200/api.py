@@ -276,12 +276,17 @@ class Optimizer:
         assert prob.cam_fixed.all(), "OptimizeLandmarker keeps every keyframe pose constant"
         return self.ctx.solve(prob, its, self.text_jac_mode)
 
-    def ThetaOptimMultiFs(self, prob, its=10):
+    def ThetaOptimMultiFs(self, prob, its=50):
         """optimizer::ThetaOptimMultiFs / PyrThetaOptim (src/optimizer.cc:2170-2242): plane parameters of text objects from several
-        frames with constant poses, followed by the 3x3 covariance of every plane (ceres::Covariance). Returns
-        (summary, final_residuals, trace, covariances (n_planes, 3, 3), flag) with flag = False when a covariance is singular —
-        the reference then reports failure for the object."""
+        frames with constant poses, followed by the 3x3 covariance of every plane (ceres::Covariance). PyrThetaOptim never sets
+        max_num_iterations (:2203-2209), so Ceres' default of 50 applies; it passes loss_function = nullptr (:2176) and
+        nume_thetaText is unweighted (include/nume_thetaText.h:67), hence the two preconditions checked here.
+        Returns (summary, final_residuals, trace, covariances (n_planes, 3, 3), flag_variance): flag_variance = False when a
+        covariance is singular — PyrThetaOptim itself still returns true in that case (:2219-2241), it only leaves
+        thetaVariance untouched, so the flag is reported beside the result and does not mean the solve failed."""
         assert prob.cam_fixed.all(), "ThetaOptimMultiFs keeps every pose constant"
+        assert prob.w_text == 1.0, "nume_thetaText is unweighted (include/nume_thetaText.h:67)"
+        assert prob.huber_text <= 0, "PyrThetaOptim uses no loss function (src/optimizer.cc:2176)"
         summ, fr, tr = self.ctx.solve(prob, its, self.text_jac_mode)
         cov, n_singular = self.ctx.theta_covariance(prob, self.text_jac_mode)
         return summ, fr, tr, cov, n_singular == 0

@@ -1,6 +1,7 @@
 // Structure analysis of a BA problem on the host — see analysis.hpp.
 #include "analysis.hpp"
 #include "nd_layout.h"
+#include "chol_sched.hpp"
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -225,6 +226,7 @@ int chol_workspace_dims(int n, int* ld, int* rows) {
 // panel k < j with L[j][k] != 0 is finished; panels of one wave are mutually independent, so a wave is three
 // launches (factor+solve, update, and later the backward solve) however many panels it holds. With the nested-
 // dissection camera order chosen below a banded problem needs ~15 waves instead of T = 47 panel steps.
+static void chol_fused_schedule(int Tn, const AVec<uint8_t>& P, const AVec<AVec<int>>& below, CholHost& H);
 void chol_symbolic_host(int n, const AVec<uint8_t>& tile_nz, CholHost& H) {
   int ld, rows;
   const int Tn = chol_workspace_dims(n, &ld, &rows);
@@ -330,6 +332,184 @@ void chol_symbolic_host(int n, const AVec<uint8_t>& tile_nz, CholHost& H) {
     H.item_ptr[w + 1] = (int)H.items.size(); H.item2_ptr[w + 1] = (int)H.items2.size();
     H.target_ptr[w + 1] = (int)H.targets.size(); H.panel_ptr[w + 1] = (int)H.panels.size();
   }
+  chol_fused_schedule(Tn, P, below, H);
+}
+
+// Fused schedule (chol_sched.hpp, chol_fused.cu). P = T1 x T1 pattern of L incl. fill and the b row, below[j] = its column lists.
+static void chol_fused_schedule(int Tn, const AVec<uint8_t>& P, const AVec<AVec<int>>& below, CholHost& H) {
+  const int T1 = Tn + 1;
+  // ---- compact ids of the pattern tiles + layout of the sync array ----
+  AVec<int> tid((size_t)T1 * T1, -1);
+  int ntile = 0;
+  for (int j = 0; j < Tn; ++j) { tid[(size_t)j * T1 + j] = ntile++; for (int i : below[j]) tid[(size_t)i * T1 + j] = ntile++; }
+  const int fin0 = FS_FIN0, bx0 = fin0 + Tn, xd0 = bx0 + Tn, uq0 = xd0 + ntile;
+  H.f_nsync = uq0 + 4 * ntile;
+  auto XD = [&](int i, int j) { return xd0 + tid[(size_t)i * T1 + j]; };
+  auto UQ = [&](int i, int k, int q) { return uq0 + 4 * tid[(size_t)i * T1 + k] + q; };
+  // ---- nodes: single tiles, or pairs (a, a+1) of coupled consecutive tiles whose second tile waits for nothing that
+  // finishes after the first tile's own inputs (every node of the tile-aligned nested-dissection layout is such a pair) ----
+  AVec<int> wave(Tn, 0);
+  for (int j = 0; j < Tn; ++j) { int w = 0; for (int k = 0; k < j; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, wave[k] + 1); wave[j] = w; }
+  AVec<int> unit_of(Tn, -1), unit_first, unit_size;
+  for (int j = 0; j < Tn;) {
+    bool pair = j + 1 < Tn && P[(size_t)(j + 1) * T1 + j];
+    if (pair) for (int k = 0; k < j; ++k) if (P[(size_t)(j + 1) * T1 + k] && wave[k] >= wave[j]) { pair = false; break; }
+    unit_of[j] = (int)unit_first.size();
+    if (pair) unit_of[j + 1] = (int)unit_first.size();
+    unit_first.push_back(j); unit_size.push_back(pair ? 2 : 1);
+    j += pair ? 2 : 1;
+  }
+  const int nunits = (int)unit_first.size();
+  H.f_nunits = nunits;
+  AVec<int> uwave(nunits, 0);
+  int nwaves = 0;
+  for (int u = 0; u < nunits; ++u) {
+    int w = 0;
+    for (int t = 0; t < unit_size[u]; ++t) { const int j = unit_first[u] + t; for (int k = 0; k < unit_first[u]; ++k) if (P[(size_t)j * T1 + k]) w = std::max(w, uwave[unit_of[k]] + 1); }
+    uwave[u] = w; nwaves = std::max(nwaves, w + 1);
+  }
+  auto twave = [&](int tile) { return tile >= Tn ? nwaves : uwave[unit_of[tile]]; };   // the b row is "needed" after everything else
+  // ---- tasks with sort keys ----
+  struct Tk { long long key; int rec[F_TASK_INTS]; int d0, d1, s0, s1; };
+  AVec<Tk> T;
+  AVec<I2> deps; AVec<int> srcs;
+  auto new_task = [&](int type, long long key) {
+    Tk t; t.key = key; for (int& v : t.rec) v = 0; t.rec[FK_TYPE] = type; t.rec[FK_SIG] = -1;
+    t.d0 = t.d1 = (int)deps.size(); t.s0 = t.s1 = (int)srcs.size(); T.push_back(t); return (int)T.size() - 1;
+  };
+  // key = ((5 * wave + slot) << 40) | secondary; slots: 0 updates needed by the wave, 1 F, 2 S of the first tile, 3 updates of the
+  // second tile's column from the first, 4 S of the second tile
+  auto KEY = [](int wv, int slot, long long sec) { return ((long long)(5 * wv + slot) << 40) | sec; };
+  // how finely the S tasks of a wave split their 64 rows: enough tasks for the machine, not more
+  AVec<int> rows_in_wave(nwaves, 0);
+  for (int j = 0; j < Tn; ++j) rows_in_wave[uwave[unit_of[j]]] += (int)below[j].size();
+  AVec<int> uq_total((size_t)4 * ntile, 0);
+  struct Upd { int i, k, wv; int s0, s1; };   // target tile, source wave, sources in usrc
+  AVec<Upd> upds; AVec<int> usrc;
+  AVec<int> tgt_index((size_t)T1 * T1, -1);
+  for (int w = 0; w < nwaves; ++w) {
+    const int nr = 4 * rows_in_wave[w] <= 160 ? 16 : (2 * rows_in_wave[w] <= 160 ? 32 : 64);
+    const size_t u_begin = upds.size();
+    AVec<AVec<int>> tsrc;
+    for (int u = 0; u < nunits; ++u) {
+      if (uwave[u] != w) continue;
+      const int a = unit_first[u], nt = unit_size[u], b = a + nt - 1;
+      {   // F
+        const int t = new_task(FT_F, KEY(w, 1, a));
+        Tk& k = T[t];
+        k.rec[FK_F_TILE] = a; k.rec[FK_F_NT] = nt; k.rec[FK_F_XBA] = nt == 2 ? XD(b, a) : -1; k.rec[FK_F_FIN] = fin0 + a;
+      }
+      for (int t2 = 0; t2 < nt; ++t2) {   // S
+        const int j = a + t2;
+        for (int i : below[j]) {
+          if (nt == 2 && j == a && i == b) continue;   // L_ba is produced inside F
+          const int step = i == Tn ? 64 : nr;
+          for (int r0 = 0; r0 < 64; r0 += step) {
+            const int t = new_task(FT_S, KEY(w, t2 == 0 ? 2 : 4, ((long long)twave(i) << 24) | ((long long)i << 8) | (r0 >> 3)));
+            Tk& k = T[t];
+            k.rec[FK_S_J] = j; k.rec[FK_S_I] = i; k.rec[FK_S_ROW0] = r0; k.rec[FK_S_NROWS] = i == Tn ? 8 : step;   // b row: only row 0 carries data
+            k.rec[FK_SIG] = XD(i, j); k.rec[FK_SIGINC] = step;
+          }
+        }
+      }
+      for (int t2 = 0; t2 < nt; ++t2) {   // updates
+        const int j = a + t2;
+        const AVec<int>& nz = below[j];
+        for (size_t x = 0; x < nz.size(); ++x)
+          for (size_t y = 0; y <= x; ++y) {
+            const int i = nz[x], k = nz[y];
+            if (i == Tn && k == Tn) continue;                 // (b row, b row) is never read
+            if (nt == 2 && j == a && k == b) {
+              if (i == b) continue;                           // A_bb -= L_ba L_ba^T happens inside F
+              upds.push_back(Upd{i, k, -1 - w, (int)usrc.size(), (int)usrc.size() + 1}); usrc.push_back(a);   // column b from tile a: slot 3 of this wave
+              continue;
+            }
+            int& ti = tgt_index[(size_t)i * T1 + k];
+            if (ti < 0) { ti = (int)tsrc.size(); tsrc.emplace_back(); upds.push_back(Upd{i, k, w, 0, 0}); }
+            tsrc[ti].push_back(j);
+          }
+      }
+    }
+    {   // flatten the per-target source lists of this wave
+      size_t x = 0;
+      for (size_t q = u_begin; q < upds.size(); ++q) {
+        Upd& U = upds[q];
+        if (U.wv < 0) continue;
+        U.s0 = (int)usrc.size(); for (int j : tsrc[x]) usrc.push_back(j); U.s1 = (int)usrc.size(); ++x;
+        tgt_index[(size_t)U.i * T1 + U.k] = -1;
+      }
+    }
+  }
+  for (const Upd& U : upds) {
+    const bool mid = U.wv < 0;
+    const int sw = mid ? -1 - U.wv : U.wv;
+    const int nq0 = U.i == Tn ? 2 : 4;   // b row: only the upper quadrants (rows 0..31) carry data
+    for (int q = 0; q < nq0; ++q) {
+      if (U.i == U.k && q == 1) continue;   // upper-right quadrant of a diagonal tile is never read
+      const bool feeds_f = U.k < Tn && U.i < Tn && unit_of[U.i] == unit_of[U.k];
+      const long long sec = ((long long)(feeds_f ? 0 : 1) << 36) | ((long long)(mid ? sw : sw) << 24) | ((long long)U.i << 12) | ((long long)U.k << 2) | q;
+      const int t = new_task(FT_U, mid ? KEY(sw, 3, sec) : KEY(twave(U.k), 0, sec));
+      Tk& k = T[t];
+      k.rec[FK_U_I] = U.i; k.rec[FK_U_K] = U.k; k.rec[FK_U_Q] = q; k.s0 = U.s0; k.s1 = U.s1;   // sources resolved below (usrc)
+      k.rec[FK_SIG] = UQ(U.i, U.k, q); k.rec[FK_SIGINC] = 1;
+      uq_total[(size_t)4 * tid[(size_t)U.i * T1 + U.k] + q]++;
+    }
+  }
+  for (int j = Tn - 1; j >= 0; --j) {   // backward solve, last tile first
+    const int t = new_task(FT_B, KEY(nwaves + 1, 0, Tn - 1 - j));
+    T[t].rec[FK_B_J] = j; T[t].rec[FK_SIG] = bx0 + j; T[t].rec[FK_SIGINC] = 1;
+  }
+  // ---- final order, then the dependencies (the order of the updates on one quadrant is their queue order) ----
+  AVec<int> ord(T.size());
+  for (size_t q = 0; q < ord.size(); ++q) ord[q] = (int)q;
+  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return T[x].key < T[y].key; });
+  AVec<int> uq_seen((size_t)4 * ntile, 0);
+  H.f_tasks.clear(); H.f_deps.clear(); H.f_srcs.clear(); H.f_below.clear();
+  H.f_tasks.reserve(T.size() * F_TASK_INTS);
+  auto need_uq = [&](int i, int k, int q) { const int n = uq_total[(size_t)4 * tid[(size_t)i * T1 + k] + q]; if (n > 0) H.f_deps.push_back(I2{UQ(i, k, q), n}); };
+  for (int o : ord) {
+    Tk& k = T[o];
+    k.rec[FK_DEP0] = (int)H.f_deps.size();
+    switch (k.rec[FK_TYPE]) {
+      case FT_F: {
+        const int a = k.rec[FK_F_TILE], nt = k.rec[FK_F_NT];
+        for (int t2 = 0; t2 < nt; ++t2) { need_uq(a + t2, a + t2, 0); need_uq(a + t2, a + t2, 2); need_uq(a + t2, a + t2, 3); }
+        if (nt == 2) for (int q = 0; q < 4; ++q) need_uq(a + 1, a, q);
+      } break;
+      case FT_S: {
+        const int j = k.rec[FK_S_J], i = k.rec[FK_S_I], r0 = k.rec[FK_S_ROW0], nr = k.rec[FK_S_NROWS];
+        H.f_deps.push_back(I2{fin0 + j, 1});
+        for (int h = r0 / 32; h <= (r0 + nr - 1) / 32; ++h) { need_uq(i, j, 2 * h); need_uq(i, j, 2 * h + 1); }
+      } break;
+      case FT_U: {
+        const int i = k.rec[FK_U_I], kk = k.rec[FK_U_K], q = k.rec[FK_U_Q];
+        k.rec[FK_U_SRC0] = (int)H.f_srcs.size();
+        for (int e = k.s0; e < k.s1; ++e) {
+          const int j = usrc[e];
+          H.f_srcs.push_back(j);
+          H.f_deps.push_back(I2{XD(i, j), 64});
+          if (kk != i) H.f_deps.push_back(I2{XD(kk, j), 64});
+        }
+        k.rec[FK_U_SRC1] = (int)H.f_srcs.size();
+        int& seen = uq_seen[(size_t)4 * tid[(size_t)i * T1 + kk] + q];
+        if (seen > 0) H.f_deps.push_back(I2{UQ(i, kk, q), seen});
+        ++seen;
+      } break;
+      case FT_B: {
+        const int j = k.rec[FK_B_J];
+        // first what is final before any x_i is (the task stages it while it waits): L_jj^-1, y_j, the L_ij tiles; then the x_i
+        H.f_deps.push_back(I2{fin0 + j, 1});
+        H.f_deps.push_back(I2{XD(Tn, j), 64});
+        k.rec[FK_B_BEL0] = (int)H.f_below.size();
+        for (int i : below[j]) if (i < Tn) { H.f_below.push_back(i); H.f_deps.push_back(I2{XD(i, j), 64}); }
+        k.rec[FK_B_BEL1] = (int)H.f_below.size();
+        for (int i : below[j]) if (i < Tn) H.f_deps.push_back(I2{bx0 + i, 1});
+      } break;
+    }
+    k.rec[FK_DEP1] = (int)H.f_deps.size();
+    for (int v : k.rec) H.f_tasks.push_back(v);
+  }
+  H.f_ntasks = (int)T.size();
 }
 
 namespace {

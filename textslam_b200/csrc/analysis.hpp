@@ -70,6 +70,13 @@ struct CholHost {  // tile-level symbolic factorisation + level schedule (see ch
   AVec<int> item_ptr, item2_ptr, target_ptr, panel_ptr;   // per wave ranges
   AVec<I2> items, items2, targets, clear_items;           // single-tile panels, two-tile panels (see analysis.cpp), update targets, all pattern tiles
   AVec<int> src_ptr, src, panels, below_ptr, below;
+  // ---- fused schedule (chol_fused.cu): the whole factorisation + both triangular solves as ONE persistent launch whose
+  // CTAs pop tasks from a topologically sorted queue and wait on counters in `sync` (zeroed before every solve) ----
+  int f_ntasks = 0, f_nsync = 0, f_nunits = 0;
+  AVec<int> f_tasks;   // F_TASK_INTS ints per task, see chol_sched.hpp
+  AVec<I2> f_deps;     // (index into sync, minimum value) pairs a task waits for
+  AVec<int> f_srcs;    // source tiles of the update tasks
+  AVec<int> f_below;   // row tiles (< Tn) of the backward-solve tasks
 };
 
 struct Analysis {

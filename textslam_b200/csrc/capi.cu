@@ -66,14 +66,25 @@ static int upload_selected(DevBuf<T>& dst, DevBuf<T>& scratch, const T* src, siz
 int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool persistent) {
   if (!p) return set_error(TSLAM_ERR_ARG, "null problem");
   if (p->n_cams <= 0 || !p->cams) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
+  if (p->n_points < 0 || p->n_planes < 0 || p->n_pobs < 0 || p->n_tobs < 0 || p->n_imgs < 0) return set_error(TSLAM_ERR_ARG, "negative count");
+  if (p->n_points > 0 && !p->rho) return set_error(TSLAM_ERR_ARG, "n_points > 0 but rho is NULL");
+  if (p->n_planes > 0 && !p->theta) return set_error(TSLAM_ERR_ARG, "n_planes > 0 but theta is NULL");
+  if (p->n_pobs > 0 && (!p->p_cam || !p->p_host || !p->p_lm || !p->p_uv || !p->p_ray)) return set_error(TSLAM_ERR_ARG, "n_pobs > 0 but a point observation array is NULL");
+  if (p->n_tobs > 0 && (!p->t_cam || !p->t_host || !p->t_plane || !p->t_img || !p->t_rays || !p->t_iref || !p->t_musigma))
+    return set_error(TSLAM_ERR_ARG, "n_tobs > 0 but a text block array is NULL");
+  if (p->n_tobs > 0 && (p->n_imgs <= 0 || !p->imgs || p->img_w <= 0 || p->img_h <= 0)) return set_error(TSLAM_ERR_ARG, "text blocks without images");
   for (int i = 0; i < p->n_pobs; ++i) {
     if ((unsigned)p->p_cam[i] >= (unsigned)p->n_cams || (unsigned)p->p_host[i] >= (unsigned)p->n_cams || (unsigned)p->p_lm[i] >= (unsigned)p->n_points)
       return set_error(TSLAM_ERR_ARG, "point observation %d has an index out of range", i);
+    // the reference skips host == target observations (src/optimizer.cc:1397-1398, 1740) and Ceres rejects a residual block that
+    // names one parameter block twice; accepting it here would silently drop the J_c^T J_h cross term
+    if (p->p_cam[i] == p->p_host[i]) return set_error(TSLAM_ERR_ARG, "point observation %d: observing and host camera are the same block", i);
   }
   for (int i = 0; i < p->n_tobs; ++i) {
     if ((unsigned)p->t_cam[i] >= (unsigned)p->n_cams || (unsigned)p->t_host[i] >= (unsigned)p->n_cams || (unsigned)p->t_plane[i] >= (unsigned)p->n_planes ||
         (unsigned)p->t_img[i] >= (unsigned)p->n_imgs)
       return set_error(TSLAM_ERR_ARG, "text block %d has an index out of range", i);
+    if (p->t_cam[i] == p->t_host[i]) return set_error(TSLAM_ERR_ARG, "text block %d: observing and host camera are the same block (src/optimizer.cc:1485-1486)", i);
   }
   cudaStream_t s = ctx->stream;
   d->n_cams = p->n_cams; d->n_points = p->n_points; d->n_planes = p->n_planes;

@@ -26,6 +26,7 @@
 #include "ctx.cuh"
 #include "solver.cuh"
 #include "chol_tile.cuh"
+#include "chol_sched.hpp"
 
 namespace tsl {
 
@@ -351,6 +352,11 @@ __global__ void copy_row_kernel(const double* __restrict__ src, double* __restri
   if (i < n) dst[i] = src[i];
 }
 
+bool chol_fused_enabled() {
+  static const bool on = [] { const char* e = getenv("TSLAM_CHOL_FUSED"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: symbolic tile factorisation + launch sequence
 // ---------------------------------------------------------------------------------------------
@@ -385,6 +391,7 @@ int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
   TSL_CUDA(sym->flags.reserve((size_t)(H.Tn ? H.Tn : 1)));
   TSL_CUDA(cudaMemsetAsync(sym->flags.p, 0, sizeof(int) * (size_t)(H.Tn ? H.Tn : 1), s));
   sym->epoch = 0;
+  { int rc = chol_fused_upload(ctx, H, sym); if (rc) return rc; }
   return TSLAM_OK;   // the caller synchronises the stream before H goes away
 }
 
@@ -395,24 +402,30 @@ int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A) {
   const int ni = sym.n_clear;
   if (ni > 0) LAUNCH(launch_k(zero_tiles_kernel, ni, 256, 0, ctx->stream, A, ld, sym.clear_items.p));
   TSL_CHECK_LAUNCH();
+  if (chol_fused_enabled() && sym.f_ntasks > 0) return chol_fused_clear(ctx, sym);
   return TSLAM_OK;
 }
 
 // Factor + solve. A: (Tn+1)*64 x ld as described above. xout: ld doubles (receives y, then x).
 int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail) {
   (void)ywork;
+  if (chol_fused_enabled() && sym.f_ntasks > 0) return chol_fused_solve(ctx, sym, A, xout, d_fail, nullptr);
+  return chol_solve_waves(ctx, sym, A, xout, d_fail);
+}
+
+// The wave-scheduled launch sequence (TSLAM_CHOL_FUSED=0): one potrf_trsm + one syrk launch per wave, then the backward solve.
+int chol_solve_waves(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* xout, int* d_fail) {
   int ld, rows;
   const int Tn = chol_workspace_dims(sym.n, &ld, &rows);
-  static bool attr_set = false;
   const int smem = 2 * QB * SPAD * (int)sizeof(double);
   const int smem_pt = 3 * NB * LD2 * (int)sizeof(double);
   const int smem_p2 = 6 * NB * LD2 * (int)sizeof(double);
-  if (!attr_set) {
+  if (!ctx->attr_chol_waves) {
     TSL_CUDA(cudaFuncSetAttribute(potrf2_trsm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p2));
     TSL_CUDA(cudaFuncSetAttribute(syrk_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
     TSL_CUDA(cudaFuncSetAttribute(potrf_trsm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pt));
-    attr_set = true;
+    ctx->attr_chol_waves = true;
   }
   cudaStream_t s = ctx->stream;
   // TSLAM_CHOL_TRACE=1: per-kernel-class device time of this call (CUDA events between launches; debugging aid only)
@@ -453,3 +466,82 @@ int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork
 }
 
 }  // namespace tsl
+
+using namespace tsl;
+
+// Test hook (host only, no device needed): the fused task schedule of an n x n system with the given lower-triangular tile
+// pattern (Tn x Tn flags, Tn = ceil(n / 64)). counts_out = {tasks, deps, srcs, below, sync ints, Tn}; the arrays are filled up to
+// their capacities (call once with zero capacities for the sizes).
+extern "C" int tslam_debug_chol_schedule(int n, const uint8_t* tile_nz, int32_t counts_out[6], int32_t* tasks, int cap_tasks, int32_t* deps, int cap_deps,
+                                         int32_t* srcs, int cap_srcs, int32_t* below, int cap_below) {
+  if (n <= 0 || !tile_nz || !counts_out) return set_error(TSLAM_ERR_ARG, "bad argument");
+  Arena arena([](size_t b) -> void* { return malloc(b); }, [](void* q) { free(q); });
+  CholHost H;
+  try { chol_symbolic_in_arena(n, tile_nz, arena, H); } catch (const std::exception& e) { return set_error(TSLAM_ERR_ARG, "symbolic factorisation failed: %s", e.what()); }
+  counts_out[0] = H.f_ntasks; counts_out[1] = (int)H.f_deps.size(); counts_out[2] = (int)H.f_srcs.size(); counts_out[3] = (int)H.f_below.size();
+  counts_out[4] = H.f_nsync; counts_out[5] = H.Tn;
+  if (tasks) std::copy(H.f_tasks.begin(), H.f_tasks.begin() + std::min<size_t>(H.f_tasks.size(), (size_t)cap_tasks * F_TASK_INTS), tasks);
+  if (deps) for (size_t e = 0; e < H.f_deps.size() && e < (size_t)cap_deps; ++e) { deps[2 * e] = H.f_deps[e].x; deps[2 * e + 1] = H.f_deps[e].y; }
+  if (srcs) std::copy(H.f_srcs.begin(), H.f_srcs.begin() + std::min<size_t>(H.f_srcs.size(), (size_t)cap_srcs), srcs);
+  if (below) std::copy(H.f_below.begin(), H.f_below.begin() + std::min<size_t>(H.f_below.size(), (size_t)cap_below), below);
+  return TSLAM_OK;
+}
+
+// Test / bench hook: solves S x = b for a dense symmetric positive definite S (n x n, row-major, lower triangle read) through the
+// reduced-system solver alone. tile_nz: Tn x Tn lower tile pattern or NULL (derived from the non-zeros of S).
+// mode 0 = wave kernels, 1 = fused persistent kernel. ms_out = mean device time of the solve over `reps` runs (the workspace is
+// restored before each). trace_out (fused only): 4 uint64 per task (pop, inputs ready, done [ns], SM id), up to trace_cap tasks.
+extern "C" int tslam_dev_chol_solve(tslam_ctx* ctx, int n, const uint8_t* tile_nz, const double* S, const double* b, double* x_out, int mode, int reps,
+                                    float* ms_out, uint64_t* trace_out, int trace_cap, int32_t* info_out /*[4]: tasks, waves, Tn, fail*/) {
+  if (!ctx || n <= 0 || !S || !b || !x_out) return set_error(TSLAM_ERR_ARG, "null argument");
+  TSL_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int ld, rows;
+  const int Tn = chol_workspace_dims(n, &ld, &rows);
+  std::vector<uint8_t> tz((size_t)Tn * Tn, 0);
+  if (tile_nz) tz.assign(tile_nz, tile_nz + (size_t)Tn * Tn);
+  else
+    for (int r = 0; r < n; ++r) for (int c = 0; c <= r; ++c) if (S[(size_t)r * n + c] != 0.0) tz[(size_t)(r / NB) * Tn + c / NB] = 1;
+  if (!ctx->host_arena)
+    ctx->host_arena = new Arena([](size_t nb) -> void* { void* q = nullptr; return cudaHostAlloc(&q, nb, cudaHostAllocDefault) == cudaSuccess ? q : nullptr; },
+                                [](void* q) { cudaFreeHost(q); });
+  CholHost H;
+  try { chol_symbolic_in_arena(n, tz.data(), *ctx->host_arena, H); } catch (const std::exception& e) { return set_error(TSLAM_ERR_CUDA, "symbolic factorisation failed: %s", e.what()); }
+  CholSymbolic sym;
+  int rc = chol_upload(ctx, H, &sym);
+  if (rc) return rc;
+  // padded workspace image: lower triangle of S, unit diagonal on the padding, b in the first row of the extra tile row
+  std::vector<double> W0((size_t)rows * ld, 0.0);
+  for (int r = 0; r < n; ++r) for (int c = 0; c <= r; ++c) W0[(size_t)r * ld + c] = S[(size_t)r * n + c];
+  for (int r = n; r < Tn * NB; ++r) W0[(size_t)r * ld + r] = 1.0;
+  for (int c = 0; c < n; ++c) W0[(size_t)Tn * NB * ld + c] = b[c];
+  DevBuf<double> A0, A, x; DevBuf<int> fail; DevBuf<unsigned long long> trace;
+  TSL_CUDA(A0.upload(W0.data(), W0.size(), st)); TSL_CUDA(A.reserve(W0.size())); TSL_CUDA(x.reserve(ld)); TSL_CUDA(fail.reserve(1));
+  TSL_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), st));
+  const bool fused = mode == 1;
+  if (fused && trace_out) { TSL_CUDA(trace.reserve(4 * (size_t)H.f_ntasks)); TSL_CUDA(cudaMemsetAsync(trace.p, 0, 32 * (size_t)H.f_ntasks, st)); }
+  float total = 0.f;
+  for (int it = 0; it < std::max(1, reps); ++it) {
+    TSL_CUDA(cudaMemcpyAsync(A.p, A0.p, W0.size() * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (fused) { if ((rc = chol_fused_clear(ctx, sym))) return rc; }
+    TSL_CUDA(cudaEventRecord(ctx->ev0, st));
+    if (fused) rc = chol_fused_solve(ctx, sym, A.p, x.p, fail.p, trace_out ? trace.p : nullptr);
+    else rc = chol_solve_waves(ctx, sym, A.p, x.p, fail.p);
+    if (rc) return rc;
+    TSL_CUDA(cudaEventRecord(ctx->ev1, st));
+    TSL_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    TSL_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    total += ms;
+  }
+  if (ms_out) *ms_out = total / std::max(1, reps);
+  std::vector<double> xh(ld);
+  int hfail = 0;
+  TSL_CUDA(cudaMemcpyAsync(xh.data(), x.p, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
+  TSL_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (fused && trace_out) TSL_CUDA(cudaMemcpyAsync(trace_out, trace.p, 32 * (size_t)std::min(trace_cap, H.f_ntasks), cudaMemcpyDeviceToHost, st));
+  TSL_CUDA(cudaStreamSynchronize(st));
+  std::copy(xh.begin(), xh.begin() + n, x_out);
+  if (info_out) { info_out[0] = H.f_ntasks; info_out[1] = H.nwaves; info_out[2] = Tn; info_out[3] = hfail; }
+  return TSLAM_OK;
+}

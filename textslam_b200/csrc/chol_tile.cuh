@@ -2,11 +2,10 @@
 // can time and verify them in isolation.
 #pragma once
 #include <cuda_runtime.h>
+#include "chol_common.cuh"
 
 namespace tsl {
 
-constexpr int NB = 64;
-constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4 fragment loads
 
 // ---------------------------------------------------------------------------------------------
 // device tile routines for the 64x64 diagonal tile (CTA = 128 threads, tile and right-hand side in shared memory).
@@ -15,7 +14,6 @@ constexpr int SPAD = NB + 4;  // smem row stride (doubles): conflict-free m8n8k4
 // between the halves is a small register-tiled GEMM. A flat 64-column unrolled version measured 64 us per launch
 // because 3 x 2016 FMAs of straight-line code miss the instruction cache (profiles/r1_notes.md).
 // ---------------------------------------------------------------------------------------------
-constexpr int HB = 32;             // half block
 constexpr int LDT = NB + 1;        // smem leading dimension (doubles)
 constexpr int PT_THREADS = 128;    // CTA size of potrf_trsm_kernel
 
@@ -128,11 +126,6 @@ __device__ __forceinline__ void trsm_tile(double* sX, const double* sT, const do
   __syncthreads();
 }
 
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
 
 // C (64x64 at C, ld) -= Xi Xk^T with Xi, Xk 64x64 tiles (ld). 4 warps (2x2), warp tile 32x32.
 __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, const double* __restrict__ Xk, double* __restrict__ C, int ld,
@@ -199,14 +192,6 @@ __device__ __forceinline__ void gemm_tile_nt(const double* __restrict__ Xi, cons
 // =============================================================================================
 constexpr int LD2 = NB + 2;
 
-// 1/sqrt(d), branch-free: MUFU.RSQ64H seed (PTX rsqrt.approx.ftz.f64, ~2^-22) and one cubic (Householder) step
-// y = y0 + y0 e (1/2 + 3/8 e), e = 1 - d y0^2  -> relative error ~ e^3, i.e. rounding level.
-__device__ __forceinline__ double rsqrt_pivot(double d) {
-  double y0;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-  const double e = fma(-d, y0 * y0, 1.0);
-  return fma(fma(e, 0.375, 0.5), y0 * e, y0);
-}
 
 // Cholesky of the 32x32 block at M (lower, in place, leading dimension LD2) by ONE warp; lane r owns row r in
 // registers. Also writes the transpose of the factor to Mt (Mt[c][r] = L[r][c]) for the right-looking solves and

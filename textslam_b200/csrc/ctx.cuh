@@ -116,6 +116,9 @@ struct tslam_ctx {
   double h_seq = 0.0;                // last sequence number handed to a publishing kernel
   // page-locked arena behind the host-side structure analysis (analysis.hpp); recycled by every solve on this context
   tsl::Arena* host_arena = nullptr;
+  // per-context (= per-device) opt-ins to more than 48 KB of dynamic shared memory
+  bool attr_chol_fused = false, attr_chol_waves = false, attr_orb = false;
+  size_t attr_textinfo_smem = 0;
 };
 
 // Device-resident problem: everything the kernels read, SoA, FP64 / int32 / u8.

@@ -49,6 +49,7 @@ extern "C" int tslam_match_hamming(tslam_ctx* ctx, const uint8_t* query_desc, in
                                    const int32_t* cand_ptr, const int32_t* cand_idx, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist) {
   if (!ctx || !query_desc || !train_desc || !cand_ptr || !best_idx || !best_dist) return set_error(TSLAM_ERR_ARG, "null argument");
   if (n_query <= 0) return TSLAM_OK;
+  if (cand_ptr[0] != 0) return set_error(TSLAM_ERR_ARG, "cand_ptr[0] must be 0");
   const int nc = cand_ptr[n_query];
   for (int i = 0; i < n_query; ++i)
     if (cand_ptr[i + 1] < cand_ptr[i] || cand_ptr[i + 1] - cand_ptr[i] > 0xFFFFF) return set_error(TSLAM_ERR_ARG, "bad candidate list of query %d", i);

@@ -714,7 +714,7 @@ static void resize_table(int sn, int dn, std::vector<int>& ofs, std::vector<shor
 static int orb_configure(tslam_orb* o, int w, int h, int n_imgs) {
   tslam_ctx* ctx = o->ctx; cudaStream_t st = ctx->stream;
   if (o->w != w || o->h != h) {
-    o->w = w; o->h = h; o->n_alloc = 0;
+    o->w = 0; o->h = 0; o->n_alloc = 0;   // committed only after every check below has passed: a failed call must not leave a half-built table behind a matching size
     o->L.assign(o->nlevels, LevelInfo());
     std::vector<CellRect> cells;
     std::vector<int> xofs, yofs; std::vector<short> xa, ya;
@@ -767,6 +767,7 @@ static int orb_configure(tslam_orb* o, int w, int h, int n_imgs) {
     TSL_CUDA(o->xofs.upload(xofs.data(), xofs.size(), st)); TSL_CUDA(o->yofs.upload(yofs.data(), yofs.size(), st));
     TSL_CUDA(o->xa.upload(xa.data(), xa.size(), st)); TSL_CUDA(o->ya.upload(ya.data(), ya.size(), st));
     TSL_CUDA(cudaStreamSynchronize(st));
+    o->w = w; o->h = h;
   }
   if (n_imgs > o->n_alloc) {
     const size_t n = n_imgs;
@@ -785,8 +786,8 @@ static int orb_configure(tslam_orb* o, int w, int h, int n_imgs) {
 // the whole extractor on images already stored as level 0 of the pyramid records
 static int orb_run(tslam_orb* o, int n) {
   tslam_ctx* ctx = o->ctx; cudaStream_t st = ctx->stream;
-  static bool attr = false;
-  if (!attr) { TSL_CUDA(cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DistSmem))); attr = true; }
+  // the opt-in is per device: tracked per context, not per process (several contexts on several GPUs may live in one process)
+  if (!ctx->attr_orb) { TSL_CUDA(cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DistSmem))); ctx->attr_orb = true; }
   TSL_CUDA(cudaMemsetAsync(o->err.p, 0, sizeof(int), st));
   for (int l = 1; l < o->nlevels; ++l) {
     const LevelInfo& s = o->L[l - 1]; const LevelInfo& d = o->L[l];

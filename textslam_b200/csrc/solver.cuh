@@ -19,10 +19,21 @@ struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (pe
   mutable DevBuf<int> flags;                          // backward solve: flags[j] == epoch <=> x_j final in the current call
   mutable int epoch = 0;
   long long gemm_tiles = 0;                           // number of 64x64x64 tile updates (2*64^3 flop each)
+  // fused schedule (chol_fused.cu, chol_sched.hpp)
+  int f_ntasks = 0, f_nsync = 0;
+  DevBuf<int> f_tasks, f_srcs, f_below;
+  DevBuf<int2> f_deps;
+  mutable DevBuf<int> f_sync;                         // queue head + dependency counters, zeroed before every solve
 };
 int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);   // device copy of the host symbolic factorisation (analysis.cpp)
 int chol_clear(tslam_ctx* ctx, const CholSymbolic& sym, double* A);
 int chol_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* ywork, double* xout, int* d_fail);
+int chol_solve_waves(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* xout, int* d_fail);
+bool chol_fused_enabled();   // TSLAM_CHOL_FUSED != "0"
+// chol_fused.cu
+int chol_fused_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);
+int chol_fused_clear(tslam_ctx* ctx, const CholSymbolic& sym);
+int chol_fused_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double* xout, int* d_fail, unsigned long long* trace);
 
 // Index structures of one problem on the device (what the structure analysis produces; analysis.cpp on the host or
 // analysis_dev.cu on the GPU) — the LM kernels of ba_solve.cu only ever read these.

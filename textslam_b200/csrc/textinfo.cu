@@ -162,8 +162,7 @@ extern "C" int tslam_text_info(tslam_ctx* ctx, const uint8_t* imgs, int n_imgs, 
   if (smem > 200 * 1024) return set_error(TSLAM_ERR_ARG, "image %dx%d too large for the shared-memory mask (%zu B)", w, h, smem);
   TSL_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) { TSL_CUDA(cudaFuncSetAttribute(text_info_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+  if (smem > ctx->attr_textinfo_smem) { TSL_CUDA(cudaFuncSetAttribute(text_info_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->attr_textinfo_smem = smem; }
   DevBuf<uint8_t> dimg; DevBuf<double> dq, dmu, dsg; DevBuf<int> dqi, dok;
   TSL_CUDA(dimg.upload(imgs, (size_t)n_imgs * w * h, st)); TSL_CUDA(dq.upload(quads, 8 * (size_t)n_quads, st)); TSL_CUDA(dqi.upload(quad_img, n_quads, st));
   TSL_CUDA(dmu.reserve(n_quads)); TSL_CUDA(dsg.reserve(n_quads)); TSL_CUDA(dok.reserve(n_quads));
