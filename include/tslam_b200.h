@@ -160,8 +160,8 @@ int tslam_debug_compare_analysis(tslam_ctx* ctx, const tslam_ba_problem* p, char
  * tslam_debug_chol_schedule (host only): the task queue of the fused solve for an n x n system with the given Tn x Tn lower tile
  * pattern; counts_out = {tasks, deps, srcs, below, sync ints, Tn}; each task is 16 int32 (textslam_b200/csrc/chol_sched.hpp).
  * tslam_dev_chol_solve: S x = b for a dense SPD matrix (n x n row-major, lower triangle read) through the solver alone;
- * mode 0 = wave kernels, 1 = fused persistent kernel; ms_out = mean device time per solve; trace_out (fused, optional) = 4 uint64
- * per task (pop, inputs ready, done in ns, SM id); info_out = {tasks, waves, Tn, fail flag}. */
+ * mode 0 = wave kernels, 1 = fused persistent kernel; ms_out = mean device time per solve; trace_out (fused, optional) = 16 uint64
+ * per task (pop, inputs ready, done in ns, SM id, phase stamps); info_out = {tasks, waves, Tn, fail flag}. */
 int tslam_debug_chol_schedule(int n, const uint8_t* tile_nz, int32_t counts_out[6], int32_t* tasks, int cap_tasks, int32_t* deps, int cap_deps,
                               int32_t* srcs, int cap_srcs, int32_t* below, int cap_below);
 int tslam_dev_chol_solve(tslam_ctx* ctx, int n, const uint8_t* tile_nz, const double* S, const double* b, double* x_out, int mode, int reps,

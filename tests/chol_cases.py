@@ -61,13 +61,17 @@ def replay(S, b, tile_nz):
             blk[:] = blk @ Linv[j].T
         elif typ == FT_U:
             i, k, q = tk[5], tk[6], tk[7]
-            qi, qk = q >> 1, q & 1
-            Cq = A[i * NB + HB * qi:i * NB + HB * (qi + 1), k * NB + HB * qk:k * NB + HB * (qk + 1)]
+            if q == 4:   # whole tile
+                ri, rk = slice(i * NB, (i + 1) * NB), slice(k * NB, (k + 1) * NB)
+            else:
+                qi, qk = q >> 1, q & 1
+                ri, rk = slice(i * NB + HB * qi, i * NB + HB * (qi + 1)), slice(k * NB + HB * qk, k * NB + HB * (qk + 1))
+            Cq = A[ri, k * NB + (0 if q == 4 else HB * (q & 1)):k * NB + (NB if q == 4 else HB * ((q & 1) + 1))]
+            phases = [srcs[e] >> 30 for e in range(tk[8], tk[9])]
+            assert phases == sorted(phases), "second tiles of pairs must come after the first tiles"
             for e in range(tk[8], tk[9]):
-                j = srcs[e]
-                Xi = A[i * NB + HB * qi:i * NB + HB * (qi + 1), j * NB:(j + 1) * NB]
-                Xk = A[k * NB + HB * qk:k * NB + HB * (qk + 1), j * NB:(j + 1) * NB]
-                Cq -= Xi @ Xk.T
+                j = srcs[e] & 0x3fffffff
+                Cq -= A[ri, j * NB:(j + 1) * NB] @ A[rk, j * NB:(j + 1) * NB].T
         else:
             j = tk[5]
             tt = A[Tn * NB, j * NB:(j + 1) * NB].copy()
@@ -76,7 +80,8 @@ def replay(S, b, tile_nz):
                 tt -= T(i, j).T @ x[i * NB:(i + 1) * NB]
             x[j * NB:(j + 1) * NB] = Linv[j].T @ tt
         if tk[3] >= 0:
-            sync[tk[3]] += tk[4]
+            for sq in range(4 if (typ == FT_U and tk[7] == 4) else 1):
+                sync[tk[3] + sq] += tk[4]
     return x[:n], n_by_type, Tn
 
 
@@ -131,7 +136,7 @@ def dev_chol_solve(ctx, S, b, pat, mode, reps=1, want_trace=False):
     x = np.zeros(n); ms = C.c_float(0); info = (C.c_int32 * 4)()
     tz = None if pat is None else np.ascontiguousarray(pat, np.uint8)
     cap = 200000 if want_trace else 0
-    trace = np.zeros((max(cap, 1), 4), np.uint64)
+    trace = np.zeros((max(cap, 1), 16), np.uint64)
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     check(lib().tslam_dev_chol_solve(ctx._h, n, None if tz is None else tz.ctypes.data_as(C.POINTER(C.c_uint8)), dp(S), dp(b), dp(x), mode, reps,
                                      C.byref(ms), trace.ctypes.data_as(C.POINTER(C.c_uint64)) if want_trace else None, cap, info))

@@ -39,7 +39,47 @@ def test_pose_only_c3(ctx, oracle):
 
 
 def test_pose_only_c3_central_diff(ctx, oracle):
-    _compare(ctx, oracle, synth.c3_pose_only(seed=22), 10, JAC_CENTRAL_DIFF, rtol=1e-4)
+    """Ceres-faithful Jacobian mode (NumericDiff CENTRAL of the functor as written, include/nume_PoseOptimText.h:81-84): the
+    device evaluates the functor with the oracle's operation sequence and no FMA contraction (ba_device.cuh:
+    text_residual_exact), so the north-star tolerance holds in this mode too."""
+    _compare(ctx, oracle, synth.c3_pose_only(seed=22), 10, JAC_CENTRAL_DIFF, rtol=RTOL)
+
+
+def test_local_ba_c4_central_diff(ctx, oracle):
+    """nume_BAText in local BA (src/optimizer.cc:1504), 35 functor calls per Jacobian. Residuals are bit-identical to the oracle's
+    and the numeric Jacobian agrees to 1e-14 (test_central_diff_jacobian_is_reproduced below), but a central difference with
+    h ~ 1e-8 carries ~1e-9 of rounding noise that is a discontinuous function of the evaluation point: two correct solvers whose
+    LM steps differ in the last digits (1e-12 here after the first step) see unrelated noise one iteration later, and on this
+    far-from-converged problem (cost 73k -> 16k in 10 iterations) the difference grows until a +-h stencil straddles a pixel
+    cell differently (iteration 7 on this seed). The north-star tolerance is therefore asserted over the first 6 iterations;
+    the full 10 are compared loosely below."""
+    _compare(ctx, oracle, synth.c4_local_ba(seed=41), 6, JAC_CENTRAL_DIFF, rtol=RTOL)
+    a, b = synth.c4_local_ba(seed=41), synth.c4_local_ba(seed=41)
+    so, _, _ = oracle.solve(a, 10, JAC_CENTRAL_DIFF)
+    sg, _, _ = ctx.solve(b, 10, JAC_CENTRAL_DIFF)
+    assert sg["iterations"] == so["iterations"] and sg["successful_steps"] == so["successful_steps"]
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-2 * so["final_cost"]
+
+
+def test_central_diff_jacobian_is_reproduced(ctx, oracle):
+    """The Ceres-faithful mode evaluates the functor with the oracle's operation sequence and no FMA contraction: residuals
+    bit-identical, translation and plane columns of the numeric Jacobian bit-identical, rotation columns (one more projection
+    through the quaternion Plus Jacobian) to rounding."""
+    from textslam_b200._abi import TX_BA, TX_POSE
+    for prob, kind in ((synth.c4_local_ba(seed=41), TX_BA), (synth.c3_pose_only(seed=22), TX_POSE)):
+        rg, Jg = ctx.eval_text(prob, kind, JAC_CENTRAL_DIFF)
+        ro, Jo = oracle.eval_text(prob, kind, JAC_CENTRAL_DIFF)
+        assert np.array_equal(rg, ro)
+        assert np.array_equal(Jg[..., 3:6], Jo[..., 3:6])
+        if kind == TX_BA:
+            assert np.array_equal(Jg[..., 9:], Jo[..., 9:])
+        assert np.abs(Jg - Jo).max() <= 1e-13 * np.abs(Jo).max()
+
+
+def test_global_ba_text_on_central_diff(ctx, oracle):
+    # the text branch of PyrGlobalBA (src/optimizer.cc:1766-1822, w_T = 1) with Ceres' numeric differentiation
+    prob = synth.c5_global_ba(seed=42, n_kf=80, n_lm=3000, n_planes=100, text_kf_stride=4)
+    _compare(ctx, oracle, prob, 6, JAC_CENTRAL_DIFF, rtol=RTOL)
 
 
 def test_local_ba_c4(ctx, oracle):
@@ -121,9 +161,13 @@ def test_global_ba_text_on(ctx, oracle):
 
 
 def test_global_ba_c5_full_size(ctx, oracle):
+    """The BASELINE.json global-BA configuration exactly as bench.py runs it: 500 KF x 100k observations, the full
+    max_num_iterations = 20 of GlobalBA (src/optimizer.cc:411-414) — every iteration's cost, radius and accept/reject decision,
+    the termination reason and the final parameters against the oracle."""
+    import os
     prob = synth.c5_global_ba(seed=0)
-    so, sg = _compare(ctx, oracle, prob, 5)
-    assert sg["reduced_dim"] == 2988
+    so, sg = _compare(ctx, oracle, prob, 20, n_threads=min(32, os.cpu_count() or 8))
+    assert sg["reduced_dim"] == 2988 and sg["iterations"] >= 10
 
 
 def test_device_resident_lm_matches_solve(ctx, oracle):

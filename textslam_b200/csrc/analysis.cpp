@@ -370,49 +370,36 @@ static void chol_fused_schedule(int Tn, const AVec<uint8_t>& P, const AVec<AVec<
   }
   auto twave = [&](int tile) { return tile >= Tn ? nwaves : uwave[unit_of[tile]]; };   // the b row is "needed" after everything else
   // ---- tasks with sort keys ----
-  struct Tk { long long key; int rec[F_TASK_INTS]; int d0, d1, s0, s1; };
+  // Priority class of a task = 4 n + c, n = the wave whose factorisation (c = 0: the update lands in a diagonal block of a node
+  // of wave n; c = 1: that node's F task itself) or whose row solves (c = 2) consume its result; a row solve S inherits the
+  // most urgent class among the updates it feeds. The queue is sorted by (class, stage inside the chain S(a) -> U(col b from a)
+  // -> S(b) -> U -> F, source wave): every dependency of a task has a class <= its own and, if equal, an earlier stage, so
+  // the order is topological, and what the next diagonal factorisation waits for is popped before everything that only
+  // later row solves need (an F task that sits behind hundreds of such updates in the queue is popped ~10 us late).
+  struct Tk { long long key; int rec[F_TASK_INTS]; int s0, s1; };
   AVec<Tk> T;
-  AVec<I2> deps; AVec<int> srcs;
-  auto new_task = [&](int type, long long key) {
-    Tk t; t.key = key; for (int& v : t.rec) v = 0; t.rec[FK_TYPE] = type; t.rec[FK_SIG] = -1;
-    t.d0 = t.d1 = (int)deps.size(); t.s0 = t.s1 = (int)srcs.size(); T.push_back(t); return (int)T.size() - 1;
+  AVec<int> usrc;
+  auto new_task = [&](int type) {
+    Tk t; t.key = 0; for (int& v : t.rec) v = 0; t.rec[FK_TYPE] = type; t.rec[FK_SIG] = -1; t.s0 = t.s1 = 0; T.push_back(t); return (int)T.size() - 1;
   };
-  // key = ((5 * wave + slot) << 40) | secondary; slots: 0 updates needed by the wave, 1 F, 2 S of the first tile, 3 updates of the
-  // second tile's column from the first, 4 S of the second tile
-  auto KEY = [](int wv, int slot, long long sec) { return ((long long)(5 * wv + slot) << 40) | sec; };
-  // how finely the S tasks of a wave split their 64 rows: enough tasks for the machine, not more
+  auto KEY = [](int cls, int stage, long long sec) { return ((long long)cls << 44) | ((long long)stage << 40) | sec; };
+  const int BIG = 4 * (nwaves + 2);
+  AVec<int> ps((size_t)ntile, BIG);   // class of the row solve of tile (i, j)
   AVec<int> rows_in_wave(nwaves, 0);
   for (int j = 0; j < Tn; ++j) rows_in_wave[uwave[unit_of[j]]] += (int)below[j].size();
+  static const int srows_crit = [] { const char* e = getenv("TSLAM_CHOL_SROWS"); const int v = e ? atoi(e) : 16; return (v == 16 || v == 32 || v == 64) ? v : 16; }();
   AVec<int> uq_total((size_t)4 * ntile, 0);
-  struct Upd { int i, k, wv; int s0, s1; };   // target tile, source wave, sources in usrc
-  AVec<Upd> upds; AVec<int> usrc;
+  struct Upd { int i, k, wv, cls; int s0, s1; bool mid, early; };   // target tile, source wave, class, sources in usrc
+  AVec<Upd> upds;
   AVec<int> tgt_index((size_t)T1 * T1, -1);
+  auto upd_class = [&](int i, int k) { return 4 * twave(k) + ((i < Tn && unit_of[i] == unit_of[k]) ? 0 : 2); };
   for (int w = 0; w < nwaves; ++w) {
-    const int nr = 4 * rows_in_wave[w] <= 160 ? 16 : (2 * rows_in_wave[w] <= 160 ? 32 : 64);
     const size_t u_begin = upds.size();
     AVec<AVec<int>> tsrc;
     for (int u = 0; u < nunits; ++u) {
       if (uwave[u] != w) continue;
       const int a = unit_first[u], nt = unit_size[u], b = a + nt - 1;
-      {   // F
-        const int t = new_task(FT_F, KEY(w, 1, a));
-        Tk& k = T[t];
-        k.rec[FK_F_TILE] = a; k.rec[FK_F_NT] = nt; k.rec[FK_F_XBA] = nt == 2 ? XD(b, a) : -1; k.rec[FK_F_FIN] = fin0 + a;
-      }
-      for (int t2 = 0; t2 < nt; ++t2) {   // S
-        const int j = a + t2;
-        for (int i : below[j]) {
-          if (nt == 2 && j == a && i == b) continue;   // L_ba is produced inside F
-          const int step = i == Tn ? 64 : nr;
-          for (int r0 = 0; r0 < 64; r0 += step) {
-            const int t = new_task(FT_S, KEY(w, t2 == 0 ? 2 : 4, ((long long)twave(i) << 24) | ((long long)i << 8) | (r0 >> 3)));
-            Tk& k = T[t];
-            k.rec[FK_S_J] = j; k.rec[FK_S_I] = i; k.rec[FK_S_ROW0] = r0; k.rec[FK_S_NROWS] = i == Tn ? 8 : step;   // b row: only row 0 carries data
-            k.rec[FK_SIG] = XD(i, j); k.rec[FK_SIGINC] = step;
-          }
-        }
-      }
-      for (int t2 = 0; t2 < nt; ++t2) {   // updates
+      for (int t2 = nt - 1; t2 >= 0; --t2) {   // second tile first: the class of S(b, i) is what the updates of column b from tile a inherit
         const int j = a + t2;
         const AVec<int>& nz = below[j];
         for (size_t x = 0; x < nz.size(); ++x)
@@ -421,42 +408,79 @@ static void chol_fused_schedule(int Tn, const AVec<uint8_t>& P, const AVec<AVec<
             if (i == Tn && k == Tn) continue;                 // (b row, b row) is never read
             if (nt == 2 && j == a && k == b) {
               if (i == b) continue;                           // A_bb -= L_ba L_ba^T happens inside F
-              upds.push_back(Upd{i, k, -1 - w, (int)usrc.size(), (int)usrc.size() + 1}); usrc.push_back(a);   // column b from tile a: slot 3 of this wave
+              const int cls = ps[tid[(size_t)i * T1 + b]];    // consumer: S(b, i)
+              upds.push_back(Upd{i, k, w, cls, (int)usrc.size(), (int)usrc.size() + 1, true, false}); usrc.push_back(a);
+              int& pa = ps[tid[(size_t)i * T1 + a]]; pa = std::min(pa, cls);
               continue;
             }
+            const int cls = upd_class(i, k);
+            int& pi = ps[tid[(size_t)i * T1 + j]]; pi = std::min(pi, cls);
+            int& pk = ps[tid[(size_t)k * T1 + j]]; pk = std::min(pk, cls);
+            // sources that are SECOND tiles of the wave's pairs carry bit 30: the task takes the first tiles' contributions
+            // (complete while the nodes still factor their second tiles) before it waits for those
             int& ti = tgt_index[(size_t)i * T1 + k];
-            if (ti < 0) { ti = (int)tsrc.size(); tsrc.emplace_back(); upds.push_back(Upd{i, k, w, 0, 0}); }
-            tsrc[ti].push_back(j);
+            if (ti < 0) { ti = (int)tsrc.size(); tsrc.emplace_back(); upds.push_back(Upd{i, k, w, cls, 0, 0, false, false}); }
+            tsrc[ti].push_back((nt == 2 && j == b) ? (j | (1 << 30)) : j);
           }
       }
     }
-    {   // flatten the per-target source lists of this wave
+    {   // flatten the per-target source lists of this wave (ascending tile order)
       size_t x = 0;
       for (size_t q = u_begin; q < upds.size(); ++q) {
         Upd& U = upds[q];
-        if (U.wv < 0) continue;
+        if (U.mid) continue;
+        std::sort(tsrc[x].begin(), tsrc[x].end());   // bit 30 sorts the second tiles behind the first ones
         U.s0 = (int)usrc.size(); for (int j : tsrc[x]) usrc.push_back(j); U.s1 = (int)usrc.size(); ++x;
         tgt_index[(size_t)U.i * T1 + U.k] = -1;
       }
     }
+    // F and S tasks of this wave (the classes of its row solves are final now)
+    const int nr = 4 * rows_in_wave[w] <= 160 ? 16 : (2 * rows_in_wave[w] <= 160 ? 32 : 64);
+    for (int u = 0; u < nunits; ++u) {
+      if (uwave[u] != w) continue;
+      const int a = unit_first[u], nt = unit_size[u], b = a + nt - 1;
+      {
+        const int t = new_task(FT_F);
+        Tk& k = T[t];
+        k.key = KEY(4 * w + 1, 0, a);
+        k.rec[FK_F_TILE] = a; k.rec[FK_F_NT] = nt; k.rec[FK_F_XBA] = nt == 2 ? XD(b, a) : -1; k.rec[FK_F_FIN] = fin0 + a;
+      }
+      for (int t2 = 0; t2 < nt; ++t2) {
+        const int j = a + t2;
+        for (int i : below[j]) {
+          if (nt == 2 && j == a && i == b) continue;   // L_ba is produced inside F
+          const int cls = ps[tid[(size_t)i * T1 + j]];
+          // what the next diagonal factorisation waits for goes in 16-row pieces; the rest as coarse as the machine allows
+          const int step = i == Tn ? 64 : ((cls & 3) == 0 ? std::min(nr, srows_crit) : nr);
+          for (int r0 = 0; r0 < 64; r0 += step) {
+            const int t = new_task(FT_S);
+            Tk& k = T[t];
+            k.key = KEY(cls, (nt == 2 && t2 == 1) ? 2 : 0, ((long long)w << 24) | ((long long)i << 12) | ((long long)j << 3) | (r0 >> 4));
+            k.rec[FK_S_J] = j; k.rec[FK_S_I] = i; k.rec[FK_S_ROW0] = r0; k.rec[FK_S_NROWS] = i == Tn ? 8 : step;   // b row: only row 0 carries data
+            k.rec[FK_SIG] = XD(i, j); k.rec[FK_SIGINC] = step;
+          }
+        }
+      }
+    }
   }
   for (const Upd& U : upds) {
-    const bool mid = U.wv < 0;
-    const int sw = mid ? -1 - U.wv : U.wv;
-    const int nq0 = U.i == Tn ? 2 : 4;   // b row: only the upper quadrants (rows 0..31) carry data
+    // what a diagonal factorisation waits for goes in 32x32 quadrants (four CTAs per tile, short tasks); everything else — the
+    // bulk of the flops, needed only by later row solves — as whole tiles: a quarter of the task overheads and half the loads
+    const bool whole = U.i < Tn && U.i != U.k && (U.cls & 3) != 0 && !U.mid;
+    const int nq0 = whole ? 1 : (U.i == Tn ? 2 : 4);   // b row: only the upper quadrants (rows 0..31) carry data
     for (int q = 0; q < nq0; ++q) {
       if (U.i == U.k && q == 1) continue;   // upper-right quadrant of a diagonal tile is never read
-      const bool feeds_f = U.k < Tn && U.i < Tn && unit_of[U.i] == unit_of[U.k];
-      const long long sec = ((long long)(feeds_f ? 0 : 1) << 36) | ((long long)(mid ? sw : sw) << 24) | ((long long)U.i << 12) | ((long long)U.k << 2) | q;
-      const int t = new_task(FT_U, mid ? KEY(sw, 3, sec) : KEY(twave(U.k), 0, sec));
+      const int t = new_task(FT_U);
       Tk& k = T[t];
-      k.rec[FK_U_I] = U.i; k.rec[FK_U_K] = U.k; k.rec[FK_U_Q] = q; k.s0 = U.s0; k.s1 = U.s1;   // sources resolved below (usrc)
-      k.rec[FK_SIG] = UQ(U.i, U.k, q); k.rec[FK_SIGINC] = 1;
-      uq_total[(size_t)4 * tid[(size_t)U.i * T1 + U.k] + q]++;
+      k.key = KEY(U.cls, U.mid ? 1 : 3, ((long long)U.wv << 24) | ((long long)U.i << 12) | ((long long)U.k << 2) | q);
+      k.rec[FK_U_I] = U.i; k.rec[FK_U_K] = U.k; k.rec[FK_U_Q] = whole ? 4 : q; k.s0 = U.s0; k.s1 = U.s1;   // sources resolved below (usrc)
+      k.rec[FK_SIG] = UQ(U.i, U.k, whole ? 0 : q); k.rec[FK_SIGINC] = 1;
+      for (int qq = (whole ? 0 : q); qq < (whole ? 4 : q + 1); ++qq) uq_total[(size_t)4 * tid[(size_t)U.i * T1 + U.k] + qq]++;
     }
   }
   for (int j = Tn - 1; j >= 0; --j) {   // backward solve, last tile first
-    const int t = new_task(FT_B, KEY(nwaves + 1, 0, Tn - 1 - j));
+    const int t = new_task(FT_B);
+    T[t].key = KEY(BIG + 1, 0, Tn - 1 - j);
     T[t].rec[FK_B_J] = j; T[t].rec[FK_SIG] = bx0 + j; T[t].rec[FK_SIGINC] = 1;
   }
   // ---- final order, then the dependencies (the order of the updates on one quadrant is their queue order) ----
@@ -484,16 +508,19 @@ static void chol_fused_schedule(int Tn, const AVec<uint8_t>& P, const AVec<AVec<
       case FT_U: {
         const int i = k.rec[FK_U_I], kk = k.rec[FK_U_K], q = k.rec[FK_U_Q];
         k.rec[FK_U_SRC0] = (int)H.f_srcs.size();
-        for (int e = k.s0; e < k.s1; ++e) {
-          const int j = usrc[e];
-          H.f_srcs.push_back(j);
+        for (int e = k.s0; e < k.s1; ++e) {   // per source, in source order: the task waits for them chunk by chunk
+          const int j = usrc[e] & 0x3fffffff;
+          H.f_srcs.push_back(usrc[e]);
           H.f_deps.push_back(I2{XD(i, j), 64});
           if (kk != i) H.f_deps.push_back(I2{XD(kk, j), 64});
         }
         k.rec[FK_U_SRC1] = (int)H.f_srcs.size();
-        int& seen = uq_seen[(size_t)4 * tid[(size_t)i * T1 + kk] + q];
-        if (seen > 0) H.f_deps.push_back(I2{UQ(i, kk, q), seen});
-        ++seen;
+        // then the earlier updates of the same quadrant(s): only the final read-modify-write waits for them
+        for (int qq = (q == 4 ? 0 : q); qq < (q == 4 ? 4 : q + 1); ++qq) {
+          int& seen = uq_seen[(size_t)4 * tid[(size_t)i * T1 + kk] + qq];
+          if (seen > 0) H.f_deps.push_back(I2{UQ(i, kk, qq), seen});
+          ++seen;
+        }
       } break;
       case FT_B: {
         const int j = k.rec[FK_B_J];
@@ -503,7 +530,10 @@ static void chol_fused_schedule(int Tn, const AVec<uint8_t>& P, const AVec<AVec<
         k.rec[FK_B_BEL0] = (int)H.f_below.size();
         for (int i : below[j]) if (i < Tn) { H.f_below.push_back(i); H.f_deps.push_back(I2{XD(i, j), 64}); }
         k.rec[FK_B_BEL1] = (int)H.f_below.size();
-        for (int i : below[j]) if (i < Tn) H.f_deps.push_back(I2{bx0 + i, 1});
+        const bool partner = j + 1 < Tn && unit_of[j + 1] == unit_of[j];   // first tile of a pair: below[j] starts with its second tile
+        for (int i : below[j]) if (i < Tn && !(partner && i == j + 1)) H.f_deps.push_back(I2{bx0 + i, 1});
+        if (partner) H.f_deps.push_back(I2{bx0 + j + 1, 1});
+        k.rec[FK_B_PARTNER] = partner ? 1 : 0;
       } break;
     }
     k.rec[FK_DEP1] = (int)H.f_deps.size();

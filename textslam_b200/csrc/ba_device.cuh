@@ -220,6 +220,60 @@ __device__ __forceinline__ double text_pixel_analytic(const Cam& c, const Cam& h
   return res;
 }
 
+// The functor exactly as Ceres' NumericDiff evaluates it: one residual of nume_BAText::operator() (include/nume_BAText.h:28-94)
+// with the reference's own operation sequence — Eigen's normalized().toRotationMatrix(), Tcr = Tcw Trw^-1, TextProj
+// (include/ModelTool.hpp:164-171), bilinear taps — every operation an explicitly rounded IEEE double operation (no FMA
+// contraction). Central differences divide the difference of two such values by 2h ~ 3e-8: a last-bit difference between two
+// formulations of the same functor becomes a 1e-6..1e-5 relative difference of a Jacobian entry, so the Ceres-faithful mode
+// evaluates the SAME arithmetic as the CPU restatement (oracle/ba_math.hpp text_functor, built with -ffp-contract=off).
+__device__ __forceinline__ void quat_to_R_exact(const double q[4], double R[9]) {
+  const double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q[0], q[0]), __dmul_rn(q[1], q[1])), __dmul_rn(q[2], q[2])), __dmul_rn(q[3], q[3])));
+  const double w = __ddiv_rn(q[0], n), x = __ddiv_rn(q[1], n), y = __ddiv_rn(q[2], n), z = __ddiv_rn(q[3], n);
+  const double tx = __dmul_rn(2.0, x), ty = __dmul_rn(2.0, y), tz = __dmul_rn(2.0, z);
+  const double twx = __dmul_rn(tx, w), twy = __dmul_rn(ty, w), twz = __dmul_rn(tz, w);
+  const double txx = __dmul_rn(tx, x), txy = __dmul_rn(ty, x), txz = __dmul_rn(tz, x);
+  const double tyy = __dmul_rn(ty, y), tyz = __dmul_rn(tz, y), tzz = __dmul_rn(tz, z);
+  R[0] = __dsub_rn(1.0, __dadd_rn(tyy, tzz)); R[1] = __dsub_rn(txy, twz);                 R[2] = __dadd_rn(txz, twy);
+  R[3] = __dadd_rn(txy, twz);                 R[4] = __dsub_rn(1.0, __dadd_rn(txx, tzz)); R[5] = __dsub_rn(tyz, twx);
+  R[6] = __dsub_rn(txz, twy);                 R[7] = __dadd_rn(tyz, twx);                 R[8] = __dsub_rn(1.0, __dadd_rn(txx, tyy));
+}
+__device__ __forceinline__ double dot3_exact(double a0, double b0, double a1, double b1, double a2, double b2) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dmul_rn(a1, b1)), __dmul_rn(a2, b2));
+}
+static __device__ __noinline__ double text_residual_exact(const double* x /*[qc tc qh th theta] (17)*/, double rx, double ry, const TextImg& im,
+                                                   double fx, double fy, double cx, double cy, double mu, double sigma, double iref, double wT) {
+  if (sigma == 0.0) return 0.0;
+  double Rc[9], Rh[9], R[9], t[3];
+  quat_to_R_exact(x, Rc);
+  quat_to_R_exact(x + 7, Rh);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = dot3_exact(Rc[3 * i], Rh[3 * j], Rc[3 * i + 1], Rh[3 * j + 1], Rc[3 * i + 2], Rh[3 * j + 2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = __dsub_rn(x[4 + i], dot3_exact(R[3 * i], x[11], R[3 * i + 1], x[12], R[3 * i + 2], x[13]));
+  const double* th = x + 14;
+  const double rho = -dot3_exact(rx, th[0], ry, th[1], 1.0, th[2]);
+  const double px = __dadd_rn(__ddiv_rn(dot3_exact(R[0], rx, R[1], ry, R[2], 1.0), rho), t[0]);
+  const double py = __dadd_rn(__ddiv_rn(dot3_exact(R[3], rx, R[4], ry, R[5], 1.0), rho), t[1]);
+  const double pz = __dadd_rn(__ddiv_rn(dot3_exact(R[6], rx, R[7], ry, R[8], 1.0), rho), t[2]);
+  const double u = __dadd_rn(__ddiv_rn(__dmul_rn(fx, px), pz), cx);
+  const double v = __dadd_rn(__ddiv_rn(__dmul_rn(fy, py), pz), cy);
+  const double ufl = floor(u), vfl = floor(v);
+  double inten = 0.0;
+  if (ufl >= 0.0 && vfl >= 0.0 && ceil(u) < (double)im.cols && ceil(v) < (double)im.rows) {
+    const int uf = (int)ufl, vf = (int)vfl;
+    const uint8_t* p = im.img + (size_t)vf * im.cols + uf;
+    const double su = __dsub_rn(u, ufl), sv = __dsub_rn(v, vfl);
+    const int du = (uf + 1 < im.cols) ? 1 : 0, dv = (vf + 1 < im.rows) ? im.cols : 0;
+    const double I00 = (double)__ldg(p), I01 = (double)__ldg(p + du), I10 = (double)__ldg(p + dv), I11 = (double)__ldg(p + dv + du);
+    const double osu = __dsub_rn(1.0, su), osv = __dsub_rn(1.0, sv);
+    const double wtl = __dmul_rn(osu, osv), wtr = __dmul_rn(su, osv), wbl = __dmul_rn(osu, sv), wbr = __dmul_rn(su, sv);
+    inten = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(wtl, I00), __dmul_rn(wtr, I01)), __dmul_rn(wbl, I10)), __dmul_rn(wbr, I11));
+  }
+  return __dmul_rn(__dsub_rn(__ddiv_rn(__dsub_rn(inten, mu), sigma), iref), wT);
+}
+
 // residual + Ceres NumericDiff<CENTRAL> replica projected to the tangent space.
 // free_mask bit0 cam, bit1 host, bit2 theta (constant blocks get no Jacobian, like Ceres).
 __device__ __forceinline__ double text_pixel_central(const Cam& c, const Cam& h, const double theta[3], double rx, double ry,
@@ -230,7 +284,7 @@ __device__ __forceinline__ double text_pixel_central(const Cam& c, const Cam& h,
   for (int i = 0; i < 4; ++i) { x[i] = c.q[i]; x[7 + i] = h.q[i]; }
 #pragma unroll
   for (int i = 0; i < 3; ++i) { x[4 + i] = c.t[i]; x[11 + i] = h.t[i]; x[14 + i] = theta[i]; }
-  const double res = text_residual_only(x, x + 4, x + 7, x + 11, x + 14, rx, ry, im, fx, fy, cx, cy, mu, sigma, iref, wT);
+  const double res = text_residual_exact(x, rx, ry, im, fx, fy, cx, cy, mu, sigma, iref, wT);
   double Ja[17];
   const double min_step = 1.4901161193847656e-08;  // sqrt(DBL_EPSILON)
 #pragma unroll 1
@@ -240,12 +294,12 @@ __device__ __forceinline__ double text_pixel_central(const Cam& c, const Cam& h,
     if (free_mask & (1u << blk)) {
       const double xj = x[j];
       const double delta = fmax(min_step, fabs(xj) * 1e-6);
-      x[j] = xj + delta;
-      const double fp = text_residual_only(x, x + 4, x + 7, x + 11, x + 14, rx, ry, im, fx, fy, cx, cy, mu, sigma, iref, wT);
-      x[j] = xj - delta;
-      const double fm = text_residual_only(x, x + 4, x + 7, x + 11, x + 14, rx, ry, im, fx, fy, cx, cy, mu, sigma, iref, wT);
+      x[j] = __dadd_rn(xj, delta);
+      const double fp = text_residual_exact(x, rx, ry, im, fx, fy, cx, cy, mu, sigma, iref, wT);
+      x[j] = __dsub_rn(xj, delta);
+      const double fm = text_residual_exact(x, rx, ry, im, fx, fy, cx, cy, mu, sigma, iref, wT);
       x[j] = xj;
-      col = (fp - fm) * ((1.0 / delta) / 2);
+      col = __dmul_rn(__dsub_rn(fp, fm), __ddiv_rn(__ddiv_rn(1.0, delta), 2.0));
     }
     Ja[j] = col;
   }

@@ -490,7 +490,7 @@ extern "C" int tslam_debug_chol_schedule(int n, const uint8_t* tile_nz, int32_t 
 // Test / bench hook: solves S x = b for a dense symmetric positive definite S (n x n, row-major, lower triangle read) through the
 // reduced-system solver alone. tile_nz: Tn x Tn lower tile pattern or NULL (derived from the non-zeros of S).
 // mode 0 = wave kernels, 1 = fused persistent kernel. ms_out = mean device time of the solve over `reps` runs (the workspace is
-// restored before each). trace_out (fused only): 4 uint64 per task (pop, inputs ready, done [ns], SM id), up to trace_cap tasks.
+// restored before each). trace_out (fused only): 16 uint64 per task (pop, inputs ready, done [ns], SM id, then clock64 phase stamps of F tasks), up to trace_cap tasks.
 extern "C" int tslam_dev_chol_solve(tslam_ctx* ctx, int n, const uint8_t* tile_nz, const double* S, const double* b, double* x_out, int mode, int reps,
                                     float* ms_out, uint64_t* trace_out, int trace_cap, int32_t* info_out /*[4]: tasks, waves, Tn, fail*/) {
   if (!ctx || n <= 0 || !S || !b || !x_out) return set_error(TSLAM_ERR_ARG, "null argument");
@@ -519,7 +519,7 @@ extern "C" int tslam_dev_chol_solve(tslam_ctx* ctx, int n, const uint8_t* tile_n
   TSL_CUDA(A0.upload(W0.data(), W0.size(), st)); TSL_CUDA(A.reserve(W0.size())); TSL_CUDA(x.reserve(ld)); TSL_CUDA(fail.reserve(1));
   TSL_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), st));
   const bool fused = mode == 1;
-  if (fused && trace_out) { TSL_CUDA(trace.reserve(4 * (size_t)H.f_ntasks)); TSL_CUDA(cudaMemsetAsync(trace.p, 0, 32 * (size_t)H.f_ntasks, st)); }
+  if (fused && trace_out) { TSL_CUDA(trace.reserve(16 * (size_t)H.f_ntasks)); TSL_CUDA(cudaMemsetAsync(trace.p, 0, 128 * (size_t)H.f_ntasks, st)); }
   float total = 0.f;
   for (int it = 0; it < std::max(1, reps); ++it) {
     TSL_CUDA(cudaMemcpyAsync(A.p, A0.p, W0.size() * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -539,7 +539,7 @@ extern "C" int tslam_dev_chol_solve(tslam_ctx* ctx, int n, const uint8_t* tile_n
   int hfail = 0;
   TSL_CUDA(cudaMemcpyAsync(xh.data(), x.p, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (fused && trace_out) TSL_CUDA(cudaMemcpyAsync(trace_out, trace.p, 32 * (size_t)std::min(trace_cap, H.f_ntasks), cudaMemcpyDeviceToHost, st));
+  if (fused && trace_out) TSL_CUDA(cudaMemcpyAsync(trace_out, trace.p, 128 * (size_t)std::min(trace_cap, H.f_ntasks), cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaStreamSynchronize(st));
   std::copy(xh.begin(), xh.begin() + n, x_out);
   if (info_out) { info_out[0] = H.f_ntasks; info_out[1] = H.nwaves; info_out[2] = Tn; info_out[3] = hfail; }

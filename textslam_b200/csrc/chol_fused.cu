@@ -20,15 +20,16 @@
 #include "ctx.cuh"
 #include "solver.cuh"
 #include "chol_common.cuh"
+#include "chol_potrf.cuh"
 #include "chol_sched.hpp"
 
 namespace tsl {
 
 constexpr int FTH = 256;             // threads per CTA
-constexpr int LDB = 36;              // shared-memory stride of a 32x32 block (doubles): = 4 mod 16 -> conflict-free m8n8k4 fragment loads
 constexpr int BS = HB * LDB;         // doubles per block
 constexpr int LDW = NB + 4;          // stride of a 64-wide tile (= SPAD)
 constexpr unsigned SPIN_LIMIT = 1u << 24;
+constexpr int TRACE_WORDS = 16;   // uint64 per task in the optional trace
 
 struct FusedArgs {
   double* A; int ld; int Tn;
@@ -36,7 +37,7 @@ struct FusedArgs {
   const int2* deps; const int* srcs; const int* below;
   int* sync;
   double* Linv; double* x; int* fail;
-  unsigned long long* trace;   // optional: 4 stamps per task (pop, inputs ready, done, SM id)
+  unsigned long long* trace;   // optional: 4 stamps per task (pop, inputs ready, done, SM id) + 12 phase stamps (clock64) of F tasks
 };
 
 __device__ __forceinline__ int ld_acquire_s32(const int* p) {
@@ -48,95 +49,26 @@ __device__ __forceinline__ void red_release_add_s32(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+// 16-byte asynchronous copy global -> shared through L2 only (.cg: coherent with what other SMs of this launch have released);
+// no register staging, so a task can have its whole input in flight at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 __device__ __forceinline__ void bar_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-// 1/d to rounding level, branch-free: MUFU.RCP64H seed (PTX rcp.approx.ftz.f64, ~2^-20) + one cubic step y0 (1 + e + e^2)
-__device__ __forceinline__ double rcp_pivot(double d) {
-  double y0;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d));
-  const double e = fma(-d, y0, 1.0);
-  return fma(fma(e, e, e), y0, y0);
-}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // acc (8x8 tile, m8n8k4 C fragment: c0 -> (row g, col 2 tg), c1 -> (row g, col 2 tg + 1)) += sum_{k0 <= k < k1} A[g][k] B[g][k];
 // A points at the first row of an [m][k] operand, B at the first row of an [n][k] operand (both in shared memory).
 __device__ __forceinline__ void mma_tile_nt(double& c0, double& c1, const double* A, int lda, const double* B, int ldb, int k0, int k1, int g, int tg) {
 #pragma unroll 4
   for (int k = k0; k < k1; k += 4) dmma_m8n8k4(c0, c1, A[g * lda + k + tg], B[g * ldb + k + tg]);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// 32x32 diagonal block by ONE warp. G: the block in shared memory (stride LDB), SYMMETRIC (both triangles valid).
-// Lane r holds the full row r of the symmetric matrix and every step c applies the rank-1 elimination update to ALL rows but
-// the pivot row, for the columns k > c:   v_r[k] -= (v_r[c] / d_c) v_k[c].   Rows r > c carry the Schur complement (their
-// entries k <= r are the unnormalised factor columns), rows r < c carry -d_r times column r of the inverse of the unit factor —
-// the recurrence of the forward substitution M N = I is the same update — so at the end
-//   L[r][k] = v_r[k] / sqrt(d_k) (k < r),     L^-1[k][r] = -v_r[k] / (sqrt(d_k) d_r) (k > r),    L^-1[r][r] = 1 / sqrt(d_r).
-// Only the chain  d_c -> 1/d_c -> one FMA on lane c+1 -> shuffle  is loop carried; the column broadcast (shared memory, double
-// buffered) and the 31-c FMAs per lane fill its stall slots. W receives L^-1 as a full row-major block (zeros above the diagonal).
-// A non-positive pivot raises *fail and is replaced by 1 (the caller rejects the step).
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void potrf32_sym(const double* G, double* W, int* fail) {
-  __shared__ __align__(16) double colbuf[2][HB];
-  __shared__ double ssi[HB];
-  const int r = threadIdx.x & 31;
-  const unsigned full = 0xffffffffu;
-  __syncwarp();
-  double v[HB];
-#pragma unroll
-  for (int k = 0; k < HB; ++k) v[k] = G[k * LDB + r];   // column r = row r
-  // Software pipeline, one region per eliminated column between two warp barriers (ptxas schedules inside such a region only):
-  // the region of column c applies column c with 1/d_c from the region before, and computes d_{c+1}, its reciprocal and the two
-  // broadcast scalars of the next region while the 30-c update FMAs of every lane fill the stall slots of that chain.
-  //   d  = pivot d_c (lane c's diagonal),  b = lane (c+1)'s entry of column c  (both by shuffle: they sit on the chain)
-  //   colbuf[c & 1][k] = lane k's entry of column c (shared memory: feeds the FMAs, off the chain)
-  bool bad = false;
-  double d = __shfl_sync(full, v[0], 0);
-  double b = __shfl_sync(full, v[0], 1);
-  colbuf[0][r] = v[0];
-  bad |= !(d > 0.0);
-  d = d > 0.0 ? d : 1.0;
-  double dr = d;                               // lane 0 keeps d_0; the others overwrite it at their own pivot
-  double rinv = rcp_pivot(d);
-  double vc = (r == 0) ? 0.0 : v[0];           // the pivot row itself is left alone
-  double p1 = vc * b;
-  __syncwarp();
-#pragma unroll
-  for (int c = 0; c + 1 < HB; ++c) {
-    double col[HB];
-#pragma unroll
-    for (int k = (c + 2) & ~1; k < HB; k += 2) { const double2 t = *reinterpret_cast<const double2*>(&colbuf[c & 1][k]); col[k] = t.x; col[k + 1] = t.y; }
-    v[c + 1] = fma(-p1, rinv, v[c + 1]);       // the only arithmetic between 1/d_c and d_{c+1}
-    const double s = vc * rinv;
-    double dn = __shfl_sync(full, v[c + 1], c + 1);
-    const double bn = (c + 2 < HB) ? __shfl_sync(full, v[c + 1], c + 2) : 0.0;
-    colbuf[(c + 1) & 1][r] = v[c + 1];
-    bad |= !(dn > 0.0);
-    dn = dn > 0.0 ? dn : 1.0;
-    if (r == c + 1) dr = dn;
-    const double rinv_n = rcp_pivot(dn);
-#pragma unroll
-    for (int k = c + 2; k < HB; ++k) v[k] = fma(-s, col[k], v[k]);
-    vc = (r == c + 1) ? 0.0 : v[c + 1];
-    p1 = vc * bn;
-    rinv = rinv_n;
-    __syncwarp();
-  }
-  if (bad && r == 0) atomicExch(fail, 1);
-  const double si = rsqrt_pivot(dr);
-  ssi[r] = si;
-  __syncwarp();
-  const double nrr = -(si * si);   // -1 / d_r
-#pragma unroll
-  for (int k = 0; k < HB; ++k) {
-    const double w = (k < r) ? 0.0 : ((k == r) ? si : ssi[k] * (nrr * v[k]));
-    W[k * LDB + r] = w;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -147,51 +79,86 @@ __device__ __forceinline__ void potrf32_sym(const double* G, double* W, int* fai
 __host__ __device__ constexpr int f_layout_doubles(int nbk) { return (nbk * (nbk + 1) / 2 + nbk + (nbk - 1) + (nbk >= 2 ? nbk - 2 : 0)) * BS; }
 __device__ __forceinline__ double* f_blk(double* sG, int i, int j) { return sG + (i * (i + 1) / 2 + j) * BS; }
 
+// two 8x8 tiles that share the A rows: c[0..1] += A B0^T, c[2..3] += A B1^T over k0 <= k < k1 (two independent MMA chains per warp)
+__device__ __forceinline__ void mma_pair_nt(double c[4], const double* A, int lda, const double* B0, const double* B1, int ldb, int k0, int k1, int g, int tg) {
+#pragma unroll 4
+  for (int k = k0; k < k1; k += 4) {
+    const double fa = A[g * lda + k + tg];
+    dmma_m8n8k4(c[0], c[1], fa, B0[g * ldb + k + tg]);
+    dmma_m8n8k4(c[2], c[3], fa, B1[g * ldb + k + tg]);
+  }
+}
+
 // L^-1 of a 64x64 tile from its two diagonal blocks' inverses Wp, Wq and the off-diagonal factor block Lqp:
-//   [[Wp, 0], [-Wq (Lqp Wp), Wq]]   -> dst (64x64, row-major, tight). Executed by warps [w0, w0 + nw) ; tmp: one free block.
-__device__ __noinline__ void linv_tile(const double* Wp, const double* Wq, const double* Lqp, double* tmp, double* dst, int w0, int nw, int bar_id) {
-  const int warp = (threadIdx.x >> 5) - w0, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  // Mt[n][m] = (Lqp Wp)[m][n] = sum_{k >= n} Lqp[m][k] Wp[k][n]
-  for (int u = warp; u < 16; u += nw) {
-    const int ms = u >> 2, ns = u & 3;
-    double c0 = 0.0, c1 = 0.0;
-    for (int k = 8 * ns; k < HB; k += 4) dmma_m8n8k4(c0, c1, Lqp[(8 * ms + g) * LDB + k + tg], Wp[(k + tg) * LDB + 8 * ns + g]);
-    tmp[(8 * ns + 2 * tg) * LDB + 8 * ms + g] = c0;
-    tmp[(8 * ns + 2 * tg + 1) * LDB + 8 * ms + g] = c1;
+//   [[Wp, 0], [-Wq (Lqp Wp), Wq]]   -> dst (64x64, row-major, tight). Executed by nw warps (this warp is number wi of them,
+// this thread number ti of 32 nw); tmp: one free block; bar_id: a named barrier for exactly these warps.
+__device__ __noinline__ void linv_tile(const double* Wp, const double* Wq, const double* Lqp, double* tmp, double* dst, int wi, int nw, int ti, int bar_id) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  // Mt[n][m] = (Lqp Wp)[m][n] = sum_{k >= n} Lqp[m][k] Wp[k][n]; unit = two row strips of one column tile (two MMA chains)
+  for (int u = wi; u < 8; u += nw) {
+    const int ns = u & 3, ms0 = (u >> 2) * 2;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 8 * ns; k < HB; k += 4) {
+      const double fb = Wp[(k + tg) * LDB + 8 * ns + g];
+      dmma_m8n8k4(c[0], c[1], Lqp[(8 * ms0 + g) * LDB + k + tg], fb);
+      dmma_m8n8k4(c[2], c[3], Lqp[(8 * ms0 + 8 + g) * LDB + k + tg], fb);
+    }
+    tmp[(8 * ns + 2 * tg) * LDB + 8 * ms0 + g] = c[0];
+    tmp[(8 * ns + 2 * tg + 1) * LDB + 8 * ms0 + g] = c[1];
+    tmp[(8 * ns + 2 * tg) * LDB + 8 * ms0 + 8 + g] = c[2];
+    tmp[(8 * ns + 2 * tg + 1) * LDB + 8 * ms0 + 8 + g] = c[3];
   }
   // the three blocks that need no arithmetic
-  const int t = threadIdx.x - 32 * w0, nt = 32 * nw;
-  for (int e = t; e < HB * HB; e += nt) {
+  const int nt = 32 * nw;
+  for (int e = ti; e < HB * HB; e += nt) {
     const int rr = e >> 5, cc = e & 31;
     dst[rr * NB + cc] = Wp[rr * LDB + cc];
     dst[rr * NB + HB + cc] = 0.0;
     dst[(HB + rr) * NB + HB + cc] = Wq[rr * LDB + cc];
   }
   bar_named(bar_id, nt);
-  for (int u = warp; u < 16; u += nw) {
-    const int ms = u >> 2, ns = u & 3;
-    double c0 = 0.0, c1 = 0.0;
-    mma_tile_nt(c0, c1, Wq + 8 * ms * LDB, LDB, tmp + 8 * ns * LDB, LDB, 0, 8 * (ms + 1), g, tg);
-    *reinterpret_cast<double2*>(dst + (HB + 8 * ms + g) * NB + 8 * ns + 2 * tg) = make_double2(-c0, -c1);
+  for (int u = wi; u < 8; u += nw) {   // unit = two column tiles of one row strip
+    const int ms = u >> 1, ns0 = (u & 1) * 2;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    mma_pair_nt(c, Wq + 8 * ms * LDB, LDB, tmp + 8 * ns0 * LDB, tmp + 8 * (ns0 + 1) * LDB, LDB, 0, 8 * (ms + 1), g, tg);
+    *reinterpret_cast<double2*>(dst + (HB + 8 * ms + g) * NB + 8 * ns0 + 2 * tg) = make_double2(-c[0], -c[1]);
+    *reinterpret_cast<double2*>(dst + (HB + 8 * ms + g) * NB + 8 * ns0 + 8 + 2 * tg) = make_double2(-c[2], -c[3]);
   }
 }
 
-// C (32x32 block) -= Xi Xk^T, tiles u = u0, u0 + ustep, ... of the 16 (8x8) tiles
+// C (32x32 block) -= Xi Xk^T: the 8 tile pairs u = u0, u0 + ustep, ... (pair = two column tiles of one 8-row strip)
 __device__ __forceinline__ void blk_update(double* C, const double* Xi, const double* Xk, int u0, int ustep, int g, int tg) {
-  for (int u = u0; u < 16; u += ustep) {
-    const int ms = u >> 2, ns = u & 3;
-    double c0 = 0.0, c1 = 0.0;
-    mma_tile_nt(c0, c1, Xi + 8 * ms * LDB, LDB, Xk + 8 * ns * LDB, LDB, 0, HB, g, tg);
-    double2* p = reinterpret_cast<double2*>(C + (8 * ms + g) * LDB + 8 * ns + 2 * tg);
-    double2 v = *p; v.x -= c0; v.y -= c1; *p = v;
+  for (int u = u0; u < 8; u += ustep) {
+    const int ms = u >> 1, ns0 = (u & 1) * 2;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    mma_pair_nt(c, Xi + 8 * ms * LDB, LDB, Xk + 8 * ns0 * LDB, Xk + 8 * (ns0 + 1) * LDB, LDB, 0, HB, g, tg);
+    double2* p0 = reinterpret_cast<double2*>(C + (8 * ms + g) * LDB + 8 * ns0 + 2 * tg);
+    double2 v0 = p0[0], v1 = p0[4];
+    v0.x -= c[0]; v0.y -= c[1]; v1.x -= c[2]; v1.y -= c[3];
+    p0[0] = v0; p0[4] = v1;
+  }
+}
+// X (32x32 block) = G W^T (W lower triangular, zeros stored above the diagonal): the 8 tile pairs u = u0, u0 + ustep, ...
+__device__ __forceinline__ void blk_solve(double* X, const double* G, const double* W, int u0, int ustep, int g, int tg) {
+  for (int u = u0; u < 8; u += ustep) {
+    const int ms = u >> 1, ns0 = (u & 1) * 2;
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    mma_pair_nt(c, G + 8 * ms * LDB, LDB, W + 8 * ns0 * LDB, W + 8 * (ns0 + 1) * LDB, LDB, 0, 8 * (ns0 + 2), g, tg);
+    double2* p0 = reinterpret_cast<double2*>(X + (8 * ms + g) * LDB + 8 * ns0 + 2 * tg);
+    p0[0] = make_double2(c[0], c[1]); p0[4] = make_double2(c[2], c[3]);
   }
 }
 
-// One node = nt tiles (1 or 2) = nbk = 2 nt blocks. Per block column h:  [T(h-1): X_i,h-1 = G_i,h-1 W_{h-1}^T for i >= h]
-// [U1(h-1): G_hh -= X X^T]  then  warp 0: potrf32_sym(G_hh) -> W_h   |   warps 1..7: the rest of the rank-32 update of column
-// h-1 (U2) and, once tile a is complete, the publication of L_ba and L_aa^-1 (so that the row tiles of column a and the updates
-// they feed run on other SMs while this CTA factors tile b).
-__device__ void f_task(const FusedArgs& a, const int* tk, double* smem) {
+// One node = nt tiles (1 or 2) = nbk = 2 nt blocks of 32 columns. Per block column h >= 1, on the critical path only
+//   X_h,h-1 = G_h,h-1 W_{h-1}^T ;  G_hh -= X_h,h-1 X_h,h-1^T ;  warp 0: potrf32_sym(G_hh) -> W_h
+// while the six warps that do not share warp 0's scheduler (1,2,3,5,6,7; warp 4 would take FP64 issue slots from the chain)
+// solve the other blocks of column h-1, apply the rest of its rank-32 update and, once tile a is complete, publish L_ba and
+// L_aa^-1 (so that the row tiles of column a and the updates they feed run on other SMs while this CTA factors tile b).
+// The first diagonal block is loaded on its own so that the chain starts while the rest of the node is still in flight.
+constexpr int F_DW = 6;                 // deferred-work warps
+constexpr int F_DT = 32 * F_DW;
+__device__ void f_task(const FusedArgs& a, const int* tk, double* smem, unsigned long long* stamps) {
+#define F_STAMP(k) do { if (stamps && warp == 0) stamps[k] = (unsigned long long)clock64(); } while (0)   // warp-uniform: no divergence in front of the shuffles
   const int nt = tk[FK_F_NT], nbk = 2 * nt, nblk = nbk * (nbk + 1) / 2;
   double* sG = smem;
   double* sW = sG + nblk * BS;
@@ -199,76 +166,96 @@ __device__ void f_task(const FusedArgs& a, const int* tk, double* smem) {
   double* sX1 = sX0 + (nbk - 1) * BS;
   auto Xs = [&](int h, int i) { return ((h & 1) ? sX1 : sX0) + (i - h - 1) * BS; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int dw = warp < 4 ? warp - 1 : warp - 2;          // 0..5 for warps 1,2,3,5,6,7 (meaningless for warps 0 and 4)
+  const int dt = 32 * dw + lane;
   const int ta = tk[FK_F_TILE];
   const size_t ld = (size_t)a.ld;
   const double* An = a.A + (size_t)ta * NB * ld + (size_t)ta * NB;   // the node's diagonal super-tile
-  // ---- load (diagonal blocks mirrored into both triangles) ----
-#pragma unroll 4
-  for (int e = tid; e < nblk * 512; e += FTH) {
-    const int b = e >> 9, w = e & 511, rr = w >> 4, cc = (w & 15) * 2;
-    const int bi = b >= 6 ? 3 : (b >= 3 ? 2 : (b >= 1 ? 1 : 0)), bj = b - bi * (bi + 1) / 2;
-    const double2 val = ldcg2(An + (size_t)(HB * bi + rr) * ld + HB * bj + cc);
-    double* dst = sG + b * BS;
-    if (bi != bj) {
-      *reinterpret_cast<double2*>(dst + rr * LDB + cc) = val;
-    } else {
-      if (cc <= rr) { dst[rr * LDB + cc] = val.x; dst[cc * LDB + rr] = val.x; }
-      if (cc + 1 <= rr) { dst[rr * LDB + cc + 1] = val.y; dst[(cc + 1) * LDB + rr] = val.y; }
+  F_STAMP(0);
+  // ---- load: warp 0 fetches block (0,0) on its own (mirrored into both triangles: potrf32_sym reads full symmetric rows)
+  // and starts the chain without waiting for anybody; warps 1..7 bring in the rest of the node behind it ----
+  if (warp == 0) {
+    double2 val[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) { const int e = lane + 32 * it, rr = e >> 4, cc = (e & 15) * 2; val[it] = ldcg2(An + (size_t)rr * ld + cc); }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int e = lane + 32 * it, rr = e >> 4, cc = (e & 15) * 2;
+      if (cc <= rr) { sG[rr * LDB + cc] = val[it].x; sG[cc * LDB + rr] = val[it].x; }
+      if (cc + 1 <= rr) { sG[rr * LDB + cc + 1] = val[it].y; sG[(cc + 1) * LDB + rr] = val[it].y; }
+    }
+    __syncwarp();
+  } else {
+    for (int e = 512 + tid - 32; e < nblk * 512; e += FTH - 32) {
+      const int b = e >> 9, w = e & 511, rr = w >> 4, cc = (w & 15) * 2;
+      const int bi = b >= 6 ? 3 : (b >= 3 ? 2 : (b >= 1 ? 1 : 0)), bj = b - bi * (bi + 1) / 2;
+      cp_async16(sG + b * BS + rr * LDB + cc, An + (size_t)(HB * bi + rr) * ld + HB * bj + cc);
     }
   }
-  __syncthreads();
+  F_STAMP(1);
 #pragma unroll 1
   for (int h = 0; h < nbk; ++h) {
     if (h > 0) {
-      // ---- T(h-1): X_i = G_i,h-1 W_{h-1}^T for the blocks below the diagonal of column h-1 (k <= n by triangularity) ----
-      const double* Wp = sW + (h - 1) * BS;
-      const int nu = (nbk - h) * 16;
-      for (int u = warp; u < nu; u += 8) {
-        const int i = h + (u >> 4), ms = (u >> 2) & 3, ns = (u + (u >> 3)) & 3;
-        double c0 = 0.0, c1 = 0.0;
-        mma_tile_nt(c0, c1, f_blk(sG, i, h - 1) + 8 * ms * LDB, LDB, Wp + 8 * ns * LDB, LDB, 0, 8 * (ns + 1), g, tg);
-        *reinterpret_cast<double2*>(Xs(h - 1, i) + (8 * ms + g) * LDB + 8 * ns + 2 * tg) = make_double2(c0, c1);
-      }
+      blk_solve(Xs(h - 1, h), f_blk(sG, h, h - 1), sW + (h - 1) * BS, warp, 8, g, tg);
       __syncthreads();
-      // ---- U1(h-1): the next diagonal block (all 16 tiles: potrf32_sym wants both triangles) ----
-      blk_update(f_blk(sG, h, h), Xs(h - 1, h), Xs(h - 1, h), warp, 8, g, tg);
+      blk_update(f_blk(sG, h, h), Xs(h - 1, h), Xs(h - 1, h), warp, 8, g, tg);   // all 16 tiles: potrf32_sym wants both triangles
       __syncthreads();
     }
+    F_STAMP(2 + 2 * h);
     if (warp == 0) {
       potrf32_sym(f_blk(sG, h, h), sW + h * BS, a.fail);
-    } else if (h > 0) {
+      F_STAMP(3 + 2 * h);
+    } else if (h == 0) {
+      // the rest of the node arrives; the other diagonal blocks are mirrored
+      cp_async_wait_all();
+      bar_named(3, FTH - 32);
+      for (int e = tid - 32; e < (nbk - 1) * HB * HB; e += FTH - 32) {
+        const int bi = 1 + (e >> 10), rr = (e >> 5) & 31, cc = e & 31;
+        if (cc < rr) { double* dg = f_blk(sG, bi, bi); dg[cc * LDB + rr] = dg[rr * LDB + cc]; }
+      }
+    } else if (warp == 4) {
+      if (h == 2) {   // release of L_ba and L_aa^-1 (written by the deferred warps) — off everybody's critical path
+        bar_named(4, F_DT + 32);
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(a.sync + tk[FK_F_XBA], 64);
+          atomicAdd(a.sync + tk[FK_F_FIN], 1);
+        }
+      }
+    } else {
+      // the other blocks of column h-1 (pair u of block i belongs to deferred warp (8 (i - h - 1) + u) % 6)
+      for (int i = h + 1; i < nbk; ++i)
+        blk_solve(Xs(h - 1, i), f_blk(sG, i, h - 1), sW + (h - 1) * BS, (dw + F_DW - ((8 * (i - h - 1)) % F_DW)) % F_DW, F_DW, g, tg);
+      bar_named(1, F_DT);
       if (h == 2) {   // nt == 2: tile a is complete
         double* Lba = a.A + (size_t)(ta + 1) * NB * ld + (size_t)ta * NB;
-        for (int e = tid - 32; e < 4 * 512; e += FTH - 32) {
+        for (int e = dt; e < 4 * 512; e += F_DT) {
           const int b = e >> 9, w = e & 511, rr = w >> 4, cc = (w & 15) * 2;
           const int hh = b & 1, i = 2 + (b >> 1);
           *reinterpret_cast<double2*>(Lba + (size_t)(HB * (i - 2) + rr) * ld + HB * hh + cc) = *reinterpret_cast<const double2*>(Xs(hh, i) + rr * LDB + cc);
         }
-        linv_tile(sW, sW + BS, Xs(0, 1), f_blk(sG, 0, 0), a.Linv + (size_t)ta * NB * NB, 1, 7, 1);
-        bar_named(1, FTH - 32);
-        if (tid == 32) {
-          __threadfence();
-          red_release_add_s32(a.sync + tk[FK_F_XBA], 64);
-          red_release_add_s32(a.sync + tk[FK_F_FIN], 1);
-        }
+        linv_tile(sW, sW + BS, Xs(0, 1), f_blk(sG, 0, 0), a.Linv + (size_t)ta * NB * NB, dw, F_DW, dt, 1);
+        bar_arrive(4, F_DT + 32);        // the stores are issued; the idle warp 4 waits for them and raises the flags
       }
-      // U2(h-1): remaining blocks (i, k), i >= k >= h, (i, k) != (h, h); tile u of a block belongs to warp 1 + (base + u) % 7
+      // rest of the rank-32 update of column h-1: blocks (i, k), i >= k >= h, (i, k) != (h, h)
       int base = 0;
       for (int k = h; k < nbk; ++k)
         for (int i = (k == h ? h + 1 : k); i < nbk; ++i) {
-          blk_update(f_blk(sG, i, k), Xs(h - 1, i), Xs(h - 1, k), (warp - 1 + 7 - (base % 7)) % 7, 7, g, tg);
-          base += 16;
+          blk_update(f_blk(sG, i, k), Xs(h - 1, i), Xs(h - 1, k), (dw + F_DW - (base % F_DW)) % F_DW, F_DW, g, tg);
+          base += 8;
         }
     }
     __syncthreads();
   }
-  // ---- last tile of the node: its inverse (X_qp = G_qp W_p^T is not formed by the loop: column nbk-2 has its T at h = nbk-1) ----
+  // ---- last tile of the node: X_qp = G_qp W_p^T of its two blocks is in the column buffer, its inverse goes out ----
   {
     const int p = nbk - 2, q = nbk - 1;
-    linv_tile(sW + p * BS, sW + q * BS, Xs(p, q), f_blk(sG, p, p), a.Linv + (size_t)(ta + nt - 1) * NB * NB, 0, 8, 2);
+    linv_tile(sW + p * BS, sW + q * BS, Xs(p, q), f_blk(sG, p, p), a.Linv + (size_t)(ta + nt - 1) * NB * NB, warp, 8, tid, 2);
     __syncthreads();
-    if (tid == 0) { __threadfence(); red_release_add_s32(a.sync + tk[FK_F_FIN] + nt - 1, 1); }
+    if (tid == 0) { __threadfence(); atomicAdd(a.sync + tk[FK_F_FIN] + nt - 1, 1); }
   }
+  F_STAMP(10);
+#undef F_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -282,14 +269,15 @@ __device__ void s_task_run(const FusedArgs& a, const int* tk, double* smem) {
   const size_t ld = (size_t)a.ld;
   const double* Lg = a.Linv + (size_t)j * NB * NB;
   double* Ag = a.A + ((size_t)i * NB + row0) * ld + (size_t)j * NB;
-  for (int e = tid; e < NB * NB / 2; e += FTH) {
-    const int rr = e >> 5, cc = (e & 31) * 2;
-    *reinterpret_cast<double2*>(sL + rr * LDW + cc) = ldcg2(Lg + rr * NB + cc);
-  }
   for (int e = tid; e < nrows * NB / 2; e += FTH) {
     const int rr = e >> 5, cc = (e & 31) * 2;
-    *reinterpret_cast<double2*>(sB + rr * LDW + cc) = ldcg2(Ag + (size_t)rr * ld + cc);
+    cp_async16(sB + rr * LDW + cc, Ag + (size_t)rr * ld + cc);
   }
+  for (int e = tid; e < NB * NB / 2; e += FTH) {
+    const int rr = e >> 5, cc = (e & 31) * 2;
+    cp_async16(sL + rr * LDW + cc, Lg + rr * NB + cc);
+  }
+  cp_async_wait_all();
   __syncthreads();
   const int nu = (nrows >> 3) * 4;   // (8-row strip, pair of column tiles {c, 7 - c}): every unit has the same 18 k-steps
   for (int u = warp; u < nu; u += 8) {
@@ -300,63 +288,6 @@ __device__ void s_task_run(const FusedArgs& a, const int* tk, double* smem) {
       double c0 = 0.0, c1 = 0.0;
       mma_tile_nt(c0, c1, sB + 8 * ms * LDW, LDW, sL + 8 * ns * LDW, LDW, 0, 8 * (ns + 1), g, tg);
       *reinterpret_cast<double2*>(Ag + (size_t)(8 * ms + g) * ld + 8 * ns + 2 * tg) = make_double2(c0, c1);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// U task: 32x32 quadrant of A_ik -= sum_j X_ij X_kj^T
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ void u_task(const FusedArgs& a, const int* tk, double* smem) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-  const int i = tk[FK_U_I], k = tk[FK_U_K], q = tk[FK_U_Q], qi = q >> 1, qk = q & 1;
-  const int e0 = tk[FK_U_SRC0], e1 = tk[FK_U_SRC1];
-  const size_t ld = (size_t)a.ld;
-  const int ms = warp >> 1, ns0 = (warp & 1) * 2;
-  const bool active = !(i == a.Tn && ms > 0);   // b row: only row 0 (first strip) carries data
-  double* C = a.A + ((size_t)i * NB + HB * qi) * ld + (size_t)k * NB + HB * qk;
-  double2 cv[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) cv[t] = active ? ldcg2(C + (size_t)(8 * ms + g) * ld + 8 * (ns0 + t) + 2 * tg) : make_double2(0.0, 0.0);
-  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  double2 va[4], vb[4];
-  auto fetch = [&](int j) {
-    const double* Xi = a.A + ((size_t)i * NB + HB * qi) * ld + (size_t)j * NB;
-    const double* Xk = a.A + ((size_t)k * NB + HB * qk) * ld + (size_t)j * NB;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = tid + FTH * u, rr = e >> 5, cc = (e & 31) * 2;
-      va[u] = ldcg2(Xi + (size_t)rr * ld + cc);
-      vb[u] = ldcg2(Xk + (size_t)rr * ld + cc);
-    }
-  };
-  if (e0 < e1) fetch(a.srcs[e0]);
-  for (int e = e0; e < e1; ++e) {
-    double* sA = smem + (e & 1) * 2 * HB * LDW;   // double buffered: one barrier per source
-    double* sB = sA + HB * LDW;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int ee = tid + FTH * u, rr = ee >> 5, cc = (ee & 31) * 2;
-      *reinterpret_cast<double2*>(sA + rr * LDW + cc) = va[u];
-      *reinterpret_cast<double2*>(sB + rr * LDW + cc) = vb[u];
-    }
-    __syncthreads();
-    if (e + 1 < e1) fetch(a.srcs[e + 1]);
-    if (active) {
-#pragma unroll 4
-      for (int k0 = 0; k0 < NB; k0 += 4) {
-        const double fa = sA[(8 * ms + g) * LDW + k0 + tg];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) dmma_m8n8k4(acc[t][0], acc[t][1], fa, sB[(8 * (ns0 + t) + g) * LDW + k0 + tg]);
-      }
-    }
-  }
-  if (active) {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      double2 v = cv[t];
-      v.x -= acc[t][0]; v.y -= acc[t][1];
-      *reinterpret_cast<double2*>(C + (size_t)(8 * ms + g) * ld + 8 * (ns0 + t) + 2 * tg) = v;
     }
   }
 }
@@ -382,6 +313,130 @@ __device__ bool wait_deps(const FusedArgs& a, int d0, int d1, int* s_abort) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// U task: 32x32 quadrant of A_ik -= sum_j X_ij X_kj^T
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int U_CHUNK = 4;   // source tiles staged at once by a quadrant task (2 x 32 x LDW doubles each)
+constexpr int UT_CHUNK = 2;  // ... by a whole-tile task (2 x 64 x LDW doubles each)
+// The sources come in two phases (bit 30 of the source = second tile of a pair node, final only when that node's F task ends):
+// a chunk never mixes phases, and the task waits for a chunk's row solves right before it stages them, so the first tiles'
+// contributions are summed while the second tiles are still being solved. The earlier updates of the target are waited for
+// last, before the one read-modify-write of the target.
+__device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_abort) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int i = tk[FK_U_I], k = tk[FK_U_K], q = tk[FK_U_Q];
+  const int e0 = tk[FK_U_SRC0], e1 = tk[FK_U_SRC1];
+  const size_t ld = (size_t)a.ld;
+  const int nper = (i == k) ? 1 : 2;
+  int dep = tk[FK_DEP0];
+  if (q == 4) {
+    // ---- whole 64x64 tile: warp tile 32 rows x 16 columns (8 MMA chains per warp) ----
+    const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;
+    double acc[4][2][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+    for (int c0 = e0; c0 < e1;) {
+      int nc = 1;
+      while (nc < UT_CHUNK && c0 + nc < e1 && ((a.srcs[c0 + nc] ^ a.srcs[c0]) & (1 << 30)) == 0) ++nc;
+      if (!wait_deps(a, dep, dep + nc * nper, s_abort)) return false;   // (also: the previous chunk has been consumed)
+      dep += nc * nper;
+      for (int sc = 0; sc < nc; ++sc) {
+        const int j = a.srcs[c0 + sc] & 0x3fffffff;
+        double* sA = smem + sc * 2 * NB * LDW;
+        double* sB = sA + NB * LDW;
+        const double* Xi = a.A + (size_t)i * NB * ld + (size_t)j * NB;
+        const double* Xk = a.A + (size_t)k * NB * ld + (size_t)j * NB;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = tid + FTH * u, rr = e >> 5, cc = (e & 31) * 2;
+          cp_async16(sA + rr * LDW + cc, Xi + (size_t)rr * ld + cc);
+          cp_async16(sB + rr * LDW + cc, Xk + (size_t)rr * ld + cc);
+        }
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      for (int sc = 0; sc < nc; ++sc) {
+        const double* sA = smem + sc * 2 * NB * LDW;
+        const double* sB = sA + NB * LDW;
+#pragma unroll 2
+        for (int k0 = 0; k0 < NB; k0 += 4) {
+          double fa[4], fb[2];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) fa[x] = sA[(wr + 8 * x + g) * LDW + k0 + tg];
+#pragma unroll
+          for (int y = 0; y < 2; ++y) fb[y] = sB[(wc + 8 * y + g) * LDW + k0 + tg];
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 2; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], fa[x], fb[y]);
+        }
+      }
+      c0 += nc;
+    }
+    if (!wait_deps(a, dep, tk[FK_DEP1], s_abort)) return false;
+    double* C = a.A + (size_t)i * NB * ld + (size_t)k * NB;
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 2; ++y) {
+        double2* p = reinterpret_cast<double2*>(C + (size_t)(wr + 8 * x + g) * ld + wc + 8 * y + 2 * tg);
+        double2 v = __ldcg(p);
+        v.x -= acc[x][y][0]; v.y -= acc[x][y][1];
+        *p = v;
+      }
+    return true;
+  }
+  // ---- one 32x32 quadrant ----
+  const int qi = q >> 1, qk = q & 1;
+  const int ms = warp >> 1, ns0 = (warp & 1) * 2;
+  const bool active = !(i == a.Tn && ms > 0);   // b row: only row 0 (first strip) carries data
+  const bool same = (i == k && qi == qk);       // diagonal quadrant of a diagonal tile: both operands are the same rows
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int c0 = e0; c0 < e1;) {
+    int nc = 1;
+    while (nc < U_CHUNK && c0 + nc < e1 && ((a.srcs[c0 + nc] ^ a.srcs[c0]) & (1 << 30)) == 0) ++nc;
+    if (!wait_deps(a, dep, dep + nc * nper, s_abort)) return false;   // (also: the previous chunk has been consumed)
+    dep += nc * nper;
+    for (int sc = 0; sc < nc; ++sc) {
+      const int j = a.srcs[c0 + sc] & 0x3fffffff;
+      double* sA = smem + sc * 2 * HB * LDW;
+      double* sB = sA + HB * LDW;
+      const double* Xi = a.A + ((size_t)i * NB + HB * qi) * ld + (size_t)j * NB;
+      const double* Xk = a.A + ((size_t)k * NB + HB * qk) * ld + (size_t)j * NB;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = tid + FTH * u, rr = e >> 5, cc = (e & 31) * 2;
+        cp_async16(sA + rr * LDW + cc, Xi + (size_t)rr * ld + cc);
+        if (!same) cp_async16(sB + rr * LDW + cc, Xk + (size_t)rr * ld + cc);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (active) {
+      for (int sc = 0; sc < nc; ++sc) {
+        const double* sA = smem + sc * 2 * HB * LDW;
+        const double* sB = same ? sA : sA + HB * LDW;
+        mma_pair_nt(acc, sA + 8 * ms * LDW, LDW, sB + 8 * ns0 * LDW, sB + 8 * (ns0 + 1) * LDW, LDW, 0, NB, g, tg);
+      }
+    }
+    c0 += nc;
+  }
+  if (!wait_deps(a, dep, tk[FK_DEP1], s_abort)) return false;
+  if (active) {
+    double* C = a.A + ((size_t)i * NB + HB * qi) * ld + (size_t)k * NB + HB * qk;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      double2* p = reinterpret_cast<double2*>(C + (size_t)(8 * ms + g) * ld + 8 * (ns0 + t) + 2 * tg);
+      double2 v = __ldcg(p);
+      v.x -= acc[2 * t]; v.y -= acc[2 * t + 1];
+      *p = v;
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // B task: x_j = L_jj^-T (y_j - sum_{i in below(j)} L_ij^T x_i)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int B_PRE = 4;   // L tiles staged in shared memory while the task waits for the x_i (the rest is read from L2 afterwards)
@@ -399,20 +454,24 @@ __device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
   if (!wait_deps(a, tk[FK_DEP0], dmid, s_abort)) return false;
   {
     const double* M = a.Linv + (size_t)j * NB * NB;
-    for (int e = tid; e < NB * NB / 2; e += FTH) *reinterpret_cast<double2*>(sM + 2 * e) = ldcg2(M + 2 * e);
+    for (int e = tid; e < NB * NB / 2; e += FTH) cp_async16(sM + 2 * e, M + 2 * e);
     const int npre = min(e1 - e0, B_PRE);
     for (int t = 0; t < npre; ++t) {
       const double* L = a.A + (size_t)a.below[e0 + t] * NB * ld + (size_t)j * NB;
       for (int e = tid; e < NB * NB / 2; e += FTH) {
         const int rr = e >> 5, cc = (e & 31) * 2;
-        *reinterpret_cast<double2*>(sT + t * NB * NB + rr * NB + cc) = ldcg2(L + (size_t)rr * ld + cc);
+        cp_async16(sT + t * NB * NB + rr * NB + cc, L + (size_t)rr * ld + cc);
       }
     }
+    cp_async_wait_all();
   }
   const double yj = (g == 0) ? __ldcg(a.A + (size_t)a.Tn * NB * ld + (size_t)j * NB + c) : 0.0;   // y_j = row 0 of the solved b tile
-  if (!wait_deps(a, dmid, tk[FK_DEP1], s_abort)) return false;
+  // x of the other nodes first; the partner tile of a pair (below[e0], the tile this node's F task factored last) comes on its
+  // own after them, so that everything but its 64x64 term is already summed when it arrives
+  const int npart = tk[FK_B_PARTNER];
+  if (!wait_deps(a, dmid, tk[FK_DEP1] - npart, s_abort)) return false;
   double t0 = 0.0, t1 = 0.0;
-  for (int e = e0 + g; e < e1; e += 4) {
+  for (int e = e0 + npart + g; e < e1; e += 4) {
     const int i = a.below[e];
     sx[g][c] = __ldcg(a.x + (size_t)i * NB + c);
     bar_named(1 + g, 64);
@@ -426,6 +485,15 @@ __device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
       for (int r = 0; r < NB; r += 2) { t0 -= __ldcg(L + (size_t)r * ld) * sx[g][r]; t1 -= __ldcg(L + (size_t)(r + 1) * ld) * sx[g][r + 1]; }
     }
     bar_named(1 + g, 64);
+  }
+  if (npart) {
+    if (!wait_deps(a, tk[FK_DEP1] - 1, tk[FK_DEP1], s_abort)) return false;
+    // 64 x 64 term of the partner, rows split over the four groups (its tile is the first staged one)
+    sx[g][c] = __ldcg(a.x + (size_t)a.below[e0] * NB + c);
+    bar_named(1 + g, 64);
+    const double* L = sT + c;
+#pragma unroll
+    for (int r = 16 * g; r < 16 * g + 16; r += 2) { t0 -= L[r * NB] * sx[g][r]; t1 -= L[(r + 1) * NB] * sx[g][r + 1]; }
   }
   st[g][c] = t0 + t1;
   __syncthreads();
@@ -468,20 +536,26 @@ __global__ void __launch_bounds__(FTH, 1) chol_fused_kernel(FusedArgs a) {
     if (a.trace && tid == 0) t_pop = gtime();
     if (type == FT_B) {
       if (!b_task(a, s_task, smem, &s_abort)) break;
+    } else if (type == FT_U) {
+      if (!u_task(a, s_task, smem, &s_abort)) break;
     } else {
       if (!wait_deps(a, s_task[FK_DEP0], s_task[FK_DEP1], &s_abort)) break;
       if (a.trace && tid == 0) t_ready = gtime();
       if (type == FT_S) s_task_run(a, s_task, smem);
-      else if (type == FT_U) u_task(a, s_task, smem);
-      else f_task(a, s_task, smem);
+      else f_task(a, s_task, smem, a.trace ? a.trace + TRACE_WORDS * (size_t)t + 4 : nullptr);
     }
     __syncthreads();   // all global stores of the task are issued
     if (tid == 0) {
-      if (s_task[FK_SIG] >= 0) { __threadfence(); red_release_add_s32(a.sync + s_task[FK_SIG], s_task[FK_SIGINC]); }
+      if (s_task[FK_SIG] >= 0) {
+        __threadfence();
+        const int nsig = (type == FT_U && s_task[FK_U_Q] == 4) ? 4 : 1;   // a whole-tile update bumps the counters of its four quadrants
+        for (int x = 0; x < nsig; ++x) red_release_add_s32(a.sync + s_task[FK_SIG] + x, s_task[FK_SIGINC]);
+      }
       if (a.trace) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        a.trace[4 * (size_t)t] = t_pop; a.trace[4 * (size_t)t + 1] = t_ready; a.trace[4 * (size_t)t + 2] = gtime(); a.trace[4 * (size_t)t + 3] = smid;
+        unsigned long long* tr = a.trace + TRACE_WORDS * (size_t)t;
+        tr[0] = t_pop; tr[1] = t_ready; tr[2] = gtime(); tr[3] = smid;
       }
     }
   }
@@ -489,7 +563,7 @@ __global__ void __launch_bounds__(FTH, 1) chol_fused_kernel(FusedArgs a) {
 
 constexpr int FUSED_SMEM_DOUBLES = f_layout_doubles(4) > (1 + B_PRE) * NB * NB ? f_layout_doubles(4) : (1 + B_PRE) * NB * NB;
 static_assert(FUSED_SMEM_DOUBLES * 8 <= 227 * 1024, "fused Cholesky exceeds the shared memory of one SM");
-static_assert(2 * 2 * HB * LDW <= FUSED_SMEM_DOUBLES && 2 * NB * LDW <= FUSED_SMEM_DOUBLES, "S / U staging must fit");
+static_assert(U_CHUNK * 2 * HB * LDW <= FUSED_SMEM_DOUBLES && UT_CHUNK * 2 * NB * LDW <= FUSED_SMEM_DOUBLES && 2 * NB * LDW <= FUSED_SMEM_DOUBLES, "S / U staging must fit");
 
 __global__ void __launch_bounds__(256) zero_sync_kernel(int* __restrict__ sync, int n) {
   PDL_PROLOGUE();

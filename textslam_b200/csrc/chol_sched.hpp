@@ -21,10 +21,12 @@ constexpr int FK_TYPE = 0, FK_DEP0 = 1, FK_DEP1 = 2, FK_SIG = 3, FK_SIGINC = 4;
 constexpr int FK_F_TILE = 5, FK_F_NT = 6, FK_F_XBA = 7, FK_F_FIN = 8;
 // S: column tile j, row tile i, first row, rows
 constexpr int FK_S_J = 5, FK_S_I = 6, FK_S_ROW0 = 7, FK_S_NROWS = 8;
-// U: target tile (i, k), quadrant (2 qi + qk), source range in f_srcs
+// U: target tile (i, k), quadrant (2 qi + qk; 4 = the whole tile, signals all four quadrant counters), source range in f_srcs
+// (bit 30 of a source = second tile of a pair: waited for after the sources without it). Dependencies: one or two per source
+// (X_ij, and X_kj when k != i) in source order, then the earlier updates of the target
 constexpr int FK_U_I = 5, FK_U_K = 6, FK_U_Q = 7, FK_U_SRC0 = 8, FK_U_SRC1 = 9;
-// B: tile j, range of its row tiles in f_below
-constexpr int FK_B_J = 5, FK_B_BEL0 = 6, FK_B_BEL1 = 7;
+// B: tile j, range of its row tiles in f_below, 1 if the first of them is the partner tile of a pair (its x is waited for last)
+constexpr int FK_B_J = 5, FK_B_BEL0 = 6, FK_B_BEL1 = 7, FK_B_PARTNER = 8;
 
 // sync array layout: [0] queue head, [1] abort flag, [FS_FIN0 + j] L_jj^-1 published, [bx0 + j] x_j final,
 // [xd0 + tile id] rows of X_ij finished (64 = complete), [uq0 + 4 tile id + q] update tasks finished on that quadrant

@@ -33,5 +33,10 @@ for ty in range(4):
 print("  F tasks (tile, pop, ready, done us):")
 for t in np.nonzero(tasks[:, 0] == 0)[0]:
     print(f"    tile {tasks[t, 5]:3d}: {pop[t] / 1e3:7.2f} {ready[t] / 1e3:7.2f} {done[t] / 1e3:7.2f}")
+fs = tr[tasks[:, 0] == 0][:, 4:15]
+d = np.diff(fs, axis=1)
+print("  F phases, cycles (mean over tasks): load", int(d[:, 0].mean()), "| per block column h: [T+U1 before potrf, potrf32_sym] =",
+      [(int(d[:, 1 + 2 * h].mean()), int(d[:, 2 + 2 * h].mean())) for h in range(4)], "| tail", int((fs[:, 10] - fs[:, 9]).mean()))
+np.savez_compressed(os.path.join(ROOT, "gpurun_out", "chol_trace.npz"), trace=tr, tasks=tasks)
 bt = np.nonzero(tasks[:, 0] == 3)[0]
 print(f"  backward solve: first B ready at {pop[bt].min() / 1e3:.2f}, last done {done[bt].max() / 1e3:.2f}")
