@@ -7,7 +7,7 @@ solves with the problem resident in HBM; `ms_per_step` = one solve; `lm_iter_ms`
 it. `e2e` = the same metric through the public C-ABI call `tslam_solve` with HOST buffers (upload,
 structure analysis, LM loop, download inside the timed region). `--impl reference` times the CPU
 oracle (Ceres-faithful restatement; the reference's Ceres/OpenCV path cannot be built here, see
-DESIGN.md) on the box's host cores on a bounded sample of the same workload.
+DESIGN.md) on the box's host cores: the same whole solve per step, all host threads (num_threads = 1 beside it).
 
 Launch: python bench.py [--gpus N --steps K --warmup W] or, for N > 1, under torchrun (one rank per GPU).
 """
@@ -26,10 +26,46 @@ sys.path.insert(0, ROOT)
 
 GLOBAL_BA_ITERS = 20  # src/optimizer.cc:411-414
 POINT_EVAL_BYTES = 268  # 44 B in + 224 B out per auto_BAScene(NW) evaluation
-# dram__bytes_read.sum + dram__bytes_write.sum of one x16 launch from the committed ncu --set full capture
-# (profiles/r1_ncu_point_eval_x16_end.txt: 76.1 MB + 299.3 MB; part of the 358 MB output is still in L2 at kernel end)
-NCU_TRAFFIC_X16 = 375.4e6
+TEXT_EVAL_BYTES = 1280  # 256 B in + 64 B r + 960 B J per nume_BAText block
+ORB_IMAGE_BYTES = 307200 + 1158012 + 1000 * (28 + 32)   # image in + pyramid + keypoints/descriptors out
+FP64_TENSOR_PEAK = 37.0e12   # measured DMMA rate of this part (tools/ubench/fp64_rates.cu, profiles/r1_notes.md); MEASURED_PEAKS.json has no FP64 entry
 WORKLOAD = "C5 global BA: 500 KF x 100k auto_BASceneNW obs (25k landmarks x 4 obs, band +-10, text off as src/optimizer.cc:1707), <=20 LM its"
+# ncu --set full captures of this round, exported with `ncu -i ... --page raw --csv` (tools/gpu_prof2.sh); dram traffic is read from them
+NCU_RAW = {"point_eval_x16": "profiles/r2_ncu_point_eval_x16_raw.csv", "text_eval": "profiles/r2_ncu_text_eval_raw.csv"}
+
+
+def bench_config(world):
+    """The `config` object of both arms (ours and --impl reference): identical by construction."""
+    return {"workload": WORKLOAD,
+            "l2": "the solve is not L2-flushed between iterations (its working set, 21 MB of J + 8 MB of factor tiles + index lists, is what a real solve keeps in L2); the stand-alone kernel timings of `roofline` flush L2 or exceed it",
+            "landmark_sharding": f"landmark % {world}" if world > 1 else "none"}
+
+
+def ncu_dram_bytes(key, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch of a kernel in a committed ncu raw-page CSV; None if absent."""
+    import csv
+    path = os.path.join(ROOT, NCU_RAW[key])
+    try:
+        with open(path, newline="") as f:
+            rows = list(csv.reader(f))
+    except OSError:
+        return None
+    hdr = next((r for r in rows if "Kernel Name" in r), None)
+    if hdr is None:
+        return None
+    units = rows[rows.index(hdr) + 1]
+    try:
+        kn, cr, cw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[rows.index(hdr) + 2:]:
+        if len(r) > max(kn, cr, cw) and kernel_substr in r[kn]:
+            try:
+                return float(r[cr].replace(",", "")) * scale.get(units[cr], 1.0) + float(r[cw].replace(",", "")) * scale.get(units[cw], 1.0)
+            except ValueError:
+                return None
+    return None
 
 
 def read_peaks():
@@ -204,8 +240,18 @@ def jac_evals(summ, prob):
     return (summ["successful_steps"] + 1) * (prob.n_pobs + prob.n_tobs)
 
 
+def oracle_full_solve(po, prob, threads):
+    q = prob.copy()
+    t0 = time.perf_counter()
+    summ, _, _ = po.solve(q, GLOBAL_BA_ITERS, n_threads=threads, want_trace=False)
+    return time.perf_counter() - t0, summ
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle restatement on host cores (the reference's own Ceres path is unbuildable here)."""
+    """CPU arm: the reference's own CPU implementation of the path is Ceres, which cannot be built here, so this
+    times the oracle restatement (Ceres-faithful LM loop, oracle/ba_lm.cpp) on the box's host cores. One step = the SAME whole
+    GlobalBA solve (<= 20 LM iterations) on the same problem as our arm, with all host threads; the reference's own setting,
+    num_threads = 1 (src/optimizer.cc:1838), is timed once beside it."""
     if rank != 0:
         return
     from textslam_b200 import synth
@@ -214,24 +260,23 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     threads = min(cores, 32)
     prob = synth.c5_global_ba(seed=0)
-    sample_iters = 2
     times, evals, its = [], [], []
     for s in range(args.warmup + args.steps):
-        q = prob.copy()
-        t0 = time.perf_counter()
-        summ, _, _ = po.solve(q, sample_iters, n_threads=threads, want_trace=False)
-        dt = time.perf_counter() - t0
+        dt, summ = oracle_full_solve(po, prob, threads)
         if s >= args.warmup:
             times.append(dt); evals.append(jac_evals(summ, prob)); its.append(summ["iterations"])
     total = sum(times)
     value = sum(evals) / total / 1e6
-    sample = f"first {sample_iters} LM iterations of the C5 solve per step (full solve = up to {GLOBAL_BA_ITERS})"
+    dt1, summ1 = oracle_full_solve(po, prob, 1)
+    sample = f"whole C5 solve per step ({its[0]} LM iterations, the same solve our arm runs), {threads} host threads"
     line = {"impl": "reference", "metric": "ba_resjac_mevals_per_s", "value": value, "unit": "M-evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "lm_iter_ms": 1e3 * total / max(1, sum(its)),
-            "cpu_baseline": {"value": value, "unit": "M-evals/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": bench_config(args.gpus),
+            "lm_iter_ms": 1e3 * total / max(1, sum(its)), "lm_iterations_per_step": sum(its) / len(its),
+            "cpu_baseline": {"value": value, "unit": "M-evals/s", "cores": threads, "kind": "port", "sample": sample,
+                             "single_thread": {"note": "num_threads = 1 as src/optimizer.cc:1838 sets it, one whole solve", "value": jac_evals(summ1, prob) / dt1 / 1e6,
+                                               "ms_per_solve": 1e3 * dt1, "lm_iter_ms": 1e3 * dt1 / max(1, summ1["iterations"])}},
             "e2e": {"value": value, "unit": "M-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -304,8 +349,7 @@ def main():
     line = {"metric": "ba_resjac_mevals_per_s", "value": value, "unit": "M-evals/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "the solve is not L2-flushed between iterations (its working set, 21 MB of J + 8 MB of factor tiles + index lists, is what a real solve keeps in L2); the stand-alone kernel timings of `roofline` flush L2 or exceed it",
-                       "landmark_sharding": f"landmark % {world}" if world > 1 else "none"},
+            "config": bench_config(world),
             "lm_iter_ms": dev_ms / max(1, its), "lm_iterations_per_step": its / K, "wall_ms_per_step": wall_ms / K,
             "gpu_launches": int(launches), "clocks": clk}
     phase_names = ["eval_resjac", "landmark_prep", "reduced_build", "allreduce", "cholesky", "backsub", "model_candidate"]
@@ -322,7 +366,8 @@ def main():
         achb = POINT_EVAL_BYTES * big.n_pobs / (msb * 1e-3) / 1e9
         line["roofline"] = {"kernel": "point_eval_kernel<0,13,J> (auto_BASceneNW residual+Jacobian), C5 x16 replica = 1.6M evals / launch (429 MB > L2)",
                             "bound": "hbm", "achieved": achb, "peak": hbm_peak, "unit": "GB/s", "frac": achb / hbm_peak,
-                            "traffic": NCU_TRAFFIC_X16, "peak_source": peak_src, "ms_per_launch": msb,
+                            "traffic": ncu_dram_bytes("point_eval_x16", "point_eval_kernel"), "traffic_source": NCU_RAW["point_eval_x16"],
+                            "peak_source": peak_src, "ms_per_launch": msb,
                             "mevals_per_s": big.n_pobs / (msb * 1e-3) / 1e6,
                             "algorithmic_bytes_per_launch": POINT_EVAL_BYTES * big.n_pobs}
         dbig.free()
@@ -333,23 +378,32 @@ def main():
                                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "ms_per_launch": ms,
                                "mevals_per_s": prob.n_pobs / (ms * 1e-3) / 1e6,
                                "note": "one partial wave (782 CTAs on 148 SMs): launch/latency bound, see DESIGN.md"}
-        line["dominant_kernel"] = {"name": "potrf_trsm_kernel (64x64 tile factor + triangular solve of the reduced camera system)",
-                                   "share_of_lm_iteration": f"largest single kernel of the step (profiles/r1_launches_lm_end.txt); {T.analyze_structure(prob)['n_waves']} dependent waves per factorisation",
-                                   "bound": "latency: 64 dependent pivots per tile (rsqrt -> scale -> update -> broadcast, ~185 cycles each, tools/ubench/chol_tile_bench.cu); FP64 tensor work of the step is syrk_wave_kernel"}
-        # ---- CPU baseline beside it: oracle port, bounded sample
+        info = T.analyze_structure(prob)
+        chol_ms = line["lm_phase_ms_per_iter"]["cholesky"]
+        chol_flops = 2.0 * 64 ** 3 * info["n_tile_updates"]   # the factor's GEMM work (64^3 tile multiply-adds of the symbolic factorisation)
+        line["dominant_kernel"] = {"name": "chol_fused_kernel (persistent, flag-ordered: tile Cholesky of the reduced camera system + forward and backward solve in one launch)",
+                                   "share_of_lm_iteration": chol_ms / line["lm_iter_ms"],
+                                   "ms_per_launch": chol_ms, "tile_updates": int(info["n_tile_updates"]), "flops": chol_flops,
+                                   "achieved_tflops": chol_flops / (chol_ms * 1e-3) / 1e12, "peak_tflops": FP64_TENSOR_PEAK / 1e12,
+                                   "frac": chol_flops / (chol_ms * 1e-3) / FP64_TENSOR_PEAK,
+                                   "bound": "latency: 5 elimination-tree levels x 128 dependent pivots (reciprocal -> fma -> shuffle, ~190 cycles each in "
+                                            "potrf32_sym, tools/ubench/potrf_sym_bench.cu) + 3 flag hand-offs per level; the FP64 tensor work (mma.sync.m8n8k4.f64) is "
+                                            "a few percent of the pipe's capacity by construction"}
+        # ---- CPU baseline beside it: the oracle port on the same whole solve (all host threads; the reference's num_threads = 1 beside it)
         from oracle import pyoracle as po
         po.build()
         threads = min(os.cpu_count() or 1, 32)
-        q = prob.copy()
-        t0 = time.perf_counter()
-        summ, _, _ = po.solve(q, 2, n_threads=threads, want_trace=False)
-        dt = time.perf_counter() - t0
+        dt, summ = oracle_full_solve(po, prob, threads)
+        dt1, summ1 = oracle_full_solve(po, prob, 1)
         line["cpu_baseline"] = {"value": jac_evals(summ, prob) / dt / 1e6, "unit": "M-evals/s", "cores": threads, "kind": "port",
-                                "sample": "first 2 LM iterations of the same C5 solve (oracle/ba_lm.cpp)",
-                                "lm_iter_ms": 1e3 * dt / max(1, summ["iterations"])}
+                                "sample": f"one whole C5 solve ({summ['iterations']} LM iterations, oracle/ba_lm.cpp), {threads} host threads",
+                                "ms_per_solve": 1e3 * dt, "lm_iter_ms": 1e3 * dt / max(1, summ["iterations"]),
+                                "single_thread": {"note": "num_threads = 1 as src/optimizer.cc:1838 sets it, one whole solve", "value": jac_evals(summ1, prob) / dt1 / 1e6,
+                                                  "ms_per_solve": 1e3 * dt1, "lm_iter_ms": 1e3 * dt1 / max(1, summ1["iterations"])}}
+        line["text_on"] = text_on_bench(ctx, T, synth, po, threads, hbm_peak, peak_src)
         line["small_problems"] = small_problem_bench(ctx, T, synth, po, threads)
         try:
-            line["orb"] = orb_bench(ctx, T, synth)
+            line["orb"] = orb_bench(ctx, T, synth, po, hbm_peak)
         except Exception as e:  # ORB is reported beside the BA metric; its absence must not hide the BA line
             line["orb"] = {"error": str(e)[:200]}
     dev.free()
@@ -400,7 +454,37 @@ def small_problem_bench(ctx, T, synth, po, threads):
     return out
 
 
-def orb_bench(ctx, T, synth):
+def text_on_bench(ctx, T, synth, po, threads, hbm_peak, peak_src):
+    """C5 with the text branch of PyrGlobalBA switched on (src/optimizer.cc:1766-1822, w_T = 1; BASELINE.md reports C5 twice):
+    1000 planes x 25 features = 25 000 nume_BAText blocks beside the 100k point blocks; the text kernel's own roofline beside it."""
+    prob = synth.c5_global_ba(seed=0, n_planes=1000)
+    dev = ctx.upload(prob)
+    for _ in range(2):
+        dev.lm_iterations(GLOBAL_BA_ITERS)
+    ms_tot, evals, its = 0.0, 0, 0
+    for _ in range(5):
+        phases, summ = dev.lm_iterations(GLOBAL_BA_ITERS)
+        ms_tot += phases[7] * max(1, summ["iterations"]); evals += jac_evals(summ, prob); its += summ["iterations"]
+    out = {"workload": "C5 + text: 500 KF x (100k auto_BASceneNW + 25k nume_BAText blocks, 1000 planes), analytic text Jacobian",
+           "value": evals / (ms_tot * 1e-3) / 1e6, "unit": "M-evals/s", "ms_per_step": ms_tot / 5, "lm_iter_ms": ms_tot / max(1, its), "lm_iterations_per_step": its / 5}
+    dev.eval_text(T.TX_BA, T.JAC_ANALYTIC, reps=3, flush_l2=True)
+    ms = dev.eval_text(T.TX_BA, T.JAC_ANALYTIC, reps=20, flush_l2=True)
+    ach = TEXT_EVAL_BYTES * prob.n_tobs / (ms * 1e-3) / 1e9
+    out["roofline_text_eval"] = {"kernel": "text_eval_kernel<0,15,analytic> (nume_BAText residual + 8x15 Jacobian), 25k blocks = 32 MB / launch, L2 flushed",
+                                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "ms_per_launch": ms,
+                                 "traffic": ncu_dram_bytes("text_eval", "text_eval_kernel"), "traffic_source": NCU_RAW["text_eval"], "peak_source": peak_src,
+                                 "algorithmic_bytes_per_launch": TEXT_EVAL_BYTES * prob.n_tobs,
+                                 "note": "one partial wave at this size (latency bound like the point kernel at the C5 size)"}
+    ms_cd = dev.eval_text(T.TX_BA, T.JAC_CENTRAL_DIFF, reps=5, flush_l2=True)
+    out["central_diff_ms_per_launch"] = ms_cd   # Ceres-faithful mode: 35 exact functor evaluations per block
+    dev.free()
+    dt, summ = oracle_full_solve(po, prob, threads)
+    out["cpu_baseline"] = {"value": jac_evals(summ, prob) / dt / 1e6, "unit": "M-evals/s", "cores": threads, "kind": "port",
+                           "sample": f"one whole solve ({summ['iterations']} LM iterations), analytic text Jacobian", "ms_per_solve": 1e3 * dt}
+    return out
+
+
+def orb_bench(ctx, T, synth, po, hbm_peak):
     imgs = synth.orb_images(seed=0, n=64)
     orb = T.ORBextractor(ctx, 1000, 1.2, 8, 20, 7)
     ms, nkp = orb.dev_bench(imgs, reps=5)
@@ -408,8 +492,38 @@ def orb_bench(ctx, T, synth):
     res = orb.extract_batch(imgs)
     dt = time.perf_counter() - t0
     n = sum(len(k) for k, _ in res)
-    return {"workload": "C2: 64 x 640x480, 8 levels x1.2, 1000 feat, FAST 20/7", "kpts_per_s": nkp / (ms * 1e-3), "ms_per_batch": ms,
-            "images_per_s": 64 / (ms * 1e-3), "e2e_kpts_per_s": n / dt, "keypoints": int(nkp)}
+    out = {"workload": "C2: 64 x 640x480, 8 levels x1.2, 1000 feat, FAST 20/7", "kpts_per_s": nkp / (ms * 1e-3), "ms_per_batch": ms,
+           "images_per_s": 64 / (ms * 1e-3), "e2e_kpts_per_s": n / dt, "keypoints": int(nkp)}
+    ach = ORB_IMAGE_BYTES * 64 / (ms * 1e-3) / 1e9
+    out["roofline"] = {"bound": "hbm (nominal; what binds is the integer ALU work of the FAST measure and the per-level launch latency of the small pyramid levels)",
+                       "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_bytes_per_image": ORB_IMAGE_BYTES}
+    # CPU baselines: the C++ restatement of ORBextractor.cc (1 core, then one image per host thread), and OpenCV's own cv::ORB for scale
+    t0 = time.perf_counter(); k1 = 0
+    for i in range(8):
+        kp, _ = po.orb_extract(imgs[i], 1000, 1.2, 8, 20, 7); k1 += len(kp)
+    dt1 = time.perf_counter() - t0
+    from concurrent.futures import ThreadPoolExecutor
+    threads = min(os.cpu_count() or 1, 32)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        ka = sum(len(kp) for kp, _ in ex.map(lambda im: po.orb_extract(im, 1000, 1.2, 8, 20, 7), list(imgs)))
+    dta = time.perf_counter() - t0
+    out["cpu_baseline"] = {"kind": "port", "unit": "kpts/s", "oracle_1core": k1 / dt1, "oracle_1core_ms_per_image": 1e3 * dt1 / 8,
+                           "oracle_all_cores": ka / dta, "cores": threads, "sample": "8 images on 1 core; the 64-image batch over a thread pool"}
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        cvo = cv2.ORB_create(nfeatures=1000, scaleFactor=1.2, nlevels=8, fastThreshold=20)
+        t0 = time.perf_counter(); kc = 0
+        for i in range(16):
+            kp, _ = cvo.detectAndCompute(imgs[i], None); kc += len(kp)
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"]["cv2_orb_1core"] = kc / dtc
+        out["cpu_baseline"]["cv2_note"] = f"cv2 {cv2.__version__} cv::ORB (Harris ranking, no quad-tree: a different selection rule, listed for scale only)"
+    except Exception as e:
+        out["cpu_baseline"]["cv2_orb_1core"] = None
+        out["cpu_baseline"]["cv2_note"] = str(e)[:100]
+    return out
 
 
 if __name__ == "__main__":
