@@ -165,6 +165,7 @@ __device__ void f_task(const FusedArgs& a, const int* tk, double* smem, unsigned
   double* sX0 = sW + nbk * BS;
   double* sX1 = sX0 + (nbk - 1) * BS;
   auto Xs = [&](int h, int i) { return ((h & 1) ? sX1 : sX0) + (i - h - 1) * BS; };
+  __shared__ double sdv[4 * HB];   // 1 / sqrt(d) of every eliminated column of the node
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int dw = warp < 4 ? warp - 1 : warp - 2;          // 0..5 for warps 1,2,3,5,6,7 (meaningless for warps 0 and 4)
   const int dt = 32 * dw + lane;
@@ -196,6 +197,8 @@ __device__ void f_task(const FusedArgs& a, const int* tk, double* smem, unsigned
 #pragma unroll 1
   for (int h = 0; h < nbk; ++h) {
     if (h > 0) {
+      potrf32_finalize(sW + (h - 1) * BS, sdv + HB * (h - 1), tid, FTH);   // raw eliminated rows -> L^-1, by everybody
+      __syncthreads();
       blk_solve(Xs(h - 1, h), f_blk(sG, h, h - 1), sW + (h - 1) * BS, warp, 8, g, tg);
       __syncthreads();
       blk_update(f_blk(sG, h, h), Xs(h - 1, h), Xs(h - 1, h), warp, 8, g, tg);   // all 16 tiles: potrf32_sym wants both triangles
@@ -203,7 +206,7 @@ __device__ void f_task(const FusedArgs& a, const int* tk, double* smem, unsigned
     }
     F_STAMP(2 + 2 * h);
     if (warp == 0) {
-      potrf32_sym(f_blk(sG, h, h), sW + h * BS, a.fail);
+      potrf32_sym_t<true, false>(f_blk(sG, h, h), sW + h * BS, a.fail, sdv + HB * h);
       F_STAMP(3 + 2 * h);
     } else if (h == 0) {
       // the rest of the node arrives; the other diagonal blocks are mirrored
@@ -250,6 +253,8 @@ __device__ void f_task(const FusedArgs& a, const int* tk, double* smem, unsigned
   // ---- last tile of the node: X_qp = G_qp W_p^T of its two blocks is in the column buffer, its inverse goes out ----
   {
     const int p = nbk - 2, q = nbk - 1;
+    potrf32_finalize(sW + q * BS, sdv + HB * q, tid, FTH);
+    __syncthreads();
     linv_tile(sW + p * BS, sW + q * BS, Xs(p, q), f_blk(sG, p, p), a.Linv + (size_t)(ta + nt - 1) * NB * NB, warp, 8, tid, 2);
     __syncthreads();
     if (tid == 0) { __threadfence(); atomicAdd(a.sync + tk[FK_F_FIN] + nt - 1, 1); }

@@ -9,21 +9,31 @@
 #include "../../textslam_b200/csrc/chol_potrf.cuh"
 using namespace tsl;
 
-template <bool ROT>
+template <int VAR>
 __global__ void __launch_bounds__(32, 1) k_potrf(const double* Gg, double* Wg, long long* out, int* fail, int reps) {
   __shared__ __align__(16) double G[32 * LDB];
   __shared__ __align__(16) double W[32 * LDB];
+  __shared__ double dv[32];
   for (int i = threadIdx.x; i < 32 * LDB; i += 32) G[i] = Gg[i];
   __syncwarp();
   long long best = 1ll << 60;
   for (int it = 0; it < reps; ++it) {
+    if (VAR >= 2) { for (int i = threadIdx.x; i < 32 * LDB; i += 32) G[i] = Gg[i]; }   // the blocked variant works in place
     __syncwarp();
     const long long t0 = clock64();
-    potrf32_sym_t<ROT>(G, W, fail);
+    if (VAR == 2) potrf32_blk(G, W, fail);
+    else if (VAR == 3) potrf32_blk_t<9, true, true, true>(G, W, fail);
+    else if (VAR == 4) potrf32_blk_t<12, false, true, true>(G, W, fail);
+    else if (VAR == 5) potrf32_blk_t<12, false, false, true>(G, W, fail);
+    else if (VAR == 6) potrf32_blk_t<12, false, false, false>(G, W, fail);
+    else if (VAR == 8) potrf32_sym_t<true, false>(G, W, fail, dv);
+    else if (VAR == 9) potrf32_sym_t<false, false>(G, W, fail, dv);
+    else potrf32_sym_t<VAR == 0>(G, W, fail);
     __syncwarp();
     const long long t1 = clock64();
     best = min(best, t1 - t0);
   }
+  if (VAR >= 8) { __syncwarp(); potrf32_finalize(W, dv, threadIdx.x, 32); __syncwarp(); }
   for (int i = threadIdx.x; i < 32 * LDB; i += 32) Wg[i] = W[i];
   if (threadIdx.x == 0) out[0] = best;
 }
@@ -166,6 +176,26 @@ __global__ void __launch_bounds__(32, 1) k_ablate(double seed, double* sink, lon
   if (r == 0) out[0] = best;
 }
 
+// two-warp blocked variant: warp 0 = chain, warp 1 = helper
+__global__ void __launch_bounds__(64, 1) k_potrf2(const double* Gg, double* Wg, long long* out, int* fail, int reps) {
+  __shared__ __align__(16) double G[32 * LDB];
+  __shared__ __align__(16) double W[32 * LDB];
+  const int warp = threadIdx.x >> 5;
+  long long best = 1ll << 60;
+  for (int it = 0; it < reps; ++it) {
+    for (int i = threadIdx.x; i < 32 * LDB; i += 64) G[i] = Gg[i];
+    __syncthreads();
+    const long long t0 = clock64();
+    potrf32_blk2(G, W, fail, warp, 1);
+    __syncwarp();
+    const long long t1 = clock64();
+    if (warp == 0) best = min(best, t1 - t0);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 32 * LDB; i += 64) Wg[i] = W[i];
+  if (threadIdx.x == 0) out[0] = best;
+}
+
 int main() {
   const int n = 32;
   std::vector<double> A(n * n), G(32 * LDB, 0.0), W(32 * LDB), L(n * n, 0.0);
@@ -193,8 +223,19 @@ int main() {
   cudaMalloc(&dG, G.size() * 8); cudaMalloc(&dW, W.size() * 8); cudaMalloc(&dsink, 32 * 8); cudaMalloc(&dout, 8); cudaMalloc(&dfail, 4);
   cudaMemcpy(dG, G.data(), G.size() * 8, cudaMemcpyHostToDevice); cudaMemset(dfail, 0, 4);
   long long cyc = 0;
-  for (int variant = 0; variant < 2; ++variant) {
-    if (variant == 0) k_potrf<true><<<1, 32>>>(dG, dW, dout, dfail, 10); else k_potrf<false><<<1, 32>>>(dG, dW, dout, dfail, 10);
+  for (int variant = 0; variant < 10; ++variant) {
+    switch (variant) {
+      case 0: k_potrf<0><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 1: k_potrf<1><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 2: k_potrf<2><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 3: k_potrf<3><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 4: k_potrf<4><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 5: k_potrf<5><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 6: k_potrf<6><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      case 7: k_potrf2<<<1, 64>>>(dG, dW, dout, dfail, 10); break;
+      case 8: k_potrf<8><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+      default: k_potrf<9><<<1, 32>>>(dG, dW, dout, dfail, 10); break;
+    }
     cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost);
     cudaMemcpy(W.data(), dW, W.size() * 8, cudaMemcpyDeviceToHost);
     double err = 0;   // || W L - I ||_max
@@ -204,7 +245,7 @@ int main() {
         for (int k = 0; k < n; ++k) s += W[i * LDB + k] * L[k * n + j];
         err = fmax(err, fabs(s - (i == j ? 1.0 : 0.0)));
       }
-    printf("potrf32_sym (%s): %lld cycles (%.1f per column), ||W L - I||_max = %.2e, %s\n", variant == 0 ? "rotating frame" : "straight line", cyc, cyc / 32.0, err,
+    printf("potrf32_sym (%s): %lld cycles (%.1f per column), ||W L - I||_max = %.2e, %s\n", (const char*[]){"rotating frame", "straight line", "blocked, panels of 8", "blocked, record stride 9", "blocked, no rank-8 update (timing only)", "blocked, no update, no epilogue", "blocked, chain + records only", "blocked, two warps (chain + helper)", "rotating frame, raw rows out (finalised outside the timed part)", "straight line, raw rows out"}[variant], cyc, cyc / 32.0, err,
            cudaGetErrorString(cudaGetLastError()));
   }
   {
