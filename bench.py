@@ -475,6 +475,11 @@ def text_on_bench(ctx, T, synth, po, threads, hbm_peak, peak_src):
                                  "traffic": ncu_dram_bytes("text_eval", "text_eval_kernel"), "traffic_source": NCU_RAW["text_eval"], "peak_source": peak_src,
                                  "algorithmic_bytes_per_launch": TEXT_EVAL_BYTES * prob.n_tobs,
                                  "note": "one partial wave at this size (latency bound like the point kernel at the C5 size)"}
+    dev.eval_text(T.TX_BA, T.JAC_ANALYTIC_TMA, reps=3, flush_l2=True)
+    ms_tma = dev.eval_text(T.TX_BA, T.JAC_ANALYTIC_TMA, reps=20, flush_l2=True)
+    out["tma_staged_variant"] = {"kernel": "text_eval_tma_kernel (one CTA per text object and keyframe; image window by cp.async.bulk.tensor.2d, parameter blocks in shared memory)",
+                                 "ms_per_launch": ms_tma, "achieved": TEXT_EVAL_BYTES * prob.n_tobs / (ms_tma * 1e-3) / 1e9, "unit": "GB/s",
+                                 "vs_ldg_taps": ms / ms_tma}
     ms_cd = dev.eval_text(T.TX_BA, T.JAC_CENTRAL_DIFF, reps=5, flush_l2=True)
     out["central_diff_ms_per_launch"] = ms_cd   # Ceres-faithful mode: 35 exact functor evaluations per block
     dev.free()

@@ -42,6 +42,8 @@ extern "C" {
 /* text Jacobian mode */
 #define TSLAM_JAC_ANALYTIC 0      /* closed form                             */
 #define TSLAM_JAC_CENTRAL_DIFF 1  /* replica of ceres::NumericDiffCostFunction<CENTRAL> step rule */
+#define TSLAM_JAC_ANALYTIC_TMA 2  /* closed form, image window of every text object staged in shared memory by a TMA tensor load
+                                   * (tslam_eval_text / tslam_dev_eval_text only; same results as TSLAM_JAC_ANALYTIC)           */
 
 /* ---- problem description (shared by eval and solve) ---------------------------------------- */
 /* Replaces the ceres::Problem built in src/optimizer.cc:1106-1208 (pose), :1359-1588 (local BA),

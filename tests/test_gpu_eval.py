@@ -90,3 +90,24 @@ def test_bad_arguments_fail_loudly(ctx):
     prob.p_cam[0] = 999
     with pytest.raises(T.TslamError):
         ctx.eval_points(prob, PT_BA)
+
+
+def test_text_tma_staged_variant_is_identical(ctx):
+    """TSLAM_JAC_ANALYTIC_TMA: the image window of every text object staged in shared memory by one cp.async.bulk.tensor.2d
+    (csrc/ba_eval_tma.cu) — same residuals and Jacobians as the __ldg-tap kernel (to rounding) on the host-buffer entry point and
+    on the device-resident one (C4 local BA, pose-only, a text-on global BA with objects near the image border)."""
+    import textslam_b200 as T
+    for prob, kind in ((synth.c4_local_ba(seed=81), T.TX_BA), (synth.c3_pose_only(seed=82), T.TX_POSE),
+                       (synth.c5_global_ba(seed=83, n_kf=60, n_lm=500, n_planes=120, text_kf_stride=2), T.TX_BA),
+                       (synth.c4_local_ba(seed=84), T.TX_THETA)):
+        r0, J0 = ctx.eval_text(prob, kind, T.JAC_ANALYTIC)
+        r1, J1 = ctx.eval_text(prob, kind, T.JAC_ANALYTIC_TMA)
+        # same tap values, same formulas; the compiler shares sub-expressions with the window computation of the staged kernel, so
+        # a few products are contracted differently: agreement to rounding, not bit for bit
+        tol = lambda x: 1e-12 * (np.abs(x).max() + 1.0)
+        assert np.abs(r0 - r1).max() <= tol(r0) and np.abs(J0 - J1).max() <= tol(J0), (np.abs(r0 - r1).max(), np.abs(J0 - J1).max())
+        d = ctx.upload(prob)
+        d.eval_text(kind, T.JAC_ANALYTIC_TMA, reps=2)
+        r2, J2 = d.download_eval(1, J0.shape[-1])
+        assert np.array_equal(r1, r2) and np.array_equal(J1, J2)
+        d.free()

@@ -8,7 +8,7 @@ import numpy as np
 
 PT_BA, PT_BA_NW, PT_POSE, PT_RHO = 0, 1, 2, 3
 TX_BA, TX_POSE, TX_THETA = 0, 1, 2
-JAC_ANALYTIC, JAC_CENTRAL_DIFF = 0, 1
+JAC_ANALYTIC, JAC_CENTRAL_DIFF, JAC_ANALYTIC_TMA = 0, 1, 2
 PT_NCOLS = {PT_BA: 13, PT_BA_NW: 13, PT_POSE: 6, PT_RHO: 1}
 TX_NCOLS = {TX_BA: 15, TX_POSE: 6, TX_THETA: 3}
 TRACE_COLS = 4

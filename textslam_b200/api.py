@@ -9,7 +9,7 @@ import numpy as np
 from ._lib import lib, check, TslamError  # noqa: F401
 from ._abi import (BAProblem, SolveSummaryC, KeyPointC, KP_DTYPE, PT_NCOLS, TX_NCOLS, TRACE_COLS, solve_options,
                    c_dp, c_bp, c_ip, PT_BA, PT_BA_NW, PT_POSE, PT_RHO, TX_BA, TX_POSE, TX_THETA, JAC_ANALYTIC,
-                   JAC_CENTRAL_DIFF, GateOptionsC, gate_options)
+                   JAC_CENTRAL_DIFF, JAC_ANALYTIC_TMA, GateOptionsC, gate_options)
 
 
 def _dp(a):

@@ -137,7 +137,9 @@ __device__ __forceinline__ void relative_pose(const double qc[4], const double t
   for (int i = 0; i < 3; ++i) P.t[i] = tc[i] - (P.R[3 * i + 0] * th[0] + P.R[3 * i + 1] * th[1] + P.R[3 * i + 2] * th[2]);
 }
 
-struct TextImg { const uint8_t* img; int cols, rows; };
+// tile != nullptr: the taps come from a shared-memory copy of the image window [tx0, tx0 + tw) x [ty0, ..) that the CTA staged
+// with a TMA tensor load (ba_eval_tma.cu); otherwise from global memory through the read-only path.
+struct TextImg { const uint8_t* img; int cols, rows; const uint8_t* tile = nullptr; int tx0 = 0, ty0 = 0, tw = 0; };
 
 // One pixel of the 8-pixel pattern: intensity + bilinear gradient (nume_BAText.h:58-91).
 template <bool WANT_G>
@@ -159,10 +161,17 @@ __device__ __forceinline__ double text_pixel(const RelPose& P, double rx, double
   // uf<0 || vf<0 || uc>=cols || vc>=rows -> 0 (NaN falls through to 0 as well)
   if (ufl >= 0.0 && vfl >= 0.0 && ceil(u) < (double)im.cols && ceil(v) < (double)im.rows) {
     const int uf = (int)ufl, vf = (int)vfl;
-    const uint8_t* p = im.img + (size_t)vf * im.cols + uf;
     const double su = u - ufl, sv = v - vfl;
-    const int du = (uf + 1 < im.cols) ? 1 : 0, dv = (vf + 1 < im.rows) ? im.cols : 0;
-    const double I00 = (double)__ldg(p), I01 = (double)__ldg(p + du), I10 = (double)__ldg(p + dv), I11 = (double)__ldg(p + dv + du);
+    double I00, I01, I10, I11;
+    if (im.tile) {
+      const uint8_t* p = im.tile + (vf - im.ty0) * im.tw + (uf - im.tx0);
+      const int du = (uf + 1 < im.cols) ? 1 : 0, dv = (vf + 1 < im.rows) ? im.tw : 0;
+      I00 = (double)p[0]; I01 = (double)p[du]; I10 = (double)p[dv]; I11 = (double)p[dv + du];
+    } else {
+      const uint8_t* p = im.img + (size_t)vf * im.cols + uf;
+      const int du = (uf + 1 < im.cols) ? 1 : 0, dv = (vf + 1 < im.rows) ? im.cols : 0;
+      I00 = (double)__ldg(p); I01 = (double)__ldg(p + du); I10 = (double)__ldg(p + dv); I11 = (double)__ldg(p + dv + du);
+    }
     const double wtl = (1.0 - su) * (1.0 - sv), wtr = su * (1.0 - sv), wbl = (1.0 - su) * sv, wbr = su * sv;
     inten = wtl * I00 + wtr * I01 + wbl * I10 + wbr * I11;
     if (WANT_G) {

@@ -248,6 +248,7 @@ static void launch_text_mode(tslam_ctx* ctx, tslam_dev_problem* d, int kind, con
 
 int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, bool want_J) {
   if (d->n_tobs == 0) return TSLAM_OK;
+  if (want_J && jac_mode == TSLAM_JAC_ANALYTIC_TMA) return launch_eval_text_tma(ctx, d, kind);
   const int ncols = kind == TSLAM_TX_BA ? 15 : (kind == TSLAM_TX_POSE ? 6 : 3);
   TSL_CUDA(d->tr.reserve(8 * (size_t)d->n_tobs));
   if (want_J) { TSL_CUDA(d->tJ.reserve((size_t)d->n_tobs * 8 * ncols)); d->tJ_cols = ncols; }

@@ -135,7 +135,19 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
     TSL_CUDA(d->t_img.upload(p->t_img, p->n_tobs, s));
     // host arrays are caller-owned and may change after return; inside a one-shot tslam_solve the caller is blocked until the
     // call ends, so the copies may still be in flight while the structure analysis is being enqueued behind them
-    if (persistent) TSL_CUDA(cudaStreamSynchronize(s));
+    if (persistent) {
+      // run table of the TMA-staged text kernel: consecutive blocks of one text object seen in one keyframe
+      std::vector<int32_t> runs;
+      for (int i = 0; i < p->n_tobs; ++i) {
+        const bool same = i > 0 && p->t_cam[i] == p->t_cam[i - 1] && p->t_host[i] == p->t_host[i - 1] && p->t_plane[i] == p->t_plane[i - 1] &&
+                          p->t_img[i] == p->t_img[i - 1] && i - runs.back() < 32;
+        if (!same) runs.push_back(i);
+      }
+      d->n_truns = (int)runs.size();
+      runs.push_back(p->n_tobs);
+      TSL_CUDA(d->t_run_ptr.upload(runs.data(), runs.size(), s));
+      TSL_CUDA(cudaStreamSynchronize(s));
+    }
     return TSLAM_OK;
   }
   // landmark-sharded upload: an observation lives with its landmark
@@ -301,7 +313,7 @@ int tslam_eval_points(tslam_ctx* ctx, int kind, const tslam_ba_problem* p, doubl
 int tslam_eval_text(tslam_ctx* ctx, int kind, int jac_mode, const tslam_ba_problem* p, double* r, double* J) {
   if (!ctx || !p || !r) return set_error(TSLAM_ERR_ARG, "null argument");
   if (kind < 0 || kind > 2) return set_error(TSLAM_ERR_ARG, "bad text kind %d", kind);
-  if (jac_mode != TSLAM_JAC_ANALYTIC && jac_mode != TSLAM_JAC_CENTRAL_DIFF) return set_error(TSLAM_ERR_ARG, "bad jac_mode %d", jac_mode);
+  if (jac_mode != TSLAM_JAC_ANALYTIC && jac_mode != TSLAM_JAC_CENTRAL_DIFF && jac_mode != TSLAM_JAC_ANALYTIC_TMA) return set_error(TSLAM_ERR_ARG, "bad jac_mode %d", jac_mode);
   TSL_CUDA(cudaSetDevice(ctx->device));
   tslam_dev_problem d;
   int rc = upload_problem(ctx, p, &d);

@@ -133,6 +133,7 @@ struct tslam_dev_problem {
   tsl::DevBuf<double> t_rays, t_iref, t_musigma;
   tsl::DevBuf<int32_t> t_cam, t_host, t_plane, t_img;
   tsl::DevBuf<uint8_t> imgs;
+  tsl::DevBuf<int32_t> t_run_ptr; int n_truns = 0;   // runs of consecutive text blocks with the same (camera, host, plane, image), <= 32 blocks each (ba_eval_tma.cu)
   // evaluation outputs (observation-major): r, J
   tsl::DevBuf<double> pr, pJ, tr, tJ;
   int pJ_cols = 0, tJ_cols = 0;
@@ -160,4 +161,5 @@ void free_solver(tslam_dev_problem* d);
 // kernels (ba_eval.cu)
 int launch_eval_points(tslam_ctx* ctx, tslam_dev_problem* d, int kind, bool want_J);
 int launch_eval_text(tslam_ctx* ctx, tslam_dev_problem* d, int kind, int jac_mode, bool want_J);
+int launch_eval_text_tma(tslam_ctx* ctx, tslam_dev_problem* d, int kind);   // ba_eval_tma.cu (jac_mode TSLAM_JAC_ANALYTIC_TMA)
 }  // namespace tsl
