@@ -85,3 +85,38 @@ def test_dev_bench_hook(ctx):
     ms, nkp = orb.dev_bench(imgs, reps=2)
     assert ms > 0 and nkp >= 4 * 1000
     orb.close()
+
+
+def test_batch_64_bit_exact_vs_oracle(ctx, oracle):
+    """BASELINE configuration C2 at its full batch: 64 images of 640x480 in one call, every keypoint field and descriptor byte
+    equal to the oracle's per-image extraction."""
+    import textslam_b200 as T
+    from concurrent.futures import ThreadPoolExecutor
+    imgs = synth.orb_images(seed=37, n=64)
+    orb = T.ORBextractor(ctx, 1000, 1.2, 8, 20, 7)
+    res = orb.extract_batch(imgs)
+    with ThreadPoolExecutor(8) as ex:   # the oracle is a ctypes call that releases the GIL
+        ref = list(ex.map(lambda im: oracle.orb_extract(im, 1000, 1.2, 8, 20, 7), imgs))
+    assert len(res) == 64
+    for i, ((kp, desc), (kpo, desco)) in enumerate(zip(res, ref)):
+        _check(kp, desc, kpo, desco, f"img{i}")
+    orb.close()
+
+
+def test_row_stride_wider_than_the_image(ctx, oracle):
+    """cv::Mat rows need not be packed (step > cols: a region of interest, an aligned allocation): the extractor takes the row
+    stride in bytes (tslam_orb_extract's `stride`) and must read exactly the w columns of every row."""
+    import textslam_b200 as T
+    packed = synth.orb_images(seed=38, n=3)
+    n, h, w = packed.shape
+    wide = np.full((n, h, w + 96), 255, np.uint8)   # the padding holds a different value than any border handling would produce
+    wide[:, :, :w] = packed
+    view = wide[:, :, :w]
+    assert view.strides[1] == w + 96 and not view.flags["C_CONTIGUOUS"]
+    orb = T.ORBextractor(ctx, 1000, 1.2, 8, 20, 7)
+    res = orb.extract_batch(view)
+    assert orb._stride == w + 96
+    for i, (kp, desc) in enumerate(res):
+        kpo, desco = oracle.orb_extract(packed[i], 1000, 1.2, 8, 20, 7)
+        _check(kp, desc, kpo, desco, f"img{i}")
+    orb.close()

@@ -314,10 +314,15 @@ class ORBextractor:
             pass
 
     def _ptrs(self, imgs):
-        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        """Row pointers + the row stride in bytes: a view whose rows are spaced wider than the image (cv::Mat with step > cols, a
+        region of interest of a larger frame) is passed as it lies, without a repacking copy."""
+        imgs = np.asarray(imgs, dtype=np.uint8)
         if imgs.ndim == 2:
             imgs = imgs[None]
         n, h, w = imgs.shape
+        if imgs.strides[2] != 1 or imgs.strides[1] < w:
+            imgs = np.ascontiguousarray(imgs)
+        self._stride = int(imgs.strides[1])
         ptrs = (C.c_void_p * n)(*[imgs[i].ctypes.data for i in range(n)])
         return imgs, ptrs, n, h, w
 
@@ -328,7 +333,7 @@ class ORBextractor:
         kp = np.zeros((n, max_kp), dtype=KP_DTYPE)
         desc = np.zeros((n, max_kp, 32), dtype=np.uint8)
         cnt = np.zeros(n, dtype=np.int32)
-        check(lib().tslam_orb_extract(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(max_kp),
+        check(lib().tslam_orb_extract(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(self._stride), C.c_int(max_kp),
                                       kp.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(c_bp),
                                       cnt.ctypes.data_as(C.POINTER(C.c_int32))))
         return [(kp[i, :cnt[i]].copy(), desc[i, :cnt[i]].copy()) for i in range(n)]
@@ -362,7 +367,7 @@ class ORBextractor:
     def dev_bench(self, imgs, reps=5):
         imgs, ptrs, n, h, w = self._ptrs(imgs)
         ms = C.c_float(); nk = C.c_int64()
-        check(lib().tslam_orb_dev_bench(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(w), C.c_int(reps),
+        check(lib().tslam_orb_dev_bench(self._h, ptrs, C.c_int(n), C.c_int(w), C.c_int(h), C.c_int(self._stride), C.c_int(reps),
                                         C.byref(ms), C.byref(nk)))
         return ms.value, nk.value
 

@@ -1401,8 +1401,23 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
   auto T0 = std::chrono::steady_clock::now();
   TSL_CUDA(cudaSetDevice(ctx->device));
   AllocStreamScope alloc_scope(ctx->stream);   // declared before every device buffer of this call: released after them, on the same stream
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  {   // pose-only / local-window sizes: one persistent kernel for the whole solve (ba_small.cu)
+    bool handled = false;
+    const double *d_rp = nullptr, *d_rt = nullptr;
+    tslam_solve_summary ssum{};
+    if ((rc = small_solve(ctx, p, opt, &ssum, final_residuals, trace, &d_rp, &d_rt, &handled))) return rc;
+    if (handled) {
+      if (gate && (rc = gate_device(ctx, d_rp, d_rt, p->n_pobs, p->n_tobs, gate->t_obj, gate->obj_size, gate->n_obj, gate->opt, gate->pt_bad, gate->tf_bad,
+                                    gate->obj_bad, gate->counts))) return rc;
+      ssum.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+      if (summary) *summary = ssum;
+      return TSLAM_OK;
+    }
+  }
   tslam_dev_problem d;
-  int rc = upload_problem(ctx, p, &d, /*shard=*/true, /*persistent=*/false);
+  rc = upload_problem(ctx, p, &d, /*shard=*/true, /*persistent=*/false);
   if (rc) return rc;
   auto Tu = std::chrono::steady_clock::now();
   struct Guard { tslam_dev_problem* d; ~Guard() { free_solver(d); } } guard{&d};

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <chrono>
 #include "ctx.cuh"
+#include "solver.cuh"
 #include "analysis.hpp"
 
 namespace tsl {
@@ -63,7 +64,7 @@ static int upload_selected(DevBuf<T>& dst, DevBuf<T>& scratch, const T* src, siz
   return TSLAM_OK;
 }
 
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool persistent) {
+int validate_problem(const tslam_ba_problem* p) {
   if (!p) return set_error(TSLAM_ERR_ARG, "null problem");
   if (p->n_cams <= 0 || !p->cams) return set_error(TSLAM_ERR_ARG, "problem has no cameras");
   if (p->n_points < 0 || p->n_planes < 0 || p->n_pobs < 0 || p->n_tobs < 0 || p->n_imgs < 0) return set_error(TSLAM_ERR_ARG, "negative count");
@@ -86,6 +87,11 @@ int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem*
       return set_error(TSLAM_ERR_ARG, "text block %d has an index out of range", i);
     if (p->t_cam[i] == p->t_host[i]) return set_error(TSLAM_ERR_ARG, "text block %d: observing and host camera are the same block (src/optimizer.cc:1485-1486)", i);
   }
+  return TSLAM_OK;
+}
+
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool persistent) {
+  { const int vrc = validate_problem(p); if (vrc) return vrc; }
   cudaStream_t s = ctx->stream;
   d->n_cams = p->n_cams; d->n_points = p->n_points; d->n_planes = p->n_planes;
   d->g_pobs = p->n_pobs; d->g_tobs = p->n_tobs;
@@ -264,6 +270,7 @@ void tslam_ctx_destroy(tslam_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   tslam_comm_destroy(c);
+  small_workspace_free(c);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);

@@ -119,6 +119,7 @@ struct tslam_ctx {
   // per-context (= per-device) opt-ins to more than 48 KB of dynamic shared memory
   bool attr_chol_fused = false, attr_chol_waves = false, attr_orb = false;
   size_t attr_textinfo_smem = 0;
+  void* small_ws = nullptr;   // tsl::SmallWorkspace (ba_small.cu): staging block + device workspace of the small-problem solve
 };
 
 // Device-resident problem: everything the kernels read, SoA, FP64 / int32 / u8.
@@ -153,6 +154,7 @@ namespace tsl {
 // copies of the observation index arrays only when the structure analysis will run on the host, and the uploads may still be in
 // flight on return (everything that follows is ordered behind them on the context stream)
 int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false, bool persistent = true);
+int validate_problem(const tslam_ba_problem* p);   // argument checks of every entry point that takes a host problem
 bool device_analysis_supported(const tslam_ctx* ctx, const tslam_dev_problem* d);
 // observation ownership rule shared by upload and the solver's structure analysis
 inline int obs_owner(bool lm_free, int lm_index, int obs_index, int world) { return (lm_free ? lm_index : obs_index) % world; }

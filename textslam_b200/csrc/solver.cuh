@@ -66,6 +66,11 @@ int launch_eval_points_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double
 int launch_eval_text_robust(tslam_ctx* ctx, tslam_dev_problem* d, const double* cams, const double* theta, const uint8_t* active,
                             const uint8_t* free_masks, int jac_mode, double* r, double* J, double* cost_part, int* n_parts);
 
+// ba_small.cu: one persistent kernel per solve for pose-only / local-window problems; *handled = false -> not eligible
+int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* opt, tslam_solve_summary* summary, double* final_residuals,
+                double* trace, const double** d_rp, const double** d_rt, bool* handled);
+void small_workspace_free(tslam_ctx* ctx);
+
 // comm.cu
 int comm_allreduce_sum(tslam_ctx* ctx, double* buf, size_t n);
 int comm_allreduce_max(tslam_ctx* ctx, double* buf, size_t n);
