@@ -180,7 +180,12 @@ def test_device_resident_lm_matches_solve(ctx, oracle):
     phases, summ = d.lm_iterations(6)
     cams, rho, theta = d.download_params()
     q = prob.copy()
-    s, _, _ = ctx.solve(q, 6)
+    import os
+    os.environ["TSLAM_SMALL"] = "0"   # the device-resident handle runs the general path: compare like with like (bit-level agreement)
+    try:
+        s, _, _ = ctx.solve(q, 6)
+    finally:
+        os.environ.pop("TSLAM_SMALL", None)
     assert summ["iterations"] == s["iterations"]
     assert np.allclose(cams, q.cams, rtol=1e-12, atol=1e-14) and np.allclose(rho, q.rho, rtol=1e-12, atol=1e-14)
     assert phases[7] > 0

@@ -30,19 +30,20 @@
 namespace tsl {
 
 constexpr int ST = 256, SW = 8;
-constexpr int S_MAX_NC = 10, S_MAX_K = 256, S_MAX_P = 16384, S_MAX_T = 4096, S_MAX_LIST = 1024, S_MAX_G = 64;
+constexpr int S_MAX_NC = 10, S_MAX_K = 256, S_MAX_P = 16384, S_MAX_T = 4096, S_MAX_LIST = 1024, S_MAX_G = 160;
 constexpr int S_EC = 64;            // columns of a landmark's E row (6 * S_MAX_NC padded)
-constexpr int S_SCR = 512;          // doubles of scratch per warp
+constexpr int S_SCR = 848;          // doubles of scratch per warp: [0, 448) staged observation blocks, [448, 832) E / W rows, [832, 848) slot list
+constexpr int S_STG = 448, S_CHUNK = 16;
 constexpr int S_SPIN = 1 << 22;
 constexpr int S_NPART = 8;
 
 struct SmallArgs {
   // ---- launch-invariant inputs ----
   const double2 *p_uv, *p_ray;
-  const int *p_cam, *p_host, *p_lm, *p_ls;
+  const int *p_cam, *p_host, *p_lm, *p_ls, *p_cs, *p_hs;   // *_cs / *_hs: free-camera slot of the observing / host camera (-1: constant)
   const double2 *t_rays, *t_musigma;
   const double* t_iref;
-  const int *t_cam, *t_host, *t_plane, *t_img, *t_ls;
+  const int *t_cam, *t_host, *t_plane, *t_img, *t_ls, *t_cs, *t_hs;
   const uint8_t* imgs; int img_w, img_h;
   const int* camslot;
   const int *vp_ptr, *vp_obs, *vp_gl, *vt_ptr, *vt_obs, *vt_gl;
@@ -57,7 +58,8 @@ struct SmallArgs {
   double *partH, *partS, *sumH, *sumS, *part0, *partG, *part;
   int* sync;                                    // [0] barrier counter, [1] abort
   double* out;                                  // result block, see OUT_*
-  double* r_final;
+  long long* prof;                              // TSLAM_SMALL_PROF: clock64 stamps of CTA 0, 16 per iteration
+  double *r_final_p, *r_final_t;
   // ---- sizes / options ----
   int K, nc, n, lp, lt, nvp, nvt, n_points, n_planes, G, max_iters;
   double ftol, gtol, ptol, radius0;
@@ -119,29 +121,53 @@ __device__ __forceinline__ void block_sums(double (&v)[NV], double* s_red) {
     for (int k = 0; k < NV; ++k) { double s = 0.0; for (int w = 0; w < SW; ++w) s += s_red[w * NV + k]; v[k] = s; }
 }
 
+// sum / max over the G per-CTA partials base[c * stride], c = lane, lane + 32, ... then a shuffle tree: the loads are independent (one
+// or two L2 round trips instead of G dependent ones) and the order of the additions is fixed. Result in every lane.
+__device__ __forceinline__ double warp_sum_ctas(const double* base, int stride, int G, int lane) {
+  double s = 0.0;
+  for (int c = lane; c < G; c += 32) s += base[(size_t)c * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+__device__ __forceinline__ double warp_max_ctas(const double* base, int stride, int G, int lane) {
+  double s = 0.0;
+  for (int c = lane; c < G; c += 32) s = fmax(s, base[(size_t)c * stride]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+  return s;
+}
+#define STAMP(k) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0 && pit < 16) a.prof[16 * pit + (k)] = clock64(); } while (0)
+
 // residuals (+ Jacobians) of every block at (cams in shared memory, rho, theta): loss-corrected, observation-major
 template <bool WJ>
 __device__ __forceinline__ void eval_pass(const SmallArgs& a, const double* scams, const double* rho, const double* theta, double* rp, double* Jp,
                                           double* rt, double* Jt, double& cost_a, double& cost_f) {
-  for (int i = blockIdx.x * ST + threadIdx.x; i < a.lp; i += a.G * ST) {
-    const double2 uv = a.p_uv[i], ray = a.p_ray[i];
-    const int ci = a.p_cam[i], hi = a.p_host[i], li = a.p_lm[i];
-    const Cam c = cam_at(scams, ci), h = cam_at(scams, hi);
-    double r[2], J[26];
-    point_eval<WJ>(c, h, rho[li], ray.x, ray.y, uv.x, uv.y, a.pfx, a.pfy, a.pcx, a.pcy, a.wx, a.wy, r, J);
-    double rho0;
-    const double sq = huber_scale(a.hub_p, r[0] * r[0] + r[1] * r[1], &rho0);
-    const bool act = a.camslot[ci] >= 0 || a.camslot[hi] >= 0 || a.p_ls[i] >= 0;
-    if (act) cost_a += 0.5 * rho0; else cost_f += 0.5 * rho0;
-    rp[2 * i] = r[0] * sq; rp[2 * i + 1] = r[1] * sq;
-    if (WJ) {
-      double* o = Jp + 26 * (size_t)i;
+  // one index space: [0, lp) point blocks, then (from the next multiple of 32) the 8 lt text pixels; a warp is all points or all
+  // text, and with G x 256 threads >= lp + 8 lt a thread evaluates one item (the two latency chains run side by side)
+  const int lp_pad = (a.lp + 31) & ~31;
+  for (int idx = blockIdx.x * ST + threadIdx.x; idx < lp_pad + ((8 * a.lt + 31) & ~31); idx += a.G * ST) {
+    if (idx < lp_pad) {
+      const int i = idx;
+      if (i >= a.lp) continue;
+      const double2 uv = a.p_uv[i], ray = a.p_ray[i];
+      const int ci = a.p_cam[i], hi = a.p_host[i], li = a.p_lm[i];
+      const Cam c = cam_at(scams, ci), h = cam_at(scams, hi);
+      double r[2], J[26];
+      point_eval<WJ>(c, h, rho[li], ray.x, ray.y, uv.x, uv.y, a.pfx, a.pfy, a.pcx, a.pcy, a.wx, a.wy, r, J);
+      double rho0;
+      const double sq = huber_scale(a.hub_p, r[0] * r[0] + r[1] * r[1], &rho0);
+      const bool act = a.p_cs[i] >= 0 || a.p_hs[i] >= 0 || a.p_ls[i] >= 0;
+      if (act) cost_a += 0.5 * rho0; else cost_f += 0.5 * rho0;
+      rp[2 * i] = r[0] * sq; rp[2 * i + 1] = r[1] * sq;
+      if (WJ) {
+        double* o = Jp + 26 * (size_t)i;
 #pragma unroll
-      for (int k = 0; k < 26; ++k) o[k] = J[k] * sq;
+        for (int k = 0; k < 26; ++k) o[k] = J[k] * sq;
+      }
+      continue;
     }
-  }
-  for (int base = blockIdx.x * ST; base < 8 * a.lt; base += a.G * ST) {
-    const int gpx = base + threadIdx.x;
+    const int gpx = idx - lp_pad;
     const int b = gpx >> 3;
     const bool valid = b < a.lt;
     double res = 0.0, Jr[15];
@@ -155,7 +181,7 @@ __device__ __forceinline__ void eval_pass(const SmallArgs& a, const double* scam
       TextImg im{a.imgs + (size_t)a.t_img[b] * a.img_w * a.img_h, a.img_w, a.img_h};
       if (WJ) res = text_pixel_analytic(c, h, th, ray.x, ray.y, im, a.tfx, a.tfy, a.tcx, a.tcy, ms.x, ms.y, a.t_iref[gpx], a.wT, Jr);
       else res = text_residual_only(c.q, c.t, h.q, h.t, th, ray.x, ray.y, im, a.tfx, a.tfy, a.tcx, a.tcy, ms.x, ms.y, a.t_iref[gpx], a.wT);
-      act = a.camslot[ci] >= 0 || a.camslot[hi] >= 0 || a.t_ls[b] >= 0;
+      act = a.t_cs[b] >= 0 || a.t_hs[b] >= 0 || a.t_ls[b] >= 0;
     }
     double s = res * res;
     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -175,11 +201,28 @@ __device__ __forceinline__ void eval_pass(const SmallArgs& a, const double* scam
   }
 }
 
-// camera part of one residual block into this warp's packed accumulator: lower triangle of H_cc, then g_c
-__device__ __forceinline__ void accum_block(double* acc, double* scr, const double* J, const double* r, int R, int JC, int cs, int hs, int NT, int lane) {
-  for (int e = lane; e < R * 12; e += 32) { const int row = e / 12, c = e - row * 12; scr[e] = J[row * JC + c]; }
-  if (lane < R) scr[96 + lane] = r[lane];
-  __syncwarp();
+// One residual block (R rows of JC Jacobian columns, then the R residuals) travels global -> registers -> this warp's scratch;
+// the loads of the next block are issued before the current one is consumed.
+template <int R, int JC>
+struct BlockRegs {
+  static constexpr int NV = (R * JC + R + 31) / 32;
+  double v[NV];
+  __device__ __forceinline__ void load(const double* J, const double* r, int lane) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int q = lane + 32 * j;
+      v[j] = q < R * JC ? J[q] : (q < R * JC + R ? r[q - R * JC] : 0.0);
+    }
+  }
+  __device__ __forceinline__ void store(double* scr, int lane) const {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { const int q = lane + 32 * j; if (q < R * JC + R) scr[q] = v[j]; }
+  }
+};
+
+// camera part of the staged block into this warp's packed accumulator: lower triangle of H_cc, then g_c
+template <int R, int JC>
+__device__ __forceinline__ void accum_block(double* acc, const double* scr, int cs, int hs, int NT, int lane) {
   for (int e = lane; e < 144; e += 32) {
     const int ia = e / 12, ib = e - 12 * ia;
     const int sa = ia < 6 ? cs : hs, sb = ib < 6 ? cs : hs;
@@ -187,38 +230,102 @@ __device__ __forceinline__ void accum_block(double* acc, double* scr, const doub
     const int I = 6 * sa + (ia < 6 ? ia : ia - 6), Jx = 6 * sb + (ib < 6 ? ib : ib - 6);
     if (I < Jx) continue;
     double v = 0.0;
-    for (int row = 0; row < R; ++row) v += scr[row * 12 + ia] * scr[row * 12 + ib];
+#pragma unroll
+    for (int row = 0; row < R; ++row) v += scr[row * JC + ia] * scr[row * JC + ib];
     acc[I * (I + 1) / 2 + Jx] += v;
   }
   if (lane < 12) {
     const int s = lane < 6 ? cs : hs;
     if (s >= 0) {
       double v = 0.0;
-      for (int row = 0; row < R; ++row) v += scr[row * 12 + lane] * scr[96 + row];
+#pragma unroll
+      for (int row = 0; row < R; ++row) v += scr[row * JC + lane] * scr[R * JC + row];
       acc[NT + 6 * s + (lane < 6 ? lane : lane - 6)] += v;
     }
   }
-  __syncwarp();
 }
 
+template <int R, int JC>
+__device__ __forceinline__ void accum_pass(double* acc, double* scr, int first, int count, int stride, const int* cs_of, const int* hs_of, const double* J,
+                                           const double* r, int NT, int lane) {
+  BlockRegs<R, JC> regs;
+  int i = first;
+  int cs = -1, hs = -1;
+  if (i < count) { cs = cs_of[i]; hs = hs_of[i]; regs.load(J + (size_t)R * JC * i, r + R * i, lane); }
+  while (i < count) {
+    const int ccs = cs, chs = hs;
+    regs.store(scr, lane);
+    __syncwarp();
+    const int nx = i + stride;
+    if (nx < count) { cs = cs_of[nx]; hs = hs_of[nx]; regs.load(J + (size_t)R * JC * nx, r + R * nx, lane); }
+    if (ccs >= 0 || chs >= 0) accum_block<R, JC>(acc, scr, ccs, chs, NT, lane);
+    __syncwarp();
+    i = nx;
+  }
+}
+
+// 1 / d for d > 0 without the division subroutine: hardware seed (rcp.approx.f64, ~2^-20) and two Newton steps (the second one
+// brings the error to the last bit); ~40 cycles instead of ~300 on the loop-carried chains below
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d, y, 1.0);
+  y = fma(fma(e, e, e), y, y);
+  return fma(fma(-d, y, 1.0), y, y);
+}
 __device__ __forceinline__ double damp_unscaled(double V, double s, double inv_radius) {
   const double s2 = s * s;
-  return fmin(fmax(s2 * V, 1e-6), 1e32) * inv_radius / s2;
+  return fmin(fmax(s2 * V, 1e-6), 1e32) * inv_radius * fast_rcp(s2);
+}
+// j-th (0-based) set bit of a <= 16-bit mask
+__device__ __forceinline__ int nth_set_bit(unsigned mask, int j) {
+  int pos = 0;
+#pragma unroll
+  for (int b = 0; b < 16; ++b) { if ((mask >> b) & 1u) { if (j == 0) pos = b; --j; } }
+  return pos;
 }
 
 // -E^T W (lower triangle over the touched camera slots) and -E^T wg into the warp's accumulator; sE / sW hold DL rows of 64
 template <int DL>
 __device__ __forceinline__ void schur_contrib(double* acc, const double* sE, const double* sW, const int* slots, int t, int NT, int lane) {
   const int T6 = 6 * t;
-  for (int e = lane; e < T6 * T6; e += 32) {
-    const int ia = e / T6, ib = e - ia * T6;
-    const int I = 6 * slots[ia / 6] + ia % 6, Jx = 6 * slots[ib / 6] + ib % 6;
-    if (I < Jx) continue;
-    double v = 0.0;
+  for (int ia = 0; ia < T6; ++ia) {   // slots ascend, so ib <= ia is the lower triangle
+    const int I = 6 * slots[ia / 6] + ia % 6;
+    for (int ib = lane; ib <= ia; ib += 32) {
+      const int Jx = 6 * slots[ib / 6] + ib % 6;
+      double v = 0.0;
 #pragma unroll
-    for (int d = 0; d < DL; ++d) v += sE[d * S_EC + I] * sW[d * S_EC + Jx];
-    acc[I * (I + 1) / 2 + Jx] += v;
+      for (int d = 0; d < DL; ++d) v += sE[d * S_EC + I] * sW[d * S_EC + Jx];
+      acc[I * (I + 1) / 2 + Jx] += v;
+    }
   }
+}
+
+// trailing update of column k by a 16 x 16 thread grid, NA x NA tiles (lower ones): a_ij -= (a_ik / d_k) a_jk for k < j <= i <= n, j < n.
+// Operands and targets go to registers first, then the FMAs, then the stores (a load behind a store to the same array would wait).
+template <int NA>
+__device__ __forceinline__ void chol_trail(double* A, int LD, int n, int k, int ty, int tx, double inv_d) {
+  double li[NA], lj[NA], tv[NA][NA];
+  const int i0 = k + 1 + ty, j0 = k + 1 + tx;
+#pragma unroll
+  for (int q = 0; q < NA; ++q) {
+    li[q] = (i0 + 16 * q <= n) ? A[(i0 + 16 * q) * LD + k] * inv_d : 0.0;
+    lj[q] = (j0 + 16 * q < n) ? A[(j0 + 16 * q) * LD + k] : 0.0;
+  }
+#pragma unroll
+  for (int qa = 0; qa < NA; ++qa)
+#pragma unroll
+    for (int qb = 0; qb <= qa; ++qb) {
+      const int i = i0 + 16 * qa, j = j0 + 16 * qb;
+      tv[qa][qb] = (i <= n && j <= min(i, n - 1)) ? A[i * LD + j] : 0.0;
+    }
+#pragma unroll
+  for (int qa = 0; qa < NA; ++qa)
+#pragma unroll
+    for (int qb = 0; qb <= qa; ++qb) {
+      const int i = i0 + 16 * qa, j = j0 + 16 * qb;
+      if (i <= n && j <= min(i, n - 1)) A[i * LD + j] = tv[qa][qb] - li[qa] * lj[qb];
+    }
 }
 
 #define GSYNC() do { if (grid_sync(bar)) { if (threadIdx.x == 0) a.out[OUT_ABORT] = 1.0; return; } } while (0)
@@ -232,7 +339,10 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
   double* s_sc = s_dc + 64;            // 64: Jacobi scale of the camera columns
   double* s_misc = s_sc + 64;          // 32: broadcast slots
   double* s_red = s_misc + 32;         // 64
-  double* s_scr = s_red + 64;          // SW x S_SCR
+  double* s_il = s_red + 64;           // 64: 1 / sqrt(pivot) of the reduced system's columns
+  double* s_cam3 = s_il + 64;          // 3 x 16: per free camera: gradient max-norm term, step^2, candidate norm^2
+  int* s_slot = reinterpret_cast<int*>(s_cam3 + 48);   // K ints (K <= 256: 128 doubles)
+  double* s_scr = s_cam3 + 48 + 128;   // SW x S_SCR
   double* s_acc = s_scr + SW * S_SCR;  // SW x P accumulators; reused as the (n + 1) x LD Cholesky workspace
   double* scr = s_scr + warp * S_SCR;
   double* acc = s_acc + warp * P;
@@ -240,6 +350,7 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
   GridBar bar{a.sync, a.sync + 1, a.G, 0};
 
   for (int e = tid; e < 7 * K; e += ST) s_cams[0][e] = a.cams_in[e];
+  for (int e = tid; e < K; e += ST) s_slot[e] = a.camslot[e];
   for (int i = blockIdx.x * ST + tid; i < a.n_points; i += a.G * ST) a.rho[1][i] = a.rho[0][i];
   for (int i = blockIdx.x * ST + tid; i < 3 * a.n_planes; i += a.G * ST) a.theta[1][i] = a.theta[0][i];
   __syncthreads();
@@ -258,13 +369,14 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
   int iter = 0, n_ok = 0, n_bad = 0, invalid_run = 0, term = TSLAM_TERM_NO_CONVERGENCE, cur = 0;
   bool newJ = true, first = true;
   {
+    if (warp < 3) { const double v = warp_sum_ctas(a.part0 + warp, 4, a.G, lane); if (lane == 0) s_misc[4 + warp] = v; }
+    __syncthreads();
     if (tid == 0) {
-      double ca = 0.0, cf = 0.0, xn = 0.0;
-      for (int c = 0; c < a.G; ++c) { ca += a.part0[4 * c]; cf += a.part0[4 * c + 1]; xn += a.part0[4 * c + 2]; }
+      double xn = s_misc[6];
       for (int k = 0; k < K; ++k)
-        if (a.camslot[k] >= 0)
+        if (s_slot[k] >= 0)
           for (int c = 0; c < 7; ++c) xn += s_cams[0][7 * k + c] * s_cams[0][7 * k + c];
-      s_misc[0] = ca; s_misc[1] = cf; s_misc[2] = sqrt(xn);
+      s_misc[0] = s_misc[4]; s_misc[1] = s_misc[5]; s_misc[2] = sqrt(xn);
     }
     __syncthreads();
     x_cost = s_misc[0]; fixed_cost = s_misc[1]; x_norm = s_misc[2];
@@ -278,20 +390,16 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
     if (radius <= 1e-32) { term = TSLAM_TERM_NO_CONVERGENCE; break; }
     if (a.nc + a.nvp + a.nvt == 0) { term = TSLAM_TERM_GRADIENT_TOL; break; }
     const double inv_radius = 1.0 / radius;
+    const int pit = n_ok + n_bad;   // loop trip, for the phase stamps
+    STAMP(0);
     const double *rp = a.rp[cur], *Jp = a.Jp[cur], *rt = a.rt[cur], *Jt = a.Jt[cur];
 
     // ---- camera block of the normal equations (only when the Jacobian is new) ----
     if (newJ && n > 0) {
       for (int e = tid; e < SW * P; e += ST) s_acc[e] = 0.0;
       __syncthreads();
-      for (int i = gw; i < a.lp; i += GW) {
-        const int cs = a.camslot[a.p_cam[i]], hs = a.camslot[a.p_host[i]];
-        if (cs >= 0 || hs >= 0) accum_block(acc, scr, Jp + 26 * (size_t)i, rp + 2 * i, 2, 13, cs, hs, NT, lane);
-      }
-      for (int i = gw; i < a.lt; i += GW) {
-        const int cs = a.camslot[a.t_cam[i]], hs = a.camslot[a.t_host[i]];
-        if (cs >= 0 || hs >= 0) accum_block(acc, scr, Jt + 120 * (size_t)i, rt + 8 * i, 8, 15, cs, hs, NT, lane);
-      }
+      accum_pass<2, 13>(acc, scr, gw, a.lp, GW, a.p_cs, a.p_hs, Jp, rp, NT, lane);
+      accum_pass<8, 15>(acc, scr, gw, a.lt, GW, a.t_cs, a.t_hs, Jt, rt, NT, lane);
       __syncthreads();
       for (int e = tid; e < P; e += ST) {
         double s = 0.0;
@@ -300,26 +408,40 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
       }
       __syncthreads();
     }
+    STAMP(1);
     // ---- landmarks: V, g, E (new Jacobian), M^-1 for this radius, Schur complement contributions ----
     for (int e = tid; e < SW * P; e += ST) s_acc[e] = 0.0;
     __syncthreads();
     double gmax_l = 0.0, fail_l = 0.0;
-    double* sE = scr; double* sW = scr + 3 * S_EC; int* slots = reinterpret_cast<int*>(scr + 6 * S_EC);
+    double* sE = scr + S_STG; double* sW = sE + 3 * S_EC; int* slots = reinterpret_cast<int*>(sW + 3 * S_EC);
     for (int v = gw; v < a.nvp; v += GW) {
       double e0 = 0.0, e1 = 0.0, V = 0.0, g = 0.0;
       unsigned mask = 0u;
       if (newJ) {
         const int s0 = lane / 6, k0 = lane % 6, s1 = (lane + 32) / 6, k1 = (lane + 32) % 6;
-        for (int o = a.vp_ptr[v]; o < a.vp_ptr[v + 1]; ++o) {
-          const int i = a.vp_obs[o];
-          const int cs = a.camslot[a.p_cam[i]], hs = a.camslot[a.p_host[i]];
-          const double* Ji = Jp + 26 * (size_t)i;
-          const double j0 = Ji[12], j1 = Ji[25];
-          V += j0 * j0 + j1 * j1; g += j0 * rp[2 * i] + j1 * rp[2 * i + 1];
-          if (cs >= 0) mask |= 1u << cs;
-          if (hs >= 0) mask |= 1u << hs;
-          if (s0 == cs) e0 += j0 * Ji[k0] + j1 * Ji[13 + k0]; else if (s0 == hs) e0 += j0 * Ji[6 + k0] + j1 * Ji[19 + k0];
-          if (s1 == cs) e1 += j0 * Ji[k1] + j1 * Ji[13 + k1]; else if (s1 == hs) e1 += j0 * Ji[6 + k1] + j1 * Ji[19 + k1];
+        const int o_end = a.vp_ptr[v + 1];
+        for (int o0 = a.vp_ptr[v]; o0 < o_end; o0 += S_CHUNK) {
+          const int cnt = min(S_CHUNK, o_end - o0);
+          int oi = 0, ocs = -1, ohs = -1;
+          if (lane < cnt) { oi = a.vp_obs[o0 + lane]; ocs = a.p_cs[oi]; ohs = a.p_hs[oi]; }
+          __syncwarp();
+          for (int q0 = 0; q0 < 28 * cnt; q0 += 32) {   // 26 Jacobian entries + 2 residuals per observation
+            const int q = q0 + lane;
+            const int k = min(q / 28, cnt - 1), e = q - 28 * k;
+            const int i = __shfl_sync(0xffffffffu, oi, k);
+            if (q < 28 * cnt) scr[q] = e < 26 ? Jp[26 * (size_t)i + e] : rp[2 * i + e - 26];
+          }
+          __syncwarp();
+          for (int k = 0; k < cnt; ++k) {
+            const int cs = __shfl_sync(0xffffffffu, ocs, k), hs = __shfl_sync(0xffffffffu, ohs, k);
+            const double* Ji = scr + 28 * k;
+            const double j0 = Ji[12], j1 = Ji[25];
+            V += j0 * j0 + j1 * j1; g += j0 * Ji[26] + j1 * Ji[27];
+            if (cs >= 0) mask |= 1u << cs;
+            if (hs >= 0) mask |= 1u << hs;
+            if (s0 == cs) e0 += j0 * Ji[k0] + j1 * Ji[13 + k0]; else if (s0 == hs) e0 += j0 * Ji[6 + k0] + j1 * Ji[19 + k0];
+            if (s1 == cs) e1 += j0 * Ji[k1] + j1 * Ji[13 + k1]; else if (s1 == hs) e1 += j0 * Ji[6 + k1] + j1 * Ji[19 + k1];
+          }
         }
         a.Ep[(size_t)v * S_EC + lane] = e0; a.Ep[(size_t)v * S_EC + lane + 32] = e1;
         if (lane == 0) { a.Vp[v] = V; a.gp[v] = g; a.maskp[v] = mask; if (first) a.sclp[v] = 1.0 / (1.0 + sqrt(V)); }
@@ -328,7 +450,7 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
         V = a.Vp[v]; g = a.gp[v]; mask = a.maskp[v];
       }
       const double sl = first ? 1.0 / (1.0 + sqrt(V)) : a.sclp[v];
-      const double Minv = 1.0 / (V + damp_unscaled(V, sl, inv_radius));
+      const double Minv = fast_rcp(V + damp_unscaled(V, sl, inv_radius));
       if (lane == 0) a.Mp[v] = Minv;
       gmax_l = fmax(gmax_l, fabs(g));
       if (n > 0 && mask) {
@@ -337,33 +459,94 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
         if (lane + 32 < n) acc[NT + lane + 32] += e1 * wg;
         sE[lane] = e0; sE[lane + 32] = e1; sW[lane] = Minv * e0; sW[lane + 32] = Minv * e1;
         const int t = __popc(mask);
-        if (lane < t) slots[lane] = __fns(mask, 0, lane + 1);
+        if (lane < t) slots[lane] = nth_set_bit(mask, lane);
         __syncwarp();
         schur_contrib<1>(acc, sE, sW, slots, t, NT, lane);
         __syncwarp();
       }
     }
-    for (int v = gw; v < a.nvt; v += GW) {
+    STAMP(14);
+    // A plane belongs to a CTA (from the far end of the grid: the first CTAs carry the inverse depths): its observation list —
+    // 25 features per keyframe that sees it — is dealt round-robin to the 8 warps, whose partial E / V / g are added in warp order by
+    // warp 0, which then eliminates the plane. (One warp per list would pay an L2 round trip per block, 25+ in a row.)
+    for (int v = a.G - 1 - (int)blockIdx.x; v < a.nvt; v += a.G) {
       double e[3][2] = {{0, 0}, {0, 0}, {0, 0}}, V[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
       unsigned mask = 0u;
       if (newJ) {
-        const int s0 = lane / 6, k0 = lane % 6, s1 = (lane + 32) / 6, k1 = (lane + 32) % 6;
-        for (int o = a.vt_ptr[v]; o < a.vt_ptr[v + 1]; ++o) {
-          const int i = a.vt_obs[o];
-          const int cs = a.camslot[a.t_cam[i]], hs = a.camslot[a.t_host[i]];
-          if (cs >= 0) mask |= 1u << cs;
-          if (hs >= 0) mask |= 1u << hs;
-          const int o0 = s0 == cs ? k0 : (s0 == hs ? 6 + k0 : -1), o1 = s1 == cs ? k1 : (s1 == hs ? 6 + k1 : -1);
-          const double* Ji = Jt + 120 * (size_t)i;
-          for (int row = 0; row < 8; ++row) {
-            const double* Jr = Ji + 15 * row;
-            const double l0 = Jr[12], l1 = Jr[13], l2 = Jr[14], rr = rt[8 * i + row];
-            V[0] += l0 * l0; V[1] += l0 * l1; V[2] += l0 * l2; V[3] += l1 * l1; V[4] += l1 * l2; V[5] += l2 * l2;
-            g[0] += l0 * rr; g[1] += l1 * rr; g[2] += l2 * rr;
-            if (o0 >= 0) { const double c = Jr[o0]; e[0][0] += l0 * c; e[1][0] += l1 * c; e[2][0] += l2 * c; }
-            if (o1 >= 0) { const double c = Jr[o1]; e[0][1] += l0 * c; e[1][1] += l1 * c; e[2][1] += l2 * c; }
+        // 45 sums over the 8 rows of a block, two per lane: E (3 x [6 camera | 6 host] columns), V (6), g (3). A lane's E sums
+        // belong to the columns of the block's camera / host slot; they are flushed into the E rows (shared memory) when that slot
+        // changes along the list (blocks of one keyframe are consecutive, the host keyframe of a plane is usually one).
+        int ia[2], ib[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int t = lane + 32 * h;
+          if (t < 36) { ia[h] = 12 + t / 12; ib[h] = t % 12; }
+          else if (t < 42) { const int k = t - 36; const int pa = k < 3 ? 0 : (k < 5 ? 1 : 2), pb = k < 3 ? k : (k < 5 ? k - 2 : 2); ia[h] = 12 + pa; ib[h] = 12 + pb; }
+          else if (t < 45) { ia[h] = 12 + (t - 42); ib[h] = 15; }
+          else { ia[h] = -1; ib[h] = 0; }
+        }
+        int offB[2], strB[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { offB[h] = ib[h] < 15 ? ib[h] : 120; strB[h] = ib[h] < 15 ? 15 : 1; }
+        for (int q = lane; q < 3 * S_EC; q += 32) sE[q] = 0.0;
+        double ac[2] = {0.0, 0.0};
+        int cur_cs = -2, cur_hs = -2;
+        const int o_beg = a.vt_ptr[v], o_end = a.vt_ptr[v + 1];
+        BlockRegs<8, 15> regs;
+        __syncwarp();
+        auto flush = [&](int slot, bool host_part) {   // add the lanes' E sums of the camera (ib < 6) or host (6 <= ib < 12) columns into row d of sE
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int t = lane + 32 * h;
+            if (t < 36 && (ib[h] >= 6) == host_part) {
+              if (slot >= 0) sE[(ia[h] - 12) * S_EC + 6 * slot + (host_part ? ib[h] - 6 : ib[h])] += ac[h];
+              ac[h] = 0.0;
+            }
+          }
+        };
+        int o = o_beg + warp, oi = 0, cs = -1, hs = -1;
+        if (o < o_end) { oi = a.vt_obs[o]; cs = a.t_cs[oi]; hs = a.t_hs[oi]; regs.load(Jt + 120 * (size_t)oi, rt + 8 * oi, lane); }
+        while (o < o_end) {
+          const int ccs = cs, chs = hs;
+          regs.store(scr, lane);
+          __syncwarp();
+          o += SW;
+          if (o < o_end) { oi = a.vt_obs[o]; cs = a.t_cs[oi]; hs = a.t_hs[oi]; regs.load(Jt + 120 * (size_t)oi, rt + 8 * oi, lane); }
+          if (ccs != cur_cs) { flush(cur_cs, false); cur_cs = ccs; }
+          if (chs != cur_hs) { flush(cur_hs, true); cur_hs = chs; }
+          if (ccs >= 0) mask |= 1u << ccs;
+          if (chs >= 0) mask |= 1u << chs;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (ia[h] < 0) continue;
+            double sacc = 0.0;
+#pragma unroll
+            for (int row = 0; row < 8; ++row) sacc += scr[15 * row + ia[h]] * scr[offB[h] + strB[h] * row];
+            ac[h] += sacc;
+          }
+          __syncwarp();
+        }
+        flush(cur_cs, false); flush(cur_hs, true);
+        // this warp's partial V, g (lanes 4..12 of the second role) and slot mask beside its partial E rows
+        if (lane >= 4 && lane < 13) sW[lane - 4] = ac[1];
+        if (lane == 0) slots[0] = (int)mask;
+        __syncthreads();
+        if (warp == 0) {
+          mask = 0u;
+          for (int w = 0; w < SW; ++w) {
+            const double* pE = s_scr + w * S_SCR + S_STG;
+            const double* pW = pE + 3 * S_EC;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { e[d][0] += pE[d * S_EC + lane]; e[d][1] += pE[d * S_EC + lane + 32]; }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) V[k] += pW[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g[k] += pW[6 + k];
+            mask |= (unsigned)reinterpret_cast<const int*>(pW + 3 * S_EC)[0];
           }
         }
+        __syncthreads();
+        if (warp != 0) continue;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { a.Et[((size_t)v * 3 + d) * S_EC + lane] = e[d][0]; a.Et[((size_t)v * 3 + d) * S_EC + lane + 32] = e[d][1]; }
         if (lane == 0) {
@@ -373,6 +556,7 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
           if (first) { a.sclt[3 * v] = 1.0 / (1.0 + sqrt(V[0])); a.sclt[3 * v + 1] = 1.0 / (1.0 + sqrt(V[3])); a.sclt[3 * v + 2] = 1.0 / (1.0 + sqrt(V[5])); }
         }
       } else {
+        if (warp != 0) continue;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { e[d][0] = a.Et[((size_t)v * 3 + d) * S_EC + lane]; e[d][1] = a.Et[((size_t)v * 3 + d) * S_EC + lane + 32]; }
         for (int k = 0; k < 6; ++k) V[k] = a.Vt[6 * (size_t)v + k];
@@ -388,7 +572,7 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
       const double c00 = md * mf - me * me, c01 = mc * me - mb * mf, c02 = mb * me - mc * md;
       const double det = ma * c00 + mb * c01 + mc * c02;
       if (!(det > 0.0) || !(ma > 0.0)) fail_l = 1.0;
-      const double id = 1.0 / det;
+      const double id = det > 0.0 ? fast_rcp(det) : 1.0 / det;
       const double Mi[6] = {c00 * id, c01 * id, c02 * id, (ma * mf - mc * mc) * id, (mb * mc - ma * me) * id, (ma * md - mb * mb) * id};
       if (lane == 0) for (int k = 0; k < 6; ++k) a.Mt[6 * (size_t)v + k] = Mi[k];
       gmax_l = fmax(gmax_l, fmax(fabs(g[0]), fmax(fabs(g[1]), fabs(g[2]))));
@@ -405,12 +589,13 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
           sW[col] = w0; sW[S_EC + col] = w1; sW[2 * S_EC + col] = w2;
         }
         const int t = __popc(mask);
-        if (lane < t) slots[lane] = __fns(mask, 0, lane + 1);
+        if (lane < t) slots[lane] = nth_set_bit(mask, lane);
         __syncwarp();
         schur_contrib<3>(acc, sE, sW, slots, t, NT, lane);
         __syncwarp();
       }
     }
+    STAMP(15);
     __syncthreads();
     for (int e = tid; e < P; e += ST) {
       double s = 0.0;
@@ -428,55 +613,66 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
         a.partG[2 * blockIdx.x] = m0; a.partG[2 * blockIdx.x + 1] = m1;
       }
     }
+    STAMP(2);
     GSYNC();
+    STAMP(3);
     // ---- fixed-order reduction over the CTAs, sliced across the grid ----
-    for (int e = blockIdx.x * ST + tid; e < P; e += a.G * ST) {
-      if (newJ) { double s = 0.0; for (int c = 0; c < a.G; ++c) s += a.partH[(size_t)c * P + e]; a.sumH[e] = s; }
-      double s = 0.0;
-      for (int c = 0; c < a.G; ++c) s += a.partS[(size_t)c * P + e];
-      a.sumS[e] = s;
+    for (int e = gw; e < P; e += GW) {   // a warp per entry: <= 5 independent loads per lane and array, then a fixed tree
+      double sh = 0.0, ss = 0.0;
+      if (newJ) for (int c = lane; c < a.G; c += 32) sh += a.partH[(size_t)c * P + e];
+      for (int c = lane; c < a.G; c += 32) ss += a.partS[(size_t)c * P + e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { sh += __shfl_xor_sync(0xffffffffu, sh, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+      if (lane == 0) { if (newJ) a.sumH[e] = sh; a.sumS[e] = ss; }
     }
     GSYNC();
+    STAMP(4);
     // ---- reduced camera system: every CTA factors it (identical arithmetic, no broadcast) ----
     double* A = s_acc;   // (n + 1) x LD, lower triangle; row n carries the right-hand side
     if (first) for (int i = tid; i < n; i += ST) s_sc[i] = 1.0 / (1.0 + sqrt(a.sumH[i * (i + 1) / 2 + i]));
     __syncthreads();
-    for (int idx = tid; idx < n * n; idx += ST) {
-      const int i = idx / n, j = idx - i * n;
-      if (j > i) continue;
-      const int e = i * (i + 1) / 2 + j;
-      const double h = a.sumH[e];
-      double v = h - a.sumS[e];
-      if (i == j) v += damp_unscaled(h, s_sc[i], inv_radius);
-      A[i * LD + j] = v;
-    }
+    const int ty = tid >> 4, tx = tid & 15;
+    for (int i = ty; i < n; i += 16)
+      for (int j = tx; j <= i; j += 16) {
+        const int e = i * (i + 1) / 2 + j;
+        const double h = a.sumH[e];
+        double v = h - a.sumS[e];
+        if (i == j) v += damp_unscaled(h, s_sc[i], inv_radius);
+        A[i * LD + j] = v;
+      }
     for (int j = tid; j < n; j += ST) A[n * LD + j] = a.sumH[NT + j] - a.sumS[NT + j];
+    if (warp == 7) { const double v0 = warp_max_ctas(a.partG, 2, a.G, lane), v1 = warp_max_ctas(a.partG + 1, 2, a.G, lane); if (lane == 0) { s_misc[6] = v0; s_misc[7] = v1; } }
     __syncthreads();
+    STAMP(5);
+    // right-looking Cholesky on the UNSCALED columns: a_ij -= a_ik a_jk / d_k needs one barrier per column; L_ik = a_ik / sqrt(d_k)
+    // is applied to all columns at once afterwards. Row n (the right-hand side) rides along: it ends as y = L^-1 b.
     int chol_fail = 0;
     for (int k = 0; k < n; ++k) {
       const double d = A[k * LD + k];
       if (!(d > 0.0)) { chol_fail = 1; break; }   // uniform: every thread reads the same value
-      const double il = 1.0 / sqrt(d);
-      __syncthreads();
-      for (int i = k + 1 + tid; i <= n; i += ST) A[i * LD + k] *= il;
-      if (tid == 0) A[k * LD + k] = sqrt(d);
-      __syncthreads();
-      const int m = n - k;   // rows k+1 .. n
-      for (int idx = tid; idx < m * m; idx += ST) {
-        const int ii = idx / m, jj = idx - ii * m;
-        const int i = k + 1 + ii, j = k + 1 + jj;
-        if (j > i || j >= n) continue;
-        A[i * LD + j] -= A[i * LD + k] * A[j * LD + k];
+      const double inv_d = fast_rcp(d);
+      {
+        const int na = (n - k + 15) >> 4;   // 16 x 16 thread tiles the trailing block needs (uniform): only those are instantiated
+        if (na == 1) chol_trail<1>(A, LD, n, k, ty, tx, inv_d);
+        else if (na == 2) chol_trail<2>(A, LD, n, k, ty, tx, inv_d);
+        else if (na == 3) chol_trail<3>(A, LD, n, k, ty, tx, inv_d);
+        else chol_trail<4>(A, LD, n, k, ty, tx, inv_d);
       }
       __syncthreads();
     }
-    double gmax = 0.0;
+    if (!chol_fail) {
+      for (int k = tid; k < n; k += ST) s_il[k] = 1.0 / sqrt(A[k * LD + k]);
+      __syncthreads();
+      for (int i = 1 + ty; i <= n; i += 16)
+        for (int j = tx; j < min(i, n); j += 16) A[i * LD + j] *= s_il[j];
+      __syncthreads();
+    }
+    STAMP(6);
     if (!chol_fail && warp == 0) {
-      // backward solve L^T u = y (row n of the workspace), columns in registers: lane holds u[lane], u[lane + 32]
+      // backward solve L^T u = y, columns in registers: lane holds u[lane], u[lane + 32]
       double y0 = lane < n ? A[n * LD + lane] : 0.0, y1 = lane + 32 < n ? A[n * LD + lane + 32] : 0.0;
       for (int k = n - 1; k >= 0; --k) {
-        const double yk = __shfl_sync(0xffffffffu, k < 32 ? y0 : y1, k & 31);
-        const double uk = yk / A[k * LD + k];
+        const double uk = __shfl_sync(0xffffffffu, k < 32 ? y0 : y1, k & 31) * s_il[k];
         if (lane == (k & 31)) { if (k < 32) y0 = uk; else y1 = uk; }
         if (lane < k) y0 -= A[k * LD + lane] * uk;
         if (lane + 32 < k) y1 -= A[k * LD + lane + 32] * uk;
@@ -485,17 +681,15 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
       if (lane + 32 < n) s_dc[lane + 32] = -y1;
     }
     __syncthreads();
-    // candidate cameras, camera part of the step / candidate norms, gradient max-norm (thread 0; cameras are few)
-    if (tid == 0) {
-      double step2 = 0.0, cn2 = 0.0, gm = 0.0, fl = 0.0;
-      for (int c = 0; c < a.G; ++c) { gm = fmax(gm, a.partG[2 * c]); fl = fmax(fl, a.partG[2 * c + 1]); }
-      for (int k = 0; k < K; ++k) {
-        const int s = a.camslot[k];
-        const double* xk = s_cams[cur] + 7 * k;
-        double* ok = s_cams[cur ^ 1] + 7 * k;
-        if (s < 0) { for (int c = 0; c < 7; ++c) ok[c] = xk[c]; continue; }
+    // candidate cameras, camera part of the step / candidate norms, gradient max-norm: a thread per camera, then slot order
+    if (tid < K) {
+      const int k = tid, sl = s_slot[k];
+      const double* xk = s_cams[cur] + 7 * k;
+      double* ok = s_cams[cur ^ 1] + 7 * k;
+      if (sl < 0) { for (int c = 0; c < 7; ++c) ok[c] = xk[c]; }
+      else {
         {   // ||x - Plus(x, -g)||_inf with the unscaled gradient
-          const double* gr = a.sumH + NT + 6 * s;
+          const double* gr = a.sumH + NT + 6 * sl;
           const double d[3] = {-gr[0], -gr[1], -gr[2]};
           const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
           double m = 0.0;
@@ -509,28 +703,37 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
             m = fmax(fmax(fabs(xk[0] - q0), fabs(xk[1] - q1)), fmax(fabs(xk[2] - q2), fabs(xk[3] - q3)));
           }
           for (int c = 3; c < 6; ++c) m = fmax(m, fabs(gr[c]));
-          gm = fmax(gm, m);
+          s_cam3[sl] = m;
         }
-        if (chol_fail) continue;
-        const double* d = s_dc + 6 * s;
-        const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        double q[4];
-        if (nrm > 0.0) {
-          const double sn = sin(nrm) / nrm;
-          const double z0 = cos(nrm), z1 = sn * d[0], z2 = sn * d[1], z3 = sn * d[2];
-          q[0] = z0 * xk[0] - z1 * xk[1] - z2 * xk[2] - z3 * xk[3];
-          q[1] = z0 * xk[1] + z1 * xk[0] + z2 * xk[3] - z3 * xk[2];
-          q[2] = z0 * xk[2] - z1 * xk[3] + z2 * xk[0] + z3 * xk[1];
-          q[3] = z0 * xk[3] + z1 * xk[2] - z2 * xk[1] + z3 * xk[0];
-        } else { q[0] = xk[0]; q[1] = xk[1]; q[2] = xk[2]; q[3] = xk[3]; }
-        for (int c = 0; c < 4; ++c) { ok[c] = q[c]; const double df = xk[c] - q[c]; step2 += df * df; cn2 += q[c] * q[c]; }
-        for (int c = 0; c < 3; ++c) { const double v = xk[4 + c] + d[3 + c]; ok[4 + c] = v; step2 += d[3 + c] * d[3 + c]; cn2 += v * v; }
+        double step2 = 0.0, cn2 = 0.0;
+        if (!chol_fail) {
+          const double* d = s_dc + 6 * sl;
+          const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+          double q[4];
+          if (nrm > 0.0) {
+            const double sn = sin(nrm) / nrm;
+            const double z0 = cos(nrm), z1 = sn * d[0], z2 = sn * d[1], z3 = sn * d[2];
+            q[0] = z0 * xk[0] - z1 * xk[1] - z2 * xk[2] - z3 * xk[3];
+            q[1] = z0 * xk[1] + z1 * xk[0] + z2 * xk[3] - z3 * xk[2];
+            q[2] = z0 * xk[2] - z1 * xk[3] + z2 * xk[0] + z3 * xk[1];
+            q[3] = z0 * xk[3] + z1 * xk[2] - z2 * xk[1] + z3 * xk[0];
+          } else { q[0] = xk[0]; q[1] = xk[1]; q[2] = xk[2]; q[3] = xk[3]; }
+          for (int c = 0; c < 4; ++c) { ok[c] = q[c]; const double df = xk[c] - q[c]; step2 += df * df; cn2 += q[c] * q[c]; }
+          for (int c = 0; c < 3; ++c) { const double v = xk[4 + c] + d[3 + c]; ok[4 + c] = v; step2 += d[3 + c] * d[3 + c]; cn2 += v * v; }
+        }
+        s_cam3[16 + sl] = step2; s_cam3[32 + sl] = cn2;
       }
-      s_misc[0] = step2; s_misc[1] = cn2; s_misc[2] = gm; s_misc[3] = fl;
     }
     __syncthreads();
+    if (tid == 0) {
+      double step2 = 0.0, cn2 = 0.0, gm = s_misc[6];
+      for (int sl = 0; sl < a.nc; ++sl) { gm = fmax(gm, s_cam3[sl]); step2 += s_cam3[16 + sl]; cn2 += s_cam3[32 + sl]; }
+      s_misc[0] = step2; s_misc[1] = cn2; s_misc[2] = gm; s_misc[3] = s_misc[7];
+    }
+    __syncthreads();
+    STAMP(7);
     const double step2_c = s_misc[0], cn2_c = s_misc[1];
-    gmax = s_misc[2];
+    const double gmax = s_misc[2];
     const bool lin_fail = chol_fail || s_misc[3] != 0.0;
     __syncthreads();
     if (gmax <= a.gtol) { term = TSLAM_TERM_GRADIENT_TOL; break; }   // Ceres tests the gradient before it computes a step
@@ -553,7 +756,7 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
           st2 += dl * dl; c2 += xn * xn;
         }
       }
-      for (int v = gw; v < a.nvt; v += GW) {
+      for (int v = GW - 1 - gw; v < a.nvt; v += GW) {
         double t[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -580,12 +783,14 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
         if (lane == 0) { s_red[2 * warp] = st2; s_red[2 * warp + 1] = c2; }
         __syncthreads();
         if (tid == 0) { double s0 = 0.0, s1 = 0.0; for (int w = 0; w < SW; ++w) { s0 += s_red[2 * w]; s1 += s_red[2 * w + 1]; } s_misc[4] = s0; s_misc[5] = s1; }
+        STAMP(8);
         GSYNC();
       } else if (tid == 0) { s_misc[4] = 0.0; s_misc[5] = 0.0; }
+      STAMP(9);
       // ---- model cost change -(J d)'(r + J d / 2) and the candidate evaluation (with its Jacobian, speculatively) ----
       double v[3] = {0.0, 0.0, 0.0};
       for (int i = blockIdx.x * ST + tid; i < a.lp; i += a.G * ST) {
-        const int cs = a.camslot[a.p_cam[i]], hs = a.camslot[a.p_host[i]], ls = a.p_ls[i];
+        const int cs = a.p_cs[i], hs = a.p_hs[i], ls = a.p_ls[i];
         if (cs < 0 && hs < 0 && ls < 0) continue;
         const double* Ji = Jp + 26 * (size_t)i;
         const double dl = ls >= 0 ? a.dlp[ls] : 0.0;
@@ -599,7 +804,7 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
       }
       for (int gpx = blockIdx.x * ST + tid; gpx < 8 * a.lt; gpx += a.G * ST) {
         const int b = gpx >> 3;
-        const int cs = a.camslot[a.t_cam[b]], hs = a.camslot[a.t_host[b]], ls = a.t_ls[b];
+        const int cs = a.t_cs[b], hs = a.t_hs[b], ls = a.t_ls[b];
         if (cs < 0 && hs < 0 && ls < 0) continue;
         const double* Jr = Jt + 15 * (size_t)gpx;
         double m = 0.0;
@@ -608,19 +813,23 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
         if (hs >= 0) for (int k = 0; k < 6; ++k) m += Jr[6 + k] * s_dc[6 * hs + k];
         v[0] -= m * (rt[gpx] + m * 0.5);
       }
+      STAMP(10);
       eval_pass<true>(a, s_cams[cur ^ 1], a.rho[cur ^ 1], a.theta[cur ^ 1], a.rp[cur ^ 1], a.Jp[cur ^ 1], a.rt[cur ^ 1], a.Jt[cur ^ 1], v[1], v[2]);
       block_sums<3>(v, s_red);
       if (tid == 0) {
         double* o = a.part + S_NPART * blockIdx.x;
         o[0] = s_misc[4]; o[1] = s_misc[5]; o[2] = v[0]; o[3] = v[1]; o[4] = v[2];
       }
+      STAMP(11);
       GSYNC();
-      if (tid < 5) { double s = 0.0; for (int c = 0; c < a.G; ++c) s += a.part[S_NPART * c + tid]; s_misc[8 + tid] = s; }
+      STAMP(12);
+      if (warp < 5) { const double v = warp_sum_ctas(a.part + warp, S_NPART, a.G, lane); if (lane == 0) s_misc[8 + warp] = v; }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < 5; ++k) sums[k] = s_misc[8 + k];
       __syncthreads();
     }
+    STAMP(13);
     // ---- accept / reject (run_lm of ba_solve.cu, statement for statement) ----
     const double mcc = sums[2], cand_cost = sums[3], step_norm = sqrt(step2_c + sums[0]);
     const bool finite = isfinite(mcc) && isfinite(cand_cost) && isfinite(step_norm);
@@ -678,8 +887,8 @@ __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
   }
   for (int i = blockIdx.x * ST + tid; i < a.n_points; i += a.G * ST) o_rho[i] = a.rho[cur][i];
   for (int i = blockIdx.x * ST + tid; i < 3 * a.n_planes; i += a.G * ST) o_theta[i] = a.theta[cur][i];
-  for (int i = blockIdx.x * ST + tid; i < 2 * a.lp; i += a.G * ST) a.r_final[i] = a.rp[cur][i];
-  for (int i = blockIdx.x * ST + tid; i < 8 * a.lt; i += a.G * ST) a.r_final[2 * a.lp + i] = a.rt[cur][i];
+  for (int i = blockIdx.x * ST + tid; i < 2 * a.lp; i += a.G * ST) a.r_final_p[i] = a.rp[cur][i];
+  for (int i = blockIdx.x * ST + tid; i < 8 * a.lt; i += a.G * ST) a.r_final_t[i] = a.rt[cur][i];
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -738,7 +947,9 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   for (int c : cntP) if (c > S_MAX_LIST) return TSLAM_OK;
   for (int c : cntT) if (c > S_MAX_LIST) return TSLAM_OK;
   const int n = 6 * nc, NT = n * (n + 1) / 2, P = NT + n;
-  int G = (lp + 8 * lt + ST - 1) / ST;
+  // one CTA per SM as soon as there is work for it: the per-warp lists (observations to accumulate, landmarks to eliminate) are what
+  // an iteration waits for, and they shrink with the number of warps
+  int G = (lp + lt + nvp + nvt + 7) / 8;
   G = std::max(1, std::min(G, std::min(S_MAX_G, ctx->sm_count)));
   const int max_iters = opt->max_iters;
 
@@ -749,6 +960,7 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   const size_t o_puv = in.take(sizeof(double) * 2 * lp), o_pray = in.take(sizeof(double) * 2 * lp);
   const size_t o_trays = in.take(sizeof(double) * 16 * lt), o_tiref = in.take(sizeof(double) * 8 * lt), o_tms = in.take(sizeof(double) * 2 * lt);
   const size_t o_pcam = in.take(4 * (size_t)lp), o_phost = in.take(4 * (size_t)lp), o_plm = in.take(4 * (size_t)lp), o_pls = in.take(4 * (size_t)lp);
+  const size_t o_pcs = in.take(4 * (size_t)lp), o_phs = in.take(4 * (size_t)lp), o_tcs = in.take(4 * (size_t)lt), o_ths = in.take(4 * (size_t)lt);
   const size_t o_tcam = in.take(4 * (size_t)lt), o_thost = in.take(4 * (size_t)lt), o_tpl = in.take(4 * (size_t)lt), o_timg = in.take(4 * (size_t)lt), o_tls = in.take(4 * (size_t)lt);
   const size_t o_slot = in.take(4 * (size_t)K);
   const size_t o_vpptr = in.take(4 * (size_t)(nvp + 1)), o_vpobs = in.take(4 * (size_t)lp), o_vpgl = in.take(4 * (size_t)nvp);
@@ -765,13 +977,18 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   const size_t o_maskp = dv.take(4 * (size_t)nvp), o_maskt = dv.take(4 * (size_t)nvt);
   const size_t o_partH = dv.take(8 * (size_t)G * P), o_partS = dv.take(8 * (size_t)G * P), o_sumH = dv.take(8 * (size_t)P), o_sumS = dv.take(8 * (size_t)P);
   const size_t o_part0 = dv.take(8 * (size_t)G * 4), o_partG = dv.take(8 * (size_t)G * 2), o_part = dv.take(8 * (size_t)G * S_NPART);
-  const size_t out_doubles = OUT_HDR + 4 * (size_t)(max_iters + 2) + 7 * (size_t)K + NP + 3 * (size_t)NPL + 2 * (size_t)lp + 8 * (size_t)lt;
-  const size_t o_out = dv.take(8 * out_doubles);
+  // result block: [summary + trace + parameters | point residuals | text residuals], three 16-byte aligned segments copied back at once
+  // (the chi^2 gate kernels read the residual segments with vector loads)
+  const size_t par_doubles = OUT_HDR + 4 * (size_t)(max_iters + 2) + 7 * (size_t)K + NP + 3 * (size_t)NPL;
+  const size_t o_out = dv.take(8 * par_doubles), o_frp = dv.take(8 * 2 * (size_t)lp), o_frt = dv.take(8 * 8 * (size_t)lt);
+  const size_t out_bytes = dv.off - o_out;
+  const bool prof = getenv("TSLAM_SMALL_PROF") != nullptr;
+  const size_t o_prof = dv.take(prof ? 8 * 16 * 16 : 0);
   const size_t dev_bytes = dv.off;
 
   if (!ctx->small_ws) ctx->small_ws = new SmallWorkspace();
   SmallWorkspace& W = *static_cast<SmallWorkspace*>(ctx->small_ws);
-  const size_t stage_need = std::max(in_bytes, 8 * out_doubles);
+  const size_t stage_need = std::max(in_bytes, out_bytes);
   if (W.h_cap < stage_need) {
     if (W.h_stage) { TSL_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFreeHost(W.h_stage); W.h_stage = nullptr; W.h_cap = 0; }
     const size_t cap = stage_need + stage_need / 2;
@@ -792,6 +1009,9 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   puti(o_tcam, p->t_cam, lt); puti(o_thost, p->t_host, lt); puti(o_tpl, p->t_plane, lt); puti(o_timg, p->t_img, lt);
   puti(o_slot, camslot.data(), K);
   {
+    int32_t *pcs = reinterpret_cast<int32_t*>(hs + o_pcs), *phs = reinterpret_cast<int32_t*>(hs + o_phs), *tcs = reinterpret_cast<int32_t*>(hs + o_tcs), *ths = reinterpret_cast<int32_t*>(hs + o_ths);
+    for (int i = 0; i < lp; ++i) { pcs[i] = camslot[p->p_cam[i]]; phs[i] = camslot[p->p_host[i]]; }
+    for (int i = 0; i < lt; ++i) { tcs[i] = camslot[p->t_cam[i]]; ths[i] = camslot[p->t_host[i]]; }
     int32_t* pls = reinterpret_cast<int32_t*>(hs + o_pls);
     int32_t* vptr = reinterpret_cast<int32_t*>(hs + o_vpptr); int32_t* vobs = reinterpret_cast<int32_t*>(hs + o_vpobs); int32_t* vgl = reinterpret_cast<int32_t*>(hs + o_vpgl);
     vptr[0] = 0;
@@ -815,7 +1035,7 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   auto D = [&](size_t off) { return reinterpret_cast<double*>(db + off); };
   auto I = [&](size_t off) { return reinterpret_cast<int*>(db + off); };
   a.p_uv = reinterpret_cast<const double2*>(db + o_puv); a.p_ray = reinterpret_cast<const double2*>(db + o_pray);
-  a.p_cam = I(o_pcam); a.p_host = I(o_phost); a.p_lm = I(o_plm); a.p_ls = I(o_pls);
+  a.p_cam = I(o_pcam); a.p_host = I(o_phost); a.p_lm = I(o_plm); a.p_ls = I(o_pls); a.p_cs = I(o_pcs); a.p_hs = I(o_phs); a.t_cs = I(o_tcs); a.t_hs = I(o_ths);
   a.t_rays = reinterpret_cast<const double2*>(db + o_trays); a.t_musigma = reinterpret_cast<const double2*>(db + o_tms); a.t_iref = D(o_tiref);
   a.t_cam = I(o_tcam); a.t_host = I(o_thost); a.t_plane = I(o_tpl); a.t_img = I(o_timg); a.t_ls = I(o_tls);
   a.imgs = db + o_img; a.img_w = p->img_w; a.img_h = p->img_h;
@@ -832,7 +1052,9 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   a.partH = D(o_partH); a.partS = D(o_partS); a.sumH = D(o_sumH); a.sumS = D(o_sumS); a.part0 = D(o_part0); a.partG = D(o_partG); a.part = D(o_part);
   a.sync = I(o_sync);
   a.out = D(o_out);
-  a.r_final = a.out + OUT_HDR + 4 * (size_t)(max_iters + 2) + 7 * (size_t)K + NP + 3 * (size_t)NPL;
+  a.prof = prof ? reinterpret_cast<long long*>(db + o_prof) : nullptr;
+  if (prof) TSL_CUDA(cudaMemsetAsync(db + o_prof, 0, 8 * 16 * 16, st));
+  a.r_final_p = D(o_frp); a.r_final_t = D(o_frt);
   a.K = K; a.nc = nc; a.n = n; a.lp = lp; a.lt = lt; a.nvp = nvp; a.nvt = nvt; a.n_points = NP; a.n_planes = NPL; a.G = G; a.max_iters = max_iters;
   a.ftol = opt->function_tolerance > 0 ? opt->function_tolerance : 1e-6;
   a.gtol = opt->gradient_tolerance > 0 ? opt->gradient_tolerance : 1e-10;
@@ -840,7 +1062,7 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   a.radius0 = opt->initial_radius > 0 ? opt->initial_radius : 1e4;
 
   const size_t acc_doubles = std::max((size_t)SW * P, (size_t)(n + 1) * (n + 1));
-  const size_t smem = sizeof(double) * (14 * (size_t)K + 64 + 64 + 32 + 64 + (size_t)SW * S_SCR + acc_doubles);
+  const size_t smem = sizeof(double) * (14 * (size_t)K + 64 + 64 + 32 + 64 + 64 + 48 + 128 + (size_t)SW * S_SCR + acc_doubles);
   if (!W.attr_set || W.attr_smem < smem) {
     TSL_CUDA(cudaFuncSetAttribute(ba_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     W.attr_set = true; W.attr_smem = 220 * 1024;
@@ -855,11 +1077,22 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
     ++g_launches;
     TSL_CUDA(cudaLaunchKernelEx(&cfg, ba_small_kernel, a));
   }
-  TSL_CUDA(cudaMemcpyAsync(hs, db + o_out, 8 * out_doubles, cudaMemcpyDeviceToHost, st));
+  TSL_CUDA(cudaMemcpyAsync(hs, db + o_out, out_bytes, cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaStreamSynchronize(st));
   auto T2 = std::chrono::steady_clock::now();
   const double* out = reinterpret_cast<const double*>(hs);
-  if (out[OUT_ABORT] != 0.0) return set_error(TSLAM_ERR_CUDA, "small-problem solve: a grid barrier timed out");
+  if (prof) {   // phase laps of CTA 0 in SM clock cycles (stamps: see STAMP() in the kernel)
+    std::vector<long long> pr(16 * 16);
+    TSL_CUDA(cudaMemcpy(pr.data(), db + o_prof, 8 * 16 * 16, cudaMemcpyDeviceToHost));
+    static const int order[15] = {1, 14, 15, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13};
+    static const char* names[15] = {"accumH", "zero+points", "planes", "partS", "bar2", "slice+bar3", "build", "chol", "solve+cams", "backsub", "bar4", "mcc", "eval", "bar5", "sums"};
+    for (int it = 0; it < 16 && pr[16 * it]; ++it) {
+      fprintf(stderr, "[small prof] trip %d (G=%d):", it, G);
+      int prev = 0;
+      for (int k = 0; k < 15; ++k) if (pr[16 * it + order[k]]) { fprintf(stderr, " %s %lld", names[k], pr[16 * it + order[k]] - pr[16 * it + prev]); prev = order[k]; }
+      fprintf(stderr, "\n");
+    }
+  }
   tslam_solve_summary sum{};
   sum.iterations = (int)out[OUT_ITER]; sum.successful_steps = (int)out[OUT_OK]; sum.unsuccessful_steps = (int)out[OUT_BAD]; sum.termination = (int)out[OUT_TERM];
   sum.initial_cost = out[OUT_INIT]; sum.final_cost = out[OUT_FINAL]; sum.fixed_cost = out[OUT_FIXED];
@@ -870,9 +1103,12 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   memcpy(p->cams, oc, sizeof(double) * 7 * (size_t)K);
   if (NP) memcpy(p->rho, oc + 7 * (size_t)K, sizeof(double) * NP);
   if (NPL) memcpy(p->theta, oc + 7 * (size_t)K + NP, sizeof(double) * 3 * (size_t)NPL);
-  if (final_residuals) memcpy(final_residuals, oc + 7 * (size_t)K + NP + 3 * (size_t)NPL, sizeof(double) * (2 * (size_t)lp + 8 * (size_t)lt));
-  if (d_rp) *d_rp = a.r_final;
-  if (d_rt) *d_rt = a.r_final + 2 * (size_t)lp;
+  if (final_residuals) {
+    if (lp) memcpy(final_residuals, hs + (o_frp - o_out), sizeof(double) * 2 * (size_t)lp);
+    if (lt) memcpy(final_residuals + 2 * (size_t)lp, hs + (o_frt - o_out), sizeof(double) * 8 * (size_t)lt);
+  }
+  if (d_rp) *d_rp = a.r_final_p;
+  if (d_rt) *d_rt = a.r_final_t;
   auto T3 = std::chrono::steady_clock::now();
   sum.setup_ms = std::chrono::duration<double, std::milli>(T1 - T0).count();
   sum.solve_ms = std::chrono::duration<double, std::milli>(T2 - T1).count();

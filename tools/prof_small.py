@@ -22,6 +22,10 @@ for name, prob in (("c3", synth.c3_pose_only(seed=0)), ("c4", synth.c4_local_ba(
             s, _, _ = ctx.solve(c, 10, want_trace=False)
         dt = (time.perf_counter() - t0) / 20
         print(f"{name} {kind}: wall {1e3*dt:.3f} ms/solve, C-ABI total_ms {s['total_ms']:.3f} setup_ms {s['setup_ms']:.3f} solve_ms {s['solve_ms']:.3f} its {s['iterations']}", flush=True)
+    os.environ["TSLAM_SMALL_PROF"] = "1"
+    ctx.solve(prob.copy(), 10, want_trace=False)
+    sys.stderr.flush()
+    os.environ.pop("TSLAM_SMALL_PROF")
     dev = ctx.upload(prob)
     for _ in range(3):
         ph, s = dev.lm_iterations(10)
