@@ -437,20 +437,73 @@ def main():
 
 
 def small_problem_bench(ctx, T, synth, po, threads):
-    """C3 pose-only and C4 local BA (BASELINE.json configs 2-3): 10 LM iterations per call, host buffers, vs the oracle."""
+    """C3 pose-only and C4 local BA (BASELINE.json configs 2-3): one pyramid level = one tslam_solve call with HOST buffers
+    (10 LM iterations allowed), through the persistent small-problem kernel (csrc/ba_small.cu) and, beside it, through the general
+    path (TSLAM_SMALL=0) and the single-threaded oracle; then the reference's three-level PoseOptim loop with its chi^2 gates
+    (src/optimizer.cc:172-186) end to end."""
+    import torch
+    from textslam_b200.api import PyramidLevel, run_pyramid
     out = {}
+
+    def timed(prob_of, n=20):
+        cps = [prob_of() for _ in range(n + 3)]
+        for c in cps[:3]:
+            summ, _, _ = ctx.solve(c, 10, want_trace=False)
+        t0 = time.perf_counter(); inner = 0.0
+        for c in cps[3:]:
+            summ, _, _ = ctx.solve(c, 10, want_trace=False)
+            inner += summ["total_ms"]
+        return 1e3 * (time.perf_counter() - t0) / n, inner / n, summ
+
     for name, prob in (("c3_pose_only_2k_pts_250_text", synth.c3_pose_only(seed=0)), ("c4_local_ba_10kf_3k_pts_750_text", synth.c4_local_ba(seed=0))):
-        for _ in range(2):
-            ctx.solve(prob.copy(), 10, want_trace=False)
-        t0 = time.perf_counter(); n = 10
-        for _ in range(n):
-            summ, _, _ = ctx.solve(prob.copy(), 10, want_trace=False)
-        gpu_ms = 1e3 * (time.perf_counter() - t0) / n
+        wall, inner, summ = timed(prob.copy)
+        wall_pin, inner_pin, _ = timed(lambda: pinned_copy(prob, torch))
+        os.environ["TSLAM_SMALL"] = "0"
+        try:
+            wall_gen, inner_gen, sgen = timed(prob.copy)
+        finally:
+            os.environ.pop("TSLAM_SMALL", None)
         t0 = time.perf_counter()
         so, _, _ = po.solve(prob.copy(), 10, n_threads=1, want_trace=False)
         cpu_ms = 1e3 * (time.perf_counter() - t0)
-        out[name] = {"gpu_ms_per_solve_e2e": gpu_ms, "lm_iterations": summ["iterations"], "oracle_1thread_ms_per_solve": cpu_ms,
-                     "oracle_iterations": so["iterations"]}
+        out[name] = {"gpu_ms_per_solve_e2e": wall, "gpu_ms_per_solve_inside_the_c_abi": inner, "gpu_ms_per_solve_e2e_pinned_host_buffers": wall_pin,
+                     "general_path_ms_per_solve_e2e": wall_gen, "lm_iterations": summ["iterations"], "general_path_lm_iterations": sgen["iterations"],
+                     "oracle_1thread_ms_per_solve": cpu_ms, "oracle_iterations": so["iterations"],
+                     "note": "e2e = wall clock around Context.solve (ctypes marshalling included); kernel launches per solve: 1"}
+
+    # three-level PoseOptim (levels 2, 1, 0; gates 12.25 / 0.5, 0.5, 0.95; 10 iterations each)
+    def levels():
+        lv = []
+        for l in (2, 1, 0):
+            p = synth.c3_pose_only(seed=5, level=l)
+            lv.append(PyramidLevel(p, t_obj=p.t_plane.copy(), t_feat=np.tile(np.arange(25), len(p.theta))))
+        return lv
+
+    def flags(lv):
+        n_obj = len(lv[0].prob.theta)
+        return np.ones(lv[0].prob.n_pobs, bool), np.ones(n_obj, bool), np.ones((n_obj, 25), bool)
+
+    def oracle_gated(prob, gate, t_obj, obj_size, max_iters):
+        summ, fr, tr = po.solve(prob, max_iters, n_threads=1, want_trace=False)
+        pb, tb, ob, cnt = po.gate_residuals(fr, prob.n_pobs, prob.n_tobs, gate, t_obj, obj_size)
+        return summ, fr, tr, pb, tb, ob, cnt
+
+    opt = T.Optimizer(ctx)
+    for _ in range(3):
+        lv = levels(); opt.PoseOptim(lv, 10, *flags(lv))
+    sets = [levels() for _ in range(10)]
+    t0 = time.perf_counter()
+    for lv in sets:
+        res = opt.PoseOptim(lv, 10, *flags(lv))
+    gpu_ms = 1e3 * (time.perf_counter() - t0) / len(sets)
+    lv = levels()
+    t0 = time.perf_counter()
+    ro = run_pyramid(oracle_gated, lv, (12.25,) * 3, (0.5, 0.5, 0.95), (10,) * 3, *flags(lv))
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    out["pose_optim_3_levels"] = {"workload": "optimizer::PoseOptim: levels 2, 1, 0 of C3 (2000 point + 250 text blocks each), chi^2 gates between the levels",
+                                  "gpu_ms_e2e": gpu_ms, "oracle_1thread_ms": cpu_ms, "lm_iterations": [r["summary"]["iterations"] for r in res],
+                                  "oracle_lm_iterations": [r["summary"]["iterations"] for r in ro],
+                                  "note": "includes the Python level loop (sub-problem assembly in numpy) on both sides"}
     return out
 
 

@@ -553,6 +553,9 @@ __global__ void __launch_bounds__(128) schur_block_kernel(BlockArgs A, const int
 }
 
 // Diagonal blocks (a CTA each) and off-diagonal blocks (8 lanes each) in ONE launch: CTAs [0, n_diag) take the diagonal list.
+// Measured and rejected in round 2 (profiles/r2_notes.md): 3 or 4 CTAs per SM through __launch_bounds__ (168 / 128 registers with
+// spills: 55.3 / 68.4 us against 54.7), and an output-stationary variant (a lane per block entry, gather lists staged through
+// shared memory with coalesced loads, no final shuffle reduction: 95 us — 7x the instructions per gather entry).
 __global__ void __launch_bounds__(128) schur_merged_kernel(BlockArgs A, const int* __restrict__ diag_list, int n_diag,
                                                            const int* __restrict__ off_list, int n_off) {
   PDL_PROLOGUE();
