@@ -82,6 +82,10 @@ struct tslam_orb {
   tsl::DevBuf<uint8_t> desc;
   tsl::DevBuf<int> counts;
   int last_n = 0;
+  // second stream: the 7x7 Gaussian of every level (needed by the descriptors only) runs beside the quad-tree distribution, whose one CTA
+  // of 8 warps per SM (115 KB of shared memory each) leaves the SMs mostly idle
+  cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~tslam_orb() { if (s2) cudaStreamDestroy(s2); if (ev_fork) cudaEventDestroy(ev_fork); if (ev_join) cudaEventDestroy(ev_join); }
 };
 
 namespace tsl {
@@ -805,13 +809,26 @@ static int orb_run(tslam_orb* o, int n) {
     else LAUNCH(fast_score_kernel<true><<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
     LAUNCH(cell_nms_kernel<<<dim3(li.ncells, n), 128, 0, st>>>(o->score.p, o->img_bytes, o->Ld.p, l, o->cells.p, o->total_cells, o->iniTh, o->minTh,
                                                                  o->slots.p, o->cell_count.p, o->err.p));
-    dim3 bgrid((li.w + 31) / 32, (li.h + 7) / 8, n);
-    LAUNCH(blur7_kernel<<<bgrid, 256, 0, st>>>(o->pyr.p, o->blur.p, o->img_bytes, li.plane_off, li.w, li.h, T[0], T[1], T[2], T[3]));
   }
+  TSL_CHECK_LAUNCH();
+  static const bool overlap = [] { const char* e = getenv("TSLAM_ORB_OVERLAP"); return !(e && e[0] == '0'); }();
+  if (overlap && !o->s2) {
+    TSL_CUDA(cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking));
+    TSL_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming)); TSL_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t sb = overlap ? o->s2 : st;
+  if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_fork, st)); TSL_CUDA(cudaStreamWaitEvent(sb, o->ev_fork, 0)); }
+  for (int l = 0; l < o->nlevels; ++l) {
+    const LevelInfo& li = o->L[l];
+    dim3 bgrid((li.w + 31) / 32, (li.h + 7) / 8, n);
+    LAUNCH(blur7_kernel<<<bgrid, 256, 0, sb>>>(o->pyr.p, o->blur.p, o->img_bytes, li.plane_off, li.w, li.h, T[0], T[1], T[2], T[3]));
+  }
+  if (overlap) TSL_CUDA(cudaEventRecord(o->ev_join, sb));
   TSL_CHECK_LAUNCH();
   LAUNCH(distribute_kernel<<<dim3(o->nlevels, n), 256, sizeof(DistSmem), st>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
                                                                                 o->sel.p, o->sel_count.p, o->sel_cap, o->nlevels, o->err.p));
   LAUNCH(counts_kernel<<<(n + 127) / 128, 128, 0, st>>>(o->sel_count.p, o->nlevels, o->out_cap, o->counts.p, n));
+  if (overlap) TSL_CUDA(cudaStreamWaitEvent(st, o->ev_join, 0));
   const int warps = o->nlevels * o->sel_cap;
   LAUNCH(orient_describe_kernel<<<dim3((warps * 32 + 127) / 128, n), 128, 0, st>>>(o->pyr.p, o->blur.p, o->img_bytes, o->Ld.p, o->nlevels, o->sel.p,
                                                                                     o->sel_count.p, o->sel_cap, o->out_cap, o->kp.p, o->desc.p, o->counts.p, o->err.p));

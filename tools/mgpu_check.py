@@ -1,6 +1,7 @@
 """Multi-GPU global BA check (run under torchrun, one rank per GPU): the landmark-sharded solve with one NCCL
 all-reduce per LM iteration must reproduce the single-GPU solve (same iteration sequence, parameters to 1e-8)."""
 import os, sys, json, time
+os.environ["TSLAM_SMALL"] = "0"   # the sharded solve runs the general path: the single-GPU reference takes the same one
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
