@@ -84,8 +84,13 @@ struct tslam_orb {
   int last_n = 0;
   // second stream: the 7x7 Gaussian of every level (needed by the descriptors only) runs beside the quad-tree distribution, whose one CTA
   // of 8 warps per SM (115 KB of shared memory each) leaves the SMs mostly idle
-  cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  ~tslam_orb() { if (s2) cudaStreamDestroy(s2); if (ev_fork) cudaEventDestroy(ev_fork); if (ev_join) cudaEventDestroy(ev_join); }
+  cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_level[16] = {};
+  ~tslam_orb() {
+    if (s2) cudaStreamDestroy(s2);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    for (cudaEvent_t e : ev_level) if (e) cudaEventDestroy(e);
+  }
 };
 
 namespace tsl {
@@ -317,10 +322,10 @@ __device__ __forceinline__ int quadrant_of(float x, float y, int mx, int my) {
 __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __restrict__ Ld, int total_cells, const uint32_t* __restrict__ slots,
                                                          const int* __restrict__ cell_count, unsigned short* __restrict__ node_of,
                                                          uint8_t* __restrict__ kq, uint32_t* __restrict__ sel, int* __restrict__ sel_count,
-                                                         int sel_cap, int nlevels, int* __restrict__ err) {
+                                                         int sel_cap, int nlevels, int* __restrict__ err, int level0) {
   extern __shared__ unsigned char dist_raw[];
   DistSmem& S = *reinterpret_cast<DistSmem*>(dist_raw);
-  const int level = blockIdx.x, img = blockIdx.y;
+  const int level = level0 + blockIdx.x, img = blockIdx.y;
   const LevelInfo li = Ld[level];
   const int N = li.nfeat;
   const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -801,6 +806,17 @@ static int orb_run(tslam_orb* o, int n) {
   }
   static const int T0[4] = {18, 34, 48, 56}, T1[4] = {18, 34, 49, 55};
   const int* T = o->blur_variant == 1 ? T1 : T0;
+  // Two streams. The quad-tree distribution of a level (64 CTAs of 8 warps holding 115 KB of shared memory each: latency bound, one
+  // per SM) starts on the second stream as soon as that level's candidates exist, and runs beside the FAST / NMS kernels of the next
+  // levels and beside the 7x7 Gaussian (which only the descriptors need); the streams join before orient_describe_kernel.
+  static const bool overlap = [] { const char* e = getenv("TSLAM_ORB_OVERLAP"); return !(e && e[0] == '0'); }();
+  if (overlap && !o->s2) {
+    TSL_CUDA(cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking));
+    TSL_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming)); TSL_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
+    for (int l = 0; l < 16; ++l) TSL_CUDA(cudaEventCreateWithFlags(&o->ev_level[l], cudaEventDisableTiming));
+  }
+  if (o->nlevels > 16) return set_error(TSLAM_ERR_ARG, "more than 16 pyramid levels");
+  cudaStream_t sd = overlap ? o->s2 : st;
   for (int l = 0; l < o->nlevels; ++l) {
     const LevelInfo& li = o->L[l];
     dim3 grid((li.w + 127) / 128, li.h, n);
@@ -809,26 +825,26 @@ static int orb_run(tslam_orb* o, int n) {
     else LAUNCH(fast_score_kernel<true><<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
     LAUNCH(cell_nms_kernel<<<dim3(li.ncells, n), 128, 0, st>>>(o->score.p, o->img_bytes, o->Ld.p, l, o->cells.p, o->total_cells, o->iniTh, o->minTh,
                                                                  o->slots.p, o->cell_count.p, o->err.p));
+    // two groups: the two finest levels (most candidates, the longest quad-tree loops) as soon as they are ready — they run beside
+    // the FAST / NMS passes of the coarser levels —, the rest beside the Gaussian. (One launch per level serialises eight
+    // latency-bound 64-CTA grids on the second stream: 3.46 ms per batch; one launch for all levels after the last NMS: 2.84 ms.)
+    const int split = o->nlevels > 2 ? 2 : o->nlevels;
+    if (l == split - 1 || l == o->nlevels - 1) {
+      const int l0 = l == split - 1 ? 0 : split;
+      if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_level[l], st)); TSL_CUDA(cudaStreamWaitEvent(sd, o->ev_level[l], 0)); }
+      if (l - l0 + 1 > 0)
+        LAUNCH(distribute_kernel<<<dim3(l - l0 + 1, n), 256, sizeof(DistSmem), sd>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
+                                                                                      o->sel.p, o->sel_count.p, o->sel_cap, o->nlevels, o->err.p, l0));
+    }
   }
-  TSL_CHECK_LAUNCH();
-  static const bool overlap = [] { const char* e = getenv("TSLAM_ORB_OVERLAP"); return !(e && e[0] == '0'); }();
-  if (overlap && !o->s2) {
-    TSL_CUDA(cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking));
-    TSL_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming)); TSL_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
-  }
-  cudaStream_t sb = overlap ? o->s2 : st;
-  if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_fork, st)); TSL_CUDA(cudaStreamWaitEvent(sb, o->ev_fork, 0)); }
   for (int l = 0; l < o->nlevels; ++l) {
     const LevelInfo& li = o->L[l];
     dim3 bgrid((li.w + 31) / 32, (li.h + 7) / 8, n);
-    LAUNCH(blur7_kernel<<<bgrid, 256, 0, sb>>>(o->pyr.p, o->blur.p, o->img_bytes, li.plane_off, li.w, li.h, T[0], T[1], T[2], T[3]));
+    LAUNCH(blur7_kernel<<<bgrid, 256, 0, st>>>(o->pyr.p, o->blur.p, o->img_bytes, li.plane_off, li.w, li.h, T[0], T[1], T[2], T[3]));
   }
-  if (overlap) TSL_CUDA(cudaEventRecord(o->ev_join, sb));
-  TSL_CHECK_LAUNCH();
-  LAUNCH(distribute_kernel<<<dim3(o->nlevels, n), 256, sizeof(DistSmem), st>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
-                                                                                o->sel.p, o->sel_count.p, o->sel_cap, o->nlevels, o->err.p));
+  if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_join, sd)); TSL_CUDA(cudaStreamWaitEvent(st, o->ev_join, 0)); }
   LAUNCH(counts_kernel<<<(n + 127) / 128, 128, 0, st>>>(o->sel_count.p, o->nlevels, o->out_cap, o->counts.p, n));
-  if (overlap) TSL_CUDA(cudaStreamWaitEvent(st, o->ev_join, 0));
+  TSL_CHECK_LAUNCH();
   const int warps = o->nlevels * o->sel_cap;
   LAUNCH(orient_describe_kernel<<<dim3((warps * 32 + 127) / 128, n), 128, 0, st>>>(o->pyr.p, o->blur.p, o->img_bytes, o->Ld.p, o->nlevels, o->sel.p,
                                                                                     o->sel_count.p, o->sel_cap, o->out_cap, o->kp.p, o->desc.p, o->counts.p, o->err.p));
