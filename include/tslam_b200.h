@@ -298,6 +298,25 @@ int tslam_solve_gated(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
 int tslam_match_hamming(tslam_ctx* ctx, const uint8_t* query_desc, int n_query, const uint8_t* train_desc, int n_train,
                         const int32_t* cand_ptr, const int32_t* cand_idx, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
 
+/* tracking::SearchFrom3D / SearchFrom3DAdd / SearchFrom3DLocalTrack up to their uniqueness bookkeeping (src/tracking.cc:1124-1176,
+ * 1206-1256, 1282-1327): per map point, projection into the frame (pose Tcw = [qw qx qy qz tx ty tz], host pose of the point from
+ * `poses`, inverse depth, ray direction (x, y, 1)), the bounds test, frame::GetFeaturesInArea (src/frame.cc:415-468) on the frame's
+ * keypoint grid and the first minimum-Hamming-distance candidate. pt_query[i] = row of query_desc (the descriptor of the point's
+ * observation in the last key frame, F1->mDescr.row(IdxObserv)); < 0 skips the point (FLAG_BAD / not observed, :1126-1132).
+ * Outputs per point: best_idx (-1: out of bounds or no candidate), best_dist (INT_MAX then), optionally the projection (u, v). */
+typedef struct tslam_frame_grid {
+  int32_t cols, rows;               /* FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48 (src/frame.h:26-27)             */
+  float min_x, min_y, max_x, max_y; /* mnMinX, mnMinY, mnMaxX, mnMaxY                                             */
+  float inv_w, inv_h;               /* mfGridElementWidthInv, mfGridElementHeightInv (src/frame.cc:124-125)       */
+  const int32_t* cell_ptr;          /* cols*rows + 1; cell id = ix * rows + iy, i.e. mGrid[ix][iy]                */
+  const int32_t* cell_idx;          /* keypoint indices, insertion order inside a cell (src/frame.cc:386-389)     */
+} tslam_frame_grid;
+int tslam_search_from_3d(tslam_ctx* ctx, const double* Tcw, const double* K, int n_pts, const double* pt_ray, const double* pt_rho,
+                         const double* poses, int n_poses, const int32_t* pt_host, const int32_t* pt_query,
+                         const uint8_t* query_desc, int n_query, const float* kp_xy, const int32_t* kp_octave,
+                         const uint8_t* train_desc, int n_kp, const tslam_frame_grid* grid, float radius, int min_level,
+                         int max_level, int32_t* best_idx, int32_t* best_dist, double* uv_out);
+
 #ifdef __cplusplus
 }
 #endif

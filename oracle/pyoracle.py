@@ -190,6 +190,92 @@ def match_hamming(query_desc, train_desc, cand_ptr, cand_idx):
     return bi, bd, sd
 
 
+def frame_grid(kp_xy, width, height, cols=64, rows=48):
+    """frame::frame bounds / cell sizes (src/frame.cc:118-125) and AssignFeaturesToGrid + PosInGrid (:376-406), restated with
+    Python loops: mGrid[ix][iy] as lists of keypoint indices in insertion order. float members -> np.float32 arithmetic."""
+    f32 = np.float32
+    g = {"cols": cols, "rows": rows, "min_x": f32(0.0), "min_y": f32(0.0), "max_x": f32(width), "max_y": f32(height)}
+    g["inv_w"] = f32(float(cols) / float(g["max_x"] - g["min_x"])); g["inv_h"] = f32(float(rows) / float(g["max_y"] - g["min_y"]))
+    cells = [[[] for _ in range(rows)] for _ in range(cols)]
+    rnd = lambda v: int(np.floor(float(v) + 0.5)) if v >= 0 else -int(np.floor(-float(v) + 0.5))   # C round(): half away from zero
+    for i, (x, y) in enumerate(np.asarray(kp_xy, dtype=f32).reshape(-1, 2)):
+        px = rnd((x - g["min_x"]) * g["inv_w"]); py = rnd((y - g["min_y"]) * g["inv_h"])
+        if px < 0 or px >= cols or py < 0 or py >= rows:
+            continue
+        cells[px][py].append(i)
+    g["cells"] = cells
+    return g
+
+
+def _quat_R(q):
+    w, x, y, z = (float(v) for v in q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def search_from_3d(Tcw, K, pt_ray, pt_rho, poses, pt_host, pt_query, query_desc, kp_xy, kp_octave, train_desc, grid, th, min_level=-1, max_level=1):
+    """tracking::SearchFrom3D (src/tracking.cc:1124-1176) per map point, with frame::GetFeaturesInArea (src/frame.cc:415-468) written
+    out: projection in double (T_cr = T_cw T_rw^-1 in closed form for rigid transforms; the reference goes through Eigen's general
+    4x4 inverse, equal up to rounding), bounds test in double, query window and distance tests in float, cells ix-outer / iy-inner,
+    strict `dist < bestDist`. Returns (best_idx, best_dist, uv)."""
+    f32 = np.float32
+    q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train_desc, dtype=np.uint8).reshape(-1, 32)
+    kp_xy = np.asarray(kp_xy, dtype=f32).reshape(-1, 2)
+    n = len(pt_rho); INT_MAX = 2147483647
+    bi = np.full(n, -1, np.int32); bd = np.full(n, INT_MAX, np.int32); uv = np.zeros((n, 2))
+    Rc = _quat_R(Tcw[:4]); tc = np.asarray(Tcw[4:], dtype=np.float64)
+    fx, fy, cx, cy = (float(v) for v in K)
+    r = f32(th) * f32(1.2)
+    for i in range(n):
+        if pt_query[i] < 0:
+            continue
+        P = poses[pt_host[i]]
+        Rr = _quat_R(P[:4]); tr = P[4:]
+        R = np.array([[(Rc[a, 0] * Rr[b, 0] + Rc[a, 1] * Rr[b, 1]) + Rc[a, 2] * Rr[b, 2] for b in range(3)] for a in range(3)])
+        ir = 1.0 / float(pt_rho[i])
+        p = np.zeros(3)
+        for a in range(3):
+            Rt = (R[a, 0] * tr[0] + R[a, 1] * tr[1]) + R[a, 2] * tr[2]
+            Rray = (R[a, 0] * pt_ray[i][0] + R[a, 1] * pt_ray[i][1]) + R[a, 2]
+            p[a] = ir * Rray + (tc[a] + -Rt)
+        X = fx * p[0] + cx * p[2]; Y = fy * p[1] + cy * p[2]
+        u = X / p[2]; v = Y / p[2]
+        uv[i] = (u, v)
+        if u < float(grid["min_x"]) or u > float(grid["max_x"]) or v < float(grid["min_y"]) or v > float(grid["max_y"]):
+            continue
+        x, y = f32(u), f32(v)
+        c0 = max(0, int(np.floor((x - grid["min_x"] - r) * grid["inv_w"])))
+        if c0 >= grid["cols"]:
+            continue
+        c1 = min(grid["cols"] - 1, int(np.ceil((x - grid["min_x"] + r) * grid["inv_w"])))
+        if c1 < 0:
+            continue
+        r0 = max(0, int(np.floor((y - grid["min_y"] - r) * grid["inv_h"])))
+        if r0 >= grid["rows"]:
+            continue
+        r1 = min(grid["rows"] - 1, int(np.ceil((y - grid["min_y"] + r) * grid["inv_h"])))
+        if r1 < 0:
+            continue
+        check = min_level > 0 or max_level >= 0
+        best, best_k = INT_MAX, -1
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for k in grid["cells"][ix][iy]:
+                    if check:
+                        if kp_octave[k] < min_level:
+                            continue
+                        if max_level >= 0 and kp_octave[k] > max_level:
+                            continue
+                    if abs(kp_xy[k, 0] - x) < r and abs(kp_xy[k, 1] - y) < r:
+                        d = int(np.unpackbits(q[pt_query[i]] ^ t[k]).sum())
+                        if d < best:
+                            best, best_k = d, k
+        if best_k >= 0:
+            bi[i] = best_k; bd[i] = best
+    return bi, bd, uv
+
+
 def gate_residuals(final_residuals, n_pobs, n_tobs, gate, t_obj=None, obj_size=None):
     """The reference's outlier loops (src/optimizer.cc:1236-1302, 1616-1684) on a final residual vector.
     Returns (pt_bad, tf_bad, obj_bad, (nBadS, nBadFeat, nBadT)); raises if the reference's asserts would fire."""

@@ -1,0 +1,40 @@
+"""GPU parity of tslam_search_from_3d (projection + frame::GetFeaturesInArea + first best Hamming candidate, src/tracking.cc:1124-1176,
+src/frame.cc:415-468) against the CPU restatement: indices and distances bit-exact (ties included), projections to rounding."""
+import numpy as np
+import pytest
+import textslam_b200 as T
+from search3d_cases import make_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed,th,levels", [(11, 15, (-1, 1)), (12, 7, (-1, 1)), (13, 40, (-1, -1)), (14, 15, (1, 3))])
+def test_matches_oracle(ctx, oracle, seed, th, levels):
+    c = make_case(seed)
+    G = T.FrameGrid(c["kp_xy"], c["width"], c["height"])
+    g = oracle.frame_grid(c["kp_xy"], c["width"], c["height"])
+    args = (c["Tcw"], c["K"], c["pt_ray"], c["pt_rho"], c["poses"], c["pt_host"], c["pt_query"], c["query_desc"], c["kp_xy"], c["kp_octave"], c["train_desc"])
+    bi, bd, uv = T.search_from_3d(ctx, *args, G, th, *levels)
+    oi, od, ouv = oracle.search_from_3d(*args, g, th, *levels)
+    live = c["pt_query"] >= 0
+    assert np.abs(uv[live] - ouv[live]).max() <= 1e-9
+    assert np.array_equal(bi, oi) and np.array_equal(bd, od)
+    assert (bi >= 0).sum() > 100
+    a = T.resolve_matches(bi, bd, c["pt_query"], len(c["kp_xy"]), len(c["query_desc"]))
+    b = T.resolve_matches(oi, od, c["pt_query"], len(c["kp_xy"]), len(c["query_desc"]))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] > 20
+
+
+def test_edge_cases(ctx, oracle):
+    c = make_case(15, n_kp=50, n_pts=40)
+    G = T.FrameGrid(c["kp_xy"], c["width"], c["height"])
+    args = [c["Tcw"], c["K"], c["pt_ray"], c["pt_rho"], c["poses"], c["pt_host"], c["pt_query"], c["query_desc"], c["kp_xy"], c["kp_octave"], c["train_desc"]]
+    skip = args.copy(); skip[6] = np.full(40, -1, np.int32)          # every point skipped
+    bi, bd, _ = T.search_from_3d(ctx, *skip, G, 15)
+    assert (bi == -1).all() and (bd == 2147483647).all()
+    bad = args.copy(); bad[5] = np.full(40, 99, np.int32)            # host pose out of range
+    with pytest.raises(T.TslamError):
+        T.search_from_3d(ctx, *bad, G, 15)
+    bad = args.copy(); bad[6] = np.full(40, 10 ** 6, np.int32)       # descriptor row out of range
+    with pytest.raises(T.TslamError):
+        T.search_from_3d(ctx, *bad, G, 15)

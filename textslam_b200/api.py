@@ -408,6 +408,80 @@ def match_hamming(ctx, query_desc, train_desc, cand_ptr, cand_idx):
     return bi, bd, sd
 
 
+# ---- projection-guided matching (tracking::SearchFrom3D*, src/tracking.cc:1114-1345) ---------------------------------
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48     # src/frame.h:26-27
+TH_HIGH, TH_LOW = 100, 50                     # src/tracking.cc:21-22
+
+
+class FrameGridC(C.Structure):
+    _fields_ = [("cols", C.c_int32), ("rows", C.c_int32), ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("inv_w", C.c_float), ("inv_h", C.c_float), ("cell_ptr", C.POINTER(C.c_int32)), ("cell_idx", C.POINTER(C.c_int32))]
+
+
+class FrameGrid:
+    """frame::AssignFeaturesToGrid / PosInGrid (src/frame.cc:376-406): keypoints binned into the 64 x 48 grid, insertion order
+    inside a cell; bounds and cell sizes as frame::frame sets them (src/frame.cc:118-125)."""
+
+    def __init__(self, kp_xy, width, height, cols=FRAME_GRID_COLS, rows=FRAME_GRID_ROWS):
+        f32 = np.float32
+        self.cols, self.rows = cols, rows
+        self.min_x, self.min_y, self.max_x, self.max_y = f32(0.0), f32(0.0), f32(width), f32(height)
+        self.inv_w = f32(float(cols) / float(self.max_x - self.min_x)); self.inv_h = f32(float(rows) / float(self.max_y - self.min_y))
+        kp_xy = np.ascontiguousarray(kp_xy, dtype=f32).reshape(-1, 2)
+        # round(): half away from zero, on the float product
+        px = (kp_xy[:, 0] - self.min_x) * self.inv_w; py = (kp_xy[:, 1] - self.min_y) * self.inv_h
+        rnd = lambda v: np.where(v >= 0, np.floor(v.astype(np.float64) + 0.5), -np.floor(-v.astype(np.float64) + 0.5)).astype(np.int64)
+        gx, gy = rnd(px), rnd(py)
+        ok = (gx >= 0) & (gx < cols) & (gy >= 0) & (gy < rows)
+        cell = np.where(ok, gx * rows + gy, -1)
+        idx = np.nonzero(ok)[0]
+        order = idx[np.argsort(cell[idx], kind="stable")]           # stable: insertion (keypoint index) order inside a cell
+        self.cell_idx = np.ascontiguousarray(order, dtype=np.int32)
+        self.cell_ptr = np.zeros(cols * rows + 1, np.int32)
+        np.cumsum(np.bincount(cell[idx], minlength=cols * rows), out=self.cell_ptr[1:])
+
+    def as_c(self):
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        return FrameGridC(self.cols, self.rows, float(self.min_x), float(self.min_y), float(self.max_x), float(self.max_y), float(self.inv_w), float(self.inv_h),
+                          ip(self.cell_ptr), ip(self.cell_idx) if len(self.cell_idx) else None)
+
+
+def search_from_3d(ctx, Tcw, K, pt_ray, pt_rho, poses, pt_host, pt_query, query_desc, kp_xy, kp_octave, train_desc, grid, th, min_level=-1, max_level=1):
+    """Per map point: projection, bounds test, GetFeaturesInArea(u, v, th * 1.2f, min_level, max_level), first best candidate.
+    Returns (best_idx, best_dist, uv)."""
+    f64 = lambda a, shape: np.ascontiguousarray(a, dtype=np.float64).reshape(shape)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    Tcw = f64(Tcw, 7); K = f64(K, 4); pt_ray = f64(pt_ray, (-1, 2)); pt_rho = f64(pt_rho, -1); poses = f64(poses, (-1, 7))
+    pt_host, pt_query, kp_octave = i32(pt_host), i32(pt_query), i32(kp_octave)
+    q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train_desc, dtype=np.uint8).reshape(-1, 32)
+    kp_xy = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+    n = len(pt_rho)
+    bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); uv = np.zeros((n, 2))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    g = grid.as_c()
+    radius = np.float32(th) * np.float32(1.2)      # float radius = th*1.2f (src/tracking.cc:1153)
+    check(lib().tslam_search_from_3d(ctx._h, _dp(Tcw), _dp(K), C.c_int(n), _dp(pt_ray), _dp(pt_rho), _dp(poses), C.c_int(len(poses)), ip(pt_host), ip(pt_query),
+                                     q.ctypes.data_as(c_bp), C.c_int(len(q)), kp_xy.ctypes.data_as(C.POINTER(C.c_float)), ip(kp_octave),
+                                     t.ctypes.data_as(c_bp), C.c_int(len(t)), C.byref(g), C.c_float(float(radius)), C.c_int(min_level), C.c_int(max_level),
+                                     ip(bi), ip(bd), _dp(uv)))
+    return bi, bd, uv
+
+
+def resolve_matches(best_idx, best_dist, pt_query, n_kp, n_query, th_high=TH_HIGH):
+    """The sequential bookkeeping of tracking::SearchFrom3D (src/tracking.cc:1178-1186): a point keeps its best keypoint if neither
+    that keypoint nor the point's observation in the last key frame has been taken by an earlier point.
+    Returns (vMatch3D2D, vMatch2D3D, nMatches)."""
+    m32 = np.full(len(best_idx), -1, np.int64); m23 = np.full(n_kp, -1, np.int64); m12 = np.full(n_query, -1, np.int64)
+    n = 0
+    for i in range(len(best_idx)):
+        if pt_query[i] < 0 or best_idx[i] < 0 or best_dist[i] > th_high:
+            continue
+        j = best_idx[i]
+        if m23[j] < 0 and m12[pt_query[i]] < 0:
+            n += 1; m32[i] = j; m23[j] = i; m12[pt_query[i]] = j
+    return m32, m23, n
+
+
 class FramePyramid:
     """Mirror of frame::GetPyrMat (src/frame.cc:178-202): vFrameImg / vFrameGrad / vFrameGradX / vFrameGradY per level."""
     IMG, GRAD, GRAD_X, GRAD_Y = 0, 1, 2, 3
