@@ -33,7 +33,6 @@ constexpr int MAX_LEVELS = 16;
 constexpr int MAXID = 2048;         // quad-tree node ids per (image, level)
 constexpr int MAXCELLS = 512;       // cells per level
 
-__constant__ int8_t c_pattern[1024];
 __constant__ int c_umax[ORB_HALF_PATCH + 1];
 // the rBRIEF pattern as one 32-bit word (x0, y0, x1, y1) per (comparison k, lane) in GLOBAL memory: every lane reads its own entries — a
 // coalesced, L1-resident load here, 32 serialised fetches per access from the constant cache (orient_describe_kernel: 509 -> 260 us per batch)
@@ -909,7 +908,6 @@ int tslam_orb_create(tslam_ctx* ctx, int nfeatures, float scale_factor, int nlev
   const double hp2 = ORB_HALF_PATCH * ORB_HALF_PATCH;
   for (v = 0; v <= vmax; ++v) o->umax[v] = cv_round_host(std::sqrt(hp2 - v * v));
   for (v = ORB_HALF_PATCH, v0 = 0; v >= vmin; --v) { while (o->umax[v0] == o->umax[v0 + 1]) ++v0; o->umax[v] = v0; ++v0; }
-  TSL_CUDA(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
   {
     uint32_t packed[8 * 32];
     for (int k = 0; k < 8; ++k)
