@@ -290,6 +290,12 @@ struct DistSmem {
   int wsum[3][8];                 // per-warp totals of the block scans
 };
 
+// Candidates of one (image, level) cached in shared memory behind DistSmem when they fit: packed key point, node id, quadrant. Every
+// pass of the quad-tree loop sweeps all candidates two or three times; from global memory each sweep is a chain of dependent loads
+// (cell count -> slot -> node id), the kernel's long-scoreboard stall (ncu: 9 % issue active, one CTA per SM).
+constexpr int KCACHE = 12288;
+constexpr size_t DIST_SMEM_BYTES = ((sizeof(DistSmem) + 15) & ~(size_t)15) + (size_t)KCACHE * 7;
+
 // exclusive scan of up to three counters over the 256 threads of the CTA (warp shuffles + one shared-memory hop);
 // tot[k] = block totals. Ends with a barrier, so wsum is reusable right away.
 template <int NV>
@@ -369,24 +375,40 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
   }
   for (int k = tid; k < MAXID - nIni; k += nthreads) S.freelist[k] = (unsigned short)(MAXID - 1 - k);   // pop from the end -> ids nIni, nIni+1, ...
   __syncthreads();
-#define FOR_EACH_KP(...)                                                        \
-  for (int c = warp; c < ncells; c += nwarps) {                                  \
-    const int cn = ccount[c];                                                    \
-    for (int s = lane; s < cn; s += 32) {                                        \
-      const int kidx = c * CELL_CAP + s;                                         \
-      const uint32_t pk = cslots[kidx];                                          \
-      const float kx = (float)(pk >> 18), ky = (float)((pk >> 8) & 1023u);       \
-      const int kresp = (int)(pk & 255u);                                        \
-      const int kord = S.cell_off[c] + s;                                        \
-      (void)kx; (void)ky; (void)kresp; (void)kord;                               \
-      __VA_ARGS__                                                                \
-    }                                                                            \
+  unsigned char* cache_base = dist_raw + ((sizeof(DistSmem) + 15) & ~(size_t)15);
+  uint32_t* s_pk = reinterpret_cast<uint32_t*>(cache_base);
+  unsigned short* s_nof = reinterpret_cast<unsigned short*>(cache_base + (size_t)KCACHE * 4);
+  uint8_t* s_kq = cache_base + (size_t)KCACHE * 6;
+  const bool cached = M <= KCACHE;
+  if (cached) {   // one pass over the cells fills the cache in vToDistributeKeys order (index = cell_off[cell] + slot)
+    for (int c = warp; c < ncells; c += nwarps) {
+      const int cn = ccount[c], o0 = S.cell_off[c];
+      for (int sl = lane; sl < cn; sl += 32) s_pk[o0 + sl] = cslots[c * CELL_CAP + sl];
+    }
+    __syncthreads();
   }
-  FOR_EACH_KP({
-    const int nid = (int)(kx / hX);
-    nof[kidx] = (unsigned short)nid;
+  // body(packed key point, order index, node id slot, quadrant slot, id to publish as the node's winner)
+  auto each_kp = [&](auto body) {
+    if (cached) {
+      for (int k = tid; k < M; k += nthreads) body(s_pk[k], k, s_nof + k, s_kq + k, k);
+    } else {
+      for (int c = warp; c < ncells; c += nwarps) {
+        const int cn = ccount[c];
+        for (int sl = lane; sl < cn; sl += 32) {
+          const int kidx = c * CELL_CAP + sl;
+          body(cslots[kidx], S.cell_off[c] + sl, nof + kidx, kqq + kidx, kidx);
+        }
+      }
+    }
+  };
+#define KP_X(pk) ((float)((pk) >> 18))
+#define KP_Y(pk) ((float)(((pk) >> 8) & 1023u))
+#define KP_RESP(pk) ((int)((pk) & 255u))
+  each_kp([&](uint32_t pk, int, unsigned short* pn, uint8_t*, int) {
+    const int nid = (int)(KP_X(pk) / hX);
+    *pn = (unsigned short)nid;
     atomicAdd(&S.cnt[nid], 1);
-  })
+  });
   __syncthreads();
   if (tid == 0) {
     int alive = 0;
@@ -411,32 +433,35 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
     if (mode == 0) {
       for (int i = tid; i < alive; i += nthreads) { const int id = S.order[i]; if (!(S.flags[id] & 2)) S.flags[id] |= 4; }
     } else {
-      if (tid == 0) {
-        // vprev = vsize sorted ascending by (cnt, seq); processed from the end
-        const int nv = S.ctl[5];
-        for (int i = 0; i < nv; ++i) S.vprev[i] = S.vsize[i];
-        for (int i = 1; i < nv; ++i) {   // insertion sort (nv is small near the limit)
-          const unsigned short v = S.vprev[i]; int j = i - 1;
-          while (j >= 0 && (S.cnt[S.vprev[j]] > S.cnt[v] || (S.cnt[S.vprev[j]] == S.cnt[v] && S.seq[S.vprev[j]] > S.seq[v]))) { S.vprev[j + 1] = S.vprev[j]; --j; }
-          S.vprev[j + 1] = v;
-        }
-        for (int i = 0; i < nv; ++i) S.flags[S.vprev[i]] |= 4;
+      // vprev = vsize sorted ascending by (cnt, seq) — the reference's sort of (size, node) pairs —, processed from the end. (cnt, seq) is a
+      // total order (seq is unique), so every entry's position is the number of smaller keys: nv^2 / 256 comparisons per thread
+      // instead of one thread's insertion sort (nv ~ 100-200 near the feature limit: ~1 M dependent shared-memory cycles, the bulk of
+      // this kernel's run time on the fine levels).
+      const int nv = S.ctl[5];
+      for (int i = tid; i < nv; i += nthreads) {
+        const unsigned short v = S.vsize[i];
+        const int ci = S.cnt[v], si = S.seq[v];
+        int rank = 0;
+        for (int j = 0; j < nv; ++j) { const unsigned short u = S.vsize[j]; const int cj = S.cnt[u]; rank += (cj < ci) || (cj == ci && S.seq[u] < si); }
+        S.vprev[rank] = v;
       }
+      __syncthreads();
+      for (int i = tid; i < nv; i += nthreads) S.flags[S.vprev[i]] |= 4;
     }
     __syncthreads();
     for (int i = tid; i < MAXID; i += nthreads)
       if (S.flags[i] & 4) { S.childcnt[i][0] = S.childcnt[i][1] = S.childcnt[i][2] = S.childcnt[i][3] = 0; }
     __syncthreads();
     // 2. child counts of every selected node
-    FOR_EACH_KP({
-      const int nid = nof[kidx];
+    each_kp([&](uint32_t pk, int, unsigned short* pn, uint8_t* pq, int) {
+      const int nid = *pn;
       if (S.flags[nid] & 4) {
         const int halfX = (int)ceilf((float)(S.urx[nid] - S.ulx[nid]) / 2), halfY = (int)ceilf((float)(S.bly[nid] - S.uly[nid]) / 2);
-        const int q = quadrant_of(kx, ky, S.ulx[nid] + halfX, S.uly[nid] + halfY);
-        kqq[kidx] = (uint8_t)q;
+        const int q = quadrant_of(KP_X(pk), KP_Y(pk), S.ulx[nid] + halfX, S.uly[nid] + halfY);
+        *pq = (uint8_t)q;
         atomicAdd(&S.childcnt[nid][q], 1);
       }
-    })
+    });
     __syncthreads();
     // 3. list surgery. Coarse mode (every dividable node splits): all threads, three block scans over the list give each
     // node its creation rank (children are numbered in list order, quadrant order), the slot of its big children in vsize
@@ -543,11 +568,11 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
     }
     __syncthreads();
     // 4. move the candidates of divided nodes to their children, then recycle the parents
-    FOR_EACH_KP({
-      const int nid = nof[kidx];
+    each_kp([&](uint32_t, int, unsigned short* pn, uint8_t* pq, int) {
+      const int nid = *pn;
       const int fl = S.flags[nid];
-      if ((fl & 4) && (mode == 0 || (fl & 8))) nof[kidx] = S.childid[nid][kqq[kidx]];
-    })
+      if ((fl & 4) && (mode == 0 || (fl & 8))) *pn = S.childid[nid][*pq];
+    });
     __syncthreads();
     {   // recycle the divided parents: ordered compaction of their ids onto the free list (ascending id, like a serial walk)
       int nfree = S.ctl[0];
@@ -571,23 +596,24 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
   // ---- best candidate per live node: max response, first in insertion order on ties ----
   for (int i = tid; i < MAXID; i += nthreads) S.best[i] = 0u;
   __syncthreads();
-  FOR_EACH_KP({
-    const int nid = nof[kidx];
-    const unsigned key = ((unsigned)kresp << 20) | (0xFFFFFu - (unsigned)kord);
-    atomicMax(&S.best[nid], key);
-  })
+  each_kp([&](uint32_t pk, int kord, unsigned short* pn, uint8_t*, int) {
+    const unsigned key = ((unsigned)KP_RESP(pk) << 20) | (0xFFFFFu - (unsigned)kord);
+    atomicMax(&S.best[*pn], key);
+  });
   __syncthreads();
-  FOR_EACH_KP({
-    const int nid = nof[kidx];
-    const unsigned key = ((unsigned)kresp << 20) | (0xFFFFFu - (unsigned)kord);
-    if (S.best[nid] == key) S.best[nid] = 0x80000000u | (unsigned)kidx;   // winner publishes its slot index (unique key)
-  })
+  each_kp([&](uint32_t pk, int kord, unsigned short* pn, uint8_t*, int kid) {
+    const int nid = *pn;
+    const unsigned key = ((unsigned)KP_RESP(pk) << 20) | (0xFFFFFu - (unsigned)kord);
+    if (S.best[nid] == key) S.best[nid] = 0x80000000u | (unsigned)kid;   // winner publishes its index (unique key)
+  });
   __syncthreads();
   const int live = S.ctl[2];
   if (live > sel_cap) { if (tid == 0) { atomicExch(err, 4); *out_count = 0; } return; }
-  for (int i = tid; i < live; i += nthreads) out[i] = cslots[S.best[S.order[i]] & 0x7FFFFFFFu];
+  for (int i = tid; i < live; i += nthreads) { const unsigned bk = S.best[S.order[i]] & 0x7FFFFFFFu; out[i] = cached ? s_pk[bk] : cslots[bk]; }
   if (tid == 0) *out_count = live;
-#undef FOR_EACH_KP
+#undef KP_X
+#undef KP_Y
+#undef KP_RESP
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -804,7 +830,7 @@ static int orb_configure(tslam_orb* o, int w, int h, int n_imgs) {
 static int orb_run(tslam_orb* o, int n) {
   tslam_ctx* ctx = o->ctx; cudaStream_t st = ctx->stream;
   // the opt-in is per device: tracked per context, not per process (several contexts on several GPUs may live in one process)
-  if (!ctx->attr_orb) { TSL_CUDA(cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DistSmem))); ctx->attr_orb = true; }
+  if (!ctx->attr_orb) { TSL_CUDA(cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM_BYTES)); ctx->attr_orb = true; }
   TSL_CUDA(cudaMemsetAsync(o->err.p, 0, sizeof(int), st));
   for (int l = 1; l < o->nlevels; ++l) {
     const LevelInfo& s = o->L[l - 1]; const LevelInfo& d = o->L[l];
@@ -841,7 +867,7 @@ static int orb_run(tslam_orb* o, int n) {
       const int l0 = l == split - 1 ? 0 : split;
       if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_level[l], st)); TSL_CUDA(cudaStreamWaitEvent(sd, o->ev_level[l], 0)); }
       if (l - l0 + 1 > 0)
-        LAUNCH(distribute_kernel<<<dim3(l - l0 + 1, n), 256, sizeof(DistSmem), sd>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
+        LAUNCH(distribute_kernel<<<dim3(l - l0 + 1, n), 256, DIST_SMEM_BYTES, sd>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
                                                                                       o->sel.p, o->sel_count.p, o->sel_cap, o->nlevels, o->err.p, l0));
     }
   }
