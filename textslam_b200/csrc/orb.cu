@@ -287,7 +287,7 @@ struct DistSmem {
   unsigned short order[MAXID], order2[MAXID], vsize[MAXID], vprev[MAXID], freelist[MAXID];
   int cell_off[MAXCELLS + 1];
   int ctl[8];
-  int wsum[3][8];                 // per-warp totals of the block scans
+  int wsum[3][32];                // per-warp totals of the block scans
 };
 
 // Candidates of one (image, level) cached in shared memory behind DistSmem when they fit: packed key point, node id, quadrant. Every
@@ -296,10 +296,10 @@ struct DistSmem {
 constexpr int KCACHE = 12288;
 constexpr size_t DIST_SMEM_BYTES = ((sizeof(DistSmem) + 15) & ~(size_t)15) + (size_t)KCACHE * 7;
 
-// exclusive scan of up to three counters over the 256 threads of the CTA (warp shuffles + one shared-memory hop);
+// exclusive scan of up to three counters over the threads of the CTA (<= 32 warps; warp shuffles + one shared-memory hop);
 // tot[k] = block totals. Ends with a barrier, so wsum is reusable right away.
 template <int NV>
-__device__ __forceinline__ void block_exscan(const int (&v)[NV], int (&e)[NV], int (&tot)[NV], int (*wsum)[8]) {
+__device__ __forceinline__ void block_exscan(const int (&v)[NV], int (&e)[NV], int (&tot)[NV], int (*wsum)[32]) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int inc[NV];
 #pragma unroll
@@ -316,7 +316,7 @@ __device__ __forceinline__ void block_exscan(const int (&v)[NV], int (&e)[NV], i
   for (int k = 0; k < NV; ++k) {
     int b = 0, t = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int x = wsum[k][j]; if (j < w) b += x; t += x; }
+    for (int j = 0; j < (int)(blockDim.x >> 5); ++j) { const int x = wsum[k][j]; if (j < w) b += x; t += x; }
     e[k] = b + inc[k] - v[k]; tot[k] = t;
   }
   __syncthreads();
@@ -327,7 +327,8 @@ __device__ __forceinline__ int quadrant_of(float x, float y, int mx, int my) {
   return (y < (float)my) ? 1 : 3;
 }
 
-__global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __restrict__ Ld, int total_cells, const uint32_t* __restrict__ slots,
+constexpr int DIST_THREADS = 1024;   // one CTA per SM (shared memory): 32 warps keep 4x the loads of the candidate sweeps in flight
+__global__ void __launch_bounds__(DIST_THREADS) distribute_kernel(const LevelInfo* __restrict__ Ld, int total_cells, const uint32_t* __restrict__ slots,
                                                          const int* __restrict__ cell_count, unsigned short* __restrict__ node_of,
                                                          uint8_t* __restrict__ kq, uint32_t* __restrict__ sel, int* __restrict__ sel_count,
                                                          int sel_cap, int nlevels, int* __restrict__ err, int level0) {
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
   // candidate index = cell_off[cell] + slot  (vToDistributeKeys order)
   {   // exclusive scan of the per-cell counts (block scan; a serial walk was ~300 dependent global loads on one thread)
     int base = 0;
-    for (int c0 = 0; c0 < ncells; c0 += 256) {
+    for (int c0 = 0; c0 < ncells; c0 += nthreads) {
       const int c = c0 + tid;
       int v[1] = {c < ncells ? ccount[c] : 0}, e[1], tot[1];
       block_exscan<1>(v, e, tot, S.wsum);
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
       const int nfree0 = S.ctl[0], seqc0 = S.ctl[1], live0 = S.ctl[2];
       int* created = reinterpret_cast<int*>(S.best);   // scratch (best[] is only used at the very end)
       int base_n = 0, base_big = 0, base_kept = 0;
-      for (int c0 = 0; c0 < live0; c0 += 256) {
+      for (int c0 = 0; c0 < live0; c0 += nthreads) {
         const int i = c0 + tid;
         int id = 0; bool sel = false;
         int v[3] = {0, 0, 0}, e[3], tot[3];
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(256) distribute_kernel(const LevelInfo* __rest
     {   // recycle the divided parents: ordered compaction of their ids onto the free list (ascending id, like a serial walk)
       int nfree = S.ctl[0];
       __syncthreads();
-      for (int c0 = 0; c0 < MAXID; c0 += 256) {
+      for (int c0 = 0; c0 < MAXID; c0 += nthreads) {
         const int i = c0 + tid;
         const int fl = S.flags[i];
         const bool fr = (fl & 4) && (mode == 0 || (fl & 8));
@@ -867,7 +868,7 @@ static int orb_run(tslam_orb* o, int n) {
       const int l0 = l == split - 1 ? 0 : split;
       if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_level[l], st)); TSL_CUDA(cudaStreamWaitEvent(sd, o->ev_level[l], 0)); }
       if (l - l0 + 1 > 0)
-        LAUNCH(distribute_kernel<<<dim3(l - l0 + 1, n), 256, DIST_SMEM_BYTES, sd>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
+        LAUNCH(distribute_kernel<<<dim3(l - l0 + 1, n), DIST_THREADS, DIST_SMEM_BYTES, sd>>>(o->Ld.p, o->total_cells, o->slots.p, o->cell_count.p, o->node_of.p, o->kq.p,
                                                                                       o->sel.p, o->sel_count.p, o->sel_cap, o->nlevels, o->err.p, l0));
     }
   }
