@@ -86,12 +86,13 @@ struct tslam_orb {
   int last_n = 0;
   // second stream: the 7x7 Gaussian of every level (needed by the descriptors only) runs beside the quad-tree distribution, whose one CTA
   // of 8 warps per SM (115 KB of shared memory each) leaves the SMs mostly idle
-  cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_level[16] = {};
+  cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_level[16] = {}, ev_res[16] = {};
   ~tslam_orb() {
     if (s2) cudaStreamDestroy(s2);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     for (cudaEvent_t e : ev_level) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_res) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -833,12 +834,6 @@ static int orb_run(tslam_orb* o, int n) {
   // the opt-in is per device: tracked per context, not per process (several contexts on several GPUs may live in one process)
   if (!ctx->attr_orb) { TSL_CUDA(cudaFuncSetAttribute(distribute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIST_SMEM_BYTES)); ctx->attr_orb = true; }
   TSL_CUDA(cudaMemsetAsync(o->err.p, 0, sizeof(int), st));
-  for (int l = 1; l < o->nlevels; ++l) {
-    const LevelInfo& s = o->L[l - 1]; const LevelInfo& d = o->L[l];
-    dim3 grid((d.w + 127) / 128, d.h, n);
-    LAUNCH(resize_kernel<<<grid, 128, 0, st>>>(o->pyr.p, o->pyr.p, o->img_bytes, s.plane_off, d.plane_off, s.w, s.h, d.w, d.h,
-                                                o->xofs.p + o->xtab_off[l], o->xa.p + 2 * o->xtab_off[l], o->yofs.p + o->ytab_off[l], o->ya.p + 2 * o->ytab_off[l]));
-  }
   static const int T0[4] = {18, 34, 48, 56}, T1[4] = {18, 34, 49, 55};
   const int* T = o->blur_variant == 1 ? T1 : T0;
   // Two streams. The quad-tree distribution of a level (64 CTAs of 8 warps holding 115 KB of shared memory each: latency bound, one
@@ -848,13 +843,24 @@ static int orb_run(tslam_orb* o, int n) {
   if (overlap && !o->s2) {
     TSL_CUDA(cudaStreamCreateWithFlags(&o->s2, cudaStreamNonBlocking));
     TSL_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming)); TSL_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
-    for (int l = 0; l < 16; ++l) TSL_CUDA(cudaEventCreateWithFlags(&o->ev_level[l], cudaEventDisableTiming));
+    for (int l = 0; l < 16; ++l) { TSL_CUDA(cudaEventCreateWithFlags(&o->ev_level[l], cudaEventDisableTiming)); TSL_CUDA(cudaEventCreateWithFlags(&o->ev_res[l], cudaEventDisableTiming)); }
   }
   if (o->nlevels > 16) return set_error(TSLAM_ERR_ARG, "more than 16 pyramid levels");
   cudaStream_t sd = overlap ? o->s2 : st;
+  // the pyramid (each level from the previous one: seven small dependent launches) on the second stream, while the first one already
+  // scores level 0; a level's FAST pass waits for that level's resize only
+  if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_fork, st)); TSL_CUDA(cudaStreamWaitEvent(sd, o->ev_fork, 0)); }
+  for (int l = 1; l < o->nlevels; ++l) {
+    const LevelInfo& s = o->L[l - 1]; const LevelInfo& d = o->L[l];
+    dim3 grid((d.w + 127) / 128, d.h, n);
+    LAUNCH(resize_kernel<<<grid, 128, 0, sd>>>(o->pyr.p, o->pyr.p, o->img_bytes, s.plane_off, d.plane_off, s.w, s.h, d.w, d.h,
+                                                o->xofs.p + o->xtab_off[l], o->xa.p + 2 * o->xtab_off[l], o->yofs.p + o->ytab_off[l], o->ya.p + 2 * o->ytab_off[l]));
+    if (overlap) TSL_CUDA(cudaEventRecord(o->ev_res[l], sd));
+  }
   for (int l = 0; l < o->nlevels; ++l) {
     const LevelInfo& li = o->L[l];
     dim3 grid((li.w + 127) / 128, li.h, n);
+    if (overlap && l > 0) TSL_CUDA(cudaStreamWaitEvent(st, o->ev_res[l], 0));
     static const bool bisect = getenv("TSLAM_FAST_BISECT") != nullptr;   // the first (bisection) formulation, kept for A/B runs
     if (bisect) LAUNCH(fast_score_kernel<false><<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
     else LAUNCH(fast_score_kernel<true><<<grid, 128, 0, st>>>(o->pyr.p, o->score.p, o->img_bytes, li.plane_off, li.w, li.h, o->minTh));
