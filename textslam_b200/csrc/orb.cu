@@ -622,27 +622,36 @@ __global__ void __launch_bounds__(DIST_THREADS) distribute_kernel(const LevelInf
 // cv::GaussianBlur(7x7, sigma=2, BORDER_REFLECT_101) for 8UC1: integer taps, (V + 2^15) >> 16
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int reflect101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; return p; }
+constexpr int BLUR_ROWS = 32;   // output rows per CTA: 38 filtered rows for 32 outputs (1.19x) instead of 14 for 8 (1.75x)
 __global__ void __launch_bounds__(256) blur7_kernel(const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, size_t img_bytes, size_t off, int w, int h,
                                                     int t0, int t1, int t2, int t3) {
-  __shared__ int hs[8 + 6][32];
+  __shared__ int hs[BLUR_ROWS + 6][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = blockIdx.x * 32 + tx, y0 = blockIdx.y * 8;
+  const int x = blockIdx.x * 32 + tx, y0 = blockIdx.y * BLUR_ROWS;
   const uint8_t* src = pyr + (size_t)blockIdx.z * img_bytes + off;
-  for (int r = ty; r < 14; r += 8) {
-    const int yy = reflect101(y0 + r - 3, h);
+  const bool interior_x = x >= 3 && x + 3 < w;   // no reflection needed along the row (all but the first / last column tile)
+  for (int r = ty; r < BLUR_ROWS + 6; r += 8) {
+    const int yr = y0 + r - 3;
+    if (yr >= h + 3) break;                       // rows below the image are not needed by any output of this tile
+    const int yy = reflect101(yr, h);
     int s = 0;
     if (x < w) {
       const uint8_t* p = src + (size_t)yy * w;
-      s = t0 * (p[reflect101(x - 3, w)] + p[reflect101(x + 3, w)]) + t1 * (p[reflect101(x - 2, w)] + p[reflect101(x + 2, w)]) +
-          t2 * (p[reflect101(x - 1, w)] + p[reflect101(x + 1, w)]) + t3 * p[x];
+      if (interior_x) s = t0 * (p[x - 3] + p[x + 3]) + t1 * (p[x - 2] + p[x + 2]) + t2 * (p[x - 1] + p[x + 1]) + t3 * p[x];
+      else s = t0 * (p[reflect101(x - 3, w)] + p[reflect101(x + 3, w)]) + t1 * (p[reflect101(x - 2, w)] + p[reflect101(x + 2, w)]) +
+               t2 * (p[reflect101(x - 1, w)] + p[reflect101(x + 1, w)]) + t3 * p[x];
     }
     hs[r][tx] = s;
   }
   __syncthreads();
-  const int y = y0 + ty;
-  if (x < w && y < h) {
-    const int v = t0 * (hs[ty][tx] + hs[ty + 6][tx]) + t1 * (hs[ty + 1][tx] + hs[ty + 5][tx]) + t2 * (hs[ty + 2][tx] + hs[ty + 4][tx]) + t3 * hs[ty + 3][tx];
-    blur[(size_t)blockIdx.z * img_bytes + off + (size_t)y * w + x] = (uint8_t)min(255, max(0, (v + (1 << 15)) >> 16));
+  if (x >= w) return;
+#pragma unroll
+  for (int k = 0; k < BLUR_ROWS / 8; ++k) {
+    const int ry = ty + 8 * k, y = y0 + ry;
+    if (y < h) {
+      const int v = t0 * (hs[ry][tx] + hs[ry + 6][tx]) + t1 * (hs[ry + 1][tx] + hs[ry + 5][tx]) + t2 * (hs[ry + 2][tx] + hs[ry + 4][tx]) + t3 * hs[ry + 3][tx];
+      blur[(size_t)blockIdx.z * img_bytes + off + (size_t)y * w + x] = (uint8_t)min(255, max(0, (v + (1 << 15)) >> 16));
+    }
   }
 }
 
@@ -880,7 +889,7 @@ static int orb_run(tslam_orb* o, int n) {
   }
   for (int l = 0; l < o->nlevels; ++l) {
     const LevelInfo& li = o->L[l];
-    dim3 bgrid((li.w + 31) / 32, (li.h + 7) / 8, n);
+    dim3 bgrid((li.w + 31) / 32, (li.h + BLUR_ROWS - 1) / BLUR_ROWS, n);
     LAUNCH(blur7_kernel<<<bgrid, 256, 0, st>>>(o->pyr.p, o->blur.p, o->img_bytes, li.plane_off, li.w, li.h, T[0], T[1], T[2], T[3]));
   }
   if (overlap) { TSL_CUDA(cudaEventRecord(o->ev_join, sd)); TSL_CUDA(cudaStreamWaitEvent(st, o->ev_join, 0)); }
