@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(128) cell_nms_kernel(const uint8_t* __restrict
                                                        uint32_t* __restrict__ slots, int* __restrict__ cell_count, int* __restrict__ err) {
   constexpr int SW = 64, SH = 64;  // interior (wCell x hCell, <= 62 x 62) plus a zero ring
   __shared__ uint8_t sm[SH][SW];
-  __shared__ uint8_t sc[SH][SW];
   __shared__ int warp_cnt[4];
   const LevelInfo li = Ld[level];
   const int cell = blockIdx.x, img = blockIdx.y;
@@ -220,32 +219,31 @@ __global__ void __launch_bounds__(128) cell_nms_kernel(const uint8_t* __restrict
   if (dw <= 0 || dh <= 0) { if (threadIdx.x == 0) *out_count = 0; return; }
   if (dw > SW - 2 || dh > SH - 2) { if (threadIdx.x == 0) { atomicExch(err, 1); *out_count = 0; } return; }
   const uint8_t* sp = score + (size_t)img * img_bytes + li.plane_off;
-  for (int e = threadIdx.x; e < SW * SH; e += 128) {
-    const int yy = e / SW, xx = e - yy * SW;
-    int m = 0;
-    if (xx >= 1 && xx <= dw && yy >= 1 && yy <= dh) m = sp[(size_t)(iy0 + yy - 1) * li.w + ix0 + xx - 1];
-    sm[yy][xx] = (uint8_t)m;
-  }
+  // only the (dh + 2) x (dw + 2) part of the tile that the cell uses (a 30-px cell: ~1000 of the 4096 entries), a warp per row
+  for (int yy = threadIdx.x >> 5; yy < dh + 2; yy += 4)
+    for (int xx = threadIdx.x & 31; xx < dw + 2; xx += 32) {
+      int m = 0;
+      if (xx >= 1 && xx <= dw && yy >= 1 && yy <= dh) m = sp[(size_t)(iy0 + yy - 1) * li.w + ix0 + xx - 1];
+      sm[yy][xx] = (uint8_t)m;
+    }
   uint32_t* my_slots = slots + ((size_t)img * total_cells + li.cell_base + cell) * CELL_CAP;
   const int npix = dw * dh;
+  __syncthreads();
+  // cv::FAST keeps a corner whose score s = m - 1 (m > th) exceeds the scores of its 8 neighbours, where a neighbour below the
+  // threshold scores 0. Since m > th >= any such neighbour's measure, that is: m > th and m greater than all 8 neighbouring measures —
+  // the second condition does not depend on the threshold, so no thresholded copy of the tile is needed for either pass.
   for (int pass = 0; pass < 2; ++pass) {
     const int th = pass == 0 ? ini_th : min_th;
-    __syncthreads();
-    for (int e = threadIdx.x; e < SW * SH; e += 128) {
-      const int yy = e / SW, xx = e - yy * SW;
-      const int m = sm[yy][xx];
-      sc[yy][xx] = (uint8_t)(m > th ? m - 1 : 0);
-    }
-    __syncthreads();
     int base = 0;
     for (int c0 = 0; c0 < npix; c0 += 128) {   // ordered (row-major) compaction, 128 pixels at a time
       const int e = c0 + threadIdx.x;
       bool keep = false; int xx = 0, yy = 0, s = 0;
       if (e < npix) {
         yy = e / dw; xx = e - yy * dw;
-        const uint8_t* c = &sc[yy + 1][xx + 1];
-        s = c[0];
-        keep = s > 0 && s > c[-1] && s > c[1] && s > c[-SW - 1] && s > c[-SW] && s > c[-SW + 1] && s > c[SW - 1] && s > c[SW] && s > c[SW + 1];
+        const uint8_t* c = &sm[yy + 1][xx + 1];
+        const int m = c[0];
+        s = m - 1;
+        keep = m > th && m > c[-1] && m > c[1] && m > c[-SW - 1] && m > c[-SW] && m > c[-SW + 1] && m > c[SW - 1] && m > c[SW] && m > c[SW + 1];
       }
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
