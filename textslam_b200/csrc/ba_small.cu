@@ -8,7 +8,7 @@
 //   host   one O(n) pass over the index arrays (free-camera slots, observation lists per free landmark), everything packed into
 //          ONE page-locked staging block -> one H2D copy (+ one for the images), one kernel, one D2H copy of the result block;
 //   device the whole Levenberg-Marquardt loop of run_lm() (same accept / reject / termination rules, same Jacobi-scaled damping)
-//          in one launch of G <= 64 CTAs that meet at grid barriers: evaluate r, J -> per-warp accumulation of the camera block
+//          in one cooperative launch of G CTAs (one per SM as soon as there is work for it) that meet at grid barriers: evaluate r, J -> per-warp accumulation of the camera block
 //          H_cc and of every landmark's V, g, E (observation lists, fixed order) -> Schur complement contributions -> fixed-order
 //          reduction over CTAs -> dense Cholesky of the <= 60 x 60 reduced camera system in shared memory (every CTA redundantly:
 //          no broadcast) -> back-substitution, candidate, model cost change, candidate evaluation (with its Jacobian,

@@ -34,7 +34,7 @@ constexpr int TRACE_WORDS = 16;   // uint64 per task in the optional trace
 struct FusedArgs {
   double* A; int ld; int Tn;
   const int* tasks; int ntasks;
-  const int2* deps; const int* srcs; const int* below;
+  const int2* deps; const int2* dep_inl; const int* idx_inl; const int* srcs; const int* below;   // dep_inl: first F_INL pairs of every task, queue order
   int* sync;
   double* Linv; double* x; int* fail;
   unsigned long long* trace;   // optional: 4 stamps per task (pop, inputs ready, done, SM id) + 12 phase stamps (clock64) of F tasks
@@ -301,9 +301,12 @@ __device__ void s_task_run(const FusedArgs& a, const int* tk, double* smem) {
 // waiting / signalling
 // ---------------------------------------------------------------------------------------------------------------------
 // Every thread takes some of the (sync index, minimum) pairs [d0, d1); returns false when the launch was aborted.
-__device__ bool wait_deps(const FusedArgs& a, int d0, int d1, int* s_abort) {
+// The first F_INL pairs of the task came with its descriptor (inl[], pair inl0 + k = inl[k]): reading a pair from global memory
+// first and polling its counter afterwards is two dependent L2 round trips (~1.5 us) per wait, and an update task waits three times.
+constexpr int F_INL = 16;
+__device__ bool wait_deps(const FusedArgs& a, int d0, int d1, int* s_abort, const int2* inl, int inl0) {
   for (int e = d0 + (int)threadIdx.x; e < d1; e += FTH) {
-    const int2 d = __ldg(a.deps + e);
+    const int2 d = (e - inl0 < F_INL) ? inl[e - inl0] : __ldg(a.deps + e);
     const int* p = a.sync + d.x;
     unsigned spins = 0;
     while (ld_acquire_s32(p) < d.y) {
@@ -326,13 +329,16 @@ constexpr int UT_CHUNK = 2;  // ... by a whole-tile task (2 x 64 x LDW doubles e
 // a chunk never mixes phases, and the task waits for a chunk's row solves right before it stages them, so the first tiles'
 // contributions are summed while the second tiles are still being solved. The earlier updates of the target are waited for
 // last, before the one read-modify-write of the target.
-__device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_abort) {
+__device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_abort, const int2* inl, const int* idx) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const int i = tk[FK_U_I], k = tk[FK_U_K], q = tk[FK_U_Q];
   const int e0 = tk[FK_U_SRC0], e1 = tk[FK_U_SRC1];
   const size_t ld = (size_t)a.ld;
   const int nper = (i == k) ? 1 : 2;
   int dep = tk[FK_DEP0];
+  // source list: the first F_INL entries came with the descriptor (a read from a.srcs is an L2 round trip, and the chunking loop
+  // below chains several of them)
+  auto SRC = [&](int e) { return e - e0 < F_INL ? idx[e - e0] : a.srcs[e]; };
   if (q == 4) {
     // ---- whole 64x64 tile: warp tile 32 rows x 16 columns (8 MMA chains per warp) ----
     const int wr = (warp >> 2) * 32, wc = (warp & 3) * 16;
@@ -343,11 +349,11 @@ __device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
       for (int y = 0; y < 2; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
     for (int c0 = e0; c0 < e1;) {
       int nc = 1;
-      while (nc < UT_CHUNK && c0 + nc < e1 && ((a.srcs[c0 + nc] ^ a.srcs[c0]) & (1 << 30)) == 0) ++nc;
-      if (!wait_deps(a, dep, dep + nc * nper, s_abort)) return false;   // (also: the previous chunk has been consumed)
+      while (nc < UT_CHUNK && c0 + nc < e1 && ((SRC(c0 + nc) ^ SRC(c0)) & (1 << 30)) == 0) ++nc;
+      if (!wait_deps(a, dep, dep + nc * nper, s_abort, inl, tk[FK_DEP0])) return false;   // (also: the previous chunk has been consumed)
       dep += nc * nper;
       for (int sc = 0; sc < nc; ++sc) {
-        const int j = a.srcs[c0 + sc] & 0x3fffffff;
+        const int j = SRC(c0 + sc) & 0x3fffffff;
         double* sA = smem + sc * 2 * NB * LDW;
         double* sB = sA + NB * LDW;
         const double* Xi = a.A + (size_t)i * NB * ld + (size_t)j * NB;
@@ -379,7 +385,7 @@ __device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
       }
       c0 += nc;
     }
-    if (!wait_deps(a, dep, tk[FK_DEP1], s_abort)) return false;
+    if (!wait_deps(a, dep, tk[FK_DEP1], s_abort, inl, tk[FK_DEP0])) return false;
     double* C = a.A + (size_t)i * NB * ld + (size_t)k * NB;
 #pragma unroll
     for (int x = 0; x < 4; ++x)
@@ -400,11 +406,11 @@ __device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int c0 = e0; c0 < e1;) {
     int nc = 1;
-    while (nc < U_CHUNK && c0 + nc < e1 && ((a.srcs[c0 + nc] ^ a.srcs[c0]) & (1 << 30)) == 0) ++nc;
-    if (!wait_deps(a, dep, dep + nc * nper, s_abort)) return false;   // (also: the previous chunk has been consumed)
+    while (nc < U_CHUNK && c0 + nc < e1 && ((SRC(c0 + nc) ^ SRC(c0)) & (1 << 30)) == 0) ++nc;
+    if (!wait_deps(a, dep, dep + nc * nper, s_abort, inl, tk[FK_DEP0])) return false;   // (also: the previous chunk has been consumed)
     dep += nc * nper;
     for (int sc = 0; sc < nc; ++sc) {
-      const int j = a.srcs[c0 + sc] & 0x3fffffff;
+      const int j = SRC(c0 + sc) & 0x3fffffff;
       double* sA = smem + sc * 2 * HB * LDW;
       double* sB = sA + HB * LDW;
       const double* Xi = a.A + ((size_t)i * NB + HB * qi) * ld + (size_t)j * NB;
@@ -427,7 +433,7 @@ __device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
     }
     c0 += nc;
   }
-  if (!wait_deps(a, dep, tk[FK_DEP1], s_abort)) return false;
+  if (!wait_deps(a, dep, tk[FK_DEP1], s_abort, inl, tk[FK_DEP0])) return false;
   if (active) {
     double* C = a.A + ((size_t)i * NB + HB * qi) * ld + (size_t)k * NB + HB * qk;
 #pragma unroll
@@ -445,7 +451,7 @@ __device__ bool u_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
 // B task: x_j = L_jj^-T (y_j - sum_{i in below(j)} L_ij^T x_i)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int B_PRE = 4;   // L tiles staged in shared memory while the task waits for the x_i (the rest is read from L2 afterwards)
-__device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_abort) {
+__device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_abort, const int2* inl, const int* idx) {
   __shared__ double sx[4][NB];
   __shared__ double st[4][NB];
   __shared__ double stt[NB];
@@ -455,14 +461,15 @@ __device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
   double* sM = smem;                    // L_jj^-1, tight
   double* sT = smem + NB * NB;          // up to B_PRE tiles, tight
   // inputs that are final before any x_i is: L_jj^-1, the L_ij tiles, y_j (the first two dependencies + the xdone of the tiles)
+  auto BEL = [&](int e) { return e - e0 < F_INL ? idx[e - e0] : a.below[e]; };   // row tiles below j: first F_INL with the descriptor
   const int dmid = tk[FK_DEP0] + 1 + (e1 - e0) + 1;   // [fin_j, xdone(Tn, j), xdone(i, j)...] then [bx_i...]
-  if (!wait_deps(a, tk[FK_DEP0], dmid, s_abort)) return false;
+  if (!wait_deps(a, tk[FK_DEP0], dmid, s_abort, inl, tk[FK_DEP0])) return false;
   {
     const double* M = a.Linv + (size_t)j * NB * NB;
     for (int e = tid; e < NB * NB / 2; e += FTH) cp_async16(sM + 2 * e, M + 2 * e);
     const int npre = min(e1 - e0, B_PRE);
     for (int t = 0; t < npre; ++t) {
-      const double* L = a.A + (size_t)a.below[e0 + t] * NB * ld + (size_t)j * NB;
+      const double* L = a.A + (size_t)BEL(e0 + t) * NB * ld + (size_t)j * NB;
       for (int e = tid; e < NB * NB / 2; e += FTH) {
         const int rr = e >> 5, cc = (e & 31) * 2;
         cp_async16(sT + t * NB * NB + rr * NB + cc, L + (size_t)rr * ld + cc);
@@ -474,10 +481,10 @@ __device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
   // x of the other nodes first; the partner tile of a pair (below[e0], the tile this node's F task factored last) comes on its
   // own after them, so that everything but its 64x64 term is already summed when it arrives
   const int npart = tk[FK_B_PARTNER];
-  if (!wait_deps(a, dmid, tk[FK_DEP1] - npart, s_abort)) return false;
+  if (!wait_deps(a, dmid, tk[FK_DEP1] - npart, s_abort, inl, tk[FK_DEP0])) return false;
   double t0 = 0.0, t1 = 0.0;
   for (int e = e0 + npart + g; e < e1; e += 4) {
-    const int i = a.below[e];
+    const int i = BEL(e);
     sx[g][c] = __ldcg(a.x + (size_t)i * NB + c);
     bar_named(1 + g, 64);
     if (e - e0 < B_PRE) {
@@ -492,9 +499,9 @@ __device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
     bar_named(1 + g, 64);
   }
   if (npart) {
-    if (!wait_deps(a, tk[FK_DEP1] - 1, tk[FK_DEP1], s_abort)) return false;
+    if (!wait_deps(a, tk[FK_DEP1] - 1, tk[FK_DEP1], s_abort, inl, tk[FK_DEP0])) return false;
     // 64 x 64 term of the partner, rows split over the four groups (its tile is the first staged one)
-    sx[g][c] = __ldcg(a.x + (size_t)a.below[e0] * NB + c);
+    sx[g][c] = __ldcg(a.x + (size_t)BEL(e0) * NB + c);
     bar_named(1 + g, 64);
     const double* L = sT + c;
 #pragma unroll
@@ -523,6 +530,8 @@ __device__ bool b_task(const FusedArgs& a, const int* tk, double* smem, int* s_a
 __global__ void __launch_bounds__(FTH, 1) chol_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_task[F_TASK_INTS];
+  __shared__ int2 s_inl[F_INL];   // the task's first dependency pairs, fetched with the descriptor
+  __shared__ int s_idx[F_INL];    // ... and its first source tiles (U) / row tiles below (B)
   __shared__ int s_next, s_abort;
   PDL_TRIGGER();
   const int tid = threadIdx.x;
@@ -535,16 +544,18 @@ __global__ void __launch_bounds__(FTH, 1) chol_fused_kernel(FusedArgs a) {
     const int t = s_next;
     if (t >= a.ntasks) break;
     if (tid < F_TASK_INTS) s_task[tid] = __ldg(a.tasks + (size_t)t * F_TASK_INTS + tid);
+    else if (tid < F_TASK_INTS + F_INL) s_inl[tid - F_TASK_INTS] = __ldg(a.dep_inl + (size_t)t * F_INL + tid - F_TASK_INTS);
+    else if (tid < F_TASK_INTS + 2 * F_INL) s_idx[tid - F_TASK_INTS - F_INL] = __ldg(a.idx_inl + (size_t)t * F_INL + tid - F_TASK_INTS - F_INL);
     __syncthreads();
     const int type = s_task[FK_TYPE];
     unsigned long long t_pop = 0, t_ready = 0;
     if (a.trace && tid == 0) t_pop = gtime();
     if (type == FT_B) {
-      if (!b_task(a, s_task, smem, &s_abort)) break;
+      if (!b_task(a, s_task, smem, &s_abort, s_inl, s_idx)) break;
     } else if (type == FT_U) {
-      if (!u_task(a, s_task, smem, &s_abort)) break;
+      if (!u_task(a, s_task, smem, &s_abort, s_inl, s_idx)) break;
     } else {
-      if (!wait_deps(a, s_task[FK_DEP0], s_task[FK_DEP1], &s_abort)) break;
+      if (!wait_deps(a, s_task[FK_DEP0], s_task[FK_DEP1], &s_abort, s_inl, s_task[FK_DEP0])) break;
       if (a.trace && tid == 0) t_ready = gtime();
       if (type == FT_S) s_task_run(a, s_task, smem);
       else f_task(a, s_task, smem, a.trace ? a.trace + TRACE_WORDS * (size_t)t + 4 : nullptr);
@@ -581,6 +592,22 @@ int chol_fused_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym) {
   static_assert(sizeof(I2) == sizeof(int2), "I2 must match int2");
   TSL_CUDA(sym->f_tasks.upload(H.f_tasks.data(), H.f_tasks.size(), s));
   TSL_CUDA(sym->f_deps.upload(reinterpret_cast<const int2*>(H.f_deps.data()), H.f_deps.size(), s));
+  {   // first F_INL dependency pairs of every task in queue order (padding: the queue head, which is never below 0)
+    std::vector<int2> inl((size_t)H.f_ntasks * F_INL, make_int2(FS_HEAD, 0));
+    for (int t = 0; t < H.f_ntasks; ++t) {
+      const int d0 = H.f_tasks[(size_t)t * F_TASK_INTS + FK_DEP0], d1 = H.f_tasks[(size_t)t * F_TASK_INTS + FK_DEP1];
+      for (int e = d0; e < d1 && e - d0 < F_INL; ++e) inl[(size_t)t * F_INL + e - d0] = make_int2(H.f_deps[e].x, H.f_deps[e].y);
+    }
+    TSL_CUDA(sym->f_dep_inl.upload(inl.data(), inl.size(), s));
+    std::vector<int> ix((size_t)H.f_ntasks * F_INL, 0);
+    for (int t = 0; t < H.f_ntasks; ++t) {
+      const int* rec = &H.f_tasks[(size_t)t * F_TASK_INTS];
+      if (rec[FK_TYPE] == FT_U) for (int e = rec[FK_U_SRC0]; e < rec[FK_U_SRC1] && e - rec[FK_U_SRC0] < F_INL; ++e) ix[(size_t)t * F_INL + e - rec[FK_U_SRC0]] = H.f_srcs[e];
+      if (rec[FK_TYPE] == FT_B) for (int e = rec[FK_B_BEL0]; e < rec[FK_B_BEL1] && e - rec[FK_B_BEL0] < F_INL; ++e) ix[(size_t)t * F_INL + e - rec[FK_B_BEL0]] = H.f_below[e];
+    }
+    TSL_CUDA(sym->f_idx_inl.upload(ix.data(), ix.size(), s));
+    TSL_CUDA(cudaStreamSynchronize(s));   // `inl` is a local
+  }
   TSL_CUDA(sym->f_srcs.upload(H.f_srcs.data(), H.f_srcs.size(), s));
   TSL_CUDA(sym->f_below.upload(H.f_below.data(), H.f_below.size(), s));
   TSL_CUDA(sym->f_sync.reserve((size_t)(H.f_nsync ? H.f_nsync : 1)));
@@ -604,7 +631,7 @@ int chol_fused_solve(tslam_ctx* ctx, const CholSymbolic& sym, double* A, double*
     ctx->attr_chol_fused = true;
   }
   FusedArgs a;
-  a.A = A; a.ld = ld; a.Tn = Tn; a.tasks = sym.f_tasks.p; a.ntasks = sym.f_ntasks; a.deps = sym.f_deps.p; a.srcs = sym.f_srcs.p; a.below = sym.f_below.p;
+  a.A = A; a.ld = ld; a.Tn = Tn; a.tasks = sym.f_tasks.p; a.ntasks = sym.f_ntasks; a.deps = sym.f_deps.p; a.dep_inl = sym.f_dep_inl.p; a.idx_inl = sym.f_idx_inl.p; a.srcs = sym.f_srcs.p; a.below = sym.f_below.p;
   a.sync = sym.f_sync.p; a.Linv = sym.Ldiag.p; a.x = xout; a.fail = d_fail; a.trace = trace;
   const int grid = std::max(1, std::min(ctx->sm_count, sym.f_ntasks));
   LAUNCH(launch_k(chol_fused_kernel, grid, FTH, smem, ctx->stream, a));

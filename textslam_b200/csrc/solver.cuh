@@ -22,7 +22,8 @@ struct CholSymbolic {  // tile-level symbolic factorisation + level schedule (pe
   // fused schedule (chol_fused.cu, chol_sched.hpp)
   int f_ntasks = 0, f_nsync = 0;
   DevBuf<int> f_tasks, f_srcs, f_below;
-  DevBuf<int2> f_deps;
+  DevBuf<int2> f_deps, f_dep_inl;
+  DevBuf<int> f_idx_inl;
   mutable DevBuf<int> f_sync;                         // queue head + dependency counters, zeroed before every solve
 };
 int chol_upload(tslam_ctx* ctx, const CholHost& H, CholSymbolic* sym);   // device copy of the host symbolic factorisation (analysis.cpp)
