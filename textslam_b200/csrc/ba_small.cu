@@ -302,33 +302,6 @@ __device__ __forceinline__ void schur_contrib(double* acc, const double* sE, con
   }
 }
 
-// trailing update of column k by a 16 x 16 thread grid, NA x NA tiles (lower ones): a_ij -= (a_ik / d_k) a_jk for k < j <= i <= n, j < n.
-// Operands and targets go to registers first, then the FMAs, then the stores (a load behind a store to the same array would wait).
-template <int NA>
-__device__ __forceinline__ void chol_trail(double* A, int LD, int n, int k, int ty, int tx, double inv_d) {
-  double li[NA], lj[NA], tv[NA][NA];
-  const int i0 = k + 1 + ty, j0 = k + 1 + tx;
-#pragma unroll
-  for (int q = 0; q < NA; ++q) {
-    li[q] = (i0 + 16 * q <= n) ? A[(i0 + 16 * q) * LD + k] * inv_d : 0.0;
-    lj[q] = (j0 + 16 * q < n) ? A[(j0 + 16 * q) * LD + k] : 0.0;
-  }
-#pragma unroll
-  for (int qa = 0; qa < NA; ++qa)
-#pragma unroll
-    for (int qb = 0; qb <= qa; ++qb) {
-      const int i = i0 + 16 * qa, j = j0 + 16 * qb;
-      tv[qa][qb] = (i <= n && j <= min(i, n - 1)) ? A[i * LD + j] : 0.0;
-    }
-#pragma unroll
-  for (int qa = 0; qa < NA; ++qa)
-#pragma unroll
-    for (int qb = 0; qb <= qa; ++qb) {
-      const int i = i0 + 16 * qa, j = j0 + 16 * qb;
-      if (i <= n && j <= min(i, n - 1)) A[i * LD + j] = tv[qa][qb] - li[qa] * lj[qb];
-    }
-}
-
 #define GSYNC() do { if (grid_sync(bar)) { if (threadIdx.x == 0) a.out[OUT_ABORT] = 1.0; return; } } while (0)
 
 __global__ void __launch_bounds__(ST, 1) ba_small_kernel(SmallArgs a) {
