@@ -963,6 +963,7 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
   // an iteration waits for, and they shrink with the number of warps
   int G = (lp + lt + nvp + nvt + 7) / 8;
   G = std::max(1, std::min(G, std::min(S_MAX_G, ctx->sm_count)));
+  if (const char* e = getenv("TSLAM_SMALL_G")) G = std::max(1, std::min(atoi(e), std::min(S_MAX_G, ctx->sm_count)));   // tuning experiments
   const int max_iters = opt->max_iters;
 
   // ---- layout ----
