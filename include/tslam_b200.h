@@ -316,6 +316,13 @@ int tslam_search_from_3d(tslam_ctx* ctx, const double* Tcw, const double* K, int
                          const uint8_t* query_desc, int n_query, const float* kp_xy, const int32_t* kp_octave,
                          const uint8_t* train_desc, int n_kp, const tslam_frame_grid* grid, float radius, int min_level,
                          int max_level, int32_t* best_idx, int32_t* best_dist, double* uv_out);
+/* tracking::SearchFrom3DLocalTrack (src/tracking.cc:1282-1345): the projections are given (mapPts::LocalTrackProj), no bounds test;
+ * kp_skip[k] != 0 excludes key point k (already matched to a map point with more than two observations, :1311-1313; may be NULL);
+ * second_dist receives the runner-up distance for the caller's ratio test bestDist <= 0.9 bestDist2 (:1331-1334; may be NULL). */
+int tslam_search_in_area(tslam_ctx* ctx, int n_pts, const double* uv, const int32_t* pt_query, const uint8_t* query_desc, int n_query,
+                         const float* kp_xy, const int32_t* kp_octave, const uint8_t* kp_skip, const uint8_t* train_desc, int n_kp,
+                         const tslam_frame_grid* grid, float radius, int min_level, int max_level, int32_t* best_idx,
+                         int32_t* best_dist, int32_t* second_dist);
 
 #ifdef __cplusplus
 }

@@ -276,6 +276,50 @@ def search_from_3d(Tcw, K, pt_ray, pt_rho, poses, pt_host, pt_query, query_desc,
     return bi, bd, uv
 
 
+def search_in_area(uv, pt_query, query_desc, kp_xy, kp_octave, train_desc, grid, th, kp_skip=None, min_level=-1, max_level=-1):
+    """tracking::SearchFrom3DLocalTrack (src/tracking.cc:1296-1329) per map point: GetFeaturesInArea at the given projection (double
+    narrowed to float at the call), candidates flagged in kp_skip left out (:1311-1313), best and runner-up distance with the
+    reference's update rule. Returns (best_idx, best_dist, second_dist)."""
+    f32 = np.float32
+    q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train_desc, dtype=np.uint8).reshape(-1, 32)
+    kp_xy = np.asarray(kp_xy, dtype=f32).reshape(-1, 2)
+    n = len(uv); INT_MAX = 2147483647
+    bi = np.full(n, -1, np.int32); bd = np.full(n, INT_MAX, np.int32); sd = np.full(n, INT_MAX, np.int32)
+    r = f32(th) * f32(1.2)
+    for i in range(n):
+        if pt_query[i] < 0:
+            continue
+        x, y = f32(uv[i][0]), f32(uv[i][1])
+        c0 = max(0, int(np.floor((x - grid["min_x"] - r) * grid["inv_w"])))
+        c1 = min(grid["cols"] - 1, int(np.ceil((x - grid["min_x"] + r) * grid["inv_w"])))
+        r0 = max(0, int(np.floor((y - grid["min_y"] - r) * grid["inv_h"])))
+        r1 = min(grid["rows"] - 1, int(np.ceil((y - grid["min_y"] + r) * grid["inv_h"])))
+        if c0 >= grid["cols"] or c1 < 0 or r0 >= grid["rows"] or r1 < 0:
+            continue
+        check = min_level > 0 or max_level >= 0
+        best, best2, best_k = INT_MAX, INT_MAX, -1
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for k in grid["cells"][ix][iy]:
+                    if check:
+                        if kp_octave[k] < min_level:
+                            continue
+                        if max_level >= 0 and kp_octave[k] > max_level:
+                            continue
+                    if not (abs(kp_xy[k, 0] - x) < r and abs(kp_xy[k, 1] - y) < r):
+                        continue
+                    if kp_skip is not None and kp_skip[k]:
+                        continue
+                    d = int(np.unpackbits(q[pt_query[i]] ^ t[k]).sum())
+                    if d < best:
+                        best2 = best; best = d; best_k = k
+                    elif d < best2:
+                        best2 = d
+        if best_k >= 0:
+            bi[i] = best_k; bd[i] = best; sd[i] = best2
+    return bi, bd, sd
+
+
 def gate_residuals(final_residuals, n_pobs, n_tobs, gate, t_obj=None, obj_size=None):
     """The reference's outlier loops (src/optimizer.cc:1236-1302, 1616-1684) on a final residual vector.
     Returns (pt_bad, tf_bad, obj_bad, (nBadS, nBadFeat, nBadT)); raises if the reference's asserts would fire."""

@@ -38,3 +38,29 @@ def test_edge_cases(ctx, oracle):
     bad = args.copy(); bad[6] = np.full(40, 10 ** 6, np.int32)       # descriptor row out of range
     with pytest.raises(T.TslamError):
         T.search_from_3d(ctx, *bad, G, 15)
+
+
+@pytest.mark.parametrize("seed,th", [(21, 15), (22, 30)])
+def test_local_track_variant_matches_oracle(ctx, oracle, seed, th):
+    """tracking::SearchFrom3DLocalTrack (src/tracking.cc:1282-1345): given projections, no level check, key points already matched to a
+    well-observed map point skipped, best + runner-up distance; then the 0.9 ratio rule on the host."""
+    c = make_case(seed)
+    rng = np.random.default_rng(seed)
+    G = T.FrameGrid(c["kp_xy"], c["width"], c["height"])
+    g = oracle.frame_grid(c["kp_xy"], c["width"], c["height"])
+    _, _, uv = oracle.search_from_3d(c["Tcw"], c["K"], c["pt_ray"], c["pt_rho"], c["poses"], c["pt_host"], c["pt_query"], c["query_desc"],
+                                     c["kp_xy"], c["kp_octave"], c["train_desc"], g, th)
+    skip = (rng.random(len(c["kp_xy"])) < 0.2).astype(np.uint8)
+    args = (uv, c["pt_query"], c["query_desc"], c["kp_xy"], c["kp_octave"], c["train_desc"])
+    bi, bd, sd = T.search_in_area(ctx, *args, G, th, kp_skip=skip)
+    oi, od, osd = oracle.search_in_area(*args, g, th, kp_skip=skip)
+    assert np.array_equal(bi, oi) and np.array_equal(bd, od) and np.array_equal(sd, osd)
+    assert not skip[bi[bi >= 0]].any() and (sd[bi >= 0] >= bd[bi >= 0]).all()
+    ok = T.resolve_local_track(bi, bd, sd)
+    assert 10 < ok.sum() < (bi >= 0).sum()
+    # without the mask and with a level range the same entry point reproduces the candidate sets of SearchFrom3D
+    b2, d2, _ = T.search_in_area(ctx, *args, G, th, min_level=-1, max_level=1)
+    o2, e2, _ = oracle.search_from_3d(c["Tcw"], c["K"], c["pt_ray"], c["pt_rho"], c["poses"], c["pt_host"], c["pt_query"], c["query_desc"],
+                                      c["kp_xy"], c["kp_octave"], c["train_desc"], g, th)
+    inb = (uv[:, 0] >= 0) & (uv[:, 0] <= c["width"]) & (uv[:, 1] >= 0) & (uv[:, 1] <= c["height"])
+    assert np.array_equal(b2[inb], o2[inb]) and np.array_equal(d2[inb], e2[inb])

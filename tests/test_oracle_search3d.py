@@ -50,3 +50,13 @@ def test_oracle_equals_brute_force(oracle):
     m32, m23, n = T.resolve_matches(bi, bd, c["pt_query"], len(c["kp_xy"]), len(c["query_desc"]))
     assert n == (m32 >= 0).sum() == (m23 >= 0).sum() and n > 10
     assert len(set(m32[m32 >= 0])) == n
+
+
+def test_add_variant_bookkeeping():
+    """SearchFrom3DAdd (src/tracking.cc:1196-1270): points matched by the first search are skipped, its 2D->3D table stays in force"""
+    bi = np.array([3, 3, 5, 7, -1]); bd = np.array([10, 20, 30, 200, 2147483647]); pq = np.array([0, 1, 2, 3, 4])
+    m32, m23, n = T.resolve_matches(bi, bd, pq, 10, 5)
+    assert n == 2 and list(m32) == [3, -1, 5, -1, -1]
+    bi2 = np.array([9, 4, 8, 6, 3]); bd2 = np.array([1, 50, 60, 70, 80])
+    a32, a23, n2 = T.resolve_matches(bi2, bd2, pq, 10, 5, m32=m32, m23=m23)
+    assert n2 == 2 and list(a32) == [3, 4, 5, 6, -1] and a23[3] == 0     # point 4 wants key point 3, which point 0 holds

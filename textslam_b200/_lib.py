@@ -17,7 +17,7 @@ EXPORTS = [
     "tslam_dev_eval_points", "tslam_dev_eval_text", "tslam_dev_lm_iterations", "tslam_dev_download_eval",
     "tslam_dev_download_params", "tslam_orb_create", "tslam_orb_destroy", "tslam_orb_extract", "tslam_orb_level_size",
     "tslam_orb_get_level", "tslam_orb_dev_bench", "tslam_orb_debug_get", "tslam_frame_pyr_create", "tslam_frame_pyr_destroy", "tslam_frame_pyr_build",
-    "tslam_frame_pyr_level_size", "tslam_frame_pyr_get", "tslam_match_hamming", "tslam_search_from_3d", "tslam_theta_covariance", "tslam_text_info", "tslam_analyze_structure", "tslam_debug_compare_analysis",
+    "tslam_frame_pyr_level_size", "tslam_frame_pyr_get", "tslam_match_hamming", "tslam_search_from_3d", "tslam_search_in_area", "tslam_theta_covariance", "tslam_text_info", "tslam_analyze_structure", "tslam_debug_compare_analysis",
     "tslam_gate_residuals", "tslam_solve_gated", "tslam_debug_chol_schedule", "tslam_dev_chol_solve",
 ]
 

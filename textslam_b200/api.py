@@ -467,19 +467,50 @@ def search_from_3d(ctx, Tcw, K, pt_ray, pt_rho, poses, pt_host, pt_query, query_
     return bi, bd, uv
 
 
-def resolve_matches(best_idx, best_dist, pt_query, n_kp, n_query, th_high=TH_HIGH):
+def search_in_area(ctx, uv, pt_query, query_desc, kp_xy, kp_octave, train_desc, grid, th, kp_skip=None, min_level=-1, max_level=-1):
+    """tracking::SearchFrom3DLocalTrack's candidate search (src/tracking.cc:1296-1329): given projections (LocalTrackProj), window
+    th * 1.2f, level range (-1, -1) = no level check, key points flagged in kp_skip left out. Returns (best_idx, best_dist, second_dist)."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+    pt_query, kp_octave = i32(pt_query), i32(kp_octave)
+    q = np.ascontiguousarray(query_desc, dtype=np.uint8).reshape(-1, 32); t = np.ascontiguousarray(train_desc, dtype=np.uint8).reshape(-1, 32)
+    kp_xy = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+    skip = None if kp_skip is None else np.ascontiguousarray(kp_skip, dtype=np.uint8)
+    n = len(uv)
+    bi = np.zeros(n, np.int32); bd = np.zeros(n, np.int32); sd = np.zeros(n, np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    g = grid.as_c()
+    radius = np.float32(th) * np.float32(1.2)
+    check(lib().tslam_search_in_area(ctx._h, C.c_int(n), _dp(uv), ip(pt_query), q.ctypes.data_as(c_bp), C.c_int(len(q)),
+                                     kp_xy.ctypes.data_as(C.POINTER(C.c_float)), ip(kp_octave), skip.ctypes.data_as(c_bp) if skip is not None else None,
+                                     t.ctypes.data_as(c_bp), C.c_int(len(t)), C.byref(g), C.c_float(float(radius)), C.c_int(min_level), C.c_int(max_level),
+                                     ip(bi), ip(bd), ip(sd)))
+    return bi, bd, sd
+
+
+def resolve_matches(best_idx, best_dist, pt_query, n_kp, n_query, th_high=TH_HIGH, m32=None, m23=None):
     """The sequential bookkeeping of tracking::SearchFrom3D (src/tracking.cc:1178-1186): a point keeps its best keypoint if neither
-    that keypoint nor the point's observation in the last key frame has been taken by an earlier point.
-    Returns (vMatch3D2D, vMatch2D3D, nMatches)."""
-    m32 = np.full(len(best_idx), -1, np.int64); m23 = np.full(n_kp, -1, np.int64); m12 = np.full(n_query, -1, np.int64)
+    that keypoint nor the point's observation in the last key frame has been taken by an earlier point. SearchFrom3DAdd (:1196-1270)
+    is the same loop on the vMatch3D2D / vMatch2D3D of an earlier search (pass them as m32 / m23; its points with m32 >= 0 are
+    skipped — give them pt_query = -1 for the device search as well). Returns (vMatch3D2D, vMatch2D3D, nMatches)."""
+    m32 = np.full(len(best_idx), -1, np.int64) if m32 is None else np.array(m32, np.int64)
+    m23 = np.full(n_kp, -1, np.int64) if m23 is None else np.array(m23, np.int64)
+    m12 = np.full(n_query, -1, np.int64)
     n = 0
     for i in range(len(best_idx)):
-        if pt_query[i] < 0 or best_idx[i] < 0 or best_dist[i] > th_high:
+        if m32[i] >= 0 or pt_query[i] < 0 or best_idx[i] < 0 or best_dist[i] > th_high:
             continue
         j = best_idx[i]
         if m23[j] < 0 and m12[pt_query[i]] < 0:
             n += 1; m32[i] = j; m23[j] = i; m12[pt_query[i]] = j
     return m32, m23, n
+
+
+def resolve_local_track(best_idx, best_dist, second_dist, th_high=TH_HIGH):
+    """Acceptance rule of tracking::SearchFrom3DLocalTrack (src/tracking.cc:1331-1340): bestDist <= TH_HIGH and not
+    bestDist > 0.9 * bestDist2. Returns the boolean mask of the points that get an observation (F.AddSceneObserv)."""
+    bd = np.asarray(best_dist, np.int64); sd = np.asarray(second_dist, np.int64)
+    return (np.asarray(best_idx) >= 0) & (bd <= th_high) & ~(bd.astype(np.float64) > 0.9 * sd.astype(np.float64))
 
 
 class FramePyramid:

@@ -55,6 +55,9 @@ struct Search3dArgs {
   int cols, rows; float min_x, min_y, max_x, max_y, inv_w, inv_h; const int* cell_ptr; const int* cell_idx;
   float radius; int min_level, max_level;
   int* best_idx; int* best_dist; double2* uv;
+  // SearchFrom3DLocalTrack (src/tracking.cc:1282-1345): projections given (mapPts::LocalTrackProj), key points already matched to a
+  // well-observed map point are skipped (:1311-1313), the runner-up distance is wanted for the ratio test (:1331-1334)
+  const double2* uv_in; const uint8_t* kp_skip; int* second_dist;
 };
 __device__ __forceinline__ void quat_R(const double* q, double R[9]) {   // unit quaternion (w, x, y, z) -> rotation, as ba_device.cuh
   const double w = q[0], x = q[1], y = q[2], z = q[3];
@@ -66,10 +69,11 @@ __global__ void __launch_bounds__(128) search3d_kernel(Search3dArgs a) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= a.n_pts) return;
   const int qi = a.query[w];
-  int out_idx = -1, out_dist = 2147483647;
+  int out_idx = -1, out_dist = 2147483647, out_second = 2147483647;
   double u = 0.0, v = 0.0;
   bool live = qi >= 0;
-  if (live) {
+  if (live && a.uv_in) { u = a.uv_in[w].x; v = a.uv_in[w].y; }
+  else if (live) {
     double Rc[9], Rr[9];
     quat_R(a.Tcw, Rc);
     const double* Pr = a.poses + 7 * (size_t)a.host[w];
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(128) search3d_kernel(Search3dArgs a) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) qd[k] = __ldg(a.qdesc + 8 * (size_t)qi + k);
       const bool check = a.min_level > 0 || a.max_level >= 0;
-      unsigned best = 0xFFFFFFFFu; int best_k = -1, base = 0;
+      unsigned best = 0xFFFFFFFFu, second = 0xFFFFFFFFu; int best_k = -1, base = 0;
       for (int ix = c0; ix <= c1; ++ix)
         for (int iy = r0; iy <= r1; ++iy) {
           const int c = ix * a.rows + iy;
@@ -118,25 +122,29 @@ __global__ void __launch_bounds__(128) search3d_kernel(Search3dArgs a) {
             }
             const float2 kp = a.kp_xy[k];
             if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+            if (a.kp_skip && a.kp_skip[k]) continue;
             const uint32_t* td = a.tdesc + 8 * (size_t)k;
             int d = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) d += __popc(qd[j] ^ __ldg(td + j));
             const unsigned key = ((unsigned)d << 20) | (unsigned)min(base + e - e0, 0xFFFFF);
-            if (key < best) { best = key; best_k = k; }
+            if (key < best) { second = best; best = key; best_k = k; } else if (key < second) second = key;
           }
           base += e1 - e0;
         }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o); const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o); const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        second = min(max(best, ob), min(second, os));   // second smallest of the union: the reference's bestDist2 is the multiset's runner-up
         if (ob < best) { best = ob; best_k = ok; }
       }
       if (best != 0xFFFFFFFFu) { out_idx = best_k; out_dist = (int)(best >> 20); }
+      if (second != 0xFFFFFFFFu) out_second = (int)(second >> 20);
     }
   }
   if (lane == 0) {
     a.best_idx[w] = out_idx; a.best_dist[w] = out_dist;
+    if (a.second_dist) a.second_dist[w] = out_second;
     if (a.uv) a.uv[w] = make_double2(u, v);
   }
 }
@@ -144,13 +152,15 @@ __global__ void __launch_bounds__(128) search3d_kernel(Search3dArgs a) {
 
 using namespace tsl;
 
-extern "C" int tslam_search_from_3d(tslam_ctx* ctx, const double* Tcw, const double* K, int n_pts, const double* pt_ray, const double* pt_rho,
-                                    const double* poses, int n_poses, const int32_t* pt_host, const int32_t* pt_query, const uint8_t* query_desc, int n_query,
-                                    const float* kp_xy, const int32_t* kp_octave, const uint8_t* train_desc, int n_kp, const tslam_frame_grid* g,
-                                    float radius, int min_level, int max_level, int32_t* best_idx, int32_t* best_dist, double* uv_out) {
-  if (!ctx || !Tcw || !K || !g || !best_idx || !best_dist) return set_error(TSLAM_ERR_ARG, "null argument");
+static int search_impl(tslam_ctx* ctx, const double* Tcw, const double* K, int n_pts, const double* pt_ray, const double* pt_rho,
+                       const double* poses, int n_poses, const int32_t* pt_host, const int32_t* pt_query, const uint8_t* query_desc, int n_query,
+                       const float* kp_xy, const int32_t* kp_octave, const uint8_t* train_desc, int n_kp, const tslam_frame_grid* g,
+                       float radius, int min_level, int max_level, int32_t* best_idx, int32_t* best_dist, double* uv_out,
+                       const double* uv_in, const uint8_t* kp_skip, int32_t* second_dist) {
+  if (!ctx || !g || !best_idx || !best_dist) return set_error(TSLAM_ERR_ARG, "null argument");
   if (n_pts <= 0) return TSLAM_OK;
-  if (!pt_ray || !pt_rho || !poses || !pt_host || !pt_query || !query_desc || !g->cell_ptr) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (!pt_query || !query_desc || !g->cell_ptr) return set_error(TSLAM_ERR_ARG, "null argument");
+  if (!uv_in && (!Tcw || !K || !pt_ray || !pt_rho || !poses || !pt_host)) return set_error(TSLAM_ERR_ARG, "null argument");
   if (n_kp > 0 && (!kp_xy || !kp_octave || !train_desc || !g->cell_idx)) return set_error(TSLAM_ERR_ARG, "null keypoint array");
   if (g->cols <= 0 || g->rows <= 0 || g->cols * (long long)g->rows > (1 << 20)) return set_error(TSLAM_ERR_ARG, "bad grid dimensions");
   const int ncell = g->cols * g->rows;
@@ -159,20 +169,27 @@ extern "C" int tslam_search_from_3d(tslam_ctx* ctx, const double* Tcw, const dou
   const int nent = g->cell_ptr[ncell];
   for (int e = 0; e < nent; ++e) if ((unsigned)g->cell_idx[e] >= (unsigned)n_kp) return set_error(TSLAM_ERR_ARG, "grid entry %d out of range", e);
   for (int i = 0; i < n_pts; ++i) {
-    if ((unsigned)pt_host[i] >= (unsigned)n_poses) return set_error(TSLAM_ERR_ARG, "map point %d: host pose out of range", i);
+    if (!uv_in && (unsigned)pt_host[i] >= (unsigned)n_poses) return set_error(TSLAM_ERR_ARG, "map point %d: host pose out of range", i);
     if (pt_query[i] >= n_query) return set_error(TSLAM_ERR_ARG, "map point %d: query descriptor out of range", i);
   }
   TSL_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   AllocStreamScope alloc_scope(st);
-  DevBuf<double> dT, dray, drho, dposes, duv; DevBuf<int> dhost, dq, doct, dcp, dci, dbi, dbd; DevBuf<uint8_t> dqd, dtd; DevBuf<float> dxy;
-  TSL_CUDA(dT.upload(Tcw, 7, st)); TSL_CUDA(dray.upload(pt_ray, 2 * (size_t)n_pts, st)); TSL_CUDA(drho.upload(pt_rho, n_pts, st));
-  TSL_CUDA(dposes.upload(poses, 7 * (size_t)n_poses, st)); TSL_CUDA(dhost.upload(pt_host, n_pts, st)); TSL_CUDA(dq.upload(pt_query, n_pts, st));
+  DevBuf<double> dT, dray, drho, dposes, duv, duvin; DevBuf<int> dhost, dq, doct, dcp, dci, dbi, dbd, dsd; DevBuf<uint8_t> dqd, dtd, dskip; DevBuf<float> dxy;
+  if (uv_in) TSL_CUDA(duvin.upload(uv_in, 2 * (size_t)n_pts, st));
+  else {
+    TSL_CUDA(dT.upload(Tcw, 7, st)); TSL_CUDA(dray.upload(pt_ray, 2 * (size_t)n_pts, st)); TSL_CUDA(drho.upload(pt_rho, n_pts, st));
+    TSL_CUDA(dposes.upload(poses, 7 * (size_t)n_poses, st)); TSL_CUDA(dhost.upload(pt_host, n_pts, st));
+  }
+  if (kp_skip && n_kp > 0) TSL_CUDA(dskip.upload(kp_skip, n_kp, st));
+  TSL_CUDA(dsd.reserve(n_pts));
+  TSL_CUDA(dq.upload(pt_query, n_pts, st));
   TSL_CUDA(dqd.upload(query_desc, 32 * (size_t)n_query, st)); TSL_CUDA(dxy.upload(kp_xy, 2 * (size_t)n_kp, st)); TSL_CUDA(doct.upload(kp_octave, n_kp, st));
   TSL_CUDA(dtd.upload(train_desc, 32 * (size_t)n_kp, st)); TSL_CUDA(dcp.upload(g->cell_ptr, (size_t)ncell + 1, st)); TSL_CUDA(dci.upload(g->cell_idx, nent, st));
   TSL_CUDA(dbi.reserve(n_pts)); TSL_CUDA(dbd.reserve(n_pts)); TSL_CUDA(duv.reserve(2 * (size_t)n_pts));
   Search3dArgs a;
-  a.Tcw = dT.p; a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
+  a.Tcw = dT.p; a.fx = K ? K[0] : 0; a.fy = K ? K[1] : 0; a.cx = K ? K[2] : 0; a.cy = K ? K[3] : 0;
+  a.uv_in = uv_in ? reinterpret_cast<const double2*>(duvin.p) : nullptr; a.kp_skip = (kp_skip && n_kp > 0) ? dskip.p : nullptr; a.second_dist = dsd.p;
   a.n_pts = n_pts; a.ray = reinterpret_cast<const double2*>(dray.p); a.rho = drho.p; a.poses = dposes.p; a.host = dhost.p; a.query = dq.p;
   a.qdesc = reinterpret_cast<const uint32_t*>(dqd.p); a.kp_xy = reinterpret_cast<const float2*>(dxy.p); a.kp_oct = doct.p; a.tdesc = reinterpret_cast<const uint32_t*>(dtd.p);
   a.cols = g->cols; a.rows = g->rows; a.min_x = g->min_x; a.min_y = g->min_y; a.max_x = g->max_x; a.max_y = g->max_y; a.inv_w = g->inv_w; a.inv_h = g->inv_h;
@@ -183,6 +200,7 @@ extern "C" int tslam_search_from_3d(tslam_ctx* ctx, const double* Tcw, const dou
   TSL_CUDA(cudaMemcpyAsync(best_idx, dbi.p, sizeof(int) * n_pts, cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaMemcpyAsync(best_dist, dbd.p, sizeof(int) * n_pts, cudaMemcpyDeviceToHost, st));
   if (uv_out) TSL_CUDA(cudaMemcpyAsync(uv_out, duv.p, sizeof(double) * 2 * n_pts, cudaMemcpyDeviceToHost, st));
+  if (second_dist) TSL_CUDA(cudaMemcpyAsync(second_dist, dsd.p, sizeof(int) * n_pts, cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaStreamSynchronize(st));
   return TSLAM_OK;
 }
@@ -210,4 +228,22 @@ extern "C" int tslam_match_hamming(tslam_ctx* ctx, const uint8_t* query_desc, in
   if (second_dist) TSL_CUDA(cudaMemcpyAsync(second_dist, dsd.p, sizeof(int) * n_query, cudaMemcpyDeviceToHost, st));
   TSL_CUDA(cudaStreamSynchronize(st));
   return TSLAM_OK;
+}
+
+extern "C" int tslam_search_from_3d(tslam_ctx* ctx, const double* Tcw, const double* K, int n_pts, const double* pt_ray, const double* pt_rho,
+                                    const double* poses, int n_poses, const int32_t* pt_host, const int32_t* pt_query, const uint8_t* query_desc, int n_query,
+                                    const float* kp_xy, const int32_t* kp_octave, const uint8_t* train_desc, int n_kp, const tslam_frame_grid* g,
+                                    float radius, int min_level, int max_level, int32_t* best_idx, int32_t* best_dist, double* uv_out) {
+  if (!Tcw || !K) return set_error(TSLAM_ERR_ARG, "null argument");
+  return search_impl(ctx, Tcw, K, n_pts, pt_ray, pt_rho, poses, n_poses, pt_host, pt_query, query_desc, n_query, kp_xy, kp_octave, train_desc, n_kp, g, radius,
+                     min_level, max_level, best_idx, best_dist, uv_out, nullptr, nullptr, nullptr);
+}
+
+extern "C" int tslam_search_in_area(tslam_ctx* ctx, int n_pts, const double* uv, const int32_t* pt_query, const uint8_t* query_desc, int n_query,
+                                    const float* kp_xy, const int32_t* kp_octave, const uint8_t* kp_skip, const uint8_t* train_desc, int n_kp,
+                                    const tslam_frame_grid* g, float radius, int min_level, int max_level, int32_t* best_idx, int32_t* best_dist,
+                                    int32_t* second_dist) {
+  if (n_pts > 0 && !uv) return set_error(TSLAM_ERR_ARG, "null argument");
+  return search_impl(ctx, nullptr, nullptr, n_pts, nullptr, nullptr, nullptr, 0, nullptr, pt_query, query_desc, n_query, kp_xy, kp_octave, train_desc, n_kp, g, radius,
+                     min_level, max_level, best_idx, best_dist, nullptr, uv, kp_skip, second_dist);
 }
