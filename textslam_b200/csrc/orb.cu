@@ -604,12 +604,12 @@ __global__ void __launch_bounds__(DIST_THREADS) distribute_kernel(const LevelInf
   each_kp([&](uint32_t pk, int kord, unsigned short* pn, uint8_t*, int kid) {
     const int nid = *pn;
     const unsigned key = ((unsigned)KP_RESP(pk) << 20) | (0xFFFFFu - (unsigned)kord);
-    if (S.best[nid] == key) S.best[nid] = 0x80000000u | (unsigned)kid;   // winner publishes its index (unique key)
+    if (S.best[nid] == key) S.seq[nid] = kid;   // the winner (unique key) publishes its index; seq[] is free once the tree is final
   });
   __syncthreads();
   const int live = S.ctl[2];
   if (live > sel_cap) { if (tid == 0) { atomicExch(err, 4); *out_count = 0; } return; }
-  for (int i = tid; i < live; i += nthreads) { const unsigned bk = S.best[S.order[i]] & 0x7FFFFFFFu; out[i] = cached ? s_pk[bk] : cslots[bk]; }
+  for (int i = tid; i < live; i += nthreads) { const int bk = S.seq[S.order[i]]; out[i] = cached ? s_pk[bk] : cslots[bk]; }
   if (tid == 0) *out_count = live;
 #undef KP_X
 #undef KP_Y
