@@ -198,3 +198,81 @@ def test_orb_extractor_through_the_class_surface(ctx, oracle, tmp_path):
     assert n == len(kpo) and np.array_equal(desc, desco)
     for fld in ("x", "y", "size", "angle", "response", "octave"):
         assert np.array_equal(kp[fld], kpo[fld]), fld
+
+
+@pytest.mark.gpu
+def test_optimize_landmarker_through_the_class_surface(ctx, tmp_path):
+    """optimizer::OptimizeLandmarker -> PyrLandmarkers x 4 levels (src/optimizer.cc:456-562, 1853-2168): every pose constant, every
+    inverse depth (auto_RhoScene, unweighted, Huber sqrt(5.991)) and plane (nume_thetaText, Huber 2.0) free, 50 iterations per level,
+    only the point gate (chi^2 = 18) between the levels."""
+    prob = synth.make_ba_problem(seed=95, n_kf=6, n_lm=200, obs_per_lm=3, band=6, fixed_cams=(0, 1), n_ext=2, frac_ext_lm=0.3, n_planes=5)
+    order = np.lexsort((np.arange(prob.n_pobs), prob.p_cam))
+    for name in ("p_uv", "p_ray", "p_cam", "p_host", "p_lm"):
+        setattr(prob, name, np.ascontiguousarray(getattr(prob, name)[order]))
+    box = plane_boxes(prob)
+    counts, cams, rho, theta, _, _ = run_shim(prob, 3, 6, box, tmp_path)
+    q = prob.copy()
+    q.cam_fixed[:] = 1; q.rho_fixed[:] = 0; q.theta_fixed[:] = 0
+    q.w_point, q.huber_point, q.w_text, q.huber_text = (1.0, 1.0), float(np.sqrt(5.991)), 1.0, 2.0
+    t_obj, _ = _objects(q)
+    pts_good = np.ones(q.n_pobs, bool)
+    g = T.gate_options(w_point=(1.0, 1.0), chi2_mono=18.0, w_text=1.0, chi2_text=1.5, gate_points=True, gate_text=False, relax_below_text_blocks=0)
+    for _ in range(4):
+        sub = q.subset(pts_good, np.ones(q.n_tobs, bool))
+        refresh_musigma(ctx, sub, box)
+        obj_size = np.bincount(t_obj, minlength=int(t_obj.max()) + 1).astype(np.int32)
+        summ, fr, _, pb, tb, ob, cnt = ctx.solve_gated(sub, g, t_obj, obj_size, 50, want_trace=False)
+        pts_good[np.nonzero(pts_good)[0][pb == 1]] = False
+        q.set_params(*sub.params())
+    # the reference keeps its vPtsGood copy local to OptimizeLandmarker (src/optimizer.cc:476-479, 532-540): the gate shapes the levels that
+    # follow, the keyframes' flags stay as they were
+    assert counts[0] == 0 and (~pts_good).sum() > 0
+    seen = np.zeros(len(q.rho), bool); seen[q.p_lm] = True
+    assert rel(rho[seen], q.rho[seen]) < 1e-6 and rel(theta, q.theta) < 1e-6
+    assert rel(quat_same(cams[:6], prob.cams[:6]), prob.cams[:6]) < 1e-12       # poses untouched
+
+
+@pytest.mark.gpu
+def test_theta_optim_multi_fs_through_the_class_surface(ctx, tmp_path):
+    """optimizer::ThetaOptimMultiFs -> PyrThetaOptim x 3 levels (src/optimizer.cc:565-624, 2170-2242): the plane of one text object from
+    every keyframe that sees it plus the current frame, poses relative to the object's host keyframe held constant, 50 iterations per
+    level (Ceres' default), no loss; then the 3x3 covariance of the plane."""
+    prob = synth.c5_global_ba(seed=96, n_kf=12, n_lm=60, n_planes=4, text_kf_stride=1)
+    # the synthetic planes are seen from one keyframe each: give the first object a second observer (keyframe 5, its own image), so that
+    # the problem has two frames besides the current one's re-insertion logic (blocks stay grouped by keyframe, then object)
+    g0 = np.nonzero(prob.t_plane == prob.t_plane.min())[0]
+    assert prob.t_cam.max() < 5 and len(prob.imgs) > 5
+    for name in ("t_rays", "t_iref", "t_musigma", "t_host", "t_plane"):
+        setattr(prob, name, np.ascontiguousarray(np.concatenate([getattr(prob, name), getattr(prob, name)[g0]])))
+    prob.t_cam = np.ascontiguousarray(np.concatenate([prob.t_cam, np.full(len(g0), 5)]).astype(np.int32))
+    prob.t_img = np.ascontiguousarray(np.concatenate([prob.t_img, np.full(len(g0), 5)]).astype(np.int32))
+    box = plane_boxes(prob)
+    counts, cams, rho, theta, cov, _ = run_shim(prob, 4, len(prob.cams), box, tmp_path)
+    assert counts[5] == 1
+    t0 = int(prob.t_plane.min())                       # M.vTexts[0]: the first text object of the map
+    cF = int(prob.t_cam[0])                            # F: the keyframe of the first text block
+    grp = np.nonzero(prob.t_plane == t0)[0]
+    host = int(prob.t_host[grp[0]])
+    first = grp[(prob.t_cam[grp] == prob.t_cam[grp[0]])]          # reference features = the object's first (keyframe, object) group
+    observers = [int(c) for c in np.unique(prob.t_cam[grp]) if c != cF and c != host] + [cF]
+    img_of = {int(c): int(i) for c, i in zip(prob.t_cam, prob.t_img)}
+    qh = prob.cams[host]
+    cam_rows = [np.array([1.0, 0, 0, 0, 0, 0, 0])]
+    for c in observers:                                 # T_cr = T_cw T_rw^-1
+        qc = prob.cams[c]
+        q_cr = synth.qmul(qc[:4], synth.qconj(qh[:4]))
+        cam_rows.append(np.r_[q_cr, qc[4:] - synth.qrot(q_cr, qh[4:])])
+    nb = len(first)
+    P = T.BAProblem(np.array(cam_rows), np.ones(len(cam_rows), np.uint8), rho=None, theta=prob.theta[t0][None], theta_fixed=[0],
+                    t_rays=np.tile(prob.t_rays[first], (len(observers), 1, 1)), t_iref=np.tile(prob.t_iref[first], (len(observers), 1)),
+                    t_musigma=np.ones((nb * len(observers), 2)), t_cam=np.repeat(np.arange(1, len(observers) + 1), nb), t_host=np.zeros(nb * len(observers)),
+                    t_plane=np.zeros(nb * len(observers)), t_img=np.repeat(np.arange(len(observers)), nb),
+                    imgs=np.stack([prob.imgs[img_of[c]] for c in observers]), K_point=prob.K_point, K_text=prob.K_text, w_text=1.0, huber_text=0.0)
+    bx = box[t0][None]
+    for _ in range(3):
+        refresh_musigma(ctx, P, bx)
+        summ, fr, tr, cv, okv = T.Optimizer(ctx).ThetaOptimMultiFs(P, 50)
+    assert rel(theta[t0], P.theta[0]) < 1e-6
+    assert okv and rel(cov, cv[0]) < 1e-5
+    others = [t for t in range(len(prob.theta)) if t != t0]
+    assert np.array_equal(theta[others], prob.theta[others])
