@@ -1459,7 +1459,7 @@ static int solve_impl(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_opt
     }
   }
   tslam_dev_problem d;
-  rc = upload_problem(ctx, p, &d, /*shard=*/true, /*persistent=*/false);
+  rc = upload_problem(ctx, p, &d, /*shard=*/true, /*persistent=*/false, /*validated=*/true);
   if (rc) return rc;
   auto Tu = std::chrono::steady_clock::now();
   struct Guard { tslam_dev_problem* d; ~Guard() { free_solver(d); } } guard{&d};

@@ -90,8 +90,8 @@ int validate_problem(const tslam_ba_problem* p) {
   return TSLAM_OK;
 }
 
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool persistent) {
-  { const int vrc = validate_problem(p); if (vrc) return vrc; }
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard, bool persistent, bool validated) {
+  if (!validated) { const int vrc = validate_problem(p); if (vrc) return vrc; }   // tslam_solve has checked the arrays already (O(observations) on the host)
   cudaStream_t s = ctx->stream;
   d->n_cams = p->n_cams; d->n_points = p->n_points; d->n_planes = p->n_planes;
   d->g_pobs = p->n_pobs; d->g_tobs = p->n_tobs;

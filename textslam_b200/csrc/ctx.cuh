@@ -153,7 +153,7 @@ namespace tsl {
 // persistent = false (one-shot tslam_solve, the caller is blocked until the call ends): no reset copies of the parameters, host
 // copies of the observation index arrays only when the structure analysis will run on the host, and the uploads may still be in
 // flight on return (everything that follows is ordered behind them on the context stream)
-int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false, bool persistent = true);
+int upload_problem(tslam_ctx* ctx, const tslam_ba_problem* p, tslam_dev_problem* d, bool shard = false, bool persistent = true, bool validated = false);
 int validate_problem(const tslam_ba_problem* p);   // argument checks of every entry point that takes a host problem
 bool device_analysis_supported(const tslam_ctx* ctx, const tslam_dev_problem* d);
 // observation ownership rule shared by upload and the solver's structure analysis
