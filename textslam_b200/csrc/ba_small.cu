@@ -1081,6 +1081,13 @@ int small_solve(tslam_ctx* ctx, tslam_ba_problem* p, const tslam_solve_options* 
     W.attr_set = true; W.attr_smem = 220 * 1024;
   }
   if (smem > 220 * 1024) return TSLAM_OK;
+  {   // the grid barrier needs every CTA resident: cap the grid by what the device can hold with this much shared memory (a smaller
+      // carve-out, MPS limits, a partitioned GPU); nothing resident -> not eligible, the general path takes the problem
+    int per_sm = 0;
+    TSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_small_kernel, ST, smem));
+    if (per_sm < 1) return TSLAM_OK;
+    if (G > per_sm * ctx->sm_count) { G = per_sm * ctx->sm_count; a.G = G; }
+  }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(G); cfg.blockDim = dim3(ST); cfg.dynamicSmemBytes = smem; cfg.stream = st;
